@@ -146,6 +146,7 @@ struct Task {
     int next;  // chain stack link (MT) / unused
     int nb;
     int alleq;       // written by prep
+    int raw;         // low-level API (tmaxo/tmaxp): use x as given with the supplied tss, no centring
     int deferred;    // did not get arena space this round
     double tss;      // written by prep
     // observed scan result (written by scan kernel, LOC mode)
@@ -181,7 +182,9 @@ struct Chain {        // MT replay: one serial stream
     uint64_t prev_len;
     long long need_off;     // this round's window
     uint64_t need_len;
-    uint64_t hist[312];     // raw MT words R[cursor .. cursor+312)
+    uint64_t hist[312];     // the NEXT 312 raw (untempered) MT words: output k of the stream, k = cursor+u,
+                            // is mt_temper(hist[u]).  A window of `need_len` words is stored as
+                            // need_len+312 raw words so that any prefix can later be committed.
 };
 
 struct SegRec { int unit, lo, hi; };
@@ -196,7 +199,9 @@ struct SplitRec {  // one per fndcpt decision (parity diagnostics)
 struct PermItem {  // one scan/shuffle work item of a round
     int task;
     int P;       // permutations (1 for the observed scan)
-    int obs;     // 1 = observed data (prep wrote sx / block stats), LOC mode
+    int obs;     // 0 = permutation of the max-t test: only its reject decision is needed
+                 // 1 = observed data (prep wrote sx / block stats): exact maximum AND location
+                 // 2 = exact maximum, no location (cbs::tmaxp through the low-level API)
 };
 struct EdgeItem {
     int task, side;
@@ -257,6 +262,8 @@ struct Dev {
     int done;
     int error;  // 0 ok; see cbs_gpu.h status codes
     unsigned long long stat_perms, stat_rounds_active;
+    int profile;                            // count scan work (bench / roofline)
+    unsigned long long stat_slots, stat_arcs;  // arc slots issued by the scan fast path / of them real arcs
 };
 
 enum { ERR_TASK_CAP = 101, ERR_SEG_CAP = 102, ERR_ARENA = 103, ERR_SPLIT_CAP = 104, ERR_INTERNAL = 105 };
@@ -290,7 +297,7 @@ struct Sched {
         if (idx < 0) return -1;
         Task& t = D.tasks[idx];
         t.unit = unit; t.lo = lo; t.hi = hi; t.n = hi - lo;
-        t.state = TS_NEW; t.next = -1; t.nb = 0; t.alleq = 0; t.deferred = 0;
+        t.state = TS_NEW; t.next = -1; t.nb = 0; t.alleq = 0; t.raw = 0; t.deferred = 0;
         t.tss = 0.0; t.ostat = 0.0; t.tmaxi = 0; t.tmaxj = 0;
         t.nrejc = 0; t.perms_done = 0; t.nrej = 0; t.exit_code = EX_NONE; t.batch_P = 0;
         t.cnt_exit = -1; t.cnt_nrej = 0;
@@ -416,12 +423,12 @@ struct Sched {
         const long long per = (long long)t.n + sx_stride(t.n) + bs_stride(t.nb);
         // never let one task take more than half of the arena
         long long fit = (D.arena_cap / 2) / per;
-        if (p.rng_mode == RNG_MT) { const long long f2 = (D.draws_cap / 2) / t.n; if (f2 < fit) fit = f2; }
+        if (p.rng_mode == RNG_MT) { const long long f2 = (D.draws_cap / 2 - 312) / t.n; if (f2 < fit) fit = f2; }
         if (fit < 1) { D.error = ERR_ARENA; return false; }
         if (want > fit) want = (int)fit;
         const long long need = per * want;
         const long long dneed = (p.rng_mode == RNG_MT) ? (long long)want * t.n : 0;
-        if (arena_used + need > D.arena_cap || rej_used + want > D.rej_cap || draws_used + dneed > D.draws_cap) {
+        if (arena_used + need > D.arena_cap || rej_used + want > D.rej_cap || draws_used + dneed + 312 > D.draws_cap) {
             t.deferred = 1;
             return false;
         }
@@ -436,7 +443,7 @@ struct Sched {
             Chain* ch = chain_of(t);
             t.off_draw = draws_used;
             ch->need_off = draws_used; ch->need_len = (uint64_t)dneed;
-            draws_used += dneed;
+            draws_used += dneed + 312;  // the generator appends the 312 words that follow the window
         }
         PermItem& it = D.items[D.n_items];
         it.task = idx; it.P = want; it.obs = 0;
@@ -461,7 +468,7 @@ struct Sched {
             e.sparse = 1; e.cols = 0; e.Q = 1;
             e.P = remaining;
             if (p.rng_mode == RNG_MT) {
-                long long fit = (D.draws_cap / 2) / m1;
+                long long fit = (D.draws_cap / 2 - 312) / m1;
                 if (fit < 1) { D.error = ERR_ARENA; return false; }
                 if (e.P > fit) e.P = (int)fit;
             }
@@ -476,7 +483,7 @@ struct Sched {
             long long P = cols * Q;
             if (P > remaining) P = remaining;
             if (p.rng_mode == RNG_MT) {
-                long long fit = (D.draws_cap / 2) / m1;
+                long long fit = (D.draws_cap / 2 - 312) / m1;
                 if (fit < 1) { D.error = ERR_ARENA; return false; }
                 if (P > fit) { P = fit; if (cols > P) cols = P; Q = (int)((P + cols - 1) / cols); }
             }
@@ -484,13 +491,13 @@ struct Sched {
             aneed = cols * n12;
         }
         const long long dneed = (p.rng_mode == RNG_MT) ? (long long)e.P * m1 : 0;
-        if (arena_used + aneed > D.arena_cap || draws_used + dneed > D.draws_cap) { t.deferred = 1; return false; }
+        if (arena_used + aneed > D.arena_cap || draws_used + dneed + 312 > D.draws_cap) { t.deferred = 1; return false; }
         if (aneed) { e.off_scratch = arena_used; arena_used += aneed; }
         if (p.rng_mode == RNG_MT) {
             Chain* ch = chain_of(t);
             e.off_draw = draws_used;
             ch->need_off = draws_used; ch->need_len = (uint64_t)dneed;
-            draws_used += dneed;
+            draws_used += dneed + 312;
         }
         t.e_batch_P = e.P;
         const int threads = e.sparse ? e.P : e.cols;

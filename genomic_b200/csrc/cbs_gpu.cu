@@ -1,0 +1,847 @@
+// cbs_gpu.cu -- host driver and C ABI (include/cbs_gpu.h) of libcbs_cuda.so.
+//
+// The host only stages buffers and enqueues rounds; every decision of the recursive split
+// (cbs::segment / cbs::fndcpt) is taken on the device by k_sched over a device-resident
+// worklist.  Rounds are enqueued in groups without reading anything back; a mapped
+// host flag written by k_sched tells the host when to stop enqueueing.
+#include <cub/cub.cuh>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/cbs_gpu.h"
+#include "host_math.h"
+#include "kernels.cuh"
+#include "smooth.cuh"
+
+using namespace cbsg;
+
+namespace {
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    template <class T> T* as() const { return (T*)p; }
+};
+
+enum KernelId { K_SCHED = 0, K_GEN, K_PREP, K_PERM, K_SCAN, K_EDGEPREP, K_EDGEPERM, K_MEANS, K_SMOOTH, K_COUNT };
+
+}  // namespace
+
+struct cbs_gpu_ctx {
+    int device = 0;
+    int sm_count = 148;
+    size_t smem_optin = 0;
+    cudaStream_t own_stream = nullptr, stream = nullptr;
+    std::string err;
+    int* h_done = nullptr;  // mapped pinned
+    int* d_done = nullptr;  // device alias of h_done
+    DevBuf x, cur, gtab, factab, bbtab, unit_off, unit_ids, tasks, ring, act0, act1, chains, segs, splits, udraws, arena,
+        rej, draws0, draws1, prep_task, items, item_prefix, edgeprep_task, edges, edge_prefix, gen_chain, means, seed312,
+        dev, staging, fv, fidx, flab, lab, diffs, diffs_sorted, gout, cubtmp, flag, goff;
+    void* h_stage = nullptr;  // pinned staging for host inputs
+    size_t h_stage_cap = 0;
+    bool profiling = false;
+    double kms[K_COUNT] = {0};
+    std::vector<cudaEvent_t> ev_pool;
+    std::vector<std::pair<int, int>> ev_used;  // (kernel id, index of start event); stop = start+1
+    size_t ev_next = 0;
+    uint64_t launches = 0;
+    uint64_t last_arcs = 0, last_slots = 0;
+    cudaEvent_t e0 = nullptr, e1 = nullptr, e2 = nullptr, e3 = nullptr, e4 = nullptr;
+    cudaEvent_t grp[2] = {nullptr, nullptr};
+};
+
+namespace {
+
+int fail(cbs_gpu_ctx* c, int code, const std::string& msg) {
+    if (c) c->err = msg;
+    return code;
+}
+
+#define CUDA_TRY(c, expr)                                                                                   \
+    do {                                                                                                    \
+        cudaError_t e__ = (expr);                                                                           \
+        if (e__ != cudaSuccess)                                                                             \
+            return fail(c, e__ == cudaErrorMemoryAllocation ? CBS_GPU_ERR_OOM : CBS_GPU_ERR_CUDA,           \
+                        std::string(#expr) + ": " + cudaGetErrorString(e__));                               \
+    } while (0)
+
+int ensure(cbs_gpu_ctx* c, DevBuf& b, size_t bytes) {
+    if (bytes <= b.cap && b.p) return CBS_GPU_OK;
+    if (b.p) { cudaFree(b.p); b.p = nullptr; b.cap = 0; }
+    size_t want = bytes + bytes / 8 + 256;
+    cudaError_t e = cudaMalloc(&b.p, want);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        want = bytes + 256;
+        e = cudaMalloc(&b.p, want);
+    }
+    if (e != cudaSuccess) { cudaGetLastError(); b.p = nullptr; return fail(c, CBS_GPU_ERR_OOM, "cudaMalloc failed for " + std::to_string(bytes) + " bytes"); }
+    b.cap = want;
+    return CBS_GPU_OK;
+}
+#define ENSURE(c, buf, bytes)                                   \
+    do {                                                        \
+        const int rc__ = ensure(c, buf, bytes);                 \
+        if (rc__ != CBS_GPU_OK) return rc__;                    \
+    } while (0)
+
+int ensure_host_stage(cbs_gpu_ctx* c, size_t bytes) {
+    if (bytes <= c->h_stage_cap) return CBS_GPU_OK;
+    if (c->h_stage) cudaFreeHost(c->h_stage);
+    c->h_stage = nullptr; c->h_stage_cap = 0;
+    CUDA_TRY(c, cudaHostAlloc(&c->h_stage, bytes + bytes / 8, cudaHostAllocDefault));
+    c->h_stage_cap = bytes + bytes / 8;
+    return CBS_GPU_OK;
+}
+
+// event-bracketed launch bookkeeping (profiling mode)
+struct LaunchTimer {
+    cbs_gpu_ctx* c;
+    int kid;
+    int idx = -1;
+    LaunchTimer(cbs_gpu_ctx* ctx, int k) : c(ctx), kid(k) {
+        c->launches++;
+        if (!c->profiling) return;
+        if (c->ev_next + 2 > c->ev_pool.size()) {
+            const size_t old = c->ev_pool.size();
+            c->ev_pool.resize(old + 1024);
+            for (size_t i = old; i < c->ev_pool.size(); ++i) cudaEventCreate(&c->ev_pool[i]);
+        }
+        idx = (int)c->ev_next;
+        c->ev_next += 2;
+        cudaEventRecord(c->ev_pool[idx], c->stream);
+    }
+    ~LaunchTimer() {
+        if (idx < 0) return;
+        cudaEventRecord(c->ev_pool[idx + 1], c->stream);
+        c->ev_used.emplace_back(kid, idx);
+    }
+};
+
+void collect_timers(cbs_gpu_ctx* c) {
+    for (auto& u : c->ev_used) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, c->ev_pool[u.second], c->ev_pool[u.second + 1]) == cudaSuccess) c->kms[u.first] += ms;
+    }
+    c->ev_used.clear();
+    c->ev_next = 0;
+}
+
+int validate_params(cbs_gpu_ctx* c, const cbs_gpu_params* p) {
+    if (!p) return fail(c, CBS_GPU_ERR_INVALID, "params is NULL");
+    if (p->ibin) return fail(c, CBS_GPU_ERR_UNSUPPORTED, "ibin=true is not on the cna segment path and is not implemented");
+    if (p->hybrid) return fail(c, CBS_GPU_ERR_UNSUPPORTED, "hybrid p-values (htmaxp/tailp) are not implemented on the GPU path yet");
+    if (p->undo_prune) return fail(c, CBS_GPU_ERR_UNSUPPORTED, "undo_prune is not implemented on the GPU path yet");
+    if (p->min_width < 1) return fail(c, CBS_GPU_ERR_INVALID, "min_width must be >= 1");
+    if (p->nperm < 0) return fail(c, CBS_GPU_ERR_INVALID, "nperm must be >= 0");
+    if (!(p->alpha >= 0.0)) return fail(c, CBS_GPU_ERR_INVALID, "alpha must be >= 0");
+    if (p->rng_mode != CBS_GPU_RNG_MT19937_64 && p->rng_mode != CBS_GPU_RNG_PHILOX)
+        return fail(c, CBS_GPU_ERR_INVALID, "unknown rng_mode");
+    if (p->do_smooth) {
+        if (p->smooth_region < 0) return fail(c, CBS_GPU_ERR_INVALID, "smooth_region must be non-negative");
+        if (p->smooth_region > SM_MAX_REGION) return fail(c, CBS_GPU_ERR_UNSUPPORTED, "smooth_region > 64 is not supported");
+    }
+    return CBS_GPU_OK;
+}
+
+// ---- smoothing on device buffers -------------------------------------------------------------
+// xin: values (double, device, N), goff: device group offsets [n_groups+1], dlab: labels or nullptr
+// (constant label per group), out: device N. host_off is the host copy of the offsets.
+int smooth_device(cbs_gpu_ctx* c, const double* xin, const long long* goff, const int* dlab, int n_groups, long long N,
+                  int region, double oscale, double sscale, double trim, double* out, const std::vector<long long>& host_off) {
+    if (region < 0) return fail(c, CBS_GPU_ERR_INVALID, "smooth_region must be non-negative");
+    if (region > SM_MAX_REGION) return fail(c, CBS_GPU_ERR_UNSUPPORTED, "smooth_region > 64 is not supported");
+    cudaStream_t st = c->stream;
+    CUDA_TRY(c, cudaMemcpyAsync(out, xin, sizeof(double) * (size_t)N, cudaMemcpyDeviceToDevice, st));
+    if (N == 0 || n_groups == 0) return CBS_GPU_OK;
+    ENSURE(c, c->fv, sizeof(double) * (size_t)N);
+    ENSURE(c, c->fidx, sizeof(int) * (size_t)N);
+    if (dlab) ENSURE(c, c->flab, sizeof(int) * (size_t)N);
+    ENSURE(c, c->diffs, sizeof(double) * (size_t)N);
+    ENSURE(c, c->diffs_sorted, sizeof(double) * (size_t)N);
+    ENSURE(c, c->gout, sizeof(SmoothGroupOut) * (size_t)n_groups);
+    int* flab = dlab ? c->flab.as<int>() : nullptr;
+    SmoothGroupOut* gout = c->gout.as<SmoothGroupOut>();
+    {
+        LaunchTimer t(c, K_SMOOTH);
+        k_sm_compact<<<std::min(n_groups, c->sm_count * 8), 256, 0, st>>>(xin, goff, dlab, n_groups, c->fv.as<double>(),
+                                                                         c->fidx.as<int>(), flab, gout);
+    }
+    // the reference validates trim only when it reaches inflfact (>= 2 finite values and n_keep > 0)
+    std::vector<SmoothGroupOut> hg((size_t)n_groups);
+    CUDA_TRY(c, cudaMemcpyAsync(hg.data(), gout, sizeof(SmoothGroupOut) * (size_t)n_groups, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(c, cudaStreamSynchronize(st));
+    bool reaches = false;
+    for (int g = 0; g < n_groups; ++g)
+        if (hg[g].m >= 2 && llround((1.0 - 2.0 * trim) * (double)(hg[g].m - 1)) > 0) reaches = true;
+    double infl = 1.0;
+    if (reaches) {
+        if (!(trim >= 0.0 && trim < 0.5)) return fail(c, CBS_GPU_ERR_INVALID, "trim must satisfy 0 <= trim < 0.5");
+        if (trim == 0.0) return fail(c, CBS_GPU_ERR_OVERFLOW, "trim == 0: normal quantile at 1 overflows (boost::math::quantile raises overflow_error)");
+        infl = inflfact(trim);
+    }
+    const int maxn = (int)std::min<long long>(N, 1 << 20);
+    {
+        LaunchTimer t(c, K_SMOOTH);
+        dim3 grid((unsigned)std::max(1, std::min((maxn + 255) / 256, 64)), (unsigned)std::min(n_groups, 65535));
+        k_sm_diffs<<<grid, 256, 0, st>>>(c->fv.as<double>(), goff, n_groups, gout, c->diffs.as<double>());
+    }
+    {
+        LaunchTimer t(c, K_SMOOTH);
+        size_t tmp = 0;
+        cub::DeviceSegmentedSort::SortKeys(nullptr, tmp, c->diffs.as<double>(), c->diffs_sorted.as<double>(), (int)N, n_groups,
+                                           goff, goff + 1, st);
+        ENSURE(c, c->cubtmp, tmp + 16);
+        CUDA_TRY(c, cub::DeviceSegmentedSort::SortKeys(c->cubtmp.p, tmp, c->diffs.as<double>(), c->diffs_sorted.as<double>(),
+                                                       (int)N, n_groups, goff, goff + 1, st));
+    }
+    {
+        LaunchTimer t(c, K_SMOOTH);
+        k_sm_sd<<<std::min((n_groups + 3) / 4, c->sm_count * 8), 128, 0, st>>>(c->diffs_sorted.as<double>(), goff, n_groups,
+                                                                              trim, infl, oscale, sscale, gout);
+    }
+    {
+        LaunchTimer t(c, K_SMOOTH);
+        dim3 grid((unsigned)std::max(1, std::min((maxn + 255) / 256, 256)), (unsigned)std::min(n_groups, 65535));
+        k_sm_window<<<grid, 256, 0, st>>>(c->fv.as<double>(), c->fidx.as<int>(), flab, goff, n_groups, region, gout, out);
+    }
+    CUDA_TRY(c, cudaGetLastError());
+    (void)host_off;
+    return CBS_GPU_OK;
+}
+
+struct RunCaps {
+    int task_cap, list_cap, seg_cap, split_cap, max_live;
+    long long arena_cap, draws_cap, rej_cap;
+};
+
+long long env_ll(const char* name, long long dflt) {
+    const char* s = getenv(name);
+    if (!s || !*s) return dflt;
+    return atoll(s);
+}
+
+// The core: x already resident (double, device, smoothed if requested) in c->x.
+int run_cbs(cbs_gpu_ctx* c, const std::vector<long long>& off, const uint64_t* unit_ids, int n_units,
+            const cbs_gpu_params* p, const uint64_t* mt_next312, bool raw_single /*unused*/, Dev& hD) {
+    (void)raw_single;
+    cudaStream_t st = c->stream;
+    const long long N = off[n_units];
+    long long Nmax = 0;
+    for (int u = 0; u < n_units; ++u) Nmax = std::max(Nmax, off[u + 1] - off[u]);
+    if (Nmax > 1000000) return fail(c, CBS_GPU_ERR_UNSUPPORTED, "units longer than 1,000,000 markers are not supported");
+    if (N > 2000000000LL) return fail(c, CBS_GPU_ERR_UNSUPPORTED, "more than 2e9 markers per call are not supported");
+    const bool mt = p->rng_mode == CBS_GPU_RNG_MT19937_64;
+
+    RunCaps cap;
+    cap.task_cap = (int)std::min<long long>(std::max<long long>(4096, 64LL * n_units + 1024), 1 << 22);
+    cap.task_cap = (int)env_ll("CBS_GPU_TASK_CAP", cap.task_cap);
+    cap.list_cap = 4 * cap.task_cap + n_units + 16;
+    cap.seg_cap = (int)std::min<long long>(N / 2 + n_units + 16, std::max<long long>(1 << 20, 256LL * n_units));
+    cap.seg_cap = (int)env_ll("CBS_GPU_SEG_CAP", cap.seg_cap);
+    cap.split_cap = p->record_splits ? 3 * cap.seg_cap + 16 : 1;
+    cap.max_live = mt ? std::max(1, cap.task_cap / 16) : std::max(1, cap.task_cap / 4);
+    cap.rej_cap = 1 << 22;
+
+    ENSURE(c, c->cur, sizeof(double) * (size_t)(N + 1));
+    ENSURE(c, c->gtab, sizeof(double) * (size_t)(N + 1));
+    ENSURE(c, c->factab, sizeof(double) * (size_t)(N + 1));
+    ENSURE(c, c->bbtab, sizeof(int) * (size_t)(N + 1));
+    ENSURE(c, c->unit_off, sizeof(long long) * (size_t)(n_units + 1));
+    ENSURE(c, c->unit_ids, sizeof(uint64_t) * (size_t)(n_units + 1));
+    ENSURE(c, c->tasks, sizeof(Task) * (size_t)cap.task_cap);
+    ENSURE(c, c->ring, sizeof(int) * (size_t)cap.task_cap);
+    ENSURE(c, c->act0, sizeof(int) * (size_t)cap.list_cap);
+    ENSURE(c, c->act1, sizeof(int) * (size_t)cap.list_cap);
+    const int n_chains = mt ? (p->chain ? 1 : n_units) : 0;
+    ENSURE(c, c->chains, sizeof(Chain) * (size_t)std::max(1, n_chains));
+    ENSURE(c, c->segs, sizeof(SegRec) * (size_t)cap.seg_cap);
+    ENSURE(c, c->splits, sizeof(SplitRec) * (size_t)cap.split_cap);
+    ENSURE(c, c->udraws, sizeof(uint64_t) * (size_t)(n_units + 1));
+    ENSURE(c, c->rej, sizeof(int) * (size_t)cap.rej_cap);
+    ENSURE(c, c->prep_task, sizeof(int) * (size_t)cap.list_cap);
+    ENSURE(c, c->items, sizeof(PermItem) * (size_t)cap.list_cap);
+    ENSURE(c, c->item_prefix, sizeof(int) * (size_t)(cap.list_cap + 1));
+    ENSURE(c, c->edgeprep_task, sizeof(int) * (size_t)cap.list_cap);
+    ENSURE(c, c->edges, sizeof(EdgeItem) * (size_t)cap.list_cap);
+    ENSURE(c, c->edge_prefix, sizeof(int) * (size_t)(cap.list_cap + 1));
+    ENSURE(c, c->gen_chain, sizeof(int) * (size_t)(n_chains + 1));
+    ENSURE(c, c->means, sizeof(double) * (size_t)cap.seg_cap);
+    ENSURE(c, c->seed312, sizeof(uint64_t) * 312);
+    ENSURE(c, c->dev, sizeof(Dev));
+
+    // arenas: sized from the workload, bounded by what the device has left
+    size_t free_b = 0, total_b = 0;
+    CUDA_TRY(c, cudaMemGetInfo(&free_b, &total_b));
+    const long long per_perm_max = 3 * Nmax + 64;
+    long long want_arena = std::min<long long>(24LL * 4096 * std::max<long long>(N, 1), 32LL << 30) / 8;
+    want_arena = std::max<long long>(want_arena, 16 * per_perm_max);
+    want_arena = std::max<long long>(want_arena, (64LL << 20) / 8);
+    long long want_draws = mt ? std::max<long long>(want_arena / 3, 8 * (Nmax + 312)) : 1;
+    const long long env_arena = env_ll("CBS_GPU_ARENA_MB", 0);
+    if (env_arena > 0) { want_arena = env_arena * (1LL << 20) / 8; if (mt) want_draws = std::max<long long>(want_arena / 3, 8 * (Nmax + 312)); }
+    {
+        const size_t have = c->arena.cap + c->draws0.cap + c->draws1.cap;
+        const double budget = 0.80 * (double)(free_b + have);
+        const double need = 8.0 * ((double)want_arena + 2.0 * (double)want_draws);
+        if (need > budget) {
+            const double f = budget / need;
+            want_arena = (long long)((double)want_arena * f);
+            want_draws = (long long)((double)want_draws * f);
+        }
+    }
+    if (want_arena < 4 * per_perm_max) return fail(c, CBS_GPU_ERR_OOM, "not enough device memory for the permutation arena");
+    if ((long long)(c->arena.cap / 8) < want_arena) ENSURE(c, c->arena, (size_t)want_arena * 8);
+    if (mt) {
+        if ((long long)(c->draws0.cap / 8) < want_draws) ENSURE(c, c->draws0, (size_t)want_draws * 8);
+        if ((long long)(c->draws1.cap / 8) < want_draws) ENSURE(c, c->draws1, (size_t)want_draws * 8);
+    }
+    cap.arena_cap = (long long)(c->arena.cap / 8);
+    cap.draws_cap = mt ? (long long)(std::min(c->draws0.cap, c->draws1.cap) / 8) : 0;
+
+    // ---- device state ---------------------------------------------------------------------
+    memset(&hD, 0, sizeof(hD));
+    hD.x = c->x.as<double>();
+    hD.unit_off = c->unit_off.as<long long>();
+    hD.unit_ids = unit_ids ? c->unit_ids.as<uint64_t>() : nullptr;
+    hD.n_units = n_units;
+    hD.prm.alpha = p->alpha; hD.prm.nperm = p->nperm; hD.prm.hybrid = p->hybrid; hD.prm.min_width = p->min_width;
+    hD.prm.kmax = p->kmax; hD.prm.nmin = p->nmin; hD.prm.eta = p->eta; hD.prm.tol = p->tol; hD.prm.ibin = p->ibin;
+    hD.prm.rng_mode = mt ? RNG_MT : RNG_PHILOX; hD.prm.chain = p->chain ? 1 : 0; hD.prm.seed = p->seed;
+    hD.prm.first_batch = p->first_batch > 0 ? p->first_batch : 256;
+    hD.prm.max_batch = p->max_batch > 0 ? p->max_batch : 2048;
+    if (hD.prm.max_batch < hD.prm.first_batch) hD.prm.max_batch = hD.prm.first_batch;
+    hD.prm.record_splits = p->record_splits ? 1 : 0;
+    hD.cur = c->cur.as<double>(); hD.gtab = c->gtab.as<double>(); hD.factab = c->factab.as<double>(); hD.bbtab = c->bbtab.as<int>();
+    hD.tasks = c->tasks.as<Task>(); hD.task_cap = cap.task_cap; hD.free_ring = c->ring.as<int>();
+    hD.free_head = 0; hD.free_tail = (unsigned)cap.task_cap;
+    hD.active[0] = c->act0.as<int>(); hD.active[1] = c->act1.as<int>(); hD.list_cap = cap.list_cap;
+    hD.chains = c->chains.as<Chain>(); hD.n_chains = n_chains;
+    hD.units_started = 0; hD.max_live = cap.max_live;
+    hD.segs = c->segs.as<SegRec>(); hD.seg_cap = cap.seg_cap;
+    hD.splits = c->splits.as<SplitRec>(); hD.split_cap = cap.split_cap;
+    hD.unit_draws = c->udraws.as<uint64_t>();
+    hD.arena = c->arena.as<double>(); hD.arena_cap = cap.arena_cap;
+    hD.rej = c->rej.as<int>(); hD.rej_cap = cap.rej_cap;
+    hD.draws[0] = c->draws0.as<uint64_t>(); hD.draws[1] = c->draws1.as<uint64_t>(); hD.draws_cap = cap.draws_cap;
+    hD.prep_task = c->prep_task.as<int>(); hD.items = c->items.as<PermItem>(); hD.item_prefix = c->item_prefix.as<int>();
+    hD.edgeprep_task = c->edgeprep_task.as<int>(); hD.edges = c->edges.as<EdgeItem>(); hD.edge_prefix = c->edge_prefix.as<int>();
+    hD.gen_chain = c->gen_chain.as<int>();
+    hD.profile = c->profiling ? 1 : 0;
+
+    CUDA_TRY(c, cudaMemcpyAsync(c->unit_off.p, off.data(), sizeof(long long) * (size_t)(n_units + 1), cudaMemcpyHostToDevice, st));
+    if (unit_ids) CUDA_TRY(c, cudaMemcpyAsync(c->unit_ids.p, unit_ids, sizeof(uint64_t) * (size_t)n_units, cudaMemcpyHostToDevice, st));
+    {
+        std::vector<int> ring((size_t)cap.task_cap);
+        for (int i = 0; i < cap.task_cap; ++i) ring[i] = i;
+        CUDA_TRY(c, cudaMemcpyAsync(c->ring.p, ring.data(), sizeof(int) * ring.size(), cudaMemcpyHostToDevice, st));
+        CUDA_TRY(c, cudaMemsetAsync(c->udraws.p, 0, sizeof(uint64_t) * (size_t)(n_units + 1), st));
+        CUDA_TRY(c, cudaMemcpyAsync(c->dev.p, &hD, sizeof(Dev), cudaMemcpyHostToDevice, st));
+        CUDA_TRY(c, cudaStreamSynchronize(st));  // `ring` is a stack temporary
+    }
+    Dev* dD = c->dev.as<Dev>();
+    if (mt) {
+        uint64_t next[312];
+        if (mt_next312) memcpy(next, mt_next312, sizeof(next)); else mt_seed_next312(p->seed, next);
+        CUDA_TRY(c, cudaMemcpyAsync(c->seed312.p, next, sizeof(next), cudaMemcpyHostToDevice, st));
+        CUDA_TRY(c, cudaStreamSynchronize(st));
+        k_init_chains<<<std::min(std::max(1, n_chains), 1024), 128, 0, st>>>(dD, c->seed312.as<uint64_t>());
+    }
+
+    // ---- scan kernel configuration ------------------------------------------------------------
+    ScanLayout lay;
+    lay.nb_max = block_count((int)std::max<long long>(Nmax, 1)) + 1;
+    {
+        int bmax = 1;
+        // the largest block of any segment length <= Nmax: ceil(n/nb)+1 is increasing in n for n >= 50
+        const int nbm = block_count((int)std::max<long long>(Nmax, 1));
+        bmax = (int)((Nmax + nbm - 1) / nbm) + 2;
+        bmax = std::max(bmax, 50);
+        lay.B_max = bmax;
+    }
+    lay.warps = 8;
+    while (lay.warps > 1 && lay.bytes() > c->smem_optin) lay.warps >>= 1;
+    if (lay.bytes() > c->smem_optin) return fail(c, CBS_GPU_ERR_UNSUPPORTED, "segment too long for the scan kernel's shared memory");
+    const size_t scan_smem = lay.bytes();
+    CUDA_TRY(c, cudaFuncSetAttribute(k_scan, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)scan_smem));
+    int scan_occ = 1;
+    CUDA_TRY(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&scan_occ, k_scan, lay.warps * 32, scan_smem));
+    scan_occ = std::max(1, scan_occ);
+    const int scan_grid = c->sm_count * scan_occ;
+
+    // ---- rounds -------------------------------------------------------------------------------
+    *c->h_done = 0;
+    const int G = 8;  // rounds per group
+    int groups_in_flight = 0, rounds = 0;
+    int gi = 0;
+    for (;;) {
+        for (int r = 0; r < G; ++r) {
+            { LaunchTimer t(c, K_SCHED); k_sched<<<1, 256, 0, st>>>(dD, c->d_done); }
+            if (mt) { LaunchTimer t(c, K_GEN); k_gen<<<std::min(std::max(1, n_chains), c->sm_count * 4), 192, 0, st>>>(dD); }
+            { LaunchTimer t(c, K_PREP); k_prep<<<c->sm_count * 2, 128, 0, st>>>(dD); }
+            { LaunchTimer t(c, K_PERM); k_perm<<<c->sm_count * 8, 128, 0, st>>>(dD); }
+            { LaunchTimer t(c, K_SCAN); k_scan<<<scan_grid, lay.warps * 32, scan_smem, st>>>(dD, lay); }
+            { LaunchTimer t(c, K_EDGEPREP); k_edgeprep<<<c->sm_count, 128, 0, st>>>(dD); }
+            { LaunchTimer t(c, K_EDGEPERM); k_edgeperm<<<c->sm_count * 4, 128, 0, st>>>(dD); }
+            ++rounds;
+        }
+        CUDA_TRY(c, cudaEventRecord(c->grp[gi], st));
+        gi ^= 1;
+        ++groups_in_flight;
+        if (groups_in_flight == 2) {
+            CUDA_TRY(c, cudaEventSynchronize(c->grp[gi]));  // the older group
+            --groups_in_flight;
+            if (*(volatile int*)c->h_done != 0) break;
+        }
+        if (rounds > 50000000) return fail(c, CBS_GPU_ERR_CUDA, "scheduler did not terminate");
+    }
+    CUDA_TRY(c, cudaStreamSynchronize(st));
+    CUDA_TRY(c, cudaGetLastError());
+    CUDA_TRY(c, cudaMemcpy(&hD, dD, sizeof(Dev), cudaMemcpyDeviceToHost));
+    if (hD.error) {
+        switch (hD.error) {
+        case ERR_TASK_CAP: return fail(c, CBS_GPU_ERR_CAPACITY, "pending-segment pool exhausted (raise CBS_GPU_TASK_CAP)");
+        case ERR_SEG_CAP: return fail(c, CBS_GPU_ERR_CAPACITY, "segment table exhausted (raise CBS_GPU_SEG_CAP)");
+        case ERR_SPLIT_CAP: return fail(c, CBS_GPU_ERR_CAPACITY, "split log exhausted");
+        case ERR_ARENA: return fail(c, CBS_GPU_ERR_OOM, "permutation arena too small for one segment (raise CBS_GPU_ARENA_MB)");
+        default: return fail(c, CBS_GPU_ERR_CUDA, "internal scheduler error " + std::to_string(hD.error));
+        }
+    }
+    if (hD.n_segs > 0) {
+        LaunchTimer t(c, K_MEANS);
+        k_means<<<std::min((hD.n_segs + 3) / 4, c->sm_count * 8), 128, 0, st>>>(dD, c->means.as<double>());
+    }
+    CUDA_TRY(c, cudaGetLastError());
+    return CBS_GPU_OK;
+}
+
+struct ResultOwner {
+    cbs_gpu_result pub;
+    std::vector<int64_t> seg_offsets;
+    std::vector<int32_t> lengths;
+    std::vector<double> means;
+    std::vector<uint64_t> draws;
+    std::vector<cbs_gpu_split> splits;
+};
+
+int fetch_results(cbs_gpu_ctx* c, const Dev& hD, int n_units, bool want_splits, ResultOwner* R) {
+    cudaStream_t st = c->stream;
+    const int ns = hD.n_segs;
+    std::vector<SegRec> segs((size_t)ns);
+    std::vector<double> means((size_t)ns);
+    R->draws.assign((size_t)n_units, 0);
+    if (ns) {
+        CUDA_TRY(c, cudaMemcpyAsync(segs.data(), c->segs.p, sizeof(SegRec) * (size_t)ns, cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(c, cudaMemcpyAsync(means.data(), c->means.p, sizeof(double) * (size_t)ns, cudaMemcpyDeviceToHost, st));
+    }
+    if (n_units) CUDA_TRY(c, cudaMemcpyAsync(R->draws.data(), c->udraws.p, sizeof(uint64_t) * (size_t)n_units, cudaMemcpyDeviceToHost, st));
+    std::vector<SplitRec> sp;
+    if (want_splits && hD.n_splits) {
+        sp.resize((size_t)hD.n_splits);
+        CUDA_TRY(c, cudaMemcpyAsync(sp.data(), c->splits.p, sizeof(SplitRec) * sp.size(), cudaMemcpyDeviceToHost, st));
+    }
+    CUDA_TRY(c, cudaStreamSynchronize(st));
+    // order segments by (unit, lo)
+    std::vector<int> order((size_t)ns);
+    for (int i = 0; i < ns; ++i) order[i] = i;
+    std::sort(order.begin(), order.end(), [&](int a, int b) {
+        if (segs[a].unit != segs[b].unit) return segs[a].unit < segs[b].unit;
+        return segs[a].lo < segs[b].lo;
+    });
+    R->seg_offsets.assign((size_t)n_units + 1, 0);
+    R->lengths.resize((size_t)ns);
+    R->means.resize((size_t)ns);
+    for (int k = 0; k < ns; ++k) {
+        const SegRec& s = segs[order[k]];
+        R->lengths[k] = s.hi - s.lo;
+        R->means[k] = means[order[k]];
+        R->seg_offsets[(size_t)s.unit + 1]++;
+    }
+    for (int u = 0; u < n_units; ++u) R->seg_offsets[u + 1] += R->seg_offsets[u];
+    R->splits.resize(sp.size());
+    for (size_t k = 0; k < sp.size(); ++k) {
+        cbs_gpu_split& o = R->splits[k];
+        const SplitRec& s = sp[k];
+        o.unit = s.unit; o.lo = s.lo; o.hi = s.hi; o.ostat = s.ostat; o.iseg0 = s.iseg0; o.iseg1 = s.iseg1;
+        o.ncpt = s.ncpt; o.icpt0 = s.icpt0; o.icpt1 = s.icpt1; o.perms_run = s.perms_run; o.nrej = s.nrej;
+        o.exit_code = s.exit_code; o.called = s.called; o.e_nrej0 = s.e_nrej0; o.e_nrej1 = s.e_nrej1;
+        o.e_status0 = s.e_status0; o.e_status1 = s.e_status1;
+    }
+    R->pub.n_units = n_units;
+    R->pub.n_segments = ns;
+    R->pub.seg_offsets = R->seg_offsets.data();
+    R->pub.lengths = R->lengths.data();
+    R->pub.means = R->means.data();
+    R->pub.draws_consumed = R->draws.data();
+    R->pub.n_splits = (int64_t)R->splits.size();
+    R->pub.splits = R->splits.empty() ? nullptr : R->splits.data();
+    R->pub.rounds = hD.round;
+    R->pub.perms_run = hD.stat_perms;
+    return CBS_GPU_OK;
+}
+
+// stage `values` into c->x as double on the device
+int stage_values(cbs_gpu_ctx* c, const void* values, int dtype, int memspace, long long N, double* dst) {
+    cudaStream_t st = c->stream;
+    if (N == 0) return CBS_GPU_OK;
+    if (dtype == CBS_GPU_F64) {
+        const cudaMemcpyKind kind = memspace == CBS_GPU_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+        CUDA_TRY(c, cudaMemcpyAsync(dst, values, sizeof(double) * (size_t)N, kind, st));
+    } else {
+        const float* src = (const float*)values;
+        if (memspace != CBS_GPU_DEVICE) {
+            ENSURE(c, c->staging, sizeof(float) * (size_t)N);
+            CUDA_TRY(c, cudaMemcpyAsync(c->staging.p, values, sizeof(float) * (size_t)N, cudaMemcpyHostToDevice, st));
+            src = c->staging.as<float>();
+        }
+        k_widen_f32<<<std::min<long long>((N + 255) / 256, c->sm_count * 16), 256, 0, st>>>(src, dst, N);
+        c->launches++;
+    }
+    return CBS_GPU_OK;
+}
+
+}  // namespace
+
+// =========================================================================================
+// C ABI
+// =========================================================================================
+extern "C" {
+
+void cbs_gpu_default_params(cbs_gpu_params* p) {
+    memset(p, 0, sizeof(*p));
+    p->alpha = 0.01; p->nperm = 200; p->hybrid = 0; p->min_width = 2; p->kmax = 25; p->nmin = 200; p->eta = 0.05;
+    p->tol = 1e-6; p->ibin = 0; p->undo_prune = 0; p->undo_prune_cutoff = 0.05;
+    p->do_smooth = 1; p->smooth_region = 10; p->outlier_sd_scale = 4.0; p->smooth_sd_scale = 2.0; p->trim = 0.025;
+    p->rng_mode = CBS_GPU_RNG_MT19937_64; p->chain = 1; p->seed = 1;
+}
+
+int cbs_gpu_create(const int* device_ids, int ndev, cbs_gpu_ctx** out) {
+    if (!out) return CBS_GPU_ERR_INVALID;
+    *out = nullptr;
+    if (ndev != 1 || !device_ids) return CBS_GPU_ERR_INVALID;
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0) return CBS_GPU_ERR_CUDA;  // no CPU fallback
+    if (device_ids[0] < 0 || device_ids[0] >= count) return CBS_GPU_ERR_INVALID;
+    cbs_gpu_ctx* c = new cbs_gpu_ctx();
+    c->device = device_ids[0];
+    if (cudaSetDevice(c->device) != cudaSuccess) { delete c; return CBS_GPU_ERR_CUDA; }
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, c->device) != cudaSuccess) { delete c; return CBS_GPU_ERR_CUDA; }
+    c->sm_count = prop.multiProcessorCount;
+    c->smem_optin = prop.sharedMemPerBlockOptin;
+    if (cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking) != cudaSuccess) { delete c; return CBS_GPU_ERR_CUDA; }
+    c->stream = c->own_stream;
+    if (cudaHostAlloc((void**)&c->h_done, sizeof(int), cudaHostAllocMapped) != cudaSuccess) { delete c; return CBS_GPU_ERR_CUDA; }
+    *c->h_done = 0;
+    if (cudaHostGetDevicePointer((void**)&c->d_done, c->h_done, 0) != cudaSuccess) { delete c; return CBS_GPU_ERR_CUDA; }
+    cudaEventCreate(&c->e0); cudaEventCreate(&c->e1); cudaEventCreate(&c->e2); cudaEventCreate(&c->e3); cudaEventCreate(&c->e4);
+    cudaEventCreateWithFlags(&c->grp[0], cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&c->grp[1], cudaEventDisableTiming);
+    *out = c;
+    return CBS_GPU_OK;
+}
+
+void cbs_gpu_destroy(cbs_gpu_ctx* c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    cudaDeviceSynchronize();
+    DevBuf* bufs[] = {&c->x, &c->cur, &c->gtab, &c->factab, &c->bbtab, &c->unit_off, &c->unit_ids, &c->tasks, &c->ring, &c->act0,
+                      &c->act1, &c->chains, &c->segs, &c->splits, &c->udraws, &c->arena, &c->rej, &c->draws0, &c->draws1,
+                      &c->prep_task, &c->items, &c->item_prefix, &c->edgeprep_task, &c->edges, &c->edge_prefix, &c->gen_chain,
+                      &c->means, &c->seed312, &c->dev, &c->staging, &c->fv, &c->fidx, &c->flab, &c->lab, &c->diffs,
+                      &c->diffs_sorted, &c->gout, &c->cubtmp, &c->flag, &c->goff};
+    for (DevBuf* b : bufs) if (b->p) cudaFree(b->p);
+    if (c->h_stage) cudaFreeHost(c->h_stage);
+    if (c->h_done) cudaFreeHost(c->h_done);
+    for (auto e : c->ev_pool) cudaEventDestroy(e);
+    cudaEvent_t evs[] = {c->e0, c->e1, c->e2, c->e3, c->e4, c->grp[0], c->grp[1]};
+    for (auto e : evs) if (e) cudaEventDestroy(e);
+    if (c->own_stream) cudaStreamDestroy(c->own_stream);
+    delete c;
+}
+
+const char* cbs_gpu_last_error(const cbs_gpu_ctx* c) { return c ? c->err.c_str() : "no context"; }
+
+int cbs_gpu_set_stream(cbs_gpu_ctx* c, void* s) {
+    if (!c) return CBS_GPU_ERR_INVALID;
+    c->stream = s ? (cudaStream_t)s : c->own_stream;
+    return CBS_GPU_OK;
+}
+
+int cbs_gpu_set_profiling(cbs_gpu_ctx* c, int on) {
+    if (!c) return CBS_GPU_ERR_INVALID;
+    c->profiling = on != 0;
+    return CBS_GPU_OK;
+}
+
+int cbs_gpu_last_kernel_ms(cbs_gpu_ctx* c, double* ms9) {
+    if (!c || !ms9) return CBS_GPU_ERR_INVALID;
+    for (int k = 0; k < 9; ++k) ms9[k] = c->kms[k];
+    return CBS_GPU_OK;
+}
+
+int cbs_gpu_last_arc_evals(cbs_gpu_ctx* c, uint64_t* arcs, uint64_t* slots) {
+    if (!c || !arcs || !slots) return CBS_GPU_ERR_INVALID;
+    *arcs = c->last_arcs;
+    *slots = c->last_slots;
+    return CBS_GPU_OK;
+}
+
+int cbs_gpu_measure_fp64(cbs_gpu_ctx* c, double* tera_inst_per_s) {
+    if (!c || !tera_inst_per_s) return CBS_GPU_ERR_INVALID;
+    if (cudaSetDevice(c->device) != cudaSuccess) return fail(c, CBS_GPU_ERR_CUDA, "cudaSetDevice failed");
+    const int grid = c->sm_count * 8, block = 256, iters = 4096;
+    ENSURE(c, c->staging, sizeof(double) * (size_t)grid * block);
+    cudaStream_t st = c->stream;
+    double best = 0.0;
+    for (int rep = 0; rep < 5; ++rep) {
+        CUDA_TRY(c, cudaEventRecord(c->e0, st));
+        k_fp64_peak<<<grid, block, 0, st>>>(c->staging.as<double>(), iters, 1e-9);
+        CUDA_TRY(c, cudaEventRecord(c->e1, st));
+        CUDA_TRY(c, cudaEventSynchronize(c->e1));
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, c->e0, c->e1);
+        // per thread: iters * 4 * 8 * 2 FP64 instructions
+        const double inst = (double)grid * block * (double)iters * 64.0;
+        if (rep > 0 && ms > 0.f) best = std::max(best, inst / (ms * 1e-3) / 1e12);
+    }
+    *tera_inst_per_s = best;
+    return CBS_GPU_OK;
+}
+
+// ---- low level: cbs::tmaxo / cbs::tmaxp on vectors as given ------------------------------------
+static int run_raw_scan(cbs_gpu_ctx* c, const double* xh, int n, int count, double tss, int al0, int ibin, int obs,
+                        std::vector<Task>& tasks_out) {
+    if (!c) return CBS_GPU_ERR_INVALID;
+    if (ibin) return fail(c, CBS_GPU_ERR_UNSUPPORTED, "ibin=true is not implemented");
+    if (n < 2 || count < 1 || !xh) return fail(c, CBS_GPU_ERR_INVALID, "bad arguments");
+    if (al0 < 1 || n < 2 * al0) return fail(c, CBS_GPU_ERR_INVALID, "need n >= 2*al0, al0 >= 1");
+    if (n > 1000000) return fail(c, CBS_GPU_ERR_UNSUPPORTED, "vectors longer than 1,000,000 are not supported");
+    if (cudaSetDevice(c->device) != cudaSuccess) return fail(c, CBS_GPU_ERR_CUDA, "cudaSetDevice failed");
+    cudaStream_t st = c->stream;
+    const long long N = (long long)n * count;
+    const int nb = block_count(n);
+    const long long per = Sched::sx_stride(n) + Sched::bs_stride(nb);
+    ENSURE(c, c->x, sizeof(double) * (size_t)(N + 1));
+    ENSURE(c, c->cur, sizeof(double) * (size_t)(N + 1));
+    ENSURE(c, c->gtab, sizeof(double) * (size_t)(N + 1));
+    ENSURE(c, c->factab, sizeof(double) * (size_t)(N + 1));
+    ENSURE(c, c->bbtab, sizeof(int) * (size_t)(N + 1));
+    ENSURE(c, c->unit_off, sizeof(long long) * (size_t)(count + 1));
+    ENSURE(c, c->tasks, sizeof(Task) * (size_t)count);
+    ENSURE(c, c->arena, sizeof(double) * (size_t)(per * count));
+    ENSURE(c, c->rej, sizeof(int) * (size_t)count);
+    ENSURE(c, c->prep_task, sizeof(int) * (size_t)count);
+    ENSURE(c, c->items, sizeof(PermItem) * (size_t)count);
+    ENSURE(c, c->item_prefix, sizeof(int) * (size_t)(count + 1));
+    ENSURE(c, c->dev, sizeof(Dev));
+    std::vector<long long> off((size_t)count + 1);
+    std::vector<Task> tasks((size_t)count);
+    std::vector<int> prep((size_t)count), prefix((size_t)count + 1);
+    std::vector<PermItem> items((size_t)count);
+    memset(tasks.data(), 0, sizeof(Task) * tasks.size());
+    for (int u = 0; u <= count; ++u) off[u] = (long long)u * n;
+    for (int u = 0; u < count; ++u) {
+        Task& t = tasks[u];
+        t.unit = u; t.lo = 0; t.hi = n; t.n = n; t.nb = nb; t.raw = 1; t.tss = tss; t.state = TS_OBS;
+        t.off_sx = per * u; t.off_bs = per * u + Sched::sx_stride(n); t.off_rej = u; t.next = -1;
+        prep[u] = u; prefix[u] = u;
+        items[u].task = u; items[u].P = 1; items[u].obs = obs;
+    }
+    prefix[count] = count;
+    Dev hD;
+    memset(&hD, 0, sizeof(hD));
+    hD.x = c->x.as<double>(); hD.unit_off = c->unit_off.as<long long>(); hD.n_units = count;
+    hD.prm.min_width = al0; hD.prm.nperm = 0; hD.prm.rng_mode = RNG_PHILOX;
+    hD.cur = c->cur.as<double>(); hD.gtab = c->gtab.as<double>(); hD.factab = c->factab.as<double>(); hD.bbtab = c->bbtab.as<int>();
+    hD.tasks = c->tasks.as<Task>(); hD.task_cap = count;
+    hD.arena = c->arena.as<double>(); hD.arena_cap = per * count; hD.rej = c->rej.as<int>(); hD.rej_cap = count;
+    hD.n_prep = count; hD.prep_task = c->prep_task.as<int>();
+    hD.n_items = count; hD.items = c->items.as<PermItem>(); hD.item_prefix = c->item_prefix.as<int>();
+    CUDA_TRY(c, cudaMemcpyAsync(c->x.p, xh, sizeof(double) * (size_t)N, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(c, cudaMemcpyAsync(c->unit_off.p, off.data(), sizeof(long long) * off.size(), cudaMemcpyHostToDevice, st));
+    CUDA_TRY(c, cudaMemcpyAsync(c->tasks.p, tasks.data(), sizeof(Task) * tasks.size(), cudaMemcpyHostToDevice, st));
+    CUDA_TRY(c, cudaMemcpyAsync(c->prep_task.p, prep.data(), sizeof(int) * prep.size(), cudaMemcpyHostToDevice, st));
+    CUDA_TRY(c, cudaMemcpyAsync(c->items.p, items.data(), sizeof(PermItem) * items.size(), cudaMemcpyHostToDevice, st));
+    CUDA_TRY(c, cudaMemcpyAsync(c->item_prefix.p, prefix.data(), sizeof(int) * prefix.size(), cudaMemcpyHostToDevice, st));
+    CUDA_TRY(c, cudaMemcpyAsync(c->dev.p, &hD, sizeof(Dev), cudaMemcpyHostToDevice, st));
+    ScanLayout lay;
+    lay.nb_max = nb + 1;
+    lay.B_max = std::max((n + nb - 1) / nb + 2, 50);
+    lay.warps = 8;
+    while (lay.warps > 1 && lay.bytes() > c->smem_optin) lay.warps >>= 1;
+    if (lay.bytes() > c->smem_optin) return fail(c, CBS_GPU_ERR_UNSUPPORTED, "vector too long for the scan kernel's shared memory");
+    CUDA_TRY(c, cudaFuncSetAttribute(k_scan, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lay.bytes()));
+    Dev* dD = c->dev.as<Dev>();
+    k_prep<<<std::min((count + 3) / 4, c->sm_count * 4), 128, 0, st>>>(dD);
+    k_scan<<<std::min(count, c->sm_count * 2), lay.warps * 32, lay.bytes(), st>>>(dD, lay);
+    CUDA_TRY(c, cudaGetLastError());
+    tasks_out.resize((size_t)count);
+    CUDA_TRY(c, cudaMemcpyAsync(tasks_out.data(), c->tasks.p, sizeof(Task) * tasks_out.size(), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(c, cudaStreamSynchronize(st));
+    return CBS_GPU_OK;
+}
+
+int cbs_gpu_tmaxo(cbs_gpu_ctx* c, const double* x, int32_t n, double tss, int32_t al0, int32_t ibin, double* statistic,
+                  int32_t* start, int32_t* end) {
+    std::vector<Task> t;
+    const int rc = run_raw_scan(c, x, n, 1, tss, al0, ibin, 1, t);
+    if (rc) return rc;
+    if (statistic) *statistic = t[0].ostat;
+    if (start) *start = t[0].tmaxi - 1;  // CBS.cpp:380
+    if (end) *end = t[0].tmaxj - 1;
+    return CBS_GPU_OK;
+}
+
+int cbs_gpu_tmaxp(cbs_gpu_ctx* c, const double* px, int32_t n, int32_t count, double tss, int32_t al0, int32_t ibin,
+                  double* statistics) {
+    std::vector<Task> t;
+    const int rc = run_raw_scan(c, px, n, count, tss, al0, ibin, 2, t);
+    if (rc) return rc;
+    for (int k = 0; k < count; ++k) statistics[k] = t[k].ostat;
+    return CBS_GPU_OK;
+}
+
+int cbs_gpu_segment_batch(cbs_gpu_ctx* c, const void* values, int dtype, int memspace, const int64_t* unit_offsets,
+                          const uint64_t* unit_ids, int32_t n_units, const cbs_gpu_params* params, cbs_gpu_result** out) {
+    if (!c) return CBS_GPU_ERR_INVALID;
+    if (!out) return fail(c, CBS_GPU_ERR_INVALID, "out is NULL");
+    *out = nullptr;
+    if (cudaSetDevice(c->device) != cudaSuccess) return fail(c, CBS_GPU_ERR_CUDA, "cudaSetDevice failed");
+    int rc = validate_params(c, params);
+    if (rc) return rc;
+    if (n_units < 0 || !unit_offsets) return fail(c, CBS_GPU_ERR_INVALID, "bad unit table");
+    if (dtype != CBS_GPU_F32 && dtype != CBS_GPU_F64) return fail(c, CBS_GPU_ERR_INVALID, "bad dtype");
+    std::vector<long long> off((size_t)n_units + 1);
+    for (int u = 0; u <= n_units; ++u) {
+        off[u] = unit_offsets[u];
+        if (u && off[u] < off[u - 1]) return fail(c, CBS_GPU_ERR_INVALID, "unit_offsets must be non-decreasing");
+    }
+    if (off[0] != 0) return fail(c, CBS_GPU_ERR_INVALID, "unit_offsets[0] must be 0");
+    const long long N = off[n_units];
+    if (N > 0 && !values) return fail(c, CBS_GPU_ERR_INVALID, "values is NULL");
+    for (int k = 0; k < K_COUNT; ++k) c->kms[k] = 0.0;
+    c->launches = 0;
+    cudaStream_t st = c->stream;
+    ENSURE(c, c->x, sizeof(double) * (size_t)(N + 1));
+    ENSURE(c, c->flag, sizeof(int));
+    CUDA_TRY(c, cudaEventRecord(c->e0, st));
+    double* xdst = c->x.as<double>();
+    if (params->do_smooth) {
+        ENSURE(c, c->diffs_sorted, sizeof(double) * (size_t)(N + 1));  // reused below as the raw copy
+        ENSURE(c, c->lab, sizeof(double) * (size_t)(N + 1));
+        xdst = c->lab.as<double>();  // raw widened values; smoothing writes c->x
+    }
+    rc = stage_values(c, values, dtype, memspace, N, xdst);
+    if (rc) return rc;
+    CUDA_TRY(c, cudaEventRecord(c->e1, st));
+    if (params->do_smooth) {
+        ENSURE(c, c->goff, sizeof(long long) * (size_t)(n_units + 1));
+        CUDA_TRY(c, cudaMemcpyAsync(c->goff.p, off.data(), sizeof(long long) * (size_t)(n_units + 1), cudaMemcpyHostToDevice, st));
+        rc = smooth_device(c, xdst, c->goff.as<long long>(), nullptr, n_units, N, params->smooth_region, params->outlier_sd_scale,
+                           params->smooth_sd_scale, params->trim, c->x.as<double>(), off);
+        if (rc) return rc;
+    }
+    CUDA_TRY(c, cudaEventRecord(c->e2, st));
+    // CBS needs finite input (the reference has no defined behaviour otherwise)
+    CUDA_TRY(c, cudaMemsetAsync(c->flag.p, 0, sizeof(int), st));
+    if (N) { k_count_nonfinite<<<std::min<long long>((N + 255) / 256, c->sm_count * 8), 256, 0, st>>>(c->x.as<double>(), N, c->flag.as<int>()); c->launches++; }
+    int bad = 0;
+    CUDA_TRY(c, cudaMemcpyAsync(&bad, c->flag.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(c, cudaStreamSynchronize(st));
+    if (bad) return fail(c, CBS_GPU_ERR_NONFINITE, "non-finite values reach CBS; remove them first (DNAcopy drops missing values before segmenting)");
+    Dev hD;
+    rc = run_cbs(c, off, unit_ids, n_units, params, nullptr, false, hD);
+    if (rc) return rc;
+    CUDA_TRY(c, cudaEventRecord(c->e3, st));
+    ResultOwner* R = new ResultOwner();
+    memset(&R->pub, 0, sizeof(R->pub));
+    rc = fetch_results(c, hD, n_units, params->record_splits != 0, R);
+    if (rc) { delete R; return rc; }
+    CUDA_TRY(c, cudaEventRecord(c->e4, st));
+    CUDA_TRY(c, cudaEventSynchronize(c->e4));
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, c->e0, c->e1); R->pub.ms_h2d = ms;
+    cudaEventElapsedTime(&ms, c->e1, c->e2); R->pub.ms_smooth = ms;
+    cudaEventElapsedTime(&ms, c->e2, c->e3); R->pub.ms_segment = ms;
+    cudaEventElapsedTime(&ms, c->e3, c->e4); R->pub.ms_d2h = ms;
+    if (c->profiling) collect_timers(c);
+    R->pub.kernel_launches = c->launches;
+    c->last_arcs = hD.stat_arcs;
+    c->last_slots = hD.stat_slots;
+    *out = &R->pub;
+    return CBS_GPU_OK;
+}
+
+void cbs_gpu_result_free(cbs_gpu_result* r) {
+    if (!r) return;
+    delete reinterpret_cast<ResultOwner*>(r);  // pub is the first member
+}
+
+int cbs_gpu_smooth(cbs_gpu_ctx* c, const double* values, const int32_t* chrom, int64_t n, int32_t smooth_region,
+                   double outlier_sd_scale, double smooth_sd_scale, double trim, double* out) {
+    if (!c) return CBS_GPU_ERR_INVALID;
+    if (n < 0 || (n > 0 && (!values || !chrom || !out))) return fail(c, CBS_GPU_ERR_INVALID, "bad arguments");
+    if (smooth_region < 0) return fail(c, CBS_GPU_ERR_INVALID, "smooth_region must be non-negative");
+    if (cudaSetDevice(c->device) != cudaSuccess) return fail(c, CBS_GPU_ERR_CUDA, "cudaSetDevice failed");
+    if (n == 0) return CBS_GPU_OK;
+    cudaStream_t st = c->stream;
+    ENSURE(c, c->x, sizeof(double) * (size_t)(n + 1));
+    ENSURE(c, c->lab, sizeof(double) * (size_t)(n + 1));
+    ENSURE(c, c->staging, sizeof(int) * (size_t)n);
+    ENSURE(c, c->goff, sizeof(long long) * 2);
+    const long long goff[2] = {0, (long long)n};
+    std::vector<long long> off(goff, goff + 2);
+    CUDA_TRY(c, cudaMemcpyAsync(c->lab.p, values, sizeof(double) * (size_t)n, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(c, cudaMemcpyAsync(c->staging.p, chrom, sizeof(int) * (size_t)n, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(c, cudaMemcpyAsync(c->goff.p, goff, sizeof(goff), cudaMemcpyHostToDevice, st));
+    const int rc = smooth_device(c, c->lab.as<double>(), c->goff.as<long long>(), c->staging.as<int>(), 1, n, smooth_region,
+                                 outlier_sd_scale, smooth_sd_scale, trim, c->x.as<double>(), off);
+    if (rc) return rc;
+    CUDA_TRY(c, cudaMemcpyAsync(out, c->x.p, sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(c, cudaStreamSynchronize(st));
+    if (c->profiling) collect_timers(c);
+    return CBS_GPU_OK;
+}
+
+int cbs_gpu_segment(cbs_gpu_ctx* c, const double* x, int32_t n, const cbs_gpu_params* params, const uint64_t* mt_next312,
+                    int32_t cap, int32_t* lengths, double* means, int32_t* n_segments, uint64_t* draws_consumed) {
+    if (!c) return CBS_GPU_ERR_INVALID;
+    if (n < 0 || (n > 0 && !x) || !n_segments) return fail(c, CBS_GPU_ERR_INVALID, "bad arguments");
+    if (cudaSetDevice(c->device) != cudaSuccess) return fail(c, CBS_GPU_ERR_CUDA, "cudaSetDevice failed");
+    cbs_gpu_params p = *params;
+    p.do_smooth = 0;  // cbs::segment does not smooth
+    int rc = validate_params(c, &p);
+    if (rc) return rc;
+    *n_segments = 0;
+    if (draws_consumed) *draws_consumed = 0;
+    if (n == 0) return CBS_GPU_OK;  // cbs::segment on an empty vector returns no segments
+    cudaStream_t st = c->stream;
+    ENSURE(c, c->x, sizeof(double) * (size_t)(n + 1));
+    ENSURE(c, c->flag, sizeof(int));
+    CUDA_TRY(c, cudaMemcpyAsync(c->x.p, x, sizeof(double) * (size_t)n, cudaMemcpyHostToDevice, st));
+    for (int i = 0; i < n; ++i) if (!std::isfinite(x[i])) return fail(c, CBS_GPU_ERR_NONFINITE, "non-finite values reach CBS");
+    std::vector<long long> off = {0, (long long)n};
+    Dev hD;
+    for (int k = 0; k < K_COUNT; ++k) c->kms[k] = 0.0;
+    rc = run_cbs(c, off, nullptr, 1, &p, mt_next312, false, hD);
+    if (rc) return rc;
+    ResultOwner R;
+    memset(&R.pub, 0, sizeof(R.pub));
+    rc = fetch_results(c, hD, 1, false, &R);
+    if (rc) return rc;
+    if (c->profiling) collect_timers(c);
+    *n_segments = (int32_t)R.pub.n_segments;
+    if (draws_consumed) *draws_consumed = R.draws[0];
+    if (R.pub.n_segments > cap) return fail(c, CBS_GPU_ERR_CAPACITY, "output capacity too small");
+    for (int64_t k = 0; k < R.pub.n_segments; ++k) { lengths[k] = R.lengths[k]; means[k] = R.means[k]; }
+    return CBS_GPU_OK;
+}
+
+}  // extern "C"

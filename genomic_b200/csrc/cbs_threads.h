@@ -252,28 +252,42 @@ CBS_HD void count_item_seq(Dev& D, const PermItem& it) {
     t.cnt_exit = hit; t.cnt_nrej = inb;
 }
 
-// MT19937-64 raw stream: commit `d` consumed words into hist, then append `need` raw words
+// MT19937-64 raw stream W[0..) following the chain's cursor: W[w] = hist[w] for w < 312 and
+// W[w] = W[w-156] ^ twist(W[w-312], W[w-311]) beyond (the engine's recurrence).
+// Commit the `commit_d` words consumed from last round's window (hist <- W_prev[d..d+312)),
+// then write this round's window W[0 .. need_len+312).
 CBS_HD void mt_generate_seq(Chain& ch, const uint64_t* prev_arena, uint64_t* cur_arena) {
-    uint64_t st[312];
     const uint64_t d = ch.commit_d;
-    for (int u = 0; u < 312; ++u) {
-        const uint64_t q = d + (uint64_t)u;
-        st[u] = (q < 312) ? ch.hist[q] : prev_arena[ch.prev_off + (long long)(q - 312)];
-    }
-    for (int u = 0; u < 312; ++u) ch.hist[u] = st[u];
-    // st = R[c .. c+312); R[c+312+w] = R[c+156+w] ^ twist(R[c+w], R[c+w+1])
+    if (d) for (int u = 0; u < 312; ++u) ch.hist[u] = prev_arena[ch.prev_off + (long long)d + u];
+    if (ch.need_len == 0) return;
     uint64_t* out = cur_arena + ch.need_off;
-    for (uint64_t w = 0; w < ch.need_len; ++w) {
-        const uint64_t a = (w < 312) ? st[w] : out[w - 312];
-        const uint64_t b = (w + 1 < 312) ? st[w + 1] : out[w + 1 - 312];
-        const uint64_t m = (w + 156 < 312) ? st[w + 156] : out[w + 156 - 312];
-        out[w] = mt_twist(a, b, m);
-    }
+    for (int u = 0; u < 312; ++u) out[u] = ch.hist[u];
+    for (uint64_t w = 312; w < ch.need_len + 312; ++w) out[w] = mt_twist(out[w - 312], out[w - 311], out[w - 156]);
 }
 
-CBS_HD void mt_seed_state(uint64_t seed, uint64_t* st) {
+// the first 312 raw words a freshly seeded std::mt19937_64(seed) will output (untempered)
+CBS_HD void mt_seed_next312(uint64_t seed, uint64_t* next) {
+    uint64_t st[312];
     st[0] = seed;
     for (int k = 1; k < 312; ++k) st[k] = 6364136223846793005ULL * (st[k - 1] ^ (st[k - 1] >> 62)) + (uint64_t)k;
+    for (int k = 0; k < 312; ++k) {
+        const uint64_t a = st[k];
+        const uint64_t b = (k + 1 < 312) ? st[k + 1] : next[0];
+        const uint64_t m = (k + 156 < 312) ? st[k + 156] : next[k + 156 - 312];
+        next[k] = mt_twist(a, b, m);
+    }
+}
+// inverse of mt_temper: recovers the raw word from an engine output
+CBS_HD uint64_t mt_untemper(uint64_t y) {
+    y ^= (y >> 43);
+    y ^= (y << 37) & 0xFFF7EEE000000000ULL;
+    // y ^= (y << 17) & mask : iterate to undo
+    uint64_t z = y;
+    for (int i = 0; i < 4; ++i) z = y ^ ((z << 17) & 0x71D67FFFEDA60000ULL);
+    y = z;
+    z = y;
+    for (int i = 0; i < 3; ++i) z = y ^ ((z >> 29) & 0x5555555555555555ULL);
+    return z;
 }
 
 }  // namespace cbsg

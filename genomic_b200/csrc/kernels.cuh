@@ -1,0 +1,764 @@
+// kernels.cuh -- sm_100a kernels of the CBS hot path.
+//
+//   k_sched      count phase + the single-thread worklist scheduler (cbs_core.h)
+//   k_gen        MT19937-64 raw stream generator, one CTA per chain (replay mode)
+//   k_prep       per pending segment: all-equal test, mean, centring, tss, observed prefix
+//                sums / block extrema, g[L] and fac[L] tables     (CBS.cpp:985-989, :79-97)
+//   k_perm       thread per permutation: Fisher-Yates + prefix sums (CBS.cpp:487-493, :79-97)
+//   k_scan       CTA per permutation: branch-and-bound max-t arc scan (CBS.cpp:99-224)
+//   k_edgeprep   tpermp set-up sums (CBS.cpp:496-522)
+//   k_edgeperm   tpermp permutation loop (CBS.cpp:524-534)
+//   k_means      segment means (CBS.cpp:1014-1022)
+//
+// All floating point that feeds a comparison is plain IEEE double with the reference's
+// operation order; the library is compiled with -fmad=false.
+#pragma once
+#include <cuda_runtime.h>
+
+#include "cbs_threads.h"
+
+namespace cbsg {
+
+#define FULL 0xffffffffu
+
+// ------------------------------------------------------------------------------------
+// small device helpers
+// ------------------------------------------------------------------------------------
+__device__ __forceinline__ double shfl_d(double v, int src) { return __shfl_sync(FULL, v, src); }
+
+__device__ __forceinline__ void atomic_max_pos_double(double* addr, double v) {
+    // non-negative doubles order like their bit patterns
+    atomicMax((unsigned long long*)addr, (unsigned long long)__double_as_longlong(v));
+}
+
+// map a global work index to (item, offset) through an exclusive prefix array
+__device__ __forceinline__ int find_item(const int* prefix, int n_items, int g) {
+    int lo = 0, hi = n_items;  // prefix[lo] <= g < prefix[hi]
+    while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (prefix[mid] <= g) lo = mid; else hi = mid;
+    }
+    return lo;
+}
+
+// ------------------------------------------------------------------------------------
+// k_sched
+// ------------------------------------------------------------------------------------
+__device__ void count_item_warp(Dev* D, const PermItem& it, int lane) {
+    if (it.obs) return;
+    Task& t = D->tasks[it.task];
+    const int* rej = D->rej + t.off_rej;
+    const int P = it.P, base = t.nrej, nrejc = t.nrejc;
+    int running = 0, hit = -1;
+    for (int p0 = 0; p0 < P; p0 += 32) {
+        const int f = (p0 + lane < P) ? rej[p0 + lane] : 0;
+        const unsigned mask = __ballot_sync(FULL, f != 0);
+        const int incl = __popc(mask & (0xffffffffu >> (31 - lane)));
+        const unsigned over = __ballot_sync(FULL, f != 0 && base + running + incl > nrejc);
+        if (over) {
+            const int l = __ffs(over) - 1;
+            hit = p0 + l;
+            running += __popc(mask & (0xffffffffu >> (31 - l)));
+            break;
+        }
+        running += __popc(mask);
+    }
+    if (lane == 0) { t.cnt_exit = hit; t.cnt_nrej = running; }
+}
+
+__global__ void __launch_bounds__(256) k_sched(Dev* D, volatile int* host_done) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (D->done) return;
+    for (int k = warp; k < D->n_items; k += 8) count_item_warp(D, D->items[k], lane);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        Sched S(*D);
+        S.run_round();
+        if (D->done) { __threadfence_system(); *host_done = D->error ? -D->error : 1; }
+    }
+}
+
+// ------------------------------------------------------------------------------------
+// k_gen: one CTA per chain. hist = the next 312 raw words of the chain's engine.  Commit the
+// words consumed from last round's window, then write this round's window: the 312 known
+// words followed by need_len further words of the recurrence (4 barriers per 312 words).
+// ------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(192) k_gen(Dev* D) {
+    __shared__ uint64_t st[312];
+    if (D->done) return;
+    const int par = D->round & 1;
+    for (int g = blockIdx.x; g < D->n_gen; g += gridDim.x) {
+        Chain& ch = D->chains[D->gen_chain[g]];
+        const uint64_t d = ch.commit_d;
+        const uint64_t* prev = D->draws[par ^ 1];
+        const uint64_t need = ch.need_len;
+        __syncthreads();
+        for (int u = threadIdx.x; u < 312; u += blockDim.x) {
+            const uint64_t v = d ? prev[ch.prev_off + (long long)d + u] : ch.hist[u];
+            st[u] = v;
+            if (d) ch.hist[u] = v;
+        }
+        __syncthreads();
+        if (need == 0) continue;
+        uint64_t* out = D->draws[par] + ch.need_off;
+        for (int u = threadIdx.x; u < 312; u += blockDim.x) out[u] = st[u];
+        const int k = threadIdx.x;
+        for (uint64_t w0 = 312; w0 < need + 312; w0 += 312) {
+            uint64_t v = 0;
+            if (k < 156) v = mt_twist(st[k], st[k + 1], st[k + 156]);
+            __syncthreads();
+            if (k < 156) { st[k] = v; if (w0 + k < need + 312) out[w0 + k] = v; }
+            __syncthreads();
+            if (k < 156) { const int kk = k + 156; v = mt_twist(st[kk], st[(kk + 1) % 312], st[kk - 156]); }
+            __syncthreads();
+            if (k < 156) { st[k + 156] = v; if (w0 + 156 + k < need + 312) out[w0 + 156 + k] = v; }
+            __syncthreads();
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------
+// k_prep: one warp per pending segment. Sums are strictly sequential (every lane runs the
+// same dependent chain on shuffled-in values), so results equal the reference bit for bit.
+// ------------------------------------------------------------------------------------
+__device__ void prep_warp(Dev* D, Task& t, int lane) {
+    const long long base = D->unit_off[t.unit] + t.lo;
+    const double* x = D->x + base;
+    double* cur = D->cur + base;
+    const int n = t.n, nb = t.nb;
+    const bool raw = t.raw != 0;
+    double avg = 0.0;
+    if (!raw) {
+        // CBS.cpp:985
+        const double x0 = x[0];
+        bool flat = true;
+        for (int i = lane; i < n; i += 32) if (!(fabs(x[i] - x0) < 1e-12)) flat = false;
+        flat = __all_sync(FULL, flat);
+        if (lane == 0) t.alleq = flat ? 1 : 0;
+        if (flat) return;
+        // CBS.cpp:986 mean, sequential
+        double s = 0.0;
+        for (int b0 = 0; b0 < n; b0 += 32) {
+            const double v = (b0 + lane < n) ? x[b0 + lane] : 0.0;
+            const int cnt = min(32, n - b0);
+#pragma unroll 8
+            for (int k = 0; k < cnt; ++k) s = s + shfl_d(v, k);
+        }
+        avg = s / (double)n;
+    }
+    int* bb = D->bbtab + base;
+    for (int b = lane; b <= nb; b += 32) bb[b] = block_end(n, nb, b);
+    const double rn = (double)n;
+    for (int L = 1 + lane; L < n; L += 32) {
+        const double rr = (double)L;
+        const double prod = rr * (rn - rr);
+        D->factab[base + L] = rn / prod;
+        D->gtab[base + L] = sqrt(prod / rn);
+    }
+    __syncwarp();
+    // CBS.cpp:987-989 + :79-97
+    double* sx = D->arena + t.off_sx;
+    BlockStats bs(D->arena + t.off_bs, nb);
+    double run = 0.0, tss = 0.0, g_lo = 0.0, g_hi = 0.0;
+    int gi_lo = n, gi_hi = n;
+    if (lane == 0) sx[0] = 0.0;
+    for (int b = 1; b <= nb; ++b) {
+        const int first = bb[b - 1] + 1, last = bb[b];
+        double lo = 0.0, hi = 0.0;
+        int ilo = first, ihi = first;
+        for (int c0 = first; c0 <= last; c0 += 32) {
+            const int i = c0 + lane;
+            double v = 0.0;
+            if (i <= last) { v = raw ? x[i - 1] : x[i - 1] - avg; cur[i - 1] = v; }
+            const int cnt = min(32, last - c0 + 1);
+            double mine = 0.0;
+            for (int k = 0; k < cnt; ++k) {
+                const double vk = shfl_d(v, k);
+                run = run + vk;
+                tss = tss + vk * vk;
+                if (k == lane) mine = run;
+                const int idx = c0 + k;
+                if (idx == first) { lo = run; hi = run; }
+                else {
+                    if (run < lo) { lo = run; ilo = idx; }
+                    if (run > hi) { hi = run; ihi = idx; }
+                }
+            }
+            if (i <= last) sx[i] = mine;
+        }
+        if (lane == 0) { bs.bmin()[b - 1] = lo; bs.bmax()[b - 1] = hi; bs.amin()[b - 1] = ilo; bs.amax()[b - 1] = ihi; }
+        if (lo < g_lo) { g_lo = lo; gi_lo = ilo; }
+        if (hi > g_hi) { g_hi = hi; gi_hi = ihi; }
+    }
+    if (lane == 0) {
+        bs.gmin() = g_lo; bs.gmax() = g_hi; bs.gidx()[0] = gi_lo; bs.gidx()[1] = gi_hi;
+        if (!raw) t.tss = tss;
+    }
+}
+
+__global__ void __launch_bounds__(128) k_prep(Dev* D) {
+    if (D->done) return;
+    const int lane = threadIdx.x & 31;
+    const int wpb = blockDim.x >> 5;
+    for (int k = blockIdx.x * wpb + (threadIdx.x >> 5); k < D->n_prep; k += gridDim.x * wpb)
+        prep_warp(D, D->tasks[D->prep_task[k]], lane);
+}
+
+// ------------------------------------------------------------------------------------
+// k_perm
+// ------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) k_perm(Dev* D) {
+    if (D->done) return;
+    __shared__ int s_base;
+    const int total = D->item_prefix[D->n_items];
+    for (;;) {
+        __syncthreads();
+        if (threadIdx.x == 0) s_base = (int)atomicAdd(&D->ctr[0], (unsigned)blockDim.x);
+        __syncthreads();
+        const int g = s_base + threadIdx.x;
+        if (s_base >= total) break;
+        if (g >= total) continue;
+        const int k = find_item(D->item_prefix, D->n_items, g);
+        const PermItem it = D->items[k];
+        if (it.obs) continue;
+        perm_thread(*D, D->tasks[it.task], it.P, g - D->item_prefix[k]);
+    }
+}
+
+// ------------------------------------------------------------------------------------
+// k_scan -- the dominant kernel.
+//
+// One CTA per (segment, permutation).  The reference finds max over arcs (i,j) of
+// fac(L) * (S_j - S_i)^2, L = j - i, by visiting sqrt(n) x sqrt(n) block pairs in order of
+// their corner statistic and pruning with the running maximum (CBS.cpp:119-216).  Here:
+//   pass 1  every thread evaluates corner arcs of block pairs; the best VALID corner gives a
+//           lower bound LB on the answer (it is an arc the reference also evaluates);
+//   pass 2  warps claim block pairs whose upper bound reaches the current level and scan
+//           them.  The scan never computes a statistic: an arc can only beat level M if
+//           |S_j - S_i| > sqrt(M) * g[L], g[L] = sqrt(L(n-L)/n), so the inner loop is one
+//           DADD and one DSETP per arc against per-diagonal thresholds held in registers
+//           (8 diagonals x 8 positions per lane per step).  A hit (rare) re-evaluates the
+//           8x32 unit exactly as fac*s*s and raises the level.
+// The set of arcs considered per block pair is exactly the reference's (its restricted
+// length ranges [lenlo,lenmax] and [n-lenmax,lenhi], CBS.cpp:179-215), so the maximum is the
+// same double; ties for the observed scan follow the reference's visiting order.
+// ------------------------------------------------------------------------------------
+struct ScanSmem {
+    double level;     // prune level (monotone, atomicMax)
+    double sms;       // sqrt(level)*(1-1e-12) (monotone)
+    double found;     // best statistic found (perm mode)
+    // LOC record (observed scan): best arc under the reference's visiting order
+    double r_stat, r_corner;
+    int r_q, r_key, r_i, r_j;
+    int lock;
+    int next_pair;
+    double red[8];
+};
+
+struct Cand {
+    double stat, corner;
+    int q, key, i, j;
+};
+// true if a precedes b: larger statistic, else earlier in the reference's visiting order
+__device__ __forceinline__ bool cand_better(const Cand& a, const Cand& b) {
+    if (a.stat != b.stat) return a.stat > b.stat;
+    if (a.corner != b.corner) return a.corner > b.corner;
+    if (a.q != b.q) return a.q > b.q;
+    if (a.key != b.key) return a.key < b.key;
+    return a.i < b.i;
+}
+
+#define SCAN_PAD_LO 32
+#define SCAN_PAD_HI 48
+// swizzled position of element e (e >= -SCAN_PAD_LO) of the j-block staging buffer
+__device__ __forceinline__ int sb_pos(int e) { const int f = e + SCAN_PAD_LO; return f + (f >> 3); }
+
+struct PairGeo {
+    int ilo, ihi, jlo, jhi, Bi, Bj, D0;
+    int lenlo, lenhi;
+    int bandLo[2], bandHi[2];  // arc-length bands actually scanned (empty if lo > hi)
+    double corner;
+    int q;
+};
+
+__device__ __forceinline__ void pair_from_index(int q, int nb, int& bi, int& bj) {
+    // rows bi = 1..nb, row r (0-based) starts at r*nb - r*(r-1)/2
+    const double t = 2.0 * nb + 1.0;
+    int r = (int)((t - sqrt(t * t - 8.0 * (double)q)) * 0.5);
+    if (r < 0) r = 0;
+    if (r > nb - 1) r = nb - 1;
+    while (r + 1 <= nb - 1 && (long long)(r + 1) * nb - (long long)(r + 1) * r / 2 <= q) ++r;
+    while (r > 0 && (long long)r * nb - (long long)r * (r - 1) / 2 > q) --r;
+    const int off = (int)((long long)r * nb - (long long)r * (r - 1) / 2);
+    bi = r + 1;
+    bj = bi + (q - off);
+}
+
+struct ScanCtx {
+    int n, nb, al0;
+    double rn, half;
+    const int* bb;          // smem
+    const double* bmin; const double* bmax; const int* amin; const int* amax;  // smem
+    const double* sx;       // global, this permutation's prefix sums sx[0..n]
+    const double* gtab; const double* factab;  // global, index by L
+    bool loc;
+    unsigned long long* slots;  // profiling counters or nullptr
+    unsigned long long* arcs;
+};
+
+// corner of a block pair (CBS.cpp:132-155): length of the corner arc and its raw spread
+__device__ __forceinline__ void pair_corner(const ScanCtx& c, int bi, int bj, double& s1, double& s2, int& clen) {
+    s1 = fabs(c.bmax[bj - 1] - c.bmin[bi - 1]);
+    s2 = fabs(c.bmax[bi - 1] - c.bmin[bj - 1]);
+    clen = (s1 > s2) ? abs(c.amax[bj - 1] - c.amin[bi - 1]) : abs(c.amin[bj - 1] - c.amax[bi - 1]);
+}
+
+__device__ __forceinline__ void pair_lengths(const ScanCtx& c, int bi, int bj, int& ilo, int& ihi, int& jlo, int& jhi,
+                                             int& lenlo, int& lenhi) {
+    ilo = c.bb[bi - 1] + 1; ihi = c.bb[bi]; jlo = c.bb[bj - 1] + 1; jhi = c.bb[bj];
+    lenhi = min(jhi - ilo, c.n - c.al0);
+    lenlo = (bi == bj) ? 1 : (jlo - ihi);
+    if (lenlo < c.al0) lenlo = c.al0;
+}
+
+// exact re-evaluation of one 8-diagonal x 32-position unit (slow path)
+__device__ void scan_unit_exact(const ScanCtx& c, const PairGeo& g, const double* sa, const double* sbs, int u0, int dq,
+                                const double* th, int La, int Lb, int side, ScanSmem* sm) {
+    double best = 0.0;
+    Cand cb; cb.stat = -1.0; cb.corner = 0.0; cb.q = 0; cb.key = 0; cb.i = 0; cb.j = 0;
+    for (int u = u0; u < u0 + 32 && u < g.Bi; ++u) {
+        const double a = sa[u];
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+            const int d = dq + r, v = u + d;
+            if (v < 0 || v >= g.Bj) continue;
+            const int L = g.D0 + d;
+            if (L < La || L > Lb) continue;
+            const double s = fabs(sbs[sb_pos(v)] - a);
+            if (!(s > th[r])) continue;
+            const double stat = c.factab[L] * s * s;  // CBS.cpp:191-193
+            if (!c.loc) { if (stat > best) best = stat; }
+            else {
+                Cand x;
+                x.stat = stat; x.corner = g.corner; x.q = g.q;
+                x.key = side ? (0x40000000 + (c.n - L)) : L;  // low side: L ascending; high side: L descending
+                x.i = g.ilo + u; x.j = g.ilo + u + L;
+                if (cb.stat < 0.0 || cand_better(x, cb)) cb = x;
+            }
+        }
+    }
+    if (!c.loc) {
+        if (best > 0.0) {
+            atomic_max_pos_double(&sm->found, best);
+            atomic_max_pos_double(&sm->level, best);
+            atomic_max_pos_double(&sm->sms, sqrt(best) * (1.0 - 1e-12));
+        }
+    } else if (cb.stat >= 0.0) {
+        bool done = false;
+        while (!done) {
+            if (atomicCAS(&sm->lock, 0, 1) == 0) {
+                Cand r;
+                r.stat = sm->r_stat; r.corner = sm->r_corner; r.q = sm->r_q; r.key = sm->r_key; r.i = sm->r_i; r.j = sm->r_j;
+                if (cand_better(cb, r)) {
+                    sm->r_stat = cb.stat; sm->r_corner = cb.corner; sm->r_q = cb.q; sm->r_key = cb.key; sm->r_i = cb.i; sm->r_j = cb.j;
+                }
+                __threadfence_block();
+                atomicExch(&sm->lock, 0);
+                done = true;
+            }
+        }
+        atomic_max_pos_double(&sm->level, cb.stat);
+        atomic_max_pos_double(&sm->sms, sqrt(cb.stat) * (1.0 - 1e-12));
+    }
+}
+
+// scan one arc-length band [La, Lb] of a staged block pair with the whole warp
+__device__ void scan_band(const ScanCtx& c, const PairGeo& g, const double* sa, const double* sbs, int* s_rowpre, int La,
+                          int Lb, int side, ScanSmem* sm, int lane) {
+    // diagonals d = L - D0; 8-aligned diagonal groups q8 (d in [8*q8, 8*q8+7]); 32-aligned u rows
+    const int dLo = La - g.D0, dHi = Lb - g.D0;
+    const int qLo = dLo >> 3, qHi = dHi >> 3;  // arithmetic shift == floor
+    const int nrows = (g.Bi + 31) >> 5;
+    // row r holds groups whose valid u-range [max(0,-(dq+7)), min(Bi-1, Bj-1-dq)] meets [32r, 32r+31]
+    int qa = 0, qb = -1;
+    if (lane < nrows) {
+        // -(dq+7) <= 32r+31  <=>  dq >= -32r-38 ; multiples of 8: q8 >= ceil((-32r-38)/8) = -4r-4
+        qa = max(qLo, -4 * lane - 4);
+        // Bj-1-dq >= 32r  <=>  dq <= Bj-1-32r
+        qb = min(qHi, (g.Bj - 1 - 32 * lane) >> 3);
+    }
+    int cnt = max(0, qb - qa + 1);
+    int incl = cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(FULL, incl, o); if (lane >= o) incl += t; }
+    const int total = __shfl_sync(FULL, incl, 31);
+    __syncwarp();
+    s_rowpre[lane] = incl - cnt;  // exclusive
+    if (lane == 0) s_rowpre[32] = total;
+    if (c.slots && lane == 0) atomicAdd(c.slots, (unsigned long long)total * 256ull);
+    unsigned long long my_arcs = 0;
+    __syncwarp();
+    for (int idx = lane; idx < total; idx += 32) {
+        // row lookup
+        int lo = 0, hi = 32;
+        while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (s_rowpre[mid] <= idx) lo = mid; else hi = mid; }
+        const int r = lo;
+        // row's first group: recompute (cheap) instead of storing
+        const int rqa = max(qLo, -4 * r - 4);
+        const int q8 = rqa + (idx - s_rowpre[r]);
+        const int dq = q8 * 8, u0 = r * 32;
+        if (c.arcs) {
+            for (int k = 0; k < 8; ++k) {
+                const int d = dq + k, L = g.D0 + d;
+                if (L < La || L > Lb) continue;
+                const int a0 = max(u0, max(0, -d)), a1 = min(u0 + 31, min(g.Bi - 1, g.Bj - 1 - d));
+                if (a1 >= a0) my_arcs += (unsigned long long)(a1 - a0 + 1);
+            }
+        }
+        // thresholds for the 8 diagonals of the group
+        const double sms = *((volatile double*)&sm->sms);
+        double th[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const int L = g.D0 + dq + k;
+            const bool in = (L >= La && L <= Lb);
+            th[k] = in ? sms * c.gtab[in ? L : 1] : __longlong_as_double(0x7ff0000000000000LL);
+        }
+        // fast path: 4 steps of 8 positions x 8 diagonals
+        const double* pa = sa + u0;
+        const double* pb = sbs + 9 * ((u0 + dq + SCAN_PAD_LO) >> 3);
+        double w[8], nw[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) w[k] = pb[k];
+        bool flag = false;
+#pragma unroll
+        for (int it = 0; it < 4; ++it) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) nw[k] = pb[9 * (it + 1) + k];
+#pragma unroll
+            for (int s = 0; s < 8; ++s) {
+                const double a = pa[8 * it + s];
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    const double xv = (s + k < 8) ? w[s + k] : nw[s + k - 8];
+                    flag |= fabs(xv - a) > th[k];
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < 8; ++k) w[k] = nw[k];
+        }
+        if (flag) scan_unit_exact(c, g, sa, sbs, u0, dq, th, La, Lb, side, sm);
+    }
+    if (c.arcs && my_arcs) atomicAdd(c.arcs, my_arcs);
+    __syncwarp();
+}
+
+// stage one block pair in this warp's shared memory and scan its bands
+__device__ void scan_pair(const ScanCtx& c, int q, double* sa, double* sbs, int* s_rowpre, ScanSmem* sm, int lane) {
+    int bi, bj;
+    pair_from_index(q, c.nb, bi, bj);
+    PairGeo g;
+    pair_lengths(c, bi, bj, g.ilo, g.ihi, g.jlo, g.jhi, g.lenlo, g.lenhi);
+    g.Bi = g.ihi - g.ilo + 1; g.Bj = g.jhi - g.jlo + 1; g.D0 = g.jlo - g.ilo; g.q = q;
+    double s1, s2; int clen;
+    pair_corner(c, bi, bj, s1, s2, clen);
+    g.corner = 0.0;
+    if (c.loc) g.corner = c.factab[min(max(clen, 1), c.n - 1)] * ((s1 > s2) ? s1 : s2) * ((s1 > s2) ? s1 : s2);
+    // CBS.cpp:179-180, 198-199
+    int lenmax = clen;
+    if (lenmax > c.n - lenmax) lenmax = c.n - lenmax;
+    g.bandLo[0] = 1; g.bandHi[0] = 0; g.bandLo[1] = 1; g.bandHi[1] = 0;
+    if (((double)g.lenlo <= c.half) && (g.lenlo <= lenmax)) { g.bandLo[0] = g.lenlo; g.bandHi[0] = lenmax; }
+    const int lenmax2 = c.n - lenmax;
+    if (((double)g.lenhi >= c.half) && (g.lenhi >= lenmax2)) { g.bandLo[1] = lenmax2; g.bandHi[1] = g.lenhi; }
+    if (g.bandLo[0] > g.bandHi[0] && g.bandLo[1] > g.bandHi[1]) return;
+    // stage: sa[u] = S[ilo+u] (NaN beyond Bi), sbs[sb_pos(v)] = S[jlo+v] (NaN outside [0,Bj))
+    const double qnan = __longlong_as_double(0x7ff8000000000000LL);
+    __syncwarp();
+    const int arows = ((g.Bi + 31) >> 5) << 5;
+    for (int u = lane; u < arows + 8; u += 32) sa[u] = (u < g.Bi) ? c.sx[g.ilo + u] : qnan;
+    // every slot of the swizzled buffer that a unit may touch
+    const int nslots = sb_pos(g.Bj + SCAN_PAD_HI) + 1;
+    for (int sidx = lane; sidx < nslots; sidx += 32) sbs[sidx] = qnan;
+    __syncwarp();
+    for (int v = lane; v < g.Bj; v += 32) sbs[sb_pos(v)] = c.sx[g.jlo + v];
+    __syncwarp();
+    if (g.bandLo[0] <= g.bandHi[0]) scan_band(c, g, sa, sbs, s_rowpre, g.bandLo[0], g.bandHi[0], 0, sm, lane);
+    if (g.bandLo[1] <= g.bandHi[1]) scan_band(c, g, sa, sbs, s_rowpre, g.bandLo[1], g.bandHi[1], 1, sm, lane);
+}
+
+// dynamic shared memory layout helper (host + device)
+struct ScanLayout {
+    int nb_max, B_max, warps;
+    CBS_HD size_t per_warp_doubles() const {
+        const int a = ((B_max + 31) / 32) * 32 + 8;
+        const int f = B_max + SCAN_PAD_HI + SCAN_PAD_LO;
+        const int b = f + (f >> 3) + 2;
+        return (size_t)a + (size_t)b + 20;  // + row prefix (33 ints)
+    }
+    CBS_HD size_t bytes() const {
+        size_t doubles = 2 * (size_t)nb_max + (size_t)warps * per_warp_doubles();
+        size_t ints = 3 * (size_t)nb_max + 8;
+        return sizeof(ScanSmem) + doubles * 8 + ints * 4 + 64;
+    }
+};
+
+__global__ void __launch_bounds__(256) k_scan(Dev* D, ScanLayout lay) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    if (D->done) return;
+    ScanSmem* sm = (ScanSmem*)smem_raw;
+    double* s_bmin = (double*)(smem_raw + ((sizeof(ScanSmem) + 15) & ~(size_t)15));
+    double* s_bmax = s_bmin + lay.nb_max;
+    double* s_warp = s_bmax + lay.nb_max;
+    int* s_amin = (int*)(s_warp + (size_t)lay.warps * lay.per_warp_doubles());
+    int* s_amax = s_amin + lay.nb_max;
+    int* s_bb = s_amax + lay.nb_max;
+    __shared__ int s_g;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int nwarps = blockDim.x >> 5;
+    const int total = D->item_prefix[D->n_items];
+    for (;;) {
+        __syncthreads();
+        if (tid == 0) s_g = (int)atomicAdd(&D->ctr[1], 1u);
+        __syncthreads();
+        const int gidx = s_g;
+        if (gidx >= total) break;
+        const int k = find_item(D->item_prefix, D->n_items, gidx);
+        const PermItem it = D->items[k];
+        Task& t = D->tasks[it.task];
+        if (it.obs && t.alleq) continue;
+        const int p = gidx - D->item_prefix[k];
+        const int n = t.n, nb = t.nb;
+        const long long base = D->unit_off[t.unit] + t.lo;
+        ScanCtx c;
+        c.n = n; c.nb = nb; c.al0 = D->prm.min_width; c.rn = (double)n; c.half = c.rn / 2.0;
+        c.bb = s_bb; c.bmin = s_bmin; c.bmax = s_bmax; c.amin = s_amin; c.amax = s_amax;
+        c.sx = D->arena + t.off_sx + (long long)p * Sched::sx_stride(n);
+        c.gtab = D->gtab + base; c.factab = D->factab + base;
+        c.loc = it.obs == 1;
+        const bool decide = it.obs == 0;
+        c.slots = D->profile ? &D->stat_slots : nullptr;
+        c.arcs = D->profile ? &D->stat_arcs : nullptr;
+        BlockStats bs(D->arena + t.off_bs + (long long)p * Sched::bs_stride(nb), nb);
+        const int* bbg = D->bbtab + base;
+        for (int b = tid; b <= nb; b += blockDim.x) s_bb[b] = bbg[b];
+        for (int b = tid; b < nb; b += blockDim.x) {
+            s_bmin[b] = bs.bmin()[b]; s_bmax[b] = bs.bmax()[b]; s_amin[b] = bs.amin()[b]; s_amax[b] = bs.amax()[b];
+        }
+        const double gmin = bs.gmin(), gmax = bs.gmax();
+        const int gimin = bs.gidx()[0], gimax = bs.gidx()[1];
+        const double spread = gmax - gmin;
+        const double tss0 = t.tss;
+        __syncthreads();
+        double final_best;
+        int fi = min(gimax, gimin), fj = max(gimax, gimin);
+        if (spread <= 0.0) {  // CBS.cpp:102-111
+            final_best = -1.0;
+        } else {
+            // CBS.cpp:113-117 initial candidate: global extrema of the prefix sums
+            const double rj = (double)abs(gimax - gimin);
+            const double init = c.rn / (rj * (c.rn - rj)) * spread * spread;
+            // ---- pass 1: best valid corner -> lower bound ---------------------------------
+            const int npairs = nb * (nb + 1) / 2;
+            double lb = 0.0;
+            for (int q = tid; q < npairs; q += blockDim.x) {
+                int bi, bj; pair_from_index(q, nb, bi, bj);
+                double s1, s2; int clen;
+                pair_corner(c, bi, bj, s1, s2, clen);
+                if (clen >= c.al0 && clen <= n - c.al0) {
+                    const double sm1 = (s1 > s2) ? s1 : s2;
+                    const double v = c.factab[clen] * sm1 * sm1;
+                    if (v > lb) lb = v;
+                }
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) { const double o2 = shfl_d(lb, lane ^ o); if (o2 > lb) lb = o2; }
+            if (lane == 0) sm->red[warp] = lb;
+            __syncthreads();
+            if (tid == 0) {
+                double m = init;
+                for (int w = 0; w < nwarps; ++w) if (sm->red[w] > m) m = sm->red[w];
+                double level = m;
+                if (decide) {
+                    // decision mode: only arcs that could make this permutation reject matter.
+                    // reject <=> thresh <= f(M), f(M) = M/((tss-M)/(n-2)) increasing for M < tss-1e-4
+                    const double thresh = t.ostat * 0.99999;
+                    const double mstar = thresh * tss0 / (c.rn - 2.0 + thresh) * (1.0 - 1e-9);
+                    if (mstar > level && mstar + 0.001 < tss0) {
+                        const double f = mstar / ((tss0 - mstar) / (c.rn - 2.0));
+                        if (f < thresh) level = mstar;
+                    }
+                }
+                sm->level = level;
+                sm->sms = sqrt(level) * (1.0 - 1e-12);
+                sm->found = init;
+                sm->r_stat = init; sm->r_corner = __longlong_as_double(0x7ff0000000000000LL);
+                sm->r_q = 0x7fffffff; sm->r_key = -1; sm->r_i = fi; sm->r_j = fj;
+                sm->lock = 0; sm->next_pair = 0;
+            }
+            __syncthreads();
+            // ---- pass 2: scan surviving block pairs ----------------------------------------
+            double* wbase = s_warp + (size_t)warp * lay.per_warp_doubles();
+            double* sa = wbase;
+            const int asz = ((lay.B_max + 31) / 32) * 32 + 8;
+            double* sbs = sa + asz;
+            const int f0 = lay.B_max + SCAN_PAD_HI + SCAN_PAD_LO;
+            int* s_rowpre = (int*)(sbs + f0 + (f0 >> 3) + 2);
+            for (;;) {
+                int q0 = 0;
+                if (lane == 0) q0 = atomicAdd(&sm->next_pair, 32);
+                q0 = __shfl_sync(FULL, q0, 0);
+                if (q0 >= npairs) break;
+                const int q = q0 + lane;
+                bool alive = false;
+                if (q < npairs) {
+                    int bi, bj; pair_from_index(q, nb, bi, bj);
+                    int ilo, ihi, jlo, jhi, lenlo, lenhi;
+                    pair_lengths(c, bi, bj, ilo, ihi, jlo, jhi, lenlo, lenhi);
+                    double s1, s2; int clen;
+                    pair_corner(c, bi, bj, s1, s2, clen);
+                    const double smx = (s1 > s2) ? s1 : s2;
+                    const double rlo = (double)lenlo, rhi = (double)lenhi;
+                    const double a = rlo * (c.rn - rlo), b2 = rhi * (c.rn - rhi);
+                    const double mn = (b2 < a) ? b2 : a;
+                    // bound = rn/mn*smx^2 >= level  (conservative, division free)
+                    const double level = *((volatile double*)&sm->level);
+                    alive = (c.rn * smx * smx >= level * mn * (1.0 - 1e-12));
+                }
+                unsigned mask = __ballot_sync(FULL, alive);
+                while (mask) {
+                    const int l = __ffs(mask) - 1;
+                    mask &= mask - 1;
+                    scan_pair(c, q0 + l, sa, sbs, s_rowpre, sm, lane);
+                }
+            }
+            __syncthreads();
+            final_best = c.loc ? sm->r_stat : sm->found;
+            if (c.loc) { fi = sm->r_i; fj = sm->r_j; }
+        }
+        if (tid == 0) {
+            double tss = tss0, stat;
+            if (final_best < 0.0) {
+                if (tss <= 0.0001) tss = 1.0;
+                stat = 0.0 / ((tss - 0.0) / (c.rn - 2.0));
+            } else {  // CBS.cpp:221-223
+                if (tss <= final_best + 0.0001) tss = final_best + 1.0;
+                stat = final_best / ((tss - final_best) / (c.rn - 2.0));
+            }
+            if (c.loc) { t.ostat = stat; t.tmaxi = fi; t.tmaxj = fj; }
+            else if (it.obs == 2) { t.ostat = stat; }
+            else D->rej[t.off_rej + p] = (t.ostat * 0.99999 <= stat) ? 1 : 0;  // CBS.cpp:838,863
+            bs.result() = stat;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------
+// edge tests
+// ------------------------------------------------------------------------------------
+__device__ void edgeprep_warp(Dev* D, Task& t, int s, int lane) {
+    const int n1 = t.e_n1[s], n2 = t.e_n2[s], n = n1 + n2;
+    const double* x = D->cur + D->unit_off[t.unit] + t.lo + t.e_off[s];
+    if (n1 == 1 || n2 == 1) { if (lane == 0) { t.e_status[s] = 1; t.e_m1[s] = 0; t.e_nrej[s] = 0; } return; }
+    double sum1 = 0.0, sum2 = 0.0, tss = 0.0;
+    for (int b0 = 0; b0 < n1; b0 += 32) {
+        const double v = (b0 + lane < n1) ? x[b0 + lane] : 0.0;
+        const int cnt = min(32, n1 - b0);
+        for (int k = 0; k < cnt; ++k) { const double vk = shfl_d(v, k); sum1 = sum1 + vk; tss = tss + vk * vk; }
+    }
+    for (int b0 = n1; b0 < n; b0 += 32) {
+        const double v = (b0 + lane < n) ? x[b0 + lane] : 0.0;
+        const int cnt = min(32, n - b0);
+        for (int k = 0; k < cnt; ++k) { const double vk = shfl_d(v, k); sum2 = sum2 + vk; tss = tss + vk * vk; }
+    }
+    if (lane == 0) { t.e_nrej[s] = 0; edgeprep_finish(t, s, sum1, sum2, tss); }
+}
+
+__global__ void __launch_bounds__(128) k_edgeprep(Dev* D) {
+    if (D->done) return;
+    const int lane = threadIdx.x & 31;
+    const int wpb = blockDim.x >> 5;
+    for (int k = blockIdx.x * wpb + (threadIdx.x >> 5); k < 2 * D->n_edgeprep; k += gridDim.x * wpb)
+        edgeprep_warp(D, D->tasks[D->edgeprep_task[k >> 1]], k & 1, lane);
+}
+
+__global__ void __launch_bounds__(128) k_edgeperm(Dev* D) {
+    if (D->done) return;
+    __shared__ int s_base;
+    const int total = D->edge_prefix[D->n_edge];
+    for (;;) {
+        __syncthreads();
+        if (threadIdx.x == 0) s_base = (int)atomicAdd(&D->ctr[2], (unsigned)blockDim.x);
+        __syncthreads();
+        const int g = s_base + threadIdx.x;
+        if (s_base >= total) break;
+        if (g >= total) continue;
+        const int k = find_item(D->edge_prefix, D->n_edge, g);
+        const EdgeItem e = D->edges[k];
+        Task& t = D->tasks[e.task];
+        const int th = g - D->edge_prefix[k];
+        const int r = e.sparse ? edge_sparse_thread(*D, t, e, th) : edge_general_thread(*D, t, e, th);
+        if (r) atomicAdd(&t.e_nrej[e.side], r);
+    }
+}
+
+// ------------------------------------------------------------------------------------
+// k_means: sequential sum of the (uncentred) values of each final segment
+// ------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) k_means(const Dev* D, double* means) {
+    const int lane = threadIdx.x & 31;
+    const int wpb = blockDim.x >> 5;
+    for (int k = blockIdx.x * wpb + (threadIdx.x >> 5); k < D->n_segs; k += gridDim.x * wpb) {
+        const SegRec sg = D->segs[k];
+        const double* x = D->x + D->unit_off[sg.unit] + sg.lo;
+        const int n = sg.hi - sg.lo;
+        double s = 0.0;
+        for (int b0 = 0; b0 < n; b0 += 32) {
+            const double v = (b0 + lane < n) ? x[b0 + lane] : 0.0;
+            const int cnt = min(32, n - b0);
+            for (int kk = 0; kk < cnt; ++kk) s = s + shfl_d(v, kk);
+        }
+        if (lane == 0) means[k] = s / (double)n;
+    }
+}
+
+// FP64 issue-rate microbenchmark with the scan kernel's instruction mix: independent
+// DADD + DSETP pairs, 8 accumulators per thread
+__global__ void __launch_bounds__(256) k_fp64_peak(double* out, int iters, double step) {
+    double a[8], th[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { a[k] = (double)(threadIdx.x + k) * 1e-3; th[k] = 1e300 + k; }
+    bool flag = false;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) { a[k] = a[k] + step; flag |= fabs(a[k]) > th[k]; }
+        }
+    }
+    double s = flag ? 1.0 : 0.0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) s += a[k];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
+__global__ void k_widen_f32(const float* in, double* out, long long n) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+        out[i] = (double)in[i];
+}
+
+__global__ void k_init_chains(Dev* D, const uint64_t* seed_state /* next 312 raw words */) {
+    const int chain = D->prm.chain;
+    for (int c = blockIdx.x; c < D->n_chains; c += gridDim.x) {
+        Chain& ch = D->chains[c];
+        for (int u = threadIdx.x; u < 312; u += blockDim.x) ch.hist[u] = seed_state[u];
+        if (threadIdx.x == 0) {
+            ch.top = -1; ch.unit_cur = -1;
+            ch.unit_next = chain ? 0 : c; ch.unit_last = chain ? D->n_units : c + 1;
+            ch.cursor = 0; ch.unit_cursor0 = 0; ch.commit_d = 0;
+            ch.prev_off = -1; ch.prev_len = 0; ch.need_off = -1; ch.need_len = 0;
+        }
+    }
+}
+
+}  // namespace cbsg

@@ -1,0 +1,159 @@
+/* cbs_gpu.h -- C ABI of libcbs_cuda.so: the B200 (sm_100a) implementation of the CBS +
+ * outlier-smoothing hot path of djhshih/genomic (`cna segment`).
+ *
+ * The reference has no FFI layer; its boundary for this path is the C++ free-function
+ * surface of lib/cbs that src/cna_segment.hpp:140-141 and tests/cbs_test.cpp call.  Each entry
+ * point below names the reference interface it replaces (paths relative to the reference
+ * root).  Plain pointers and sizes only; no C++ types, no exceptions cross this boundary:
+ * every call returns a status code and cbs_gpu_last_error() gives the text.
+ * The header-only C++ shim genomic_b200/host/cbs_gpu.hpp wraps these with the reference's
+ * exact signatures (namespace cbs_gpu) and rethrows std::invalid_argument / runtime_error.
+ */
+#ifndef CBS_GPU_H
+#define CBS_GPU_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CBS_GPU_OK 0
+#define CBS_GPU_ERR_INVALID 1      /* what the reference reports as std::invalid_argument */
+#define CBS_GPU_ERR_CUDA 2
+#define CBS_GPU_ERR_OOM 3
+#define CBS_GPU_ERR_CAPACITY 4     /* an internal table overflowed (message says which knob) */
+#define CBS_GPU_ERR_UNSUPPORTED 5  /* argument combination not implemented on the GPU path */
+#define CBS_GPU_ERR_NONFINITE 6    /* non-finite value reached CBS */
+#define CBS_GPU_ERR_OVERFLOW 7     /* reference: std::overflow_error from boost quantile (trim == 0) */
+
+#define CBS_GPU_RNG_MT19937_64 0   /* bit-exact replay of std::mt19937_64 + generate_canonical */
+#define CBS_GPU_RNG_PHILOX 1       /* Philox4x32-10 counter mode, keyed per (seed, unit, segment) */
+
+#define CBS_GPU_F32 0
+#define CBS_GPU_F64 1
+#define CBS_GPU_HOST 0
+#define CBS_GPU_DEVICE 1
+
+typedef struct cbs_gpu_ctx cbs_gpu_ctx;
+
+/* One POD mirroring 1:1 the arguments of cbs::segment (lib/cbs/CBS.hpp:100-113) and cbs::smooth
+ * (lib/cbs/smooth.hpp:8-13), i.e. the options of `cna segment` (src/cna_segment.hpp:67-79). */
+typedef struct cbs_gpu_params {
+    double alpha;
+    int32_t nperm;
+    int32_t hybrid;
+    int32_t min_width;
+    int32_t kmax;
+    int32_t nmin;
+    double eta; /* accepted, unused -- as in the reference */
+    double tol;
+    int32_t ibin;
+    int32_t undo_prune;
+    double undo_prune_cutoff;
+    int32_t do_smooth;
+    int32_t smooth_region;
+    double outlier_sd_scale;
+    double smooth_sd_scale;
+    double trim;
+    int32_t rng_mode; /* CBS_GPU_RNG_* */
+    int32_t chain;    /* MT only. 1: ONE stream shared serially by all units, exactly what
+                         `cna segment` does (cna_segment.hpp:129); 0: a fresh engine seeded with
+                         `seed` per unit (what tests/cbs_test.cpp does per call) -- units independent */
+    uint64_t seed;
+    int32_t first_batch;   /* scheduling knobs, 0 = default; never change results */
+    int32_t max_batch;
+    int32_t record_splits; /* keep one record per split decision (parity diagnostics) */
+    int32_t reserved;
+} cbs_gpu_params;
+
+/* CLI defaults of `cna segment` (src/cna_segment.hpp:67-79): alpha .01, nperm 200, min_width 2,
+ * kmax 25, nmin 200, eta .05, tol 1e-6, hybrid 0, smoothing on (10, 4.0, 2.0, .025), MT seed 1, chain 1 */
+void cbs_gpu_default_params(cbs_gpu_params* p);
+
+/* One record per call of the reference's fndcpt (CBS.cpp:830-892) */
+typedef struct cbs_gpu_split {
+    int32_t unit, lo, hi;       /* segment tested, [lo,hi) in markers of the unit */
+    double ostat;               /* observed max-t statistic (ChangePointResult::ostat) */
+    int32_t iseg0, iseg1;       /* ChangePointResult::iseg (0-based) */
+    int32_t ncpt, icpt0, icpt1; /* ChangePointResult::ncpt / icpt */
+    int32_t perms_run, nrej, exit_code, called;
+    int32_t e_nrej0, e_nrej1, e_status0, e_status1;
+} cbs_gpu_split;
+
+/* Library-allocated result of a batched call; release with cbs_gpu_result_free. */
+typedef struct cbs_gpu_result {
+    int32_t n_units;
+    int64_t n_segments;
+    const int64_t* seg_offsets;     /* [n_units+1] into lengths/means */
+    const int32_t* lengths;         /* SegmentationResult::lengths, concatenated */
+    const double* means;            /* SegmentationResult::means, concatenated */
+    const uint64_t* draws_consumed; /* [n_units], uniforms taken from the engine (MT mode) */
+    int64_t n_splits;
+    const cbs_gpu_split* splits;    /* only with record_splits */
+    int32_t rounds;                 /* scheduler rounds executed */
+    uint64_t perms_run;             /* max-t permutations actually evaluated */
+    uint64_t kernel_launches;       /* kernels launched by this call */
+    double ms_h2d, ms_smooth, ms_segment, ms_d2h; /* CUDA-event timings on the call's stream */
+} cbs_gpu_result;
+
+/* ---- context -----------------------------------------------------------------------
+ * One context drives ONE device (the process-per-GPU model); device_ids[0] is used, ndev must
+ * be 1.  A context is not thread-safe. */
+int cbs_gpu_create(const int* device_ids, int ndev, cbs_gpu_ctx** out);
+void cbs_gpu_destroy(cbs_gpu_ctx* ctx);
+const char* cbs_gpu_last_error(const cbs_gpu_ctx* ctx);
+/* launch the round kernels on this CUDA stream (cudaStream_t) instead of the context's own */
+int cbs_gpu_set_stream(cbs_gpu_ctx* ctx, void* cuda_stream);
+
+/* ---- batched entry: replaces the loop body of Segment::segment_raw ------------------
+ * (src/cna_segment.hpp:132-157): for every unit (one chromosome of one sample):
+ *   x = widen(values[unit]);  if do_smooth: x = cbs::smooth(x, const label);  cbs::segment(x, ...)
+ * values: all units end to end, float32 or float64, in host or device memory;
+ * unit_offsets: host, [n_units+1]; unit_ids: host, global ids used for Philox keys (NULL = index).
+ * Empty units yield zero segments (cna_segment.hpp:138). */
+int cbs_gpu_segment_batch(cbs_gpu_ctx* ctx, const void* values, int dtype, int memspace, const int64_t* unit_offsets,
+                          const uint64_t* unit_ids, int32_t n_units, const cbs_gpu_params* params,
+                          cbs_gpu_result** out);
+void cbs_gpu_result_free(cbs_gpu_result* r);
+
+/* ---- single-call surface -------------------------------------------------------------
+ * cbs::smooth (lib/cbs/smooth.hpp:8-13, smooth.cpp:119-153): values/chrom/out host arrays of n. */
+int cbs_gpu_smooth(cbs_gpu_ctx* ctx, const double* values, const int32_t* chrom, int64_t n, int32_t smooth_region,
+                   double outlier_sd_scale, double smooth_sd_scale, double trim, double* out);
+
+/* cbs::segment (lib/cbs/CBS.hpp:100-113, CBS.cpp:959-1024) on one vector.
+ * mt_next312 (MT mode, may be NULL): the NEXT 312 raw (untempered) words of the caller's
+ * std::mt19937_64, i.e. the engine state in the form the device generator continues from;
+ * NULL = engine freshly seeded with params->seed.  *draws_consumed tells the caller how far to
+ * discard() its engine afterwards.  Returns CBS_GPU_ERR_CAPACITY if cap is too small
+ * (*n_segments then holds the needed size). */
+int cbs_gpu_segment(cbs_gpu_ctx* ctx, const double* x, int32_t n, const cbs_gpu_params* params,
+                    const uint64_t* mt_next312, int32_t cap, int32_t* lengths, double* means, int32_t* n_segments,
+                    uint64_t* draws_consumed);
+
+/* cbs::tmaxo (CBS.hpp:32, CBS.cpp:378-381): max-t statistic and 0-based arc of x as given
+ * (no centring), with tss supplied by the caller. */
+int cbs_gpu_tmaxo(cbs_gpu_ctx* ctx, const double* x, int32_t n, double tss, int32_t al0, int32_t ibin,
+                  double* statistic, int32_t* start, int32_t* end);
+/* cbs::tmaxp (CBS.hpp:33, CBS.cpp:383-385) for `count` vectors of length n laid end to end */
+int cbs_gpu_tmaxp(cbs_gpu_ctx* ctx, const double* px, int32_t n, int32_t count, double tss, int32_t al0, int32_t ibin,
+                  double* statistics);
+
+/* ---- device info / peak measurement helpers (used by bench.py) -------------------------
+ * Measured FP64 add+compare issue rate of this device with the library's own microbenchmark:
+ * returns 1e12 double-precision pipe instructions per second. */
+int cbs_gpu_measure_fp64(cbs_gpu_ctx* ctx, double* tera_inst_per_s);
+/* timing (CUDA events) of the kernels of the last batched call, ms summed per kernel:
+ * order: sched, gen, prep, perm, scan, edgeprep, edgeperm, means, smooth */
+int cbs_gpu_last_kernel_ms(cbs_gpu_ctx* ctx, double* ms9);
+/* when nonzero, every round is bracketed by CUDA events per kernel (slower; for bench.py) */
+int cbs_gpu_set_profiling(cbs_gpu_ctx* ctx, int on);
+/* scan-kernel work of the last batched call (needs profiling on): arcs = real (i,j) pairs examined
+ * by the inner loop, slots = compare slots issued (arcs + padding of partially filled units) */
+int cbs_gpu_last_arc_evals(cbs_gpu_ctx* ctx, uint64_t* arcs, uint64_t* slots);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -79,7 +79,7 @@ extern "C" int64_t emul_segment_units(const double* values, const int64_t* unit_
         ch.top = -1; ch.unit_cur = -1;
         ch.unit_next = chain ? 0 : c; ch.unit_last = chain ? n_units : c + 1;
         ch.need_off = -1; ch.prev_off = -1;
-        mt_seed_state(seed, ch.hist);
+        mt_seed_next312(seed, ch.hist);
     }
     D.chains = chains.data();
     D.max_live = max_live;

@@ -1,0 +1,223 @@
+"""-m gpu: the CUDA path (through the C ABI, genomic_b200.Context) against the oracle on the same
+seeded inputs.  Integer outputs (segment counts, lengths = breakpoints, arc locations, draws
+consumed) must be identical; in MT replay mode the floating point outputs are bit-identical too
+(the device sums are strictly sequential and no FMA is contracted); the north star asks 1e-9."""
+import numpy as np
+import pytest
+
+from helpers import f32, make_unit, pack
+from oracle.pyoracle import SegParams
+import genomic_b200
+from genomic_b200 import Params, RNG_MT19937_64, RNG_PHILOX
+
+pytestmark = pytest.mark.gpu
+RTOL = 1e-9  # north-star tolerance for means and t statistics
+
+
+def gparams(p: SegParams, **kw) -> Params:
+    return Params(alpha=p.alpha, nperm=p.nperm, hybrid=p.hybrid, min_width=p.min_width, kmax=p.kmax, nmin=p.nmin,
+                  eta=p.eta, tol=p.tol, do_smooth=p.do_smooth, smooth_region=p.smooth_region,
+                  outlier_sd_scale=p.outlier_sd_scale, smooth_sd_scale=p.smooth_sd_scale, trim=p.trim,
+                  rng_mode=RNG_PHILOX if p.rng_kind else RNG_MT19937_64, chain=p.chain, seed=p.seed, **kw)
+
+
+def check_batch(ctx, oracle, vals, off, p: SegParams, unit_ids=None, **kw):
+    lab = np.ones(len(off) - 1, np.int32)
+    want = oracle.segment_units(vals, off, lab, p, unit_ids=unit_ids)
+    got = ctx.segment_batch(vals, off, gparams(p, **kw), unit_ids=unit_ids)
+    assert np.array_equal(got.seg_count, want["seg_count"])
+    assert np.array_equal(got.lengths, want["lengths"])
+    assert np.allclose(got.means, want["means"], rtol=RTOL, atol=0)
+    if p.rng_kind == 0:
+        assert np.array_equal(got.means, want["means"])  # bit-exact in replay mode
+        assert np.array_equal(got.draws, want["draws"])
+    return got, want
+
+
+def test_tmaxo_kat_case1(ctx):
+    # tests/cbs_test.cpp:154-177 (inputs literal in tests/cbs_generate.R:90-92)
+    x = np.array([0.0] * 20 + [1.5] * 20 + [0.0] * 20)
+    tss = float((x * x).sum() - x.sum() ** 2 / len(x))
+    stat, s, e = ctx.tmaxo(x, tss, 2, False)
+    assert (s, e) == (0, 58)
+    assert stat == 27000.0
+
+
+def test_tmaxo_matches_oracle(ctx, oracle):
+    rng = np.random.default_rng(11)
+    for trial in range(120):
+        n = int(rng.integers(4, 4000))
+        x = make_unit(rng, n, trial % 5)
+        xc = x - x.mean()
+        tss = float((xc * xc).sum())
+        for al0 in (2, 3, 5):
+            if n < 2 * al0:
+                continue
+            assert ctx.tmaxo(xc, tss, al0) == oracle.tmaxo(xc, tss, al0), (trial, n, al0)
+
+
+def test_tmaxo_large(ctx, oracle):
+    rng = np.random.default_rng(12)
+    for n in (20000, 147726):
+        x = f32(rng.normal(0, 0.2, n))
+        xc = x - x.mean()
+        tss = float((xc * xc).sum())
+        assert ctx.tmaxo(xc, tss, 2) == oracle.tmaxo(xc, tss, 2)
+        x[n // 3: n // 2] += 0.4
+        xc = x - x.mean()
+        tss = float((xc * xc).sum())
+        assert ctx.tmaxo(xc, tss, 2) == oracle.tmaxo(xc, tss, 2)
+
+
+def test_tmaxp_matches_oracle(ctx, oracle):
+    rng = np.random.default_rng(13)
+    for n in (4, 7, 49, 50, 51, 200, 1000, 5000):
+        m = np.stack([f32(rng.normal(0, 0.2, n)) for _ in range(40)])
+        m -= m.mean(axis=1, keepdims=True)
+        tss = float((m[0] * m[0]).sum())
+        got = ctx.tmaxp(m, tss, 2)
+        want = np.array([oracle.tmaxp(r, tss, 2) for r in m])
+        assert np.array_equal(got, want), n
+
+
+@pytest.mark.parametrize("mode", ["mt_chain", "mt_unit", "philox"])
+def test_segment_batch_small_units(ctx, oracle, mode):
+    rng = np.random.default_rng({"mt_chain": 1, "mt_unit": 2, "philox": 3}[mode])
+    for trial in range(12):
+        units = [make_unit(rng, int(rng.integers(1, 1500)), int(rng.integers(0, 5))) for _ in range(int(rng.integers(1, 7)))]
+        if trial % 4 == 0:
+            units.insert(1, np.zeros(0))  # empty chromosome is skipped (cna_segment.hpp:138)
+        vals, off = pack(units)
+        p = SegParams(nperm=int(rng.choice([50, 200, 1000])), alpha=float(rng.choice([0.01, 0.05])),
+                      min_width=int(rng.choice([2, 3])), do_smooth=False, rng_kind=1 if mode == "philox" else 0,
+                      chain=(mode == "mt_chain"), seed=int(rng.integers(1, 100)))
+        check_batch(ctx, oracle, vals, off, p, first_batch=int(rng.choice([16, 64, 256])), max_batch=int(rng.choice([256, 2048])))
+
+
+def test_split_log_matches(ctx, oracle):
+    rng = np.random.default_rng(21)
+    units = [make_unit(rng, 900, k) for k in (0, 1, 1, 3)]
+    vals, off = pack(units)
+    p = SegParams(nperm=500, alpha=0.01, do_smooth=False, chain=True, seed=1)
+    want = oracle.segment_units(vals, off, np.ones(4, np.int32), p, want_log=True)
+    got = ctx.segment_batch(vals, off, gparams(p, record_splits=True))
+    assert len(got.splits) == len(want["log"])
+    for g, (u, w) in zip(got.splits, want["log"]):
+        assert (g["unit"], g["lo"], g["hi"], g["called"], g["ncpt"]) == (u, w.lo, w.hi, w.called, w.ncpt)
+        assert g["ostat"] == w.ostat  # t statistic, bit-exact (tolerance allowed: 1e-9)
+        if w.called:
+            assert (g["iseg0"], g["iseg1"], g["perms_run"], g["exit_code"]) == (w.iseg0, w.iseg1, w.perms_run, w.exit_code)
+            if w.ncpt >= 1:
+                assert g["icpt0"] == w.icpt0
+            if w.ncpt == 2:
+                assert g["icpt1"] == w.icpt1
+
+
+def test_edge_tests_large_m1(ctx, oracle):
+    # weak shifts in the middle: tpermp runs with large m1 (general edge kernel), CBS.cpp:495-536
+    rng = np.random.default_rng(31)
+    for trial in range(8):
+        n = int(rng.integers(300, 1500))
+        x = rng.normal(0, 0.2, n)
+        a = int(rng.integers(n // 5, n // 2))
+        b = int(rng.integers(a + 70, n - 70))
+        x[a:b] += float(rng.choice([0.08, 0.1, 0.12, 0.15]))
+        vals, off = pack([f32(x)])
+        for mode in range(3):
+            p = SegParams(nperm=300, alpha=0.05, do_smooth=False, rng_kind=1 if mode == 2 else 0, chain=(mode == 0), seed=3)
+            check_batch(ctx, oracle, vals, off, p, first_batch=32, max_batch=128)
+
+
+def test_smooth_matches_oracle(ctx, oracle):
+    rng = np.random.default_rng(41)
+    for trial in range(40):
+        n = int(rng.integers(0, 6000))
+        x = rng.normal(0, 0.2, n)
+        for i in (rng.integers(0, max(n, 1), max(1, n // 50)) if n else []):
+            x[i] += rng.choice([-1, 1]) * (3 + abs(rng.normal()))
+        if trial % 3 == 0 and n:
+            for i in rng.integers(0, n, 3):
+                x[i] = rng.choice([np.nan, np.inf, -np.inf])
+        chrom = np.sort(rng.integers(1, 4, n)).astype(np.int32) if trial % 2 else np.ones(n, np.int32)
+        reg = int(rng.choice([0, 1, 2, 10]))
+        trim = float(rng.choice([0.025, 0.01, 0.1, 0.49]))
+        got = ctx.smooth(x, chrom, reg, 4.0, 2.0, trim)
+        want = oracle.smooth(x, chrom, reg, 4.0, 2.0, trim)
+        assert np.array_equal(got, want, equal_nan=True), (trial, n, reg, trim)
+        if n > 200 and trial % 3:
+            assert (got != x).sum() > 0  # the replacement branch fires on injected outliers
+
+
+def test_smooth_errors(ctx):
+    x = np.arange(10.0)
+    lab = np.ones(10, np.int32)
+    with pytest.raises(ValueError):
+        ctx.smooth(x, lab, -1)  # smooth.cpp:126
+    with pytest.raises(ValueError):
+        ctx.smooth(x, lab[:5])  # smooth.cpp:125
+    with pytest.raises(ValueError):
+        ctx.smooth(x, lab, 10, 4.0, 2.0, -0.1)  # smooth.cpp:16-18
+    ctx.smooth(x, lab, 10, 4.0, 2.0, 0.7)  # reference: n_keep <= 0 returns before validating trim
+
+
+def test_smooth_plus_segment_cohort(ctx, oracle):
+    # config 3 shape at 1/100 scale: smoothing + CBS on units with injected outliers
+    from genomic_b200 import synth
+    vals, off, lab, ids = synth.cohort([0, 1], scale=0.01, outliers=True)
+    for mode in range(3):
+        p = SegParams(nperm=1000, alpha=0.01, do_smooth=True, rng_kind=1 if mode == 2 else 0, chain=(mode == 0), seed=1)
+        want = oracle.segment_units(vals.astype(np.float64), off, lab, p, unit_ids=ids)
+        got = ctx.segment_batch(vals, off, gparams(p), unit_ids=ids)  # float32 in, widened on device
+        assert np.array_equal(got.seg_count, want["seg_count"])
+        assert np.array_equal(got.lengths, want["lengths"])
+        assert np.array_equal(got.means, want["means"])
+
+
+def test_golden_cli_fixture(ctx):
+    # tests/cna_test.cpp:258-270: `cna segment` on segment_cli_case1_input.cn, byte-identical .seg
+    import os
+    from cnio import cohort_from_cn, seg_text
+    here = os.path.dirname(os.path.abspath(__file__))
+    names, positions, _, values, off, lab, units = cohort_from_cn(os.path.join(here, "golden", "segment_cli_case1_input.cn"))
+    got = ctx.segment_batch(values.astype(np.float32), off, Params())  # CLI defaults, MT seed 1, chain
+    txt = seg_text(names, positions, units, got.seg_count, got.lengths, got.means)
+    assert txt == open(os.path.join(here, "golden", "segment_cli_case1_expected.seg")).read()
+
+
+def test_nonfinite_rejected(ctx):
+    x = np.array([0.1, np.nan, -0.2, 0.3, 0.0, 0.5])
+    with pytest.raises(genomic_b200.CbsGpuError):
+        ctx.segment_batch(x, np.array([0, 6]), Params(do_smooth=False))
+
+
+def test_segment_single_call_with_engine_state(ctx, oracle):
+    # cbs::segment with a caller-owned engine that has already been used (rng is in/out)
+    import ctypes as C
+    rng = np.random.default_rng(51)
+    x = make_unit(rng, 700, 1)
+    eng = oracle.rng_mt(9)
+    oracle.lib.orc_rng_discard(C.byref(eng), 1234)
+    # next 312 raw words of that engine
+    probe = oracle.rng_mt(9)
+    oracle.lib.orc_rng_discard(C.byref(probe), 1234)
+    outs = np.array([oracle.lib.orc_rng_u64(C.byref(probe)) for _ in range(312)], dtype=np.uint64)
+
+    def untemper(y):
+        y = int(y)
+        M = (1 << 64) - 1
+        y ^= y >> 43
+        y ^= (y << 37) & 0xFFF7EEE000000000 & M
+        z = y
+        for _ in range(4):
+            z = y ^ ((z << 17) & 0x71D67FFFEDA60000 & M)
+        y = z
+        z = y
+        for _ in range(3):
+            z = y ^ ((z >> 29) & 0x5555555555555555)
+        return z
+    nxt = np.array([untemper(v) for v in outs], dtype=np.uint64)
+    p = SegParams(nperm=500, alpha=0.01, do_smooth=False, seed=9)
+    wl, wm = oracle.segment(x, p, eng)
+    gl, gm, draws = ctx.segment(x, gparams(p), mt_next312=nxt)
+    assert np.array_equal(gl, wl) and np.array_equal(gm, wm)
+    assert draws == eng.draws - 1234
