@@ -260,13 +260,14 @@ struct Dev {
     unsigned ctr[8];   // work-stealing counters (reset every round)
     // ---- status -----------------------------------------------------------------------
     int done;
+    int stall;  // consecutive rounds with live tasks but no planned work
     int error;  // 0 ok; see cbs_gpu.h status codes
     unsigned long long stat_perms, stat_rounds_active;
     int profile;                            // count scan work (bench / roofline)
     unsigned long long stat_slots, stat_arcs;  // arc slots issued by the scan fast path / of them real arcs
 };
 
-enum { ERR_TASK_CAP = 101, ERR_SEG_CAP = 102, ERR_ARENA = 103, ERR_SPLIT_CAP = 104, ERR_INTERNAL = 105 };
+enum { ERR_TASK_CAP = 101, ERR_SEG_CAP = 102, ERR_ARENA = 103, ERR_SPLIT_CAP = 104, ERR_INTERNAL = 105, ERR_STALL = 106 };
 
 // ------------------------------------------------------------------------------------
 // Scheduler (runs in ONE thread per round; plain sequential C++ so that the very same
@@ -428,7 +429,7 @@ struct Sched {
         if (want > fit) want = (int)fit;
         const long long need = per * want;
         const long long dneed = (p.rng_mode == RNG_MT) ? (long long)want * t.n : 0;
-        if (arena_used + need > D.arena_cap || rej_used + want > D.rej_cap || draws_used + dneed + 312 > D.draws_cap) {
+        if (arena_used + need > D.arena_cap || rej_used + want > D.rej_cap || (p.rng_mode == RNG_MT && draws_used + dneed + 312 > D.draws_cap)) {
             t.deferred = 1;
             return false;
         }
@@ -491,7 +492,7 @@ struct Sched {
             aneed = cols * n12;
         }
         const long long dneed = (p.rng_mode == RNG_MT) ? (long long)e.P * m1 : 0;
-        if (arena_used + aneed > D.arena_cap || draws_used + dneed + 312 > D.draws_cap) { t.deferred = 1; return false; }
+        if (arena_used + aneed > D.arena_cap || (p.rng_mode == RNG_MT && draws_used + dneed + 312 > D.draws_cap)) { t.deferred = 1; return false; }
         if (aneed) { e.off_scratch = arena_used; arena_used += aneed; }
         if (p.rng_mode == RNG_MT) {
             Chain* ch = chain_of(t);
@@ -700,8 +701,9 @@ struct Sched {
             const bool more = mt ? (D.units_started < D.n_chains) : (D.units_started < D.n_units);
             if (!more) D.done = 1;
         }
+        if (D.n_items || D.n_edge || D.n_edgeprep || D.n_prep) { D.stat_rounds_active++; D.stall = 0; }
+        else if (n_out > 0 && ++D.stall > 16) D.error = ERR_STALL;  // a livelock must not spin forever
         if (D.error) D.done = 1;
-        if (D.n_items || D.n_edge || D.n_edgeprep) D.stat_rounds_active++;
     }
 };
 

@@ -362,6 +362,7 @@ int run_cbs(cbs_gpu_ctx* c, const std::vector<long long>& off, const uint64_t* u
         // the largest block of any segment length <= Nmax: ceil(n/nb)+1 is increasing in n for n >= 50
         const int nbm = block_count((int)std::max<long long>(Nmax, 1));
         bmax = (int)((Nmax + nbm - 1) / nbm) + 2;
+        bmax = std::max(bmax, (int)std::sqrt((double)Nmax) + 4);
         bmax = std::max(bmax, 50);
         lay.B_max = bmax;
     }
@@ -378,6 +379,7 @@ int run_cbs(cbs_gpu_ctx* c, const std::vector<long long>& off, const uint64_t* u
     // ---- rounds -------------------------------------------------------------------------------
     *c->h_done = 0;
     const int G = 8;  // rounds per group
+    const bool debug = env_ll("CBS_GPU_DEBUG", 0) != 0;
     int groups_in_flight = 0, rounds = 0;
     int gi = 0;
     for (;;) {
@@ -398,6 +400,13 @@ int run_cbs(cbs_gpu_ctx* c, const std::vector<long long>& off, const uint64_t* u
             CUDA_TRY(c, cudaEventSynchronize(c->grp[gi]));  // the older group
             --groups_in_flight;
             if (*(volatile int*)c->h_done != 0) break;
+            if (debug) {
+                Dev snap;
+                cudaMemcpy(&snap, dD, sizeof(Dev), cudaMemcpyDeviceToHost);  // synchronises: debugging only
+                fprintf(stderr, "[cbs_gpu] enq=%d round=%d live=%d items=%d perms=%d prep=%d edgeprep=%d edge=%d gen=%d segs=%d perms_done=%llu err=%d\n",
+                        rounds, snap.round, snap.n_active[snap.cur_list], snap.n_items, snap.item_prefix ? -1 : 0, snap.n_prep,
+                        snap.n_edgeprep, snap.n_edge, snap.n_gen, snap.n_segs, snap.stat_perms, snap.error);
+            }
         }
         if (rounds > 50000000) return fail(c, CBS_GPU_ERR_CUDA, "scheduler did not terminate");
     }
@@ -409,6 +418,7 @@ int run_cbs(cbs_gpu_ctx* c, const std::vector<long long>& off, const uint64_t* u
         case ERR_TASK_CAP: return fail(c, CBS_GPU_ERR_CAPACITY, "pending-segment pool exhausted (raise CBS_GPU_TASK_CAP)");
         case ERR_SEG_CAP: return fail(c, CBS_GPU_ERR_CAPACITY, "segment table exhausted (raise CBS_GPU_SEG_CAP)");
         case ERR_SPLIT_CAP: return fail(c, CBS_GPU_ERR_CAPACITY, "split log exhausted");
+        case ERR_STALL: return fail(c, CBS_GPU_ERR_CUDA, "scheduler stalled: live segments but no work could be planned");
         case ERR_ARENA: return fail(c, CBS_GPU_ERR_OOM, "permutation arena too small for one segment (raise CBS_GPU_ARENA_MB)");
         default: return fail(c, CBS_GPU_ERR_CUDA, "internal scheduler error " + std::to_string(hD.error));
         }
@@ -673,7 +683,7 @@ static int run_raw_scan(cbs_gpu_ctx* c, const double* xh, int n, int count, doub
     CUDA_TRY(c, cudaMemcpyAsync(c->dev.p, &hD, sizeof(Dev), cudaMemcpyHostToDevice, st));
     ScanLayout lay;
     lay.nb_max = nb + 1;
-    lay.B_max = std::max((n + nb - 1) / nb + 2, 50);
+    lay.B_max = std::max(std::max((n + nb - 1) / nb + 2, (int)std::sqrt((double)n) + 4), 50);
     lay.warps = 8;
     while (lay.warps > 1 && lay.bytes() > c->smem_optin) lay.warps >>= 1;
     if (lay.bytes() > c->smem_optin) return fail(c, CBS_GPU_ERR_UNSUPPORTED, "vector too long for the scan kernel's shared memory");

@@ -97,7 +97,7 @@ extern "C" int64_t emul_segment_units(const double* values, const int64_t* unit_
     D.rej_cap = 1 << 20;
     std::vector<int> rej(D.rej_cap);
     D.rej = rej.data();
-    D.draws_cap = draws_cap;
+    D.draws_cap = (rng_mode == RNG_MT) ? draws_cap : 0;  // as the product does
     std::vector<uint64_t> d0(draws_cap > 0 ? draws_cap : 1), d1(draws_cap > 0 ? draws_cap : 1);
     D.draws[0] = d0.data(); D.draws[1] = d1.data();
     std::vector<int> prep_task(D.list_cap), edgeprep_task(D.list_cap), item_prefix(D.list_cap + 1),
