@@ -1,0 +1,361 @@
+#!/usr/bin/env python
+"""bench.py -- CBS markers*samples segmented per second (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo, N B200s of one node
+    python bench.py --impl reference --gpus N --steps K ...  # the reference's own CPU code (oracle/_ref)
+
+A "step" segments one batch of synthetic SNP6-scale input end to end (smoothing + CBS):
+N=1 runs BASELINE.json configs[1] -- ONE synthetic sample, 1.8M markers over 23 chromosomes,
+10k permutations, alpha 0.01, full-permutation p-values.  With N ranks every rank segments its own
+sample(s) (weak scaling, the cohort shards by sample, no data-path collective) and the segment
+tables are gathered at the end of the step.
+
+One JSON line on rank 0.  `value` = device-resident input (float32 already in HBM when the timed
+region starts); `e2e` = the same step through the C-ABI call with pinned HOST buffers (H2D copy of
+the values and D2H of the segment table inside the timed region).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "cbs_markers_samples_per_sec"
+UNIT = "markers*samples/s"
+NPERM = 10000
+ALPHA = 0.01
+
+
+def workload_name(samples_per_gpu: int, scale: float) -> str:
+    m = int(round(1800000 * scale))
+    return (f"configs[1]: {samples_per_gpu} synthetic SNP6-scale sample(s) per GPU, {m} markers x 23 chromosomes, "
+            f"nperm={NPERM}, alpha={ALPHA}, smoothing on, full-permutation p-values")
+
+
+# ---------------------------------------------------------------------------------------------
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "200", "-i", str(self.gpu)], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self) -> dict:
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def read_peaks() -> dict:
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return {"hbm_gbs": float(d.get("hbm_gbs", 6650.0)), "source": "measured (MEASURED_PEAKS.json)"}
+    return {"hbm_gbs": 6650.0, "source": "fallback (B200_PROFILING.md)"}
+
+
+# ---------------------------------------------------------------------------------------------
+def cpu_reference_run(chroms, nperm: int, threads: int, sample: int = 0, repeat: int = 1):
+    """Times the reference's own lib/cbs (oracle/_ref, unmodified sources) on the given chromosomes of
+    the synthetic sample: smoothing + CBS per chromosome, one std::mt19937_64(1) per unit, units spread
+    over `threads` host threads.  Returns (markers, seconds, kind)."""
+    from genomic_b200 import synth
+    from oracle.pyoracle import Oracle, Ref, SegParams
+    vals, off, lab, _ = synth.cohort([sample], scale=1.0, chroms=chroms)
+    p = SegParams(nperm=nperm, alpha=ALPHA, do_smooth=True, rng_kind=0, chain=False, seed=1)
+    x = vals.astype(np.float64)
+    best = None
+    if Ref.available():
+        eng, kind = Ref(), "reference"
+        for _ in range(repeat):
+            t0 = time.perf_counter()
+            eng.segment_units(x, off, lab, p, nthreads=threads)
+            dt = time.perf_counter() - t0
+            best = dt if best is None else min(best, dt)
+    else:  # reference sources were never available on this box: time the C restatement instead
+        eng, kind = Oracle(), "port"
+        threads = 1
+        for _ in range(repeat):
+            t0 = time.perf_counter()
+            eng.segment_units(x, off, lab, p)
+            dt = time.perf_counter() - t0
+            best = dt if best is None else min(best, dt)
+    return int(off[-1]), best, kind, threads
+
+
+CPU_SAMPLE_CHROMS = [19, 20, 21, 22]  # the four smallest autosomes: 131,113 markers
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return  # rank 0 alone runs and prints the reference arm
+    threads = os.cpu_count() or 1
+    chroms = [13, 14, 15, 16, 17, 18, 19, 20, 21, 22] if threads >= 8 else CPU_SAMPLE_CHROMS
+    times = []
+    markers = 0
+    kind = "reference"
+    used = threads
+    for it in range(args.warmup + args.steps):
+        markers, dt, kind, used = cpu_reference_run(chroms, NPERM, threads, sample=0)
+        if it >= args.warmup:
+            times.append(dt)
+    total = sum(times)
+    value = markers * len(times) / total
+    sample = (f"chromosomes {chroms} of synthetic sample 0 ({markers} of 1,800,000 markers), one unit per host "
+              f"thread; per-marker cost grows with chromosome length, so this OVERSTATES the CPU rate on the full sample")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": workload_name(1, 1.0), "sample": sample},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": used, "kind": kind, "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------
+def run_gpu_arm(args):
+    import torch
+    import genomic_b200
+    from genomic_b200 import Params, RNG_MT19937_64, RNG_PHILOX, synth
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    dist = None
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    dev = torch.device("cuda", local_rank)
+    ctx = genomic_b200.Context(local_rank)  # raises if libcbs_cuda.so or the device is missing
+    stream = torch.cuda.current_stream(dev)
+    ctx.set_stream(stream.cuda_stream)
+
+    S = args.samples_per_gpu
+    my_samples = [rank * S + k for k in range(S)]  # global sample ids: results do not depend on the sharding
+    vals, off, lab, ids = synth.cohort(my_samples, scale=args.scale)
+    markers_rank = int(off[-1])
+    rng_mode = RNG_PHILOX if args.rng == "philox" else RNG_MT19937_64
+    gp = Params(alpha=ALPHA, nperm=NPERM, rng_mode=rng_mode, chain=False, seed=1)
+
+    host_pinned = torch.from_numpy(vals).pin_memory()
+    d_vals = host_pinned.to(dev, non_blocking=False)
+    l2_flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    def gather_tables(res):
+        """the only cross-GPU step: gather of the per-rank segment tables (NCCL all_gather)"""
+        if dist is None:
+            return len(res.lengths)
+        n = torch.tensor([len(res.lengths)], device=dev, dtype=torch.int64)
+        counts = [torch.zeros_like(n) for _ in range(world)]
+        dist.all_gather(counts, n)
+        mx = int(max(int(c.item()) for c in counts))
+        tab = torch.zeros((mx, 2), device=dev, dtype=torch.float64)
+        tab[: len(res.lengths), 0] = torch.from_numpy(res.lengths.astype(np.float64)).to(dev)
+        tab[: len(res.lengths), 1] = torch.from_numpy(res.means).to(dev)
+        out = [torch.zeros_like(tab) for _ in range(world)]
+        dist.all_gather(out, tab)
+        return int(sum(int(c.item()) for c in counts))
+
+    def step_device():
+        r = ctx.segment_batch(None, off, gp, unit_ids=ids, device_ptr=d_vals.data_ptr(), dtype=genomic_b200.binding.F32)
+        gather_tables(r)
+        return r
+
+    def step_host():
+        r = ctx.segment_batch(host_pinned.numpy(), off, gp, unit_ids=ids)
+        gather_tables(r)
+        return r
+
+    def timed(fn, steps, warmup, sample_clocks=False):
+        for _ in range(warmup):
+            fn()
+        sampler = ClockSampler(local_rank) if sample_clocks else None
+        per_step = []
+        last = None
+        barrier()
+        if sampler:
+            sampler.start()
+        for _ in range(steps):
+            l2_flush.zero_()
+            e0 = torch.cuda.Event(enable_timing=True)
+            e1 = torch.cuda.Event(enable_timing=True)
+            torch.cuda.synchronize(dev)
+            e0.record(stream)
+            last = fn()
+            e1.record(stream)
+            torch.cuda.synchronize(dev)
+            per_step.append(e0.elapsed_time(e1))
+        barrier()
+        clocks = sampler.stop() if sampler else None
+        total_ms = float(sum(per_step))
+        t = torch.tensor([total_ms], device=dev, dtype=torch.float64)
+        if dist is not None:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)  # max over ranks
+        return float(t.item()), last, clocks
+
+    warm = max(args.warmup, 3)
+    total_ms, res, clocks = timed(step_device, args.steps, warm, sample_clocks=True)
+    e2e_ms, res_h, _ = timed(step_host, args.steps, 1)
+    launches_per_step = int(res.kernel_launches)
+
+    # per-kernel device times and scan work: one more step with per-launch CUDA events on the
+    # launching stream (kept out of the timed steps; its total is reported as profiled_ms)
+    ctx.set_profiling(True)
+    torch.cuda.synchronize(dev)
+    p0 = time.perf_counter()
+    res_p = step_device()
+    torch.cuda.synchronize(dev)
+    profiled_ms = 1e3 * (time.perf_counter() - p0)
+    kms = ctx.last_kernel_ms()
+    arcs, slots = ctx.last_arc_evals()
+    ctx.set_profiling(False)
+    fp64_tinst = ctx.measure_fp64()
+
+    markers_total = markers_rank * world
+    value = markers_total * args.steps / (total_ms * 1e-3)
+    e2e_value = markers_total * args.steps / (e2e_ms * 1e-3)
+
+    if rank == 0:
+        peaks = read_peaks()
+        ksum = sum(kms.values()) or 1.0
+        dominant = max(kms, key=kms.get)
+        # roofline of the dominant kernel.  perm (Fisher-Yates + prefix sums): HBM/L2 bound, SURVEY 8(d):
+        # 16 B per marker per permutation for the shuffle + 16 B for the prefix pass (read px, write S).
+        # scan: FP64 pipe, 2 pipe instructions (DADD + DSETP) per arc examined.
+        perm_elems = float(res_p.perms_run) * 0.0
+        roof_scan = {
+            "bound": "fp64", "kernel": "k_scan", "achieved": 2.0 * arcs / (kms["scan"] * 1e-3) / 1e12 if kms["scan"] else None,
+            "peak": fp64_tinst, "unit": "T fp64-pipe lane-inst/s",
+            "frac": (2.0 * arcs / (kms["scan"] * 1e-3) / 1e12 / fp64_tinst) if kms["scan"] and fp64_tinst else None,
+            "traffic": None, "arcs": arcs, "slots_issued": slots, "share_of_step": kms["scan"] / ksum,
+            "peak_source": "cbs_gpu_measure_fp64 (DADD+DSETP microbenchmark on this GPU, same run)",
+        }
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": warm,
+            "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": workload_name(S, args.scale), "rng": args.rng, "chain": False,
+                       "samples_per_gpu": S, "l2": "256 MB buffer zeroed between timed steps; scratch arenas >> L2",
+                       "parallelism": f"sample-sharded x{world}, final all_gather of segment tables"},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(vals.nbytes) * world,
+                    "d2h_bytes_per_step": int(len(res_h.lengths) * 12 + len(off) * 16) * world,
+                    "ms_per_step": e2e_ms / args.steps},
+            "gpu_launches": launches_per_step * args.steps,
+            "clocks": clocks,
+            "kernel_ms_profiled_step": {k: round(v, 3) for k, v in kms.items()},
+            "profiled_step_ms": profiled_ms,
+            "dominant_kernel": dominant,
+            "roofline": None,
+            "roofline_scan": roof_scan,
+            "segments": int(len(res.lengths)), "perms_run": int(res.perms_run), "rounds": int(res.rounds),
+        }
+        # HBM-side view of the permutation kernel
+        from genomic_b200.binding import KERNEL_NAMES  # noqa: F401
+        line["roofline"] = build_perm_roofline(kms, res_p, off, peaks, ksum) if dominant in ("perm", "gen") else {
+            **roof_scan, "note": "dominant kernel is FP64-pipe bound; the contract's hbm|tensor choice does not apply"}
+        if world == 1 and not args.no_cpu:
+            m, dt, kind, used = cpu_reference_run(CPU_SAMPLE_CHROMS, NPERM, min(os.cpu_count() or 1, len(CPU_SAMPLE_CHROMS)))
+            line["cpu_baseline"] = {
+                "value": m / dt, "unit": UNIT, "cores": used, "kind": kind,
+                "sample": (f"chromosomes {CPU_SAMPLE_CHROMS} of the same synthetic sample ({m} of 1,800,000 markers, "
+                           f"{dt:.1f} s); smaller chromosomes are cheaper per marker, so this overstates the CPU rate"),
+            }
+        print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+    ctx.close()
+
+
+def build_perm_roofline(kms, res_p, off, peaks, ksum):
+    # marker*permutation elements shuffled in the profiled step are not counted on the device;
+    # bound them from below by perms_run * (mean pending-segment length) is not exact, so the
+    # library reports perms_run and we use the exact per-task sum when available.
+    elems = getattr(res_p, "perm_elems", None)
+    ach = None
+    if elems:
+        ach = 32.0 * elems / (kms["perm"] * 1e-3) / 1e9
+    return {"bound": "hbm", "kernel": "k_perm", "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+            "frac": (ach / peaks["hbm_gbs"]) if ach else None, "traffic": None,
+            "algorithmic_bytes_per_marker_perm": 32, "peak_source": peaks["source"], "share_of_step": kms["perm"] / ksum}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--rng", default="mt", choices=["mt", "philox"],
+                    help="mt: bit-exact std::mt19937_64 replay (parity mode, default); philox: fast mode")
+    ap.add_argument("--samples-per-gpu", type=int, default=1)
+    ap.add_argument("--scale", type=float, default=1.0, help="shrink every chromosome (smoke runs only)")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference_arm(args)
+    else:
+        run_gpu_arm(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -21,7 +21,8 @@ RNG_MT19937_64, RNG_PHILOX = 0, 1
 F32, F64 = 0, 1
 HOST, DEVICE = 0, 1
 
-KERNEL_NAMES = ("sched", "gen", "prep", "perm", "scan", "edgeprep", "edgeperm", "means", "smooth")
+KERNEL_NAMES = ("sched", "gen", "prep", "perm", "scan", "edgeprep", "edgeperm", "means", "smooth", "shuf0", "shuf1",
+                "shuf2", "shuf3", "prefix")
 
 
 class CbsGpuError(RuntimeError):
@@ -55,7 +56,7 @@ class CResult(C.Structure):
         ("n_units", C.c_int32), ("n_segments", C.c_int64), ("seg_offsets", C.POINTER(C.c_int64)),
         ("lengths", C.POINTER(C.c_int32)), ("means", C.POINTER(C.c_double)),
         ("draws_consumed", C.POINTER(C.c_uint64)), ("n_splits", C.c_int64), ("splits", C.POINTER(CSplit)),
-        ("rounds", C.c_int32), ("perms_run", C.c_uint64), ("kernel_launches", C.c_uint64), ("ms_h2d", C.c_double),
+        ("rounds", C.c_int32), ("perms_run", C.c_uint64), ("perm_elements", C.c_uint64), ("kernel_launches", C.c_uint64), ("ms_h2d", C.c_double),
         ("ms_smooth", C.c_double), ("ms_segment", C.c_double), ("ms_d2h", C.c_double),
     ]
 
@@ -103,6 +104,7 @@ class BatchResult:
     splits: list = field(default_factory=list)
     rounds: int = 0
     perms_run: int = 0
+    perm_elems: int = 0
     kernel_launches: int = 0
     ms: dict = field(default_factory=dict)
 
@@ -188,11 +190,12 @@ class Context:
     def set_stream(self, cuda_stream_ptr: int | None):
         self._check(self.lib.cbs_gpu_set_stream(self.h, C.c_void_p(cuda_stream_ptr or 0)))
 
-    def set_profiling(self, on: bool):
-        self._check(self.lib.cbs_gpu_set_profiling(self.h, int(on)))
+    def set_profiling(self, events: bool = False, counters: bool = False):
+        """events: per-launch CUDA event timing; counters: scan work counters (slow, never time with them)."""
+        self._check(self.lib.cbs_gpu_set_profiling(self.h, int(bool(events)) | (2 if counters else 0)))
 
     def last_kernel_ms(self) -> dict:
-        a = (C.c_double * 9)()
+        a = (C.c_double * 14)()
         self._check(self.lib.cbs_gpu_last_kernel_ms(self.h, a))
         return dict(zip(KERNEL_NAMES, list(a)))
 
@@ -239,7 +242,7 @@ class Context:
                 lengths=np.ctypeslib.as_array(r.lengths, shape=(ns,)).copy() if ns else np.zeros(0, np.int32),
                 means=np.ctypeslib.as_array(r.means, shape=(ns,)).copy() if ns else np.zeros(0),
                 draws=np.ctypeslib.as_array(r.draws_consumed, shape=(n_units,)).copy() if n_units else np.zeros(0, np.uint64),
-                rounds=int(r.rounds), perms_run=int(r.perms_run), kernel_launches=int(r.kernel_launches),
+                rounds=int(r.rounds), perms_run=int(r.perms_run), perm_elems=int(r.perm_elements), kernel_launches=int(r.kernel_launches),
                 ms=dict(h2d=r.ms_h2d, smooth=r.ms_smooth, segment=r.ms_segment, d2h=r.ms_d2h),
             )
             if r.n_splits:

@@ -248,26 +248,38 @@ struct Dev {
     long long arena_cap;
     int* rej;               // rejection flags of this round's permutations
     long long rej_cap;
-    uint64_t* draws[2];     // MT windows, ping-pong by round parity
+    uint64_t* draws[2];     // MT per-chain windows (chain==1), ping-pong by round parity
     long long draws_cap;
+    // MT, chain==0: every unit starts from the same engine state, so all chains read ONE raw stream
+    // W[0..) that is generated once and extended on demand (positions are absolute cursors)
+    int shared_stream;
+    uint64_t* stream;
+    long long stream_cap, stream_len, stream_target;
     // ---- round plan -------------------------------------------------------------------
     int round;
     int n_prep;   int* prep_task;
     int n_items;  PermItem* items; int* item_prefix;  // exclusive prefix of P, [n_items+1]
+    int* item_uprefix;                                 // exclusive prefix of ceil(P/32) (k_prefix work units)
     int n_edgeprep; int* edgeprep_task;
     int n_edge;   EdgeItem* edges; int* edge_prefix;  // exclusive prefix of threads, [n_edge+1]
     int n_gen;    int* gen_chain;
+    // shuffle work lists by segment-length class (index arrays of the shared-memory shuffle):
+    // 0: n<=4096  1: n<=16384  2: n<=32768  3: n<=65535  4: longer (global-memory kernel)
+    int n_shuf[5]; int* shuf_item[5]; int* shuf_prefix[5];
     unsigned ctr[8];   // work-stealing counters (reset every round)
     // ---- status -----------------------------------------------------------------------
     int done;
     int stall;  // consecutive rounds with live tasks but no planned work
     int error;  // 0 ok; see cbs_gpu.h status codes
     unsigned long long stat_perms, stat_rounds_active;
+    unsigned long long stat_perm_elems;     // sum over max-t permutations of the segment length
     int profile;                            // count scan work (bench / roofline)
     unsigned long long stat_slots, stat_arcs;  // arc slots issued by the scan fast path / of them real arcs
 };
 
-enum { ERR_TASK_CAP = 101, ERR_SEG_CAP = 102, ERR_ARENA = 103, ERR_SPLIT_CAP = 104, ERR_INTERNAL = 105, ERR_STALL = 106 };
+enum { ERR_TASK_CAP = 101, ERR_SEG_CAP = 102, ERR_ARENA = 103, ERR_SPLIT_CAP = 104, ERR_INTERNAL = 105, ERR_STALL = 106, ERR_STREAM_CAP = 107 };
+
+CBS_HD int shuffle_class(int n) { return n <= 4096 ? 0 : n <= 16384 ? 1 : n <= 32768 ? 2 : n <= 65535 ? 3 : 4; }
 
 // ------------------------------------------------------------------------------------
 // Scheduler (runs in ONE thread per round; plain sequential C++ so that the very same
@@ -402,6 +414,7 @@ struct Sched {
         PermItem& it = D.items[D.n_items];
         it.task = idx; it.P = 1; it.obs = 1;
         D.item_prefix[D.n_items + 1] = D.item_prefix[D.n_items] + 1;
+        D.item_uprefix[D.n_items + 1] = D.item_uprefix[D.n_items] + 1;
         D.n_items++;
         t.deferred = 0;
         return true;
@@ -421,34 +434,52 @@ struct Sched {
         }
         if (want > p.max_batch) want = p.max_batch;
         if (want > p.nperm - t.perms_done) want = p.nperm - t.perms_done;
-        const long long per = (long long)t.n + sx_stride(t.n) + bs_stride(t.nb);
+        const int cls = shuffle_class(t.n);
+        // the global-memory shuffle (class 4) keeps a 32-bit index array per permutation in the arena
+        const long long idxd = (cls == 4) ? ((long long)t.n + 1) / 2 + 1 : 0;  // doubles per permutation
+        const long long per = idxd + sx_stride(t.n) + bs_stride(t.nb);
+        const bool mtwin = p.rng_mode == RNG_MT && !D.shared_stream;
         // never let one task take more than half of the arena
         long long fit = (D.arena_cap / 2) / per;
-        if (p.rng_mode == RNG_MT) { const long long f2 = (D.draws_cap / 2 - 312) / t.n; if (f2 < fit) fit = f2; }
+        if (mtwin) { const long long f2 = (D.draws_cap / 2 - 312) / t.n; if (f2 < fit) fit = f2; }
         if (fit < 1) { D.error = ERR_ARENA; return false; }
         if (want > fit) want = (int)fit;
         const long long need = per * want;
         const long long dneed = (p.rng_mode == RNG_MT) ? (long long)want * t.n : 0;
-        if (arena_used + need > D.arena_cap || rej_used + want > D.rej_cap || (p.rng_mode == RNG_MT && draws_used + dneed + 312 > D.draws_cap)) {
+        if (arena_used + need > D.arena_cap || rej_used + want > D.rej_cap || (mtwin && draws_used + dneed + 312 > D.draws_cap)) {
             t.deferred = 1;
             return false;
         }
-        t.off_A = arena_used;
-        t.off_sx = t.off_A + (long long)t.n * want;
+        if (p.rng_mode == RNG_MT) {
+            Chain* ch = chain_of(t);
+            if (D.shared_stream) {
+                const long long pos = (long long)(ch->cursor + ch->commit_d);
+                if (pos + dneed + 312 > D.stream_cap) { D.error = ERR_STREAM_CAP; return false; }
+                t.off_draw = pos;
+                if (pos + dneed > D.stream_target) D.stream_target = pos + dneed;
+            } else {
+                t.off_draw = draws_used;
+                ch->need_off = draws_used; ch->need_len = (uint64_t)dneed;
+                draws_used += dneed + 312;  // the generator appends the 312 words that follow the window
+            }
+        }
+        t.off_A = (cls == 4) ? arena_used : -1;
+        t.off_sx = arena_used + idxd * want;
         t.off_bs = t.off_sx + sx_stride(t.n) * want;
         arena_used += need;
         t.off_rej = rej_used; rej_used += want;
         t.batch_P = want;
         t.cnt_exit = -1; t.cnt_nrej = 0;
-        if (p.rng_mode == RNG_MT) {
-            Chain* ch = chain_of(t);
-            t.off_draw = draws_used;
-            ch->need_off = draws_used; ch->need_len = (uint64_t)dneed;
-            draws_used += dneed + 312;  // the generator appends the 312 words that follow the window
-        }
         PermItem& it = D.items[D.n_items];
         it.task = idx; it.P = want; it.obs = 0;
         D.item_prefix[D.n_items + 1] = D.item_prefix[D.n_items] + want;
+        D.item_uprefix[D.n_items + 1] = D.item_uprefix[D.n_items] + ((want + 31) >> 5);
+        {
+            const int q = D.n_shuf[cls];
+            D.shuf_item[cls][q] = D.n_items;
+            D.shuf_prefix[cls][q + 1] = D.shuf_prefix[cls][q] + want;
+            D.n_shuf[cls] = q + 1;
+        }
         D.n_items++;
         t.deferred = 0;
         t.state = TS_PERM;
@@ -464,11 +495,12 @@ struct Sched {
         const int remaining = p.nperm - t.e_done;
         EdgeItem e;
         e.task = idx; e.side = s; e.perm0 = t.e_done; e.off_scratch = -1; e.off_draw = -1;
+        const bool mtwin = p.rng_mode == RNG_MT && !D.shared_stream;
         long long aneed = 0;
         if (m1 <= 64) {
             e.sparse = 1; e.cols = 0; e.Q = 1;
             e.P = remaining;
-            if (p.rng_mode == RNG_MT) {
+            if (mtwin) {
                 long long fit = (D.draws_cap / 2 - 312) / m1;
                 if (fit < 1) { D.error = ERR_ARENA; return false; }
                 if (e.P > fit) e.P = (int)fit;
@@ -483,7 +515,7 @@ struct Sched {
             if (Q > 8) Q = 8;
             long long P = cols * Q;
             if (P > remaining) P = remaining;
-            if (p.rng_mode == RNG_MT) {
+            if (mtwin) {
                 long long fit = (D.draws_cap / 2 - 312) / m1;
                 if (fit < 1) { D.error = ERR_ARENA; return false; }
                 if (P > fit) { P = fit; if (cols > P) cols = P; Q = (int)((P + cols - 1) / cols); }
@@ -492,14 +524,21 @@ struct Sched {
             aneed = cols * n12;
         }
         const long long dneed = (p.rng_mode == RNG_MT) ? (long long)e.P * m1 : 0;
-        if (arena_used + aneed > D.arena_cap || (p.rng_mode == RNG_MT && draws_used + dneed + 312 > D.draws_cap)) { t.deferred = 1; return false; }
-        if (aneed) { e.off_scratch = arena_used; arena_used += aneed; }
+        if (arena_used + aneed > D.arena_cap || (mtwin && draws_used + dneed + 312 > D.draws_cap)) { t.deferred = 1; return false; }
         if (p.rng_mode == RNG_MT) {
             Chain* ch = chain_of(t);
-            e.off_draw = draws_used;
-            ch->need_off = draws_used; ch->need_len = (uint64_t)dneed;
-            draws_used += dneed + 312;
+            if (D.shared_stream) {
+                const long long pos = (long long)(ch->cursor + ch->commit_d);
+                if (pos + dneed + 312 > D.stream_cap) { D.error = ERR_STREAM_CAP; return false; }
+                e.off_draw = pos;
+                if (pos + dneed > D.stream_target) D.stream_target = pos + dneed;
+            } else {
+                e.off_draw = draws_used;
+                ch->need_off = draws_used; ch->need_len = (uint64_t)dneed;
+                draws_used += dneed + 312;
+            }
         }
+        if (aneed) { e.off_scratch = arena_used; arena_used += aneed; }
         t.e_batch_P = e.P;
         const int threads = e.sparse ? e.P : e.cols;
         D.edges[D.n_edge] = e;
@@ -594,12 +633,14 @@ struct Sched {
                     t.perms_done += used; t.nrej = t.nrejc + 1; t.exit_code = EX_EARLY;
                     consume(t, (uint64_t)used * (uint64_t)t.n);
                     D.stat_perms += (unsigned long long)used;
+                    D.stat_perm_elems += (unsigned long long)used * (unsigned long long)t.n;
                     finish(idx, 1, 0, 0, 0);
                     return false;
                 }
                 t.perms_done += t.batch_P; t.nrej += t.cnt_nrej;
                 consume(t, (uint64_t)t.batch_P * (uint64_t)t.n);
                 D.stat_perms += (unsigned long long)t.batch_P;
+                D.stat_perm_elems += (unsigned long long)t.batch_P * (unsigned long long)t.n;
                 if (t.perms_done >= p.nperm) {
                     if (begin_edges(idx)) return false;
                     return true;
@@ -639,7 +680,8 @@ struct Sched {
         out_list = D.active[outl];
         n_out = 0;
         D.n_prep = 0; D.n_items = 0; D.n_edgeprep = 0; D.n_edge = 0; D.n_gen = 0;
-        D.item_prefix[0] = 0; D.edge_prefix[0] = 0;
+        D.item_prefix[0] = 0; D.item_uprefix[0] = 0; D.edge_prefix[0] = 0;
+        for (int k = 0; k < 5; ++k) { D.n_shuf[k] = 0; D.shuf_prefix[k][0] = 0; }
         for (int k = 0; k < 8; ++k) D.ctr[k] = 0;
         arena_used = 0; rej_used = 0; draws_used = 0;
         const bool mt = D.prm.rng_mode == RNG_MT;
@@ -665,7 +707,7 @@ struct Sched {
                 }
                 if (alive) {
                     out_list[wpos++] = c;
-                    if (ch.commit_d || ch.need_len) D.gen_chain[D.n_gen++] = c;
+                    if (!D.shared_stream && (ch.commit_d || ch.need_len)) D.gen_chain[D.n_gen++] = c;
                 }
             }
             n_out = wpos;

@@ -28,7 +28,7 @@ struct DevBuf {
     template <class T> T* as() const { return (T*)p; }
 };
 
-enum KernelId { K_SCHED = 0, K_GEN, K_PREP, K_PERM, K_SCAN, K_EDGEPREP, K_EDGEPERM, K_MEANS, K_SMOOTH, K_COUNT };
+enum KernelId { K_SCHED = 0, K_GEN, K_PREP, K_PERM, K_SCAN, K_EDGEPREP, K_EDGEPERM, K_MEANS, K_SMOOTH, K_SHUF0, K_SHUF1, K_SHUF2, K_SHUF3, K_PREFIX, K_COUNT };
 
 }  // namespace
 
@@ -42,10 +42,11 @@ struct cbs_gpu_ctx {
     int* d_done = nullptr;  // device alias of h_done
     DevBuf x, cur, gtab, factab, bbtab, unit_off, unit_ids, tasks, ring, act0, act1, chains, segs, splits, udraws, arena,
         rej, draws0, draws1, prep_task, items, item_prefix, edgeprep_task, edges, edge_prefix, gen_chain, means, seed312,
-        dev, staging, fv, fidx, flab, lab, diffs, diffs_sorted, gout, cubtmp, flag, goff;
+        dev, staging, fv, fidx, flab, lab, diffs, diffs_sorted, gout, cubtmp, flag, goff, stream_buf, shuf;
     void* h_stage = nullptr;  // pinned staging for host inputs
     size_t h_stage_cap = 0;
-    bool profiling = false;
+    bool profiling = false;   // per-launch CUDA events
+    bool counting = false;    // scan work counters (atomics in the kernel: slows it, never combine with timing)
     double kms[K_COUNT] = {0};
     std::vector<cudaEvent_t> ev_pool;
     std::vector<std::pair<int, int>> ev_used;  // (kernel id, index of start event); stop = start+1
@@ -272,6 +273,7 @@ int run_cbs(cbs_gpu_ctx* c, const std::vector<long long>& off, const uint64_t* u
     ENSURE(c, c->edges, sizeof(EdgeItem) * (size_t)cap.list_cap);
     ENSURE(c, c->edge_prefix, sizeof(int) * (size_t)(cap.list_cap + 1));
     ENSURE(c, c->gen_chain, sizeof(int) * (size_t)(n_chains + 1));
+    ENSURE(c, c->shuf, sizeof(int) * 11 * (size_t)(cap.list_cap + 1));
     ENSURE(c, c->means, sizeof(double) * (size_t)cap.seg_cap);
     ENSURE(c, c->seed312, sizeof(uint64_t) * 312);
     ENSURE(c, c->dev, sizeof(Dev));
@@ -283,27 +285,32 @@ int run_cbs(cbs_gpu_ctx* c, const std::vector<long long>& off, const uint64_t* u
     long long want_arena = std::min<long long>(24LL * 4096 * std::max<long long>(N, 1), 32LL << 30) / 8;
     want_arena = std::max<long long>(want_arena, 16 * per_perm_max);
     want_arena = std::max<long long>(want_arena, (64LL << 20) / 8);
-    long long want_draws = mt ? std::max<long long>(want_arena / 3, 8 * (Nmax + 312)) : 1;
+    const bool shared_stream = mt && !p->chain;
+    long long want_draws = (mt && !shared_stream) ? std::max<long long>(want_arena / 3, 8 * (Nmax + 312)) : 1;
+    // shared raw MT stream (chain == 0): as long as the largest consumption of any one unit
+    long long want_stream = shared_stream ? std::max<long long>(env_ll("CBS_GPU_STREAM_MB", 4096) * (1LL << 20) / 8, 4 * (Nmax + 312)) : 0;
     const long long env_arena = env_ll("CBS_GPU_ARENA_MB", 0);
-    if (env_arena > 0) { want_arena = env_arena * (1LL << 20) / 8; if (mt) want_draws = std::max<long long>(want_arena / 3, 8 * (Nmax + 312)); }
+    if (env_arena > 0) { want_arena = env_arena * (1LL << 20) / 8; if (mt && !shared_stream) want_draws = std::max<long long>(want_arena / 3, 8 * (Nmax + 312)); }
     {
-        const size_t have = c->arena.cap + c->draws0.cap + c->draws1.cap;
+        const size_t have = c->arena.cap + c->draws0.cap + c->draws1.cap + c->stream_buf.cap;
         const double budget = 0.80 * (double)(free_b + have);
-        const double need = 8.0 * ((double)want_arena + 2.0 * (double)want_draws);
+        const double need = 8.0 * ((double)want_arena + 2.0 * (double)want_draws + (double)want_stream);
         if (need > budget) {
             const double f = budget / need;
             want_arena = (long long)((double)want_arena * f);
             want_draws = (long long)((double)want_draws * f);
+            want_stream = (long long)((double)want_stream * f);
         }
     }
     if (want_arena < 4 * per_perm_max) return fail(c, CBS_GPU_ERR_OOM, "not enough device memory for the permutation arena");
     if ((long long)(c->arena.cap / 8) < want_arena) ENSURE(c, c->arena, (size_t)want_arena * 8);
-    if (mt) {
+    if (shared_stream && (long long)(c->stream_buf.cap / 8) < want_stream) ENSURE(c, c->stream_buf, (size_t)want_stream * 8);
+    if (mt && !shared_stream) {
         if ((long long)(c->draws0.cap / 8) < want_draws) ENSURE(c, c->draws0, (size_t)want_draws * 8);
         if ((long long)(c->draws1.cap / 8) < want_draws) ENSURE(c, c->draws1, (size_t)want_draws * 8);
     }
     cap.arena_cap = (long long)(c->arena.cap / 8);
-    cap.draws_cap = mt ? (long long)(std::min(c->draws0.cap, c->draws1.cap) / 8) : 0;
+    cap.draws_cap = (mt && !shared_stream) ? (long long)(std::min(c->draws0.cap, c->draws1.cap) / 8) : 0;
 
     // ---- device state ---------------------------------------------------------------------
     memset(&hD, 0, sizeof(hD));
@@ -333,7 +340,16 @@ int run_cbs(cbs_gpu_ctx* c, const std::vector<long long>& off, const uint64_t* u
     hD.prep_task = c->prep_task.as<int>(); hD.items = c->items.as<PermItem>(); hD.item_prefix = c->item_prefix.as<int>();
     hD.edgeprep_task = c->edgeprep_task.as<int>(); hD.edges = c->edges.as<EdgeItem>(); hD.edge_prefix = c->edge_prefix.as<int>();
     hD.gen_chain = c->gen_chain.as<int>();
-    hD.profile = c->profiling ? 1 : 0;
+    for (int k = 0; k < 5; ++k) {
+        hD.shuf_item[k] = c->shuf.as<int>() + (size_t)(2 * k) * (cap.list_cap + 1);
+        hD.shuf_prefix[k] = c->shuf.as<int>() + (size_t)(2 * k + 1) * (cap.list_cap + 1);
+    }
+    hD.item_uprefix = c->shuf.as<int>() + (size_t)10 * (cap.list_cap + 1);
+    hD.shared_stream = shared_stream ? 1 : 0;
+    hD.stream = c->stream_buf.as<uint64_t>();
+    hD.stream_cap = shared_stream ? (long long)(c->stream_buf.cap / 8) : 0;
+    hD.stream_len = 312; hD.stream_target = 312;
+    hD.profile = c->counting ? 1 : 0;
 
     CUDA_TRY(c, cudaMemcpyAsync(c->unit_off.p, off.data(), sizeof(long long) * (size_t)(n_units + 1), cudaMemcpyHostToDevice, st));
     if (unit_ids) CUDA_TRY(c, cudaMemcpyAsync(c->unit_ids.p, unit_ids, sizeof(uint64_t) * (size_t)n_units, cudaMemcpyHostToDevice, st));
@@ -352,6 +368,8 @@ int run_cbs(cbs_gpu_ctx* c, const std::vector<long long>& off, const uint64_t* u
         CUDA_TRY(c, cudaMemcpyAsync(c->seed312.p, next, sizeof(next), cudaMemcpyHostToDevice, st));
         CUDA_TRY(c, cudaStreamSynchronize(st));
         k_init_chains<<<std::min(std::max(1, n_chains), 1024), 128, 0, st>>>(dD, c->seed312.as<uint64_t>());
+        if (shared_stream) CUDA_TRY(c, cudaMemcpyAsync(c->stream_buf.p, next, sizeof(next), cudaMemcpyHostToDevice, st));
+        CUDA_TRY(c, cudaStreamSynchronize(st));
     }
 
     // ---- scan kernel configuration ------------------------------------------------------------
@@ -376,6 +394,16 @@ int run_cbs(cbs_gpu_ctx* c, const std::vector<long long>& off, const uint64_t* u
     scan_occ = std::max(1, scan_occ);
     const int scan_grid = c->sm_count * scan_occ;
 
+    // shared-memory shuffle kernel, one launch per segment-length class present in this call
+    static const int kClsMax[4] = {4096, 16384, 32768, 65535};
+    size_t shuf_smem[4]; int shuf_occ[4]; int shuf_limit[4];
+    for (int cls = 0; cls < 4; ++cls) {
+        shuf_smem[cls] = (size_t)kClsMax[cls] * 2 + 32;
+        shuf_limit[cls] = (cls == 0 || Nmax > kClsMax[cls - 1]) ? 1 : 0;
+        shuf_occ[cls] = (int)std::max<size_t>(1, std::min<size_t>(32, (c->smem_optin + 1024) / (shuf_smem[cls] + 1024)));
+    }
+    CUDA_TRY(c, cudaFuncSetAttribute(k_perm_smem, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shuf_smem[3]));
+
     // ---- rounds -------------------------------------------------------------------------------
     *c->h_done = 0;
     const int G = 8;  // rounds per group
@@ -385,9 +413,19 @@ int run_cbs(cbs_gpu_ctx* c, const std::vector<long long>& off, const uint64_t* u
     for (;;) {
         for (int r = 0; r < G; ++r) {
             { LaunchTimer t(c, K_SCHED); k_sched<<<1, 256, 0, st>>>(dD, c->d_done); }
-            if (mt) { LaunchTimer t(c, K_GEN); k_gen<<<std::min(std::max(1, n_chains), c->sm_count * 4), 192, 0, st>>>(dD); }
+            if (mt) {
+                LaunchTimer t(c, K_GEN);
+                if (shared_stream) k_gen_shared<<<1, 192, 0, st>>>(dD);
+                else k_gen<<<std::min(std::max(1, n_chains), c->sm_count * 4), 192, 0, st>>>(dD);
+            }
             { LaunchTimer t(c, K_PREP); k_prep<<<c->sm_count * 2, 128, 0, st>>>(dD); }
-            { LaunchTimer t(c, K_PERM); k_perm<<<c->sm_count * 8, 128, 0, st>>>(dD); }
+            for (int cls = 0; cls < 4; ++cls) {
+                if (shuf_limit[cls] == 0) continue;  // no unit is long enough for this class
+                LaunchTimer t(c, K_SHUF0 + cls);
+                k_perm_smem<<<c->sm_count * shuf_occ[cls], 32, shuf_smem[cls], st>>>(dD, cls);
+            }
+            if (Nmax > 65535) { LaunchTimer t(c, K_PERM); k_perm<<<c->sm_count * 8, 128, 0, st>>>(dD); }
+            { LaunchTimer t(c, K_PREFIX); k_prefix<<<c->sm_count * 6, PFX_WARPS * 32, 0, st>>>(dD); }
             { LaunchTimer t(c, K_SCAN); k_scan<<<scan_grid, lay.warps * 32, scan_smem, st>>>(dD, lay); }
             { LaunchTimer t(c, K_EDGEPREP); k_edgeprep<<<c->sm_count, 128, 0, st>>>(dD); }
             { LaunchTimer t(c, K_EDGEPERM); k_edgeperm<<<c->sm_count * 4, 128, 0, st>>>(dD); }
@@ -419,6 +457,7 @@ int run_cbs(cbs_gpu_ctx* c, const std::vector<long long>& off, const uint64_t* u
         case ERR_SEG_CAP: return fail(c, CBS_GPU_ERR_CAPACITY, "segment table exhausted (raise CBS_GPU_SEG_CAP)");
         case ERR_SPLIT_CAP: return fail(c, CBS_GPU_ERR_CAPACITY, "split log exhausted");
         case ERR_STALL: return fail(c, CBS_GPU_ERR_CUDA, "scheduler stalled: live segments but no work could be planned");
+        case ERR_STREAM_CAP: return fail(c, CBS_GPU_ERR_CAPACITY, "shared MT stream buffer exhausted (raise CBS_GPU_STREAM_MB)");
         case ERR_ARENA: return fail(c, CBS_GPU_ERR_OOM, "permutation arena too small for one segment (raise CBS_GPU_ARENA_MB)");
         default: return fail(c, CBS_GPU_ERR_CUDA, "internal scheduler error " + std::to_string(hD.error));
         }
@@ -493,6 +532,7 @@ int fetch_results(cbs_gpu_ctx* c, const Dev& hD, int n_units, bool want_splits, 
     R->pub.splits = R->splits.empty() ? nullptr : R->splits.data();
     R->pub.rounds = hD.round;
     R->pub.perms_run = hD.stat_perms;
+    R->pub.perm_elements = hD.stat_perm_elems;
     return CBS_GPU_OK;
 }
 
@@ -565,7 +605,7 @@ void cbs_gpu_destroy(cbs_gpu_ctx* c) {
                       &c->act1, &c->chains, &c->segs, &c->splits, &c->udraws, &c->arena, &c->rej, &c->draws0, &c->draws1,
                       &c->prep_task, &c->items, &c->item_prefix, &c->edgeprep_task, &c->edges, &c->edge_prefix, &c->gen_chain,
                       &c->means, &c->seed312, &c->dev, &c->staging, &c->fv, &c->fidx, &c->flab, &c->lab, &c->diffs,
-                      &c->diffs_sorted, &c->gout, &c->cubtmp, &c->flag, &c->goff};
+                      &c->diffs_sorted, &c->gout, &c->cubtmp, &c->flag, &c->goff, &c->stream_buf, &c->shuf};
     for (DevBuf* b : bufs) if (b->p) cudaFree(b->p);
     if (c->h_stage) cudaFreeHost(c->h_stage);
     if (c->h_done) cudaFreeHost(c->h_done);
@@ -586,13 +626,14 @@ int cbs_gpu_set_stream(cbs_gpu_ctx* c, void* s) {
 
 int cbs_gpu_set_profiling(cbs_gpu_ctx* c, int on) {
     if (!c) return CBS_GPU_ERR_INVALID;
-    c->profiling = on != 0;
+    c->profiling = (on & 1) != 0;
+    c->counting = (on & 2) != 0;
     return CBS_GPU_OK;
 }
 
-int cbs_gpu_last_kernel_ms(cbs_gpu_ctx* c, double* ms9) {
-    if (!c || !ms9) return CBS_GPU_ERR_INVALID;
-    for (int k = 0; k < 9; ++k) ms9[k] = c->kms[k];
+int cbs_gpu_last_kernel_ms(cbs_gpu_ctx* c, double* ms14) {
+    if (!c || !ms14) return CBS_GPU_ERR_INVALID;
+    for (int k = 0; k < 14; ++k) ms14[k] = c->kms[k];
     return CBS_GPU_OK;
 }
 

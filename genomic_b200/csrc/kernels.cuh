@@ -205,23 +205,266 @@ __global__ void __launch_bounds__(128) k_prep(Dev* D) {
 }
 
 // ------------------------------------------------------------------------------------
-// k_perm
+// k_gen_shared: MT replay with one engine state for all units (chain == 0).  One CTA extends the
+// single raw stream W[0..stream_len) to stream_target; every chain reads it at its own cursor.
+// ------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(192) k_gen_shared(Dev* D) {
+    __shared__ uint64_t st[312];
+    if (D->done || !D->shared_stream) return;
+    long long len = D->stream_len;
+    const long long target = D->stream_target;
+    if (len >= target) return;
+    uint64_t* w = D->stream;
+    for (int u = threadIdx.x; u < 312; u += blockDim.x) st[u] = w[len - 312 + u];
+    __syncthreads();
+    const int k = threadIdx.x;
+    for (; len < target; len += 312) {
+        uint64_t v = 0;
+        if (k < 156) v = mt_twist(st[k], st[k + 1], st[k + 156]);
+        __syncthreads();
+        if (k < 156) { st[k] = v; w[len + k] = v; }
+        __syncthreads();
+        if (k < 156) { const int kk = k + 156; v = mt_twist(st[kk], st[(kk + 1) % 312], st[kk - 156]); }
+        __syncthreads();
+        if (k < 156) { st[k + 156] = v; w[len + 156 + k] = v; }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) D->stream_len = len;
+}
+
+// ------------------------------------------------------------------------------------
+// k_perm_smem: one warp per permutation, segments of up to 65535 markers.
+//   * the permutation is built on a 16-bit INDEX array in shared memory (2 B per marker), so
+//     the Fisher-Yates random accesses never leave the SM;
+//   * 32 consecutive steps of CBS.cpp:489-492 are taken per warp iteration: a step commutes
+//     with the others of its group unless it shares a position with one of them; those few
+//     (detected with match.any / redux.or) are replayed in order afterwards -- the result is
+//     the sequential shuffle, bit for bit;
+//   * the prefix sums are then accumulated in index order: every lane runs the same
+//     dependent DADD chain on shuffled-in values x[idx[k]], lane k keeps S_k and stores it
+//     coalesced (CBS.cpp:83-90 order, hence identical rounding).
+// ------------------------------------------------------------------------------------
+// index-array accessors: shared memory (16-bit) or global memory (32-bit, L2 only: ld/st.cg)
+struct IdxSmem {
+    unsigned short* a;
+    __device__ __forceinline__ int ld(int k) const { return a[k]; }
+    __device__ __forceinline__ void st(int k, int v) const { a[k] = (unsigned short)v; }
+};
+struct IdxGlobal {
+    unsigned int* a;
+    __device__ __forceinline__ int ld(int k) const { return (int)__ldcg(a + k); }
+    __device__ __forceinline__ void st(int k, int v) const { __stcg(a + k, (unsigned int)v); }
+};
+
+template <class Idx>
+__device__ void perm_warp(Dev* D, const Task& t, int p, Idx s_idx, int lane) {
+    const int n = t.n;
+    const long long base = D->unit_off[t.unit] + t.lo;
+    const double* __restrict__ cur = D->cur + base;
+    const bool mt = D->prm.rng_mode == RNG_MT;
+    const uint64_t* win = nullptr;
+    if (mt) win = (D->shared_stream ? D->stream : D->draws[D->round & 1]) + t.off_draw + (long long)p * n;
+    const uint32_t k0 = (uint32_t)t.key, k1 = (uint32_t)(t.key >> 32), permno = (uint32_t)(t.perms_done + p);
+    for (int k = lane; k < n; k += 32) s_idx.st(k, k);
+    __syncwarp();
+    int i0 = n;
+    for (; i0 >= 64; i0 -= 32) {
+        const int i = i0 - lane;          // this lane's step, rows i-1
+        const uint32_t kd = (uint32_t)(n - i);
+        uint64_t u;
+        if (mt) u = mt_temper(win[kd]);
+        else {
+            uint32_t o[4];
+            philox4x32_10(kd >> 1, permno, 0u, 0u, k0, k1, o);
+            u = (kd & 1u) ? (((uint64_t)o[3] << 32) | o[2]) : (((uint64_t)o[1] << 32) | o[0]);
+        }
+        const int j = draw_index(u, i);
+        const unsigned same = __match_any_sync(FULL, j);
+        const int m = i0 - j;  // lane whose row is my target
+        const bool tgt = (m >= 0) && (m < 32) && (m != lane);
+        const unsigned tmask = __reduce_or_sync(FULL, tgt ? (1u << m) : 0u);
+        const bool conflict = (__popc(same) > 1) || tgt || ((tmask >> lane) & 1u);
+        int vi = 0, vj = 0;
+        if (!conflict) { vi = s_idx.ld(i - 1); vj = s_idx.ld(j - 1); }
+        __syncwarp();
+        if (!conflict) { s_idx.st(i - 1, vj); s_idx.st(j - 1, vi); }
+        __syncwarp();
+        unsigned cm = __ballot_sync(FULL, conflict);
+        while (cm) {
+            const int l = __ffs(cm) - 1;
+            cm &= cm - 1;
+            if (lane == l) {
+                const int a = s_idx.ld(i - 1), b = s_idx.ld(j - 1);
+                s_idx.st(i - 1, b); s_idx.st(j - 1, a);
+            }
+            __syncwarp();
+        }
+    }
+    if (lane == 0) {
+        DrawSrc src;
+        if (mt) src.init_mt(win); else src.init_philox(t.key, 0u, permno);
+        for (int i = i0; i >= 1; --i) {
+            const int j = draw_index(src.u64((uint32_t)(n - i)), i);
+            const int a = s_idx.ld(i - 1), b = s_idx.ld(j - 1);
+            s_idx.st(i - 1, b); s_idx.st(j - 1, a);
+        }
+    }
+    __syncwarp();
+    // gather the permuted values into the prefix-sum slots: S[k+1] <- x[idx[k]] (coalesced store);
+    // k_prefix turns them into prefix sums in place
+    double* sx = D->arena + t.off_sx + (long long)p * Sched::sx_stride(n);
+    if (lane == 0) sx[0] = 0.0;
+    int k = lane;
+    for (; k + 96 < n; k += 128) {
+        const double v0 = cur[s_idx.ld(k)], v1 = cur[s_idx.ld(k + 32)], v2 = cur[s_idx.ld(k + 64)], v3 = cur[s_idx.ld(k + 96)];
+        sx[k + 1] = v0; sx[k + 33] = v1; sx[k + 65] = v2; sx[k + 97] = v3;
+    }
+    for (; k < n; k += 32) sx[k + 1] = cur[s_idx.ld(k)];
+    __syncwarp();
+}
+
+__global__ void __launch_bounds__(32) k_perm_smem(Dev* D, int cls) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    unsigned short* s_idx = (unsigned short*)smem_raw;
+    if (D->done) return;
+    const int lane = threadIdx.x;
+    const int nl = D->n_shuf[cls];
+    const int total = D->shuf_prefix[cls][nl];
+    for (;;) {
+        int g = 0;
+        if (lane == 0) g = (int)atomicAdd(&D->ctr[3 + cls], 1u);
+        g = __shfl_sync(FULL, g, 0);
+        if (g >= total) break;
+        const int k = find_item(D->shuf_prefix[cls], nl, g);
+        const PermItem it = D->items[D->shuf_item[cls][k]];
+        perm_warp(D, D->tasks[it.task], g - D->shuf_prefix[cls][k], IdxSmem{s_idx}, lane);
+    }
+}
+
+// ------------------------------------------------------------------------------------
+// k_perm: the same warp-per-permutation shuffle for segments of 65536+ markers, whose index
+// array (32-bit) does not fit in shared memory and lives in the arena (L2-resident accesses).
 // ------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128) k_perm(Dev* D) {
     if (D->done) return;
-    __shared__ int s_base;
-    const int total = D->item_prefix[D->n_items];
+    const int lane = threadIdx.x & 31;
+    const int nl = D->n_shuf[4];
+    const int total = D->shuf_prefix[4][nl];
     for (;;) {
-        __syncthreads();
-        if (threadIdx.x == 0) s_base = (int)atomicAdd(&D->ctr[0], (unsigned)blockDim.x);
-        __syncthreads();
-        const int g = s_base + threadIdx.x;
-        if (s_base >= total) break;
-        if (g >= total) continue;
-        const int k = find_item(D->item_prefix, D->n_items, g);
+        int g = 0;
+        if (lane == 0) g = (int)atomicAdd(&D->ctr[0], 1u);
+        g = __shfl_sync(FULL, g, 0);
+        if (g >= total) break;
+        const int k = find_item(D->shuf_prefix[4], nl, g);
+        const PermItem it = D->items[D->shuf_item[4][k]];
+        const Task& t = D->tasks[it.task];
+        const int p = g - D->shuf_prefix[4][k];
+        const long long idxd = ((long long)t.n + 1) / 2 + 1;  // doubles per permutation (cbs_core.h plan_perm)
+        unsigned int* idx = (unsigned int*)(D->arena + t.off_A + (long long)p * idxd);
+        perm_warp(D, t, p, IdxGlobal{idx}, lane);
+    }
+}
+
+// ------------------------------------------------------------------------------------
+// k_prefix: turns the gathered values S[1..n] of every permutation into prefix sums IN PLACE with
+// one strictly sequential DADD chain per permutation (the reference's order, CBS.cpp:83-90) and
+// records the per-block first-occurrence extrema (CBS.cpp:88-94).  A warp owns 32 permutations
+// of one segment: 32x32 tiles are moved with coalesced 256 B row accesses and transposed through
+// shared memory, so that each lane walks ITS permutation from registers.
+// ------------------------------------------------------------------------------------
+#define PFX_WARPS 4
+__global__ void __launch_bounds__(PFX_WARPS * 32) k_prefix(Dev* D) {
+    __shared__ double tile_all[PFX_WARPS][32][33];
+    if (D->done) return;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    double (*tile)[33] = tile_all[warp];
+    // work unit: 32 consecutive permutations of one item
+    const int total_units = D->item_uprefix[D->n_items];
+    for (;;) {
+        int wu = 0;
+        if (lane == 0) wu = (int)atomicAdd(&D->ctr[7], 1u);
+        wu = __shfl_sync(FULL, wu, 0);
+        if (wu >= total_units) break;
+        const int k = find_item(D->item_uprefix, D->n_items, wu);
+        const int u_in = wu - D->item_uprefix[k];
         const PermItem it = D->items[k];
         if (it.obs) continue;
-        perm_thread(*D, D->tasks[it.task], it.P, g - D->item_prefix[k]);
+        const Task& t = D->tasks[it.task];
+        const int n = t.n, nb = t.nb;
+        const int p0 = u_in * 32;
+        const int np = min(32, it.P - p0);
+        const long long stride = Sched::sx_stride(n);
+        double* sx0 = D->arena + t.off_sx + (long long)p0 * stride;
+        const int* __restrict__ bb = D->bbtab + D->unit_off[t.unit] + t.lo;
+        // per-lane state: permutation p0+lane
+        double run = 0.0, g_lo = 0.0, g_hi = 0.0, lo = 0.0, hi = 0.0;
+        int gi_lo = n, gi_hi = n, ilo = 1, ihi = 1;
+        int b = 1, first = 1, last = bb[1];
+        BlockStats bs(D->arena + t.off_bs + (long long)(p0 + (lane < np ? lane : 0)) * Sched::bs_stride(nb), nb);
+        if (lane < np) sx0[(long long)lane * stride] = 0.0;
+        // software pipeline: the 32 row segments of chunk c+1 are in flight (registers) while the
+        // chain of chunk c runs
+        double nxt[32];
+        {
+            const int cnt0 = min(32, n);
+#pragma unroll
+            for (int r = 0; r < 32; ++r) nxt[r] = (r < np && lane < cnt0) ? sx0[(long long)r * stride + 1 + lane] : 0.0;
+        }
+        for (int i0 = 1; i0 <= n; i0 += 32) {
+            const int cnt = min(32, n - i0 + 1);
+            __syncwarp();
+#pragma unroll
+            for (int r = 0; r < 32; ++r) tile[r][lane] = nxt[r];
+            __syncwarp();
+            if (i0 + 32 <= n) {
+                const int cnt1 = min(32, n - i0 - 31);
+#pragma unroll
+                for (int r = 0; r < 32; ++r) nxt[r] = (r < np && lane < cnt1) ? sx0[(long long)r * stride + i0 + 32 + lane] : 0.0;
+            }
+            if (lane < np) {
+                double v[32];
+#pragma unroll
+                for (int kk = 0; kk < 32; ++kk) v[kk] = tile[lane][kk];
+                const bool plain = (cnt == 32) && (i0 > first) && (i0 + 31 < last);  // chunk strictly inside one block
+                if (plain) {
+#pragma unroll
+                    for (int kk = 0; kk < 32; ++kk) {
+                        run = run + v[kk];
+                        v[kk] = run;
+                        if (run < lo) { lo = run; ilo = i0 + kk; }
+                        if (run > hi) { hi = run; ihi = i0 + kk; }
+                    }
+                } else {
+#pragma unroll 1
+                    for (int kk = 0; kk < cnt; ++kk) {
+                        const int idx = i0 + kk;
+                        run = run + tile[lane][kk];
+                        tile[lane][kk] = run;
+                        if (idx == first) { lo = run; hi = run; ilo = idx; ihi = idx; }
+                        else {
+                            if (run < lo) { lo = run; ilo = idx; }
+                            if (run > hi) { hi = run; ihi = idx; }
+                        }
+                        if (idx == last) {
+                            bs.bmin()[b - 1] = lo; bs.bmax()[b - 1] = hi; bs.amin()[b - 1] = ilo; bs.amax()[b - 1] = ihi;
+                            if (lo < g_lo) { g_lo = lo; gi_lo = ilo; }
+                            if (hi > g_hi) { g_hi = hi; gi_hi = ihi; }
+                            ++b;
+                            first = last + 1;
+                            last = (b <= nb) ? bb[b] : n + 1;
+                        }
+                    }
+                }
+                if (plain) {
+#pragma unroll
+                    for (int kk = 0; kk < 32; ++kk) tile[lane][kk] = v[kk];
+                }
+            }
+            __syncwarp();
+#pragma unroll 8
+            for (int r = 0; r < np; ++r) if (lane < cnt) sx0[(long long)r * stride + i0 + lane] = tile[r][lane];
+        }
+        if (lane < np) { bs.gmin() = g_lo; bs.gmax() = g_hi; bs.gidx()[0] = gi_lo; bs.gidx()[1] = gi_hi; }
     }
 }
 

@@ -93,6 +93,7 @@ typedef struct cbs_gpu_result {
     const cbs_gpu_split* splits;    /* only with record_splits */
     int32_t rounds;                 /* scheduler rounds executed */
     uint64_t perms_run;             /* max-t permutations actually evaluated */
+    uint64_t perm_elements;         /* sum over those permutations of the segment length (markers shuffled) */
     uint64_t kernel_launches;       /* kernels launched by this call */
     double ms_h2d, ms_smooth, ms_segment, ms_d2h; /* CUDA-event timings on the call's stream */
 } cbs_gpu_result;
@@ -145,9 +146,12 @@ int cbs_gpu_tmaxp(cbs_gpu_ctx* ctx, const double* px, int32_t n, int32_t count, 
  * returns 1e12 double-precision pipe instructions per second. */
 int cbs_gpu_measure_fp64(cbs_gpu_ctx* ctx, double* tera_inst_per_s);
 /* timing (CUDA events) of the kernels of the last batched call, ms summed per kernel:
- * order: sched, gen, prep, perm, scan, edgeprep, edgeperm, means, smooth */
-int cbs_gpu_last_kernel_ms(cbs_gpu_ctx* ctx, double* ms9);
-/* when nonzero, every round is bracketed by CUDA events per kernel (slower; for bench.py) */
+ * order: sched, gen, prep, perm (global-memory shuffle), scan, edgeprep, edgeperm, means, smooth,
+ * shuf0..shuf3 (shared-memory shuffle by length class), prefix */
+int cbs_gpu_last_kernel_ms(cbs_gpu_ctx* ctx, double* ms14);
+/* bit 0: bracket every kernel launch with CUDA events (cbs_gpu_last_kernel_ms);
+ * bit 1: count scan-kernel work with device atomics (cbs_gpu_last_arc_evals) -- this slows the scan
+ * kernel several times, so time and count in separate calls */
 int cbs_gpu_set_profiling(cbs_gpu_ctx* ctx, int on);
 /* scan-kernel work of the last batched call (needs profiling on): arcs = real (i,j) pairs examined
  * by the inner loop, slots = compare slots issued (arcs + padding of partially filled units) */

@@ -100,6 +100,18 @@ extern "C" int64_t emul_segment_units(const double* values, const int64_t* unit_
     D.draws_cap = (rng_mode == RNG_MT) ? draws_cap : 0;  // as the product does
     std::vector<uint64_t> d0(draws_cap > 0 ? draws_cap : 1), d1(draws_cap > 0 ? draws_cap : 1);
     D.draws[0] = d0.data(); D.draws[1] = d1.data();
+    // shared stream exactly as the product configures it: MT replay with one engine per unit
+    D.shared_stream = (rng_mode == RNG_MT && !chain) ? 1 : 0;
+    std::vector<uint64_t> stream(D.shared_stream ? (size_t)(1 << 24) : 1);
+    D.stream = stream.data(); D.stream_cap = D.shared_stream ? (1 << 24) : 0;
+    if (D.shared_stream) { mt_seed_next312(seed, D.stream); D.stream_len = 312; D.stream_target = 312; }
+    std::vector<int> shuf_store(10 * (size_t)(4 * 4096 + n_units + 32));
+    for (int k = 0; k < 5; ++k) {
+        D.shuf_item[k] = shuf_store.data() + (size_t)(2 * k) * (4 * 4096 + n_units + 32);
+        D.shuf_prefix[k] = shuf_store.data() + (size_t)(2 * k + 1) * (4 * 4096 + n_units + 32);
+    }
+    std::vector<int> item_uprefix(D.list_cap + 1);
+    D.item_uprefix = item_uprefix.data();
     std::vector<int> prep_task(D.list_cap), edgeprep_task(D.list_cap), item_prefix(D.list_cap + 1),
         edge_prefix(D.list_cap + 1), gen_chain(D.n_chains + 1);
     std::vector<PermItem> items(D.list_cap);
@@ -119,6 +131,7 @@ extern "C" int64_t emul_segment_units(const double* values, const int64_t* unit_
         if (D.done) break;
         if (rounds > 1000000) { D.error = ERR_INTERNAL; break; }
         const int par = D.round & 1;
+        if (D.shared_stream) mt_extend_stream_seq(D);
         for (int g = 0; g < D.n_gen; ++g) {
             Chain& ch = D.chains[D.gen_chain[g]];
             mt_generate_seq(ch, D.draws[par ^ 1], D.draws[par]);
@@ -136,8 +149,21 @@ extern "C" int64_t emul_segment_units(const double* values, const int64_t* unit_
             }
             px.resize(t.n);
             for (int p = 0; p < it.P; ++p) {
-                perm_thread(D, t, it.P, p);
-                for (int i = 0; i < t.n; ++i) px[i] = D.arena[t.off_A + (long long)i * it.P + p];
+                // the emulation always uses the global-memory thread (class 4 path): give it a scratch
+                std::vector<double> A((size_t)t.n * it.P);
+                Task tt = t; tt.off_A = 0;
+                Dev DD = D; DD.arena = nullptr;
+                {
+                    const long long base = D.unit_off[t.unit] + t.lo;
+                    DrawSrc src;
+                    if (D.prm.rng_mode == RNG_MT) src.init_mt((D.shared_stream ? D.stream : D.draws[D.round & 1]) + t.off_draw + (long long)p * t.n);
+                    else src.init_philox(t.key, 0u, (uint32_t)(t.perms_done + p));
+                    fy_shuffle_column(A.data(), it.P, p, D.cur + base, t.n, src);
+                    ColumnGet g{A.data(), it.P, p};
+                    prefix_and_block_stats(g, t.n, t.nb, D.bbtab + base, D.arena + t.off_sx + (long long)p * Sched::sx_stride(t.n),
+                                           BlockStats(D.arena + t.off_bs + (long long)p * Sched::bs_stride(t.nb), t.nb));
+                }
+                for (int i = 0; i < t.n; ++i) px[i] = A[(size_t)i * it.P + p];
                 // check the prefix sums the thread produced
                 const double* sx = D.arena + t.off_sx + (long long)p * Sched::sx_stride(t.n);
                 double run = 0.0;

@@ -221,3 +221,14 @@ def test_segment_single_call_with_engine_state(ctx, oracle):
     gl, gm, draws = ctx.segment(x, gparams(p), mt_next312=nxt)
     assert np.array_equal(gl, wl) and np.array_equal(gm, wm)
     assert draws == eng.draws - 1234
+
+
+@pytest.mark.parametrize("mode", ["mt_unit", "philox"])
+def test_segment_long_units(ctx, oracle, mode):
+    # one unit per shuffle size class, including > 65535 markers (index array in global memory)
+    rng = np.random.default_rng(61)
+    units = [f32(rng.normal(0, 0.2, n)) for n in (5000, 20000, 40000, 70000)]
+    units[1][9000:] += 0.05
+    vals, off = pack(units)
+    p = SegParams(nperm=40, alpha=0.05, do_smooth=False, rng_kind=1 if mode == "philox" else 0, chain=False, seed=4)
+    check_batch(ctx, oracle, vals, off, p, first_batch=24, max_batch=64)
