@@ -257,17 +257,28 @@ def run_gpu_arm(args):
     e2e_ms, res_h, _ = timed(step_host, args.steps, 1)
     launches_per_step = int(res.kernel_launches)
 
-    # per-kernel device times and scan work: one more step with per-launch CUDA events on the
-    # launching stream (kept out of the timed steps; its total is reported as profiled_ms)
-    ctx.set_profiling(True)
-    torch.cuda.synchronize(dev)
-    p0 = time.perf_counter()
-    res_p = step_device()
-    torch.cuda.synchronize(dev)
-    profiled_ms = 1e3 * (time.perf_counter() - p0)
-    kms = ctx.last_kernel_ms()
+    # Roofline inputs, kept OUT of the timed steps:
+    #  (1) the same K steps once more with every kernel launch bracketed by CUDA events on the launching
+    #      stream -> per-kernel device time (sum over launches) and each kernel's share of the step;
+    #  (2) one step with the scan kernel's work counters on (device atomics slow that kernel, so this
+    #      step is never timed) -> arcs examined = the kernel's algorithmic work.
+    ctx.set_profiling(events=True)
+    kms = None
+    prof_ms = 0.0
+    for _ in range(args.steps):
+        l2_flush.zero_()
+        torch.cuda.synchronize(dev)
+        p0 = time.perf_counter()
+        step_device()
+        torch.cuda.synchronize(dev)
+        prof_ms += 1e3 * (time.perf_counter() - p0)
+        k1 = ctx.last_kernel_ms()
+        kms = k1 if kms is None else {k: kms[k] + v for k, v in k1.items()}
+    kms = {k: v / args.steps for k, v in kms.items()}
+    ctx.set_profiling(counters=True)
+    res_c = step_device()
     arcs, slots = ctx.last_arc_evals()
-    ctx.set_profiling(False)
+    ctx.set_profiling()
     fp64_tinst = ctx.measure_fp64()
 
     markers_total = markers_rank * world
@@ -277,18 +288,38 @@ def run_gpu_arm(args):
     if rank == 0:
         peaks = read_peaks()
         ksum = sum(kms.values()) or 1.0
-        dominant = max(kms, key=kms.get)
-        # roofline of the dominant kernel.  perm (Fisher-Yates + prefix sums): HBM/L2 bound, SURVEY 8(d):
-        # 16 B per marker per permutation for the shuffle + 16 B for the prefix pass (read px, write S).
-        # scan: FP64 pipe, 2 pipe instructions (DADD + DSETP) per arc examined.
-        perm_elems = float(res_p.perms_run) * 0.0
+        groups = {"scan": kms["scan"], "shuffle": kms["shuf0"] + kms["shuf1"] + kms["shuf2"] + kms["shuf3"] + kms["perm"],
+                  "prefix": kms["prefix"], "gen": kms["gen"], "prep": kms["prep"],
+                  "edge": kms["edgeprep"] + kms["edgeperm"], "smooth": kms["smooth"], "sched": kms["sched"], "means": kms["means"]}
+        dominant = max(groups, key=groups.get)
+        elems = float(res_c.perm_elems)  # markers x permutations actually shuffled in one step
+        scan_s = kms["scan"] * 1e-3
         roof_scan = {
-            "bound": "fp64", "kernel": "k_scan", "achieved": 2.0 * arcs / (kms["scan"] * 1e-3) / 1e12 if kms["scan"] else None,
-            "peak": fp64_tinst, "unit": "T fp64-pipe lane-inst/s",
-            "frac": (2.0 * arcs / (kms["scan"] * 1e-3) / 1e12 / fp64_tinst) if kms["scan"] and fp64_tinst else None,
-            "traffic": None, "arcs": arcs, "slots_issued": slots, "share_of_step": kms["scan"] / ksum,
-            "peak_source": "cbs_gpu_measure_fp64 (DADD+DSETP microbenchmark on this GPU, same run)",
+            "bound": "fp64", "kernel": "k_scan",
+            "achieved": 2.0 * arcs / scan_s / 1e12 if scan_s else None, "peak": fp64_tinst,
+            "unit": "T fp64-pipe lane-inst/s", "frac": (2.0 * arcs / scan_s / 1e12 / fp64_tinst) if scan_s and fp64_tinst else None,
+            "traffic": None, "arcs_per_step": arcs, "slots_issued_per_step": slots,
+            "algorithmic_work": "2 FP64-pipe instructions (DADD + DSETP) per arc (i,j) examined",
+            "ms_per_step": kms["scan"], "share_of_step": kms["scan"] / ksum,
+            "peak_source": "cbs_gpu_measure_fp64: DADD+DSETP issue-rate microbenchmark on this GPU in this run "
+                           "(MEASURED_PEAKS.json has no FP64 figure)",
         }
+        pfx_s = kms["prefix"] * 1e-3
+        roof_prefix = {
+            "bound": "hbm", "kernel": "k_prefix", "achieved": 16.0 * elems / pfx_s / 1e9 if pfx_s else None,
+            "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": (16.0 * elems / pfx_s / 1e9 / peaks["hbm_gbs"]) if pfx_s else None,
+            "traffic": None, "algorithmic_bytes": "16 B per marker per permutation (read x_perm, write S)",
+            "ms_per_step": kms["prefix"], "share_of_step": kms["prefix"] / ksum, "peak_source": peaks["source"],
+        }
+        shuf_s = groups["shuffle"] * 1e-3
+        roof_shuffle = {
+            "bound": "hbm", "kernel": "k_perm_smem/k_perm", "achieved": 16.0 * elems / shuf_s / 1e9 if shuf_s else None,
+            "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": (16.0 * elems / shuf_s / 1e9 / peaks["hbm_gbs"]) if shuf_s else None,
+            "traffic": None, "algorithmic_bytes": "16 B per marker per permutation (8 B gather + 8 B write, SURVEY 8d)",
+            "ms_per_step": groups["shuffle"], "share_of_step": groups["shuffle"] / ksum, "peak_source": peaks["source"],
+            "note": "the Fisher-Yates itself runs on 16-bit indices in shared memory; it is latency bound, not HBM bound",
+        }
+        roofs = {"scan": roof_scan, "prefix": roof_prefix, "shuffle": roof_shuffle}
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": warm,
             "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -301,17 +332,15 @@ def run_gpu_arm(args):
                     "ms_per_step": e2e_ms / args.steps},
             "gpu_launches": launches_per_step * args.steps,
             "clocks": clocks,
-            "kernel_ms_profiled_step": {k: round(v, 3) for k, v in kms.items()},
-            "profiled_step_ms": profiled_ms,
+            "kernel_ms_per_step": {k: round(v, 3) for k, v in kms.items()},
+            "kernel_groups_ms_per_step": {k: round(v, 3) for k, v in groups.items()},
+            "event_profiled_ms_per_step": prof_ms / args.steps,
             "dominant_kernel": dominant,
-            "roofline": None,
-            "roofline_scan": roof_scan,
-            "segments": int(len(res.lengths)), "perms_run": int(res.perms_run), "rounds": int(res.rounds),
+            "roofline": roofs.get(dominant, roof_scan),
+            "roofline_scan": roof_scan, "roofline_prefix": roof_prefix, "roofline_shuffle": roof_shuffle,
+            "segments": int(len(res.lengths)), "perms_run": int(res.perms_run), "perm_elements": int(res.perm_elems),
+            "rounds": int(res.rounds),
         }
-        # HBM-side view of the permutation kernel
-        from genomic_b200.binding import KERNEL_NAMES  # noqa: F401
-        line["roofline"] = build_perm_roofline(kms, res_p, off, peaks, ksum) if dominant in ("perm", "gen") else {
-            **roof_scan, "note": "dominant kernel is FP64-pipe bound; the contract's hbm|tensor choice does not apply"}
         if world == 1 and not args.no_cpu:
             m, dt, kind, used = cpu_reference_run(CPU_SAMPLE_CHROMS, NPERM, min(os.cpu_count() or 1, len(CPU_SAMPLE_CHROMS)))
             line["cpu_baseline"] = {
@@ -324,19 +353,6 @@ def run_gpu_arm(args):
         dist.barrier()
         dist.destroy_process_group()
     ctx.close()
-
-
-def build_perm_roofline(kms, res_p, off, peaks, ksum):
-    # marker*permutation elements shuffled in the profiled step are not counted on the device;
-    # bound them from below by perms_run * (mean pending-segment length) is not exact, so the
-    # library reports perms_run and we use the exact per-task sum when available.
-    elems = getattr(res_p, "perm_elems", None)
-    ach = None
-    if elems:
-        ach = 32.0 * elems / (kms["perm"] * 1e-3) / 1e9
-    return {"bound": "hbm", "kernel": "k_perm", "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-            "frac": (ach / peaks["hbm_gbs"]) if ach else None, "traffic": None,
-            "algorithmic_bytes_per_marker_perm": 32, "peak_source": peaks["source"], "share_of_step": kms["perm"] / ksum}
 
 
 def main():

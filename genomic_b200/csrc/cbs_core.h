@@ -255,6 +255,9 @@ struct Dev {
     int shared_stream;
     uint64_t* stream;
     long long stream_cap, stream_len, stream_target;
+    const uint64_t* jump_polys;             // table g_{c*S} (mt_jump.h) or nullptr: sequential generation only
+    long long gen_base, gen_E, gen_lead_end;  // extension in flight (written by k_gen_lead)
+    long long span_max;                       // words the generator may add per round
     // ---- round plan -------------------------------------------------------------------
     int round;
     int n_prep;   int* prep_task;
@@ -444,6 +447,11 @@ struct Sched {
         if (mtwin) { const long long f2 = (D.draws_cap / 2 - 312) / t.n; if (f2 < fit) fit = f2; }
         if (fit < 1) { D.error = ERR_ARENA; return false; }
         if (want > fit) want = (int)fit;
+        if (D.shared_stream && p.rng_mode == RNG_MT) {
+            const long long by_span = D.span_max / t.n;  // a batch must fit in one generator span
+            if (by_span < 1) { D.error = ERR_ARENA; return false; }
+            if (want > by_span) want = (int)by_span;
+        }
         const long long need = per * want;
         const long long dneed = (p.rng_mode == RNG_MT) ? (long long)want * t.n : 0;
         if (arena_used + need > D.arena_cap || rej_used + want > D.rej_cap || (mtwin && draws_used + dneed + 312 > D.draws_cap)) {
@@ -455,6 +463,7 @@ struct Sched {
             if (D.shared_stream) {
                 const long long pos = (long long)(ch->cursor + ch->commit_d);
                 if (pos + dneed + 312 > D.stream_cap) { D.error = ERR_STREAM_CAP; return false; }
+                if (pos + dneed > D.stream_len + D.span_max) { t.deferred = 1; return false; }  // generator span per round
                 t.off_draw = pos;
                 if (pos + dneed > D.stream_target) D.stream_target = pos + dneed;
             } else {
@@ -530,6 +539,7 @@ struct Sched {
             if (D.shared_stream) {
                 const long long pos = (long long)(ch->cursor + ch->commit_d);
                 if (pos + dneed + 312 > D.stream_cap) { D.error = ERR_STREAM_CAP; return false; }
+                if (pos + dneed > D.stream_len + D.span_max) { t.deferred = 1; return false; }
                 e.off_draw = pos;
                 if (pos + dneed > D.stream_target) D.stream_target = pos + dneed;
             } else {
@@ -685,6 +695,7 @@ struct Sched {
         for (int k = 0; k < 8; ++k) D.ctr[k] = 0;
         arena_used = 0; rej_used = 0; draws_used = 0;
         const bool mt = D.prm.rng_mode == RNG_MT;
+        if (D.shared_stream && D.gen_E > 0) { D.stream_len = D.gen_base + D.gen_E; D.gen_E = 0; }
         int wpos = 0;
         if (mt) {
             // carried-over chains first, then admit new ones up to max_live

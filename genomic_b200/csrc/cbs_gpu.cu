@@ -16,9 +16,13 @@
 #include "../../include/cbs_gpu.h"
 #include "host_math.h"
 #include "kernels.cuh"
+#include "mt_jump.h"
 #include "smooth.cuh"
 
 using namespace cbsg;
+
+static_assert(GEN_SEG == cbsg::mtjump::SEG && GEN_NSEG == cbsg::mtjump::NSEG && GEN_LEAD == cbsg::mtjump::LEAD,
+              "generator geometry must match the jump table");
 
 namespace {
 
@@ -42,7 +46,8 @@ struct cbs_gpu_ctx {
     int* d_done = nullptr;  // device alias of h_done
     DevBuf x, cur, gtab, factab, bbtab, unit_off, unit_ids, tasks, ring, act0, act1, chains, segs, splits, udraws, arena,
         rej, draws0, draws1, prep_task, items, item_prefix, edgeprep_task, edges, edge_prefix, gen_chain, means, seed312,
-        dev, staging, fv, fidx, flab, lab, diffs, diffs_sorted, gout, cubtmp, flag, goff, stream_buf, shuf;
+        dev, staging, fv, fidx, flab, lab, diffs, diffs_sorted, gout, cubtmp, flag, goff, stream_buf, shuf, jump;
+    bool jump_ready = false;
     void* h_stage = nullptr;  // pinned staging for host inputs
     size_t h_stage_cap = 0;
     bool profiling = false;   // per-launch CUDA events
@@ -349,6 +354,21 @@ int run_cbs(cbs_gpu_ctx* c, const std::vector<long long>& off, const uint64_t* u
     hD.stream = c->stream_buf.as<uint64_t>();
     hD.stream_cap = shared_stream ? (long long)(c->stream_buf.cap / 8) : 0;
     hD.stream_len = 312; hD.stream_target = 312;
+    hD.jump_polys = nullptr;
+    hD.span_max = 1LL << 40;
+    if (shared_stream && (long long)Nmax * hD.prm.first_batch > mtjump::SEG && !env_ll("CBS_GPU_NO_JUMP", 0)) {
+        // parallel generation of the one stream: table of x^(c*S) mod phi, built once per process
+        if (!c->jump_ready) {
+            const mtjump::Table& T = mtjump::table();
+            if (T.ok) {
+                ENSURE(c, c->jump, sizeof(uint64_t) * T.polys.size());
+                CUDA_TRY(c, cudaMemcpyAsync(c->jump.p, T.polys.data(), sizeof(uint64_t) * T.polys.size(), cudaMemcpyHostToDevice, st));
+                CUDA_TRY(c, cudaStreamSynchronize(st));
+                c->jump_ready = true;
+            }
+        }
+        if (c->jump_ready) { hD.jump_polys = c->jump.as<uint64_t>(); hD.span_max = (long long)mtjump::NSEG * mtjump::SEG; }
+    }
     hD.profile = c->counting ? 1 : 0;
 
     CUDA_TRY(c, cudaMemcpyAsync(c->unit_off.p, off.data(), sizeof(long long) * (size_t)(n_units + 1), cudaMemcpyHostToDevice, st));
@@ -415,7 +435,10 @@ int run_cbs(cbs_gpu_ctx* c, const std::vector<long long>& off, const uint64_t* u
             { LaunchTimer t(c, K_SCHED); k_sched<<<1, 256, 0, st>>>(dD, c->d_done); }
             if (mt) {
                 LaunchTimer t(c, K_GEN);
-                if (shared_stream) k_gen_shared<<<1, 192, 0, st>>>(dD);
+                if (shared_stream) {
+                    k_gen_lead<<<1, 192, 0, st>>>(dD);
+                    if (hD.jump_polys) { k_gen_par<<<GEN_NSEG, 320, 0, st>>>(dD); c->launches++; }
+                }
                 else k_gen<<<std::min(std::max(1, n_chains), c->sm_count * 4), 192, 0, st>>>(dD);
             }
             { LaunchTimer t(c, K_PREP); k_prep<<<c->sm_count * 2, 128, 0, st>>>(dD); }
@@ -605,7 +628,7 @@ void cbs_gpu_destroy(cbs_gpu_ctx* c) {
                       &c->act1, &c->chains, &c->segs, &c->splits, &c->udraws, &c->arena, &c->rej, &c->draws0, &c->draws1,
                       &c->prep_task, &c->items, &c->item_prefix, &c->edgeprep_task, &c->edges, &c->edge_prefix, &c->gen_chain,
                       &c->means, &c->seed312, &c->dev, &c->staging, &c->fv, &c->fidx, &c->flab, &c->lab, &c->diffs,
-                      &c->diffs_sorted, &c->gout, &c->cubtmp, &c->flag, &c->goff, &c->stream_buf, &c->shuf};
+                      &c->diffs_sorted, &c->gout, &c->cubtmp, &c->flag, &c->goff, &c->stream_buf, &c->shuf, &c->jump};
     for (DevBuf* b : bufs) if (b->p) cudaFree(b->p);
     if (c->h_stage) cudaFreeHost(c->h_stage);
     if (c->h_done) cudaFreeHost(c->h_done);

@@ -205,31 +205,84 @@ __global__ void __launch_bounds__(128) k_prep(Dev* D) {
 }
 
 // ------------------------------------------------------------------------------------
-// k_gen_shared: MT replay with one engine state for all units (chain == 0).  One CTA extends the
-// single raw stream W[0..stream_len) to stream_target; every chain reads it at its own cursor.
+// Shared MT stream (chain == 0: every unit starts from the same engine state, so all chains read
+// ONE raw stream W[0..)).  It is extended on demand, in parallel (mt_jump.h):
+//   k_gen_lead  one CTA: sequential lead-in of GEN_LEAD words after the current end (or the whole
+//               extension if it is short / no jump table)
+//   k_gen_par   CTA c: first 312 words of segment c as the GF(2) combination
+//               W[base+c*S+u] = XOR_{i: g_cS[i]=1} W[base+u+i], then the ordinary recurrence to the
+//               end of the segment.  All segments advance concurrently.
 // ------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(192) k_gen_shared(Dev* D) {
-    __shared__ uint64_t st[312];
-    if (D->done || !D->shared_stream) return;
-    long long len = D->stream_len;
-    const long long target = D->stream_target;
-    if (len >= target) return;
-    uint64_t* w = D->stream;
-    for (int u = threadIdx.x; u < 312; u += blockDim.x) st[u] = w[len - 312 + u];
-    __syncthreads();
+#define GEN_SEG (1LL << 18)
+#define GEN_NSEG 128
+#define GEN_LEAD 20480
+
+// extend the raw stream sequentially from `from` to `to` (state = the 312 words before `from`);
+// called by all threads of a CTA with >= 156 threads
+__device__ void gen_sequential(uint64_t* w, long long from, long long to, uint64_t* st) {
     const int k = threadIdx.x;
-    for (; len < target; len += 312) {
+    __syncthreads();
+    for (int u = k; u < 312; u += blockDim.x) st[u] = w[from - 312 + u];
+    __syncthreads();
+    for (long long pos = from; pos < to; pos += 312) {
         uint64_t v = 0;
         if (k < 156) v = mt_twist(st[k], st[k + 1], st[k + 156]);
         __syncthreads();
-        if (k < 156) { st[k] = v; w[len + k] = v; }
+        if (k < 156) { st[k] = v; if (pos + k < to) w[pos + k] = v; }
         __syncthreads();
         if (k < 156) { const int kk = k + 156; v = mt_twist(st[kk], st[(kk + 1) % 312], st[kk - 156]); }
         __syncthreads();
-        if (k < 156) { st[k + 156] = v; w[len + 156 + k] = v; }
+        if (k < 156) { st[k + 156] = v; if (pos + 156 + k < to) w[pos + 156 + k] = v; }
         __syncthreads();
     }
-    if (threadIdx.x == 0) D->stream_len = len;
+}
+
+__global__ void __launch_bounds__(192) k_gen_lead(Dev* D) {
+    __shared__ uint64_t st[312];
+    if (D->done || !D->shared_stream) return;
+    const long long len = D->stream_len, target = D->stream_target;
+    if (len >= target) { if (threadIdx.x == 0) { D->gen_base = len; D->gen_E = 0; } return; }
+    const long long E = target - len;
+    long long lead_end = target;
+    if (D->jump_polys && E > GEN_SEG) lead_end = len + GEN_LEAD;
+    gen_sequential(D->stream, len, lead_end, st);
+    if (threadIdx.x == 0) { D->gen_base = len; D->gen_E = E; D->gen_lead_end = lead_end; }
+}
+
+__global__ void __launch_bounds__(320) k_gen_par(Dev* D) {
+    __shared__ uint64_t st[312];
+    __shared__ uint64_t sp[312];
+    if (D->done || !D->shared_stream || !D->jump_polys) return;
+    const long long base = D->gen_base, E = D->gen_E;
+    if (E <= GEN_SEG) return;  // k_gen_lead did everything
+    const int c = blockIdx.x;
+    if ((long long)c * GEN_SEG >= E) return;
+    uint64_t* w = D->stream;
+    const long long seg_lo = base + (long long)c * GEN_SEG;
+    const long long seg_hi = base + ((E < (long long)(c + 1) * GEN_SEG) ? E : (long long)(c + 1) * GEN_SEG);
+    long long from = D->gen_lead_end;
+    if (c > 0) {
+        const uint64_t* g = D->jump_polys + (size_t)c * 312;
+        for (int u = threadIdx.x; u < 312; u += blockDim.x) sp[u] = g[u];
+        __syncthreads();
+        if (threadIdx.x < 312) {
+            const uint64_t* src = w + base + threadIdx.x;
+            uint64_t acc0 = 0, acc1 = 0;
+            for (int wd = 0; wd < 312; ++wd) {
+                const uint64_t bits = sp[wd];
+                const uint64_t* s0 = src + wd * 64;
+#pragma unroll 8
+                for (int bpos = 0; bpos < 64; bpos += 2) {
+                    if ((bits >> bpos) & 1ULL) acc0 ^= s0[bpos];
+                    if ((bits >> (bpos + 1)) & 1ULL) acc1 ^= s0[bpos + 1];
+                }
+            }
+            w[seg_lo + threadIdx.x] = acc0 ^ acc1;
+        }
+        __syncthreads();
+        from = seg_lo + 312;
+    }
+    if (from < seg_hi) gen_sequential(w, from, seg_hi, st);
 }
 
 // ------------------------------------------------------------------------------------
