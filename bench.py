@@ -185,7 +185,8 @@ def run_gpu_arm(args):
     ctx.set_stream(stream.cuda_stream)
 
     S = args.samples_per_gpu
-    my_samples = [rank * S + k for k in range(S)]  # global sample ids: results do not depend on the sharding
+    from genomic_b200.shard import samples_of_rank
+    my_samples = samples_of_rank(S * world, rank, world)  # global sample ids: results do not depend on the sharding
     vals, off, lab, ids = synth.cohort(my_samples, scale=args.scale)
     markers_rank = int(off[-1])
     rng_mode = RNG_PHILOX if args.rng == "philox" else RNG_MT19937_64
@@ -200,20 +201,12 @@ def run_gpu_arm(args):
             dist.barrier()
         torch.cuda.synchronize(dev)
 
+    from genomic_b200 import shard
+
     def gather_tables(res):
         """the only cross-GPU step: gather of the per-rank segment tables (NCCL all_gather)"""
-        if dist is None:
-            return len(res.lengths)
-        n = torch.tensor([len(res.lengths)], device=dev, dtype=torch.int64)
-        counts = [torch.zeros_like(n) for _ in range(world)]
-        dist.all_gather(counts, n)
-        mx = int(max(int(c.item()) for c in counts))
-        tab = torch.zeros((mx, 2), device=dev, dtype=torch.float64)
-        tab[: len(res.lengths), 0] = torch.from_numpy(res.lengths.astype(np.float64)).to(dev)
-        tab[: len(res.lengths), 1] = torch.from_numpy(res.means).to(dev)
-        out = [torch.zeros_like(tab) for _ in range(world)]
-        dist.all_gather(out, tab)
-        return int(sum(int(c.item()) for c in counts))
+        tab = shard.pack_table(res.seg_count, res.lengths, res.means, ids)
+        return shard.gather_tables(tab, dist, dev).shape[0]
 
     def step_device():
         r = ctx.segment_batch(None, off, gp, unit_ids=ids, device_ptr=d_vals.data_ptr(), dtype=genomic_b200.binding.F32)

@@ -149,7 +149,7 @@ EXPORTED_SYMBOLS = (
     "cbs_gpu_default_params", "cbs_gpu_create", "cbs_gpu_destroy", "cbs_gpu_last_error", "cbs_gpu_set_stream",
     "cbs_gpu_segment_batch", "cbs_gpu_result_free", "cbs_gpu_smooth", "cbs_gpu_segment", "cbs_gpu_tmaxo",
     "cbs_gpu_tmaxp", "cbs_gpu_measure_fp64", "cbs_gpu_last_kernel_ms", "cbs_gpu_set_profiling",
-    "cbs_gpu_last_arc_evals",
+    "cbs_gpu_last_arc_evals", "cbs_gpu_selftest",
 )
 
 

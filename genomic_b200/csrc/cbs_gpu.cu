@@ -60,6 +60,9 @@ struct cbs_gpu_ctx {
     uint64_t last_arcs = 0, last_slots = 0;
     cudaEvent_t e0 = nullptr, e1 = nullptr, e2 = nullptr, e3 = nullptr, e4 = nullptr;
     cudaEvent_t grp[2] = {nullptr, nullptr};
+    // side streams: kernels of one round that do not depend on each other run concurrently
+    cudaStream_t side[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t ev_sched = nullptr, ev_gen = nullptr, ev_side[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
 };
 
 namespace {
@@ -111,7 +114,8 @@ struct LaunchTimer {
     cbs_gpu_ctx* c;
     int kid;
     int idx = -1;
-    LaunchTimer(cbs_gpu_ctx* ctx, int k) : c(ctx), kid(k) {
+    cudaStream_t s;
+    LaunchTimer(cbs_gpu_ctx* ctx, int k, cudaStream_t stream = nullptr) : c(ctx), kid(k), s(stream ? stream : ctx->stream) {
         c->launches++;
         if (!c->profiling) return;
         if (c->ev_next + 2 > c->ev_pool.size()) {
@@ -121,11 +125,11 @@ struct LaunchTimer {
         }
         idx = (int)c->ev_next;
         c->ev_next += 2;
-        cudaEventRecord(c->ev_pool[idx], c->stream);
+        cudaEventRecord(c->ev_pool[idx], s);
     }
     ~LaunchTimer() {
         if (idx < 0) return;
-        cudaEventRecord(c->ev_pool[idx + 1], c->stream);
+        cudaEventRecord(c->ev_pool[idx + 1], s);
         c->ev_used.emplace_back(kid, idx);
     }
 };
@@ -432,26 +436,56 @@ int run_cbs(cbs_gpu_ctx* c, const std::vector<long long>& off, const uint64_t* u
     int gi = 0;
     for (;;) {
         for (int r = 0; r < G; ++r) {
+            // One round.  Dependencies: everything after k_sched; shuffles after the generator;
+            // k_prefix after the shuffles; k_scan after k_prefix and k_prep; next k_sched after all.
+            //   main : sched, gen, [shuffle class 3 | global], prefix, scan
+            //   side0: prep            side1: edgeprep, edgeperm
+            //   side2: shuffle class 0,1      side3: shuffle class 2      side4: shuffle global (if class 3 on main)
             { LaunchTimer t(c, K_SCHED); k_sched<<<1, 256, 0, st>>>(dD, c->d_done); }
+            cudaEventRecord(c->ev_sched, st);
+            cudaStreamWaitEvent(c->side[0], c->ev_sched, 0);
+            { LaunchTimer t(c, K_PREP, c->side[0]); k_prep<<<c->sm_count * 2, 128, 0, c->side[0]>>>(dD); }
+            cudaEventRecord(c->ev_side[0], c->side[0]);
+            cudaStreamWaitEvent(c->side[1], c->ev_sched, 0);
+            { LaunchTimer t(c, K_EDGEPREP, c->side[1]); k_edgeprep<<<c->sm_count, 128, 0, c->side[1]>>>(dD); }
+            { LaunchTimer t(c, K_EDGEPERM, c->side[1]); k_edgeperm<<<c->sm_count * 4, 128, 0, c->side[1]>>>(dD); }
+            cudaEventRecord(c->ev_side[1], c->side[1]);
             if (mt) {
                 LaunchTimer t(c, K_GEN);
                 if (shared_stream) {
                     k_gen_lead<<<1, 192, 0, st>>>(dD);
                     if (hD.jump_polys) { k_gen_par<<<GEN_NSEG, 320, 0, st>>>(dD); c->launches++; }
-                }
-                else k_gen<<<std::min(std::max(1, n_chains), c->sm_count * 4), 192, 0, st>>>(dD);
+                } else k_gen<<<std::min(std::max(1, n_chains), c->sm_count * 4), 192, 0, st>>>(dD);
             }
-            { LaunchTimer t(c, K_PREP); k_prep<<<c->sm_count * 2, 128, 0, st>>>(dD); }
+            cudaEventRecord(c->ev_gen, st);
+            // shuffles: the largest class present stays on the main stream, the others go to side streams
+            int main_cls = -1;
+            for (int cls = 3; cls >= 0; --cls) if (shuf_limit[cls]) { main_cls = cls; break; }
+            bool used_side[5] = {false, false, false, false, false};
             for (int cls = 0; cls < 4; ++cls) {
-                if (shuf_limit[cls] == 0) continue;  // no unit is long enough for this class
-                LaunchTimer t(c, K_SHUF0 + cls);
-                k_perm_smem<<<c->sm_count * shuf_occ[cls], 32, shuf_smem[cls], st>>>(dD, cls);
+                if (shuf_limit[cls] == 0 || cls == main_cls) continue;  // no unit is long enough for this class
+                const int sidx = (cls <= 1) ? 2 : 3;
+                cudaStream_t ss = c->side[sidx];
+                if (!used_side[sidx]) { cudaStreamWaitEvent(ss, c->ev_gen, 0); used_side[sidx] = true; }
+                LaunchTimer t(c, K_SHUF0 + cls, ss);
+                k_perm_smem<<<c->sm_count * shuf_occ[cls], 32, shuf_smem[cls], ss>>>(dD, cls);
             }
-            if (Nmax > 65535) { LaunchTimer t(c, K_PERM); k_perm<<<c->sm_count * 8, 128, 0, st>>>(dD); }
+            if (Nmax > 65535) {
+                cudaStream_t ss = c->side[4];
+                cudaStreamWaitEvent(ss, c->ev_gen, 0);
+                used_side[4] = true;
+                LaunchTimer t(c, K_PERM, ss);
+                k_perm<<<c->sm_count * 8, 128, 0, ss>>>(dD);
+            }
+            if (main_cls >= 0) {
+                LaunchTimer t(c, K_SHUF0 + main_cls);
+                k_perm_smem<<<c->sm_count * shuf_occ[main_cls], 32, shuf_smem[main_cls], st>>>(dD, main_cls);
+            }
+            for (int k = 2; k < 5; ++k) if (used_side[k]) { cudaEventRecord(c->ev_side[k], c->side[k]); cudaStreamWaitEvent(st, c->ev_side[k], 0); }
             { LaunchTimer t(c, K_PREFIX); k_prefix<<<c->sm_count * 6, PFX_WARPS * 32, 0, st>>>(dD); }
+            cudaStreamWaitEvent(st, c->ev_side[0], 0);
             { LaunchTimer t(c, K_SCAN); k_scan<<<scan_grid, lay.warps * 32, scan_smem, st>>>(dD, lay); }
-            { LaunchTimer t(c, K_EDGEPREP); k_edgeprep<<<c->sm_count, 128, 0, st>>>(dD); }
-            { LaunchTimer t(c, K_EDGEPERM); k_edgeperm<<<c->sm_count * 4, 128, 0, st>>>(dD); }
+            cudaStreamWaitEvent(st, c->ev_side[1], 0);
             ++rounds;
         }
         CUDA_TRY(c, cudaEventRecord(c->grp[gi], st));
@@ -616,6 +650,12 @@ int cbs_gpu_create(const int* device_ids, int ndev, cbs_gpu_ctx** out) {
     cudaEventCreate(&c->e0); cudaEventCreate(&c->e1); cudaEventCreate(&c->e2); cudaEventCreate(&c->e3); cudaEventCreate(&c->e4);
     cudaEventCreateWithFlags(&c->grp[0], cudaEventDisableTiming);
     cudaEventCreateWithFlags(&c->grp[1], cudaEventDisableTiming);
+    for (int k = 0; k < 5; ++k) {
+        cudaStreamCreateWithFlags(&c->side[k], cudaStreamNonBlocking);
+        cudaEventCreateWithFlags(&c->ev_side[k], cudaEventDisableTiming);
+    }
+    cudaEventCreateWithFlags(&c->ev_sched, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&c->ev_gen, cudaEventDisableTiming);
     *out = c;
     return CBS_GPU_OK;
 }
@@ -635,6 +675,9 @@ void cbs_gpu_destroy(cbs_gpu_ctx* c) {
     for (auto e : c->ev_pool) cudaEventDestroy(e);
     cudaEvent_t evs[] = {c->e0, c->e1, c->e2, c->e3, c->e4, c->grp[0], c->grp[1]};
     for (auto e : evs) if (e) cudaEventDestroy(e);
+    for (int k = 0; k < 5; ++k) { if (c->side[k]) cudaStreamDestroy(c->side[k]); if (c->ev_side[k]) cudaEventDestroy(c->ev_side[k]); }
+    if (c->ev_sched) cudaEventDestroy(c->ev_sched);
+    if (c->ev_gen) cudaEventDestroy(c->ev_gen);
     if (c->own_stream) cudaStreamDestroy(c->own_stream);
     delete c;
 }
@@ -665,6 +708,11 @@ int cbs_gpu_last_arc_evals(cbs_gpu_ctx* c, uint64_t* arcs, uint64_t* slots) {
     *arcs = c->last_arcs;
     *slots = c->last_slots;
     return CBS_GPU_OK;
+}
+
+int cbs_gpu_selftest(void) {
+    // host-only checks (no device needed): the MT19937-64 jump-ahead table against sequential generation
+    return mtjump::table().ok ? 0 : 1;
 }
 
 int cbs_gpu_measure_fp64(cbs_gpu_ctx* c, double* tera_inst_per_s) {

@@ -1,0 +1,260 @@
+// cna_segment_gpu -- the `cna segment` command on the B200 path.
+//
+// C++ host driver equivalent to Segment::run / Segment::segment_raw (src/cna_segment.hpp:45-62,
+// :127-159): reads a raw log-ratio matrix (.cn), checks log scale, hands every (sample, chromosome)
+// unit to libcbs_cuda.so through the C ABI (one batched call: smoothing + CBS on the device, ONE
+// std::mt19937_64(1) stream shared serially by all units exactly as the reference does), and writes
+// the segment table (.seg) with the reference's row layout.
+//
+//   reader : lib/RawSampleSet.hpp:217-285 (+ per-chromosome position sort :332-386), lib/parse.hpp:20-26,
+//            chromosome names lib/global.hpp:62-90
+//   writer : lib/SegmentedSampleSet.hpp:519-535 (float state, default ostream precision)
+//   options: src/cna_segment.hpp:23-42, defaults :67-79
+//
+// usage: cna_segment_gpu [options] <raw sample matrix file> [<output segmentation file>]
+#include <algorithm>
+#include <charconv>
+#include <cmath>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <fstream>
+#include <iostream>
+#include <map>
+#include <stdexcept>
+#include <string>
+#include <string_view>
+#include <vector>
+
+#include "cbs_gpu.h"
+
+namespace {
+
+constexpr int kChromosomes = 24;
+
+// 1..24, 0 = unknown (lib/global.hpp:62-90)
+int chromosome_index(const std::string& name) {
+    static const std::map<std::string, int> table = [] {
+        std::map<std::string, int> m;
+        for (int i = 1; i <= kChromosomes; ++i) {
+            m[std::to_string(i)] = i;
+            m["chr" + std::to_string(i)] = i;
+        }
+        m["X"] = 23; m["Y"] = 24; m["chrX"] = 23; m["chrY"] = 24;
+        return m;
+    }();
+    const auto it = table.find(name);
+    return it == table.end() ? 0 : it->second;
+}
+
+// tab separated fields; an empty trailing field counts (lib/parse.cpp:27-38)
+struct Fields {
+    std::string_view line;
+    size_t pos = 0;
+    explicit Fields(const std::string& s) : line(s) {}
+    bool next(std::string_view& f) {
+        if (pos > line.size()) return false;
+        const size_t start = pos;
+        while (pos < line.size() && line[pos] != '\t') ++pos;
+        f = line.substr(start, pos - start);
+        pos = (pos < line.size()) ? pos + 1 : line.size() + 1;
+        return true;
+    }
+};
+
+template <class T>
+bool parse_number(std::string_view text, T& value) {  // lib/parse.hpp:20-26
+    const char* b = text.data();
+    const char* e = b + text.size();
+    const auto r = std::from_chars(b, e, value);
+    return r.ec == std::errc() && r.ptr == e;
+}
+
+struct RawMatrix {
+    std::vector<std::string> sample_names;
+    std::vector<unsigned long> positions[kChromosomes];
+    std::vector<std::vector<float>> values[kChromosomes];  // [chrom][sample][marker]
+};
+
+RawMatrix read_cn(const std::string& path) {
+    std::ifstream file(path);
+    if (!file.is_open()) throw std::runtime_error("Failed to open input file '" + path + "'.");
+    RawMatrix m;
+    std::string line;
+    size_t line_no = 0;
+    for (;;) {
+        std::getline(file, line);
+        if (file.eof()) break;  // as the reference: a last line without newline is not processed
+        ++line_no;
+        Fields fields(line);
+        std::string_view f;
+        if (line_no == 1) {
+            for (int i = 0; i < 3 && fields.next(f); ++i) {}
+            while (fields.next(f)) m.sample_names.emplace_back(f);
+            for (auto& v : m.values) v.assign(m.sample_names.size(), {});
+            continue;
+        }
+        std::string chrom_name;
+        unsigned long pos = 0;
+        if (!fields.next(f)) continue;  // marker name
+        if (!fields.next(f)) continue;
+        chrom_name.assign(f);
+        if (!fields.next(f) || !parse_number(f, pos)) continue;
+        const int chr = chromosome_index(chrom_name);
+        if (chr == 0) continue;  // unknown chromosome: row ignored
+        m.positions[chr - 1].push_back(pos);
+        size_t s = 0;
+        while (fields.next(f)) {
+            float v;
+            if (!parse_number(f, v)) continue;  // unparsable fields are skipped, later columns shift
+            if (s < m.sample_names.size()) m.values[chr - 1][s].push_back(v);
+            ++s;
+        }
+    }
+    // sort every chromosome by position
+    for (int c = 0; c < kChromosomes; ++c) {
+        const size_t n = m.positions[c].size();
+        std::vector<size_t> order(n);
+        for (size_t i = 0; i < n; ++i) order[i] = i;
+        std::stable_sort(order.begin(), order.end(), [&](size_t a, size_t b) { return m.positions[c][a] < m.positions[c][b]; });
+        std::vector<unsigned long> p(n);
+        for (size_t i = 0; i < n; ++i) p[i] = m.positions[c][order[i]];
+        m.positions[c].swap(p);
+        for (auto& sv : m.values[c]) {
+            if (sv.size() != n) throw std::runtime_error("sample column count differs from marker count (unparsable fields?)");
+            std::vector<float> v(n);
+            for (size_t i = 0; i < n; ++i) v[i] = sv[order[i]];
+            sv.swap(v);
+        }
+    }
+    return m;
+}
+
+// src/cna_segment.hpp:109-125
+void ensure_log_scale(const RawMatrix& m) {
+    bool neg = false, pos = false;
+    for (const auto& chrom : m.values)
+        for (const auto& sample : chrom)
+            for (float v : sample) {
+                if (!std::isfinite(v)) continue;
+                if (v < 0) neg = true;
+                if (v > 0) pos = true;
+            }
+    if (!(neg && pos)) throw std::invalid_argument("Input does not appear to be in log scale: expected both negative and positive values.");
+}
+
+std::string filestem(const std::string& s) {  // lib/global.cpp name::filestem
+    size_t start = s.find_last_of('/');
+    start = (start == std::string::npos) ? 0 : start + 1;
+    const size_t end = s.find_last_of('.');
+    return s.substr(start, (end == std::string::npos) ? std::string::npos : end - start);
+}
+
+}  // namespace
+
+int main(int argc, char** argv) {
+    try {
+        cbs_gpu_params p;
+        cbs_gpu_default_params(&p);
+        std::string input, output;
+        int device = 0;
+        std::vector<std::string> positional;
+        auto value_of = [&](int& i, const std::string& arg, const std::string& name, std::string& out) -> bool {
+            if (arg == name) { if (i + 1 >= argc) throw std::invalid_argument("missing value for " + name); out = argv[++i]; return true; }
+            if (arg.rfind(name + "=", 0) == 0) { out = arg.substr(name.size() + 1); return true; }
+            return false;
+        };
+        for (int i = 1; i < argc; ++i) {
+            const std::string a = argv[i];
+            std::string v;
+            if (a == "--help") {
+                std::cout << "usage:  cna_segment_gpu [options] <raw sample matrix file> <output segmentation file>\n"
+                             "  --alpha --nperm --min_width --kmax --nmin --eta --trim --smooth_region --outlier_sd_scale\n"
+                             "  --smooth_sd_scale --hybrid --undo_prune --undo_prune_cutoff  (as `cna segment`)\n"
+                             "  --device N   --rng mt|philox   --seed S\n";
+                return 0;
+            } else if (value_of(i, a, "--input", v) || value_of(i, a, "-i", v)) input = v;
+            else if (value_of(i, a, "--output", v) || value_of(i, a, "-o", v)) output = v;
+            else if (value_of(i, a, "--alpha", v)) p.alpha = std::stod(v);
+            else if (value_of(i, a, "--nperm", v)) p.nperm = std::stoi(v);
+            else if (value_of(i, a, "--min_width", v)) p.min_width = std::stoi(v);
+            else if (value_of(i, a, "--kmax", v)) p.kmax = std::stoi(v);
+            else if (value_of(i, a, "--nmin", v)) p.nmin = std::stoi(v);
+            else if (value_of(i, a, "--eta", v)) p.eta = std::stod(v);
+            else if (value_of(i, a, "--trim", v)) p.trim = std::stod(v);
+            else if (value_of(i, a, "--smooth_region", v)) p.smooth_region = std::stoi(v);
+            else if (value_of(i, a, "--outlier_sd_scale", v)) p.outlier_sd_scale = std::stod(v);
+            else if (value_of(i, a, "--smooth_sd_scale", v)) p.smooth_sd_scale = std::stod(v);
+            else if (value_of(i, a, "--hybrid", v)) p.hybrid = (v == "1" || v == "true");
+            else if (value_of(i, a, "--undo_prune", v)) p.undo_prune = (v == "1" || v == "true");
+            else if (value_of(i, a, "--undo_prune_cutoff", v)) p.undo_prune_cutoff = std::stod(v);
+            else if (value_of(i, a, "--device", v)) device = std::stoi(v);
+            else if (value_of(i, a, "--seed", v)) p.seed = std::stoull(v);
+            else if (value_of(i, a, "--rng", v)) { p.rng_mode = (v == "philox") ? CBS_GPU_RNG_PHILOX : CBS_GPU_RNG_MT19937_64; p.chain = (v == "philox") ? 0 : 1; }
+            else if (!a.empty() && a[0] == '-') throw std::invalid_argument("unknown option " + a);
+            else positional.push_back(a);
+        }
+        if (input.empty() && !positional.empty()) { input = positional.front(); positional.erase(positional.begin()); }
+        if (output.empty() && !positional.empty()) output = positional.front();
+        if (input.empty()) throw std::invalid_argument("Input file not specified.");
+        {
+            const size_t dot = input.find_last_of('.');
+            const std::string ext = (dot == std::string::npos || dot == input.size() - 1) ? input : input.substr(dot + 1);
+            if (ext != "cn") throw std::invalid_argument("segment command currently supports raw log-ratio matrices only.");
+        }
+        if (output.empty()) output = filestem(input) + ".seg";
+
+        const RawMatrix m = read_cn(input);
+        ensure_log_scale(m);
+
+        // units in the reference's order: samples in file order, chromosomes 1..24, empty ones skipped
+        std::vector<float> values;
+        std::vector<int64_t> off{0};
+        struct Unit { size_t sample; int chrom; };
+        std::vector<Unit> units;
+        for (size_t s = 0; s < m.sample_names.size(); ++s)
+            for (int c = 0; c < kChromosomes; ++c) {
+                const auto& v = m.values[c][s];
+                if (v.empty()) continue;
+                values.insert(values.end(), v.begin(), v.end());
+                off.push_back((int64_t)values.size());
+                units.push_back({s, c});
+            }
+
+        const int ids[1] = {device};
+        cbs_gpu_ctx* ctx = nullptr;
+        if (cbs_gpu_create(ids, 1, &ctx) != CBS_GPU_OK) throw std::runtime_error("no usable CUDA device (there is no CPU fallback)");
+        cbs_gpu_result* res = nullptr;
+        const int rc = cbs_gpu_segment_batch(ctx, values.data(), CBS_GPU_F32, CBS_GPU_HOST, off.data(), nullptr, (int32_t)units.size(), &p, &res);
+        if (rc != CBS_GPU_OK) {
+            const std::string msg = cbs_gpu_last_error(ctx);
+            cbs_gpu_destroy(ctx);
+            if (rc == CBS_GPU_ERR_INVALID) throw std::invalid_argument(msg);
+            throw std::runtime_error(msg);
+        }
+
+        std::ofstream out(output);
+        if (!out.is_open()) throw std::runtime_error("Failed to open output file '" + output + "'.");
+        out << "sample\tchromosome\tstart\tend\tcount\tstate" << std::endl;
+        for (size_t u = 0; u < units.size(); ++u) {
+            const auto& pos = m.positions[units[u].chrom];
+            size_t start = 0;
+            for (int64_t k = res->seg_offsets[u]; k < res->seg_offsets[u + 1]; ++k) {
+                const size_t len = (size_t)res->lengths[k];
+                if (len == 0) continue;
+                const size_t end = start + len - 1;
+                const float state = (float)res->means[k];  // Segment<rvalue>: rvalue = float (lib/typedefs.h:20)
+                out << m.sample_names[units[u].sample] << '\t' << (units[u].chrom + 1) << '\t' << pos[start] << '\t' << pos[end]
+                    << '\t' << (unsigned long)len << '\t' << state << std::endl;
+                start += len;
+            }
+        }
+        cbs_gpu_result_free(res);
+        cbs_gpu_destroy(ctx);
+        return 0;
+    } catch (const std::exception& e) {
+        std::cerr << "error: " << e.what() << std::endl;  // src/cna.cpp:96-99
+        return 1;
+    }
+}

@@ -141,6 +141,10 @@ int cbs_gpu_tmaxo(cbs_gpu_ctx* ctx, const double* x, int32_t n, double tss, int3
 int cbs_gpu_tmaxp(cbs_gpu_ctx* ctx, const double* px, int32_t n, int32_t count, double tss, int32_t al0, int32_t ibin,
                   double* statistics);
 
+/* host-only self test (needs no device): 0 if the MT19937-64 jump-ahead polynomials reproduce
+ * sequential generation */
+int cbs_gpu_selftest(void);
+
 /* ---- device info / peak measurement helpers (used by bench.py) -------------------------
  * Measured FP64 add+compare issue rate of this device with the library's own microbenchmark:
  * returns 1e12 double-precision pipe instructions per second. */

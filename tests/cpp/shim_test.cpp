@@ -1,0 +1,83 @@
+// GPU test of the header-only shim (genomic_b200/host/cbs_gpu.hpp): the reference's own unit tests
+// (tests/cbs_test.cpp:154-177, :287-307; tests/smooth_test.cpp) with namespace cbs -> cbs_gpu, plus a
+// noisy vector checked against the oracle (liboracle.so) including the in/out engine state.
+#include <cmath>
+#include <cstdio>
+#include <random>
+#include <vector>
+
+#include "../../genomic_b200/host/cbs_gpu.hpp"
+#include "../../oracle/cbs_oracle.h"
+
+static int fails = 0;
+#define CHECK(c) do { if (!(c)) { std::printf("FAIL line %d: %s\n", __LINE__, #c); ++fails; } } while (0)
+
+int main() {
+    std::vector<double> x;
+    for (int i = 0; i < 20; ++i) x.push_back(0.0);
+    for (int i = 0; i < 20; ++i) x.push_back(1.5);
+    for (int i = 0; i < 20; ++i) x.push_back(0.0);
+    double sumx = 0, sumsq = 0;
+    for (double v : x) { sumx += v; sumsq += v * v; }
+    const double tss = sumsq - (sumx * sumx) / x.size();
+    {   // Unweighted_tmaxo_Matches_FortranRawStatisticBehavior
+        const auto obs = cbs_gpu::tmaxo(x, tss, 2, false);
+        CHECK(obs.start == 0); CHECK(obs.end == 58); CHECK(obs.statistic > 1000.0);
+    }
+    {   // Unweighted_SegmentDriver_MatchesDNAcopy_SimpleCase (full-permutation rows)
+        const struct { double alpha; int nperm; int mw; } cases[] = {{0.01, 200, 2}, {0.05, 100, 3}};
+        for (const auto& tc : cases) {
+            std::mt19937_64 rng(1);
+            std::vector<int> sbdry((tc.nperm + 1) * (tc.nperm + 2) / 2 + 2, tc.nperm + 1);
+            const auto seg = cbs_gpu::segment(x, false, tc.alpha, tc.nperm, false, tc.mw, 25, 200, 0.05, sbdry, 1e-6, rng, false, 0.05);
+            CHECK(seg.lengths.size() == 3);
+            if (seg.lengths.size() == 3) {
+                CHECK(seg.lengths[0] == 20 && seg.lengths[1] == 20 && seg.lengths[2] == 20);
+                CHECK(std::fabs(seg.means[0]) < 1e-9 && std::fabs(seg.means[1] - 1.5) < 1e-9 && std::fabs(seg.means[2]) < 1e-9);
+            }
+        }
+    }
+    {   // noisy vector, engine used before and after the call
+        std::mt19937_64 g(99);
+        std::normal_distribution<double> nz(0.0, 0.2);
+        std::vector<double> y(900);
+        for (size_t i = 0; i < y.size(); ++i) y[i] = (double)(float)(nz(g) + ((i >= 300 && i < 420) ? 0.5 : 0.0));
+        std::mt19937_64 rng(7);
+        rng.discard(1000);
+        orc_rng orng;
+        orc_rng_seed_mt(&orng, 7);
+        orc_rng_discard(&orng, 1000);
+        const int nperm = 500;
+        std::vector<int> sbdry(2000, nperm + 1);
+        const auto seg = cbs_gpu::segment(y, false, 0.01, nperm, false, 2, 25, 200, 0.05, sbdry, 1e-6, rng);
+        orc_seg_opts o = {0, 0.01, nperm, 0, 2, 25, 200, 0.05, 1e-6, 0, 0.05};
+        std::vector<int> len(y.size());
+        std::vector<double> mean(y.size());
+        const int k = orc_segment(y.data(), (int)y.size(), &o, &orng, 7, 0, (int)y.size(), len.data(), mean.data(), nullptr, 0, nullptr);
+        CHECK(k == (int)seg.lengths.size());
+        for (int i = 0; i < k && i < (int)seg.lengths.size(); ++i) { CHECK(len[i] == seg.lengths[i]); CHECK(mean[i] == seg.means[i]); }
+        // both engines must now be at the same position
+        for (int i = 0; i < 5; ++i) CHECK(rng() == orc_rng_u64(&orng));
+    }
+    {   // smooth: size mismatch and negative region throw std::invalid_argument (smooth.cpp:125-126)
+        bool threw = false;
+        try { cbs_gpu::smooth({1.0, 2.0}, {1}); } catch (const std::invalid_argument&) { threw = true; }
+        CHECK(threw);
+        threw = false;
+        try { cbs_gpu::smooth({1.0, 2.0}, {1, 1}, -1); } catch (const std::invalid_argument&) { threw = true; }
+        CHECK(threw);
+        std::vector<double> v(500);
+        std::vector<int> lab(500, 1);
+        std::mt19937_64 g(3);
+        std::normal_distribution<double> nz(0.0, 0.2);
+        for (auto& e : v) e = nz(g);
+        v[100] += 4.0; v[300] -= 5.0; v[7] = NAN;
+        const auto got = cbs_gpu::smooth(v, lab);
+        std::vector<double> want(v.size());
+        CHECK(orc_smooth(v.data(), lab.data(), (int64_t)v.size(), 10, 4.0, 2.0, 0.025, want.data()) == 0);
+        for (size_t i = 0; i < v.size(); ++i) CHECK((got[i] == want[i]) || (std::isnan(got[i]) && std::isnan(want[i])));
+        CHECK(got[100] != v[100]);
+    }
+    std::printf(fails ? "shim_test: %d failures\n" : "shim_test: ok\n", fails);
+    return fails ? 1 : 0;
+}

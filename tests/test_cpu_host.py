@@ -1,0 +1,149 @@
+"""CPU (-m "not gpu"): host-side logic without a device.
+ * libcbs_cuda.so loads and exports every symbol include/cbs_gpu.h declares; creating a context
+   without a GPU fails loudly (no CPU fallback);
+ * the worklist scheduler + thread-per-permutation code, compiled for the host (tests/emul), reproduce
+   the oracle in all three RNG modes, under tiny batches / tiny arenas (deferral paths);
+ * the MT19937-64 jump-ahead table passes its self test against sequential generation;
+ * the sharded (world_size 2, gloo) gather of segment tables equals the single-process table."""
+import ctypes as C
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from helpers import make_unit, pack
+from oracle.pyoracle import SegParams, _dp, _ip, c_i64_p, c_u64_p
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+
+
+def test_library_exports_header_symbols():
+    import genomic_b200
+    lib = genomic_b200.load_library()
+    header = open(os.path.join(ROOT, "include", "cbs_gpu.h")).read()
+    declared = set(re.findall(r"\b(cbs_gpu_[a-z0-9_]+)\s*\(", header))
+    assert declared, "no declarations parsed"
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in cbs_gpu.h but not exported"
+    assert declared == set(genomic_b200.EXPORTED_SYMBOLS)
+
+
+def test_no_cpu_fallback():
+    import torch
+    import genomic_b200
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    with pytest.raises(genomic_b200.CbsGpuError):
+        genomic_b200.Context(0)
+
+
+def test_mt_jump_selftest():
+    import genomic_b200
+    lib = genomic_b200.load_library()
+    assert lib.cbs_gpu_selftest() == 0
+
+
+@pytest.fixture(scope="module")
+def emul():
+    d = os.path.join(HERE, "emul")
+    subprocess.run(["g++", "-std=c++17", "-O2", "-fPIC", "-ffp-contract=off", "-shared", "-o", os.path.join(d, "libemul.so"),
+                    os.path.join(d, "emul.cpp"), "-L" + os.path.join(ROOT, "oracle"), "-l:liboracle.so",
+                    "-Wl,-rpath," + os.path.join(ROOT, "oracle")], check=True)
+    L = C.CDLL(os.path.join(d, "libemul.so"))
+    L.emul_segment_units.restype = C.c_int64
+
+    def run(values, off, p, first_batch=64, max_batch=512, arena_cap=1 << 22, draws_cap=1 << 22, max_live=64):
+        values = np.ascontiguousarray(values, dtype=np.float64)
+        off = np.ascontiguousarray(off, dtype=np.int64)
+        nu = len(off) - 1
+        cap = len(values) + nu + 16
+        sc = np.zeros(nu, np.int32); ln = np.zeros(cap, np.int32); mn = np.zeros(cap); dr = np.zeros(nu, np.uint64)
+        nr = C.c_int(0)
+        tot = L.emul_segment_units(_dp(values), off.ctypes.data_as(c_i64_p), None, nu, C.c_double(p.alpha), p.nperm,
+                                   p.min_width, p.rng_kind, int(p.chain), C.c_uint64(p.seed), first_batch, max_batch,
+                                   C.c_longlong(arena_cap), C.c_longlong(draws_cap), max_live, C.c_int64(cap), _ip(sc), _ip(ln),
+                                   _dp(mn), dr.ctypes.data_as(c_u64_p), C.byref(nr), 0, None, None)
+        assert tot >= 0, tot
+        return dict(seg_count=sc, lengths=ln[:tot].copy(), means=mn[:tot].copy(), draws=dr)
+    return run
+
+
+@pytest.mark.parametrize("mode", [0, 1, 2])
+def test_scheduler_emulation_matches_oracle(oracle, emul, mode):
+    rng = np.random.default_rng(5 + mode)
+    for trial in range(25):
+        units = [make_unit(rng, int(rng.integers(1, 1200)), int(rng.integers(0, 5))) for _ in range(int(rng.integers(1, 6)))]
+        if trial % 7 == 0:
+            units.insert(1, np.zeros(0))
+        vals, off = pack(units)
+        p = SegParams(nperm=int(rng.choice([50, 200, 1000])), alpha=float(rng.choice([0.01, 0.05])),
+                      min_width=int(rng.choice([2, 3])), do_smooth=False, rng_kind=1 if mode == 2 else 0,
+                      chain=(mode == 0), seed=int(rng.integers(1, 100)))
+        want = oracle.segment_units(vals, off, np.ones(len(off) - 1, np.int32), p)
+        fb = int(rng.choice([3, 16, 64, 256]))
+        got = emul(vals, off, p, first_batch=fb, max_batch=max(fb, int(rng.choice([8, 64, 2048]))),
+                   arena_cap=int(rng.choice([1 << 16, 1 << 22])), draws_cap=int(rng.choice([1 << 16, 1 << 22])),
+                   max_live=int(rng.choice([1, 2, 64])))
+        assert np.array_equal(want["seg_count"], got["seg_count"])
+        assert np.array_equal(want["lengths"], got["lengths"]) and np.array_equal(want["means"], got["means"])
+        if mode < 2:
+            assert np.array_equal(want["draws"], got["draws"])
+
+
+def test_scheduler_emulation_edge_tests(oracle, emul):
+    rng = np.random.default_rng(9)
+    for trial in range(12):
+        n = int(rng.integers(300, 1500))
+        x = rng.normal(0, 0.2, n)
+        a = int(rng.integers(n // 5, n // 2)); b = int(rng.integers(a + 70, n - 70))
+        x[a:b] += float(rng.choice([0.08, 0.1, 0.12, 0.15]))
+        x = x.astype(np.float32).astype(np.float64)
+        off = np.array([0, n])
+        for mode in range(3):
+            p = SegParams(nperm=300, alpha=0.05, do_smooth=False, rng_kind=1 if mode == 2 else 0, chain=(mode == 0), seed=3)
+            want = oracle.segment_units(x, off, np.ones(1, np.int32), p)
+            got = emul(x, off, p, first_batch=32, max_batch=128, arena_cap=1 << 20, draws_cap=1 << 20)
+            assert np.array_equal(want["lengths"], got["lengths"]) and np.array_equal(want["means"], got["means"])
+
+
+_WORKER = r'''
+import os, sys
+sys.path.insert(0, {root!r}); sys.path.insert(0, os.path.join({root!r}, "tests"))
+import numpy as np, torch.distributed as dist
+from genomic_b200 import shard, synth
+from oracle.pyoracle import Oracle, SegParams
+rank, world = int(sys.argv[1]), 2
+os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = sys.argv[2]
+dist.init_process_group("gloo", rank=rank, world_size=world)
+mine = shard.samples_of_rank(3, rank, world)
+vals, off, lab, ids = synth.cohort(mine, scale=0.002)
+p = SegParams(nperm=100, rng_kind=1, seed=11)
+r = Oracle().segment_units(vals.astype(np.float64), off, lab, p, unit_ids=ids)
+tab = shard.gather_tables(shard.pack_table(r["seg_count"], r["lengths"], r["means"], ids), dist)
+if rank == 0:
+    np.save(sys.argv[3], tab)
+dist.barrier(); dist.destroy_process_group()
+'''
+
+
+def test_sharded_gather_gloo_world2(tmp_path, oracle):
+    """the N>1 path without GPUs: two gloo ranks segment their samples (oracle as the stand-in engine) and
+    gather; the gathered table must equal the single-process table (global unit ids => identical philox keys)"""
+    from genomic_b200 import shard, synth
+    script = tmp_path / "w.py"
+    script.write_text(_WORKER.format(root=ROOT))
+    out = tmp_path / "tab.npy"
+    port = str(29500 + os.getpid() % 2000)
+    procs = [subprocess.Popen([sys.executable, str(script), str(r), port, str(out)]) for r in range(2)]
+    for pr in procs:
+        assert pr.wait(timeout=300) == 0
+    got = np.load(out)
+    assert shard.samples_of_rank(3, 0, 2) == [0, 1] and shard.samples_of_rank(3, 1, 2) == [2]
+    vals, off, lab, ids = synth.cohort([0, 1, 2], scale=0.002)
+    r = oracle.segment_units(vals.astype(np.float64), off, lab, SegParams(nperm=100, rng_kind=1, seed=11), unit_ids=ids)
+    want = shard.pack_table(r["seg_count"], r["lengths"], r["means"], ids)
+    assert np.array_equal(got, want)
