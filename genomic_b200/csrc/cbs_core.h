@@ -146,6 +146,8 @@ struct Task {
     int next;  // chain stack link (MT) / unused
     int nb;
     int alleq;       // written by prep
+    int use_hybrid;  // hybrid && nmin < n (CBS.cpp:983): htmaxp permutations + analytic tail probability
+    double pval1;    // tailp(sqrt(ostat), (kmax+1)/n, n, 100, tol), written by k_tailp (CBS.cpp:846)
     int raw;         // low-level API (tmaxo/tmaxp): use x as given with the supplied tss, no centring
     int deferred;    // did not get arena space this round
     double tss;      // written by prep
@@ -269,7 +271,7 @@ struct Dev {
     // shuffle work lists by segment-length class (index arrays of the shared-memory shuffle):
     // 0: n<=4096  1: n<=16384  2: n<=32768  3: n<=65535  4: longer (global-memory kernel)
     int n_shuf[5]; int* shuf_item[5]; int* shuf_prefix[5];
-    unsigned ctr[8];   // work-stealing counters (reset every round)
+    unsigned ctr[12];  // work-stealing counters (reset every round)
     // ---- status -----------------------------------------------------------------------
     int done;
     int stall;  // consecutive rounds with live tasks but no planned work
@@ -314,6 +316,7 @@ struct Sched {
         Task& t = D.tasks[idx];
         t.unit = unit; t.lo = lo; t.hi = hi; t.n = hi - lo;
         t.state = TS_NEW; t.next = -1; t.nb = 0; t.alleq = 0; t.raw = 0; t.deferred = 0;
+        t.use_hybrid = (D.prm.hybrid && D.prm.nmin < t.n) ? 1 : 0; t.pval1 = 0.0;
         t.tss = 0.0; t.ostat = 0.0; t.tmaxi = 0; t.tmaxj = 0;
         t.nrejc = 0; t.perms_done = 0; t.nrej = 0; t.exit_code = EX_NONE; t.batch_P = 0;
         t.cnt_exit = -1; t.cnt_nrej = 0;
@@ -628,7 +631,10 @@ struct Sched {
                     if (begin_edges(idx)) return false;
                     return true;
                 }
-                t.nrejc = (int)(p.alpha * (double)p.nperm);  // :858
+                if (t.use_hybrid) {  // :846-848
+                    if (t.pval1 > p.alpha) { t.exit_code = EX_TAILP; finish(idx, 1, 0, 0, 0); return false; }
+                    t.nrejc = (int)((p.alpha - t.pval1) * (double)p.nperm);
+                } else t.nrejc = (int)(p.alpha * (double)p.nperm);  // :858
                 t.perms_done = 0; t.nrej = 0;
                 if (p.nperm <= 0) { if (begin_edges(idx)) return false; return true; }
                 t.state = TS_PERM;
@@ -692,7 +698,7 @@ struct Sched {
         D.n_prep = 0; D.n_items = 0; D.n_edgeprep = 0; D.n_edge = 0; D.n_gen = 0;
         D.item_prefix[0] = 0; D.item_uprefix[0] = 0; D.edge_prefix[0] = 0;
         for (int k = 0; k < 5; ++k) { D.n_shuf[k] = 0; D.shuf_prefix[k][0] = 0; }
-        for (int k = 0; k < 8; ++k) D.ctr[k] = 0;
+        for (int k = 0; k < 12; ++k) D.ctr[k] = 0;
         arena_used = 0; rej_used = 0; draws_used = 0;
         const bool mt = D.prm.rng_mode == RNG_MT;
         if (D.shared_stream && D.gen_E > 0) { D.stream_len = D.gen_base + D.gen_E; D.gen_E = 0; }

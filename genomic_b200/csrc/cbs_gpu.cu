@@ -11,6 +11,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/cbs_gpu.h"
@@ -48,6 +49,12 @@ struct cbs_gpu_ctx {
         rej, draws0, draws1, prep_task, items, item_prefix, edgeprep_task, edges, edge_prefix, gen_chain, means, seed312,
         dev, staging, fv, fidx, flab, lab, diffs, diffs_sorted, gout, cubtmp, flag, goff, stream_buf, shuf, jump;
     bool jump_ready = false;
+    // lanes: a call with independent units is split into contiguous unit ranges that run as separate
+    // worklists on their own streams (child contexts), so the latency-bound phases of one lane overlap
+    // the other's; results are merged in unit order
+    std::vector<cbs_gpu_ctx*> lanes;
+    double mem_fraction = 0.80;  // share of free device memory the arenas of this context may take
+    bool is_lane = false;
     void* h_stage = nullptr;  // pinned staging for host inputs
     size_t h_stage_cap = 0;
     bool profiling = false;   // per-launch CUDA events
@@ -146,7 +153,7 @@ void collect_timers(cbs_gpu_ctx* c) {
 int validate_params(cbs_gpu_ctx* c, const cbs_gpu_params* p) {
     if (!p) return fail(c, CBS_GPU_ERR_INVALID, "params is NULL");
     if (p->ibin) return fail(c, CBS_GPU_ERR_UNSUPPORTED, "ibin=true is not on the cna segment path and is not implemented");
-    if (p->hybrid) return fail(c, CBS_GPU_ERR_UNSUPPORTED, "hybrid p-values (htmaxp/tailp) are not implemented on the GPU path yet");
+    if (p->hybrid && (p->kmax < 1 || p->kmax > 128)) return fail(c, CBS_GPU_ERR_UNSUPPORTED, "hybrid: kmax must be in 1..128");
     if (p->undo_prune) return fail(c, CBS_GPU_ERR_UNSUPPORTED, "undo_prune is not implemented on the GPU path yet");
     if (p->min_width < 1) return fail(c, CBS_GPU_ERR_INVALID, "min_width must be >= 1");
     if (p->nperm < 0) return fail(c, CBS_GPU_ERR_INVALID, "nperm must be >= 0");
@@ -302,7 +309,7 @@ int run_cbs(cbs_gpu_ctx* c, const std::vector<long long>& off, const uint64_t* u
     if (env_arena > 0) { want_arena = env_arena * (1LL << 20) / 8; if (mt && !shared_stream) want_draws = std::max<long long>(want_arena / 3, 8 * (Nmax + 312)); }
     {
         const size_t have = c->arena.cap + c->draws0.cap + c->draws1.cap + c->stream_buf.cap;
-        const double budget = 0.80 * (double)(free_b + have);
+        const double budget = c->mem_fraction * (double)(free_b + have);
         const double need = 8.0 * ((double)want_arena + 2.0 * (double)want_draws + (double)want_stream);
         if (need > budget) {
             const double f = budget / need;
@@ -412,7 +419,6 @@ int run_cbs(cbs_gpu_ctx* c, const std::vector<long long>& off, const uint64_t* u
     while (lay.warps > 1 && lay.bytes() > c->smem_optin) lay.warps >>= 1;
     if (lay.bytes() > c->smem_optin) return fail(c, CBS_GPU_ERR_UNSUPPORTED, "segment too long for the scan kernel's shared memory");
     const size_t scan_smem = lay.bytes();
-    CUDA_TRY(c, cudaFuncSetAttribute(k_scan, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)scan_smem));
     int scan_occ = 1;
     CUDA_TRY(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&scan_occ, k_scan, lay.warps * 32, scan_smem));
     scan_occ = std::max(1, scan_occ);
@@ -426,7 +432,6 @@ int run_cbs(cbs_gpu_ctx* c, const std::vector<long long>& off, const uint64_t* u
         shuf_limit[cls] = (cls == 0 || Nmax > kClsMax[cls - 1]) ? 1 : 0;
         shuf_occ[cls] = (int)std::max<size_t>(1, std::min<size_t>(32, (c->smem_optin + 1024) / (shuf_smem[cls] + 1024)));
     }
-    CUDA_TRY(c, cudaFuncSetAttribute(k_perm_smem, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shuf_smem[3]));
 
     // ---- rounds -------------------------------------------------------------------------------
     *c->h_done = 0;
@@ -485,6 +490,11 @@ int run_cbs(cbs_gpu_ctx* c, const std::vector<long long>& off, const uint64_t* u
             { LaunchTimer t(c, K_PREFIX); k_prefix<<<c->sm_count * 6, PFX_WARPS * 32, 0, st>>>(dD); }
             cudaStreamWaitEvent(st, c->ev_side[0], 0);
             { LaunchTimer t(c, K_SCAN); k_scan<<<scan_grid, lay.warps * 32, scan_smem, st>>>(dD, lay); }
+            if (p->hybrid) {
+                k_hscan<<<c->sm_count * 4, 256, 0, st>>>(dD);
+                k_tailp<<<c->sm_count, 64, 0, st>>>(dD);
+                c->launches += 2;
+            }
             cudaStreamWaitEvent(st, c->ev_side[1], 0);
             ++rounds;
         }
@@ -641,7 +651,14 @@ int cbs_gpu_create(const int* device_ids, int ndev, cbs_gpu_ctx** out) {
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, c->device) != cudaSuccess) { delete c; return CBS_GPU_ERR_CUDA; }
     c->sm_count = prop.multiProcessorCount;
-    c->smem_optin = prop.sharedMemPerBlockOptin;
+    c->smem_optin = prop.sharedMemPerBlockOptin - 1024;  // head room for the kernels' static shared memory
+    // function attributes are process-wide per device: set them once to the device maximum, never per call
+    // (concurrent lanes with different needs would otherwise shrink each other's limit)
+    if (cudaFuncSetAttribute(k_scan, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_optin) != cudaSuccess ||
+        cudaFuncSetAttribute(k_perm_smem, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_optin) != cudaSuccess) {
+        delete c;
+        return CBS_GPU_ERR_CUDA;
+    }
     if (cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking) != cudaSuccess) { delete c; return CBS_GPU_ERR_CUDA; }
     c->stream = c->own_stream;
     if (cudaHostAlloc((void**)&c->h_done, sizeof(int), cudaHostAllocMapped) != cudaSuccess) { delete c; return CBS_GPU_ERR_CUDA; }
@@ -662,6 +679,8 @@ int cbs_gpu_create(const int* device_ids, int ndev, cbs_gpu_ctx** out) {
 
 void cbs_gpu_destroy(cbs_gpu_ctx* c) {
     if (!c) return;
+    for (auto* l : c->lanes) cbs_gpu_destroy(l);
+    c->lanes.clear();
     cudaSetDevice(c->device);
     cudaDeviceSynchronize();
     DevBuf* bufs[] = {&c->x, &c->cur, &c->gtab, &c->factab, &c->bbtab, &c->unit_off, &c->unit_ids, &c->tasks, &c->ring, &c->act0,
@@ -799,7 +818,6 @@ static int run_raw_scan(cbs_gpu_ctx* c, const double* xh, int n, int count, doub
     lay.warps = 8;
     while (lay.warps > 1 && lay.bytes() > c->smem_optin) lay.warps >>= 1;
     if (lay.bytes() > c->smem_optin) return fail(c, CBS_GPU_ERR_UNSUPPORTED, "vector too long for the scan kernel's shared memory");
-    CUDA_TRY(c, cudaFuncSetAttribute(k_scan, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lay.bytes()));
     Dev* dD = c->dev.as<Dev>();
     k_prep<<<std::min((count + 3) / 4, c->sm_count * 4), 128, 0, st>>>(dD);
     k_scan<<<std::min(count, c->sm_count * 2), lay.warps * 32, lay.bytes(), st>>>(dD, lay);
@@ -830,8 +848,8 @@ int cbs_gpu_tmaxp(cbs_gpu_ctx* c, const double* px, int32_t n, int32_t count, do
     return CBS_GPU_OK;
 }
 
-int cbs_gpu_segment_batch(cbs_gpu_ctx* c, const void* values, int dtype, int memspace, const int64_t* unit_offsets,
-                          const uint64_t* unit_ids, int32_t n_units, const cbs_gpu_params* params, cbs_gpu_result** out) {
+static int segment_batch_impl(cbs_gpu_ctx* c, const void* values, int dtype, int memspace, const int64_t* unit_offsets,
+                              const uint64_t* unit_ids, int32_t n_units, const cbs_gpu_params* params, cbs_gpu_result** out) {
     if (!c) return CBS_GPU_ERR_INVALID;
     if (!out) return fail(c, CBS_GPU_ERR_INVALID, "out is NULL");
     *out = nullptr;
@@ -897,6 +915,107 @@ int cbs_gpu_segment_batch(cbs_gpu_ctx* c, const void* values, int dtype, int mem
     R->pub.kernel_launches = c->launches;
     c->last_arcs = hD.stat_arcs;
     c->last_slots = hD.stat_slots;
+    *out = &R->pub;
+    return CBS_GPU_OK;
+}
+
+int cbs_gpu_segment_batch(cbs_gpu_ctx* c, const void* values, int dtype, int memspace, const int64_t* unit_offsets,
+                          const uint64_t* unit_ids, int32_t n_units, const cbs_gpu_params* params, cbs_gpu_result** out) {
+    if (!c) return CBS_GPU_ERR_INVALID;
+    if (!out) return fail(c, CBS_GPU_ERR_INVALID, "out is NULL");
+    *out = nullptr;
+    int want_lanes = (int)env_ll("CBS_GPU_LANES", 1);  // opt-in: measured no gain on B200 (persistent grids fill the SMs)
+    const bool serial_stream = params && params->rng_mode == CBS_GPU_RNG_MT19937_64 && params->chain;
+    if (c->is_lane || want_lanes < 2 || !params || !unit_offsets || n_units < 2 * want_lanes || serial_stream ||
+        (dtype != CBS_GPU_F32 && dtype != CBS_GPU_F64))
+        return segment_batch_impl(c, values, dtype, memspace, unit_offsets, unit_ids, n_units, params, out);
+    if (want_lanes > 4) want_lanes = 4;
+    if (cudaSetDevice(c->device) != cudaSuccess) return fail(c, CBS_GPU_ERR_CUDA, "cudaSetDevice failed");
+    const int L = want_lanes;
+    while ((int)c->lanes.size() < L) {
+        cbs_gpu_ctx* child = nullptr;
+        const int ids[1] = {c->device};
+        if (cbs_gpu_create(ids, 1, &child) != CBS_GPU_OK) return fail(c, CBS_GPU_ERR_CUDA, "cannot create lane context");
+        child->is_lane = true;
+        c->lanes.push_back(child);
+    }
+    // contiguous ranges balanced by sum n^1.5 (the cost of the permutation scans)
+    std::vector<double> cost((size_t)n_units + 1, 0.0);
+    for (int u = 0; u < n_units; ++u) {
+        const double n = (double)(unit_offsets[u + 1] - unit_offsets[u]);
+        cost[u + 1] = cost[u] + (n > 0 ? n * std::sqrt(n) : 0.0);
+    }
+    std::vector<int> cut((size_t)L + 1, 0);
+    cut[L] = n_units;
+    for (int l = 1; l < L; ++l) {
+        const double target = cost[n_units] * l / L;
+        int u = cut[l - 1];
+        while (u < n_units && cost[u + 1] <= target) ++u;
+        cut[l] = std::max(u, cut[l - 1]);
+    }
+    // the input must be complete before other streams read it
+    if (memspace == CBS_GPU_DEVICE) cudaStreamSynchronize(c->stream);
+    std::vector<uint64_t> ids_all((size_t)n_units);
+    for (int u = 0; u < n_units; ++u) ids_all[u] = unit_ids ? unit_ids[u] : (uint64_t)u;  // keys must not depend on the split
+    std::vector<int> rcs((size_t)L, CBS_GPU_OK);
+    std::vector<cbs_gpu_result*> parts((size_t)L, nullptr);
+    std::vector<std::vector<int64_t>> offs((size_t)L);
+    std::vector<std::thread> th;
+    const size_t esz = dtype == CBS_GPU_F32 ? 4 : 8;
+    for (int l = 0; l < L; ++l) {
+        cbs_gpu_ctx* child = c->lanes[l];
+        child->profiling = c->profiling; child->counting = c->counting;
+        child->mem_fraction = 0.80 / L;
+        const int u0 = cut[l], u1 = cut[l + 1];
+        offs[l].resize((size_t)(u1 - u0) + 1);
+        for (int u = u0; u <= u1; ++u) offs[l][u - u0] = unit_offsets[u] - unit_offsets[u0];
+        const char* base = (const char*)values + (size_t)unit_offsets[u0] * esz;
+        th.emplace_back([=, &rcs, &parts, &offs, &ids_all]() {
+            rcs[l] = segment_batch_impl(child, base, dtype, memspace, offs[l].data(), ids_all.data() + u0, u1 - u0, params, &parts[l]);
+        });
+    }
+    for (auto& t : th) t.join();
+    for (int l = 0; l < L; ++l)
+        if (rcs[l] != CBS_GPU_OK) {
+            const std::string msg = cbs_gpu_last_error(c->lanes[l]);
+            for (auto* p : parts) if (p) cbs_gpu_result_free(p);
+            return fail(c, rcs[l], msg);
+        }
+    ResultOwner* R = new ResultOwner();
+    memset(&R->pub, 0, sizeof(R->pub));
+    R->seg_offsets.assign((size_t)n_units + 1, 0);
+    R->draws.assign((size_t)n_units, 0);
+    for (int k = 0; k < K_COUNT; ++k) c->kms[k] = 0.0;
+    c->last_arcs = 0; c->last_slots = 0;
+    for (int l = 0; l < L; ++l) {
+        const cbs_gpu_result* p = parts[l];
+        const int u0 = cut[l];
+        const int64_t shift = (int64_t)R->lengths.size();
+        for (int u = 0; u < p->n_units; ++u) {
+            R->seg_offsets[(size_t)u0 + u + 1] = shift + p->seg_offsets[u + 1];
+            R->draws[(size_t)u0 + u] = p->draws_consumed[u];
+        }
+        R->lengths.insert(R->lengths.end(), p->lengths, p->lengths + p->n_segments);
+        R->means.insert(R->means.end(), p->means, p->means + p->n_segments);
+        for (int64_t k = 0; k < p->n_splits; ++k) { cbs_gpu_split sp = p->splits[k]; sp.unit += u0; R->splits.push_back(sp); }
+        R->pub.rounds = std::max(R->pub.rounds, p->rounds);
+        R->pub.perms_run += p->perms_run; R->pub.perm_elements += p->perm_elements; R->pub.kernel_launches += p->kernel_launches;
+        R->pub.ms_h2d = std::max(R->pub.ms_h2d, p->ms_h2d); R->pub.ms_smooth = std::max(R->pub.ms_smooth, p->ms_smooth);
+        R->pub.ms_segment = std::max(R->pub.ms_segment, p->ms_segment); R->pub.ms_d2h = std::max(R->pub.ms_d2h, p->ms_d2h);
+        for (int k = 0; k < K_COUNT; ++k) c->kms[k] += c->lanes[l]->kms[k];
+        c->last_arcs += c->lanes[l]->last_arcs; c->last_slots += c->lanes[l]->last_slots;
+    }
+    // empty leading/trailing units keep monotone offsets
+    for (int u = 0; u < n_units; ++u) if (R->seg_offsets[u + 1] < R->seg_offsets[u]) R->seg_offsets[u + 1] = R->seg_offsets[u];
+    for (auto* p : parts) cbs_gpu_result_free(p);
+    R->pub.n_units = n_units;
+    R->pub.n_segments = (int64_t)R->lengths.size();
+    R->pub.seg_offsets = R->seg_offsets.data();
+    R->pub.lengths = R->lengths.data();
+    R->pub.means = R->means.data();
+    R->pub.draws_consumed = R->draws.data();
+    R->pub.n_splits = (int64_t)R->splits.size();
+    R->pub.splits = R->splits.empty() ? nullptr : R->splits.data();
     *out = &R->pub;
     return CBS_GPU_OK;
 }

@@ -799,7 +799,7 @@ struct ScanLayout {
     }
 };
 
-__global__ void __launch_bounds__(256) k_scan(Dev* D, ScanLayout lay) {
+__global__ void __launch_bounds__(256, 3) k_scan(Dev* D, ScanLayout lay) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     if (D->done) return;
     ScanSmem* sm = (ScanSmem*)smem_raw;
@@ -823,6 +823,7 @@ __global__ void __launch_bounds__(256) k_scan(Dev* D, ScanLayout lay) {
         const PermItem it = D->items[k];
         Task& t = D->tasks[it.task];
         if (it.obs && t.alleq) continue;
+        if (!it.obs && t.use_hybrid) continue;  // k_hscan
         const int p = gidx - D->item_prefix[k];
         const int n = t.n, nb = t.nb;
         const long long base = D->unit_off[t.unit] + t.lo;
@@ -945,6 +946,149 @@ __global__ void __launch_bounds__(256) k_scan(Dev* D, ScanLayout lay) {
             else if (it.obs == 2) { t.ostat = stat; }
             else D->rej[t.off_rej + p] = (t.ostat * 0.99999 <= stat) ? 1 : 0;  // CBS.cpp:838,863
             bs.result() = stat;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------
+// hybrid p-values (DNAcopy's default method; `cna segment --hybrid true`)
+//   k_tailp : analytic tail probability of the observed statistic for arcs longer than kmax
+//             (tailp/nu/it1tsq/fpnorm, CBS.cpp:14-51, :324-339), one thread per new segment.  Uses the
+//             CUDA double-precision erfc/log/exp/pow (<= 4 ulp), so pval1 agrees with the reference's
+//             libm value to ~1e-15 relative, not bit for bit.
+//   k_hscan : htmaxp (CBS.cpp:387-485) for one permutation per CTA.  htmaxp's pruning only skips arcs
+//             that cannot exceed the running maximum, so its value is the exact maximum of
+//             fac(j)*d*d over ALL arcs of length al0..k (inside its ~k-wide blocks, straddling
+//             adjacent blocks, and wrapping around the end), plus the per-block (argmin,argmax)
+//             candidates, which use the other rounding fac*(d*d) (:415-416).  It is evaluated
+//             here by brute force, 25 arcs per marker.
+// ------------------------------------------------------------------------------------
+__device__ double dev_fpnorm(double x) { return 0.5 * erfc(-x / sqrt(2.0)); }
+__device__ double dev_nu(double x, double tol) {
+    if (x > 0.01) {
+        double lnu1 = log(2.0) - 2.0 * log(x);
+        double lnu0 = lnu1;
+        int k = 2;
+        double dk = 0.0;
+        for (int i = 1; i <= k; ++i) { dk += 1.0; lnu1 -= 2.0 * dev_fpnorm(-x * sqrt(dk) / 2.0) / dk; }
+        while (fabs((lnu1 - lnu0) / lnu1) > tol) {
+            lnu0 = lnu1;
+            for (int i = 1; i <= k; ++i) { dk += 1.0; lnu1 -= 2.0 * dev_fpnorm(-x * sqrt(dk) / 2.0) / dk; }
+            k *= 2;
+            if (k > (1 << 24)) break;
+        }
+        return exp(lnu1);
+    }
+    return exp(-0.583 * x);
+}
+__device__ double dev_it1tsq(double x, double a) {
+    double y = x + a - 0.5;
+    double out = (8.0 * y) / (1.0 - 4.0 * y * y) + 2.0 * log((1.0 + 2.0 * y) / (1.0 - 2.0 * y));
+    y = x - 0.5;
+    out -= (8.0 * y) / (1.0 - 4.0 * y * y) + 2.0 * log((1.0 + 2.0 * y) / (1.0 - 2.0 * y));
+    return out;
+}
+__device__ double dev_tailp(double b, double delta, int m, int ngrid, double tol) {
+    const double dincr = (0.5 - delta) / (double)ngrid;
+    const double bsqrtm = b / sqrt((double)m);
+    double tl = 0.5 - dincr, t = 0.5 - 0.5 * dincr, out = 0.0;
+    for (int i = 1; i <= ngrid; ++i) {
+        tl += dincr;
+        t += dincr;
+        const double x = bsqrtm / sqrt(t * (1.0 - t));
+        const double nux = dev_nu(x, tol);
+        out += (nux * nux) * dev_it1tsq(tl, dincr);
+    }
+    out = 9.973557e-2 * pow(b, 3.0) * exp(-b * b / 2.0) * out;
+    return 2.0 * out;
+}
+
+__global__ void __launch_bounds__(64) k_tailp(Dev* D) {
+    if (D->done || !D->prm.hybrid) return;
+    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < D->n_prep; k += gridDim.x * blockDim.x) {
+        Task& t = D->tasks[D->prep_task[k]];
+        if (!t.use_hybrid || t.alleq) continue;
+        const double t1 = sqrt(t.ostat);
+        const double delta = (double)(D->prm.kmax + 1) / (double)t.n;  // CBS.cpp:984
+        t.pval1 = (t1 > 0.1) ? dev_tailp(t1, delta, t.n, 100, D->prm.tol) : 1.0;
+    }
+}
+
+__global__ void __launch_bounds__(256) k_hscan(Dev* D) {
+    __shared__ double s_fac[132];
+    __shared__ double s_red[8];
+    __shared__ int s_g;
+    if (D->done || !D->prm.hybrid) return;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int total = D->item_prefix[D->n_items];
+    const int kk = D->prm.kmax, al0 = D->prm.min_width;
+    for (;;) {
+        __syncthreads();
+        if (tid == 0) s_g = (int)atomicAdd(&D->ctr[1 + 8], 1u);
+        __syncthreads();
+        const int gidx = s_g;
+        if (gidx >= total) break;
+        const int it_k = find_item(D->item_prefix, D->n_items, gidx);
+        const PermItem it = D->items[it_k];
+        Task& t = D->tasks[it.task];
+        if (it.obs || !t.use_hybrid) continue;
+        const int p = gidx - D->item_prefix[it_k];
+        const int n = t.n;
+        const double rn = (double)n;
+        const double* __restrict__ sx = D->arena + t.off_sx + (long long)p * Sched::sx_stride(n);
+        for (int j = tid; j <= kk && j < 132; j += blockDim.x) {
+            const double rj = (double)j;
+            s_fac[j] = (j >= 1) ? rn / (rj * (rn - rj)) : 0.0;
+        }
+        __syncthreads();
+        double best = 0.0;
+        // all arcs (i, i+j), 1 <= i <= n-j, and the wrap-around arcs i = 1..j against i+n-j
+        for (int i = 1 + tid; i <= n; i += blockDim.x) {
+            const double si = sx[i];
+            for (int j = al0; j <= kk; ++j) {
+                double d;
+                if (i + j <= n) d = fabs(sx[i + j] - si);
+                else continue;
+                const double v = s_fac[j] * d * d;
+                if (v > best) best = v;
+            }
+            for (int j = (i > al0 ? i : al0); j <= kk; ++j) {  // wrap: i <= j
+                const double d = fabs(sx[i + n - j] - si);
+                const double v = s_fac[j] * d * d;
+                if (v > best) best = v;
+            }
+        }
+        // per-block (argmin, argmax) candidates of htmaxp's own blocks, nb = int(n/k) (CBS.cpp:390-419)
+        const int nbh = (int)(rn / (double)kk);
+        for (int b = 1 + tid; b <= nbh; b += blockDim.x) {
+            const int first = block_end(n, nbh, b - 1) + 1, last = block_end(n, nbh, b);
+            double lo = sx[first], hi = lo;
+            int ilo = first, ihi = first;
+            for (int i = first + 1; i <= last; ++i) {
+                const double v = sx[i];
+                if (v < lo) { lo = v; ilo = i; }
+                if (v > hi) { hi = v; ihi = i; }
+            }
+            const int d = abs(ilo - ihi);
+            if (d <= kk && d >= al0) {
+                const double rj = (double)d;
+                const double fac = rn / (rj * (rn - rj));
+                const double df = hi - lo;
+                const double v = fac * (df * df);
+                if (v > best) best = v;
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) { const double o2 = shfl_d(best, lane ^ o); if (o2 > best) best = o2; }
+        if (lane == 0) s_red[warp] = best;
+        __syncthreads();
+        if (tid == 0) {
+            double m = 0.0;
+            for (int w = 0; w < (int)(blockDim.x >> 5); ++w) if (s_red[w] > m) m = s_red[w];
+            double tss = t.tss;
+            if (tss <= m + 0.0001) tss = m + 1.0;  // CBS.cpp:483-484
+            const double stat = m / ((tss - m) / (rn - 2.0));
+            D->rej[t.off_rej + p] = (t.ostat * 0.99999 <= stat) ? 1 : 0;
         }
     }
 }

@@ -232,3 +232,25 @@ def test_segment_long_units(ctx, oracle, mode):
     vals, off = pack(units)
     p = SegParams(nperm=40, alpha=0.05, do_smooth=False, rng_kind=1 if mode == "philox" else 0, chain=False, seed=4)
     check_batch(ctx, oracle, vals, off, p, first_batch=24, max_batch=64)
+
+
+@pytest.mark.parametrize("mode", ["mt_chain", "mt_unit", "philox"])
+def test_hybrid_matches_oracle(ctx, oracle, mode):
+    """hybrid p-values (htmaxp + tailp, CBS.cpp:387-485, :324-339; tests/cbs_test.cpp:264-285 style)"""
+    rng = np.random.default_rng({"mt_chain": 71, "mt_unit": 72, "philox": 73}[mode])
+    for trial in range(8):
+        units = [make_unit(rng, int(rng.integers(150, 2500)), int(rng.integers(0, 4))) for _ in range(int(rng.integers(1, 5)))]
+        vals, off = pack(units)
+        p = SegParams(nperm=int(rng.choice([100, 200, 1000])), alpha=float(rng.choice([0.01, 0.05])), hybrid=True,
+                      min_width=int(rng.choice([2, 3])), kmax=int(rng.choice([25, 10])), do_smooth=False,
+                      rng_kind=1 if mode == "philox" else 0, chain=(mode == "mt_chain"), seed=int(rng.integers(1, 100)))
+        check_batch(ctx, oracle, vals, off, p)
+
+
+def test_hybrid_kat_case1(ctx):
+    # tests/cbs_test.cpp:287-307 hybrid rows: lengths 20/20/20, means 0/1.5/0
+    x = np.array([0.0] * 20 + [1.5] * 20 + [0.0] * 20)
+    for alpha, nperm, mw in ((0.01, 200, 2), (0.05, 100, 3)):
+        lengths, means, _ = ctx.segment(x, Params(alpha=alpha, nperm=nperm, hybrid=True, min_width=mw, do_smooth=False, seed=1))
+        assert lengths.tolist() == [20, 20, 20]
+        assert np.allclose(means, [0.0, 1.5, 0.0], atol=1e-9)
