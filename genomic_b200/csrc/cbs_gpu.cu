@@ -18,6 +18,7 @@
 #include "host_math.h"
 #include "kernels.cuh"
 #include "mt_jump.h"
+#include "prune.h"
 #include "smooth.cuh"
 
 using namespace cbsg;
@@ -154,7 +155,6 @@ int validate_params(cbs_gpu_ctx* c, const cbs_gpu_params* p) {
     if (!p) return fail(c, CBS_GPU_ERR_INVALID, "params is NULL");
     if (p->ibin) return fail(c, CBS_GPU_ERR_UNSUPPORTED, "ibin=true is not on the cna segment path and is not implemented");
     if (p->hybrid && (p->kmax < 1 || p->kmax > 128)) return fail(c, CBS_GPU_ERR_UNSUPPORTED, "hybrid: kmax must be in 1..128");
-    if (p->undo_prune) return fail(c, CBS_GPU_ERR_UNSUPPORTED, "undo_prune is not implemented on the GPU path yet");
     if (p->min_width < 1) return fail(c, CBS_GPU_ERR_INVALID, "min_width must be >= 1");
     if (p->nperm < 0) return fail(c, CBS_GPU_ERR_INVALID, "nperm must be >= 0");
     if (!(p->alpha >= 0.0)) return fail(c, CBS_GPU_ERR_INVALID, "alpha must be >= 0");
@@ -546,7 +546,8 @@ struct ResultOwner {
     std::vector<cbs_gpu_split> splits;
 };
 
-int fetch_results(cbs_gpu_ctx* c, const Dev& hD, int n_units, bool want_splits, ResultOwner* R) {
+int fetch_results(cbs_gpu_ctx* c, const Dev& hD, int n_units, bool want_splits, ResultOwner* R, const cbs_gpu_params* prm = nullptr,
+                  const std::vector<long long>* unit_off = nullptr) {
     cudaStream_t st = c->stream;
     const int ns = hD.n_segs;
     std::vector<SegRec> segs((size_t)ns);
@@ -580,6 +581,31 @@ int fetch_results(cbs_gpu_ctx* c, const Dev& hD, int n_units, bool want_splits, 
         R->seg_offsets[(size_t)s.unit + 1]++;
     }
     for (int u = 0; u < n_units; ++u) R->seg_offsets[u + 1] += R->seg_offsets[u];
+    if (prm && prm->undo_prune && unit_off) {
+        // CBS.cpp:1013-1022: prune on the host, then means of the merged segments (sequential sums)
+        const long long N = (*unit_off)[n_units];
+        std::vector<double> hx((size_t)N);
+        if (N) CUDA_TRY(c, cudaMemcpy(hx.data(), c->x.p, sizeof(double) * (size_t)N, cudaMemcpyDeviceToHost));
+        std::vector<int64_t> noff((size_t)n_units + 1, 0);
+        std::vector<int32_t> nlen;
+        std::vector<double> nmean;
+        for (int u = 0; u < n_units; ++u) {
+            std::vector<int> lseg(R->lengths.begin() + R->seg_offsets[u], R->lengths.begin() + R->seg_offsets[u + 1]);
+            const double* xu = hx.data() + (*unit_off)[u];
+            const int n = (int)((*unit_off)[u + 1] - (*unit_off)[u]);
+            if (lseg.size() > 1) lseg = prune_lengths(xu, n, lseg, prm->undo_prune_cutoff);
+            int pos = 0;
+            for (int len : lseg) {
+                double acc = 0.0;
+                for (int i = pos; i < pos + len; ++i) acc += xu[i];
+                nlen.push_back(len);
+                nmean.push_back(acc / (double)len);
+                pos += len;
+            }
+            noff[u + 1] = (int64_t)nlen.size();
+        }
+        R->seg_offsets.swap(noff); R->lengths.swap(nlen); R->means.swap(nmean);
+    }
     R->splits.resize(sp.size());
     for (size_t k = 0; k < sp.size(); ++k) {
         cbs_gpu_split& o = R->splits[k];
@@ -590,7 +616,7 @@ int fetch_results(cbs_gpu_ctx* c, const Dev& hD, int n_units, bool want_splits, 
         o.e_status0 = s.e_status0; o.e_status1 = s.e_status1;
     }
     R->pub.n_units = n_units;
-    R->pub.n_segments = ns;
+    R->pub.n_segments = (int64_t)R->lengths.size();
     R->pub.seg_offsets = R->seg_offsets.data();
     R->pub.lengths = R->lengths.data();
     R->pub.means = R->means.data();
@@ -902,7 +928,7 @@ static int segment_batch_impl(cbs_gpu_ctx* c, const void* values, int dtype, int
     CUDA_TRY(c, cudaEventRecord(c->e3, st));
     ResultOwner* R = new ResultOwner();
     memset(&R->pub, 0, sizeof(R->pub));
-    rc = fetch_results(c, hD, n_units, params->record_splits != 0, R);
+    rc = fetch_results(c, hD, n_units, params->record_splits != 0, R, params, &off);
     if (rc) { delete R; return rc; }
     CUDA_TRY(c, cudaEventRecord(c->e4, st));
     CUDA_TRY(c, cudaEventSynchronize(c->e4));
@@ -1075,7 +1101,7 @@ int cbs_gpu_segment(cbs_gpu_ctx* c, const double* x, int32_t n, const cbs_gpu_pa
     if (rc) return rc;
     ResultOwner R;
     memset(&R.pub, 0, sizeof(R.pub));
-    rc = fetch_results(c, hD, 1, false, &R);
+    rc = fetch_results(c, hD, 1, false, &R, &p, &off);
     if (rc) return rc;
     if (c->profiling) collect_timers(c);
     *n_segments = (int32_t)R.pub.n_segments;

@@ -254,3 +254,24 @@ def test_hybrid_kat_case1(ctx):
         lengths, means, _ = ctx.segment(x, Params(alpha=alpha, nperm=nperm, hybrid=True, min_width=mw, do_smooth=False, seed=1))
         assert lengths.tolist() == [20, 20, 20]
         assert np.allclose(means, [0.0, 1.5, 0.0], atol=1e-9)
+
+
+def test_undo_prune_matches_oracle(ctx, oracle):
+    # undo.splits="prune" (CBS.cpp:266-320): weak extra steps get merged back
+    rng = np.random.default_rng(81)
+    hits = 0
+    for trial in range(10):
+        n = int(rng.integers(400, 1500))
+        x = rng.normal(0, 0.2, n)
+        for _ in range(int(rng.integers(2, 5))):
+            a = int(rng.integers(0, n - 40)); b = int(rng.integers(a + 20, n))
+            x[a:b] += float(rng.choice([0.12, 0.2, 0.5]))
+        vals, off = pack([f32(x)])
+        for cutoff in (0.05, 0.5):
+            p = SegParams(nperm=200, alpha=0.05, do_smooth=False, undo_prune=True, undo_prune_cutoff=cutoff, seed=2)
+            base = oracle.segment_units(vals, off, np.ones(1, np.int32), SegParams(nperm=200, alpha=0.05, do_smooth=False, seed=2))
+            want = oracle.segment_units(vals, off, np.ones(1, np.int32), p)
+            got = ctx.segment_batch(vals, off, gparams(p, undo_prune=True, undo_prune_cutoff=cutoff))
+            assert np.array_equal(got.lengths, want["lengths"]) and np.array_equal(got.means, want["means"])
+            hits += int(len(want["lengths"]) != len(base["lengths"]))
+    assert hits > 0  # pruning actually changed something
