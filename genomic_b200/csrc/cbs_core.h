@@ -150,6 +150,7 @@ struct Task {
     double pval1;    // tailp(sqrt(ostat), (kmax+1)/n, n, 100, tol), written by k_tailp (CBS.cpp:846)
     int raw;         // low-level API (tmaxo/tmaxp): use x as given with the supplied tss, no centring
     int deferred;    // did not get arena space this round
+    int obs_round;   // round in which prep + observed scan were planned (results exist from the next round on)
     double tss;      // written by prep
     // observed scan result (written by scan kernel, LOC mode)
     double ostat;
@@ -284,7 +285,10 @@ struct Dev {
 
 enum { ERR_TASK_CAP = 101, ERR_SEG_CAP = 102, ERR_ARENA = 103, ERR_SPLIT_CAP = 104, ERR_INTERNAL = 105, ERR_STALL = 106, ERR_STREAM_CAP = 107 };
 
-CBS_HD int shuffle_class(int n) { return n <= 4096 ? 0 : n <= 16384 ? 1 : n <= 32768 ? 2 : n <= 65535 ? 3 : 4; }
+// 0,1: 16-bit index array in shared memory (8 KB / 32 KB per permutation, 24 / 6 warps per SM);
+// 4: 32-bit index array in the arena (L2), thousands of permutations in flight.  Classes 2,3 (larger
+// shared-memory arrays, 3 / 1 warps per SM) exist in the kernels but lose to the L2 version on B200.
+CBS_HD int shuffle_class(int n) { return n <= 4096 ? 0 : n <= 16384 ? 1 : 4; }
 
 // ------------------------------------------------------------------------------------
 // Scheduler (runs in ONE thread per round; plain sequential C++ so that the very same
@@ -316,7 +320,7 @@ struct Sched {
         Task& t = D.tasks[idx];
         t.unit = unit; t.lo = lo; t.hi = hi; t.n = hi - lo;
         t.state = TS_NEW; t.next = -1; t.nb = 0; t.alleq = 0; t.raw = 0; t.deferred = 0;
-        t.use_hybrid = (D.prm.hybrid && D.prm.nmin < t.n) ? 1 : 0; t.pval1 = 0.0;
+        t.use_hybrid = (D.prm.hybrid && D.prm.nmin < t.n) ? 1 : 0; t.pval1 = 0.0; t.obs_round = -1;
         t.tss = 0.0; t.ostat = 0.0; t.tmaxi = 0; t.tmaxj = 0;
         t.nrejc = 0; t.perms_done = 0; t.nrej = 0; t.exit_code = EX_NONE; t.batch_P = 0;
         t.cnt_exit = -1; t.cnt_nrej = 0;
@@ -378,6 +382,14 @@ struct Sched {
             int link = below;
             for (int k = 0; k < nk; ++k) { D.tasks[kids[k]].next = link; link = kids[k]; }
             ch->top = link;
+            // The serial RNG stream only orders the PERMUTATION tests.  The observed scan of a pending
+            // segment draws nothing, so the siblings that wait below the top are prepared and scanned
+            // now; when their turn comes they continue from TS_OBS without spending a round on it.
+            for (int k = 0; k + 1 < nk; ++k) {
+                Task& kid = D.tasks[kids[k]];
+                if (kid.n >= 2 * D.prm.min_width && plan_obs(kids[k])) kid.state = TS_OBS;
+                else kid.deferred = 0;
+            }
         } else {
             for (int k = 0; k < nk; ++k) push_out(kids[k]);
         }
@@ -419,6 +431,7 @@ struct Sched {
         D.prep_task[D.n_prep++] = idx;
         PermItem& it = D.items[D.n_items];
         it.task = idx; it.P = 1; it.obs = 1;
+        t.obs_round = D.round;
         D.item_prefix[D.n_items + 1] = D.item_prefix[D.n_items] + 1;
         D.item_uprefix[D.n_items + 1] = D.item_uprefix[D.n_items] + 1;
         D.n_items++;
@@ -621,6 +634,7 @@ struct Sched {
                 return true;
             }
             case TS_OBS: {
+                if (t.obs_round == D.round) return true;  // planned ahead in this very round: kernels have not run yet
                 if (t.alleq) { finish(idx, 0, 0, 0, 0); return false; }  // CBS.cpp:985
                 const double t1 = sqrt(t.ostat);
                 if (t1 <= 0.1) { t.exit_code = EX_SMALL_T; finish(idx, 1, 0, 0, 0); return false; }  // :839

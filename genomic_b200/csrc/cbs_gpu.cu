@@ -143,10 +143,18 @@ struct LaunchTimer {
 };
 
 void collect_timers(cbs_gpu_ctx* c) {
+    const bool dump = getenv("CBS_GPU_DEBUG_ROUNDS") != nullptr;
+    static const char* names[] = {"sched", "gen", "prep", "perm", "scan", "edgeprep", "edgeperm", "means", "smooth", "shuf0", "shuf1", "shuf2", "shuf3", "prefix"};
+    int round = 0;
     for (auto& u : c->ev_used) {
         float ms = 0.f;
         if (cudaEventElapsedTime(&ms, c->ev_pool[u.second], c->ev_pool[u.second + 1]) == cudaSuccess) c->kms[u.first] += ms;
+        if (dump) {
+            if (u.first == K_SCHED) fprintf(stderr, "\n[round %d]", round++);
+            if (ms > 0.05f) fprintf(stderr, " %s=%.2f", names[u.first], ms);
+        }
     }
+    if (dump) fprintf(stderr, "\n");
     c->ev_used.clear();
     c->ev_next = 0;
 }
@@ -429,7 +437,7 @@ int run_cbs(cbs_gpu_ctx* c, const std::vector<long long>& off, const uint64_t* u
     size_t shuf_smem[4]; int shuf_occ[4]; int shuf_limit[4];
     for (int cls = 0; cls < 4; ++cls) {
         shuf_smem[cls] = (size_t)kClsMax[cls] * 2 + 32;
-        shuf_limit[cls] = (cls == 0 || Nmax > kClsMax[cls - 1]) ? 1 : 0;
+        shuf_limit[cls] = (cls < 2 && (cls == 0 || Nmax > kClsMax[cls - 1])) ? 1 : 0;  // classes 2,3 are routed to k_perm (cbs_core.h shuffle_class)
         shuf_occ[cls] = (int)std::max<size_t>(1, std::min<size_t>(32, (c->smem_optin + 1024) / (shuf_smem[cls] + 1024)));
     }
 
@@ -475,7 +483,7 @@ int run_cbs(cbs_gpu_ctx* c, const std::vector<long long>& off, const uint64_t* u
                 LaunchTimer t(c, K_SHUF0 + cls, ss);
                 k_perm_smem<<<c->sm_count * shuf_occ[cls], 32, shuf_smem[cls], ss>>>(dD, cls);
             }
-            if (Nmax > 65535) {
+            if (Nmax > 16384) {
                 cudaStream_t ss = c->side[4];
                 cudaStreamWaitEvent(ss, c->ev_gen, 0);
                 used_side[4] = true;

@@ -321,12 +321,15 @@ __device__ void perm_warp(Dev* D, const Task& t, int p, Idx s_idx, int lane) {
     for (int k = lane; k < n; k += 32) s_idx.st(k, k);
     __syncwarp();
     int i0 = n;
+    uint64_t raw_next = (mt && n >= 64) ? win[lane] : 0;  // software pipeline: the next group's raw word is in flight
     for (; i0 >= 64; i0 -= 32) {
         const int i = i0 - lane;          // this lane's step, rows i-1
         const uint32_t kd = (uint32_t)(n - i);
         uint64_t u;
-        if (mt) u = mt_temper(win[kd]);
-        else {
+        if (mt) {
+            u = mt_temper(raw_next);
+            if (i0 - 32 >= 64) raw_next = win[kd + 32];
+        } else {
             uint32_t o[4];
             philox4x32_10(kd >> 1, permno, 0u, 0u, k0, k1, o);
             u = (kd & 1u) ? (((uint64_t)o[3] << 32) | o[2]) : (((uint64_t)o[1] << 32) | o[0]);
@@ -368,9 +371,15 @@ __device__ void perm_warp(Dev* D, const Task& t, int p, Idx s_idx, int lane) {
     double* sx = D->arena + t.off_sx + (long long)p * Sched::sx_stride(n);
     if (lane == 0) sx[0] = 0.0;
     int k = lane;
-    for (; k + 96 < n; k += 128) {
-        const double v0 = cur[s_idx.ld(k)], v1 = cur[s_idx.ld(k + 32)], v2 = cur[s_idx.ld(k + 64)], v3 = cur[s_idx.ld(k + 96)];
-        sx[k + 1] = v0; sx[k + 33] = v1; sx[k + 65] = v2; sx[k + 97] = v3;
+    for (; k + 224 < n; k += 256) {
+        int id[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) id[q] = s_idx.ld(k + 32 * q);
+        double v[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) v[q] = cur[id[q]];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) sx[k + 1 + 32 * q] = v[q];
     }
     for (; k < n; k += 32) sx[k + 1] = cur[s_idx.ld(k)];
     __syncwarp();
