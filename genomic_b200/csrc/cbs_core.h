@@ -269,10 +269,12 @@ struct Dev {
     int n_edgeprep; int* edgeprep_task;
     int n_edge;   EdgeItem* edges; int* edge_prefix;  // exclusive prefix of threads, [n_edge+1]
     int n_gen;    int* gen_chain;
-    // shuffle work lists by segment-length class (index arrays of the shared-memory shuffle):
-    // 0: n<=4096  1: n<=16384  2: n<=32768  3: n<=65535  4: longer (global-memory kernel)
-    int n_shuf[5]; int* shuf_item[5]; int* shuf_prefix[5];
-    unsigned ctr[12];  // work-stealing counters (reset every round)
+    // shuffle work lists by segment-length class (shuffle_class below): 0..6 index arrays in shared
+    // memory (16-bit), 7 = longer than 65535 markers (32-bit index array in the arena)
+    int n_shuf[8]; int* shuf_item[8]; int* shuf_prefix[8];
+    // work-stealing counters (reset every round): 0 global shuffle, 1 scan, 2 edge, 3 prefix, 4 hscan,
+    // 8+cls shared-memory shuffle of class cls
+    unsigned ctr[16];
     // ---- status -----------------------------------------------------------------------
     int done;
     int stall;  // consecutive rounds with live tasks but no planned work
@@ -285,10 +287,17 @@ struct Dev {
 
 enum { ERR_TASK_CAP = 101, ERR_SEG_CAP = 102, ERR_ARENA = 103, ERR_SPLIT_CAP = 104, ERR_INTERNAL = 105, ERR_STALL = 106, ERR_STREAM_CAP = 107 };
 
-// 0,1: 16-bit index array in shared memory (8 KB / 32 KB per permutation, 24 / 6 warps per SM);
-// 4: 32-bit index array in the arena (L2), thousands of permutations in flight.  Classes 2,3 (larger
-// shared-memory arrays, 3 / 1 warps per SM) exist in the kernels but lose to the L2 version on B200.
-CBS_HD int shuffle_class(int n) { return n <= 4096 ? 0 : n <= 16384 ? 1 : 4; }
+// Shuffle classes.  0..6: the permutation is built on a 16-bit index array in shared memory, one warp per
+// permutation; the class fixes the array size, hence how many permutations an SM holds at once
+// (24 / 13 / 6 / 4 / 3 / 2 / 1).  7: 32-bit index array in the arena (L2 / HBM latency per step).
+enum { SHUF_NCLS = 8, SHUF_GLOBAL = 7 };
+CBS_HD int shuffle_class_max(int cls) {
+    return cls == 0 ? 4096 : cls == 1 ? 8192 : cls == 2 ? 16384 : cls == 3 ? 24576 : cls == 4 ? 32768 : cls == 5 ? 49152 : 65535;
+}
+CBS_HD int shuffle_class(int n) {
+    for (int cls = 0; cls < SHUF_GLOBAL; ++cls) if (n <= shuffle_class_max(cls)) return cls;
+    return SHUF_GLOBAL;
+}
 
 // ------------------------------------------------------------------------------------
 // Scheduler (runs in ONE thread per round; plain sequential C++ so that the very same
@@ -352,7 +361,10 @@ struct Sched {
 
     // arena helpers ---------------------------------------------------------------------
     CBS_HD static long long sx_stride(int n) { return ((long long)n + 1 + 3) & ~3LL; }
-    CBS_HD static long long bs_stride(int nb) { return 3LL * nb + 4; }
+    CBS_HD static long long bs_stride(int nb) { return (3LL * nb + 4 + 3) & ~3LL; }
+    // 32-bit index array of the global-memory shuffle, in doubles; all strides are multiples of 4 doubles so
+    // that every row of prefix sums starts on a 32-byte boundary (k_prefix moves rows with 128-bit accesses)
+    CBS_HD static long long idx_stride(int n) { return (((long long)n + 1) / 2 + 1 + 3) & ~3LL; }
 
     // Task finished with `ncpt` change points at 0-based icpt (relative to lo):
     // emits the final segment or creates the children (CBS.cpp:996-1004).
@@ -454,8 +466,8 @@ struct Sched {
         if (want > p.max_batch) want = p.max_batch;
         if (want > p.nperm - t.perms_done) want = p.nperm - t.perms_done;
         const int cls = shuffle_class(t.n);
-        // the global-memory shuffle (class 4) keeps a 32-bit index array per permutation in the arena
-        const long long idxd = (cls == 4) ? ((long long)t.n + 1) / 2 + 1 : 0;  // doubles per permutation
+        // the global-memory shuffle keeps a 32-bit index array per permutation in the arena
+        const long long idxd = (cls == SHUF_GLOBAL) ? idx_stride(t.n) : 0;  // doubles per permutation
         const long long per = idxd + sx_stride(t.n) + bs_stride(t.nb);
         const bool mtwin = p.rng_mode == RNG_MT && !D.shared_stream;
         // never let one task take more than half of the arena
@@ -488,7 +500,7 @@ struct Sched {
                 draws_used += dneed + 312;  // the generator appends the 312 words that follow the window
             }
         }
-        t.off_A = (cls == 4) ? arena_used : -1;
+        t.off_A = (cls == SHUF_GLOBAL) ? arena_used : -1;
         t.off_sx = arena_used + idxd * want;
         t.off_bs = t.off_sx + sx_stride(t.n) * want;
         arena_used += need;
@@ -711,8 +723,8 @@ struct Sched {
         n_out = 0;
         D.n_prep = 0; D.n_items = 0; D.n_edgeprep = 0; D.n_edge = 0; D.n_gen = 0;
         D.item_prefix[0] = 0; D.item_uprefix[0] = 0; D.edge_prefix[0] = 0;
-        for (int k = 0; k < 5; ++k) { D.n_shuf[k] = 0; D.shuf_prefix[k][0] = 0; }
-        for (int k = 0; k < 12; ++k) D.ctr[k] = 0;
+        for (int k = 0; k < SHUF_NCLS; ++k) { D.n_shuf[k] = 0; D.shuf_prefix[k][0] = 0; }
+        for (int k = 0; k < 16; ++k) D.ctr[k] = 0;
         arena_used = 0; rej_used = 0; draws_used = 0;
         const bool mt = D.prm.rng_mode == RNG_MT;
         if (D.shared_stream && D.gen_E > 0) { D.stream_len = D.gen_base + D.gen_E; D.gen_E = 0; }

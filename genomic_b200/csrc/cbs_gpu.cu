@@ -297,7 +297,7 @@ int run_cbs(cbs_gpu_ctx* c, const std::vector<long long>& off, const uint64_t* u
     ENSURE(c, c->edges, sizeof(EdgeItem) * (size_t)cap.list_cap);
     ENSURE(c, c->edge_prefix, sizeof(int) * (size_t)(cap.list_cap + 1));
     ENSURE(c, c->gen_chain, sizeof(int) * (size_t)(n_chains + 1));
-    ENSURE(c, c->shuf, sizeof(int) * 11 * (size_t)(cap.list_cap + 1));
+    ENSURE(c, c->shuf, sizeof(int) * (2 * SHUF_NCLS + 1) * (size_t)(cap.list_cap + 1));
     ENSURE(c, c->means, sizeof(double) * (size_t)cap.seg_cap);
     ENSURE(c, c->seed312, sizeof(uint64_t) * 312);
     ENSURE(c, c->dev, sizeof(Dev));
@@ -364,11 +364,11 @@ int run_cbs(cbs_gpu_ctx* c, const std::vector<long long>& off, const uint64_t* u
     hD.prep_task = c->prep_task.as<int>(); hD.items = c->items.as<PermItem>(); hD.item_prefix = c->item_prefix.as<int>();
     hD.edgeprep_task = c->edgeprep_task.as<int>(); hD.edges = c->edges.as<EdgeItem>(); hD.edge_prefix = c->edge_prefix.as<int>();
     hD.gen_chain = c->gen_chain.as<int>();
-    for (int k = 0; k < 5; ++k) {
+    for (int k = 0; k < SHUF_NCLS; ++k) {
         hD.shuf_item[k] = c->shuf.as<int>() + (size_t)(2 * k) * (cap.list_cap + 1);
         hD.shuf_prefix[k] = c->shuf.as<int>() + (size_t)(2 * k + 1) * (cap.list_cap + 1);
     }
-    hD.item_uprefix = c->shuf.as<int>() + (size_t)10 * (cap.list_cap + 1);
+    hD.item_uprefix = c->shuf.as<int>() + (size_t)(2 * SHUF_NCLS) * (cap.list_cap + 1);
     hD.shared_stream = shared_stream ? 1 : 0;
     hD.stream = c->stream_buf.as<uint64_t>();
     hD.stream_cap = shared_stream ? (long long)(c->stream_buf.cap / 8) : 0;
@@ -433,13 +433,13 @@ int run_cbs(cbs_gpu_ctx* c, const std::vector<long long>& off, const uint64_t* u
     const int scan_grid = c->sm_count * scan_occ;
 
     // shared-memory shuffle kernel, one launch per segment-length class present in this call
-    static const int kClsMax[4] = {4096, 16384, 32768, 65535};
-    size_t shuf_smem[4]; int shuf_occ[4]; int shuf_limit[4];
-    for (int cls = 0; cls < 4; ++cls) {
-        shuf_smem[cls] = (size_t)kClsMax[cls] * 2 + 32;
-        shuf_limit[cls] = (cls < 2 && (cls == 0 || Nmax > kClsMax[cls - 1])) ? 1 : 0;  // classes 2,3 are routed to k_perm (cbs_core.h shuffle_class)
+    size_t shuf_smem[SHUF_GLOBAL]; int shuf_occ[SHUF_GLOBAL]; bool shuf_on[SHUF_GLOBAL];
+    for (int cls = 0; cls < SHUF_GLOBAL; ++cls) {
+        shuf_smem[cls] = (size_t)shuffle_class_max(cls) * 2 + 32 + PERM_CHUNK * sizeof(double);
+        shuf_on[cls] = (cls == 0) || Nmax > shuffle_class_max(cls - 1);  // no unit is long enough otherwise
         shuf_occ[cls] = (int)std::max<size_t>(1, std::min<size_t>(32, (c->smem_optin + 1024) / (shuf_smem[cls] + 1024)));
     }
+    static const int kShufTimer[SHUF_GLOBAL] = {K_SHUF0, K_SHUF1, K_SHUF1, K_SHUF2, K_SHUF2, K_SHUF3, K_SHUF3};
 
     // ---- rounds -------------------------------------------------------------------------------
     *c->h_done = 0;
@@ -451,16 +451,16 @@ int run_cbs(cbs_gpu_ctx* c, const std::vector<long long>& off, const uint64_t* u
         for (int r = 0; r < G; ++r) {
             // One round.  Dependencies: everything after k_sched; shuffles after the generator;
             // k_prefix after the shuffles; k_scan after k_prefix and k_prep; next k_sched after all.
-            //   main : sched, gen, [shuffle class 3 | global], prefix, scan
+            //   main : sched, gen, [shuffle classes], prefix, scan
             //   side0: prep            side1: edgeprep, edgeperm
-            //   side2: shuffle class 0,1      side3: shuffle class 2      side4: shuffle global (if class 3 on main)
+            //   side2, side3: other shuffle classes      side4: shuffle of segments > 65535 markers
             { LaunchTimer t(c, K_SCHED); k_sched<<<1, 256, 0, st>>>(dD, c->d_done); }
             cudaEventRecord(c->ev_sched, st);
             cudaStreamWaitEvent(c->side[0], c->ev_sched, 0);
-            { LaunchTimer t(c, K_PREP, c->side[0]); k_prep<<<c->sm_count * 2, 128, 0, c->side[0]>>>(dD); }
+            { LaunchTimer t(c, K_PREP, c->side[0]); k_prep<<<c->sm_count * 8, 32, 0, c->side[0]>>>(dD); }
             cudaEventRecord(c->ev_side[0], c->side[0]);
             cudaStreamWaitEvent(c->side[1], c->ev_sched, 0);
-            { LaunchTimer t(c, K_EDGEPREP, c->side[1]); k_edgeprep<<<c->sm_count, 128, 0, c->side[1]>>>(dD); }
+            { LaunchTimer t(c, K_EDGEPREP, c->side[1]); k_edgeprep<<<c->sm_count * 4, 32, 0, c->side[1]>>>(dD); }
             { LaunchTimer t(c, K_EDGEPERM, c->side[1]); k_edgeperm<<<c->sm_count * 4, 128, 0, c->side[1]>>>(dD); }
             cudaEventRecord(c->ev_side[1], c->side[1]);
             if (mt) {
@@ -471,31 +471,28 @@ int run_cbs(cbs_gpu_ctx* c, const std::vector<long long>& off, const uint64_t* u
                 } else k_gen<<<std::min(std::max(1, n_chains), c->sm_count * 4), 192, 0, st>>>(dD);
             }
             cudaEventRecord(c->ev_gen, st);
-            // shuffles: the largest class present stays on the main stream, the others go to side streams
-            int main_cls = -1;
-            for (int cls = 3; cls >= 0; --cls) if (shuf_limit[cls]) { main_cls = cls; break; }
+            // shuffles: classes alternate between the main stream and three side streams so that they run
+            // concurrently (each class is latency bound on its own); the longest present class goes first
             bool used_side[5] = {false, false, false, false, false};
-            for (int cls = 0; cls < 4; ++cls) {
-                if (shuf_limit[cls] == 0 || cls == main_cls) continue;  // no unit is long enough for this class
-                const int sidx = (cls <= 1) ? 2 : 3;
-                cudaStream_t ss = c->side[sidx];
-                if (!used_side[sidx]) { cudaStreamWaitEvent(ss, c->ev_gen, 0); used_side[sidx] = true; }
-                LaunchTimer t(c, K_SHUF0 + cls, ss);
-                k_perm_smem<<<c->sm_count * shuf_occ[cls], 32, shuf_smem[cls], ss>>>(dD, cls);
-            }
-            if (Nmax > 16384) {
-                cudaStream_t ss = c->side[4];
-                cudaStreamWaitEvent(ss, c->ev_gen, 0);
-                used_side[4] = true;
-                LaunchTimer t(c, K_PERM, ss);
-                k_perm<<<c->sm_count * 8, 128, 0, ss>>>(dD);
-            }
-            if (main_cls >= 0) {
-                LaunchTimer t(c, K_SHUF0 + main_cls);
-                k_perm_smem<<<c->sm_count * shuf_occ[main_cls], 32, shuf_smem[main_cls], st>>>(dD, main_cls);
+            {
+                int slot = 0;
+                if (Nmax > 65535) {
+                    cudaStream_t ss = c->side[4];
+                    cudaStreamWaitEvent(ss, c->ev_gen, 0);
+                    used_side[4] = true;
+                    LaunchTimer t(c, K_PERM, ss);
+                    k_perm<<<c->sm_count * 8, 128, 0, ss>>>(dD);
+                }
+                for (int cls = SHUF_GLOBAL - 1; cls >= 0; --cls) {
+                    if (!shuf_on[cls]) continue;
+                    const int where = slot++ % 3;  // 0 = main stream, 1,2 = side[2], side[3]
+                    cudaStream_t ss = where == 0 ? st : c->side[1 + where];
+                    if (where != 0 && !used_side[1 + where]) { cudaStreamWaitEvent(ss, c->ev_gen, 0); used_side[1 + where] = true; }
+                    LaunchTimer t(c, kShufTimer[cls], ss);
+                    k_perm_smem<<<c->sm_count * shuf_occ[cls], 32, shuf_smem[cls], ss>>>(dD, cls);
+                }
             }
             for (int k = 2; k < 5; ++k) if (used_side[k]) { cudaEventRecord(c->ev_side[k], c->side[k]); cudaStreamWaitEvent(st, c->ev_side[k], 0); }
-            { LaunchTimer t(c, K_PREFIX); k_prefix<<<c->sm_count * 6, PFX_WARPS * 32, 0, st>>>(dD); }
             cudaStreamWaitEvent(st, c->ev_side[0], 0);
             { LaunchTimer t(c, K_SCAN); k_scan<<<scan_grid, lay.warps * 32, scan_smem, st>>>(dD, lay); }
             if (p->hybrid) {
@@ -539,7 +536,7 @@ int run_cbs(cbs_gpu_ctx* c, const std::vector<long long>& off, const uint64_t* u
     }
     if (hD.n_segs > 0) {
         LaunchTimer t(c, K_MEANS);
-        k_means<<<std::min((hD.n_segs + 3) / 4, c->sm_count * 8), 128, 0, st>>>(dD, c->means.as<double>());
+        k_means<<<std::min(hD.n_segs, c->sm_count * 8), 32, 0, st>>>(dD, c->means.as<double>());
     }
     CUDA_TRY(c, cudaGetLastError());
     return CBS_GPU_OK;
@@ -782,8 +779,8 @@ int cbs_gpu_measure_fp64(cbs_gpu_ctx* c, double* tera_inst_per_s) {
         CUDA_TRY(c, cudaEventSynchronize(c->e1));
         float ms = 0.f;
         cudaEventElapsedTime(&ms, c->e0, c->e1);
-        // per thread: iters * 4 * 8 * 2 FP64 instructions
-        const double inst = (double)grid * block * (double)iters * 64.0;
+        // per thread: iters * 4 * 8 DADD
+        const double inst = (double)grid * block * (double)iters * 32.0;
         if (rep > 0 && ms > 0.f) best = std::max(best, inst / (ms * 1e-3) / 1e12);
     }
     *tera_inst_per_s = best;
@@ -853,7 +850,7 @@ static int run_raw_scan(cbs_gpu_ctx* c, const double* xh, int n, int count, doub
     while (lay.warps > 1 && lay.bytes() > c->smem_optin) lay.warps >>= 1;
     if (lay.bytes() > c->smem_optin) return fail(c, CBS_GPU_ERR_UNSUPPORTED, "vector too long for the scan kernel's shared memory");
     Dev* dD = c->dev.as<Dev>();
-    k_prep<<<std::min((count + 3) / 4, c->sm_count * 4), 128, 0, st>>>(dD);
+    k_prep<<<std::min(count, c->sm_count * 8), 32, 0, st>>>(dD);
     k_scan<<<std::min(count, c->sm_count * 2), lay.warps * 32, lay.bytes(), st>>>(dD, lay);
     CUDA_TRY(c, cudaGetLastError());
     tasks_out.resize((size_t)count);
