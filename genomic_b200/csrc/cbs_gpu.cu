@@ -241,6 +241,23 @@ int smooth_device(cbs_gpu_ctx* c, const double* xin, const long long* goff, cons
     return CBS_GPU_OK;
 }
 
+// warps per scan CTA: the per-block tables are per CTA, the staging buffers per warp; take the CTA shape that
+// keeps the most warps resident on an SM (12 warps x 2 CTAs for SNP6-scale chromosomes, 8 x 3 for short units)
+bool pick_scan_warps(cbs_gpu_ctx* c, ScanLayout& lay, int* occ_out) {
+    int best_w = 0, best_res = 0, best_occ = 1;
+    for (int w : {12, 8, 4, 2, 1}) {
+        lay.warps = w;
+        if (lay.bytes() > c->smem_optin) continue;
+        int occ = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_scan, w * 32, lay.bytes()) != cudaSuccess) { cudaGetLastError(); continue; }
+        if (occ * w > best_res || (occ * w == best_res && w == 8)) { best_res = occ * w; best_w = w; best_occ = occ; }
+    }
+    if (!best_w) return false;
+    lay.warps = best_w;
+    if (occ_out) *occ_out = std::max(1, best_occ);
+    return true;
+}
+
 struct RunCaps {
     int task_cap, list_cap, seg_cap, split_cap, max_live;
     long long arena_cap, draws_cap, rej_cap;
@@ -423,13 +440,9 @@ int run_cbs(cbs_gpu_ctx* c, const std::vector<long long>& off, const uint64_t* u
         bmax = std::max(bmax, 50);
         lay.B_max = bmax;
     }
-    lay.warps = 8;
-    while (lay.warps > 1 && lay.bytes() > c->smem_optin) lay.warps >>= 1;
-    if (lay.bytes() > c->smem_optin) return fail(c, CBS_GPU_ERR_UNSUPPORTED, "segment too long for the scan kernel's shared memory");
-    const size_t scan_smem = lay.bytes();
     int scan_occ = 1;
-    CUDA_TRY(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&scan_occ, k_scan, lay.warps * 32, scan_smem));
-    scan_occ = std::max(1, scan_occ);
+    if (!pick_scan_warps(c, lay, &scan_occ)) return fail(c, CBS_GPU_ERR_UNSUPPORTED, "segment too long for the scan kernel's shared memory");
+    const size_t scan_smem = lay.bytes();
     const int scan_grid = c->sm_count * scan_occ;
 
     // shared-memory shuffle kernel, one launch per segment-length class present in this call
@@ -846,9 +859,7 @@ static int run_raw_scan(cbs_gpu_ctx* c, const double* xh, int n, int count, doub
     ScanLayout lay;
     lay.nb_max = nb + 1;
     lay.B_max = std::max(std::max((n + nb - 1) / nb + 2, (int)std::sqrt((double)n) + 4), 50);
-    lay.warps = 8;
-    while (lay.warps > 1 && lay.bytes() > c->smem_optin) lay.warps >>= 1;
-    if (lay.bytes() > c->smem_optin) return fail(c, CBS_GPU_ERR_UNSUPPORTED, "vector too long for the scan kernel's shared memory");
+    if (!pick_scan_warps(c, lay, nullptr)) return fail(c, CBS_GPU_ERR_UNSUPPORTED, "vector too long for the scan kernel's shared memory");
     Dev* dD = c->dev.as<Dev>();
     k_prep<<<std::min(count, c->sm_count * 8), 32, 0, st>>>(dD);
     k_scan<<<std::min(count, c->sm_count * 2), lay.warps * 32, lay.bytes(), st>>>(dD, lay);

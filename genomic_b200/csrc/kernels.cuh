@@ -327,6 +327,33 @@ struct IdxGlobal {
     __device__ __forceinline__ void st(int k, int v) const { __stcg(a + k, (unsigned int)v); }
 };
 
+// 32 consecutive Fisher-Yates steps (CBS.cpp:489-492) taken by the 32 lanes at once: lane l swaps row i-1
+// (i = i0-l) with row j-1.  A step commutes with the others of its group unless it shares a row with one of
+// them; those few (match.any on j, or a target inside the group's own rows) are replayed in order afterwards.
+template <class Idx>
+__device__ __forceinline__ void fy_group(Idx s_idx, int i0, int i, int j, int lane) {
+    const unsigned same = __match_any_sync(FULL, j);
+    const int m = i0 - j;  // lane whose row is my target
+    const bool tgt = (m >= 0) && (m < 32) && (m != lane);
+    const unsigned tmask = __reduce_or_sync(FULL, tgt ? (1u << m) : 0u);
+    const bool conflict = (__popc(same) > 1) || tgt || ((tmask >> lane) & 1u);
+    int vi = 0, vj = 0;
+    if (!conflict) { vi = s_idx.ld(i - 1); vj = s_idx.ld(j - 1); }
+    __syncwarp();
+    if (!conflict) { s_idx.st(i - 1, vj); s_idx.st(j - 1, vi); }
+    __syncwarp();
+    unsigned cm = __ballot_sync(FULL, conflict);
+    while (cm) {
+        const int l = __ffs(cm) - 1;
+        cm &= cm - 1;
+        if (lane == l) {
+            const int a = s_idx.ld(i - 1), b = s_idx.ld(j - 1);
+            s_idx.st(i - 1, b); s_idx.st(j - 1, a);
+        }
+        __syncwarp();
+    }
+}
+
 #define PERM_CHUNK 512
 template <class Idx>
 __device__ void perm_warp(Dev* D, const Task& t, int p, Idx s_idx, double* buf, int lane) {
@@ -339,49 +366,59 @@ __device__ void perm_warp(Dev* D, const Task& t, int p, Idx s_idx, double* buf, 
     const uint32_t k0 = (uint32_t)t.key, k1 = (uint32_t)(t.key >> 32), permno = (uint32_t)(t.perms_done + p);
     for (int k = lane; k < n; k += 32) s_idx.st(k, k);
     __syncwarp();
+    // groups of 32 steps while i0 >= 64; group g covers steps i = n-32g .. n-32g-31, lane l takes i = n-32g-l
+    // and draw number 32g+l of this permutation
+    const int G = (n >= 64) ? ((n - 64) / 32 + 1) : 0;
     int i0 = n;
-    uint64_t raw_next = (mt && n >= 64) ? win[lane] : 0;  // software pipeline: the next group's raw word is in flight
-    for (; i0 >= 64; i0 -= 32) {
-        const int i = i0 - lane;          // this lane's step, rows i-1
-        const uint32_t kd = (uint32_t)(n - i);
-        uint64_t u;
-        if (mt) {
-            u = mt_temper(raw_next);
-            if (i0 - 32 >= 64) raw_next = win[kd + 32];
-        } else {
-            uint32_t o[4];
-            philox4x32_10(kd >> 1, permno, 0u, 0u, k0, k1, o);
-            u = (kd & 1u) ? (((uint64_t)o[3] << 32) | o[2]) : (((uint64_t)o[1] << 32) | o[0]);
+    if (mt) {
+        // the raw words of the next 8 groups are in flight (registers) while 8 groups are shuffled: the
+        // stream lives in HBM / L2, one load per group would expose its latency in every group
+        uint64_t raw[8], nxt[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) raw[q] = (q < G) ? win[32 * q + lane] : 0ull;
+        for (int g0 = 0; g0 < G; g0 += 8) {
+#pragma unroll
+            for (int q = 0; q < 8; ++q) { const int g = g0 + 8 + q; nxt[q] = (g < G) ? win[32 * g + lane] : 0ull; }
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                if (g0 + q < G) {
+                    const int i = i0 - lane;
+                    fy_group(s_idx, i0, i, draw_index(mt_temper(raw[q]), i), lane);
+                    i0 -= 32;
+                }
+            }
+#pragma unroll
+            for (int q = 0; q < 8; ++q) raw[q] = nxt[q];
         }
-        const int j = draw_index(u, i);
-        const unsigned same = __match_any_sync(FULL, j);
-        const int m = i0 - j;  // lane whose row is my target
-        const bool tgt = (m >= 0) && (m < 32) && (m != lane);
-        const unsigned tmask = __reduce_or_sync(FULL, tgt ? (1u << m) : 0u);
-        const bool conflict = (__popc(same) > 1) || tgt || ((tmask >> lane) & 1u);
-        int vi = 0, vj = 0;
-        if (!conflict) { vi = s_idx.ld(i - 1); vj = s_idx.ld(j - 1); }
-        __syncwarp();
-        if (!conflict) { s_idx.st(i - 1, vj); s_idx.st(j - 1, vi); }
-        __syncwarp();
-        unsigned cm = __ballot_sync(FULL, conflict);
-        while (cm) {
-            const int l = __ffs(cm) - 1;
-            cm &= cm - 1;
-            if (lane == l) {
+        // tail (i0 < 64 steps): the remaining raw words are loaded once, lane 0 replays the steps
+        const uint64_t w0 = (lane < i0) ? win[32 * G + lane] : 0ull;
+        const uint64_t w1 = (32 + lane < i0) ? win[32 * G + 32 + lane] : 0ull;
+        for (int tt = 0; tt < i0; ++tt) {
+            const uint64_t rw = __shfl_sync(FULL, (tt < 32) ? w0 : w1, tt & 31);
+            if (lane == 0) {
+                const int i = i0 - tt;
+                const int j = draw_index(mt_temper(rw), i);
                 const int a = s_idx.ld(i - 1), b = s_idx.ld(j - 1);
                 s_idx.st(i - 1, b); s_idx.st(j - 1, a);
             }
-            __syncwarp();
         }
-    }
-    if (lane == 0) {
-        DrawSrc src;
-        if (mt) src.init_mt(win); else src.init_philox(t.key, 0u, permno);
-        for (int i = i0; i >= 1; --i) {
-            const int j = draw_index(src.u64((uint32_t)(n - i)), i);
-            const int a = s_idx.ld(i - 1), b = s_idx.ld(j - 1);
-            s_idx.st(i - 1, b); s_idx.st(j - 1, a);
+    } else {
+        for (int g = 0; g < G; ++g, i0 -= 32) {
+            const int i = i0 - lane;
+            const uint32_t kd = (uint32_t)(n - i);
+            uint32_t o[4];
+            philox4x32_10(kd >> 1, permno, 0u, 0u, k0, k1, o);
+            const uint64_t u = (kd & 1u) ? (((uint64_t)o[3] << 32) | o[2]) : (((uint64_t)o[1] << 32) | o[0]);
+            fy_group(s_idx, i0, i, draw_index(u, i), lane);
+        }
+        if (lane == 0) {
+            DrawSrc src;
+            src.init_philox(t.key, 0u, permno);
+            for (int i = i0; i >= 1; --i) {
+                const int j = draw_index(src.u64((uint32_t)(n - i)), i);
+                const int a = s_idx.ld(i - 1), b = s_idx.ld(j - 1);
+                s_idx.st(i - 1, b); s_idx.st(j - 1, a);
+            }
         }
     }
     __syncwarp();
@@ -527,8 +564,9 @@ struct PairGeo {
 
 __device__ __forceinline__ void pair_from_index(int q, int nb, int& bi, int& bj) {
     // rows bi = 1..nb, row r (0-based) starts at r*nb - r*(r-1)/2
-    const double t = 2.0 * nb + 1.0;
-    int r = (int)((t - sqrt(t * t - 8.0 * (double)q)) * 0.5);
+    // single precision estimate (all quantities are integers below 2^24), corrected exactly below
+    const float t = 2.0f * (float)nb + 1.0f;
+    int r = (int)((t - __fsqrt_rn(t * t - 8.0f * (float)q)) * 0.5f);
     if (r < 0) r = 0;
     if (r > nb - 1) r = nb - 1;
     while (r + 1 <= nb - 1 && (long long)(r + 1) * nb - (long long)(r + 1) * r / 2 <= q) ++r;
@@ -622,9 +660,54 @@ __device__ void scan_unit_exact(const ScanCtx& c, const PairGeo& g, const double
     }
 }
 
-// scan one arc-length band [La, Lb] of a staged block pair with the whole warp
-__device__ void scan_band(const ScanCtx& c, const PairGeo& g, const double* sa, const double* sbs, int* s_rowpre, int La,
-                          int Lb, int side, ScanSmem* sm, int lane) {
+// per-warp scratch of the unit-level bounds (single precision, rounded outwards)
+struct UnitStats {
+    float* wmin; float* wmax;  // extrema of the five 8-groups of the j buffer a unit reads, by first group
+    float* rmin; float* rmax;  // extrema of every 32-row group of the i buffer
+    int* queue;                // surviving units of the band (64 entries)
+};
+
+// extrema used to discard whole 8-diagonal x 32-position units before any arc is examined
+__device__ void unit_stats(const PairGeo& g, const double* sa, const double* sbs, const UnitStats& us, int lane) {
+    const int nf = g.Bj + SCAN_PAD_HI + SCAN_PAD_LO;
+    const int NG = (nf >> 3) + 1;
+    const float finf = __int_as_float(0x7f800000);
+    for (int gi = lane; gi < NG; gi += 32) {
+        double lo = __longlong_as_double(0x7ff0000000000000LL), hi = -lo;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            if (8 * gi + k <= nf) { const double v = sbs[9 * gi + k]; lo = fmin(lo, v); hi = fmax(hi, v); }
+        }
+        us.wmin[gi] = __double2float_rd(lo); us.wmax[gi] = __double2float_ru(hi);
+    }
+    __syncwarp();
+    float wl[5], wh[5];  // NG <= 136 for the longest supported unit (1,000,000 markers)
+#pragma unroll
+    for (int t = 0; t < 5; ++t) {
+        const int gi = lane + 32 * t;
+        wl[t] = finf; wh[t] = -finf;
+        if (gi < NG) {
+            for (int k = 0; k < 5 && gi + k < NG; ++k) { wl[t] = fminf(wl[t], us.wmin[gi + k]); wh[t] = fmaxf(wh[t], us.wmax[gi + k]); }
+        }
+    }
+    __syncwarp();
+#pragma unroll
+    for (int t = 0; t < 5; ++t) { const int gi = lane + 32 * t; if (gi < NG) { us.wmin[gi] = wl[t]; us.wmax[gi] = wh[t]; } }
+    const int nrows = (g.Bi + 31) >> 5;
+    if (lane < nrows) {
+        double lo = __longlong_as_double(0x7ff0000000000000LL), hi = -lo;
+        for (int u = 32 * lane; u < 32 * lane + 32; ++u) { const double v = sa[u]; lo = fmin(lo, v); hi = fmax(hi, v); }
+        us.rmin[lane] = __double2float_rd(lo); us.rmax[lane] = __double2float_ru(hi);
+    }
+    __syncwarp();
+}
+
+// scan one arc-length band [La, Lb] of a staged block pair with the whole warp.  Work unit: 8 diagonals x
+// 32 positions.  A unit is first tested against the level with the extrema of the values it would read
+// (|S_j - S_i| <= max(maxJ - minI, maxI - minJ)); the survivors are compacted through a small queue so
+// that all 32 lanes examine arcs.
+__device__ void scan_band(const ScanCtx& c, const PairGeo& g, const double* sa, const double* sbs, int* s_rowpre,
+                          const UnitStats& us, int La, int Lb, int side, ScanSmem* sm, int lane) {
     // diagonals d = L - D0; 8-aligned diagonal groups q8 (d in [8*q8, 8*q8+7]); 32-aligned u rows
     const int dLo = La - g.D0, dHi = Lb - g.D0;
     const int qLo = dLo >> 3, qHi = dHi >> 3;  // arithmetic shift == floor
@@ -645,75 +728,109 @@ __device__ void scan_band(const ScanCtx& c, const PairGeo& g, const double* sa, 
     __syncwarp();
     s_rowpre[lane] = incl - cnt;  // exclusive
     if (lane == 0) s_rowpre[32] = total;
-    if (c.slots && lane == 0) atomicAdd(c.slots, (unsigned long long)total * 256ull);
-    unsigned long long my_arcs = 0;
+    unsigned long long my_arcs = 0, my_slots = 0;
     __syncwarp();
-    for (int idx = lane; idx < total; idx += 32) {
-        // row lookup
-        int lo = 0, hi = 32;
-        while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (s_rowpre[mid] <= idx) lo = mid; else hi = mid; }
-        const int r = lo;
-        // row's first group: recompute (cheap) instead of storing
-        const int rqa = max(qLo, -4 * r - 4);
-        const int q8 = rqa + (idx - s_rowpre[r]);
-        const int dq = q8 * 8, u0 = r * 32;
-        if (c.arcs) {
-            for (int k = 0; k < 8; ++k) {
-                const int d = dq + k, L = g.D0 + d;
-                if (L < La || L > Lb) continue;
-                const int a0 = max(u0, max(0, -d)), a1 = min(u0 + 31, min(g.Bi - 1, g.Bj - 1 - d));
-                if (a1 >= a0) my_arcs += (unsigned long long)(a1 - a0 + 1);
+    int r = 0, qn = 0;
+    for (int base = 0;; base += 32) {
+        const bool more = base < total;
+        if (more) {
+            const int idx = base + lane;
+            bool keep = false;
+            int code = 0;
+            if (idx < total) {
+                while (s_rowpre[r + 1] <= idx) ++r;  // idx only grows, so the row index only advances
+                const int rqa = max(qLo, -4 * r - 4);  // the row's first group
+                const int q8 = rqa + (idx - s_rowpre[r]);
+                const int dq = q8 * 8, u0 = r * 32;
+                const int g0 = (u0 + dq + SCAN_PAD_LO) >> 3;
+                const float bound = fmaxf(__fsub_ru(us.wmax[g0], us.rmin[r]), __fsub_ru(us.rmax[r], us.wmin[g0]));
+                // g[L] is concave: its minimum over the unit's diagonals inside the band is at one end
+                const int Lf = max(La, g.D0 + dq), Ll = min(Lb, g.D0 + dq + 7);
+                const double thmin = *((volatile double*)&sm->sms) * fmin(c.gtab[Lf], c.gtab[Ll]);
+                keep = !((double)bound < thmin);
+                code = (r << 20) | (q8 + 65536);
             }
+            const unsigned mask = __ballot_sync(FULL, keep);
+            if (keep) us.queue[qn + __popc(mask & ((1u << lane) - 1u))] = code;
+            qn += __popc(mask);
+            __syncwarp();
         }
-        // thresholds for the 8 diagonals of the group.  The fast path never compares doubles (DSETP issues at
-        // a quarter of the DADD rate on B200): an arc can only beat the level if |S_j - S_i| > th, and then the
-        // high word of |S_j - S_i| is >= the high word of th.  Per diagonal the maximum of (hi << 1) (the shift
-        // drops the sign) is kept with one integer instruction per arc (VIADDMNMX.U32) next to the DADD.
-        const double sms = *((volatile double*)&sm->sms);
-        unsigned thk[8];
-#pragma unroll
-        for (int k = 0; k < 8; ++k) {
-            const int L = g.D0 + dq + k;
-            const bool in = (L >= La && L <= Lb);
-            thk[k] = in ? (((unsigned)__double2hiint(sms * c.gtab[in ? L : 1])) << 1) : 0xffffffffu;
-        }
-        // fast path: 4 steps of 8 positions x 8 diagonals; positions outside the blocks hold the real
-        // neighbouring prefix sums (finite), a spurious hit there is discarded by the exact re-evaluation
-        const double* pa = sa + u0;
-        const double* pb = sbs + 9 * ((u0 + dq + SCAN_PAD_LO) >> 3);
-        double w[8], nw[8];
-        unsigned m[8];
-#pragma unroll
-        for (int k = 0; k < 8; ++k) { w[k] = pb[k]; m[k] = 0u; }
-#pragma unroll
-        for (int it = 0; it < 4; ++it) {
-#pragma unroll
-            for (int k = 0; k < 8; ++k) nw[k] = pb[9 * (it + 1) + k];
-#pragma unroll
-            for (int s = 0; s < 8; ++s) {
-                const double a = pa[8 * it + s];
+        if (qn >= 32 || (!more && qn > 0)) {
+            const int take = min(qn, 32);
+            if (lane < take) {
+                const int code = us.queue[lane];
+                const int dq = ((code & 0xfffff) - 65536) * 8, u0 = (code >> 20) * 32;
+                my_slots += 256;
+                if (c.arcs) {
+                    for (int k = 0; k < 8; ++k) {
+                        const int d = dq + k, L = g.D0 + d;
+                        if (L < La || L > Lb) continue;
+                        const int a0 = max(u0, max(0, -d)), a1 = min(u0 + 31, min(g.Bi - 1, g.Bj - 1 - d));
+                        if (a1 >= a0) my_arcs += (unsigned long long)(a1 - a0 + 1);
+                    }
+                }
+                // thresholds for the 8 diagonals of the group.  The fast path never compares doubles (DSETP issues
+                // at a quarter of the DADD rate on B200): an arc can only beat the level if |S_j - S_i| > th, and
+                // then the high word of |S_j - S_i| is >= the high word of th.  Per diagonal the maximum of
+                // (hi << 1) (the shift drops the sign) is kept with one integer instruction per arc
+                // (VIADDMNMX.U32) next to the DADD.
+                const double sms = *((volatile double*)&sm->sms);
+                unsigned thk[8];
 #pragma unroll
                 for (int k = 0; k < 8; ++k) {
-                    const double xv = (s + k < 8) ? w[s + k] : nw[s + k - 8];
-                    m[k] = max(m[k], ((unsigned)__double2hiint(xv - a)) << 1);
+                    const int L = g.D0 + dq + k;
+                    const bool in = (L >= La && L <= Lb);
+                    thk[k] = in ? (((unsigned)__double2hiint(sms * c.gtab[in ? L : 1])) << 1) : 0xffffffffu;
                 }
+                // fast path: 4 steps of 8 positions x 8 diagonals; positions outside the blocks hold the real
+                // neighbouring prefix sums (finite), a spurious hit there is discarded by the exact re-evaluation
+                const double* pa = sa + u0;
+                const double* pb = sbs + 9 * ((u0 + dq + SCAN_PAD_LO) >> 3);
+                double w[8], nw[8];
+                unsigned m[8];
+#pragma unroll
+                for (int k = 0; k < 8; ++k) { w[k] = pb[k]; m[k] = 0u; }
+#pragma unroll
+                for (int it = 0; it < 4; ++it) {
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) nw[k] = pb[9 * (it + 1) + k];
+#pragma unroll
+                    for (int s = 0; s < 8; ++s) {
+                        const double a = pa[8 * it + s];
+#pragma unroll
+                        for (int k = 0; k < 8; ++k) {
+                            const double xv = (s + k < 8) ? w[s + k] : nw[s + k - 8];
+                            m[k] = max(m[k], ((unsigned)__double2hiint(xv - a)) << 1);
+                        }
+                    }
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) w[k] = nw[k];
+                }
+                bool flag = false;
+#pragma unroll
+                for (int k = 0; k < 8; ++k) flag |= (m[k] >= thk[k]);
+                if (flag) scan_unit_exact(c, g, sa, sbs, u0, dq, sms, La, Lb, side, sm);
             }
-#pragma unroll
-            for (int k = 0; k < 8; ++k) w[k] = nw[k];
+            __syncwarp();
+            const int rem = qn - take;
+            const int moved = (lane < rem) ? us.queue[32 + lane] : 0;
+            __syncwarp();
+            if (lane < rem) us.queue[lane] = moved;
+            qn = rem;
+            __syncwarp();
         }
-        bool flag = false;
-#pragma unroll
-        for (int k = 0; k < 8; ++k) flag |= (m[k] >= thk[k]);
-        if (flag) scan_unit_exact(c, g, sa, sbs, u0, dq, sms, La, Lb, side, sm);
+        if (!more && qn == 0) break;
     }
+    if (c.slots && my_slots) atomicAdd(c.slots, my_slots);
     if (c.arcs && my_arcs) atomicAdd(c.arcs, my_arcs);
     __syncwarp();
 }
 
 // stage one block pair in this warp's shared memory and scan its bands
-__device__ void scan_pair(const ScanCtx& c, int q, double* sa, double* sbs, int* s_rowpre, ScanSmem* sm, int lane) {
-    int bi, bj;
-    pair_from_index(q, c.nb, bi, bj);
+__device__ void scan_pair(const ScanCtx& c, int bi, int bj, double* sa, double* sbs, int* s_rowpre, const UnitStats& us,
+                          ScanSmem* sm, int lane) {
+    // position of the pair in the reference's enumeration (row bi, then bj): the tie-break key of LOC mode
+    const int q = (bi - 1) * c.nb - ((bi - 1) * (bi - 2)) / 2 + (bj - bi);
     PairGeo g;
     pair_lengths(c, bi, bj, g.ilo, g.ihi, g.jlo, g.jhi, g.lenlo, g.lenhi);
     g.Bi = g.ihi - g.ilo + 1; g.Bj = g.jhi - g.jlo + 1; g.D0 = g.jlo - g.ilo; g.q = q;
@@ -737,18 +854,21 @@ __device__ void scan_pair(const ScanCtx& c, int q, double* sa, double* sbs, int*
     const int nf = g.Bj + SCAN_PAD_HI + SCAN_PAD_LO;
     for (int f = lane; f <= nf; f += 32) sbs[f + (f >> 3)] = c.sx[min(max(g.jlo + f - SCAN_PAD_LO, 0), c.n)];
     __syncwarp();
-    if (g.bandLo[0] <= g.bandHi[0]) scan_band(c, g, sa, sbs, s_rowpre, g.bandLo[0], g.bandHi[0], 0, sm, lane);
-    if (g.bandLo[1] <= g.bandHi[1]) scan_band(c, g, sa, sbs, s_rowpre, g.bandLo[1], g.bandHi[1], 1, sm, lane);
+    unit_stats(g, sa, sbs, us, lane);
+    if (g.bandLo[0] <= g.bandHi[0]) scan_band(c, g, sa, sbs, s_rowpre, us, g.bandLo[0], g.bandHi[0], 0, sm, lane);
+    if (g.bandLo[1] <= g.bandHi[1]) scan_band(c, g, sa, sbs, s_rowpre, us, g.bandLo[1], g.bandHi[1], 1, sm, lane);
 }
 
 // dynamic shared memory layout helper (host + device)
 struct ScanLayout {
     int nb_max, B_max, warps;
+    CBS_HD int a_doubles() const { return ((B_max + 31) / 32) * 32 + 8; }
+    CBS_HD int b_doubles() const { const int f = B_max + SCAN_PAD_HI + SCAN_PAD_LO; return f + (f >> 3) + 2; }
+    CBS_HD int n_groups() const { return ((B_max + SCAN_PAD_HI + SCAN_PAD_LO) >> 3) + 2; }  // 8-groups of the j buffer
+    CBS_HD int n_rows() const { return (B_max + 31) / 32 + 1; }
+    // i buffer, j buffer, row prefix (33 ints) + unit queue (64 ints), unit-level extrema (floats)
     CBS_HD size_t per_warp_doubles() const {
-        const int a = ((B_max + 31) / 32) * 32 + 8;
-        const int f = B_max + SCAN_PAD_HI + SCAN_PAD_LO;
-        const int b = f + (f >> 3) + 2;
-        return (size_t)a + (size_t)b + 20;  // + row prefix (33 ints)
+        return (size_t)a_doubles() + (size_t)b_doubles() + 50 + (size_t)n_groups() + (size_t)n_rows() + 2;
     }
     CBS_HD size_t bytes() const {
         size_t doubles = 2 * (size_t)nb_max + (size_t)warps * per_warp_doubles();
@@ -757,7 +877,7 @@ struct ScanLayout {
     }
 };
 
-__global__ void __launch_bounds__(256, 3) k_scan(Dev* D, ScanLayout lay) {
+__global__ void __launch_bounds__(384, 2) k_scan(Dev* D, ScanLayout lay) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     if (D->done) return;
     ScanSmem* sm = (ScanSmem*)smem_raw;
@@ -896,19 +1016,27 @@ __global__ void __launch_bounds__(256, 3) k_scan(Dev* D, ScanLayout lay) {
             // ---- pass 2: scan surviving block pairs ----------------------------------------
             double* wbase = s_warp + (size_t)warp * lay.per_warp_doubles();
             double* sa = wbase;
-            const int asz = ((lay.B_max + 31) / 32) * 32 + 8;
-            double* sbs = sa + asz;
-            const int f0 = lay.B_max + SCAN_PAD_HI + SCAN_PAD_LO;
-            int* s_rowpre = (int*)(sbs + f0 + (f0 >> 3) + 2);
+            double* sbs = sa + lay.a_doubles();
+            int* s_rowpre = (int*)(sbs + lay.b_doubles());
+            UnitStats us;
+            us.queue = s_rowpre + 34;
+            us.wmin = (float*)(s_rowpre + 100);
+            us.wmax = us.wmin + lay.n_groups();
+            us.rmin = us.wmax + lay.n_groups();
+            us.rmax = us.rmin + lay.n_rows();
             for (;;) {
                 int q0 = 0;
                 if (lane == 0) q0 = atomicAdd(&sm->next_pair, 32);
                 q0 = __shfl_sync(FULL, q0, 0);
                 if (q0 >= npairs) break;
+                // pairs are claimed diagonal by diagonal (bj - bi = 0, 1, 2, ...): the pairs with the longest
+                // arc-length bands come first, the tail of a permutation is made of cheap, mostly pruned pairs
                 const int q = q0 + lane;
                 bool alive = false;
+                int bi = 1, bj = 1;
                 if (q < npairs) {
-                    int bi, bj; pair_from_index(q, nb, bi, bj);
+                    int da, db; pair_from_index(q, nb, da, db);
+                    bi = db - da + 1; bj = bi + (da - 1);
                     int ilo, ihi, jlo, jhi, lenlo, lenhi;
                     pair_lengths(c, bi, bj, ilo, ihi, jlo, jhi, lenlo, lenhi);
                     double s1, s2; int clen;
@@ -925,7 +1053,7 @@ __global__ void __launch_bounds__(256, 3) k_scan(Dev* D, ScanLayout lay) {
                 while (mask) {
                     const int l = __ffs(mask) - 1;
                     mask &= mask - 1;
-                    scan_pair(c, q0 + l, sa, sbs, s_rowpre, sm, lane);
+                    scan_pair(c, __shfl_sync(FULL, bi, l), __shfl_sync(FULL, bj, l), sa, sbs, s_rowpre, us, sm, lane);
                 }
             }
             __syncthreads();
