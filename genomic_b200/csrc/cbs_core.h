@@ -18,6 +18,7 @@
 namespace cbsg {
 
 enum { RNG_MT = 0, RNG_PHILOX = 1 };
+enum { SX_PAD = 48 };  // finite values kept behind the prefix sums of every permutation
 
 // mirrors the reference call arguments 1:1 (CBS.hpp:100-113) + rng selection
 struct Params {
@@ -360,7 +361,8 @@ struct Sched {
     }
 
     // arena helpers ---------------------------------------------------------------------
-    CBS_HD static long long sx_stride(int n) { return ((long long)n + 1 + 3) & ~3LL; }
+    // S[0..n] followed by SX_PAD finite values (the scan's fast path reads whole 32 x 8 units)
+    CBS_HD static long long sx_stride(int n) { return ((long long)n + 1 + SX_PAD + 3) & ~3LL; }
     CBS_HD static long long bs_stride(int nb) { return (3LL * nb + 4 + 3) & ~3LL; }
     // 32-bit index array of the global-memory shuffle, in doubles; all strides are multiples of 4 doubles so
     // that every row of prefix sums starts on a 32-byte boundary (k_prefix moves rows with 128-bit accesses)

@@ -241,11 +241,11 @@ int smooth_device(cbs_gpu_ctx* c, const double* xin, const long long* goff, cons
     return CBS_GPU_OK;
 }
 
-// warps per scan CTA: the per-block tables are per CTA, the staging buffers per warp; take the CTA shape that
-// keeps the most warps resident on an SM (12 warps x 2 CTAs for SNP6-scale chromosomes, 8 x 3 for short units)
+// warps per scan CTA: the block and extrema tables are per CTA; take the CTA shape that keeps the most warps
+// resident on an SM
 bool pick_scan_warps(cbs_gpu_ctx* c, ScanLayout& lay, int* occ_out) {
     int best_w = 0, best_res = 0, best_occ = 1;
-    for (int w : {12, 8, 4, 2, 1}) {
+    for (int w : {8, 4, 2, 1}) {
         lay.warps = w;
         if (lay.bytes() > c->smem_optin) continue;
         int occ = 0;
@@ -430,16 +430,8 @@ int run_cbs(cbs_gpu_ctx* c, const std::vector<long long>& off, const uint64_t* u
 
     // ---- scan kernel configuration ------------------------------------------------------------
     ScanLayout lay;
-    lay.nb_max = block_count((int)std::max<long long>(Nmax, 1)) + 1;
-    {
-        int bmax = 1;
-        // the largest block of any segment length <= Nmax: ceil(n/nb)+1 is increasing in n for n >= 50
-        const int nbm = block_count((int)std::max<long long>(Nmax, 1));
-        bmax = (int)((Nmax + nbm - 1) / nbm) + 2;
-        bmax = std::max(bmax, (int)std::sqrt((double)Nmax) + 4);
-        bmax = std::max(bmax, 50);
-        lay.B_max = bmax;
-    }
+    lay.nb_max = block_count((int)std::max<long long>(Nmax, 1)) + 2;
+    lay.set_table(std::max<long long>(Nmax, 1));
     int scan_occ = 1;
     if (!pick_scan_warps(c, lay, &scan_occ)) return fail(c, CBS_GPU_ERR_UNSUPPORTED, "segment too long for the scan kernel's shared memory");
     const size_t scan_smem = lay.bytes();
@@ -857,8 +849,8 @@ static int run_raw_scan(cbs_gpu_ctx* c, const double* xh, int n, int count, doub
     CUDA_TRY(c, cudaMemcpyAsync(c->item_prefix.p, prefix.data(), sizeof(int) * prefix.size(), cudaMemcpyHostToDevice, st));
     CUDA_TRY(c, cudaMemcpyAsync(c->dev.p, &hD, sizeof(Dev), cudaMemcpyHostToDevice, st));
     ScanLayout lay;
-    lay.nb_max = nb + 1;
-    lay.B_max = std::max(std::max((n + nb - 1) / nb + 2, (int)std::sqrt((double)n) + 4), 50);
+    lay.nb_max = nb + 2;
+    lay.set_table(n);
     if (!pick_scan_warps(c, lay, nullptr)) return fail(c, CBS_GPU_ERR_UNSUPPORTED, "vector too long for the scan kernel's shared memory");
     Dev* dD = c->dev.as<Dev>();
     k_prep<<<std::min(count, c->sm_count * 8), 32, 0, st>>>(dD);

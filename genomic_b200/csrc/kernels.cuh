@@ -213,6 +213,8 @@ __device__ void prep_warp(Dev* D, Task& t, int lane, double* buf) {
         __syncwarp();
         for (int k = lane; k < cnt; k += 32) sx[c0 + 1 + k] = buf[k];
     }
+    run = shfl_d(run, 0);
+    for (int k = lane; k < SX_PAD; k += 32) sx[n + 1 + k] = run;  // finite padding behind S_n (read by k_scan)
     if (lane == 0 && !raw) t.tss = tss;
 }
 
@@ -456,6 +458,9 @@ __device__ void perm_warp(Dev* D, const Task& t, int p, Idx s_idx, double* buf, 
         __syncwarp();
         for (int k = lane; k < cnt; k += 32) sx[c0 + 1 + k] = buf[k];
     }
+    // the scan reads up to SX_PAD values behind S_n without bounds checks: keep them finite
+    run = shfl_d(run, 0);
+    for (int k = lane; k < SX_PAD; k += 32) sx[n + 1 + k] = run;
     __syncwarp();
 }
 
@@ -505,19 +510,23 @@ __global__ void __launch_bounds__(128) k_perm(Dev* D) {
 }
 
 // ------------------------------------------------------------------------------------
-// k_scan -- the dominant kernel.
+// k_scan -- the max-t arc scan.
 //
 // One CTA per (segment, permutation).  The reference finds max over arcs (i,j) of
 // fac(L) * (S_j - S_i)^2, L = j - i, by visiting sqrt(n) x sqrt(n) block pairs in order of
 // their corner statistic and pruning with the running maximum (CBS.cpp:119-216).  Here:
+//   phase 0 the per-block extrema of the prefix sums with their first occurrence (CBS.cpp:88-94) and a
+//           table of the extrema of every aligned run of 32 (64, 128) prefix sums, in shared memory;
 //   pass 1  every thread evaluates corner arcs of block pairs; the best VALID corner gives a
 //           lower bound LB on the answer (it is an arc the reference also evaluates);
-//   pass 2  warps claim block pairs whose upper bound reaches the current level and scan
-//           them.  The scan never computes a statistic: an arc can only beat level M if
-//           |S_j - S_i| > sqrt(M) * g[L], g[L] = sqrt(L(n-L)/n), so the inner loop is one
-//           DADD and one DSETP per arc against per-diagonal thresholds held in registers
-//           (8 diagonals x 8 positions per lane per step).  A hit (rare) re-evaluates the
-//           8x32 unit exactly as fac*s*s and raises the level.
+//   pass 2  warps claim block pairs whose upper bound reaches the current level.  A pair is cut
+//           into units of 32 positions x 8 arc lengths on the global index grid.  A unit can only hold
+//           an arc above level M if max|S_j - S_i| over the values it touches exceeds
+//           sqrt(M) * min g[L], g[L] = sqrt(L(n-L)/n): this is decided from the table (first for 32
+//           lengths at once, then per unit) without reading a prefix sum.  Surviving units go through
+//           a per-warp queue so that all 32 lanes examine arcs: one DADD (S_j - S_i) and one integer
+//           max of the high word per arc against per-length thresholds in registers; a hit (rare)
+//           re-evaluates the unit exactly as fac*s*s and raises the level.
 // The set of arcs considered per block pair is exactly the reference's (its restricted
 // length ranges [lenlo,lenmax] and [n-lenmax,lenhi], CBS.cpp:179-215), so the maximum is the
 // same double; ties for the observed scan follow the reference's visiting order.
@@ -549,13 +558,10 @@ __device__ __forceinline__ bool cand_better(const Cand& a, const Cand& b) {
     return a.i < b.i;
 }
 
-#define SCAN_PAD_LO 32
-#define SCAN_PAD_HI 48
-// swizzled position of element e (e >= -SCAN_PAD_LO) of the j-block staging buffer
-__device__ __forceinline__ int sb_pos(int e) { const int f = e + SCAN_PAD_LO; return f + (f >> 3); }
+#define SCAN_QUEUE 256  // per-warp ring of surviving units (entries)
 
 struct PairGeo {
-    int ilo, ihi, jlo, jhi, Bi, Bj, D0;
+    int ilo, ihi, jlo, jhi;
     int lenlo, lenhi;
     int bandLo[2], bandHi[2];  // arc-length bands actually scanned (empty if lo > hi)
     double corner;
@@ -579,9 +585,12 @@ __device__ __forceinline__ void pair_from_index(int q, int nb, int& bi, int& bj)
 struct ScanCtx {
     int n, nb, al0;
     double rn, half;
+    float inv_n_rd;         // 1/n rounded down
     const int* bb;          // smem
     const double* bmin; const double* bmax; const int* amin; const int* amax;  // smem
-    const double* sx;       // global, this permutation's prefix sums sx[0..n]
+    const float* tmin; const float* tmax;  // smem: extrema of prefix sums [e << tsh, (e+1) << tsh), rounded outwards
+    int tsh;
+    const double* sx;       // global, this permutation's prefix sums sx[0..n] (+ SX_PAD finite values)
     const double* gtab; const double* factab;  // global, index by L
     bool loc;
     unsigned long long* slots;  // profiling counters or nullptr
@@ -603,26 +612,26 @@ __device__ __forceinline__ void pair_lengths(const ScanCtx& c, int bi, int bj, i
     if (lenlo < c.al0) lenlo = c.al0;
 }
 
-// exact re-evaluation of one 8-diagonal x 32-position unit (slow path)
-__device__ void scan_unit_exact(const ScanCtx& c, const PairGeo& g, const double* sa, const double* sbs, int u0, int dq,
-                                double sms, int La, int Lb, int side, ScanSmem* sm) {
+// exact re-evaluation of one unit (slow path): rows i0..i0+31, arc lengths L0..L0+7, restricted to the pair's
+// blocks and to the band [La, Lb]
+__device__ void scan_unit_exact(const ScanCtx& c, const PairGeo& g, int i0, int L0, double sms, int La, int Lb, int side,
+                                ScanSmem* sm) {
     double best = 0.0;
     double th[8];
 #pragma unroll
     for (int r = 0; r < 8; ++r) {
-        const int L = g.D0 + dq + r;
+        const int L = L0 + r;
         th[r] = (L >= La && L <= Lb) ? sms * c.gtab[L] : __longlong_as_double(0x7ff0000000000000LL);
     }
     Cand cb; cb.stat = -1.0; cb.corner = 0.0; cb.q = 0; cb.key = 0; cb.i = 0; cb.j = 0;
-    for (int u = u0; u < u0 + 32 && u < g.Bi; ++u) {
-        const double a = sa[u];
+    const int ia = max(i0, g.ilo), ib = min(i0 + 31, g.ihi);
+    for (int i = ia; i <= ib; ++i) {
+        const double a = c.sx[i];
 #pragma unroll
         for (int r = 0; r < 8; ++r) {
-            const int d = dq + r, v = u + d;
-            if (v < 0 || v >= g.Bj) continue;
-            const int L = g.D0 + d;
-            if (L < La || L > Lb) continue;
-            const double s = fabs(sbs[sb_pos(v)] - a);
+            const int L = L0 + r, j = i + L;
+            if (L < La || L > Lb || j < g.jlo || j > g.jhi) continue;
+            const double s = fabs(c.sx[j] - a);
             if (!(s > th[r])) continue;
             const double stat = c.factab[L] * s * s;  // CBS.cpp:191-193
             if (!c.loc) { if (stat > best) best = stat; }
@@ -630,7 +639,7 @@ __device__ void scan_unit_exact(const ScanCtx& c, const PairGeo& g, const double
                 Cand x;
                 x.stat = stat; x.corner = g.corner; x.q = g.q;
                 x.key = side ? (0x40000000 + (c.n - L)) : L;  // low side: L ascending; high side: L descending
-                x.i = g.ilo + u; x.j = g.ilo + u + L;
+                x.i = i; x.j = j;
                 if (cb.stat < 0.0 || cand_better(x, cb)) cb = x;
             }
         }
@@ -660,237 +669,202 @@ __device__ void scan_unit_exact(const ScanCtx& c, const PairGeo& g, const double
     }
 }
 
-// per-warp scratch of the unit-level bounds (single precision, rounded outwards)
-struct UnitStats {
-    float* wmin; float* wmax;  // extrema of the five 8-groups of the j buffer a unit reads, by first group
-    float* rmin; float* rmax;  // extrema of every 32-row group of the i buffer
-    int* queue;                // surviving units of the band (64 entries)
-};
-
-// extrema used to discard whole 8-diagonal x 32-position units before any arc is examined
-__device__ void unit_stats(const PairGeo& g, const double* sa, const double* sbs, const UnitStats& us, int lane) {
-    const int nf = g.Bj + SCAN_PAD_HI + SCAN_PAD_LO;
-    const int NG = (nf >> 3) + 1;
-    const float finf = __int_as_float(0x7f800000);
-    for (int gi = lane; gi < NG; gi += 32) {
-        double lo = __longlong_as_double(0x7ff0000000000000LL), hi = -lo;
-#pragma unroll
-        for (int k = 0; k < 8; ++k) {
-            if (8 * gi + k <= nf) { const double v = sbs[9 * gi + k]; lo = fmin(lo, v); hi = fmax(hi, v); }
-        }
-        us.wmin[gi] = __double2float_rd(lo); us.wmax[gi] = __double2float_ru(hi);
-    }
-    __syncwarp();
-    float wl[5], wh[5];  // NG <= 136 for the longest supported unit (1,000,000 markers)
-#pragma unroll
-    for (int t = 0; t < 5; ++t) {
-        const int gi = lane + 32 * t;
-        wl[t] = finf; wh[t] = -finf;
-        if (gi < NG) {
-            for (int k = 0; k < 5 && gi + k < NG; ++k) { wl[t] = fminf(wl[t], us.wmin[gi + k]); wh[t] = fmaxf(wh[t], us.wmax[gi + k]); }
-        }
-    }
-    __syncwarp();
-#pragma unroll
-    for (int t = 0; t < 5; ++t) { const int gi = lane + 32 * t; if (gi < NG) { us.wmin[gi] = wl[t]; us.wmax[gi] = wh[t]; } }
-    const int nrows = (g.Bi + 31) >> 5;
-    if (lane < nrows) {
-        double lo = __longlong_as_double(0x7ff0000000000000LL), hi = -lo;
-        for (int u = 32 * lane; u < 32 * lane + 32; ++u) { const double v = sa[u]; lo = fmin(lo, v); hi = fmax(hi, v); }
-        us.rmin[lane] = __double2float_rd(lo); us.rmax[lane] = __double2float_ru(hi);
-    }
-    __syncwarp();
+// lower bound (single precision, every operation rounded down) of g[L] = sqrt(L(n-L)/n); L, n-L < 2^24 are exact
+__device__ __forceinline__ float g_lower(const ScanCtx& c, int L) {
+    return __fsqrt_rd(__fmul_rd(__fmul_rd((float)L, (float)(c.n - L)), c.inv_n_rd));
+}
+// upper bound of max |S_j - S_i| over i in the aligned row starting at i0 and j in [js, je], from the table
+__device__ __forceinline__ float window_bound(const ScanCtx& c, int i0, int js, int je) {
+    const int re = i0 >> c.tsh;
+    const float rmin = c.tmin[re], rmax = c.tmax[re];
+    const int e1 = min(je, c.n) >> c.tsh;
+    int e = js >> c.tsh;
+    float wmin = c.tmin[e], wmax = c.tmax[e];
+    for (++e; e <= e1; ++e) { wmin = fminf(wmin, c.tmin[e]); wmax = fmaxf(wmax, c.tmax[e]); }
+    return fmaxf(__fsub_ru(wmax, rmin), __fsub_ru(rmax, wmin));
 }
 
-// scan one arc-length band [La, Lb] of a staged block pair with the whole warp.  Work unit: 8 diagonals x
-// 32 positions.  A unit is first tested against the level with the extrema of the values it would read
-// (|S_j - S_i| <= max(maxJ - minI, maxI - minJ)); the survivors are compacted through a small queue so
-// that all 32 lanes examine arcs.
-__device__ void scan_band(const ScanCtx& c, const PairGeo& g, const double* sa, const double* sbs, int* s_rowpre,
-                          const UnitStats& us, int La, int Lb, int side, ScanSmem* sm, int lane) {
-    // diagonals d = L - D0; 8-aligned diagonal groups q8 (d in [8*q8, 8*q8+7]); 32-aligned u rows
-    const int dLo = La - g.D0, dHi = Lb - g.D0;
-    const int qLo = dLo >> 3, qHi = dHi >> 3;  // arithmetic shift == floor
-    const int nrows = (g.Bi + 31) >> 5;
-    // row r holds groups whose valid u-range [max(0,-(dq+7)), min(Bi-1, Bj-1-dq)] meets [32r, 32r+31]
-    int qa = 0, qb = -1;
-    if (lane < nrows) {
-        // -(dq+7) <= 32r+31  <=>  dq >= -32r-38 ; multiples of 8: q8 >= ceil((-32r-38)/8) = -4r-4
-        qa = max(qLo, -4 * lane - 4);
-        // Bj-1-dq >= 32r  <=>  dq <= Bj-1-32r
-        qb = min(qHi, (g.Bj - 1 - 32 * lane) >> 3);
-    }
-    int cnt = max(0, qb - qa + 1);
-    int incl = cnt;
+// examine the arcs of one queued unit (fast path): rows i0..i0+31 x lengths L0..L0+7, 4 steps of 8 rows x 8 lengths
+// from registers.  Values beyond the blocks are real neighbouring prefix sums (or the padding behind S_n, finite):
+// a spurious hit there is discarded by the exact re-evaluation.
+__device__ __forceinline__ void scan_unit(const ScanCtx& c, const PairGeo& g, int i0, int L0, int La, int Lb, int side,
+                                          ScanSmem* sm) {
+    // Thresholds for the 8 lengths.  The fast path never compares doubles (DSETP issues at a quarter of the DADD
+    // rate on B200): an arc can only beat the level if |S_j - S_i| > th, and then the high word of |S_j - S_i|
+    // is >= the high word of th.  Per length the maximum of (hi << 1) (the shift drops the sign) is kept with one
+    // integer instruction per arc (VIADDMNMX.U32) next to the DADD.
+    const double sms = *((volatile double*)&sm->sms);
+    unsigned thk[8];
 #pragma unroll
-    for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(FULL, incl, o); if (lane >= o) incl += t; }
-    const int total = __shfl_sync(FULL, incl, 31);
-    __syncwarp();
-    s_rowpre[lane] = incl - cnt;  // exclusive
-    if (lane == 0) s_rowpre[32] = total;
+    for (int k = 0; k < 8; ++k) {
+        const int L = L0 + k;
+        const bool in = (L >= La && L <= Lb);
+        thk[k] = in ? (((unsigned)__double2hiint(sms * c.gtab[in ? L : 1])) << 1) : 0xffffffffu;
+    }
+    const double2* pa = reinterpret_cast<const double2*>(c.sx + i0);        // i0 is a multiple of 32,
+    const double2* pb = reinterpret_cast<const double2*>(c.sx + i0 + L0);   // L0 of 8: 16-byte aligned
+    double w[8], nw[8];
+    unsigned m[8];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { const double2 v = __ldg(pb + k); w[2 * k] = v.x; w[2 * k + 1] = v.y; }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) m[k] = 0u;
+#pragma unroll
+    for (int it = 0; it < 4; ++it) {
+        double av[8];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const double2 v = __ldg(pb + 4 * (it + 1) + k); nw[2 * k] = v.x; nw[2 * k + 1] = v.y;
+            const double2 u = __ldg(pa + 4 * it + k); av[2 * k] = u.x; av[2 * k + 1] = u.y;
+        }
+#pragma unroll
+        for (int s = 0; s < 8; ++s) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const double xv = (s + k < 8) ? w[s + k] : nw[s + k - 8];
+                m[k] = max(m[k], ((unsigned)__double2hiint(xv - av[s])) << 1);
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < 8; ++k) w[k] = nw[k];
+    }
+    bool flag = false;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) flag |= (m[k] >= thk[k]);
+    if (flag) scan_unit_exact(c, g, i0, L0, sms, La, Lb, side, sm);
+}
+
+// scan one arc-length band [La, Lb] of a block pair with the whole warp
+__device__ void scan_band(const ScanCtx& c, const PairGeo& g, int* queue, int La, int Lb, int side, ScanSmem* sm, int lane) {
+    const int a0 = g.ilo >> 5, nra = (g.ihi >> 5) - a0 + 1;   // aligned rows of 32 positions meeting block i
+    const int s0 = La >> 5, nsg = (Lb >> 5) - s0 + 1;         // aligned groups of 32 arc lengths meeting the band
+    const int total = nra * nsg;
     unsigned long long my_arcs = 0, my_slots = 0;
-    __syncwarp();
-    int r = 0, qn = 0;
+    unsigned head = 0, qn = 0;  // ring: entries [head, head+qn)
     for (int base = 0;; base += 32) {
         const bool more = base < total;
         if (more) {
             const int idx = base + lane;
-            bool keep = false;
-            int code = 0;
+            unsigned keep4 = 0, code0 = 0;  // surviving 8-length units of this lane's 32-length group
             if (idx < total) {
-                while (s_rowpre[r + 1] <= idx) ++r;  // idx only grows, so the row index only advances
-                const int rqa = max(qLo, -4 * r - 4);  // the row's first group
-                const int q8 = rqa + (idx - s_rowpre[r]);
-                const int dq = q8 * 8, u0 = r * 32;
-                const int g0 = (u0 + dq + SCAN_PAD_LO) >> 3;
-                const float bound = fmaxf(__fsub_ru(us.wmax[g0], us.rmin[r]), __fsub_ru(us.rmax[r], us.wmin[g0]));
-                // g[L] is concave: its minimum over the unit's diagonals inside the band is at one end
-                const int Lf = max(La, g.D0 + dq), Ll = min(Lb, g.D0 + dq + 7);
-                const double thmin = *((volatile double*)&sm->sms) * fmin(c.gtab[Lf], c.gtab[Ll]);
-                keep = !((double)bound < thmin);
-                code = (r << 20) | (q8 + 65536);
+                const int ar = idx / nsg;
+                const int a = a0 + ar, sg = s0 + (idx - ar * nsg);
+                const int i0 = a << 5, Ls = sg << 5;
+                const int imin = max(i0, g.ilo), imax = min(i0 + 31, g.ihi);
+                const int Lmin = max(Ls, La), Lmax = min(Ls + 31, Lb);
+                code0 = ((unsigned)a << 17) | (unsigned)(Ls >> 3);
+                if (imax + Lmax >= g.jlo && imin + Lmin <= g.jhi) {
+                    // g[L] is concave: its minimum over a run of lengths is at one end
+                    const float smsf = __double2float_rd(*((volatile double*)&sm->sms));
+                    const float th32 = __fmul_rd(smsf, fminf(g_lower(c, Lmin), g_lower(c, Lmax)));
+                    if (!(window_bound(c, i0, i0 + Ls, i0 + Ls + 62) < th32)) {
+#pragma unroll
+                        for (int t = 0; t < 4; ++t) {
+                            const int L0 = Ls + 8 * t;
+                            const int l0 = max(L0, La), l1 = min(L0 + 7, Lb);
+                            if (l0 > l1 || imax + l1 < g.jlo || imin + l0 > g.jhi) continue;
+                            const float th8 = __fmul_rd(smsf, fminf(g_lower(c, l0), g_lower(c, l1)));
+                            if (window_bound(c, i0, i0 + L0, i0 + L0 + 38) < th8) continue;
+                            keep4 |= 1u << t;
+                        }
+                    }
+                }
             }
-            const unsigned mask = __ballot_sync(FULL, keep);
-            if (keep) us.queue[qn + __popc(mask & ((1u << lane) - 1u))] = code;
-            qn += __popc(mask);
-            __syncwarp();
+            const int cnt = __popc(keep4);
+            int incl = cnt;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(FULL, incl, o); if (lane >= o) incl += v; }
+            const int added = __shfl_sync(FULL, incl, 31);
+            if (added) {
+                const unsigned at = head + qn + (unsigned)(incl - cnt);
+#pragma unroll
+                for (int t = 0; t < 4; ++t)
+                    if ((keep4 >> t) & 1u) queue[(at + __popc(keep4 & ((1u << t) - 1u))) & (SCAN_QUEUE - 1)] = (int)(code0 + (unsigned)t);
+                qn += (unsigned)added;
+                __syncwarp();
+            }
         }
-        if (qn >= 32 || (!more && qn > 0)) {
-            const int take = min(qn, 32);
+        while (qn >= 32 || (!more && qn > 0)) {
+            const unsigned take = min(qn, 32u);
             if (lane < take) {
-                const int code = us.queue[lane];
-                const int dq = ((code & 0xfffff) - 65536) * 8, u0 = (code >> 20) * 32;
+                const unsigned code = (unsigned)queue[(head + lane) & (SCAN_QUEUE - 1)];
+                const int i0 = (int)(code >> 17) << 5, L0 = (int)(code & 0x1ffffu) << 3;
                 my_slots += 256;
                 if (c.arcs) {
                     for (int k = 0; k < 8; ++k) {
-                        const int d = dq + k, L = g.D0 + d;
+                        const int L = L0 + k;
                         if (L < La || L > Lb) continue;
-                        const int a0 = max(u0, max(0, -d)), a1 = min(u0 + 31, min(g.Bi - 1, g.Bj - 1 - d));
-                        if (a1 >= a0) my_arcs += (unsigned long long)(a1 - a0 + 1);
+                        const int ia = max(max(i0, g.ilo), g.jlo - L), ib = min(min(i0 + 31, g.ihi), g.jhi - L);
+                        if (ib >= ia) my_arcs += (unsigned long long)(ib - ia + 1);
                     }
                 }
-                // thresholds for the 8 diagonals of the group.  The fast path never compares doubles (DSETP issues
-                // at a quarter of the DADD rate on B200): an arc can only beat the level if |S_j - S_i| > th, and
-                // then the high word of |S_j - S_i| is >= the high word of th.  Per diagonal the maximum of
-                // (hi << 1) (the shift drops the sign) is kept with one integer instruction per arc
-                // (VIADDMNMX.U32) next to the DADD.
-                const double sms = *((volatile double*)&sm->sms);
-                unsigned thk[8];
-#pragma unroll
-                for (int k = 0; k < 8; ++k) {
-                    const int L = g.D0 + dq + k;
-                    const bool in = (L >= La && L <= Lb);
-                    thk[k] = in ? (((unsigned)__double2hiint(sms * c.gtab[in ? L : 1])) << 1) : 0xffffffffu;
-                }
-                // fast path: 4 steps of 8 positions x 8 diagonals; positions outside the blocks hold the real
-                // neighbouring prefix sums (finite), a spurious hit there is discarded by the exact re-evaluation
-                const double* pa = sa + u0;
-                const double* pb = sbs + 9 * ((u0 + dq + SCAN_PAD_LO) >> 3);
-                double w[8], nw[8];
-                unsigned m[8];
-#pragma unroll
-                for (int k = 0; k < 8; ++k) { w[k] = pb[k]; m[k] = 0u; }
-#pragma unroll
-                for (int it = 0; it < 4; ++it) {
-#pragma unroll
-                    for (int k = 0; k < 8; ++k) nw[k] = pb[9 * (it + 1) + k];
-#pragma unroll
-                    for (int s = 0; s < 8; ++s) {
-                        const double a = pa[8 * it + s];
-#pragma unroll
-                        for (int k = 0; k < 8; ++k) {
-                            const double xv = (s + k < 8) ? w[s + k] : nw[s + k - 8];
-                            m[k] = max(m[k], ((unsigned)__double2hiint(xv - a)) << 1);
-                        }
-                    }
-#pragma unroll
-                    for (int k = 0; k < 8; ++k) w[k] = nw[k];
-                }
-                bool flag = false;
-#pragma unroll
-                for (int k = 0; k < 8; ++k) flag |= (m[k] >= thk[k]);
-                if (flag) scan_unit_exact(c, g, sa, sbs, u0, dq, sms, La, Lb, side, sm);
+                scan_unit(c, g, i0, L0, La, Lb, side, sm);
             }
             __syncwarp();
-            const int rem = qn - take;
-            const int moved = (lane < rem) ? us.queue[32 + lane] : 0;
-            __syncwarp();
-            if (lane < rem) us.queue[lane] = moved;
-            qn = rem;
-            __syncwarp();
+            head += take; qn -= take;
         }
-        if (!more && qn == 0) break;
+        if (!more) break;
     }
     if (c.slots && my_slots) atomicAdd(c.slots, my_slots);
     if (c.arcs && my_arcs) atomicAdd(c.arcs, my_arcs);
     __syncwarp();
 }
 
-// stage one block pair in this warp's shared memory and scan its bands
-__device__ void scan_pair(const ScanCtx& c, int bi, int bj, double* sa, double* sbs, int* s_rowpre, const UnitStats& us,
-                          ScanSmem* sm, int lane) {
-    // position of the pair in the reference's enumeration (row bi, then bj): the tie-break key of LOC mode
-    const int q = (bi - 1) * c.nb - ((bi - 1) * (bi - 2)) / 2 + (bj - bi);
+// bands of one block pair (CBS.cpp:179-180, 198-199) and their scan
+__device__ void scan_pair(const ScanCtx& c, int bi, int bj, int* queue, ScanSmem* sm, int lane) {
     PairGeo g;
     pair_lengths(c, bi, bj, g.ilo, g.ihi, g.jlo, g.jhi, g.lenlo, g.lenhi);
-    g.Bi = g.ihi - g.ilo + 1; g.Bj = g.jhi - g.jlo + 1; g.D0 = g.jlo - g.ilo; g.q = q;
+    // position of the pair in the reference's enumeration (row bi, then bj): the tie-break key of LOC mode
+    g.q = (bi - 1) * c.nb - ((bi - 1) * (bi - 2)) / 2 + (bj - bi);
     double s1, s2; int clen;
     pair_corner(c, bi, bj, s1, s2, clen);
     g.corner = 0.0;
     if (c.loc) g.corner = c.factab[min(max(clen, 1), c.n - 1)] * ((s1 > s2) ? s1 : s2) * ((s1 > s2) ? s1 : s2);
-    // CBS.cpp:179-180, 198-199
     int lenmax = clen;
     if (lenmax > c.n - lenmax) lenmax = c.n - lenmax;
     g.bandLo[0] = 1; g.bandHi[0] = 0; g.bandLo[1] = 1; g.bandHi[1] = 0;
     if (((double)g.lenlo <= c.half) && (g.lenlo <= lenmax)) { g.bandLo[0] = g.lenlo; g.bandHi[0] = lenmax; }
     const int lenmax2 = c.n - lenmax;
     if (((double)g.lenhi >= c.half) && (g.lenhi >= lenmax2)) { g.bandLo[1] = lenmax2; g.bandHi[1] = g.lenhi; }
-    if (g.bandLo[0] > g.bandHi[0] && g.bandLo[1] > g.bandHi[1]) return;
-    // stage: sa[u] = S[ilo+u], sbs[sb_pos(v)] = S[jlo+v]; beyond the blocks the buffers hold the real
-    // neighbouring prefix sums (indices clamped to [0,n]) so that every slot a unit may touch is finite
-    __syncwarp();
-    const int arows = ((g.Bi + 31) >> 5) << 5;
-    for (int u = lane; u < arows + 8; u += 32) sa[u] = c.sx[min(g.ilo + u, c.n)];
-    const int nf = g.Bj + SCAN_PAD_HI + SCAN_PAD_LO;
-    for (int f = lane; f <= nf; f += 32) sbs[f + (f >> 3)] = c.sx[min(max(g.jlo + f - SCAN_PAD_LO, 0), c.n)];
-    __syncwarp();
-    unit_stats(g, sa, sbs, us, lane);
-    if (g.bandLo[0] <= g.bandHi[0]) scan_band(c, g, sa, sbs, s_rowpre, us, g.bandLo[0], g.bandHi[0], 0, sm, lane);
-    if (g.bandLo[1] <= g.bandHi[1]) scan_band(c, g, sa, sbs, s_rowpre, us, g.bandLo[1], g.bandHi[1], 1, sm, lane);
+    if (g.bandLo[0] <= g.bandHi[0]) scan_band(c, g, queue, g.bandLo[0], g.bandHi[0], 0, sm, lane);
+    if (g.bandLo[1] <= g.bandHi[1]) scan_band(c, g, queue, g.bandLo[1], g.bandHi[1], 1, sm, lane);
 }
 
 // dynamic shared memory layout helper (host + device)
 struct ScanLayout {
-    int nb_max, B_max, warps;
-    CBS_HD int a_doubles() const { return ((B_max + 31) / 32) * 32 + 8; }
-    CBS_HD int b_doubles() const { const int f = B_max + SCAN_PAD_HI + SCAN_PAD_LO; return f + (f >> 3) + 2; }
-    CBS_HD int n_groups() const { return ((B_max + SCAN_PAD_HI + SCAN_PAD_LO) >> 3) + 2; }  // 8-groups of the j buffer
-    CBS_HD int n_rows() const { return (B_max + 31) / 32 + 1; }
-    // i buffer, j buffer, row prefix (33 ints) + unit queue (64 ints), unit-level extrema (floats)
-    CBS_HD size_t per_warp_doubles() const {
-        return (size_t)a_doubles() + (size_t)b_doubles() + 50 + (size_t)n_groups() + (size_t)n_rows() + 2;
-    }
+    int nb_max;   // blocks of the longest segment + 1
+    int nt;       // entries of the extrema table
+    int tsh;      // log2 of the run of prefix sums one table entry covers
+    int warps;
     CBS_HD size_t bytes() const {
-        size_t doubles = 2 * (size_t)nb_max + (size_t)warps * per_warp_doubles();
-        size_t ints = 3 * (size_t)nb_max + 8;
-        return sizeof(ScanSmem) + doubles * 8 + ints * 4 + 64;
+        return ((sizeof(ScanSmem) + 15) & ~(size_t)15) + 2 * (size_t)nb_max * 8 + 3 * (size_t)nb_max * 4 + 2 * (size_t)nt * 4 +
+               (size_t)warps * SCAN_QUEUE * 4 + 64;
+    }
+    // table geometry for units of up to nmax markers: at most 16384 entries (128 KB)
+    CBS_HD void set_table(long long nmax) {
+        tsh = 5;
+        while (((nmax >> tsh) + 2) > 16384) ++tsh;
+        nt = (int)(nmax >> tsh) + 2;
     }
 };
 
-__global__ void __launch_bounds__(384, 2) k_scan(Dev* D, ScanLayout lay) {
+__global__ void __launch_bounds__(256, 3) k_scan(Dev* D, ScanLayout lay) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     if (D->done) return;
     ScanSmem* sm = (ScanSmem*)smem_raw;
     double* s_bmin = (double*)(smem_raw + ((sizeof(ScanSmem) + 15) & ~(size_t)15));
     double* s_bmax = s_bmin + lay.nb_max;
-    double* s_warp = s_bmax + lay.nb_max;
-    int* s_amin = (int*)(s_warp + (size_t)lay.warps * lay.per_warp_doubles());
+    int* s_amin = (int*)(s_bmax + lay.nb_max);
     int* s_amax = s_amin + lay.nb_max;
     int* s_bb = s_amax + lay.nb_max;
+    float* s_tmin = (float*)(s_bb + lay.nb_max);
+    float* s_tmax = s_tmin + lay.nt;
+    int* s_queue = (int*)(s_tmax + lay.nt);
     __shared__ int s_g;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int nwarps = blockDim.x >> 5;
     const int total = D->item_prefix[D->n_items];
+    const float finf = __int_as_float(0x7f800000);
     for (;;) {
         __syncthreads();
         if (tid == 0) s_g = (int)atomicAdd(&D->ctr[1], 1u);
@@ -907,7 +881,9 @@ __global__ void __launch_bounds__(384, 2) k_scan(Dev* D, ScanLayout lay) {
         const long long base = D->unit_off[t.unit] + t.lo;
         ScanCtx c;
         c.n = n; c.nb = nb; c.al0 = D->prm.min_width; c.rn = (double)n; c.half = c.rn / 2.0;
+        c.inv_n_rd = __frcp_rd((float)n);
         c.bb = s_bb; c.bmin = s_bmin; c.bmax = s_bmax; c.amin = s_amin; c.amax = s_amax;
+        c.tmin = s_tmin; c.tmax = s_tmax; c.tsh = lay.tsh;
         c.sx = D->arena + t.off_sx + (long long)p * Sched::sx_stride(n);
         c.gtab = D->gtab + base; c.factab = D->factab + base;
         c.loc = it.obs == 1;
@@ -917,8 +893,42 @@ __global__ void __launch_bounds__(384, 2) k_scan(Dev* D, ScanLayout lay) {
         BlockStats bs(D->arena + t.off_bs + (long long)p * Sched::bs_stride(nb), nb);
         const int* bbg = D->bbtab + base;
         for (int b = tid; b <= nb; b += blockDim.x) s_bb[b] = bbg[b];
+        // ---- phase 0a: extrema table.  A warp takes 1024 consecutive prefix sums (coalesced loads); a
+        // reduce-scatter over the lanes leaves lane l with the extrema of run l of 32, in single precision
+        // rounded outwards; runs are merged 2 or 4 to an entry when the table is coarser (tsh 6, 7).
+        for (int c0 = warp * 1024; c0 <= n; c0 += nwarps * 1024) {
+            float lo[32], hi[32];
+#pragma unroll
+            for (int r = 0; r < 32; ++r) {
+                const int e = c0 + 32 * r + lane;
+                if (e <= n) { const double v = c.sx[e]; lo[r] = __double2float_rd(v); hi[r] = __double2float_ru(v); }
+                else { lo[r] = finf; hi[r] = -finf; }
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                const bool up = (lane & o) != 0;
+#pragma unroll
+                for (int r = 0; r < o; ++r) {
+                    const float keep_lo = up ? lo[r + o] : lo[r], send_lo = up ? lo[r] : lo[r + o];
+                    const float keep_hi = up ? hi[r + o] : hi[r], send_hi = up ? hi[r] : hi[r + o];
+                    lo[r] = fminf(keep_lo, __shfl_xor_sync(FULL, send_lo, o));
+                    hi[r] = fmaxf(keep_hi, __shfl_xor_sync(FULL, send_hi, o));
+                }
+            }
+            float l0 = lo[0], h0 = hi[0];
+            for (int sft = 5; sft < lay.tsh; ++sft) {
+                const int o = 1 << (sft - 5);
+                l0 = fminf(l0, __shfl_xor_sync(FULL, l0, o));
+                h0 = fmaxf(h0, __shfl_xor_sync(FULL, h0, o));
+            }
+            const int per = 1 << (lay.tsh - 5);  // runs per entry
+            if ((lane & (per - 1)) == 0 && c0 + 32 * lane <= n) {
+                const int e = (c0 + 32 * lane) >> lay.tsh;
+                s_tmin[e] = l0; s_tmax[e] = h0;
+            }
+        }
         __syncthreads();
-        // per-block extrema of the prefix sums with their FIRST occurrence (CBS.cpp:88-94): a warp per block
+        // ---- phase 0b: per-block extrema with their FIRST occurrence (CBS.cpp:88-94): a warp per block
         for (int b = warp; b < nb; b += nwarps) {
             const int first = s_bb[b] + 1, last = s_bb[b + 1];
             double lo = __longlong_as_double(0x7ff0000000000000LL), hi = -lo;
@@ -965,7 +975,6 @@ __global__ void __launch_bounds__(384, 2) k_scan(Dev* D, ScanLayout lay) {
         const int gimin = sm->g_imin, gimax = sm->g_imax;
         const double spread = gmax - gmin;
         const double tss0 = t.tss;
-        __syncthreads();
         double final_best;
         int fi = min(gimax, gimin), fj = max(gimax, gimin);
         if (spread <= 0.0) {  // CBS.cpp:102-111
@@ -1014,16 +1023,7 @@ __global__ void __launch_bounds__(384, 2) k_scan(Dev* D, ScanLayout lay) {
             }
             __syncthreads();
             // ---- pass 2: scan surviving block pairs ----------------------------------------
-            double* wbase = s_warp + (size_t)warp * lay.per_warp_doubles();
-            double* sa = wbase;
-            double* sbs = sa + lay.a_doubles();
-            int* s_rowpre = (int*)(sbs + lay.b_doubles());
-            UnitStats us;
-            us.queue = s_rowpre + 34;
-            us.wmin = (float*)(s_rowpre + 100);
-            us.wmax = us.wmin + lay.n_groups();
-            us.rmin = us.wmax + lay.n_groups();
-            us.rmax = us.rmin + lay.n_rows();
+            int* queue = s_queue + warp * SCAN_QUEUE;
             for (;;) {
                 int q0 = 0;
                 if (lane == 0) q0 = atomicAdd(&sm->next_pair, 32);
@@ -1053,7 +1053,7 @@ __global__ void __launch_bounds__(384, 2) k_scan(Dev* D, ScanLayout lay) {
                 while (mask) {
                     const int l = __ffs(mask) - 1;
                     mask &= mask - 1;
-                    scan_pair(c, __shfl_sync(FULL, bi, l), __shfl_sync(FULL, bj, l), sa, sbs, s_rowpre, us, sm, lane);
+                    scan_pair(c, __shfl_sync(FULL, bi, l), __shfl_sync(FULL, bj, l), queue, sm, lane);
                 }
             }
             __syncthreads();
