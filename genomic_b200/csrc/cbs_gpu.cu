@@ -363,7 +363,7 @@ int run_cbs(cbs_gpu_ctx* c, const std::vector<long long>& off, const uint64_t* u
     hD.prm.kmax = p->kmax; hD.prm.nmin = p->nmin; hD.prm.eta = p->eta; hD.prm.tol = p->tol; hD.prm.ibin = p->ibin;
     hD.prm.rng_mode = mt ? RNG_MT : RNG_PHILOX; hD.prm.chain = p->chain ? 1 : 0; hD.prm.seed = p->seed;
     hD.prm.first_batch = p->first_batch > 0 ? p->first_batch : 256;
-    hD.prm.max_batch = p->max_batch > 0 ? p->max_batch : 2048;
+    hD.prm.max_batch = p->max_batch > 0 ? p->max_batch : 4096;
     if (hD.prm.max_batch < hD.prm.first_batch) hD.prm.max_batch = hD.prm.first_batch;
     hD.prm.record_splits = p->record_splits ? 1 : 0;
     hD.cur = c->cur.as<double>(); hD.gtab = c->gtab.as<double>(); hD.factab = c->factab.as<double>(); hD.bbtab = c->bbtab.as<int>();
@@ -440,7 +440,7 @@ int run_cbs(cbs_gpu_ctx* c, const std::vector<long long>& off, const uint64_t* u
     // shared-memory shuffle kernel, one launch per segment-length class present in this call
     size_t shuf_smem[SHUF_GLOBAL]; int shuf_occ[SHUF_GLOBAL]; bool shuf_on[SHUF_GLOBAL];
     for (int cls = 0; cls < SHUF_GLOBAL; ++cls) {
-        shuf_smem[cls] = (size_t)shuffle_class_max(cls) * 2 + 32 + PERM_CHUNK * sizeof(double);
+        shuf_smem[cls] = (size_t)shuffle_class_max(cls) * 2 + 32;
         shuf_on[cls] = (cls == 0) || Nmax > shuffle_class_max(cls - 1);  // no unit is long enough otherwise
         shuf_occ[cls] = (int)std::max<size_t>(1, std::min<size_t>(32, (c->smem_optin + 1024) / (shuf_smem[cls] + 1024)));
     }
@@ -498,6 +498,7 @@ int run_cbs(cbs_gpu_ctx* c, const std::vector<long long>& off, const uint64_t* u
                 }
             }
             for (int k = 2; k < 5; ++k) if (used_side[k]) { cudaEventRecord(c->ev_side[k], c->side[k]); cudaStreamWaitEvent(st, c->ev_side[k], 0); }
+            { LaunchTimer t(c, K_PREFIX); k_chain<<<c->sm_count * 12, CHAIN_WARPS * 32, 0, st>>>(dD); }
             cudaStreamWaitEvent(st, c->ev_side[0], 0);
             { LaunchTimer t(c, K_SCAN); k_scan<<<scan_grid, lay.warps * 32, scan_smem, st>>>(dD, lay); }
             if (p->hybrid) {

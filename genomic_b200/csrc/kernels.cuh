@@ -234,7 +234,7 @@ __global__ void __launch_bounds__(32) k_prep(Dev* D) {
 //               end of the segment.  All segments advance concurrently.
 // ------------------------------------------------------------------------------------
 #define GEN_SEG (1LL << 18)
-#define GEN_NSEG 128
+#define GEN_NSEG 512
 #define GEN_LEAD 20480
 
 // extend the raw stream sequentially from `from` to `to` (state = the 312 words before `from`);
@@ -358,7 +358,7 @@ __device__ __forceinline__ void fy_group(Idx s_idx, int i0, int i, int j, int la
 
 #define PERM_CHUNK 512
 template <class Idx>
-__device__ void perm_warp(Dev* D, const Task& t, int p, Idx s_idx, double* buf, int lane) {
+__device__ void perm_warp(Dev* D, const Task& t, int p, Idx s_idx, int lane) {
     const int n = t.n;
     const long long base = D->unit_off[t.unit] + t.lo;
     const double* __restrict__ cur = D->cur + base;
@@ -424,50 +424,28 @@ __device__ void perm_warp(Dev* D, const Task& t, int p, Idx s_idx, double* buf, 
         }
     }
     __syncwarp();
-    // prefix sums of the permuted values, S[k+1] = S[k] + x[idx[k]], with ONE strictly sequential DADD chain
-    // (the reference's order, CBS.cpp:83-90): lane 0 walks a chunk staged in shared memory (8 cycles per
-    // marker, the DADD latency) while all lanes already gather the next chunk into registers; the
-    // finished chunk is stored coalesced.  The per-block extrema are computed by k_scan, in parallel.
+    // gather the permuted values into the prefix-sum slots: S[k+1] <- x[idx[k]] (coalesced stores); k_chain turns
+    // them into prefix sums in place.  (The chain is a separate kernel because it needs no index array: an SM holds
+    // only a few index arrays, but dozens of chains.)
     double* sx = D->arena + t.off_sx + (long long)p * Sched::sx_stride(n);
-    if (lane == 0) sx[0] = 0.0;
-    double run = 0.0;
-    double r[PERM_CHUNK / 32];
+    int k = lane;
+    for (; k + 224 < n; k += 256) {
+        int id[8];
 #pragma unroll
-    for (int q = 0; q < PERM_CHUNK / 32; ++q) { const int k = lane + 32 * q; r[q] = (k < n) ? cur[s_idx.ld(k)] : 0.0; }
-    for (int c0 = 0; c0 < n; c0 += PERM_CHUNK) {
-        const int cnt = min(PERM_CHUNK, n - c0);
-        __syncwarp();
+        for (int q = 0; q < 8; ++q) id[q] = s_idx.ld(k + 32 * q);
+        double v[8];
 #pragma unroll
-        for (int q = 0; q < PERM_CHUNK / 32; ++q) buf[lane + 32 * q] = r[q];
-        __syncwarp();
-        if (c0 + PERM_CHUNK < n) {
+        for (int q = 0; q < 8; ++q) v[q] = cur[id[q]];
 #pragma unroll
-            for (int q = 0; q < PERM_CHUNK / 32; ++q) { const int k = c0 + PERM_CHUNK + lane + 32 * q; r[q] = (k < n) ? cur[s_idx.ld(k)] : 0.0; }
-        }
-        if (lane == 0) {
-            int k = 0;
-#pragma unroll 8
-            for (; k + 1 < cnt; k += 2) {
-                double2 v = *reinterpret_cast<const double2*>(buf + k);
-                run = run + v.x; v.x = run;
-                run = run + v.y; v.y = run;
-                *reinterpret_cast<double2*>(buf + k) = v;
-            }
-            if (k < cnt) { run = run + buf[k]; buf[k] = run; }
-        }
-        __syncwarp();
-        for (int k = lane; k < cnt; k += 32) sx[c0 + 1 + k] = buf[k];
+        for (int q = 0; q < 8; ++q) sx[k + 1 + 32 * q] = v[q];
     }
-    // the scan reads up to SX_PAD values behind S_n without bounds checks: keep them finite
-    run = shfl_d(run, 0);
-    for (int k = lane; k < SX_PAD; k += 32) sx[n + 1 + k] = run;
+    for (; k < n; k += 32) sx[k + 1] = cur[s_idx.ld(k)];
     __syncwarp();
 }
 
 __global__ void __launch_bounds__(32) k_perm_smem(Dev* D, int cls) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    double* buf = (double*)smem_raw;  // PERM_CHUNK doubles, then the index array
-    unsigned short* s_idx = (unsigned short*)(smem_raw + PERM_CHUNK * sizeof(double));
+    unsigned short* s_idx = (unsigned short*)smem_raw;
     if (D->done) return;
     const int lane = threadIdx.x;
     const int nl = D->n_shuf[cls];
@@ -479,7 +457,7 @@ __global__ void __launch_bounds__(32) k_perm_smem(Dev* D, int cls) {
         if (g >= total) break;
         const int k = find_item(D->shuf_prefix[cls], nl, g);
         const PermItem it = D->items[D->shuf_item[cls][k]];
-        perm_warp(D, D->tasks[it.task], g - D->shuf_prefix[cls][k], IdxSmem{s_idx}, buf, lane);
+        perm_warp(D, D->tasks[it.task], g - D->shuf_prefix[cls][k], IdxSmem{s_idx}, lane);
     }
 }
 
@@ -488,10 +466,8 @@ __global__ void __launch_bounds__(32) k_perm_smem(Dev* D, int cls) {
 // array (32-bit) does not fit in shared memory and lives in the arena (L2-resident accesses).
 // ------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128) k_perm(Dev* D) {
-    __shared__ __align__(16) double buf_all[4][PERM_CHUNK];
     if (D->done) return;
     const int lane = threadIdx.x & 31;
-    double* buf = buf_all[threadIdx.x >> 5];
     const int nl = D->n_shuf[SHUF_GLOBAL];
     const int total = D->shuf_prefix[SHUF_GLOBAL][nl];
     for (;;) {
@@ -505,7 +481,69 @@ __global__ void __launch_bounds__(128) k_perm(Dev* D) {
         const int p = g - D->shuf_prefix[SHUF_GLOBAL][k];
         const long long idxd = Sched::idx_stride(t.n);  // doubles per permutation (cbs_core.h plan_perm)
         unsigned int* idx = (unsigned int*)(D->arena + t.off_A + (long long)p * idxd);
-        perm_warp(D, t, p, IdxGlobal{idx}, buf, lane);
+        perm_warp(D, t, p, IdxGlobal{idx}, lane);
+    }
+}
+
+// ------------------------------------------------------------------------------------
+// k_chain: turns the gathered values S[1..n] of every permutation into prefix sums IN PLACE with ONE strictly
+// sequential DADD chain per permutation (the reference's order, CBS.cpp:83-90, hence identical rounding).  A warp
+// owns a permutation: lane 0 walks a chunk staged in shared memory at the DADD latency (8 cycles per marker on
+// B200) while all lanes already hold the next chunk in registers; finished chunks are stored coalesced.  Dozens of
+// warps per SM keep the FP64 pipe and HBM busy when many permutations are in flight.
+// ------------------------------------------------------------------------------------
+#define CHAIN_WARPS 4
+__global__ void __launch_bounds__(CHAIN_WARPS * 32) k_chain(Dev* D) {
+    __shared__ __align__(16) double buf_all[CHAIN_WARPS][PERM_CHUNK];
+    if (D->done) return;
+    const int lane = threadIdx.x & 31;
+    double* buf = buf_all[threadIdx.x >> 5];
+    const int total = D->item_prefix[D->n_items];
+    for (;;) {
+        int g = 0;
+        if (lane == 0) g = (int)atomicAdd(&D->ctr[3], 1u);
+        g = __shfl_sync(FULL, g, 0);
+        if (g >= total) break;
+        const int k = find_item(D->item_prefix, D->n_items, g);
+        const PermItem it = D->items[k];
+        if (it.obs) continue;  // k_prep wrote the prefix sums of observed data
+        const Task& t = D->tasks[it.task];
+        const int n = t.n;
+        double* sx = D->arena + t.off_sx + (long long)(g - D->item_prefix[k]) * Sched::sx_stride(n);
+        const double* __restrict__ src = sx + 1;
+        if (lane == 0) sx[0] = 0.0;
+        double run = 0.0;
+        double r[PERM_CHUNK / 32];
+#pragma unroll
+        for (int q = 0; q < PERM_CHUNK / 32; ++q) { const int i = lane + 32 * q; r[q] = (i < n) ? src[i] : 0.0; }
+        for (int c0 = 0; c0 < n; c0 += PERM_CHUNK) {
+            const int cnt = min(PERM_CHUNK, n - c0);
+            __syncwarp();
+#pragma unroll
+            for (int q = 0; q < PERM_CHUNK / 32; ++q) buf[lane + 32 * q] = r[q];
+            __syncwarp();
+            if (c0 + PERM_CHUNK < n) {
+#pragma unroll
+                for (int q = 0; q < PERM_CHUNK / 32; ++q) { const int i = c0 + PERM_CHUNK + lane + 32 * q; r[q] = (i < n) ? src[i] : 0.0; }
+            }
+            if (lane == 0) {
+                int kk = 0;
+#pragma unroll 8
+                for (; kk + 1 < cnt; kk += 2) {
+                    double2 v = *reinterpret_cast<const double2*>(buf + kk);
+                    run = run + v.x; v.x = run;
+                    run = run + v.y; v.y = run;
+                    *reinterpret_cast<double2*>(buf + kk) = v;
+                }
+                if (kk < cnt) { run = run + buf[kk]; buf[kk] = run; }
+            }
+            __syncwarp();
+            for (int kk = lane; kk < cnt; kk += 32) sx[c0 + 1 + kk] = buf[kk];
+        }
+        // the scan reads up to SX_PAD values behind S_n without bounds checks: keep them finite
+        run = shfl_d(run, 0);
+        for (int kk = lane; kk < SX_PAD; kk += 32) sx[n + 1 + kk] = run;
+        __syncwarp();
     }
 }
 
@@ -543,6 +581,7 @@ struct ScanSmem {
     double red[8];
     double g_min, g_max;  // global extrema of the prefix sums (0.0 unless below / above it)
     int g_imin, g_imax;
+    int n_list, pop;      // list of block pairs that reach the level: entries / next entry to scan
 };
 
 struct Cand {
@@ -559,6 +598,7 @@ __device__ __forceinline__ bool cand_better(const Cand& a, const Cand& b) {
 }
 
 #define SCAN_QUEUE 256  // per-warp ring of surviving units (entries)
+#define SCAN_LIST 2048  // per-CTA list of block pairs that reach the level (entries)
 
 struct PairGeo {
     int ilo, ihi, jlo, jhi;
@@ -610,6 +650,19 @@ __device__ __forceinline__ void pair_lengths(const ScanCtx& c, int bi, int bj, i
     lenhi = min(jhi - ilo, c.n - c.al0);
     lenlo = (bi == bj) ? 1 : (jlo - ihi);
     if (lenlo < c.al0) lenlo = c.al0;
+}
+
+// can the pair hold an arc at or above the level?  bound = rn/min(L(n-L)) * (corner spread)^2, division free
+__device__ __forceinline__ bool pair_alive(const ScanCtx& c, int bi, int bj, double level) {
+    int ilo, ihi, jlo, jhi, lenlo, lenhi;
+    pair_lengths(c, bi, bj, ilo, ihi, jlo, jhi, lenlo, lenhi);
+    double s1, s2; int clen;
+    pair_corner(c, bi, bj, s1, s2, clen);
+    const double smx = (s1 > s2) ? s1 : s2;
+    const double rlo = (double)lenlo, rhi = (double)lenhi;
+    const double a = rlo * (c.rn - rlo), b2 = rhi * (c.rn - rhi);
+    const double mn = (b2 < a) ? b2 : a;
+    return c.rn * smx * smx >= level * mn * (1.0 - 1e-12);
 }
 
 // exact re-evaluation of one unit (slow path): rows i0..i0+31, arc lengths L0..L0+7, restricted to the pair's
@@ -672,6 +725,12 @@ __device__ void scan_unit_exact(const ScanCtx& c, const PairGeo& g, int i0, int 
 // lower bound (single precision, every operation rounded down) of g[L] = sqrt(L(n-L)/n); L, n-L < 2^24 are exact
 __device__ __forceinline__ float g_lower(const ScanCtx& c, int L) {
     return __fsqrt_rd(__fmul_rd(__fmul_rd((float)L, (float)(c.n - L)), c.inv_n_rd));
+}
+// lower bound of min g[L] over L in [l0, l1]: g increases up to n/2 and decreases behind it
+__device__ __forceinline__ float g_lower_min(const ScanCtx& c, int l0, int l1) {
+    if (2 * l1 <= c.n) return g_lower(c, l0);
+    if (2 * l0 >= c.n) return g_lower(c, l1);
+    return fminf(g_lower(c, l0), g_lower(c, l1));
 }
 // upper bound of max |S_j - S_i| over i in the aligned row starting at i0 and j in [js, je], from the table
 __device__ __forceinline__ float window_bound(const ScanCtx& c, int i0, int js, int je) {
@@ -756,14 +815,14 @@ __device__ void scan_band(const ScanCtx& c, const PairGeo& g, int* queue, int La
                 if (imax + Lmax >= g.jlo && imin + Lmin <= g.jhi) {
                     // g[L] is concave: its minimum over a run of lengths is at one end
                     const float smsf = __double2float_rd(*((volatile double*)&sm->sms));
-                    const float th32 = __fmul_rd(smsf, fminf(g_lower(c, Lmin), g_lower(c, Lmax)));
+                    const float th32 = __fmul_rd(smsf, g_lower_min(c, Lmin, Lmax));
                     if (!(window_bound(c, i0, i0 + Ls, i0 + Ls + 62) < th32)) {
 #pragma unroll
                         for (int t = 0; t < 4; ++t) {
                             const int L0 = Ls + 8 * t;
                             const int l0 = max(L0, La), l1 = min(L0 + 7, Lb);
                             if (l0 > l1 || imax + l1 < g.jlo || imin + l0 > g.jhi) continue;
-                            const float th8 = __fmul_rd(smsf, fminf(g_lower(c, l0), g_lower(c, l1)));
+                            const float th8 = __fmul_rd(smsf, g_lower_min(c, l0, l1));
                             if (window_bound(c, i0, i0 + L0, i0 + L0 + 38) < th8) continue;
                             keep4 |= 1u << t;
                         }
@@ -838,7 +897,7 @@ struct ScanLayout {
     int warps;
     CBS_HD size_t bytes() const {
         return ((sizeof(ScanSmem) + 15) & ~(size_t)15) + 2 * (size_t)nb_max * 8 + 3 * (size_t)nb_max * 4 + 2 * (size_t)nt * 4 +
-               (size_t)warps * SCAN_QUEUE * 4 + 64;
+               (size_t)warps * SCAN_QUEUE * 4 + (size_t)SCAN_LIST * 4 + 64;
     }
     // table geometry for units of up to nmax markers: at most 16384 entries (128 KB)
     CBS_HD void set_table(long long nmax) {
@@ -860,6 +919,7 @@ __global__ void __launch_bounds__(256, 3) k_scan(Dev* D, ScanLayout lay) {
     float* s_tmin = (float*)(s_bb + lay.nb_max);
     float* s_tmax = s_tmin + lay.nt;
     int* s_queue = (int*)(s_tmax + lay.nt);
+    int* s_list = s_queue + lay.warps * SCAN_QUEUE;
     __shared__ int s_g;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int nwarps = blockDim.x >> 5;
@@ -1019,42 +1079,57 @@ __global__ void __launch_bounds__(256, 3) k_scan(Dev* D, ScanLayout lay) {
                 sm->found = init;
                 sm->r_stat = init; sm->r_corner = __longlong_as_double(0x7ff0000000000000LL);
                 sm->r_q = 0x7fffffff; sm->r_key = -1; sm->r_i = fi; sm->r_j = fj;
-                sm->lock = 0; sm->next_pair = 0;
+                sm->lock = 0; sm->next_pair = 0; sm->n_list = 0; sm->pop = 0;
             }
             __syncthreads();
             // ---- pass 2: scan surviving block pairs ----------------------------------------
+            // (a) the warps evaluate the pair bounds 32 pairs at a time and append the pairs that reach the level to
+            // a list in shared memory; (b) the warps pop ONE pair at a time and scan it, so that the load is balanced
+            // at the grain of a pair.  Repeated while pairs remain (the list is bounded).
             int* queue = s_queue + warp * SCAN_QUEUE;
             for (;;) {
-                int q0 = 0;
-                if (lane == 0) q0 = atomicAdd(&sm->next_pair, 32);
-                q0 = __shfl_sync(FULL, q0, 0);
-                if (q0 >= npairs) break;
-                // pairs are claimed diagonal by diagonal (bj - bi = 0, 1, 2, ...): the pairs with the longest
-                // arc-length bands come first, the tail of a permutation is made of cheap, mostly pruned pairs
-                const int q = q0 + lane;
-                bool alive = false;
-                int bi = 1, bj = 1;
-                if (q < npairs) {
-                    int da, db; pair_from_index(q, nb, da, db);
-                    bi = db - da + 1; bj = bi + (da - 1);
-                    int ilo, ihi, jlo, jhi, lenlo, lenhi;
-                    pair_lengths(c, bi, bj, ilo, ihi, jlo, jhi, lenlo, lenhi);
-                    double s1, s2; int clen;
-                    pair_corner(c, bi, bj, s1, s2, clen);
-                    const double smx = (s1 > s2) ? s1 : s2;
-                    const double rlo = (double)lenlo, rhi = (double)lenhi;
-                    const double a = rlo * (c.rn - rlo), b2 = rhi * (c.rn - rhi);
-                    const double mn = (b2 < a) ? b2 : a;
-                    // bound = rn/mn*smx^2 >= level  (conservative, division free)
-                    const double level = *((volatile double*)&sm->level);
-                    alive = (c.rn * smx * smx >= level * mn * (1.0 - 1e-12));
+                for (;;) {
+                    if (*((volatile int*)&sm->n_list) > SCAN_LIST - 32 * nwarps) break;  // every warp may still add 32
+                    int q0 = 0;
+                    if (lane == 0) q0 = atomicAdd(&sm->next_pair, 32);
+                    q0 = __shfl_sync(FULL, q0, 0);
+                    if (q0 >= npairs) break;
+                    // pairs are enumerated diagonal by diagonal (bj - bi = 0, 1, 2, ...): the pairs with the longest
+                    // arc-length bands come first
+                    const int q = q0 + lane;
+                    bool alive = false;
+                    int bi = 1, bj = 1;
+                    if (q < npairs) {
+                        int da, db; pair_from_index(q, nb, da, db);
+                        bi = db - da + 1; bj = bi + (da - 1);
+                        alive = pair_alive(c, bi, bj, *((volatile double*)&sm->level));
+                    }
+                    const unsigned mask = __ballot_sync(FULL, alive);
+                    if (mask) {
+                        int at = 0;
+                        if (lane == 0) at = atomicAdd(&sm->n_list, __popc(mask));
+                        at = __shfl_sync(FULL, at, 0);
+                        if (alive) s_list[at + __popc(mask & ((1u << lane) - 1u))] = (bi << 16) | bj;
+                    }
                 }
-                unsigned mask = __ballot_sync(FULL, alive);
-                while (mask) {
-                    const int l = __ffs(mask) - 1;
-                    mask &= mask - 1;
-                    scan_pair(c, __shfl_sync(FULL, bi, l), __shfl_sync(FULL, bj, l), queue, sm, lane);
+                __syncthreads();
+                const int n_list = sm->n_list;
+                for (;;) {
+                    int w = 0;
+                    if (lane == 0) w = atomicAdd(&sm->pop, 1);
+                    w = __shfl_sync(FULL, w, 0);
+                    if (w >= n_list) break;
+                    const int code = s_list[w];
+                    const int bi = code >> 16, bj = code & 0xffff;
+                    if (!pair_alive(c, bi, bj, *((volatile double*)&sm->level))) continue;  // the level may have risen
+                    scan_pair(c, bi, bj, queue, sm, lane);
                 }
+                __syncthreads();
+                const bool finished = sm->next_pair >= npairs;
+                __syncthreads();
+                if (finished) break;
+                if (tid == 0) { sm->n_list = 0; sm->pop = 0; }
+                __syncthreads();
             }
             __syncthreads();
             final_best = c.loc ? sm->r_stat : sm->found;

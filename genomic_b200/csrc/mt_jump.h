@@ -13,6 +13,7 @@
 #pragma once
 #include <cstdint>
 #include <cstring>
+#include <thread>
 #include <vector>
 
 namespace cbsg {
@@ -22,7 +23,7 @@ constexpr int DEG = 19937;
 constexpr int PW = 312;             // words per polynomial (19968 bits >= DEG)
 constexpr int SEG_LOG2 = 18;
 constexpr long long SEG = 1LL << SEG_LOG2;  // words per segment
-constexpr int NSEG = 128;           // segments per parallel span
+constexpr int NSEG = 512;           // segments per parallel span
 constexpr int LEAD = 20480;         // sequential lead-in words (>= DEG + PW)
 
 using Poly = std::vector<uint64_t>;  // little endian bit array, PW words (2*PW for products)
@@ -153,7 +154,7 @@ struct Table {
     std::vector<uint64_t> polys;  // NSEG * PW words; entry c = x^(c*SEG) mod phi (entry 0 unused)
 };
 
-// builds the table (about a second of host time, once per process) and checks one jump against
+// builds the table (one to two seconds of host time, once per process) and checks one jump against
 // the sequential recurrence
 inline const Table& table() {
     static Table T;
@@ -165,11 +166,24 @@ inline const Table& table() {
     if (!F.ok) return T;
     const Poly gS = F.x_pow_2k(SEG_LOG2);
     T.polys.assign((size_t)NSEG * PW, 0);
-    Poly cur = gS;
-    for (int c = 1; c < NSEG; ++c) {
-        if (c > 1) cur = F.mulmod(cur, gS);
-        std::memcpy(&T.polys[(size_t)c * PW], cur.data(), sizeof(uint64_t) * PW);
-    }
+    // g_c = g_S^c: the first NT entries one after another, then NT host threads step through c, c+NT, c+2NT, ...
+    // with the common factor g_{NT*S}
+    int NT = (int)std::thread::hardware_concurrency();
+    NT = NT < 1 ? 1 : (NT > 16 ? 16 : NT);
+    std::vector<Poly> first((size_t)NT + 1);
+    first[1] = gS;
+    for (int c = 2; c <= NT; ++c) first[c] = F.mulmod(first[c - 1], gS);
+    const Poly step = first[NT];
+    std::vector<std::thread> pool;
+    for (int th = 1; th <= NT; ++th)
+        pool.emplace_back([&, th]() {
+            Poly cur = first[th];
+            for (int c = th; c < NSEG; c += NT) {
+                if (c > th) cur = F.mulmod(cur, step);
+                std::memcpy(&T.polys[(size_t)c * PW], cur.data(), sizeof(uint64_t) * PW);
+            }
+        });
+    for (auto& t : pool) t.join();
     // self test: jump by SEG and by 3*SEG from t = 1000 of seed 1
     const size_t need = 1000 + 3 * (size_t)SEG + 400 + LEAD;
     const std::vector<uint64_t> w = raw_stream(1ULL, need);
