@@ -282,7 +282,7 @@ def run_gpu_arm(args):
         peaks = read_peaks()
         ksum = sum(kms.values()) or 1.0
         groups = {"scan": kms["scan"], "shuffle": kms["shuf0"] + kms["shuf1"] + kms["shuf2"] + kms["shuf3"] + kms["perm"],
-                  "prefix": kms["prefix"], "gen": kms["gen"], "prep": kms["prep"],
+                  "chain": kms["prefix"], "gen": kms["gen"], "prep": kms["prep"],
                   "edge": kms["edgeprep"] + kms["edgeperm"], "smooth": kms["smooth"], "sched": kms["sched"], "means": kms["means"]}
         dominant = max(groups, key=groups.get)
         elems = float(res_c.perm_elems)  # markers x permutations actually shuffled in one step
@@ -292,17 +292,26 @@ def run_gpu_arm(args):
             "achieved": arcs / scan_s / 1e12 if scan_s else None, "peak": fp64_tinst,
             "unit": "T fp64-pipe lane-inst/s", "frac": (arcs / scan_s / 1e12 / fp64_tinst) if scan_s and fp64_tinst else None,
             "traffic": None, "arcs_per_step": arcs, "slots_issued_per_step": slots,
-            "algorithmic_work": "1 FP64-pipe instruction (DADD S_j - S_i) per arc (i,j) examined; the compare runs on the integer pipe",
+            "algorithmic_work": "1 FP64-pipe instruction (DADD S_j - S_i) per arc (i,j) actually examined; the compare runs on "
+                                "the integer pipe.  Units of 32x8 arcs are discarded beforehand from a table of local extrema, so "
+                                "only a few percent of the reference's candidate arcs are examined: the kernel is bound by the "
+                                "issue of the pruning tests, not by the FP64 pipe",
+            "markers_perms_per_s": elems / scan_s if scan_s else None,
+            "hbm_equivalent": {"bytes_per_marker_perm": 8, "achieved_gbs": 8.0 * elems / scan_s / 1e9 if scan_s else None,
+                               "peak_gbs": peaks["hbm_gbs"], "frac": (8.0 * elems / scan_s / 1e9 / peaks["hbm_gbs"]) if scan_s else None,
+                               "note": "every prefix sum is read at least once (8 B per marker per permutation)"},
             "ms_per_step": kms["scan"], "share_of_step": kms["scan"] / ksum,
             "peak_source": "cbs_gpu_measure_fp64: DADD issue-rate microbenchmark on this GPU in this run "
                            "(MEASURED_PEAKS.json has no FP64 figure)",
         }
         pfx_s = kms["prefix"] * 1e-3
         roof_prefix = {
-            "bound": "hbm", "kernel": "k_prefix", "achieved": 16.0 * elems / pfx_s / 1e9 if pfx_s else None,
+            "bound": "hbm", "kernel": "k_chain", "achieved": 16.0 * elems / pfx_s / 1e9 if pfx_s else None,
             "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": (16.0 * elems / pfx_s / 1e9 / peaks["hbm_gbs"]) if pfx_s else None,
-            "traffic": None, "algorithmic_bytes": "16 B per marker per permutation (read x_perm, write S)",
+            "traffic": None, "algorithmic_bytes": "16 B per marker per permutation (read the permuted value, write S)",
             "ms_per_step": kms["prefix"], "share_of_step": kms["prefix"] / ksum, "peak_source": peaks["source"],
+            "note": "one dependent DADD chain per permutation (8 cycles per marker): latency bound unless thousands of "
+                    "permutations are in flight",
         }
         shuf_s = groups["shuffle"] * 1e-3
         roof_shuffle = {
@@ -310,9 +319,10 @@ def run_gpu_arm(args):
             "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": (16.0 * elems / shuf_s / 1e9 / peaks["hbm_gbs"]) if shuf_s else None,
             "traffic": None, "algorithmic_bytes": "16 B per marker per permutation (8 B gather + 8 B write, SURVEY 8d)",
             "ms_per_step": groups["shuffle"], "share_of_step": groups["shuffle"] / ksum, "peak_source": peaks["source"],
-            "note": "the Fisher-Yates itself runs on 16-bit indices in shared memory; it is latency bound, not HBM bound",
+            "note": "the Fisher-Yates itself runs on 16-bit indices in shared memory; it is latency bound, not HBM bound; "
+                    "classes run concurrently on several streams, so the sum of their times exceeds their share of the step",
         }
-        roofs = {"scan": roof_scan, "prefix": roof_prefix, "shuffle": roof_shuffle}
+        roofs = {"scan": roof_scan, "chain": roof_prefix, "shuffle": roof_shuffle}
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": warm,
             "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -330,7 +340,7 @@ def run_gpu_arm(args):
             "event_profiled_ms_per_step": prof_ms / args.steps,
             "dominant_kernel": dominant,
             "roofline": roofs.get(dominant, roof_scan),
-            "roofline_scan": roof_scan, "roofline_prefix": roof_prefix, "roofline_shuffle": roof_shuffle,
+            "roofline_scan": roof_scan, "roofline_chain": roof_prefix, "roofline_shuffle": roof_shuffle,
             "segments": int(len(res.lengths)), "perms_run": int(res.perms_run), "perm_elements": int(res.perm_elems),
             "rounds": int(res.rounds),
         }

@@ -598,6 +598,7 @@ __device__ __forceinline__ bool cand_better(const Cand& a, const Cand& b) {
 }
 
 #define SCAN_QUEUE 256  // per-warp ring of surviving units (entries)
+#define SCAN_GRING 64   // per-warp ring of surviving groups of 128 arc lengths (entries)
 #define SCAN_LIST 2048  // per-CTA list of block pairs that reach the level (entries)
 
 struct PairGeo {
@@ -665,10 +666,29 @@ __device__ __forceinline__ bool pair_alive(const ScanCtx& c, int bi, int bj, dou
     return c.rn * smx * smx >= level * mn * (1.0 - 1e-12);
 }
 
+// geometry of a block pair: blocks, tie-break data and the two arc-length bands (CBS.cpp:179-180, 198-199)
+__device__ __forceinline__ void pair_geometry(const ScanCtx& c, int bi, int bj, PairGeo& g) {
+    pair_lengths(c, bi, bj, g.ilo, g.ihi, g.jlo, g.jhi, g.lenlo, g.lenhi);
+    // position of the pair in the reference's enumeration (row bi, then bj): the tie-break key of LOC mode
+    g.q = (bi - 1) * c.nb - ((bi - 1) * (bi - 2)) / 2 + (bj - bi);
+    double s1, s2; int clen;
+    pair_corner(c, bi, bj, s1, s2, clen);
+    g.corner = 0.0;
+    if (c.loc) g.corner = c.factab[min(max(clen, 1), c.n - 1)] * ((s1 > s2) ? s1 : s2) * ((s1 > s2) ? s1 : s2);
+    int lenmax = clen;
+    if (lenmax > c.n - lenmax) lenmax = c.n - lenmax;
+    g.bandLo[0] = 1; g.bandHi[0] = 0; g.bandLo[1] = 1; g.bandHi[1] = 0;
+    if (((double)g.lenlo <= c.half) && (g.lenlo <= lenmax)) { g.bandLo[0] = g.lenlo; g.bandHi[0] = lenmax; }
+    const int lenmax2 = c.n - lenmax;
+    if (((double)g.lenhi >= c.half) && (g.lenhi >= lenmax2)) { g.bandLo[1] = lenmax2; g.bandHi[1] = g.lenhi; }
+}
+
 // exact re-evaluation of one unit (slow path): rows i0..i0+31, arc lengths L0..L0+7, restricted to the pair's
-// blocks and to the band [La, Lb]
-__device__ void scan_unit_exact(const ScanCtx& c, const PairGeo& g, int i0, int L0, double sms, int La, int Lb, int side,
-                                ScanSmem* sm) {
+// blocks and to the band of `side`
+__device__ void scan_unit_exact(const ScanCtx& c, int bi, int bj, int side, int i0, int L0, double sms, ScanSmem* sm) {
+    PairGeo g;
+    pair_geometry(c, bi, bj, g);
+    const int La = g.bandLo[side], Lb = g.bandHi[side];
     double best = 0.0;
     double th[8];
 #pragma unroll
@@ -743,11 +763,18 @@ __device__ __forceinline__ float window_bound(const ScanCtx& c, int i0, int js, 
     return fmaxf(__fsub_ru(wmax, rmin), __fsub_ru(rmax, wmin));
 }
 
+// per-warp ring of units that survived the pruning tests; it lives across the pairs of a permutation so that the
+// arcs are (almost) always examined by 32 busy lanes
+struct UnitQueue {
+    int* q;             // SCAN_QUEUE x (unit code, pair code)
+    unsigned head, n;   // entries [head, head+n)
+};
+
 // examine the arcs of one queued unit (fast path): rows i0..i0+31 x lengths L0..L0+7, 4 steps of 8 rows x 8 lengths
-// from registers.  Values beyond the blocks are real neighbouring prefix sums (or the padding behind S_n, finite):
-// a spurious hit there is discarded by the exact re-evaluation.
-__device__ __forceinline__ void scan_unit(const ScanCtx& c, const PairGeo& g, int i0, int L0, int La, int Lb, int side,
-                                          ScanSmem* sm) {
+// from registers.  Nothing is clipped here: arcs outside the pair's blocks or band, and the values behind S_n
+// (finite padding), can only produce a spurious hit, which the exact re-evaluation discards.
+__device__ __forceinline__ void scan_unit(const ScanCtx& c, unsigned code, unsigned pcode, ScanSmem* sm) {
+    const int i0 = (int)(code >> 17) << 5, L0 = (int)(code & 0x1ffffu) << 3;
     // Thresholds for the 8 lengths.  The fast path never compares doubles (DSETP issues at a quarter of the DADD
     // rate on B200): an arc can only beat the level if |S_j - S_i| > th, and then the high word of |S_j - S_i|
     // is >= the high word of th.  Per length the maximum of (hi << 1) (the shift drops the sign) is kept with one
@@ -757,7 +784,7 @@ __device__ __forceinline__ void scan_unit(const ScanCtx& c, const PairGeo& g, in
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
         const int L = L0 + k;
-        const bool in = (L >= La && L <= Lb);
+        const bool in = (L >= c.al0 && L <= c.n - c.al0);
         thk[k] = in ? (((unsigned)__double2hiint(sms * c.gtab[in ? L : 1])) << 1) : 0xffffffffu;
     }
     const double2* pa = reinterpret_cast<const double2*>(c.sx + i0);        // i0 is a multiple of 32,
@@ -790,77 +817,107 @@ __device__ __forceinline__ void scan_unit(const ScanCtx& c, const PairGeo& g, in
     bool flag = false;
 #pragma unroll
     for (int k = 0; k < 8; ++k) flag |= (m[k] >= thk[k]);
-    if (flag) scan_unit_exact(c, g, i0, L0, sms, La, Lb, side, sm);
+    if (flag) scan_unit_exact(c, (int)(pcode >> 16), (int)((pcode >> 1) & 0x7fffu), (int)(pcode & 1u), i0, L0, sms, sm);
 }
 
-// scan one arc-length band [La, Lb] of a block pair with the whole warp
-__device__ void scan_band(const ScanCtx& c, const PairGeo& g, int* queue, int La, int Lb, int side, ScanSmem* sm, int lane) {
-    const int a0 = g.ilo >> 5, nra = (g.ihi >> 5) - a0 + 1;   // aligned rows of 32 positions meeting block i
-    const int s0 = La >> 5, nsg = (Lb >> 5) - s0 + 1;         // aligned groups of 32 arc lengths meeting the band
-    const int total = nra * nsg;
+// examine queued units 32 at a time (all of them if `all`)
+__device__ __forceinline__ void drain_units(const ScanCtx& c, UnitQueue& uq, ScanSmem* sm, int lane, bool all) {
+    while (uq.n >= 32 || (all && uq.n > 0)) {
+        const unsigned take = min(uq.n, 32u);
+        if (lane < take) {
+            const int2 e = *reinterpret_cast<const int2*>(uq.q + 2 * ((uq.head + lane) & (SCAN_QUEUE - 1)));
+            scan_unit(c, (unsigned)e.x, (unsigned)e.y, sm);
+        }
+        __syncwarp();
+        uq.head += take; uq.n -= take;
+    }
+}
+
+// Can the arcs with rows [32a, 32a+31] and lengths [L0, L0+width) that belong to the pair and to the band [La, Lb]
+// reach the level?  False if there are none, or if the extrema of the values they touch stay below the smallest
+// threshold of their lengths.
+__device__ __forceinline__ bool group_may_reach(const ScanCtx& c, const PairGeo& g, const ScanSmem* sm, int a, int L0,
+                                                int width, int La, int Lb) {
+    const int i0 = a << 5;
+    const int imin = max(i0, g.ilo), imax = min(i0 + 31, g.ihi);
+    const int l0 = max(L0, La), l1 = min(L0 + width - 1, Lb);
+    if (l0 > l1 || imax + l1 < g.jlo || imin + l0 > g.jhi) return false;
+    const float smsf = __double2float_rd(*((volatile const double*)&sm->sms));
+    const float th = __fmul_rd(smsf, g_lower_min(c, l0, l1));
+    return !(window_bound(c, i0, i0 + L0, i0 + 31 + L0 + width - 1) < th);
+}
+
+// scan one arc-length band [La, Lb] of a block pair with the whole warp.  The (row, length) plane of the pair is
+// refined top down: groups of 32 rows x 128 lengths, then x 32 lengths, then units of 32 x 8; the survivors of
+// each level are compacted through small rings in shared memory so that all 32 lanes stay busy at the next level.
+__device__ void scan_band(const ScanCtx& c, const PairGeo& g, unsigned pcode, UnitQueue& uq, int* gring, int La, int Lb,
+                          ScanSmem* sm, int lane) {
+    const int a0 = g.ilo >> 5, nra = (g.ihi >> 5) - a0 + 1;    // aligned rows of 32 positions meeting block i
+    const int c0 = La >> 7, ncg = (Lb >> 7) - c0 + 1;          // aligned groups of 128 arc lengths meeting the band
+    const int total = nra * ncg;
     unsigned long long my_arcs = 0, my_slots = 0;
-    unsigned head = 0, qn = 0;  // ring: entries [head, head+qn)
+    unsigned ghead = 0, gn = 0;   // ring of surviving 128-length groups
     for (int base = 0;; base += 32) {
         const bool more = base < total;
         if (more) {
             const int idx = base + lane;
-            unsigned keep4 = 0, code0 = 0;  // surviving 8-length units of this lane's 32-length group
+            bool keep = false;
+            unsigned code = 0;
             if (idx < total) {
-                const int ar = idx / nsg;
-                const int a = a0 + ar, sg = s0 + (idx - ar * nsg);
-                const int i0 = a << 5, Ls = sg << 5;
-                const int imin = max(i0, g.ilo), imax = min(i0 + 31, g.ihi);
-                const int Lmin = max(Ls, La), Lmax = min(Ls + 31, Lb);
+                const int ar = idx / ncg;
+                const int a = a0 + ar, Lc = (c0 + (idx - ar * ncg)) << 7;
+                keep = group_may_reach(c, g, sm, a, Lc, 128, La, Lb);
+                code = ((unsigned)a << 17) | (unsigned)(Lc >> 3);
+            }
+            const unsigned mask = __ballot_sync(FULL, keep);
+            if (mask) {
+                if (keep) gring[(ghead + gn + __popc(mask & ((1u << lane) - 1u))) & (SCAN_GRING - 1)] = (int)code;
+                gn += __popc(mask);
+                __syncwarp();
+            }
+        }
+        // 8 surviving groups -> 32 groups of 32 lengths, one per lane
+        while (gn >= 8 || (!more && gn > 0)) {
+            const unsigned gtake = min(gn, 8u);
+            unsigned keep4 = 0, code0 = 0;  // surviving 8-length units of this lane's 32-length group
+            if ((unsigned)(lane >> 2) < gtake) {
+                const unsigned gc = (unsigned)gring[(ghead + (lane >> 2)) & (SCAN_GRING - 1)];
+                const int a = (int)(gc >> 17), Ls = ((int)(gc & 0x1ffffu) << 3) + 32 * (lane & 3);
                 code0 = ((unsigned)a << 17) | (unsigned)(Ls >> 3);
-                if (imax + Lmax >= g.jlo && imin + Lmin <= g.jhi) {
-                    // g[L] is concave: its minimum over a run of lengths is at one end
-                    const float smsf = __double2float_rd(*((volatile double*)&sm->sms));
-                    const float th32 = __fmul_rd(smsf, g_lower_min(c, Lmin, Lmax));
-                    if (!(window_bound(c, i0, i0 + Ls, i0 + Ls + 62) < th32)) {
+                if (group_may_reach(c, g, sm, a, Ls, 32, La, Lb)) {
 #pragma unroll
-                        for (int t = 0; t < 4; ++t) {
-                            const int L0 = Ls + 8 * t;
-                            const int l0 = max(L0, La), l1 = min(L0 + 7, Lb);
-                            if (l0 > l1 || imax + l1 < g.jlo || imin + l0 > g.jhi) continue;
-                            const float th8 = __fmul_rd(smsf, g_lower_min(c, l0, l1));
-                            if (window_bound(c, i0, i0 + L0, i0 + L0 + 38) < th8) continue;
-                            keep4 |= 1u << t;
-                        }
+                    for (int t = 0; t < 4; ++t)
+                        if (group_may_reach(c, g, sm, a, Ls + 8 * t, 8, La, Lb)) keep4 |= 1u << t;
+                }
+                if (keep4 && (c.arcs || c.slots)) {  // profiling: arcs of the pair and band inside the queued units
+                    const int i0 = a << 5;
+                    for (int k = 0; k < 32; ++k) {
+                        const int L = Ls + k;
+                        if (!((keep4 >> (k >> 3)) & 1u) || L < La || L > Lb) continue;
+                        const int ia = max(max(i0, g.ilo), g.jlo - L), ib = min(min(i0 + 31, g.ihi), g.jhi - L);
+                        if (ib >= ia) my_arcs += (unsigned long long)(ib - ia + 1);
                     }
+                    my_slots += 256ull * __popc(keep4);
                 }
             }
+            __syncwarp();
+            ghead += gtake; gn -= gtake;
             const int cnt = __popc(keep4);
             int incl = cnt;
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(FULL, incl, o); if (lane >= o) incl += v; }
             const int added = __shfl_sync(FULL, incl, 31);
             if (added) {
-                const unsigned at = head + qn + (unsigned)(incl - cnt);
+                const unsigned at = uq.head + uq.n + (unsigned)(incl - cnt);
 #pragma unroll
                 for (int t = 0; t < 4; ++t)
-                    if ((keep4 >> t) & 1u) queue[(at + __popc(keep4 & ((1u << t) - 1u))) & (SCAN_QUEUE - 1)] = (int)(code0 + (unsigned)t);
-                qn += (unsigned)added;
+                    if ((keep4 >> t) & 1u)
+                        *reinterpret_cast<int2*>(uq.q + 2 * ((at + __popc(keep4 & ((1u << t) - 1u))) & (SCAN_QUEUE - 1))) =
+                            make_int2((int)(code0 + (unsigned)t), (int)pcode);
+                uq.n += (unsigned)added;
                 __syncwarp();
             }
-        }
-        while (qn >= 32 || (!more && qn > 0)) {
-            const unsigned take = min(qn, 32u);
-            if (lane < take) {
-                const unsigned code = (unsigned)queue[(head + lane) & (SCAN_QUEUE - 1)];
-                const int i0 = (int)(code >> 17) << 5, L0 = (int)(code & 0x1ffffu) << 3;
-                my_slots += 256;
-                if (c.arcs) {
-                    for (int k = 0; k < 8; ++k) {
-                        const int L = L0 + k;
-                        if (L < La || L > Lb) continue;
-                        const int ia = max(max(i0, g.ilo), g.jlo - L), ib = min(min(i0 + 31, g.ihi), g.jhi - L);
-                        if (ib >= ia) my_arcs += (unsigned long long)(ib - ia + 1);
-                    }
-                }
-                scan_unit(c, g, i0, L0, La, Lb, side, sm);
-            }
-            __syncwarp();
-            head += take; qn -= take;
+            drain_units(c, uq, sm, lane, false);
         }
         if (!more) break;
     }
@@ -869,24 +926,13 @@ __device__ void scan_band(const ScanCtx& c, const PairGeo& g, int* queue, int La
     __syncwarp();
 }
 
-// bands of one block pair (CBS.cpp:179-180, 198-199) and their scan
-__device__ void scan_pair(const ScanCtx& c, int bi, int bj, int* queue, ScanSmem* sm, int lane) {
+// the two bands of one block pair
+__device__ void scan_pair(const ScanCtx& c, int bi, int bj, UnitQueue& uq, int* gring, ScanSmem* sm, int lane) {
     PairGeo g;
-    pair_lengths(c, bi, bj, g.ilo, g.ihi, g.jlo, g.jhi, g.lenlo, g.lenhi);
-    // position of the pair in the reference's enumeration (row bi, then bj): the tie-break key of LOC mode
-    g.q = (bi - 1) * c.nb - ((bi - 1) * (bi - 2)) / 2 + (bj - bi);
-    double s1, s2; int clen;
-    pair_corner(c, bi, bj, s1, s2, clen);
-    g.corner = 0.0;
-    if (c.loc) g.corner = c.factab[min(max(clen, 1), c.n - 1)] * ((s1 > s2) ? s1 : s2) * ((s1 > s2) ? s1 : s2);
-    int lenmax = clen;
-    if (lenmax > c.n - lenmax) lenmax = c.n - lenmax;
-    g.bandLo[0] = 1; g.bandHi[0] = 0; g.bandLo[1] = 1; g.bandHi[1] = 0;
-    if (((double)g.lenlo <= c.half) && (g.lenlo <= lenmax)) { g.bandLo[0] = g.lenlo; g.bandHi[0] = lenmax; }
-    const int lenmax2 = c.n - lenmax;
-    if (((double)g.lenhi >= c.half) && (g.lenhi >= lenmax2)) { g.bandLo[1] = lenmax2; g.bandHi[1] = g.lenhi; }
-    if (g.bandLo[0] <= g.bandHi[0]) scan_band(c, g, queue, g.bandLo[0], g.bandHi[0], 0, sm, lane);
-    if (g.bandLo[1] <= g.bandHi[1]) scan_band(c, g, queue, g.bandLo[1], g.bandHi[1], 1, sm, lane);
+    pair_geometry(c, bi, bj, g);
+    const unsigned pcode = (((unsigned)bi << 15) | (unsigned)bj) << 1;
+    if (g.bandLo[0] <= g.bandHi[0]) scan_band(c, g, pcode, uq, gring, g.bandLo[0], g.bandHi[0], sm, lane);
+    if (g.bandLo[1] <= g.bandHi[1]) scan_band(c, g, pcode | 1u, uq, gring, g.bandLo[1], g.bandHi[1], sm, lane);
 }
 
 // dynamic shared memory layout helper (host + device)
@@ -897,7 +943,7 @@ struct ScanLayout {
     int warps;
     CBS_HD size_t bytes() const {
         return ((sizeof(ScanSmem) + 15) & ~(size_t)15) + 2 * (size_t)nb_max * 8 + 3 * (size_t)nb_max * 4 + 2 * (size_t)nt * 4 +
-               (size_t)warps * SCAN_QUEUE * 4 + (size_t)SCAN_LIST * 4 + 64;
+               (size_t)warps * (2 * SCAN_QUEUE + SCAN_GRING) * 4 + (size_t)SCAN_LIST * 4 + 64;
     }
     // table geometry for units of up to nmax markers: at most 16384 entries (128 KB)
     CBS_HD void set_table(long long nmax) {
@@ -918,8 +964,8 @@ __global__ void __launch_bounds__(256, 3) k_scan(Dev* D, ScanLayout lay) {
     int* s_bb = s_amax + lay.nb_max;
     float* s_tmin = (float*)(s_bb + lay.nb_max);
     float* s_tmax = s_tmin + lay.nt;
-    int* s_queue = (int*)(s_tmax + lay.nt);
-    int* s_list = s_queue + lay.warps * SCAN_QUEUE;
+    int* s_queue = (int*)(((size_t)(s_tmax + lay.nt) + 7) & ~(size_t)7);  // entries are int2
+    int* s_list = s_queue + lay.warps * (2 * SCAN_QUEUE + SCAN_GRING);
     __shared__ int s_g;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int nwarps = blockDim.x >> 5;
@@ -1086,7 +1132,10 @@ __global__ void __launch_bounds__(256, 3) k_scan(Dev* D, ScanLayout lay) {
             // (a) the warps evaluate the pair bounds 32 pairs at a time and append the pairs that reach the level to
             // a list in shared memory; (b) the warps pop ONE pair at a time and scan it, so that the load is balanced
             // at the grain of a pair.  Repeated while pairs remain (the list is bounded).
-            int* queue = s_queue + warp * SCAN_QUEUE;
+            UnitQueue uq;
+            uq.q = s_queue + warp * (2 * SCAN_QUEUE + SCAN_GRING);
+            uq.head = 0; uq.n = 0;
+            int* gring = uq.q + 2 * SCAN_QUEUE;
             for (;;) {
                 for (;;) {
                     if (*((volatile int*)&sm->n_list) > SCAN_LIST - 32 * nwarps) break;  // every warp may still add 32
@@ -1122,8 +1171,9 @@ __global__ void __launch_bounds__(256, 3) k_scan(Dev* D, ScanLayout lay) {
                     const int code = s_list[w];
                     const int bi = code >> 16, bj = code & 0xffff;
                     if (!pair_alive(c, bi, bj, *((volatile double*)&sm->level))) continue;  // the level may have risen
-                    scan_pair(c, bi, bj, queue, sm, lane);
+                    scan_pair(c, bi, bj, uq, gring, sm, lane);
                 }
+                drain_units(c, uq, sm, lane, true);  // the level may still rise: flush before the next list
                 __syncthreads();
                 const bool finished = sm->next_pair >= npairs;
                 __syncthreads();
