@@ -440,7 +440,7 @@ int run_cbs(cbs_gpu_ctx* c, const std::vector<long long>& off, const uint64_t* u
     // shared-memory shuffle kernel, one launch per segment-length class present in this call
     size_t shuf_smem[SHUF_GLOBAL]; int shuf_occ[SHUF_GLOBAL]; bool shuf_on[SHUF_GLOBAL];
     for (int cls = 0; cls < SHUF_GLOBAL; ++cls) {
-        shuf_smem[cls] = (size_t)shuffle_class_max(cls) * 2 + 32;
+        shuf_smem[cls] = (size_t)shuffle_class_max(cls) * 2 + 32 + FY_SCRATCH;
         shuf_on[cls] = (cls == 0) || Nmax > shuffle_class_max(cls - 1);  // no unit is long enough otherwise
         shuf_occ[cls] = (int)std::max<size_t>(1, std::min<size_t>(32, (c->smem_optin + 1024) / (shuf_smem[cls] + 1024)));
     }

@@ -331,17 +331,28 @@ struct IdxGlobal {
 
 // 32 consecutive Fisher-Yates steps (CBS.cpp:489-492) taken by the 32 lanes at once: lane l swaps row i-1
 // (i = i0-l) with row j-1.  A step commutes with the others of its group unless it shares a row with one of
-// them; those few (match.any on j, or a target inside the group's own rows) are replayed in order afterwards.
+// them; those few are replayed in order afterwards, so the result is the sequential shuffle.  Sharing is
+// detected through a small table in shared memory (match.any costs ~400 cycles on B200): every lane writes its
+// id into slot j mod 2048 and reads it back -- whoever does not find itself shares the slot with the winner
+// (same target, or a harmless hash collision); a target inside the group's own rows flags the owner of that row.
+#define FY_TAB 2048
+#define FY_SCRATCH (FY_TAB + 128)  // bytes of per-warp scratch: claim table + one flag per step of a round
 template <class Idx>
-__device__ __forceinline__ void fy_group(Idx s_idx, int i0, int i, int j, int lane) {
-    const unsigned same = __match_any_sync(FULL, j);
+__device__ __forceinline__ void fy_group(Idx s_idx, unsigned char* tab, int i0, int i, int j, int lane) {
+    unsigned char* cflag = tab + FY_TAB;
+    const int slot = j & (FY_TAB - 1);
     const int m = i0 - j;  // lane whose row is my target
     const bool tgt = (m >= 0) && (m < 32) && (m != lane);
-    const unsigned tmask = __reduce_or_sync(FULL, tgt ? (1u << m) : 0u);
-    const bool conflict = (__popc(same) > 1) || tgt || ((tmask >> lane) & 1u);
-    int vi = 0, vj = 0;
-    if (!conflict) { vi = s_idx.ld(i - 1); vj = s_idx.ld(j - 1); }
+    tab[slot] = (unsigned char)lane;
+    if (tgt) cflag[m] = 1;
     __syncwarp();
+    const int w = tab[slot];
+    const bool loser = (w != lane);
+    if (loser) cflag[w] = 1;
+    const int vi = s_idx.ld(i - 1), vj = s_idx.ld(j - 1);
+    __syncwarp();
+    const bool conflict = loser || tgt || (cflag[lane] != 0);
+    cflag[lane] = 0;
     if (!conflict) { s_idx.st(i - 1, vj); s_idx.st(j - 1, vi); }
     __syncwarp();
     unsigned cm = __ballot_sync(FULL, conflict);
@@ -356,9 +367,59 @@ __device__ __forceinline__ void fy_group(Idx s_idx, int i0, int i, int j, int la
     }
 }
 
+// K*32 consecutive steps at once: lane l takes steps i = i0 - 32k - l, k = 0..K-1 (step id 32k+l).  Same scheme as
+// fy_group with one round of claims for all K*32 steps, so the three shared-memory round trips of a round are
+// paid once per K*32 steps.  Used while i0 is large (few steps of a round share a row).
+template <int K, class Idx>
+__device__ __forceinline__ void fy_multi(Idx s_idx, unsigned char* tab, int i0, const int (&j)[K], int lane) {
+    unsigned char* cflag = tab + FY_TAB;
+    bool tgt[K], loser[K];
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        const int m = i0 - j[k];  // id of the step whose row is my target
+        tgt[k] = (m >= 0) && (m < 32 * K) && (m != 32 * k + lane);
+        tab[j[k] & (FY_TAB - 1)] = (unsigned char)(32 * k + lane);
+        if (tgt[k]) cflag[m] = 1;
+    }
+    __syncwarp();
+    int vi[K], vj[K];
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        const int w = tab[j[k] & (FY_TAB - 1)];
+        loser[k] = (w != 32 * k + lane);
+        if (loser[k]) cflag[w] = 1;
+        vi[k] = s_idx.ld(i0 - 32 * k - lane - 1);
+        vj[k] = s_idx.ld(j[k] - 1);
+    }
+    __syncwarp();
+    bool conflict[K];
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        conflict[k] = loser[k] || tgt[k] || (cflag[32 * k + lane] != 0);
+        cflag[32 * k + lane] = 0;
+        if (!conflict[k]) { s_idx.st(i0 - 32 * k - lane - 1, vj[k]); s_idx.st(j[k] - 1, vi[k]); }
+    }
+    __syncwarp();
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        unsigned cm = __ballot_sync(FULL, conflict[k]);
+        while (cm) {
+            const int l = __ffs(cm) - 1;
+            cm &= cm - 1;
+            if (lane == l) {
+                const int r = i0 - 32 * k - lane - 1;
+                const int a = s_idx.ld(r), b = s_idx.ld(j[k] - 1);
+                s_idx.st(r, b); s_idx.st(j[k] - 1, a);
+            }
+            __syncwarp();
+        }
+    }
+}
+#define FY_MULTI_MIN 8192  // rounds of 128 steps while i0 is at least this
+
 #define PERM_CHUNK 512
 template <class Idx>
-__device__ void perm_warp(Dev* D, const Task& t, int p, Idx s_idx, int lane) {
+__device__ void perm_warp(Dev* D, const Task& t, int p, Idx s_idx, unsigned char* tab, int lane) {
     const int n = t.n;
     const long long base = D->unit_off[t.unit] + t.lo;
     const double* __restrict__ cur = D->cur + base;
@@ -382,11 +443,22 @@ __device__ void perm_warp(Dev* D, const Task& t, int p, Idx s_idx, int lane) {
 #pragma unroll
             for (int q = 0; q < 8; ++q) { const int g = g0 + 8 + q; nxt[q] = (g < G) ? win[32 * g + lane] : 0ull; }
 #pragma unroll
-            for (int q = 0; q < 8; ++q) {
-                if (g0 + q < G) {
-                    const int i = i0 - lane;
-                    fy_group(s_idx, i0, i, draw_index(mt_temper(raw[q]), i), lane);
-                    i0 -= 32;
+            for (int h = 0; h < 2; ++h) {
+                if (g0 + 4 * h + 3 < G && i0 >= FY_MULTI_MIN) {
+                    int j4[4];
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) j4[k] = draw_index(mt_temper(raw[4 * h + k]), i0 - 32 * k - lane);
+                    fy_multi<4>(s_idx, tab, i0, j4, lane);
+                    i0 -= 128;
+                } else {
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        if (g0 + 4 * h + k < G) {
+                            const int i = i0 - lane;
+                            fy_group(s_idx, tab, i0, i, draw_index(mt_temper(raw[4 * h + k]), i), lane);
+                            i0 -= 32;
+                        }
+                    }
                 }
             }
 #pragma unroll
@@ -405,13 +477,23 @@ __device__ void perm_warp(Dev* D, const Task& t, int p, Idx s_idx, int lane) {
             }
         }
     } else {
-        for (int g = 0; g < G; ++g, i0 -= 32) {
-            const int i = i0 - lane;
+        auto philox_j = [&](int i) {
             const uint32_t kd = (uint32_t)(n - i);
             uint32_t o[4];
             philox4x32_10(kd >> 1, permno, 0u, 0u, k0, k1, o);
             const uint64_t u = (kd & 1u) ? (((uint64_t)o[3] << 32) | o[2]) : (((uint64_t)o[1] << 32) | o[0]);
-            fy_group(s_idx, i0, i, draw_index(u, i), lane);
+            return draw_index(u, i);
+        };
+        int g = 0;
+        for (; g + 3 < G && i0 >= FY_MULTI_MIN; g += 4, i0 -= 128) {
+            int j4[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) j4[k] = philox_j(i0 - 32 * k - lane);
+            fy_multi<4>(s_idx, tab, i0, j4, lane);
+        }
+        for (; g < G; ++g, i0 -= 32) {
+            const int i = i0 - lane;
+            fy_group(s_idx, tab, i0, i, philox_j(i), lane);
         }
         if (lane == 0) {
             DrawSrc src;
@@ -445,9 +527,12 @@ __device__ void perm_warp(Dev* D, const Task& t, int p, Idx s_idx, int lane) {
 
 __global__ void __launch_bounds__(32) k_perm_smem(Dev* D, int cls) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    unsigned short* s_idx = (unsigned short*)smem_raw;
+    unsigned char* tab = smem_raw;  // FY_SCRATCH bytes, then the index array
+    unsigned short* s_idx = (unsigned short*)(smem_raw + FY_SCRATCH);
     if (D->done) return;
     const int lane = threadIdx.x;
+    for (int k = lane; k < FY_SCRATCH - FY_TAB; k += 32) tab[FY_TAB + k] = 0;
+    __syncwarp();
     const int nl = D->n_shuf[cls];
     const int total = D->shuf_prefix[cls][nl];
     for (;;) {
@@ -457,7 +542,7 @@ __global__ void __launch_bounds__(32) k_perm_smem(Dev* D, int cls) {
         if (g >= total) break;
         const int k = find_item(D->shuf_prefix[cls], nl, g);
         const PermItem it = D->items[D->shuf_item[cls][k]];
-        perm_warp(D, D->tasks[it.task], g - D->shuf_prefix[cls][k], IdxSmem{s_idx}, lane);
+        perm_warp(D, D->tasks[it.task], g - D->shuf_prefix[cls][k], IdxSmem{s_idx}, tab, lane);
     }
 }
 
@@ -466,8 +551,12 @@ __global__ void __launch_bounds__(32) k_perm_smem(Dev* D, int cls) {
 // array (32-bit) does not fit in shared memory and lives in the arena (L2-resident accesses).
 // ------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128) k_perm(Dev* D) {
+    __shared__ __align__(16) unsigned char tab_all[4][FY_SCRATCH];
     if (D->done) return;
     const int lane = threadIdx.x & 31;
+    unsigned char* tab = tab_all[threadIdx.x >> 5];
+    for (int k = lane; k < FY_SCRATCH - FY_TAB; k += 32) tab[FY_TAB + k] = 0;
+    __syncwarp();
     const int nl = D->n_shuf[SHUF_GLOBAL];
     const int total = D->shuf_prefix[SHUF_GLOBAL][nl];
     for (;;) {
@@ -481,7 +570,7 @@ __global__ void __launch_bounds__(128) k_perm(Dev* D) {
         const int p = g - D->shuf_prefix[SHUF_GLOBAL][k];
         const long long idxd = Sched::idx_stride(t.n);  // doubles per permutation (cbs_core.h plan_perm)
         unsigned int* idx = (unsigned int*)(D->arena + t.off_A + (long long)p * idxd);
-        perm_warp(D, t, p, IdxGlobal{idx}, lane);
+        perm_warp(D, t, p, IdxGlobal{idx}, tab, lane);
     }
 }
 
