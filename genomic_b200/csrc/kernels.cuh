@@ -319,11 +319,13 @@ __global__ void __launch_bounds__(320) k_gen_par(Dev* D) {
 // ------------------------------------------------------------------------------------
 // index-array accessors: shared memory (16-bit) or global memory (32-bit, L2 only: ld/st.cg)
 struct IdxSmem {
+    static constexpr bool kClaimTable = true;   // conflicts through the claim table (a false positive costs ~80 cycles)
     unsigned short* a;
     __device__ __forceinline__ int ld(int k) const { return a[k]; }
     __device__ __forceinline__ void st(int k, int v) const { a[k] = (unsigned short)v; }
 };
 struct IdxGlobal {
+    static constexpr bool kClaimTable = false;  // a replayed step costs an L2 round trip: exact detection (match.any)
     unsigned int* a;
     __device__ __forceinline__ int ld(int k) const { return (int)__ldcg(a + k); }
     __device__ __forceinline__ void st(int k, int v) const { __stcg(a + k, (unsigned int)v); }
@@ -333,12 +335,34 @@ struct IdxGlobal {
 // (i = i0-l) with row j-1.  A step commutes with the others of its group unless it shares a row with one of
 // them; those few are replayed in order afterwards, so the result is the sequential shuffle.  Sharing is
 // detected through a small table in shared memory (match.any costs ~400 cycles on B200): every lane writes its
-// id into slot j mod 2048 and reads it back -- whoever does not find itself shares the slot with the winner
+// id into slot j mod 8192 and reads it back -- whoever does not find itself shares the slot with the winner
 // (same target, or a harmless hash collision); a target inside the group's own rows flags the owner of that row.
-#define FY_TAB 2048
+#define FY_TAB 8192
 #define FY_SCRATCH (FY_TAB + 128)  // bytes of per-warp scratch: claim table + one flag per step of a round
 template <class Idx>
 __device__ __forceinline__ void fy_group(Idx s_idx, unsigned char* tab, int i0, int i, int j, int lane) {
+    if (!Idx::kClaimTable) {
+        const int vi = s_idx.ld(i - 1), vj = s_idx.ld(j - 1);  // in flight while match.any resolves
+        const unsigned same = __match_any_sync(FULL, j);
+        const int m = i0 - j;  // lane whose row is my target
+        const bool tgt = (m >= 0) && (m < 32) && (m != lane);
+        const unsigned tmask = __reduce_or_sync(FULL, tgt ? (1u << m) : 0u);
+        const bool conflict = (__popc(same) > 1) || tgt || ((tmask >> lane) & 1u);
+        __syncwarp();
+        if (!conflict) { s_idx.st(i - 1, vj); s_idx.st(j - 1, vi); }
+        __syncwarp();
+        unsigned cm = __ballot_sync(FULL, conflict);
+        while (cm) {
+            const int l = __ffs(cm) - 1;
+            cm &= cm - 1;
+            if (lane == l) {
+                const int a = s_idx.ld(i - 1), b = s_idx.ld(j - 1);
+                s_idx.st(i - 1, b); s_idx.st(j - 1, a);
+            }
+            __syncwarp();
+        }
+        return;
+    }
     unsigned char* cflag = tab + FY_TAB;
     const int slot = j & (FY_TAB - 1);
     const int m = i0 - j;  // lane whose row is my target
@@ -373,29 +397,48 @@ __device__ __forceinline__ void fy_group(Idx s_idx, unsigned char* tab, int i0, 
 template <int K, class Idx>
 __device__ __forceinline__ void fy_multi(Idx s_idx, unsigned char* tab, int i0, const int (&j)[K], int lane) {
     unsigned char* cflag = tab + FY_TAB;
-    bool tgt[K], loser[K];
+    bool tgt[K], dup[K];
 #pragma unroll
     for (int k = 0; k < K; ++k) {
         const int m = i0 - j[k];  // id of the step whose row is my target
         tgt[k] = (m >= 0) && (m < 32 * K) && (m != 32 * k + lane);
         tab[j[k] & (FY_TAB - 1)] = (unsigned char)(32 * k + lane);
         if (tgt[k]) cflag[m] = 1;
+        dup[k] = false;
     }
     __syncwarp();
     int vi[K], vj[K];
+    bool loser[K];
 #pragma unroll
     for (int k = 0; k < K; ++k) {
-        const int w = tab[j[k] & (FY_TAB - 1)];
-        loser[k] = (w != 32 * k + lane);
-        if (loser[k]) cflag[w] = 1;
         vi[k] = s_idx.ld(i0 - 32 * k - lane - 1);
         vj[k] = s_idx.ld(j[k] - 1);
+        loser[k] = (tab[j[k] & (FY_TAB - 1)] != 32 * k + lane);
+    }
+    // a step that lost its slot shares it with a step of the same target (a real conflict) or merely of the same
+    // hash: settle it exactly, the targets of all K*32 steps are in registers
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        unsigned lm = __ballot_sync(FULL, loser[k]);
+        while (lm) {
+            const int l = __ffs(lm) - 1;
+            lm &= lm - 1;
+            const int jj = __shfl_sync(FULL, j[k], l);
+            bool hit = false;
+#pragma unroll
+            for (int k2 = 0; k2 < K; ++k2) {
+                const bool same = (j[k2] == jj) && !(k2 == k && lane == l);
+                dup[k2] |= same;
+                hit |= same;
+            }
+            if (__any_sync(FULL, hit) && lane == l) dup[k] = true;
+        }
     }
     __syncwarp();
     bool conflict[K];
 #pragma unroll
     for (int k = 0; k < K; ++k) {
-        conflict[k] = loser[k] || tgt[k] || (cflag[32 * k + lane] != 0);
+        conflict[k] = dup[k] || tgt[k] || (cflag[32 * k + lane] != 0);
         cflag[32 * k + lane] = 0;
         if (!conflict[k]) { s_idx.st(i0 - 32 * k - lane - 1, vj[k]); s_idx.st(j[k] - 1, vi[k]); }
     }
@@ -444,7 +487,7 @@ __device__ void perm_warp(Dev* D, const Task& t, int p, Idx s_idx, unsigned char
             for (int q = 0; q < 8; ++q) { const int g = g0 + 8 + q; nxt[q] = (g < G) ? win[32 * g + lane] : 0ull; }
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
-                if (g0 + 4 * h + 3 < G && i0 >= FY_MULTI_MIN) {
+                if (Idx::kClaimTable && g0 + 4 * h + 3 < G && i0 >= FY_MULTI_MIN) {
                     int j4[4];
 #pragma unroll
                     for (int k = 0; k < 4; ++k) j4[k] = draw_index(mt_temper(raw[4 * h + k]), i0 - 32 * k - lane);
@@ -485,7 +528,7 @@ __device__ void perm_warp(Dev* D, const Task& t, int p, Idx s_idx, unsigned char
             return draw_index(u, i);
         };
         int g = 0;
-        for (; g + 3 < G && i0 >= FY_MULTI_MIN; g += 4, i0 -= 128) {
+        for (; Idx::kClaimTable && g + 3 < G && i0 >= FY_MULTI_MIN; g += 4, i0 -= 128) {
             int j4[4];
 #pragma unroll
             for (int k = 0; k < 4; ++k) j4[k] = philox_j(i0 - 32 * k - lane);
@@ -511,15 +554,15 @@ __device__ void perm_warp(Dev* D, const Task& t, int p, Idx s_idx, unsigned char
     // only a few index arrays, but dozens of chains.)
     double* sx = D->arena + t.off_sx + (long long)p * Sched::sx_stride(n);
     int k = lane;
-    for (; k + 224 < n; k += 256) {
-        int id[8];
+    for (; k + 480 < n; k += 512) {
+        int id[16];
 #pragma unroll
-        for (int q = 0; q < 8; ++q) id[q] = s_idx.ld(k + 32 * q);
-        double v[8];
+        for (int q = 0; q < 16; ++q) id[q] = s_idx.ld(k + 32 * q);
+        double v[16];
 #pragma unroll
-        for (int q = 0; q < 8; ++q) v[q] = cur[id[q]];
+        for (int q = 0; q < 16; ++q) v[q] = __ldg(cur + id[q]);
 #pragma unroll
-        for (int q = 0; q < 8; ++q) sx[k + 1 + 32 * q] = v[q];
+        for (int q = 0; q < 16; ++q) sx[k + 1 + 32 * q] = v[q];
     }
     for (; k < n; k += 32) sx[k + 1] = cur[s_idx.ld(k)];
     __syncwarp();
@@ -551,12 +594,9 @@ __global__ void __launch_bounds__(32) k_perm_smem(Dev* D, int cls) {
 // array (32-bit) does not fit in shared memory and lives in the arena (L2-resident accesses).
 // ------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128) k_perm(Dev* D) {
-    __shared__ __align__(16) unsigned char tab_all[4][FY_SCRATCH];
     if (D->done) return;
     const int lane = threadIdx.x & 31;
-    unsigned char* tab = tab_all[threadIdx.x >> 5];
-    for (int k = lane; k < FY_SCRATCH - FY_TAB; k += 32) tab[FY_TAB + k] = 0;
-    __syncwarp();
+    unsigned char* tab = nullptr;  // IdxGlobal does not use the claim table (measured: 128-step rounds lose on L2 arrays)
     const int nl = D->n_shuf[SHUF_GLOBAL];
     const int total = D->shuf_prefix[SHUF_GLOBAL][nl];
     for (;;) {
