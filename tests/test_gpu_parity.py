@@ -69,6 +69,17 @@ def test_tmaxo_large(ctx, oracle):
         assert ctx.tmaxo(xc, tss, 2) == oracle.tmaxo(xc, tss, 2)
 
 
+def test_tmaxo_very_long_vector_coarse_table(ctx, oracle):
+    # > 524288 markers: the scan's extrema table covers runs of 64 prefix sums per entry instead of 32
+    rng = np.random.default_rng(13)
+    n = 600000
+    x = f32(rng.normal(0, 0.2, n))
+    x[n // 5: n // 4] += 0.02
+    xc = x - x.mean()
+    tss = float((xc * xc).sum())
+    assert ctx.tmaxo(xc, tss, 2) == oracle.tmaxo(xc, tss, 2)
+
+
 def test_tmaxp_matches_oracle(ctx, oracle):
     rng = np.random.default_rng(13)
     for n in (4, 7, 49, 50, 51, 200, 1000, 5000):
