@@ -71,6 +71,8 @@ struct cbs_gpu_ctx {
     // side streams: kernels of one round that do not depend on each other run concurrently
     cudaStream_t side[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
     cudaEvent_t ev_sched = nullptr, ev_gen = nullptr, ev_side[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    cudaStream_t gen_stream = nullptr;  // the MT stream is generated one round ahead on this stream
+    cudaEvent_t ev_ahead = nullptr;
 };
 
 namespace {
@@ -451,6 +453,7 @@ int run_cbs(cbs_gpu_ctx* c, const std::vector<long long>& off, const uint64_t* u
     const int G = 8;  // rounds per group
     const bool debug = env_ll("CBS_GPU_DEBUG", 0) != 0;
     int groups_in_flight = 0, rounds = 0;
+    bool ahead_pending = false;
     int gi = 0;
     for (;;) {
         for (int r = 0; r < G; ++r) {
@@ -459,6 +462,7 @@ int run_cbs(cbs_gpu_ctx* c, const std::vector<long long>& off, const uint64_t* u
             //   main : sched, gen, [shuffle classes], prefix, scan
             //   side0: prep            side1: edgeprep, edgeperm
             //   side2, side3: other shuffle classes      side4: shuffle of segments > 65535 markers
+            if (ahead_pending) { cudaStreamWaitEvent(st, c->ev_ahead, 0); ahead_pending = false; }
             { LaunchTimer t(c, K_SCHED); k_sched<<<1, 256, 0, st>>>(dD, c->d_done); }
             cudaEventRecord(c->ev_sched, st);
             cudaStreamWaitEvent(c->side[0], c->ev_sched, 0);
@@ -471,11 +475,20 @@ int run_cbs(cbs_gpu_ctx* c, const std::vector<long long>& off, const uint64_t* u
             if (mt) {
                 LaunchTimer t(c, K_GEN);
                 if (shared_stream) {
-                    k_gen_lead<<<1, 192, 0, st>>>(dD);
+                    k_gen_lead<<<1, 192, 0, st>>>(dD, 0);
                     if (hD.jump_polys) { k_gen_par<<<GEN_NSEG, 320, 0, st>>>(dD); c->launches++; }
                 } else k_gen<<<std::min(std::max(1, n_chains), c->sm_count * 4), 192, 0, st>>>(dD);
             }
             cudaEventRecord(c->ev_gen, st);
+            if (mt && shared_stream && hD.jump_polys) {
+                // generate ahead for the next round, next to this round's shuffles and scan
+                cudaStreamWaitEvent(c->gen_stream, c->ev_gen, 0);
+                k_gen_lead<<<1, 192, 0, c->gen_stream>>>(dD, 1);
+                k_gen_par<<<GEN_NSEG, 320, 0, c->gen_stream>>>(dD);
+                c->launches += 2;
+                cudaEventRecord(c->ev_ahead, c->gen_stream);
+                ahead_pending = true;
+            }
             // shuffles: classes alternate between the main stream and three side streams so that they run
             // concurrently (each class is latency bound on its own); the longest present class goes first
             bool used_side[5] = {false, false, false, false, false};
@@ -526,6 +539,7 @@ int run_cbs(cbs_gpu_ctx* c, const std::vector<long long>& off, const uint64_t* u
         }
         if (rounds > 50000000) return fail(c, CBS_GPU_ERR_CUDA, "scheduler did not terminate");
     }
+    CUDA_TRY(c, cudaStreamSynchronize(c->gen_stream));
     CUDA_TRY(c, cudaStreamSynchronize(st));
     CUDA_TRY(c, cudaGetLastError());
     CUDA_TRY(c, cudaMemcpy(&hD, dD, sizeof(Dev), cudaMemcpyDeviceToHost));
@@ -710,6 +724,8 @@ int cbs_gpu_create(const int* device_ids, int ndev, cbs_gpu_ctx** out) {
     }
     cudaEventCreateWithFlags(&c->ev_sched, cudaEventDisableTiming);
     cudaEventCreateWithFlags(&c->ev_gen, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&c->ev_ahead, cudaEventDisableTiming);
+    cudaStreamCreateWithFlags(&c->gen_stream, cudaStreamNonBlocking);
     *out = c;
     return CBS_GPU_OK;
 }
@@ -734,6 +750,8 @@ void cbs_gpu_destroy(cbs_gpu_ctx* c) {
     for (int k = 0; k < 5; ++k) { if (c->side[k]) cudaStreamDestroy(c->side[k]); if (c->ev_side[k]) cudaEventDestroy(c->ev_side[k]); }
     if (c->ev_sched) cudaEventDestroy(c->ev_sched);
     if (c->ev_gen) cudaEventDestroy(c->ev_gen);
+    if (c->ev_ahead) cudaEventDestroy(c->ev_ahead);
+    if (c->gen_stream) cudaStreamDestroy(c->gen_stream);
     if (c->own_stream) cudaStreamDestroy(c->own_stream);
     delete c;
 }

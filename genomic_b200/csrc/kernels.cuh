@@ -257,10 +257,25 @@ __device__ void gen_sequential(uint64_t* w, long long from, long long to, uint64
     }
 }
 
-__global__ void __launch_bounds__(192) k_gen_lead(Dev* D) {
+// ahead = 0: extend the stream to what this round's shuffles need (normally nothing: see ahead = 1).
+// ahead = 1: runs on its own stream next to the shuffles and the scan of the round and extends the stream
+//            GEN_AHEAD words beyond the need, so that the next round usually finds its words already generated.
+#define GEN_AHEAD (64LL << 20)
+__global__ void __launch_bounds__(192) k_gen_lead(Dev* D, int ahead) {
     __shared__ uint64_t st[312];
     if (D->done || !D->shared_stream) return;
-    const long long len = D->stream_len, target = D->stream_target;
+    if (ahead) {  // fold the extension of the ahead = 0 pass of this round (k_sched folds the last one of a round)
+        __syncthreads();
+        if (threadIdx.x == 0 && D->gen_E > 0) { D->stream_len = D->gen_base + D->gen_E; D->gen_E = 0; }
+        __syncthreads();
+    }
+    const long long len = D->stream_len;
+    long long target = D->stream_target;
+    if (ahead) {
+        target += GEN_AHEAD;
+        if (target > len + D->span_max) target = len + D->span_max;
+        if (target > D->stream_cap - 312) target = D->stream_cap - 312;
+    }
     if (len >= target) { if (threadIdx.x == 0) { D->gen_base = len; D->gen_E = 0; } return; }
     const long long E = target - len;
     long long lead_end = target;
