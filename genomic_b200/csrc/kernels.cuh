@@ -744,6 +744,8 @@ __device__ __forceinline__ bool cand_better(const Cand& a, const Cand& b) {
 #define SCAN_QUEUE 256  // per-warp ring of surviving units (entries)
 #define SCAN_GRING 64   // per-warp ring of surviving groups of 128 arc lengths (entries)
 #define SCAN_LIST 2048  // per-CTA list of block pairs that reach the level (entries)
+#define SCAN_LSMALL 128 // arcs shorter than this are swept row by row over the whole segment, not pair by pair
+#define PCODE_FLAT 0xffffffffu  // unit of the short-arc sweep: the block pair is looked up per arc
 
 struct PairGeo {
     int ilo, ihi, jlo, jhi;
@@ -797,10 +799,13 @@ __device__ __forceinline__ void pair_lengths(const ScanCtx& c, int bi, int bj, i
     if (lenlo < c.al0) lenlo = c.al0;
 }
 
-// can the pair hold an arc at or above the level?  bound = rn/min(L(n-L)) * (corner spread)^2, division free
+// can the pair hold an arc of SCAN_LSMALL markers or more at or above the level?  (shorter arcs: sweep_short)
+// bound = rn/min(L(n-L)) * (corner spread)^2, division free
 __device__ __forceinline__ bool pair_alive(const ScanCtx& c, int bi, int bj, double level) {
     int ilo, ihi, jlo, jhi, lenlo, lenhi;
     pair_lengths(c, bi, bj, ilo, ihi, jlo, jhi, lenlo, lenhi);
+    if (lenlo < SCAN_LSMALL) lenlo = SCAN_LSMALL;
+    if (lenlo > lenhi) return false;
     double s1, s2; int clen;
     pair_corner(c, bi, bj, s1, s2, clen);
     const double smx = (s1 > s2) ? s1 : s2;
@@ -808,6 +813,16 @@ __device__ __forceinline__ bool pair_alive(const ScanCtx& c, int bi, int bj, dou
     const double a = rlo * (c.rn - rlo), b2 = rhi * (c.rn - rhi);
     const double mn = (b2 < a) ? b2 : a;
     return c.rn * smx * smx >= level * mn * (1.0 - 1e-12);
+}
+
+// block (1-based) that holds prefix index i, 1 <= i <= n
+__device__ __forceinline__ int block_of(const ScanCtx& c, int i) {
+    int lo = 0, hi = c.nb;  // bb[lo] < i <= bb[hi]
+    while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (c.bb[mid] < i) lo = mid; else hi = mid;
+    }
+    return hi;
 }
 
 // geometry of a block pair: blocks, tie-break data and the two arc-length bands (CBS.cpp:179-180, 198-199)
@@ -827,12 +842,23 @@ __device__ __forceinline__ void pair_geometry(const ScanCtx& c, int bi, int bj, 
     if (((double)g.lenhi >= c.half) && (g.lenhi >= lenmax2)) { g.bandLo[1] = lenmax2; g.bandHi[1] = g.lenhi; }
 }
 
-// exact re-evaluation of one unit (slow path): rows i0..i0+31, arc lengths L0..L0+7, restricted to the pair's
-// blocks and to the band of `side`
-__device__ void scan_unit_exact(const ScanCtx& c, int bi, int bj, int side, int i0, int L0, double sms, ScanSmem* sm) {
+// exact re-evaluation of one unit (slow path): rows i0..i0+31, arc lengths L0..L0+7.  A unit of a block pair is
+// restricted to the pair's blocks and to the band of its side; a unit of the short-arc sweep (PCODE_FLAT) looks
+// the pair of every arc up and keeps the arc only if its length lies in one of that pair's bands.
+__device__ void scan_unit_exact(const ScanCtx& c, unsigned pcode, int i0, int L0, double sms, ScanSmem* sm) {
+    const bool flat = pcode == PCODE_FLAT;
     PairGeo g;
-    pair_geometry(c, bi, bj, g);
-    const int La = g.bandLo[side], Lb = g.bandHi[side];
+    int side = 0, La, Lb, ia, ib, cbi = -1, cbj = -1;
+    if (!flat) {
+        side = (int)(pcode & 1u);
+        pair_geometry(c, (int)(pcode >> 16), (int)((pcode >> 1) & 0x7fffu), g);
+        La = max(g.bandLo[side], SCAN_LSMALL); Lb = g.bandHi[side];
+        ia = max(i0, g.ilo); ib = min(i0 + 31, g.ihi);
+    } else {
+        La = c.al0; Lb = min(c.n - c.al0, SCAN_LSMALL - 1);
+        ia = max(i0, 1); ib = min(i0 + 31, c.n);
+        g.jlo = 1; g.jhi = c.n;
+    }
     double best = 0.0;
     double th[8];
 #pragma unroll
@@ -841,15 +867,22 @@ __device__ void scan_unit_exact(const ScanCtx& c, int bi, int bj, int side, int 
         th[r] = (L >= La && L <= Lb) ? sms * c.gtab[L] : __longlong_as_double(0x7ff0000000000000LL);
     }
     Cand cb; cb.stat = -1.0; cb.corner = 0.0; cb.q = 0; cb.key = 0; cb.i = 0; cb.j = 0;
-    const int ia = max(i0, g.ilo), ib = min(i0 + 31, g.ihi);
     for (int i = ia; i <= ib; ++i) {
         const double a = c.sx[i];
 #pragma unroll
         for (int r = 0; r < 8; ++r) {
             const int L = L0 + r, j = i + L;
-            if (L < La || L > Lb || j < g.jlo || j > g.jhi) continue;
+            if (L < La || L > Lb) continue;
+            if (flat ? (j > c.n) : (j < g.jlo || j > g.jhi)) continue;
             const double s = fabs(c.sx[j] - a);
             if (!(s > th[r])) continue;
+            if (flat) {
+                const int bi = block_of(c, i), bj = block_of(c, j);
+                if (bi != cbi || bj != cbj) { pair_geometry(c, bi, bj, g); cbi = bi; cbj = bj; }
+                if (L >= g.bandLo[0] && L <= g.bandHi[0]) side = 0;
+                else if (L >= g.bandLo[1] && L <= g.bandHi[1]) side = 1;
+                else continue;  // not an arc the reference evaluates
+            }
             const double stat = c.factab[L] * s * s;  // CBS.cpp:191-193
             if (!c.loc) { if (stat > best) best = stat; }
             else {
@@ -961,7 +994,7 @@ __device__ __forceinline__ void scan_unit(const ScanCtx& c, unsigned code, unsig
     bool flag = false;
 #pragma unroll
     for (int k = 0; k < 8; ++k) flag |= (m[k] >= thk[k]);
-    if (flag) scan_unit_exact(c, (int)(pcode >> 16), (int)((pcode >> 1) & 0x7fffu), (int)(pcode & 1u), i0, L0, sms, sm);
+    if (flag) scan_unit_exact(c, pcode, i0, L0, sms, sm);
 }
 
 // examine queued units 32 at a time (all of them if `all`)
@@ -989,6 +1022,65 @@ __device__ __forceinline__ bool group_may_reach(const ScanCtx& c, const PairGeo&
     const float smsf = __double2float_rd(*((volatile const double*)&sm->sms));
     const float th = __fmul_rd(smsf, g_lower_min(c, l0, l1));
     return !(window_bound(c, i0, i0 + L0, i0 + 31 + L0 + width - 1) < th);
+}
+
+// append the surviving units of this lane's 32-length group (bit t of keep4: unit t) to the warp's unit queue
+__device__ __forceinline__ void push_units(UnitQueue& uq, unsigned keep4, unsigned code0, unsigned pcode, int lane) {
+    const int cnt = __popc(keep4);
+    int incl = cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(FULL, incl, o); if (lane >= o) incl += v; }
+    const int added = __shfl_sync(FULL, incl, 31);
+    if (added) {
+        const unsigned at = uq.head + uq.n + (unsigned)(incl - cnt);
+#pragma unroll
+        for (int t = 0; t < 4; ++t)
+            if ((keep4 >> t) & 1u)
+                *reinterpret_cast<int2*>(uq.q + 2 * ((at + __popc(keep4 & ((1u << t) - 1u))) & (SCAN_QUEUE - 1))) =
+                    make_int2((int)(code0 + (unsigned)t), (int)pcode);
+        uq.n += (unsigned)added;
+        __syncwarp();
+    }
+}
+
+// Short arcs (length below SCAN_LSMALL) have low thresholds whatever block pair they belong to, so the pair bounds
+// cannot discard them; they are swept here over the whole segment, row by row (32 rows x 32 lengths, then units of
+// 32 x 8), with the same table tests.  The warps of the CTA share the rows.
+__device__ void sweep_short(const ScanCtx& c, UnitQueue& uq, ScanSmem* sm, int warp, int nwarps, int lane) {
+    PairGeo gs;
+    gs.ilo = 1; gs.ihi = c.n; gs.jlo = 1; gs.jhi = c.n;
+    const int La = c.al0, Lb = min(c.n - c.al0, SCAN_LSMALL - 1);
+    if (La > Lb) return;
+    const int ngs = (Lb >> 5) + 1, total = ((c.n >> 5) + 1) * ngs;
+    unsigned long long my_arcs = 0, my_slots = 0;
+    for (int base = warp * 32; base < total; base += nwarps * 32) {
+        const int idx = base + lane;
+        unsigned keep4 = 0, code0 = 0;
+        if (idx < total) {
+            const int a = idx / ngs, Ls = (idx - a * ngs) << 5;
+            code0 = ((unsigned)a << 17) | (unsigned)(Ls >> 3);
+            if (group_may_reach(c, gs, sm, a, Ls, 32, La, Lb)) {
+#pragma unroll
+                for (int t = 0; t < 4; ++t)
+                    if (group_may_reach(c, gs, sm, a, Ls + 8 * t, 8, La, Lb)) keep4 |= 1u << t;
+            }
+            if (keep4 && (c.arcs || c.slots)) {  // profiling: arcs inside the queued units
+                const int i0 = a << 5;
+                for (int k = 0; k < 32; ++k) {
+                    const int L = Ls + k;
+                    if (!((keep4 >> (k >> 3)) & 1u) || L < La || L > Lb) continue;
+                    const int ia = max(i0, 1), ib = min(i0 + 31, c.n - L);
+                    if (ib >= ia) my_arcs += (unsigned long long)(ib - ia + 1);
+                }
+                my_slots += 256ull * __popc(keep4);
+            }
+        }
+        push_units(uq, keep4, code0, PCODE_FLAT, lane);
+        drain_units(c, uq, sm, lane, false);
+    }
+    if (c.slots && my_slots) atomicAdd(c.slots, my_slots);
+    if (c.arcs && my_arcs) atomicAdd(c.arcs, my_arcs);
+    __syncwarp();
 }
 
 // scan one arc-length band [La, Lb] of a block pair with the whole warp.  The (row, length) plane of the pair is
@@ -1046,21 +1138,7 @@ __device__ void scan_band(const ScanCtx& c, const PairGeo& g, unsigned pcode, Un
             }
             __syncwarp();
             ghead += gtake; gn -= gtake;
-            const int cnt = __popc(keep4);
-            int incl = cnt;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(FULL, incl, o); if (lane >= o) incl += v; }
-            const int added = __shfl_sync(FULL, incl, 31);
-            if (added) {
-                const unsigned at = uq.head + uq.n + (unsigned)(incl - cnt);
-#pragma unroll
-                for (int t = 0; t < 4; ++t)
-                    if ((keep4 >> t) & 1u)
-                        *reinterpret_cast<int2*>(uq.q + 2 * ((at + __popc(keep4 & ((1u << t) - 1u))) & (SCAN_QUEUE - 1))) =
-                            make_int2((int)(code0 + (unsigned)t), (int)pcode);
-                uq.n += (unsigned)added;
-                __syncwarp();
-            }
+            push_units(uq, keep4, code0, pcode, lane);
             drain_units(c, uq, sm, lane, false);
         }
         if (!more) break;
@@ -1075,8 +1153,10 @@ __device__ void scan_pair(const ScanCtx& c, int bi, int bj, UnitQueue& uq, int* 
     PairGeo g;
     pair_geometry(c, bi, bj, g);
     const unsigned pcode = (((unsigned)bi << 15) | (unsigned)bj) << 1;
-    if (g.bandLo[0] <= g.bandHi[0]) scan_band(c, g, pcode, uq, gring, g.bandLo[0], g.bandHi[0], sm, lane);
-    if (g.bandLo[1] <= g.bandHi[1]) scan_band(c, g, pcode | 1u, uq, gring, g.bandLo[1], g.bandHi[1], sm, lane);
+    // arcs shorter than SCAN_LSMALL are covered by sweep_short
+    const int lo0 = max(g.bandLo[0], SCAN_LSMALL), lo1 = max(g.bandLo[1], SCAN_LSMALL);
+    if (lo0 <= g.bandHi[0]) scan_band(c, g, pcode, uq, gring, lo0, g.bandHi[0], sm, lane);
+    if (lo1 <= g.bandHi[1]) scan_band(c, g, pcode | 1u, uq, gring, lo1, g.bandHi[1], sm, lane);
 }
 
 // dynamic shared memory layout helper (host + device)
@@ -1280,6 +1360,7 @@ __global__ void __launch_bounds__(256, 3) k_scan(Dev* D, ScanLayout lay) {
             uq.q = s_queue + warp * (2 * SCAN_QUEUE + SCAN_GRING);
             uq.head = 0; uq.n = 0;
             int* gring = uq.q + 2 * SCAN_QUEUE;
+            sweep_short(c, uq, sm, warp, nwarps, lane);
             for (;;) {
                 for (;;) {
                     if (*((volatile int*)&sm->n_list) > SCAN_LIST - 32 * nwarps) break;  // every warp may still add 32
