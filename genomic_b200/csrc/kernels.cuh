@@ -1298,6 +1298,7 @@ __global__ void __launch_bounds__(256, 3) k_scan(Dev* D, ScanLayout lay) {
                 const bool below = lo < 0.0, above = hi > 0.0;
                 sm->g_min = below ? lo : 0.0; sm->g_imin = below ? s_amin[blo] : n;
                 sm->g_max = above ? hi : 0.0; sm->g_imax = above ? s_amax[bhi] : n;
+                sm->n_list = 0;
             }
         }
         __syncthreads();
@@ -1313,17 +1314,50 @@ __global__ void __launch_bounds__(256, 3) k_scan(Dev* D, ScanLayout lay) {
             // CBS.cpp:113-117 initial candidate: global extrema of the prefix sums
             const double rj = (double)abs(gimax - gimin);
             const double init = c.rn / (rj * (c.rn - rj)) * spread * spread;
-            // ---- pass 1: best valid corner -> lower bound ---------------------------------
+            // ---- pass 1: best valid corner -> lower bound; the pairs whose bound reaches a provisional level (the
+            // level before the corners are known) are appended to the pair list on the way, so that the pairs are
+            // normally enumerated once.  Thread t takes pairs t, t+256, ... and steps (bi, bj) incrementally.
             const int npairs = nb * (nb + 1) / 2;
+            double prov = init;
+            if (decide) {
+                const double thresh = t.ostat * 0.99999;
+                const double mstar = thresh * tss0 / (c.rn - 2.0 + thresh) * (1.0 - 1e-9);
+                if (mstar > prov && mstar + 0.001 < tss0 && mstar / ((tss0 - mstar) / (c.rn - 2.0)) < thresh) prov = mstar;
+            }
             double lb = 0.0;
-            for (int q = tid; q < npairs; q += blockDim.x) {
-                int bi, bj; pair_from_index(q, nb, bi, bj);
-                double s1, s2; int clen;
-                pair_corner(c, bi, bj, s1, s2, clen);
-                if (clen >= c.al0 && clen <= n - c.al0) {
-                    const double sm1 = (s1 > s2) ? s1 : s2;
-                    const double v = c.factab[clen] * sm1 * sm1;
-                    if (v > lb) lb = v;
+            {
+                int bi = 1, bj = 1;
+                if (tid < npairs) pair_from_index(tid, nb, bi, bj);
+                for (int q0 = 0; q0 < npairs; q0 += blockDim.x) {
+                    const int q = q0 + tid;
+                    bool alive = false;
+                    if (q < npairs) {
+                        double s1, s2; int clen;
+                        pair_corner(c, bi, bj, s1, s2, clen);
+                        const double smx = (s1 > s2) ? s1 : s2;
+                        if (clen >= c.al0 && clen <= n - c.al0) {
+                            const double v = c.factab[clen] * smx * smx;
+                            if (v > lb) lb = v;
+                        }
+                        int ilo, ihi, jlo, jhi, lenlo, lenhi;
+                        pair_lengths(c, bi, bj, ilo, ihi, jlo, jhi, lenlo, lenhi);
+                        if (lenlo < SCAN_LSMALL) lenlo = SCAN_LSMALL;
+                        if (lenlo <= lenhi) {
+                            const double rlo = (double)lenlo, rhi = (double)lenhi;
+                            const double a = rlo * (c.rn - rlo), b2 = rhi * (c.rn - rhi);
+                            alive = c.rn * smx * smx >= prov * ((b2 < a) ? b2 : a) * (1.0 - 1e-12);
+                        }
+                    }
+                    const unsigned mask = __ballot_sync(FULL, alive);
+                    if (mask) {
+                        int at = 0;
+                        if (lane == 0) at = atomicAdd(&sm->n_list, __popc(mask));
+                        at = __shfl_sync(FULL, at, 0) + __popc(mask & ((1u << lane) - 1u));
+                        if (alive && at < SCAN_LIST) s_list[at] = (bi << 16) | bj;
+                    }
+                    // advance by blockDim.x pairs: row bi holds bj = bi..nb
+                    bj += blockDim.x;
+                    while (bj > nb && bi <= nb) { const int excess = bj - nb; ++bi; bj = bi - 1 + excess; }
                 }
             }
 #pragma unroll
@@ -1349,7 +1383,9 @@ __global__ void __launch_bounds__(256, 3) k_scan(Dev* D, ScanLayout lay) {
                 sm->found = init;
                 sm->r_stat = init; sm->r_corner = __longlong_as_double(0x7ff0000000000000LL);
                 sm->r_q = 0x7fffffff; sm->r_key = -1; sm->r_i = fi; sm->r_j = fj;
-                sm->lock = 0; sm->next_pair = 0; sm->n_list = 0; sm->pop = 0;
+                sm->lock = 0; sm->pop = 0;
+                // the list is complete unless it overflowed: then pass 2 enumerates the pairs again, list by list
+                if (sm->n_list > SCAN_LIST) { sm->n_list = 0; sm->next_pair = 0; } else sm->next_pair = npairs;
             }
             __syncthreads();
             // ---- pass 2: scan surviving block pairs ----------------------------------------
