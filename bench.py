@@ -44,7 +44,10 @@ def workload_name(samples_per_gpu: int, scale: float) -> str:
 
 # ---------------------------------------------------------------------------------------------
 class ClockSampler:
-    """nvidia-smi clocks/throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    """SM clock and throttle reasons during the timed region (B200_PROFILING.md recipe).  Sampled through NVML in a
+    thread (nvidia_ml_py): a polling `nvidia-smi -lms` process contends for the driver with the ~500 kernel launches
+    of a step and was measured to stretch single steps by up to 60 %; NVML queries do not.  Falls back to the
+    nvidia-smi loop if NVML is not importable."""
 
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
@@ -54,11 +57,48 @@ class ClockSampler:
         self.gpu = gpu_index
         self.proc = None
         self.lines = []
+        self.sm, self.mx, self.reasons = [], [], set()
+        self.stop_flag = False
+        self.thread = None
+        self.nvml = None
+
+    def _nvml_loop(self):
+        nv = self.nvml
+        try:
+            h = nv.nvmlDeviceGetHandleByIndex(self.gpu)
+            mx = float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
+            names = (("hw_slowdown", nv.nvmlClocksThrottleReasonHwSlowdown),
+                     ("hw_thermal_slowdown", nv.nvmlClocksThrottleReasonHwThermalSlowdown),
+                     ("sw_thermal_slowdown", nv.nvmlClocksThrottleReasonSwThermalSlowdown),
+                     ("sw_power_cap", nv.nvmlClocksThrottleReasonSwPowerCap))
+            while not self.stop_flag:
+                self.sm.append(float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)))
+                self.mx.append(mx)
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                for name, bit in names:
+                    if r & bit:
+                        self.reasons.add(name)
+                time.sleep(0.1)
+        except Exception:
+            pass
 
     def start(self):
         try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nvml = pynvml
+            # NVML indexes physical devices: honour CUDA_VISIBLE_DEVICES if it is a plain list of indices
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES", "")
+            if vis and all(x.strip().isdigit() for x in vis.split(",")):
+                self.gpu = int(vis.split(",")[self.gpu])
+            self.thread = threading.Thread(target=self._nvml_loop, daemon=True)
+            self.thread.start()
+            return
+        except Exception:
+            self.nvml = None
+        try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "200", "-i", str(self.gpu)], stdout=subprocess.PIPE,
+                                          "-lms", "500", "-i", str(self.gpu)], stdout=subprocess.PIPE,
                                          stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
@@ -70,6 +110,11 @@ class ClockSampler:
             self.lines.append(line.strip())
 
     def stop(self) -> dict:
+        if self.nvml is not None:
+            self.stop_flag = True
+            self.thread.join(timeout=2)
+            return {"sm_mhz": float(np.median(self.sm)) if self.sm else None, "sm_max_mhz": max(self.mx) if self.mx else None,
+                    "reasons": sorted(self.reasons), "samples": len(self.sm), "source": "nvml"}
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.25)
@@ -92,7 +137,7 @@ class ClockSampler:
                 if v.lower().startswith("active"):
                     reasons.add(name)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "source": "nvidia-smi"}
 
 
 def read_peaks() -> dict:
@@ -243,11 +288,14 @@ def run_gpu_arm(args):
         t = torch.tensor([total_ms], device=dev, dtype=torch.float64)
         if dist is not None:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)  # max over ranks
+        timed.last_steps = [round(x, 3) for x in per_step]  # this rank's per-step times (diagnostics)
         return float(t.item()), last, clocks
 
     warm = max(args.warmup, 3)
     total_ms, res, clocks = timed(step_device, args.steps, warm, sample_clocks=True)
+    steps_device = timed.last_steps
     e2e_ms, res_h, _ = timed(step_host, args.steps, 1)
+    steps_host = timed.last_steps
     launches_per_step = int(res.kernel_launches)
 
     # Roofline inputs, kept OUT of the timed steps:
@@ -334,6 +382,7 @@ def run_gpu_arm(args):
                     "d2h_bytes_per_step": int(len(res_h.lengths) * 12 + len(off) * 16) * world,
                     "ms_per_step": e2e_ms / args.steps},
             "gpu_launches": launches_per_step * args.steps,
+            "step_ms": {"device_resident": steps_device, "e2e": steps_host},
             "clocks": clocks,
             "kernel_ms_per_step": {k: round(v, 3) for k, v in kms.items()},
             "kernel_groups_ms_per_step": {k: round(v, 3) for k, v in groups.items()},

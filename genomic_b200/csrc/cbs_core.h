@@ -361,8 +361,12 @@ struct Sched {
     }
 
     // arena helpers ---------------------------------------------------------------------
-    // S[0..n] followed by SX_PAD finite values (the scan's fast path reads whole 32 x 8 units)
-    CBS_HD static long long sx_stride(int n) { return ((long long)n + 1 + SX_PAD + 3) & ~3LL; }
+    // One row per permutation: S[0..n], SX_PAD finite values (the scan's fast path reads whole 32 x 8 units), then
+    // the extrema table of the row: tbl_entries(n) floats of minima and as many of maxima, entry e = extrema of
+    // S[32e .. 32e+31], rounded outwards (written next to the prefix sums by k_chain / k_prep, read by k_scan)
+    CBS_HD static long long tbl_offset(int n) { return ((long long)n + 1 + SX_PAD + 3) & ~3LL; }  // in doubles
+    CBS_HD static long long tbl_entries(int n) { return ((long long)n >> 5) + 2; }
+    CBS_HD static long long sx_stride(int n) { return tbl_offset(n) + ((tbl_entries(n) + 3) & ~3LL); }
     CBS_HD static long long bs_stride(int nb) { return (3LL * nb + 4 + 3) & ~3LL; }
     // 32-bit index array of the global-memory shuffle, in doubles; all strides are multiples of 4 doubles so
     // that every row of prefix sums starts on a 32-byte boundary (k_prefix moves rows with 128-bit accesses)

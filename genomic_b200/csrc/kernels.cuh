@@ -118,6 +118,68 @@ __global__ void __launch_bounds__(192) k_gen(Dev* D) {
 }
 
 // ------------------------------------------------------------------------------------
+// Statistics of a row of prefix sums, computed chunk by chunk by the warp that has just produced the chunk in
+// shared memory (k_chain, k_prep), so that k_scan does not have to read the row again:
+//   * per block of the reference's sqrt(n) blocks: extrema with their FIRST occurrence (CBS.cpp:88-94), double;
+//   * per aligned run of 32 prefix sums: extrema in single precision rounded outwards (the scan's pruning table).
+// buf[k] = S[c0+1+k], k < cnt; prev_last = S[c0].  The state is uniform over the warp.
+// ------------------------------------------------------------------------------------
+struct RowStats {
+    int b;           // block in progress (1-based)
+    double lo, hi;   // its extrema so far
+    int ilo, ihi;
+};
+__device__ __forceinline__ void row_stats_init(RowStats& st) {
+    st.b = 1; st.lo = __longlong_as_double(0x7ff0000000000000LL); st.hi = -st.lo; st.ilo = 0x7fffffff; st.ihi = 0x7fffffff;
+}
+template <int CHUNK>
+__device__ void row_stats_chunk(const double* buf, int c0, int cnt, int n, double prev_last, const int* __restrict__ bb, int nb,
+                                BlockStats bs, float* tmin, float* tmax, RowStats& st, int lane) {
+    const double dinf = __longlong_as_double(0x7ff0000000000000LL);
+    const int hi_idx = c0 + cnt;
+    while (st.b <= nb) {
+        const int first = bb[st.b - 1] + 1, last = bb[st.b];
+        const int a = max(first, c0 + 1), z = min(last, hi_idx);
+        if (a > z) break;
+        double lo = dinf, hi = -dinf;
+        int ilo = 0x7fffffff, ihi = 0x7fffffff;
+        for (int i = a + lane; i <= z; i += 32) {
+            const double v = buf[i - c0 - 1];
+            if (v < lo) { lo = v; ilo = i; }
+            if (v > hi) { hi = v; ihi = i; }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const double olo = shfl_d(lo, lane ^ o), ohi = shfl_d(hi, lane ^ o);
+            const int oilo = __shfl_xor_sync(FULL, ilo, o), oihi = __shfl_xor_sync(FULL, ihi, o);
+            if (olo < lo || (olo == lo && oilo < ilo)) { lo = olo; ilo = oilo; }
+            if (ohi > hi || (ohi == hi && oihi < ihi)) { hi = ohi; ihi = oihi; }
+        }
+        if (lo < st.lo) { st.lo = lo; st.ilo = ilo; }  // the part seen earlier holds the earlier indices: it wins ties
+        if (hi > st.hi) { st.hi = hi; st.ihi = ihi; }
+        if (last > hi_idx) break;  // the block continues in the next chunk
+        if (lane == 0) { bs.bmin()[st.b - 1] = st.lo; bs.bmax()[st.b - 1] = st.hi; bs.amin()[st.b - 1] = st.ilo; bs.amax()[st.b - 1] = st.ihi; }
+        ++st.b; st.lo = dinf; st.hi = -dinf; st.ilo = 0x7fffffff; st.ihi = 0x7fffffff;
+    }
+    // table entries e = c0/32 + l cover S[32e .. 32e+31] = buf[32l-1 .. 32l+30] (buf[-1] = prev_last); an entry that
+    // continues in the next chunk is computed there
+    const bool last_chunk = hi_idx >= n;
+    for (int l = lane; l <= CHUNK / 32; l += 32) {
+        if (32 * l - 1 > cnt - 1 || (l == CHUNK / 32 && !last_chunk)) continue;
+        float lo = __int_as_float(0x7f800000), hi = -lo;
+#pragma unroll 4
+        for (int tt = 0; tt < 32; ++tt) {
+            const int k = 32 * l - 1 + ((tt + l) & 31);  // skewed: the lanes hit different banks
+            if (k <= cnt - 1) {
+                const double v = (k < 0) ? prev_last : buf[k];
+                lo = fminf(lo, __double2float_rd(v)); hi = fmaxf(hi, __double2float_ru(v));
+            }
+        }
+        tmin[(c0 >> 5) + l] = lo; tmax[(c0 >> 5) + l] = hi;
+    }
+}
+
+// ------------------------------------------------------------------------------------
 // k_prep: one warp per pending segment.  The sums of the reference are strictly sequential
 // (CBS.cpp:986-989 mean and tss, :83-87 prefix sums), so lane 0 runs them as ONE dependent DADD chain
 // (8 cycles per marker on B200) over chunks staged in shared memory, while the other lanes already have
@@ -475,7 +537,7 @@ __device__ __forceinline__ void fy_multi(Idx s_idx, unsigned char* tab, int i0, 
 }
 #define FY_MULTI_MIN 8192  // rounds of 128 steps while i0 is at least this
 
-#define PERM_CHUNK 512
+#define PERM_CHUNK 1024
 template <class Idx>
 __device__ void perm_warp(Dev* D, const Task& t, int p, Idx s_idx, unsigned char* tab, int lane) {
     const int n = t.n;
@@ -653,7 +715,15 @@ __global__ void __launch_bounds__(CHAIN_WARPS * 32) k_chain(Dev* D) {
         if (it.obs) continue;  // k_prep wrote the prefix sums of observed data
         const Task& t = D->tasks[it.task];
         const int n = t.n;
-        double* sx = D->arena + t.off_sx + (long long)(g - D->item_prefix[k]) * Sched::sx_stride(n);
+        const int pp = g - D->item_prefix[k], nb = t.nb;
+        double* sx = D->arena + t.off_sx + (long long)pp * Sched::sx_stride(n);
+        BlockStats bs(D->arena + t.off_bs + (long long)pp * Sched::bs_stride(nb), nb);
+        const int* __restrict__ bb = D->bbtab + D->unit_off[t.unit] + t.lo;
+        float* tmin = (float*)(sx + Sched::tbl_offset(n));
+        float* tmax = tmin + Sched::tbl_entries(n);
+        RowStats rst;
+        row_stats_init(rst);
+        double prev_last = 0.0;  // S[0]
         const double* __restrict__ src = sx + 1;
         if (lane == 0) sx[0] = 0.0;
         double run = 0.0;
@@ -683,6 +753,8 @@ __global__ void __launch_bounds__(CHAIN_WARPS * 32) k_chain(Dev* D) {
             }
             __syncwarp();
             for (int kk = lane; kk < cnt; kk += 32) sx[c0 + 1 + kk] = buf[kk];
+            row_stats_chunk<PERM_CHUNK>(buf, c0, cnt, n, prev_last, bb, nb, bs, tmin, tmax, rst, lane);
+            prev_last = buf[cnt - 1];
         }
         // the scan reads up to SX_PAD values behind S_n without bounds checks: keep them finite
         run = shfl_d(run, 0);
@@ -1223,61 +1295,86 @@ __global__ void __launch_bounds__(256, 3) k_scan(Dev* D, ScanLayout lay) {
         BlockStats bs(D->arena + t.off_bs + (long long)p * Sched::bs_stride(nb), nb);
         const int* bbg = D->bbtab + base;
         for (int b = tid; b <= nb; b += blockDim.x) s_bb[b] = bbg[b];
+        if (it.obs) {
+            // observed data (one row per pending segment, written by k_prep): the statistics are computed here
+            __syncthreads();
         // ---- phase 0a: extrema table.  A warp takes 1024 consecutive prefix sums (coalesced loads); a
-        // reduce-scatter over the lanes leaves lane l with the extrema of run l of 32, in single precision
-        // rounded outwards; runs are merged 2 or 4 to an entry when the table is coarser (tsh 6, 7).
-        for (int c0 = warp * 1024; c0 <= n; c0 += nwarps * 1024) {
-            float lo[32], hi[32];
-#pragma unroll
-            for (int r = 0; r < 32; ++r) {
-                const int e = c0 + 32 * r + lane;
-                if (e <= n) { const double v = c.sx[e]; lo[r] = __double2float_rd(v); hi[r] = __double2float_ru(v); }
-                else { lo[r] = finf; hi[r] = -finf; }
-            }
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-                const bool up = (lane & o) != 0;
-#pragma unroll
-                for (int r = 0; r < o; ++r) {
-                    const float keep_lo = up ? lo[r + o] : lo[r], send_lo = up ? lo[r] : lo[r + o];
-                    const float keep_hi = up ? hi[r + o] : hi[r], send_hi = up ? hi[r] : hi[r + o];
-                    lo[r] = fminf(keep_lo, __shfl_xor_sync(FULL, send_lo, o));
-                    hi[r] = fmaxf(keep_hi, __shfl_xor_sync(FULL, send_hi, o));
+            // reduce-scatter over the lanes leaves lane l with the extrema of run l of 32, in single precision
+            // rounded outwards; runs are merged 2 or 4 to an entry when the table is coarser (tsh 6, 7).
+            for (int c0 = warp * 1024; c0 <= n; c0 += nwarps * 1024) {
+                float lo[32], hi[32];
+    #pragma unroll
+                for (int r = 0; r < 32; ++r) {
+                    const int e = c0 + 32 * r + lane;
+                    if (e <= n) { const double v = c.sx[e]; lo[r] = __double2float_rd(v); hi[r] = __double2float_ru(v); }
+                    else { lo[r] = finf; hi[r] = -finf; }
+                }
+    #pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                    const bool up = (lane & o) != 0;
+    #pragma unroll
+                    for (int r = 0; r < o; ++r) {
+                        const float keep_lo = up ? lo[r + o] : lo[r], send_lo = up ? lo[r] : lo[r + o];
+                        const float keep_hi = up ? hi[r + o] : hi[r], send_hi = up ? hi[r] : hi[r + o];
+                        lo[r] = fminf(keep_lo, __shfl_xor_sync(FULL, send_lo, o));
+                        hi[r] = fmaxf(keep_hi, __shfl_xor_sync(FULL, send_hi, o));
+                    }
+                }
+                float l0 = lo[0], h0 = hi[0];
+                for (int sft = 5; sft < lay.tsh; ++sft) {
+                    const int o = 1 << (sft - 5);
+                    l0 = fminf(l0, __shfl_xor_sync(FULL, l0, o));
+                    h0 = fmaxf(h0, __shfl_xor_sync(FULL, h0, o));
+                }
+                const int per = 1 << (lay.tsh - 5);  // runs per entry
+                if ((lane & (per - 1)) == 0 && c0 + 32 * lane <= n) {
+                    const int e = (c0 + 32 * lane) >> lay.tsh;
+                    s_tmin[e] = l0; s_tmax[e] = h0;
                 }
             }
-            float l0 = lo[0], h0 = hi[0];
-            for (int sft = 5; sft < lay.tsh; ++sft) {
-                const int o = 1 << (sft - 5);
-                l0 = fminf(l0, __shfl_xor_sync(FULL, l0, o));
-                h0 = fmaxf(h0, __shfl_xor_sync(FULL, h0, o));
+            __syncthreads();
+            // ---- phase 0b: per-block extrema with their FIRST occurrence (CBS.cpp:88-94): a warp per block
+            for (int b = warp; b < nb; b += nwarps) {
+                const int first = s_bb[b] + 1, last = s_bb[b + 1];
+                double lo = __longlong_as_double(0x7ff0000000000000LL), hi = -lo;
+                int ilo = 0x7fffffff, ihi = 0x7fffffff;
+                for (int i = first + lane; i <= last; i += 32) {
+                    const double v = c.sx[i];
+                    if (v < lo) { lo = v; ilo = i; }
+                    if (v > hi) { hi = v; ihi = i; }
+                }
+    #pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                    const double olo = shfl_d(lo, lane ^ o), ohi = shfl_d(hi, lane ^ o);
+                    const int oilo = __shfl_xor_sync(FULL, ilo, o), oihi = __shfl_xor_sync(FULL, ihi, o);
+                    if (olo < lo || (olo == lo && oilo < ilo)) { lo = olo; ilo = oilo; }
+                    if (ohi > hi || (ohi == hi && oihi < ihi)) { hi = ohi; ihi = oihi; }
+                }
+                if (lane == 0) { s_bmin[b] = lo; s_bmax[b] = hi; s_amin[b] = ilo; s_amax[b] = ihi; }
             }
-            const int per = 1 << (lay.tsh - 5);  // runs per entry
-            if ((lane & (per - 1)) == 0 && c0 + 32 * lane <= n) {
-                const int e = (c0 + 32 * lane) >> lay.tsh;
-                s_tmin[e] = l0; s_tmax[e] = h0;
+            __syncthreads();
+        } else {
+            // ---- phase 0: the statistics of the row were written next to it by k_chain: the extrema of every
+            // aligned run of 32 prefix sums (merged 2 or 4 to an entry when the table is coarser) and the per-block
+            // extrema with their first occurrence (CBS.cpp:88-94)
+            {
+                const float* gmin = (const float*)(c.sx + Sched::tbl_offset(n));
+                const float* gmax = gmin + Sched::tbl_entries(n);
+                const int fine = (n >> 5) + 1, per = 1 << (lay.tsh - 5);
+                for (int e = tid; e <= (n >> lay.tsh); e += blockDim.x) {
+                    float lo = finf, hi = -finf;
+                    for (int r = 0; r < per; ++r) {
+                        const int f = e * per + r;
+                        if (f < fine) { lo = fminf(lo, gmin[f]); hi = fmaxf(hi, gmax[f]); }
+                    }
+                    s_tmin[e] = lo; s_tmax[e] = hi;
+                }
+                for (int b2 = tid; b2 < nb; b2 += blockDim.x) {
+                    s_bmin[b2] = bs.bmin()[b2]; s_bmax[b2] = bs.bmax()[b2]; s_amin[b2] = bs.amin()[b2]; s_amax[b2] = bs.amax()[b2];
+                }
             }
+            __syncthreads();
         }
-        __syncthreads();
-        // ---- phase 0b: per-block extrema with their FIRST occurrence (CBS.cpp:88-94): a warp per block
-        for (int b = warp; b < nb; b += nwarps) {
-            const int first = s_bb[b] + 1, last = s_bb[b + 1];
-            double lo = __longlong_as_double(0x7ff0000000000000LL), hi = -lo;
-            int ilo = 0x7fffffff, ihi = 0x7fffffff;
-            for (int i = first + lane; i <= last; i += 32) {
-                const double v = c.sx[i];
-                if (v < lo) { lo = v; ilo = i; }
-                if (v > hi) { hi = v; ihi = i; }
-            }
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-                const double olo = shfl_d(lo, lane ^ o), ohi = shfl_d(hi, lane ^ o);
-                const int oilo = __shfl_xor_sync(FULL, ilo, o), oihi = __shfl_xor_sync(FULL, ihi, o);
-                if (olo < lo || (olo == lo && oilo < ilo)) { lo = olo; ilo = oilo; }
-                if (ohi > hi || (ohi == hi && oihi < ihi)) { hi = ohi; ihi = oihi; }
-            }
-            if (lane == 0) { s_bmin[b] = lo; s_bmax[b] = hi; s_amin[b] = ilo; s_amax[b] = ihi; }
-        }
-        __syncthreads();
         // global extrema: the first block that attains the overall minimum / maximum, and only if it is
         // below / above 0.0 (CBS.cpp:80-81, 93-94)
         if (warp == 0) {
