@@ -370,6 +370,22 @@ def run_gpu_arm(args):
             "note": "the Fisher-Yates itself runs on 16-bit indices in shared memory; it is latency bound, not HBM bound; "
                     "classes run concurrently on several streams, so the sum of their times exceeds their share of the step",
         }
+        # DRAM traffic per launch from the committed ncu --set full capture (profiles/ncu_traffic.json, written by
+        # tools/ncu_kernel_summary.py): dram__bytes_read.sum + dram__bytes_write.sum, averaged over the captured launches
+        # (a busy round of the same workload); null if the file is absent
+        try:
+            ncu = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
+        except Exception:
+            ncu = {}
+        def traffic(kernel):
+            k = ncu.get(kernel)
+            if not k:
+                return None
+            return {"dram_bytes_per_launch": k["dram_read_bytes_per_launch"] + k["dram_write_bytes_per_launch"],
+                    "launch_ms": k["avg_ms"], "launches_captured": k["launches"], "source": "profiles/ncu_traffic.json"}
+        roof_scan["traffic"] = traffic("k_scan")
+        roof_prefix["traffic"] = traffic("k_chain")
+        roof_shuffle["traffic"] = traffic("k_perm_smem")
         roofs = {"scan": roof_scan, "chain": roof_prefix, "shuffle": roof_shuffle}
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": warm,

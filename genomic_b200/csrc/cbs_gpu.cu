@@ -230,7 +230,7 @@ int smooth_device(cbs_gpu_ctx* c, const double* xin, const long long* goff, cons
     }
     {
         LaunchTimer t(c, K_SMOOTH);
-        k_sm_sd<<<std::min((n_groups + 3) / 4, c->sm_count * 8), 128, 0, st>>>(c->diffs_sorted.as<double>(), goff, n_groups,
+        k_sm_sd<<<std::min(n_groups, c->sm_count * 8), 32, 0, st>>>(c->diffs_sorted.as<double>(), goff, n_groups,
                                                                               trim, infl, oscale, sscale, gout);
     }
     {

@@ -72,25 +72,21 @@ __global__ void k_sm_diffs(const double* __restrict__ fv, const long long* __res
     }
 }
 
-// one warp per group: ascending-order sum of squares, exactly as the reference accumulates it
-__global__ void __launch_bounds__(128) k_sm_sd(const double* __restrict__ dsorted, const long long* __restrict__ off,
-                                               int n_groups, double trim, double inflfact, double outlier_scale,
-                                               double smooth_scale, SmoothGroupOut* __restrict__ gout) {
-    const int lane = threadIdx.x & 31;
-    const int wpb = blockDim.x >> 5;
-    for (int g = blockIdx.x * wpb + (threadIdx.x >> 5); g < n_groups; g += gridDim.x * wpb) {
+// one warp per group: ascending-order sum of squares, exactly as the reference accumulates it (lane 0 runs the
+// dependent chain over chunks staged in shared memory, chain_sum_sq in kernels.cuh)
+__global__ void __launch_bounds__(32) k_sm_sd(const double* __restrict__ dsorted, const long long* __restrict__ off,
+                                              int n_groups, double trim, double inflfact, double outlier_scale,
+                                              double smooth_scale, SmoothGroupOut* __restrict__ gout) {
+    __shared__ __align__(16) double buf[PREP_CHUNK];
+    const int lane = threadIdx.x;
+    for (int g = blockIdx.x; g < n_groups; g += gridDim.x) {
         const int m = gout[g].m;
         if (m < 2) continue;  // smooth.cpp:142
         double tvar = 0.0;
         const long long keep = llround((1.0 - 2.0 * trim) * (double)(m - 1));  // smooth.cpp:36
         if (keep > 0) {
-            const double* d = dsorted + off[g];
-            double ss = 0.0;
-            for (long long b0 = 0; b0 < keep; b0 += 32) {
-                const double v = (b0 + lane < keep) ? d[b0 + lane] : 0.0;
-                const int cnt = (int)((keep - b0 < 32) ? (keep - b0) : 32);
-                for (int k = 0; k < cnt; ++k) { const double vk = __shfl_sync(0xffffffffu, v, k); ss = ss + vk * vk; }
-            }
+            double sum = 0.0, ss = 0.0;
+            chain_sum_sq(dsorted + off[g], (int)keep, buf, lane, sum, ss);
             tvar = inflfact * (ss / (2.0 * (double)keep));
         }
         if (lane == 0) {
