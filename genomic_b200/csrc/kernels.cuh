@@ -415,7 +415,7 @@ struct IdxGlobal {
 // id into slot j mod 8192 and reads it back -- whoever does not find itself shares the slot with the winner
 // (same target, or a harmless hash collision); a target inside the group's own rows flags the owner of that row.
 #define FY_TAB 8192
-#define FY_SCRATCH (FY_TAB + 128)  // bytes of per-warp scratch: claim table + one flag per step of a round
+#define FY_SCRATCH (FY_TAB + 256)  // bytes of per-warp scratch: claim table + one flag per step of a round
 template <class Idx>
 __device__ __forceinline__ void fy_group(Idx s_idx, unsigned char* tab, int i0, int i, int j, int lane) {
     if (!Idx::kClaimTable) {
@@ -535,7 +535,8 @@ __device__ __forceinline__ void fy_multi(Idx s_idx, unsigned char* tab, int i0, 
         }
     }
 }
-#define FY_MULTI_MIN 8192  // rounds of 128 steps while i0 is at least this
+#define FY_MULTI_MIN 8192    // rounds of 128 steps while i0 is at least this
+#define FY_MULTI8_MIN 20480  // rounds of 256 steps while i0 is at least this
 
 #define PERM_CHUNK 1024
 template <class Idx>
@@ -560,8 +561,18 @@ __device__ void perm_warp(Dev* D, const Task& t, int p, Idx s_idx, unsigned char
 #pragma unroll
         for (int q = 0; q < 8; ++q) raw[q] = (q < G) ? win[32 * q + lane] : 0ull;
         for (int g0 = 0; g0 < G; g0 += 8) {
+            // the stream lives in HBM: pull the words of four blocks ahead into L2 (2 KB = 16 lines per block), the
+            // register prefetch one block ahead then only pays an L2 hit
+            if (lane < 16 && g0 + 40 < G) asm volatile("prefetch.global.L2 [%0];" ::"l"(win + 32 * (g0 + 32) + 16 * lane));
 #pragma unroll
             for (int q = 0; q < 8; ++q) { const int g = g0 + 8 + q; nxt[q] = (g < G) ? win[32 * g + lane] : 0ull; }
+            if (Idx::kClaimTable && g0 + 7 < G && i0 >= FY_MULTI8_MIN) {
+                int j8[8];
+#pragma unroll
+                for (int k = 0; k < 8; ++k) j8[k] = draw_index(mt_temper(raw[k]), i0 - 32 * k - lane);
+                fy_multi<8>(s_idx, tab, i0, j8, lane);
+                i0 -= 256;
+            } else
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
                 if (Idx::kClaimTable && g0 + 4 * h + 3 < G && i0 >= FY_MULTI_MIN) {
@@ -605,6 +616,12 @@ __device__ void perm_warp(Dev* D, const Task& t, int p, Idx s_idx, unsigned char
             return draw_index(u, i);
         };
         int g = 0;
+        for (; Idx::kClaimTable && g + 7 < G && i0 >= FY_MULTI8_MIN; g += 8, i0 -= 256) {
+            int j8[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) j8[k] = philox_j(i0 - 32 * k - lane);
+            fy_multi<8>(s_idx, tab, i0, j8, lane);
+        }
         for (; Idx::kClaimTable && g + 3 < G && i0 >= FY_MULTI_MIN; g += 4, i0 -= 128) {
             int j4[4];
 #pragma unroll
