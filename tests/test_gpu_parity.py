@@ -245,6 +245,20 @@ def test_segment_long_units(ctx, oracle, mode):
     check_batch(ctx, oracle, vals, off, p, first_batch=24, max_batch=64)
 
 
+def test_stress_50k_segments_replay(ctx, oracle):
+    """BASELINE configs[4] in small: units of exactly 50,000 markers, deterministic MT replay.  (i) pure null: the
+    permutation loop stops at the early exit; (ii) a shift at 25,000 small enough (t ~ 5.6 < 7) that fndcpt does not
+    take the big-t shortcut, so all nperm permutations and both edge tests run.  nperm is what the CPU oracle can do
+    in seconds (the full 100k-permutation case is a bench-only property run); results must be bit-identical."""
+    from genomic_b200 import synth
+    units = [synth.null_unit(20260105, 50000).astype(np.float64),
+             synth.null_unit(20260106, 50000, shift_at=25000, shift=0.01).astype(np.float64)]
+    vals, off = pack(units)
+    p = SegParams(nperm=300, alpha=0.01, do_smooth=False, rng_kind=0, chain=False, seed=1)
+    got, want = check_batch(ctx, oracle, vals, off, p)
+    assert got.perms_run >= 300  # unit (ii) ran the whole permutation loop at least once
+
+
 @pytest.mark.parametrize("mode", ["mt_chain", "mt_unit", "philox"])
 def test_hybrid_matches_oracle(ctx, oracle, mode):
     """hybrid p-values (htmaxp + tailp, CBS.cpp:387-485, :324-339; tests/cbs_test.cpp:264-285 style)"""

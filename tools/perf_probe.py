@@ -16,7 +16,8 @@ print("fp64 pipe: %.3f T inst/s" % ctx.measure_fp64(), flush=True)
 for scale in scales:
     vals, off, lab, ids = synth.cohort(list(range(nsamp)), scale=scale)
     for mode in modes:
-        gp = Params(nperm=nperm, rng_mode=RNG_PHILOX if mode == "philox" else RNG_MT19937_64, chain=False, seed=1)
+        gp = Params(nperm=nperm, rng_mode=RNG_PHILOX if mode == "philox" else RNG_MT19937_64, chain=False, seed=1,
+                    first_batch=int(os.environ.get("FIRST_BATCH", "0")), max_batch=int(os.environ.get("MAX_BATCH", "0")))
         for rep in range(3):
             ctx.set_profiling(events=(rep == 1), counters=(rep == 2))
             t0 = time.time()
