@@ -331,7 +331,7 @@ int run_cbs(cbs_gpu_ctx* c, const std::vector<long long>& off, const uint64_t* u
     const bool shared_stream = mt && !p->chain;
     long long want_draws = (mt && !shared_stream) ? std::max<long long>(want_arena / 3, 8 * (Nmax + 312)) : 1;
     // shared raw MT stream (chain == 0): as long as the largest consumption of any one unit
-    long long want_stream = shared_stream ? std::max<long long>(env_ll("CBS_GPU_STREAM_MB", 4096) * (1LL << 20) / 8, 4 * (Nmax + 312)) : 0;
+    long long want_stream = shared_stream ? std::max<long long>(env_ll("CBS_GPU_STREAM_MB", 16384) * (1LL << 20) / 8, 4 * (Nmax + 312)) : 0;
     const long long env_arena = env_ll("CBS_GPU_ARENA_MB", 0);
     if (env_arena > 0) { want_arena = env_arena * (1LL << 20) / 8; if (mt && !shared_stream) want_draws = std::max<long long>(want_arena / 3, 8 * (Nmax + 312)); }
     {
