@@ -273,6 +273,9 @@ struct Dev {
     // shuffle work lists by segment-length class (shuffle_class below): 0..6 index arrays in shared
     // memory (16-bit), 7 = longer than 65535 markers (32-bit index array in the arena)
     int n_shuf[8]; int* shuf_item[8]; int* shuf_prefix[8];
+    int* shuf_p0[8];   // first permutation of the item that the entry covers (an item can be split between its
+                       // shared-memory class and the L2 shuffle)
+    int shuf_cap[8];   // permutations of the class that fit on the GPU at once (0: never spill to the L2 shuffle)
     // work-stealing counters (reset every round): 0 global shuffle, 1 scan, 2 edge, 3 prefix, 4 hscan,
     // 8+cls shared-memory shuffle of class cls
     unsigned ctr[16];
@@ -292,6 +295,10 @@ enum { ERR_TASK_CAP = 101, ERR_SEG_CAP = 102, ERR_ARENA = 103, ERR_SPLIT_CAP = 1
 // permutation; the class fixes the array size, hence how many permutations an SM holds at once
 // (24 / 13 / 6 / 4 / 3 / 2 / 1).  7: 32-bit index array in the arena (L2 / HBM latency per step).
 enum { SHUF_NCLS = 8, SHUF_GLOBAL = 7 };
+// A shared-memory class holds few permutations at once (1..4 per SM from class 3 on).  When a round brings more than
+// SHUF_WAVES times that many, the rest of a batch goes to the L2 shuffle: slower per permutation, but thousands run at
+// once, so both parts finish at about the same time.
+enum { SHUF_SPILL_MIN = 3, SHUF_WAVES = 4, SHUF_SPILL_LEAST = 64 };
 CBS_HD int shuffle_class_max(int cls) {
     return cls == 0 ? 4096 : cls == 1 ? 8192 : cls == 2 ? 16384 : cls == 3 ? 24576 : cls == 4 ? 32768 : cls == 5 ? 49152 : 65535;
 }
@@ -311,7 +318,10 @@ struct Sched {
     int* out_list;
     int n_out;
     long long arena_used, rej_used, draws_used;
-    CBS_HD explicit Sched(Dev& d) : D(d), out_list(nullptr), n_out(0), arena_used(0), rej_used(0), draws_used(0) {}
+    int shuf_used[SHUF_NCLS];  // permutations given to each shared-memory class this round
+    CBS_HD explicit Sched(Dev& d) : D(d), out_list(nullptr), n_out(0), arena_used(0), rej_used(0), draws_used(0) {
+        for (int k = 0; k < SHUF_NCLS; ++k) shuf_used[k] = 0;
+    }
 
     CBS_HD int alloc_task() {
         if (D.free_head == D.free_tail) { D.error = ERR_TASK_CAP; return -1; }
@@ -473,7 +483,7 @@ struct Sched {
         if (want > p.nperm - t.perms_done) want = p.nperm - t.perms_done;
         const int cls = shuffle_class(t.n);
         // the global-memory shuffle keeps a 32-bit index array per permutation in the arena
-        const long long idxd = (cls == SHUF_GLOBAL) ? idx_stride(t.n) : 0;  // doubles per permutation
+        const long long idxd = (cls >= SHUF_SPILL_MIN) ? idx_stride(t.n) : 0;  // doubles per permutation (if it goes to L2)
         const long long per = idxd + sx_stride(t.n) + bs_stride(t.nb);
         const bool mtwin = p.rng_mode == RNG_MT && !D.shared_stream;
         // never let one task take more than half of the arena
@@ -486,7 +496,15 @@ struct Sched {
             if (by_span < 1) { D.error = ERR_ARENA; return false; }
             if (want > by_span) want = (int)by_span;
         }
-        const long long need = per * want;
+        // how many of the batch go to the L2 shuffle
+        int gpart = (cls == SHUF_GLOBAL) ? want : 0;
+        if (cls != SHUF_GLOBAL && cls >= SHUF_SPILL_MIN && D.shuf_cap[cls] > 0) {
+            const int room = SHUF_WAVES * D.shuf_cap[cls] - shuf_used[cls];
+            const int spart = want < room ? want : (room > 0 ? room : 0);
+            gpart = want - spart;
+            if (gpart < SHUF_SPILL_LEAST) gpart = 0;
+        }
+        const long long need = idxd * gpart + (sx_stride(t.n) + bs_stride(t.nb)) * want;
         const long long dneed = (p.rng_mode == RNG_MT) ? (long long)want * t.n : 0;
         if (arena_used + need > D.arena_cap || rej_used + want > D.rej_cap || (mtwin && draws_used + dneed + 312 > D.draws_cap)) {
             t.deferred = 1;
@@ -506,8 +524,8 @@ struct Sched {
                 draws_used += dneed + 312;  // the generator appends the 312 words that follow the window
             }
         }
-        t.off_A = (cls == SHUF_GLOBAL) ? arena_used : -1;
-        t.off_sx = arena_used + idxd * want;
+        t.off_A = gpart ? arena_used : -1;
+        t.off_sx = arena_used + idxd * gpart;
         t.off_bs = t.off_sx + sx_stride(t.n) * want;
         arena_used += need;
         t.off_rej = rej_used; rej_used += want;
@@ -517,11 +535,18 @@ struct Sched {
         it.task = idx; it.P = want; it.obs = 0;
         D.item_prefix[D.n_items + 1] = D.item_prefix[D.n_items] + want;
         D.item_uprefix[D.n_items + 1] = D.item_uprefix[D.n_items] + ((want + 31) >> 5);
-        {
+        if (want - gpart > 0) {  // permutations [0, want-gpart): the class's own shuffle
             const int q = D.n_shuf[cls];
-            D.shuf_item[cls][q] = D.n_items;
-            D.shuf_prefix[cls][q + 1] = D.shuf_prefix[cls][q] + want;
+            D.shuf_item[cls][q] = D.n_items; D.shuf_p0[cls][q] = 0;
+            D.shuf_prefix[cls][q + 1] = D.shuf_prefix[cls][q] + (want - gpart);
             D.n_shuf[cls] = q + 1;
+            shuf_used[cls] += want - gpart;
+        }
+        if (gpart > 0) {  // permutations [want-gpart, want): L2 shuffle (all of them for segments > 65535 markers)
+            const int q = D.n_shuf[SHUF_GLOBAL];
+            D.shuf_item[SHUF_GLOBAL][q] = D.n_items; D.shuf_p0[SHUF_GLOBAL][q] = want - gpart;
+            D.shuf_prefix[SHUF_GLOBAL][q + 1] = D.shuf_prefix[SHUF_GLOBAL][q] + gpart;
+            D.n_shuf[SHUF_GLOBAL] = q + 1;
         }
         D.n_items++;
         t.deferred = 0;
@@ -732,6 +757,7 @@ struct Sched {
         for (int k = 0; k < SHUF_NCLS; ++k) { D.n_shuf[k] = 0; D.shuf_prefix[k][0] = 0; }
         for (int k = 0; k < 16; ++k) D.ctr[k] = 0;
         arena_used = 0; rej_used = 0; draws_used = 0;
+        for (int k = 0; k < SHUF_NCLS; ++k) shuf_used[k] = 0;
         const bool mt = D.prm.rng_mode == RNG_MT;
         if (D.shared_stream && D.gen_E > 0) { D.stream_len = D.gen_base + D.gen_E; D.gen_E = 0; }
         int wpos = 0;

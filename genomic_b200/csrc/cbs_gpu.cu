@@ -260,6 +260,12 @@ bool pick_scan_warps(cbs_gpu_ctx* c, ScanLayout& lay, int* occ_out) {
     return true;
 }
 
+// shared-memory shuffle classes: dynamic shared memory of a CTA (one warp, one permutation) and CTAs per SM
+size_t shuffle_smem_bytes(int cls) { return (size_t)shuffle_class_max(cls) * 2 + 32 + FY_SCRATCH; }
+int shuffle_occupancy(const cbs_gpu_ctx* c, int cls) {
+    return (int)std::max<size_t>(1, std::min<size_t>(32, (c->smem_optin + 1024) / (shuffle_smem_bytes(cls) + 1024)));
+}
+
 struct RunCaps {
     int task_cap, list_cap, seg_cap, split_cap, max_live;
     long long arena_cap, draws_cap, rej_cap;
@@ -316,7 +322,7 @@ int run_cbs(cbs_gpu_ctx* c, const std::vector<long long>& off, const uint64_t* u
     ENSURE(c, c->edges, sizeof(EdgeItem) * (size_t)cap.list_cap);
     ENSURE(c, c->edge_prefix, sizeof(int) * (size_t)(cap.list_cap + 1));
     ENSURE(c, c->gen_chain, sizeof(int) * (size_t)(n_chains + 1));
-    ENSURE(c, c->shuf, sizeof(int) * (2 * SHUF_NCLS + 1) * (size_t)(cap.list_cap + 1));
+    ENSURE(c, c->shuf, sizeof(int) * (3 * SHUF_NCLS + 1) * (size_t)(cap.list_cap + 1));
     ENSURE(c, c->means, sizeof(double) * (size_t)cap.seg_cap);
     ENSURE(c, c->seed312, sizeof(uint64_t) * 312);
     ENSURE(c, c->dev, sizeof(Dev));
@@ -388,6 +394,7 @@ int run_cbs(cbs_gpu_ctx* c, const std::vector<long long>& off, const uint64_t* u
         hD.shuf_prefix[k] = c->shuf.as<int>() + (size_t)(2 * k + 1) * (cap.list_cap + 1);
     }
     hD.item_uprefix = c->shuf.as<int>() + (size_t)(2 * SHUF_NCLS) * (cap.list_cap + 1);
+    for (int k = 0; k < SHUF_NCLS; ++k) hD.shuf_p0[k] = c->shuf.as<int>() + (size_t)(2 * SHUF_NCLS + 1 + k) * (cap.list_cap + 1);
     hD.shared_stream = shared_stream ? 1 : 0;
     hD.stream = c->stream_buf.as<uint64_t>();
     hD.stream_cap = shared_stream ? (long long)(c->stream_buf.cap / 8) : 0;
@@ -408,6 +415,12 @@ int run_cbs(cbs_gpu_ctx* c, const std::vector<long long>& off, const uint64_t* u
         if (c->jump_ready) { hD.jump_polys = c->jump.as<uint64_t>(); hD.span_max = (long long)mtjump::NSEG * mtjump::SEG; }
     }
     hD.profile = c->counting ? 1 : 0;
+    // permutations a shared-memory shuffle class holds on the GPU at once (the scheduler spills oversized batches of the
+    // classes with few resident permutations to the L2 shuffle)
+    for (int cls = 0; cls < SHUF_NCLS; ++cls) hD.shuf_cap[cls] = 0;
+    if (env_ll("CBS_GPU_SPILL", 0) || getenv("CBS_GPU_SPILL_CAP"))  // opt-in: measured slower on B200 (the L2 shuffle is DRAM bound)
+        for (int cls = SHUF_SPILL_MIN; cls < SHUF_GLOBAL; ++cls)
+            hD.shuf_cap[cls] = (int)env_ll("CBS_GPU_SPILL_CAP", (long long)c->sm_count * shuffle_occupancy(c, cls));  // override: tests
 
     CUDA_TRY(c, cudaMemcpyAsync(c->unit_off.p, off.data(), sizeof(long long) * (size_t)(n_units + 1), cudaMemcpyHostToDevice, st));
     if (unit_ids) CUDA_TRY(c, cudaMemcpyAsync(c->unit_ids.p, unit_ids, sizeof(uint64_t) * (size_t)n_units, cudaMemcpyHostToDevice, st));
@@ -442,10 +455,11 @@ int run_cbs(cbs_gpu_ctx* c, const std::vector<long long>& off, const uint64_t* u
     // shared-memory shuffle kernel, one launch per segment-length class present in this call
     size_t shuf_smem[SHUF_GLOBAL]; int shuf_occ[SHUF_GLOBAL]; bool shuf_on[SHUF_GLOBAL];
     for (int cls = 0; cls < SHUF_GLOBAL; ++cls) {
-        shuf_smem[cls] = (size_t)shuffle_class_max(cls) * 2 + 32 + FY_SCRATCH;
+        shuf_smem[cls] = shuffle_smem_bytes(cls);
         shuf_on[cls] = (cls == 0) || Nmax > shuffle_class_max(cls - 1);  // no unit is long enough otherwise
-        shuf_occ[cls] = (int)std::max<size_t>(1, std::min<size_t>(32, (c->smem_optin + 1024) / (shuf_smem[cls] + 1024)));
+        shuf_occ[cls] = shuffle_occupancy(c, cls);
     }
+    const bool l2_shuffle_on = Nmax > shuffle_class_max(SHUF_SPILL_MIN - 1);  // own class (> 65535) or spilled batches
     static const int kShufTimer[SHUF_GLOBAL] = {K_SHUF0, K_SHUF1, K_SHUF1, K_SHUF2, K_SHUF2, K_SHUF3, K_SHUF3};
 
     // ---- rounds -------------------------------------------------------------------------------
@@ -494,7 +508,7 @@ int run_cbs(cbs_gpu_ctx* c, const std::vector<long long>& off, const uint64_t* u
             bool used_side[5] = {false, false, false, false, false};
             {
                 int slot = 0;
-                if (Nmax > 65535) {
+                if (l2_shuffle_on) {
                     cudaStream_t ss = c->side[4];
                     cudaStreamWaitEvent(ss, c->ev_gen, 0);
                     used_side[4] = true;

@@ -679,7 +679,7 @@ __global__ void __launch_bounds__(32) k_perm_smem(Dev* D, int cls) {
         if (g >= total) break;
         const int k = find_item(D->shuf_prefix[cls], nl, g);
         const PermItem it = D->items[D->shuf_item[cls][k]];
-        perm_warp(D, D->tasks[it.task], g - D->shuf_prefix[cls][k], IdxSmem{s_idx}, tab, lane);
+        perm_warp(D, D->tasks[it.task], D->shuf_p0[cls][k] + (g - D->shuf_prefix[cls][k]), IdxSmem{s_idx}, tab, lane);
     }
 }
 
@@ -701,9 +701,10 @@ __global__ void __launch_bounds__(128) k_perm(Dev* D) {
         const int k = find_item(D->shuf_prefix[SHUF_GLOBAL], nl, g);
         const PermItem it = D->items[D->shuf_item[SHUF_GLOBAL][k]];
         const Task& t = D->tasks[it.task];
-        const int p = g - D->shuf_prefix[SHUF_GLOBAL][k];
+        const int slot = g - D->shuf_prefix[SHUF_GLOBAL][k];  // the entry's permutations have consecutive index arrays
+        const int p = D->shuf_p0[SHUF_GLOBAL][k] + slot;
         const long long idxd = Sched::idx_stride(t.n);  // doubles per permutation (cbs_core.h plan_perm)
-        unsigned int* idx = (unsigned int*)(D->arena + t.off_A + (long long)p * idxd);
+        unsigned int* idx = (unsigned int*)(D->arena + t.off_A + (long long)slot * idxd);
         perm_warp(D, t, p, IdxGlobal{idx}, tab, lane);
     }
 }

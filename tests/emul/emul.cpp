@@ -106,7 +106,8 @@ extern "C" int64_t emul_segment_units(const double* values, const int64_t* unit_
     D.stream = stream.data(); D.stream_cap = D.shared_stream ? (1 << 24) : 0;
     if (D.shared_stream) { mt_seed_next312(seed, D.stream); D.stream_len = 312; D.stream_target = 312; }
     D.span_max = 1LL << 40;
-    std::vector<int> shuf_store(2 * SHUF_NCLS * (size_t)(4 * 4096 + n_units + 32));
+    std::vector<int> shuf_store(3 * SHUF_NCLS * (size_t)(4 * 4096 + n_units + 32));
+    for (int k = 0; k < SHUF_NCLS; ++k) D.shuf_p0[k] = shuf_store.data() + (size_t)(2 * SHUF_NCLS + k) * (4 * 4096 + n_units + 32);
     for (int k = 0; k < SHUF_NCLS; ++k) {
         D.shuf_item[k] = shuf_store.data() + (size_t)(2 * k) * (4 * 4096 + n_units + 32);
         D.shuf_prefix[k] = shuf_store.data() + (size_t)(2 * k + 1) * (4 * 4096 + n_units + 32);
