@@ -18,6 +18,7 @@
 namespace cbsg {
 
 enum { RNG_MT = 0, RNG_PHILOX = 1 };
+enum { SHUF_NCLS_MAX = 12 };  // room for the shuffle class tables (cbs_core.h: SHUF_NCLS)
 enum { SX_PAD = 48 };  // finite values kept behind the prefix sums of every permutation
 
 // mirrors the reference call arguments 1:1 (CBS.hpp:100-113) + rng selection
@@ -272,13 +273,13 @@ struct Dev {
     int n_gen;    int* gen_chain;
     // shuffle work lists by segment-length class (shuffle_class below): 0..6 index arrays in shared
     // memory (16-bit), 7 = longer than 65535 markers (32-bit index array in the arena)
-    int n_shuf[8]; int* shuf_item[8]; int* shuf_prefix[8];
-    int* shuf_p0[8];   // first permutation of the item that the entry covers (an item can be split between its
+    int n_shuf[SHUF_NCLS_MAX]; int* shuf_item[SHUF_NCLS_MAX]; int* shuf_prefix[SHUF_NCLS_MAX];
+    int* shuf_p0[SHUF_NCLS_MAX];   // first permutation of the item that the entry covers (an item can be split between its
                        // shared-memory class and the L2 shuffle)
-    int shuf_cap[8];   // permutations of the class that fit on the GPU at once (0: never spill to the L2 shuffle)
+    int shuf_cap[SHUF_NCLS_MAX];   // permutations of the class that fit on the GPU at once (0: never spill to the L2 shuffle)
     // work-stealing counters (reset every round): 0 global shuffle, 1 scan, 2 edge, 3 prefix, 4 hscan,
     // 8+cls shared-memory shuffle of class cls
-    unsigned ctr[16];
+    unsigned ctr[24];
     // ---- status -----------------------------------------------------------------------
     int done;
     int stall;  // consecutive rounds with live tasks but no planned work
@@ -291,21 +292,24 @@ struct Dev {
 
 enum { ERR_TASK_CAP = 101, ERR_SEG_CAP = 102, ERR_ARENA = 103, ERR_SPLIT_CAP = 104, ERR_INTERNAL = 105, ERR_STALL = 106, ERR_STREAM_CAP = 107 };
 
-// Shuffle classes.  0..6: the permutation is built on a 16-bit index array in shared memory, one warp per
-// permutation; the class fixes the array size, hence how many permutations an SM holds at once
-// (24 / 13 / 6 / 4 / 3 / 2 / 1).  7: 32-bit index array in the arena (L2 / HBM latency per step).
-enum { SHUF_NCLS = 8, SHUF_GLOBAL = 7 };
-// A shared-memory class holds few permutations at once (1..4 per SM from class 3 on).  When a round brings more than
-// SHUF_WAVES times that many, the rest of a batch goes to the L2 shuffle: slower per permutation, but thousands run at
-// once, so both parts finish at about the same time.
-enum { SHUF_SPILL_MIN = 3, SHUF_WAVES = 4, SHUF_SPILL_LEAST = 64 };
+// Shuffle classes.  0..7: the permutation is built on a 16-bit index array in shared memory, one warp per
+// permutation; the class fixes the array size, hence how many permutations an SM holds at once.  The limits are
+// the longest segments for which 22 / 8 / 6 / 5 / 4 / 3 / 2 / 1 arrays (plus 8.5 KB of scratch each) fit in the
+// 227 KB of an SM.  8: 32-bit index array in the arena (L2 / HBM latency per step).
+enum { SHUF_NCLS = 9, SHUF_GLOBAL = 8 };
 CBS_HD int shuffle_class_max(int cls) {
-    return cls == 0 ? 4096 : cls == 1 ? 8192 : cls == 2 ? 16384 : cls == 3 ? 24576 : cls == 4 ? 32768 : cls == 5 ? 49152 : 65535;
+    return cls == 0 ? 4096 : cls == 1 ? 8192 : cls == 2 ? 14500 : cls == 3 ? 18400 : cls == 4 ? 24200 : cls == 5 ? 33900
+         : cls == 6 ? 53200 : 65535;
 }
 CBS_HD int shuffle_class(int n) {
     for (int cls = 0; cls < SHUF_GLOBAL; ++cls) if (n <= shuffle_class_max(cls)) return cls;
     return SHUF_GLOBAL;
 }
+
+// A shared-memory class holds few permutations at once (1..4 per SM from class 3 on).  When a round brings more than
+// SHUF_WAVES times that many, the rest of a batch goes to the L2 shuffle: slower per permutation, but thousands run at
+// once, so both parts finish at about the same time.
+enum { SHUF_SPILL_MIN = 4, SHUF_WAVES = 4, SHUF_SPILL_LEAST = 64 };
 
 // ------------------------------------------------------------------------------------
 // Scheduler (runs in ONE thread per round; plain sequential C++ so that the very same
@@ -755,7 +759,7 @@ struct Sched {
         D.n_prep = 0; D.n_items = 0; D.n_edgeprep = 0; D.n_edge = 0; D.n_gen = 0;
         D.item_prefix[0] = 0; D.item_uprefix[0] = 0; D.edge_prefix[0] = 0;
         for (int k = 0; k < SHUF_NCLS; ++k) { D.n_shuf[k] = 0; D.shuf_prefix[k][0] = 0; }
-        for (int k = 0; k < 16; ++k) D.ctr[k] = 0;
+        for (int k = 0; k < 24; ++k) D.ctr[k] = 0;
         arena_used = 0; rej_used = 0; draws_used = 0;
         for (int k = 0; k < SHUF_NCLS; ++k) shuf_used[k] = 0;
         const bool mt = D.prm.rng_mode == RNG_MT;

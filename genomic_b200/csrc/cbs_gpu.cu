@@ -460,7 +460,7 @@ int run_cbs(cbs_gpu_ctx* c, const std::vector<long long>& off, const uint64_t* u
         shuf_occ[cls] = shuffle_occupancy(c, cls);
     }
     const bool l2_shuffle_on = Nmax > shuffle_class_max(SHUF_SPILL_MIN - 1);  // own class (> 65535) or spilled batches
-    static const int kShufTimer[SHUF_GLOBAL] = {K_SHUF0, K_SHUF1, K_SHUF1, K_SHUF2, K_SHUF2, K_SHUF3, K_SHUF3};
+    static const int kShufTimer[SHUF_GLOBAL] = {K_SHUF0, K_SHUF1, K_SHUF1, K_SHUF1, K_SHUF2, K_SHUF2, K_SHUF3, K_SHUF3};
 
     // ---- rounds -------------------------------------------------------------------------------
     *c->h_done = 0;
