@@ -464,7 +464,8 @@ int run_cbs(cbs_gpu_ctx* c, const std::vector<long long>& off, const uint64_t* u
 
     // ---- rounds -------------------------------------------------------------------------------
     *c->h_done = 0;
-    const int G = 8;  // rounds per group
+    const int G = 16;  // rounds per group; two groups are kept in flight, so a typical call (20-30 rounds) is enqueued up front and
+                       // host scheduling jitter cannot starve the GPU (the surplus rounds are empty launches, ~0.1 ms each)
     const bool debug = env_ll("CBS_GPU_DEBUG", 0) != 0;
     int groups_in_flight = 0, rounds = 0;
     bool ahead_pending = false;
