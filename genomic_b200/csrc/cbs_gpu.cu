@@ -481,7 +481,7 @@ int run_cbs(cbs_gpu_ctx* c, const std::vector<long long>& off, const uint64_t* u
             { LaunchTimer t(c, K_SCHED); k_sched<<<1, 256, 0, st>>>(dD, c->d_done); }
             cudaEventRecord(c->ev_sched, st);
             cudaStreamWaitEvent(c->side[0], c->ev_sched, 0);
-            { LaunchTimer t(c, K_PREP, c->side[0]); k_prep<<<c->sm_count * 8, 32, 0, c->side[0]>>>(dD); }
+            { LaunchTimer t(c, K_PREP, c->side[0]); k_tables<<<dim3(16, 64), 256, 0, c->side[0]>>>(dD); k_prep<<<c->sm_count * 8, 32, 0, c->side[0]>>>(dD); c->launches++; }
             cudaEventRecord(c->ev_side[0], c->side[0]);
             cudaStreamWaitEvent(c->side[1], c->ev_sched, 0);
             { LaunchTimer t(c, K_EDGEPREP, c->side[1]); k_edgeprep<<<c->sm_count * 4, 32, 0, c->side[1]>>>(dD); }
@@ -887,6 +887,7 @@ static int run_raw_scan(cbs_gpu_ctx* c, const double* xh, int n, int count, doub
     lay.set_table(n);
     if (!pick_scan_warps(c, lay, nullptr)) return fail(c, CBS_GPU_ERR_UNSUPPORTED, "vector too long for the scan kernel's shared memory");
     Dev* dD = c->dev.as<Dev>();
+    k_tables<<<dim3(16, 64), 256, 0, st>>>(dD);
     k_prep<<<std::min(count, c->sm_count * 8), 32, 0, st>>>(dD);
     k_scan<<<std::min(count, c->sm_count * 2), lay.warps * 32, lay.bytes(), st>>>(dD, lay);
     CUDA_TRY(c, cudaGetLastError());

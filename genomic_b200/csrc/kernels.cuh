@@ -231,15 +231,7 @@ __device__ void prep_warp(Dev* D, Task& t, int lane, double* buf) {
         s = shfl_d(s, 0);
         avg = s / (double)n;
     }
-    int* bb = D->bbtab + base;
-    for (int b = lane; b <= nb; b += 32) bb[b] = block_end(n, nb, b);
-    const double rn = (double)n;
-    for (int L = 1 + lane; L < n; L += 32) {
-        const double rr = (double)L;
-        const double prod = rr * (rn - rr);
-        D->factab[base + L] = rn / prod;
-        D->gtab[base + L] = sqrt(prod / rn);
-    }
+    // (block ends, fac[L] and g[L] of the segment: k_tables, which runs before this kernel on the same stream)
     // CBS.cpp:987-989 centring and tss, :83-87 prefix sums
     double* sx = D->arena + t.off_sx;
     double run = 0.0, tss = 0.0;
@@ -278,6 +270,28 @@ __device__ void prep_warp(Dev* D, Task& t, int lane, double* buf) {
     run = shfl_d(run, 0);
     for (int k = lane; k < SX_PAD; k += 32) sx[n + 1 + k] = run;  // finite padding behind S_n (read by k_scan)
     if (lane == 0 && !raw) t.tss = tss;
+}
+
+// k_tables: per new segment the block ends bb[0..nb] (CBS.cpp:71,77), fac[L] = n/(L(n-L)) (the reference's expression,
+// :191-193) and g[L] = sqrt(L(n-L)/n); divisions and square roots in double, spread over the whole grid
+__global__ void __launch_bounds__(256) k_tables(Dev* D) {
+    if (D->done) return;
+    for (int k = blockIdx.y; k < D->n_prep; k += gridDim.y) {
+        const Task& t = D->tasks[D->prep_task[k]];
+        const long long base = D->unit_off[t.unit] + t.lo;
+        const int n = t.n, nb = t.nb;
+        const double rn = (double)n;
+        for (int L = blockIdx.x * blockDim.x + threadIdx.x; L < n; L += gridDim.x * blockDim.x) {
+            if (L <= nb) D->bbtab[base + L] = block_end(n, nb, L);
+            if (L >= 1) {
+                const double rr = (double)L;
+                const double prod = rr * (rn - rr);
+                D->factab[base + L] = rn / prod;
+                D->gtab[base + L] = sqrt(prod / rn);
+            }
+        }
+        if (n <= nb && blockIdx.x == 0 && threadIdx.x == 0) for (int b = n; b <= nb; ++b) D->bbtab[base + b] = block_end(n, nb, b);
+    }
 }
 
 __global__ void __launch_bounds__(32) k_prep(Dev* D) {
