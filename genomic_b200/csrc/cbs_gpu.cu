@@ -48,7 +48,7 @@ struct cbs_gpu_ctx {
     int* d_done = nullptr;  // device alias of h_done
     DevBuf x, cur, gtab, factab, bbtab, unit_off, unit_ids, tasks, ring, act0, act1, chains, segs, splits, udraws, arena,
         rej, draws0, draws1, prep_task, items, item_prefix, edgeprep_task, edges, edge_prefix, gen_chain, means, seed312,
-        dev, staging, fv, fidx, flab, lab, diffs, diffs_sorted, gout, cubtmp, flag, goff, stream_buf, shuf, jump;
+        dev, staging, fv, fidx, flab, lab, diffs, diffs_sorted, gout, cubtmp, flag, goff, stream_buf, shuf, jump, tailp;
     bool jump_ready = false;
     // lanes: a call with independent units is split into contiguous unit ranges that run as separate
     // worklists on their own streams (child contexts), so the latency-bound phases of one lane overlap
@@ -326,6 +326,7 @@ int run_cbs(cbs_gpu_ctx* c, const std::vector<long long>& off, const uint64_t* u
     ENSURE(c, c->means, sizeof(double) * (size_t)cap.seg_cap);
     ENSURE(c, c->seed312, sizeof(uint64_t) * 312);
     ENSURE(c, c->dev, sizeof(Dev));
+    if (p->hybrid) ENSURE(c, c->tailp, sizeof(double) * 100 * (size_t)cap.list_cap);  // tailp quadrature terms per new segment
 
     // arenas: sized from the workload, bounded by what the device has left
     size_t free_b = 0, total_b = 0;
@@ -531,8 +532,9 @@ int run_cbs(cbs_gpu_ctx* c, const std::vector<long long>& off, const uint64_t* u
             { LaunchTimer t(c, K_SCAN); k_scan<<<scan_grid, lay.warps * 32, scan_smem, st>>>(dD, lay); }
             if (p->hybrid) {
                 k_hscan<<<c->sm_count * 4, 256, 0, st>>>(dD);
-                k_tailp<<<c->sm_count, 64, 0, st>>>(dD);
-                c->launches += 2;
+                k_tailp_terms<<<c->sm_count * 8, 128, 0, st>>>(dD, c->tailp.as<double>());
+                k_tailp_sum<<<c->sm_count, 64, 0, st>>>(dD, c->tailp.as<double>());
+                c->launches += 3;
             }
             cudaStreamWaitEvent(st, c->ev_side[1], 0);
             ++rounds;
@@ -755,7 +757,7 @@ void cbs_gpu_destroy(cbs_gpu_ctx* c) {
                       &c->act1, &c->chains, &c->segs, &c->splits, &c->udraws, &c->arena, &c->rej, &c->draws0, &c->draws1,
                       &c->prep_task, &c->items, &c->item_prefix, &c->edgeprep_task, &c->edges, &c->edge_prefix, &c->gen_chain,
                       &c->means, &c->seed312, &c->dev, &c->staging, &c->fv, &c->fidx, &c->flab, &c->lab, &c->diffs,
-                      &c->diffs_sorted, &c->gout, &c->cubtmp, &c->flag, &c->goff, &c->stream_buf, &c->shuf, &c->jump};
+                      &c->diffs_sorted, &c->gout, &c->cubtmp, &c->flag, &c->goff, &c->stream_buf, &c->shuf, &c->jump, &c->tailp};
     for (DevBuf* b : bufs) if (b->p) cudaFree(b->p);
     if (c->h_stage) cudaFreeHost(c->h_stage);
     if (c->h_done) cudaFreeHost(c->h_done);

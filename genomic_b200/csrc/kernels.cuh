@@ -1630,29 +1630,69 @@ __device__ double dev_it1tsq(double x, double a) {
     out -= (8.0 * y) / (1.0 - 4.0 * y * y) + 2.0 * log((1.0 + 2.0 * y) / (1.0 - 2.0 * y));
     return out;
 }
-__device__ double dev_tailp(double b, double delta, int m, int ngrid, double tol) {
-    const double dincr = (0.5 - delta) / (double)ngrid;
-    const double bsqrtm = b / sqrt((double)m);
-    double tl = 0.5 - dincr, t = 0.5 - 0.5 * dincr, out = 0.0;
-    for (int i = 1; i <= ngrid; ++i) {
-        tl += dincr;
-        t += dincr;
-        const double x = bsqrtm / sqrt(t * (1.0 - t));
-        const double nux = dev_nu(x, tol);
-        out += (nux * nux) * dev_it1tsq(tl, dincr);
+// nu() (CBS.cpp:18-41) by a whole warp: the terms 2*Phi(-x*sqrt(dk)/2)/dk of the series are evaluated 32 at a time
+// (dk is an exact integer, so lane l evaluates the very expression the sequential loop would), and subtracted from
+// lnu1 in the sequential order by every lane (the value stays uniform over the warp).
+__device__ double warp_nu(double x, double tol, int lane) {
+    if (!(x > 0.01)) return exp(-0.583 * x);
+    double lnu1 = log(2.0) - 2.0 * log(x);
+    double lnu0 = lnu1;
+    long long done = 0;  // terms subtracted so far (= dk)
+    auto take = [&](int k) {  // the next k terms
+        for (int c0 = 0; c0 < k; c0 += 32) {
+            const int cnt = min(32, k - c0);
+            const double dk = (double)(done + lane + 1);
+            const double term = (lane < cnt) ? 2.0 * dev_fpnorm(-x * sqrt(dk) / 2.0) / dk : 0.0;
+            for (int q = 0; q < cnt; ++q) lnu1 -= shfl_d(term, q);
+            done += cnt;
+        }
+    };
+    int k = 2;
+    take(k);
+    while (fabs((lnu1 - lnu0) / lnu1) > tol) {
+        lnu0 = lnu1;
+        take(k);
+        k *= 2;
+        if (k > (1 << 24)) break;
     }
-    out = 9.973557e-2 * pow(b, 3.0) * exp(-b * b / 2.0) * out;
-    return 2.0 * out;
+    return exp(lnu1);
 }
 
-__global__ void __launch_bounds__(64) k_tailp(Dev* D) {
+// tailp (CBS.cpp:324-339).  k_tailp_terms: a warp per quadrature point (ngrid = 100 per segment; a point's nu() series
+// has up to ~1e6 terms for the small x of SNP6-scale segments); k_tailp_sum: the terms are added in the reference's order.
+#define TAILP_NGRID 100
+__global__ void __launch_bounds__(128) k_tailp_terms(Dev* D, double* terms) {
+    if (D->done || !D->prm.hybrid) return;
+    const int lane = threadIdx.x & 31;
+    const int total = D->n_prep * TAILP_NGRID;
+    for (int w = blockIdx.x * 4 + (threadIdx.x >> 5); w < total; w += gridDim.x * 4) {
+        const int k = w / TAILP_NGRID, i = w - k * TAILP_NGRID + 1;  // quadrature point i = 1..ngrid of prep task k
+        const Task& t = D->tasks[D->prep_task[k]];
+        if (!t.use_hybrid || t.alleq) continue;
+        const double b = sqrt(t.ostat);
+        if (!(b > 0.1)) continue;
+        const double delta = (double)(D->prm.kmax + 1) / (double)t.n;  // CBS.cpp:984
+        const double dincr = (0.5 - delta) / (double)TAILP_NGRID;
+        const double bsqrtm = b / sqrt((double)t.n);
+        // tl and t after i increments of dincr, accumulated as the reference does (repeated addition)
+        double tl = 0.5 - dincr, tt = 0.5 - 0.5 * dincr;
+        for (int q = 0; q < i; ++q) { tl += dincr; tt += dincr; }
+        const double x = bsqrtm / sqrt(tt * (1.0 - tt));
+        const double nux = warp_nu(x, D->prm.tol, lane);
+        if (lane == 0) terms[(long long)k * TAILP_NGRID + (i - 1)] = (nux * nux) * dev_it1tsq(tl, dincr);
+    }
+}
+__global__ void __launch_bounds__(64) k_tailp_sum(Dev* D, const double* terms) {
     if (D->done || !D->prm.hybrid) return;
     for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < D->n_prep; k += gridDim.x * blockDim.x) {
         Task& t = D->tasks[D->prep_task[k]];
         if (!t.use_hybrid || t.alleq) continue;
-        const double t1 = sqrt(t.ostat);
-        const double delta = (double)(D->prm.kmax + 1) / (double)t.n;  // CBS.cpp:984
-        t.pval1 = (t1 > 0.1) ? dev_tailp(t1, delta, t.n, 100, D->prm.tol) : 1.0;
+        const double b = sqrt(t.ostat);
+        if (!(b > 0.1)) { t.pval1 = 1.0; continue; }
+        double out = 0.0;
+        for (int q = 0; q < TAILP_NGRID; ++q) out += terms[(long long)k * TAILP_NGRID + q];
+        out = 9.973557e-2 * pow(b, 3.0) * exp(-b * b / 2.0) * out;
+        t.pval1 = 2.0 * out;
     }
 }
 
