@@ -286,6 +286,16 @@ def test_hybrid_matches_oracle(ctx, oracle, mode):
         check_batch(ctx, oracle, vals, off, p)
 
 
+def test_hybrid_long_unit(ctx, oracle):
+    # 60,000 markers: the analytic tail probability (tailp/nu, CBS.cpp:18-41, :324-339) sums ~1e5 series terms per
+    # quadrature point here; on the device a warp evaluates them 32 at a time and subtracts them in the reference's order
+    from genomic_b200 import synth
+    units = [synth.null_unit(20260107, 60000, shift_at=20000, shift=0.012).astype(np.float64)]
+    vals, off = pack(units)
+    p = SegParams(nperm=200, alpha=0.01, hybrid=True, do_smooth=False, rng_kind=0, chain=False, seed=1)
+    check_batch(ctx, oracle, vals, off, p)
+
+
 def test_hybrid_kat_case1(ctx):
     # tests/cbs_test.cpp:287-307 hybrid rows: lengths 20/20/20, means 0/1.5/0
     x = np.array([0.0] * 20 + [1.5] * 20 + [0.0] * 20)
