@@ -1465,7 +1465,9 @@ __global__ void __launch_bounds__(256, 3) k_scan(Dev* D, ScanLayout lay) {
                         pair_corner(c, bi, bj, s1, s2, clen);
                         const double smx = (s1 > s2) ? s1 : s2;
                         if (clen >= c.al0 && clen <= n - c.al0) {
-                            const double v = c.factab[clen] * smx * smx;
+                            // fac[clen] recomputed (same expression as the table: one division instead of an L2 round trip)
+                            const double rr = (double)clen;
+                            const double v = c.rn / (rr * (c.rn - rr)) * smx * smx;
                             if (v > lb) lb = v;
                         }
                         int ilo, ihi, jlo, jhi, lenlo, lenhi;
