@@ -138,6 +138,12 @@ def load_library(path: str | None = None) -> C.CDLL:
     L.cbs_gpu_segment.argtypes = [vp, C.POINTER(C.c_double), C.c_int32, C.POINTER(CParams), C.POINTER(C.c_uint64),
                                   C.c_int32, C.POINTER(C.c_int32), C.POINTER(C.c_double), C.POINTER(C.c_int32),
                                   C.POINTER(C.c_uint64)]
+    L.cbs_gpu_segment_weighted.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_double), C.c_int32,
+                                           C.POINTER(CParams), C.POINTER(C.c_uint64), C.c_int32, C.POINTER(C.c_int32),
+                                           C.POINTER(C.c_double), C.POINTER(C.c_int32), C.POINTER(C.c_uint64)]
+    L.cbs_gpu_segment_weighted_batch.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_double), C.c_int,
+                                                 C.POINTER(C.c_int64), C.POINTER(C.c_uint64), C.c_int32,
+                                                 C.POINTER(CParams), C.POINTER(C.POINTER(CResult))]
     L.cbs_gpu_tmaxo.argtypes = [vp, C.POINTER(C.c_double), C.c_int32, C.c_double, C.c_int32, C.c_int32,
                                 C.POINTER(C.c_double), C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
     L.cbs_gpu_tmaxp.argtypes = [vp, C.POINTER(C.c_double), C.c_int32, C.c_int32, C.c_double, C.c_int32, C.c_int32,
@@ -149,7 +155,7 @@ EXPORTED_SYMBOLS = (
     "cbs_gpu_default_params", "cbs_gpu_create", "cbs_gpu_destroy", "cbs_gpu_last_error", "cbs_gpu_set_stream",
     "cbs_gpu_segment_batch", "cbs_gpu_result_free", "cbs_gpu_smooth", "cbs_gpu_segment", "cbs_gpu_tmaxo",
     "cbs_gpu_tmaxp", "cbs_gpu_measure_fp64", "cbs_gpu_last_kernel_ms", "cbs_gpu_set_profiling",
-    "cbs_gpu_last_arc_evals", "cbs_gpu_selftest",
+    "cbs_gpu_last_arc_evals", "cbs_gpu_selftest", "cbs_gpu_segment_weighted", "cbs_gpu_segment_weighted_batch",
 )
 
 
@@ -235,20 +241,23 @@ class Context:
                                             n_units, C.byref(cp), C.byref(out))
         self._check(rc)
         try:
-            r = out.contents
-            ns = int(r.n_segments)
-            res = BatchResult(
-                seg_offsets=np.ctypeslib.as_array(r.seg_offsets, shape=(n_units + 1,)).copy(),
-                lengths=np.ctypeslib.as_array(r.lengths, shape=(ns,)).copy() if ns else np.zeros(0, np.int32),
-                means=np.ctypeslib.as_array(r.means, shape=(ns,)).copy() if ns else np.zeros(0),
-                draws=np.ctypeslib.as_array(r.draws_consumed, shape=(n_units,)).copy() if n_units else np.zeros(0, np.uint64),
-                rounds=int(r.rounds), perms_run=int(r.perms_run), perm_elems=int(r.perm_elements), kernel_launches=int(r.kernel_launches),
-                ms=dict(h2d=r.ms_h2d, smooth=r.ms_smooth, segment=r.ms_segment, d2h=r.ms_d2h),
-            )
-            if r.n_splits:
-                res.splits = [dict((f, getattr(r.splits[i], f)) for f, _ in CSplit._fields_) for i in range(int(r.n_splits))]
+            return self._unpack(out.contents, n_units)
         finally:
             self.lib.cbs_gpu_result_free(out)
+
+    @staticmethod
+    def _unpack(r, n_units) -> BatchResult:
+        ns = int(r.n_segments)
+        res = BatchResult(
+            seg_offsets=np.ctypeslib.as_array(r.seg_offsets, shape=(n_units + 1,)).copy(),
+            lengths=np.ctypeslib.as_array(r.lengths, shape=(ns,)).copy() if ns else np.zeros(0, np.int32),
+            means=np.ctypeslib.as_array(r.means, shape=(ns,)).copy() if ns else np.zeros(0),
+            draws=np.ctypeslib.as_array(r.draws_consumed, shape=(n_units,)).copy() if n_units else np.zeros(0, np.uint64),
+            rounds=int(r.rounds), perms_run=int(r.perms_run), perm_elems=int(r.perm_elements), kernel_launches=int(r.kernel_launches),
+            ms=dict(h2d=r.ms_h2d, smooth=r.ms_smooth, segment=r.ms_segment, d2h=r.ms_d2h),
+        )
+        if r.n_splits:
+            res.splits = [dict((f, getattr(r.splits[i], f)) for f, _ in CSplit._fields_) for i in range(int(r.n_splits))]
         return res
 
     # ---- single-call surface (reference signatures) -----------------------------------------------
@@ -284,6 +293,49 @@ class Context:
                                              C.byref(draws)))
         k = nseg.value
         return lengths[:k].copy(), means[:k].copy(), draws.value
+
+    def segment_weighted(self, x, weights, params: Params, mt_next312=None):
+        """cbs::segment_weighted (lib/cbs/CBS.hpp:115-128) -> (lengths, means, draws_consumed)."""
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        w = np.ascontiguousarray(weights, dtype=np.float64)
+        if len(x) != len(w):
+            raise ValueError("x and weights must have the same length")
+        cap = max(16, len(x))
+        lengths = np.zeros(cap, dtype=np.int32)
+        means = np.zeros(cap, dtype=np.float64)
+        nseg, draws = C.c_int32(0), C.c_uint64(0)
+        cp = params.c()
+        st = None
+        if mt_next312 is not None:
+            st = np.ascontiguousarray(mt_next312, dtype=np.uint64)
+            assert len(st) == 312
+        dp = C.POINTER(C.c_double)
+        self._check(self.lib.cbs_gpu_segment_weighted(
+            self.h, x.ctypes.data_as(dp), w.ctypes.data_as(dp), len(x), C.byref(cp),
+            st.ctypes.data_as(C.POINTER(C.c_uint64)) if st is not None else None, cap,
+            lengths.ctypes.data_as(C.POINTER(C.c_int32)), means.ctypes.data_as(dp), C.byref(nseg), C.byref(draws)))
+        k = nseg.value
+        return lengths[:k].copy(), means[:k].copy(), draws.value
+
+    def segment_weighted_batch(self, values, weights, unit_offsets, params: Params, unit_ids=None) -> BatchResult:
+        """cbs::segment_weighted for every unit of a flat float64 array (host memory); no smoothing."""
+        values = np.ascontiguousarray(values, dtype=np.float64)
+        weights = np.ascontiguousarray(weights, dtype=np.float64)
+        if len(values) != len(weights):
+            raise ValueError("values and weights must have the same length")
+        off = np.ascontiguousarray(unit_offsets, dtype=np.int64)
+        ids = None if unit_ids is None else np.ascontiguousarray(unit_ids, dtype=np.uint64)
+        cp = params.c()
+        res = C.POINTER(CResult)()
+        dp = C.POINTER(C.c_double)
+        self._check(self.lib.cbs_gpu_segment_weighted_batch(
+            self.h, values.ctypes.data_as(dp), weights.ctypes.data_as(dp), 0, off.ctypes.data_as(C.POINTER(C.c_int64)),
+            ids.ctypes.data_as(C.POINTER(C.c_uint64)) if ids is not None else None, len(off) - 1, C.byref(cp),
+            C.byref(res)))
+        try:
+            return self._unpack(res.contents, len(off) - 1)
+        finally:
+            self.lib.cbs_gpu_result_free(res)
 
     def tmaxo(self, x, tss, al0=2, ibin=False):
         """cbs::tmaxo (CBS.hpp:32) -> (statistic, start, end)."""

@@ -288,6 +288,11 @@ struct Dev {
     unsigned long long stat_perm_elems;     // sum over max-t permutations of the segment length
     int profile;                            // count scan work (bench / roofline)
     unsigned long long stat_slots, stat_arcs;  // arc slots issued by the scan fast path / of them real arcs
+    // ---- weighted CBS (cbs::segment_weighted, CBS.cpp:1026-1099); w == nullptr otherwise ----------
+    const double* w;  // weights, laid out like x
+    double* rw;       // sqrt(w) (CBS.cpp:1056)
+    double* cw;       // per pending segment, at the segment's offset: cumsum(w)/sqrt(sum w) (CBS.cpp:1062-1066)
+    double* ycur;     // cur * rw: what wxperm shuffles (CBS.cpp:540)
 };
 
 enum { ERR_TASK_CAP = 101, ERR_SEG_CAP = 102, ERR_ARENA = 103, ERR_SPLIT_CAP = 104, ERR_INTERNAL = 105, ERR_STALL = 106, ERR_STREAM_CAP = 107 };

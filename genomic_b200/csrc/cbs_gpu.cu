@@ -17,6 +17,7 @@
 #include "../../include/cbs_gpu.h"
 #include "host_math.h"
 #include "kernels.cuh"
+#include "weighted.cuh"
 #include "mt_jump.h"
 #include "prune.h"
 #include "smooth.cuh"
@@ -48,7 +49,8 @@ struct cbs_gpu_ctx {
     int* d_done = nullptr;  // device alias of h_done
     DevBuf x, cur, gtab, factab, bbtab, unit_off, unit_ids, tasks, ring, act0, act1, chains, segs, splits, udraws, arena,
         rej, draws0, draws1, prep_task, items, item_prefix, edgeprep_task, edges, edge_prefix, gen_chain, means, seed312,
-        dev, staging, fv, fidx, flab, lab, diffs, diffs_sorted, gout, cubtmp, flag, goff, stream_buf, shuf, jump, tailp;
+        dev, staging, fv, fidx, flab, lab, diffs, diffs_sorted, gout, cubtmp, flag, goff, stream_buf, shuf, jump, tailp,
+        wts, rw, cw, ycur;  // weighted CBS
     bool jump_ready = false;
     // lanes: a call with independent units is split into contiguous unit ranges that run as separate
     // worklists on their own streams (child contexts), so the latency-bound phases of one lane overlap
@@ -279,8 +281,7 @@ long long env_ll(const char* name, long long dflt) {
 
 // The core: x already resident (double, device, smoothed if requested) in c->x.
 int run_cbs(cbs_gpu_ctx* c, const std::vector<long long>& off, const uint64_t* unit_ids, int n_units,
-            const cbs_gpu_params* p, const uint64_t* mt_next312, bool raw_single /*unused*/, Dev& hD) {
-    (void)raw_single;
+            const cbs_gpu_params* p, const uint64_t* mt_next312, bool weighted /* weights resident in c->wts */, Dev& hD) {
     cudaStream_t st = c->stream;
     const long long N = off[n_units];
     long long Nmax = 0;
@@ -288,6 +289,8 @@ int run_cbs(cbs_gpu_ctx* c, const std::vector<long long>& off, const uint64_t* u
     if (Nmax > 1000000) return fail(c, CBS_GPU_ERR_UNSUPPORTED, "units longer than 1,000,000 markers are not supported");
     if (N > 2000000000LL) return fail(c, CBS_GPU_ERR_UNSUPPORTED, "more than 2e9 markers per call are not supported");
     const bool mt = p->rng_mode == CBS_GPU_RNG_MT19937_64;
+    if (weighted && p->hybrid && Nmax > p->nmin)
+        return fail(c, CBS_GPU_ERR_UNSUPPORTED, "weighted CBS with hybrid p-values (hwtmaxp) is not implemented: units must not exceed nmin");
 
     RunCaps cap;
     cap.task_cap = (int)std::min<long long>(std::max<long long>(4096, 64LL * n_units + 1024), 1 << 22);
@@ -303,6 +306,12 @@ int run_cbs(cbs_gpu_ctx* c, const std::vector<long long>& off, const uint64_t* u
     ENSURE(c, c->gtab, sizeof(double) * (size_t)(N + 1));
     ENSURE(c, c->factab, sizeof(double) * (size_t)(N + 1));
     ENSURE(c, c->bbtab, sizeof(int) * (size_t)(N + 1));
+    if (weighted) {
+        ENSURE(c, c->rw, sizeof(double) * (size_t)(N + 1));
+        ENSURE(c, c->cw, sizeof(double) * (size_t)(N + 1));
+        ENSURE(c, c->ycur, sizeof(double) * (size_t)(N + 1));
+        ENSURE(c, c->flag, sizeof(int));
+    }
     ENSURE(c, c->unit_off, sizeof(long long) * (size_t)(n_units + 1));
     ENSURE(c, c->unit_ids, sizeof(uint64_t) * (size_t)(n_units + 1));
     ENSURE(c, c->tasks, sizeof(Task) * (size_t)cap.task_cap);
@@ -416,6 +425,15 @@ int run_cbs(cbs_gpu_ctx* c, const std::vector<long long>& off, const uint64_t* u
         if (c->jump_ready) { hD.jump_polys = c->jump.as<uint64_t>(); hD.span_max = (long long)mtjump::NSEG * mtjump::SEG; }
     }
     hD.profile = c->counting ? 1 : 0;
+    if (weighted) {
+        hD.w = c->wts.as<double>(); hD.rw = c->rw.as<double>(); hD.cw = c->cw.as<double>(); hD.ycur = c->ycur.as<double>();
+        CUDA_TRY(c, cudaMemsetAsync(c->flag.p, 0, sizeof(int), st));
+        if (N) { k_wsetup<<<std::min<long long>((N + 255) / 256, c->sm_count * 8), 256, 0, st>>>(hD.w, hD.rw, N, c->flag.as<int>()); c->launches++; }
+        int bad = 0;
+        CUDA_TRY(c, cudaMemcpyAsync(&bad, c->flag.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(c, cudaStreamSynchronize(st));
+        if (bad) return fail(c, CBS_GPU_ERR_INVALID, "weights must be finite and positive");
+    }
     // permutations a shared-memory shuffle class holds on the GPU at once (the scheduler spills oversized batches of the
     // classes with few resident permutations to the L2 shuffle)
     for (int cls = 0; cls < SHUF_NCLS; ++cls) hD.shuf_cap[cls] = 0;
@@ -451,6 +469,7 @@ int run_cbs(cbs_gpu_ctx* c, const std::vector<long long>& off, const uint64_t* u
     int scan_occ = 1;
     if (!pick_scan_warps(c, lay, &scan_occ)) return fail(c, CBS_GPU_ERR_UNSUPPORTED, "segment too long for the scan kernel's shared memory");
     const size_t scan_smem = lay.bytes();
+    const size_t wscan_smem = ((sizeof(WScanSmem) + 15) & ~(size_t)15) + (size_t)lay.nb_max * (2 * sizeof(double) + 3 * sizeof(int)) + 16;
     const int scan_grid = c->sm_count * scan_occ;
 
     // shared-memory shuffle kernel, one launch per segment-length class present in this call
@@ -482,11 +501,11 @@ int run_cbs(cbs_gpu_ctx* c, const std::vector<long long>& off, const uint64_t* u
             { LaunchTimer t(c, K_SCHED); k_sched<<<1, 256, 0, st>>>(dD, c->d_done); }
             cudaEventRecord(c->ev_sched, st);
             cudaStreamWaitEvent(c->side[0], c->ev_sched, 0);
-            { LaunchTimer t(c, K_PREP, c->side[0]); k_tables<<<dim3(16, 64), 256, 0, c->side[0]>>>(dD); k_prep<<<c->sm_count * 8, 32, 0, c->side[0]>>>(dD); c->launches++; }
+            { LaunchTimer t(c, K_PREP, c->side[0]); k_tables<<<dim3(16, 64), 256, 0, c->side[0]>>>(dD); if (weighted) k_wprep<<<c->sm_count * 8, 32, 0, c->side[0]>>>(dD); else k_prep<<<c->sm_count * 8, 32, 0, c->side[0]>>>(dD); c->launches++; }
             cudaEventRecord(c->ev_side[0], c->side[0]);
             cudaStreamWaitEvent(c->side[1], c->ev_sched, 0);
-            { LaunchTimer t(c, K_EDGEPREP, c->side[1]); k_edgeprep<<<c->sm_count * 4, 32, 0, c->side[1]>>>(dD); }
-            { LaunchTimer t(c, K_EDGEPERM, c->side[1]); k_edgeperm<<<c->sm_count * 4, 128, 0, c->side[1]>>>(dD); }
+            { LaunchTimer t(c, K_EDGEPREP, c->side[1]); if (weighted) k_wedgeprep<<<c->sm_count * 4, 32, 0, c->side[1]>>>(dD); else k_edgeprep<<<c->sm_count * 4, 32, 0, c->side[1]>>>(dD); }
+            { LaunchTimer t(c, K_EDGEPERM, c->side[1]); if (weighted) k_wedgeperm<<<c->sm_count * 4, 128, 0, c->side[1]>>>(dD); else k_edgeperm<<<c->sm_count * 4, 128, 0, c->side[1]>>>(dD); }
             cudaEventRecord(c->ev_side[1], c->side[1]);
             if (mt) {
                 LaunchTimer t(c, K_GEN);
@@ -529,7 +548,9 @@ int run_cbs(cbs_gpu_ctx* c, const std::vector<long long>& off, const uint64_t* u
             for (int k = 2; k < 5; ++k) if (used_side[k]) { cudaEventRecord(c->ev_side[k], c->side[k]); cudaStreamWaitEvent(st, c->ev_side[k], 0); }
             { LaunchTimer t(c, K_PREFIX); k_chain<<<c->sm_count * 12, CHAIN_WARPS * 32, 0, st>>>(dD); }
             cudaStreamWaitEvent(st, c->ev_side[0], 0);
-            { LaunchTimer t(c, K_SCAN); k_scan<<<scan_grid, lay.warps * 32, scan_smem, st>>>(dD, lay); }
+            { LaunchTimer t(c, K_SCAN);
+              if (weighted) k_wscan<<<c->sm_count * 4, 256, wscan_smem, st>>>(dD, lay.nb_max);
+              else k_scan<<<scan_grid, lay.warps * 32, scan_smem, st>>>(dD, lay); }
             if (p->hybrid) {
                 k_hscan<<<c->sm_count * 4, 256, 0, st>>>(dD);
                 k_tailp_terms<<<c->sm_count * 8, 128, 0, st>>>(dD, c->tailp.as<double>());
@@ -573,7 +594,8 @@ int run_cbs(cbs_gpu_ctx* c, const std::vector<long long>& off, const uint64_t* u
     }
     if (hD.n_segs > 0) {
         LaunchTimer t(c, K_MEANS);
-        k_means<<<std::min(hD.n_segs, c->sm_count * 8), 32, 0, st>>>(dD, c->means.as<double>());
+        if (weighted) k_wmeans<<<std::min(hD.n_segs, c->sm_count * 8), 32, 0, st>>>(dD, c->means.as<double>());
+        else k_means<<<std::min(hD.n_segs, c->sm_count * 8), 32, 0, st>>>(dD, c->means.as<double>());
     }
     CUDA_TRY(c, cudaGetLastError());
     return CBS_GPU_OK;
@@ -589,7 +611,7 @@ struct ResultOwner {
 };
 
 int fetch_results(cbs_gpu_ctx* c, const Dev& hD, int n_units, bool want_splits, ResultOwner* R, const cbs_gpu_params* prm = nullptr,
-                  const std::vector<long long>* unit_off = nullptr) {
+                  const std::vector<long long>* unit_off = nullptr, bool weighted = false) {
     cudaStream_t st = c->stream;
     const int ns = hD.n_segs;
     std::vector<SegRec> segs((size_t)ns);
@@ -628,6 +650,8 @@ int fetch_results(cbs_gpu_ctx* c, const Dev& hD, int n_units, bool want_splits, 
         const long long N = (*unit_off)[n_units];
         std::vector<double> hx((size_t)N);
         if (N) CUDA_TRY(c, cudaMemcpy(hx.data(), c->x.p, sizeof(double) * (size_t)N, cudaMemcpyDeviceToHost));
+        std::vector<double> hw;
+        if (weighted && N) { hw.resize((size_t)N); CUDA_TRY(c, cudaMemcpy(hw.data(), c->wts.p, sizeof(double) * (size_t)N, cudaMemcpyDeviceToHost)); }
         std::vector<int64_t> noff((size_t)n_units + 1, 0);
         std::vector<int32_t> nlen;
         std::vector<double> nmean;
@@ -638,10 +662,17 @@ int fetch_results(cbs_gpu_ctx* c, const Dev& hD, int n_units, bool want_splits, 
             if (lseg.size() > 1) lseg = prune_lengths(xu, n, lseg, prm->undo_prune_cutoff);
             int pos = 0;
             for (int len : lseg) {
-                double acc = 0.0;
-                for (int i = pos; i < pos + len; ++i) acc += xu[i];
                 nlen.push_back(len);
-                nmean.push_back(acc / (double)len);
+                if (weighted) {  // CBS.cpp:1091-1097 (prune_segments itself is unweighted in the reference, :1089)
+                    const double* wu = hw.data() + (*unit_off)[u];
+                    double sw = 0.0, swx = 0.0;
+                    for (int i = pos; i < pos + len; ++i) { sw += wu[i]; swx += wu[i] * xu[i]; }
+                    nmean.push_back(swx / sw);
+                } else {
+                    double acc = 0.0;
+                    for (int i = pos; i < pos + len; ++i) acc += xu[i];
+                    nmean.push_back(acc / (double)len);
+                }
                 pos += len;
             }
             noff[u + 1] = (int64_t)nlen.size();
@@ -757,7 +788,8 @@ void cbs_gpu_destroy(cbs_gpu_ctx* c) {
                       &c->act1, &c->chains, &c->segs, &c->splits, &c->udraws, &c->arena, &c->rej, &c->draws0, &c->draws1,
                       &c->prep_task, &c->items, &c->item_prefix, &c->edgeprep_task, &c->edges, &c->edge_prefix, &c->gen_chain,
                       &c->means, &c->seed312, &c->dev, &c->staging, &c->fv, &c->fidx, &c->flab, &c->lab, &c->diffs,
-                      &c->diffs_sorted, &c->gout, &c->cubtmp, &c->flag, &c->goff, &c->stream_buf, &c->shuf, &c->jump, &c->tailp};
+                      &c->diffs_sorted, &c->gout, &c->cubtmp, &c->flag, &c->goff, &c->stream_buf, &c->shuf, &c->jump, &c->tailp,
+                      &c->wts, &c->rw, &c->cw, &c->ycur};
     for (DevBuf* b : bufs) if (b->p) cudaFree(b->p);
     if (c->h_stage) cudaFreeHost(c->h_stage);
     if (c->h_done) cudaFreeHost(c->h_done);
@@ -1088,6 +1120,102 @@ int cbs_gpu_segment_batch(cbs_gpu_ctx* c, const void* values, int dtype, int mem
     R->pub.n_splits = (int64_t)R->splits.size();
     R->pub.splits = R->splits.empty() ? nullptr : R->splits.data();
     *out = &R->pub;
+    return CBS_GPU_OK;
+}
+
+// cbs::segment_weighted (CBS.cpp:1026-1099) for every unit; values and weights: float64, laid out alike
+int cbs_gpu_segment_weighted_batch(cbs_gpu_ctx* c, const double* values, const double* weights, int memspace,
+                                   const int64_t* unit_offsets, const uint64_t* unit_ids, int32_t n_units,
+                                   const cbs_gpu_params* params, cbs_gpu_result** out) {
+    if (!c) return CBS_GPU_ERR_INVALID;
+    if (!out) return fail(c, CBS_GPU_ERR_INVALID, "out is NULL");
+    *out = nullptr;
+    if (!params || !unit_offsets || n_units < 0) return fail(c, CBS_GPU_ERR_INVALID, "bad arguments");
+    if (cudaSetDevice(c->device) != cudaSuccess) return fail(c, CBS_GPU_ERR_CUDA, "cudaSetDevice failed");
+    cbs_gpu_params p = *params;
+    p.do_smooth = 0;  // cbs::segment_weighted does not smooth
+    int rc = validate_params(c, &p);
+    if (rc) return rc;
+    std::vector<long long> off((size_t)n_units + 1);
+    for (int u = 0; u <= n_units; ++u) off[u] = unit_offsets[u];
+    if (off[0] != 0) return fail(c, CBS_GPU_ERR_INVALID, "unit_offsets[0] must be 0");
+    for (int u = 0; u < n_units; ++u) if (off[u + 1] < off[u]) return fail(c, CBS_GPU_ERR_INVALID, "unit_offsets must be non-decreasing");
+    const long long N = off[n_units];
+    if (N > 0 && (!values || !weights)) return fail(c, CBS_GPU_ERR_INVALID, "values / weights is NULL");
+    for (int k = 0; k < K_COUNT; ++k) c->kms[k] = 0.0;
+    c->launches = 0;
+    cudaStream_t st = c->stream;
+    ENSURE(c, c->x, sizeof(double) * (size_t)(N + 1));
+    ENSURE(c, c->wts, sizeof(double) * (size_t)(N + 1));
+    ENSURE(c, c->flag, sizeof(int));
+    CUDA_TRY(c, cudaEventRecord(c->e0, st));
+    const cudaMemcpyKind kind = memspace == CBS_GPU_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+    if (N) {
+        CUDA_TRY(c, cudaMemcpyAsync(c->x.p, values, sizeof(double) * (size_t)N, kind, st));
+        CUDA_TRY(c, cudaMemcpyAsync(c->wts.p, weights, sizeof(double) * (size_t)N, kind, st));
+    }
+    CUDA_TRY(c, cudaEventRecord(c->e1, st));
+    CUDA_TRY(c, cudaMemsetAsync(c->flag.p, 0, sizeof(int), st));
+    if (N) { k_count_nonfinite<<<std::min<long long>((N + 255) / 256, c->sm_count * 8), 256, 0, st>>>(c->x.as<double>(), N, c->flag.as<int>()); c->launches++; }
+    int bad = 0;
+    CUDA_TRY(c, cudaMemcpyAsync(&bad, c->flag.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(c, cudaStreamSynchronize(st));
+    if (bad) return fail(c, CBS_GPU_ERR_NONFINITE, "non-finite values reach CBS");
+    CUDA_TRY(c, cudaEventRecord(c->e2, st));
+    Dev hD;
+    rc = run_cbs(c, off, unit_ids, n_units, &p, nullptr, true, hD);
+    if (rc) return rc;
+    CUDA_TRY(c, cudaEventRecord(c->e3, st));
+    ResultOwner* R = new ResultOwner();
+    memset(&R->pub, 0, sizeof(R->pub));
+    rc = fetch_results(c, hD, n_units, p.record_splits != 0, R, &p, &off, true);
+    if (rc) { delete R; return rc; }
+    CUDA_TRY(c, cudaEventRecord(c->e4, st));
+    CUDA_TRY(c, cudaEventSynchronize(c->e4));
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, c->e0, c->e1); R->pub.ms_h2d = ms;
+    cudaEventElapsedTime(&ms, c->e2, c->e3); R->pub.ms_segment = ms;
+    cudaEventElapsedTime(&ms, c->e3, c->e4); R->pub.ms_d2h = ms;
+    if (c->profiling) collect_timers(c);
+    R->pub.kernel_launches = c->launches;
+    *out = &R->pub;
+    return CBS_GPU_OK;
+}
+
+// cbs::segment_weighted on one vector (CBS.hpp:115-128)
+int cbs_gpu_segment_weighted(cbs_gpu_ctx* c, const double* x, const double* weights, int32_t n, const cbs_gpu_params* params,
+                             const uint64_t* mt_next312, int32_t cap, int32_t* lengths, double* means, int32_t* n_segments,
+                             uint64_t* draws_consumed) {
+    if (!c) return CBS_GPU_ERR_INVALID;
+    if (n < 0 || (n > 0 && (!x || !weights)) || !n_segments || !params) return fail(c, CBS_GPU_ERR_INVALID, "bad arguments");
+    if (cudaSetDevice(c->device) != cudaSuccess) return fail(c, CBS_GPU_ERR_CUDA, "cudaSetDevice failed");
+    cbs_gpu_params p = *params;
+    p.do_smooth = 0;
+    int rc = validate_params(c, &p);
+    if (rc) return rc;
+    *n_segments = 0;
+    if (draws_consumed) *draws_consumed = 0;
+    if (n == 0) return CBS_GPU_OK;
+    for (int i = 0; i < n; ++i) if (!std::isfinite(x[i])) return fail(c, CBS_GPU_ERR_NONFINITE, "non-finite values reach CBS");
+    cudaStream_t st = c->stream;
+    ENSURE(c, c->x, sizeof(double) * (size_t)(n + 1));
+    ENSURE(c, c->wts, sizeof(double) * (size_t)(n + 1));
+    CUDA_TRY(c, cudaMemcpyAsync(c->x.p, x, sizeof(double) * (size_t)n, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(c, cudaMemcpyAsync(c->wts.p, weights, sizeof(double) * (size_t)n, cudaMemcpyHostToDevice, st));
+    std::vector<long long> off = {0, (long long)n};
+    Dev hD;
+    for (int k = 0; k < K_COUNT; ++k) c->kms[k] = 0.0;
+    rc = run_cbs(c, off, nullptr, 1, &p, mt_next312, true, hD);
+    if (rc) return rc;
+    ResultOwner R;
+    memset(&R.pub, 0, sizeof(R.pub));
+    rc = fetch_results(c, hD, 1, false, &R, &p, &off, true);
+    if (rc) return rc;
+    if (c->profiling) collect_timers(c);
+    *n_segments = (int32_t)R.pub.n_segments;
+    if (draws_consumed) *draws_consumed = R.draws[0];
+    if (R.pub.n_segments > cap) return fail(c, CBS_GPU_ERR_CAPACITY, "output capacity too small");
+    for (int64_t k = 0; k < R.pub.n_segments; ++k) { lengths[k] = R.lengths[k]; means[k] = R.means[k]; }
     return CBS_GPU_OK;
 }
 

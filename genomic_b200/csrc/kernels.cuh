@@ -661,6 +661,28 @@ __device__ void perm_warp(Dev* D, const Task& t, int p, Idx s_idx, unsigned char
     // them into prefix sums in place.  (The chain is a separate kernel because it needs no index array: an SM holds
     // only a few index arrays, but dozens of chains.)
     double* sx = D->arena + t.off_sx + (long long)p * Sched::sx_stride(n);
+    if (D->w) {
+        // weighted CBS, wxperm (CBS.cpp:538-547): the Fisher-Yates runs on y = cur*rw and position i-1 receives
+        // y[.]/rw[i-1] at step i -- unless the step drew j == i, in which case the reference's swap restores the
+        // undivided value.  Draw number n-i of the permutation belongs to step i.
+        const double* __restrict__ ycur = D->ycur + base;
+        const double* __restrict__ rw = D->rw + base;
+        for (int k = lane; k < n; k += 32) {
+            const int i = k + 1;
+            uint64_t u;
+            if (mt) u = mt_temper(win[n - i]);
+            else {
+                const uint32_t kd = (uint32_t)(n - i);
+                uint32_t o[4];
+                philox4x32_10(kd >> 1, permno, 0u, 0u, k0, k1, o);
+                u = (kd & 1u) ? (((uint64_t)o[3] << 32) | o[2]) : (((uint64_t)o[1] << 32) | o[0]);
+            }
+            const double y = ycur[s_idx.ld(k)];
+            sx[k + 1] = (draw_index(u, i) == i) ? y : y / rw[k];
+        }
+        __syncwarp();
+        return;
+    }
     int k = lane;
     for (; k + 480 < n; k += 512) {
         int id[16];
@@ -757,11 +779,13 @@ __global__ void __launch_bounds__(CHAIN_WARPS * 32) k_chain(Dev* D) {
         row_stats_init(rst);
         double prev_last = 0.0;  // S[0]
         const double* __restrict__ src = sx + 1;
+        // weighted CBS: the chain adds px*w (wtmaxo, CBS.cpp:623,627); the product is rounded before the addition
+        const double* __restrict__ wt = D->w ? D->w + D->unit_off[t.unit] + t.lo : nullptr;
         if (lane == 0) sx[0] = 0.0;
         double run = 0.0;
         double r[PERM_CHUNK / 32];
 #pragma unroll
-        for (int q = 0; q < PERM_CHUNK / 32; ++q) { const int i = lane + 32 * q; r[q] = (i < n) ? src[i] : 0.0; }
+        for (int q = 0; q < PERM_CHUNK / 32; ++q) { const int i = lane + 32 * q; r[q] = (i < n) ? (wt ? src[i] * wt[i] : src[i]) : 0.0; }
         for (int c0 = 0; c0 < n; c0 += PERM_CHUNK) {
             const int cnt = min(PERM_CHUNK, n - c0);
             __syncwarp();
@@ -770,7 +794,7 @@ __global__ void __launch_bounds__(CHAIN_WARPS * 32) k_chain(Dev* D) {
             __syncwarp();
             if (c0 + PERM_CHUNK < n) {
 #pragma unroll
-                for (int q = 0; q < PERM_CHUNK / 32; ++q) { const int i = c0 + PERM_CHUNK + lane + 32 * q; r[q] = (i < n) ? src[i] : 0.0; }
+                for (int q = 0; q < PERM_CHUNK / 32; ++q) { const int i = c0 + PERM_CHUNK + lane + 32 * q; r[q] = (i < n) ? (wt ? src[i] * wt[i] : src[i]) : 0.0; }
             }
             if (lane == 0) {
                 int kk = 0;

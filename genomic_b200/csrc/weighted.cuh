@@ -1,0 +1,636 @@
+// weighted.cuh -- sm_100a kernels of weighted CBS (cbs::segment_weighted, /root/reference lib/cbs/CBS.cpp:1026-1099).
+//
+// The control flow of wfindcpt (CBS.cpp:894-957) is the one of fndcpt, so the device worklist and its scheduler
+// (cbs_core.h) are shared with the unweighted path; what changes is the arithmetic of every kernel:
+//   k_wsetup   rw = sqrt(w) for the whole call (CBS.cpp:1056), weights validated
+//   k_wprep    per pending segment: all-equal test, weighted mean, centring, weighted tss, cw = cumsum(w)/sqrt(sum w),
+//              prefix sums of cur*w (CBS.cpp:1051-1067, wtmaxo :621-637) -- every sum is ONE sequential chain on lane 0
+//   (shuffle)  perm_warp gathers ycur[idx]/rw[pos] (wxperm, CBS.cpp:538-547, including its j == i quirk)
+//   (k_chain)  multiplies the gathered values by w before the sequential prefix chain (wtmaxo :623,627)
+//   k_wscan    wtmaxo / wtmaxp (CBS.cpp:610-743): CTA per (segment, permutation)
+//   k_wedgeprep, k_wedgeperm   wtpermp (CBS.cpp:549-591)
+//   k_wmeans   weighted segment means (CBS.cpp:1091-1097)
+// The hybrid method (hwtmaxp/getmncwt) is not built: calls that would reach it are rejected by the host.
+#pragma once
+
+namespace cbsg {
+
+__global__ void k_wsetup(const double* __restrict__ w, double* __restrict__ rw, long long N, int* bad) {
+    int b = 0;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < N; i += (long long)gridDim.x * blockDim.x) {
+        const double v = w[i];
+        if (!(v > 0.0) || isinf(v)) b = 1;
+        rw[i] = sqrt(v);
+    }
+    if (b) atomicOr(bad, 1);
+}
+
+// ------------------------------------------------------------------------------------
+// k_wprep: one warp per new pending segment (CBS.cpp:1046-1067 and the prefix sums of wtmaxo :621-637 on observed data)
+// ------------------------------------------------------------------------------------
+#define WPREP_CHUNK 512
+__device__ void wprep_warp(Dev* D, Task& t, int lane, double* bx, double* bw) {
+    const long long base = D->unit_off[t.unit] + t.lo;
+    const double* __restrict__ x = D->x + base;
+    const double* __restrict__ w = D->w + base;
+    const double* __restrict__ rw = D->rw + base;
+    double* cur = D->cur + base;
+    double* cw = D->cw + base;
+    double* ycur = D->ycur + base;
+    const int n = t.n;
+    // CBS.cpp:1051 all-equal test
+    const double x0 = x[0];
+    bool flat = true;
+    for (int i = lane; i < n; i += 32) if (!(fabs(x[i] - x0) < 1e-12)) flat = false;
+    flat = __all_sync(FULL, flat);
+    if (lane == 0) t.alleq = flat ? 1 : 0;
+    if (flat) return;
+    // CBS.cpp:1053-1058: wsum, wxsum (sequential)
+    double wsum = 0.0, wxsum = 0.0;
+    for (int c0 = 0; c0 < n; c0 += WPREP_CHUNK) {
+        const int cnt = min(WPREP_CHUNK, n - c0);
+        __syncwarp();
+        for (int k = lane; k < cnt; k += 32) { bx[k] = x[c0 + k]; bw[k] = w[c0 + k]; }
+        __syncwarp();
+        if (lane == 0)
+            for (int k = 0; k < cnt; ++k) { const double ww = bw[k]; wsum = wsum + ww; wxsum = wxsum + ww * bx[k]; }
+    }
+    wsum = shfl_d(wsum, 0); wxsum = shfl_d(wxsum, 0);
+    const double avg = wxsum / wsum;
+    const double cwscale = sqrt(wsum);
+    // CBS.cpp:1061-1066 centring, weighted tss, cw; wtmaxo :623,627 prefix sums of cur*w
+    double* sx = D->arena + t.off_sx;
+    double wxx = 0.0, csum = 0.0, run = 0.0;
+    if (lane == 0) sx[0] = 0.0;
+    for (int c0 = 0; c0 < n; c0 += WPREP_CHUNK) {
+        const int cnt = min(WPREP_CHUNK, n - c0);
+        __syncwarp();
+        for (int k = lane; k < cnt; k += 32) {
+            const double v = x[c0 + k] - avg;
+            bx[k] = v; bw[k] = w[c0 + k];
+            cur[c0 + k] = v;
+            ycur[c0 + k] = v * rw[c0 + k];
+        }
+        __syncwarp();
+        if (lane == 0)
+            for (int k = 0; k < cnt; ++k) {
+                const double v = bx[k], ww = bw[k];
+                wxx = wxx + ww * v * v;
+                csum = csum + ww;
+                run = run + v * ww;
+                bx[k] = run; bw[k] = csum;
+            }
+        __syncwarp();
+        for (int k = lane; k < cnt; k += 32) { sx[c0 + 1 + k] = bx[k]; cw[c0 + k] = bw[k] / cwscale; }
+    }
+    run = shfl_d(run, 0);
+    for (int k = lane; k < SX_PAD; k += 32) sx[n + 1 + k] = run;
+    if (lane == 0) t.tss = wxx;
+}
+
+__global__ void __launch_bounds__(32) k_wprep(Dev* D) {
+    __shared__ __align__(16) double bx[WPREP_CHUNK];
+    __shared__ __align__(16) double bw[WPREP_CHUNK];
+    if (D->done) return;
+    for (int k = blockIdx.x; k < D->n_prep; k += gridDim.x) wprep_warp(D, D->tasks[D->prep_task[k]], threadIdx.x, bx, bw);
+}
+
+// ------------------------------------------------------------------------------------
+// k_wscan: wtmaxo (observed data: statistic and location) / wtmaxp (permutation: reject decision), CBS.cpp:610-743.
+//
+// The reference lists the block pairs whose bound reaches the statistic of the global-extrema arc (:650-693), visits
+// them by descending corner statistic and scans, per pair, the arcs (i, j) whose weight awt1 = cw[j-1]-cw[i-1] lies in
+// the pair's bands awt1 <= awtmax (:708-719) and awt1 >= psrn-awtmax (:721-733); a pair is skipped when the running
+// maximum exceeds its bound.  The bound is an upper bound of every arc of the pair, so the maximum is the maximum over
+// the arcs of all listed pairs: here the warps of a CTA take the pairs 32 at a time, each lane evaluates the bound of
+// one pair, and the warp scans the pairs that reach the current level (rows of the pair one after the other, the lanes
+// along j; cw is monotone, so a row ends at the first 32 arcs outside the band).  An arc costs two subtractions and
+// three multiplications (s*s > level*den); only a hit divides.  Permutations only need their reject decision: the level
+// starts at the statistic M* a permutation must reach to reject (decision mode, as in k_scan).
+// Location (observed data): ties follow the reference's visiting order -- the global-extrema arc first, then pairs by
+// descending corner statistic, low band (i descending, j ascending) before high band (i ascending, j descending); it is
+// resolved in a second pass over the arcs that attain the maximum.  Pairs with EQUAL corner statistics are ordered by
+// their position in the list (the reference's std::sort order is unspecified there).
+// ------------------------------------------------------------------------------------
+struct WScanSmem {
+    unsigned long long level;  // bit pattern of the prune level (positive doubles order like integers)
+    unsigned long long found;  // bit pattern of the best statistic found
+    double g_min, g_max;
+    int g_imin, g_imax;
+    int next_pair, lock;
+    // location record: best arc among those that attain the maximum
+    double r_corner;
+    int r_q, r_phase, r_o1, r_o2, r_i, r_j, r_set;
+};
+
+struct WRow {
+    int n, nb, al0, nal0;
+    const double* sx;   // prefix sums sx[0..n]
+    const double* cw;   // cw[0..n-1]
+    const int* bb;      // smem bb[0..nb]
+    const double* bmin; const double* bmax; const int* amin; const int* amax;  // smem, per block (0-based)
+    double psrn, psrnov2, init;
+};
+
+struct WPair {
+    int bi, bj, ilo1, ihi, jlo, jhi;
+    double bsslim;   // bound (:676)
+    double awt;      // weight of the corner arc (:683,686)
+    double corner;   // its statistic bssbij (:684,687)
+    bool listed;     // bssmax0 <= bsslim (:677)
+};
+
+__device__ __forceinline__ void wpair_from_index(int q, int nb, int& bi, int& bj) { pair_from_index(q, nb, bi, bj); }
+
+// bound and corner of block pair (bi, bj), 1-based (CBS.cpp:652-689)
+__device__ void wpair_eval(const WRow& r, int bi, int bj, WPair& p) {
+    const double* cw = r.cw;
+    p.bi = bi; p.bj = bj;
+    p.ilo1 = r.bb[bi - 1] + 1; p.ihi = r.bb[bi]; p.jlo = r.bb[bj - 1] + 1; p.jhi = r.bb[bj];
+    const int al0 = r.al0;
+    double awthi = cw[p.jhi - 1] - cw[p.ilo1 - 1];
+    if (p.jhi - p.ilo1 > r.nal0) {
+        awthi = 0.0;
+        for (int kk = 1; kk <= al0; ++kk) awthi = fmax(awthi, cw[r.nal0 + kk - 1] - cw[kk - 1]);
+    }
+    double awtlo;
+    if (bi == bj) {
+        awtlo = cw[min(p.ilo1 + al0, r.n) - 1] - cw[p.ilo1 - 1];
+        for (int kk = p.ilo1 + 1; kk <= p.ihi - al0; ++kk) awtlo = fmin(awtlo, cw[kk + al0 - 1] - cw[kk - 1]);
+    } else if (bi + 1 == bj) {
+        awtlo = cw[p.jlo - 1] - cw[max(p.jlo - al0, 1) - 1];
+        for (int kk = max(p.jlo - al0 + 1, 1); kk <= p.ihi; ++kk) awtlo = fmin(awtlo, cw[min(kk + al0, r.n) - 1] - cw[kk - 1]);
+    } else {
+        awtlo = cw[p.jlo - 1] - cw[p.ihi - 1];
+    }
+    const double sij1 = fabs(r.bmax[bj - 1] - r.bmin[bi - 1]);
+    const double sij2 = fabs(r.bmax[bi - 1] - r.bmin[bj - 1]);
+    const double sijmx0 = fmax(sij1, sij2);
+    p.bsslim = (sijmx0 * sijmx0) / fmin(awtlo * (r.psrn - awtlo), awthi * (r.psrn - awthi));
+    p.listed = r.init <= p.bsslim;
+    if (sij1 > sij2) {
+        p.awt = fabs(cw[r.amax[bj - 1] - 1] - cw[r.amin[bi - 1] - 1]);
+        p.corner = (sij1 * sij1) / (p.awt * (r.psrn - p.awt));
+    } else {
+        p.awt = fabs(cw[r.amin[bj - 1] - 1] - cw[r.amax[bi - 1] - 1]);
+        p.corner = (sij2 * sij2) / (p.awt * (r.psrn - p.awt));
+    }
+}
+
+struct WCand {
+    double corner;
+    int q, phase, o1, o2, i, j;
+    bool set;
+};
+// true if a is visited before b by the reference
+__device__ __forceinline__ bool wcand_before(const WCand& a, const WCand& b) {
+    if (!b.set) return a.set;
+    if (!a.set) return false;
+    if (a.corner != b.corner) return a.corner > b.corner;
+    if (a.q != b.q) return a.q < b.q;
+    if (a.phase != b.phase) return a.phase < b.phase;
+    if (a.o1 != b.o1) return a.o1 < b.o1;
+    return a.o2 < b.o2;
+}
+
+// one warp scans the two bands of a pair (CBS.cpp:700-734).  LOC == false: raise level/found; LOC == true: record the
+// first-visited arc whose statistic equals `target`.
+template <bool LOC>
+__device__ void wscan_pair(const WRow& r, const WPair& p, int q, WScanSmem* sm, double target, WCand& best, int lane) {
+    const double* __restrict__ sx = r.sx;
+    const double* __restrict__ cw = r.cw;
+    const double psrn = r.psrn;
+    double awtmax = p.awt;
+    const double awthi = cw[p.jhi - 1] - cw[p.ilo1 - 1];
+    const double awtlo = (p.bi == p.bj) ? 0.0 : (cw[p.jlo - 1] - cw[p.ihi - 1]);
+    if (awtmax > psrn - awtmax) awtmax = psrn - awtmax;
+    const volatile unsigned long long* vlevel = &sm->level;
+    if (awtlo <= r.psrnov2) {
+        const int ihi1 = (p.bi == p.bj) ? p.ihi - r.al0 : p.ihi;
+        for (int i = ihi1; i >= p.ilo1; --i) {
+            const double sxi = sx[i], cwi = cw[i - 1];
+            const double lvl = LOC ? target * (1.0 - 1e-12) : __longlong_as_double((long long)*vlevel) * (1.0 - 1e-12);
+            const int jlo1 = max(i + r.al0, p.jlo);
+            for (int j0 = jlo1; j0 <= p.jhi; j0 += 32) {
+                const int j = j0 + lane;
+                bool in = false;
+                if (j <= p.jhi) {
+                    const double a1 = cw[j - 1] - cwi;
+                    in = a1 <= awtmax;
+                    if (in) {
+                        const double d = sx[j] - sxi;
+                        const double d2 = d * d, den = a1 * (psrn - a1);
+                        if (d2 > lvl * den) {
+                            const double v = d2 / den;
+                            if (LOC) {
+                                if (v == target) {
+                                    WCand c{p.corner, q, 0, ihi1 - i, j, i, j, true};
+                                    if (wcand_before(c, best)) best = c;
+                                }
+                            } else if (v > __longlong_as_double((long long)*vlevel)) {
+                                atomicMax(&sm->found, (unsigned long long)__double_as_longlong(v));
+                                atomicMax(&sm->level, (unsigned long long)__double_as_longlong(v));
+                            }
+                        }
+                    }
+                }
+                if (!__any_sync(FULL, in)) break;
+            }
+        }
+    }
+    awtmax = psrn - awtmax;
+    if (awthi >= r.psrnov2) {
+        const bool wrap = (p.bi == 1) && (p.bj == r.nb);
+        for (int i = p.ilo1; i <= p.ihi; ++i) {
+            const double sxi = sx[i], cwi = cw[i - 1];
+            const double lvl = LOC ? target * (1.0 - 1e-12) : __longlong_as_double((long long)*vlevel) * (1.0 - 1e-12);
+            const int jhi1 = wrap ? min(p.jhi, p.jhi - r.al0 + i) : p.jhi;
+            for (int j0 = jhi1; j0 >= p.jlo; j0 -= 32) {
+                const int j = j0 - lane;
+                bool in = false;
+                if (j >= p.jlo) {
+                    const double a1 = cw[j - 1] - cwi;
+                    in = a1 >= awtmax;
+                    if (in) {
+                        const double d = sx[j] - sxi;
+                        const double d2 = d * d, den = a1 * (psrn - a1);
+                        if (d2 > lvl * den) {
+                            const double v = d2 / den;
+                            if (LOC) {
+                                if (v == target) {
+                                    WCand c{p.corner, q, 1, i - p.ilo1, -j, i, j, true};
+                                    if (wcand_before(c, best)) best = c;
+                                }
+                            } else if (v > __longlong_as_double((long long)*vlevel)) {
+                                atomicMax(&sm->found, (unsigned long long)__double_as_longlong(v));
+                                atomicMax(&sm->level, (unsigned long long)__double_as_longlong(v));
+                            }
+                        }
+                    }
+                }
+                if (!__any_sync(FULL, in)) break;
+            }
+        }
+    }
+}
+
+// all warps of the CTA walk the pair list once
+template <bool LOC>
+__device__ void wscan_pass(const WRow& r, WScanSmem* sm, double target, int lane) {
+    const int npairs = r.nb * (r.nb + 1) / 2;
+    WCand best;
+    best.set = false; best.corner = 0.0; best.q = 0; best.phase = 0; best.o1 = 0; best.o2 = 0; best.i = 0; best.j = 0;
+    for (;;) {
+        int q0 = 0;
+        if (lane == 0) q0 = atomicAdd(&sm->next_pair, 32);
+        q0 = __shfl_sync(FULL, q0, 0);
+        if (q0 >= npairs) break;
+        const int q = q0 + lane;
+        WPair p;
+        bool alive = false;
+        if (q < npairs) {
+            int bi, bj;
+            wpair_from_index(q, r.nb, bi, bj);
+            wpair_eval(r, bi, bj, p);
+            const double lvl = LOC ? target : __longlong_as_double((long long)*((volatile unsigned long long*)&sm->level));
+            alive = p.listed && !(p.bsslim * (1.0 + 1e-12) < lvl);
+        }
+        unsigned mask = __ballot_sync(FULL, alive);
+        while (mask) {
+            const int src = __ffs(mask) - 1;
+            mask &= mask - 1;
+            WPair s;
+            s.bi = __shfl_sync(FULL, p.bi, src); s.bj = __shfl_sync(FULL, p.bj, src);
+            s.ilo1 = __shfl_sync(FULL, p.ilo1, src); s.ihi = __shfl_sync(FULL, p.ihi, src);
+            s.jlo = __shfl_sync(FULL, p.jlo, src); s.jhi = __shfl_sync(FULL, p.jhi, src);
+            s.bsslim = shfl_d(p.bsslim, src); s.awt = shfl_d(p.awt, src); s.corner = shfl_d(p.corner, src);
+            s.listed = true;
+            if (!LOC) {  // the level may have risen since the bound was evaluated (read once per warp: uniform branch)
+                double lvl = 0.0;
+                if (lane == 0) lvl = __longlong_as_double((long long)*((volatile unsigned long long*)&sm->level));
+                lvl = shfl_d(lvl, 0);
+                if (s.bsslim * (1.0 + 1e-12) < lvl) continue;
+            }
+            wscan_pair<LOC>(r, s, q0 + src, sm, target, best, lane);
+        }
+    }
+    if (LOC) {
+        // warp reduction of the first-visited arc, then merge into the CTA's record under a lock
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            WCand c;
+            c.corner = shfl_d(best.corner, lane ^ o);
+            c.q = __shfl_xor_sync(FULL, best.q, o); c.phase = __shfl_xor_sync(FULL, best.phase, o);
+            c.o1 = __shfl_xor_sync(FULL, best.o1, o); c.o2 = __shfl_xor_sync(FULL, best.o2, o);
+            c.i = __shfl_xor_sync(FULL, best.i, o); c.j = __shfl_xor_sync(FULL, best.j, o);
+            c.set = __shfl_xor_sync(FULL, best.set ? 1 : 0, o) != 0;
+            if (wcand_before(c, best)) best = c;
+        }
+        if (lane == 0 && best.set) {
+            while (atomicCAS(&sm->lock, 0, 1) != 0) {}
+            __threadfence_block();
+            WCand cur{sm->r_corner, sm->r_q, sm->r_phase, sm->r_o1, sm->r_o2, sm->r_i, sm->r_j, sm->r_set != 0};
+            if (wcand_before(best, cur)) {
+                sm->r_corner = best.corner; sm->r_q = best.q; sm->r_phase = best.phase; sm->r_o1 = best.o1; sm->r_o2 = best.o2;
+                sm->r_i = best.i; sm->r_j = best.j; sm->r_set = 1;
+            }
+            __threadfence_block();
+            atomicExch(&sm->lock, 0);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) k_wscan(Dev* D, int nb_max) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    if (D->done) return;
+    WScanSmem* sm = (WScanSmem*)smem_raw;
+    double* s_bmin = (double*)(smem_raw + ((sizeof(WScanSmem) + 15) & ~(size_t)15));
+    double* s_bmax = s_bmin + nb_max;
+    int* s_amin = (int*)(s_bmax + nb_max);
+    int* s_amax = s_amin + nb_max;
+    int* s_bb = s_amax + nb_max;
+    __shared__ int s_g;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int nwarps = blockDim.x >> 5;
+    const int total = D->item_prefix[D->n_items];
+    for (;;) {
+        __syncthreads();
+        if (tid == 0) s_g = (int)atomicAdd(&D->ctr[1], 1u);
+        __syncthreads();
+        const int gidx = s_g;
+        if (gidx >= total) break;
+        const int k = find_item(D->item_prefix, D->n_items, gidx);
+        const PermItem it = D->items[k];
+        Task& t = D->tasks[it.task];
+        if (it.obs && t.alleq) continue;
+        const int p = gidx - D->item_prefix[k];
+        const int n = t.n, nb = t.nb;
+        const long long base = D->unit_off[t.unit] + t.lo;
+        WRow r;
+        r.n = n; r.nb = nb; r.al0 = D->prm.min_width; r.nal0 = n - r.al0;
+        r.sx = D->arena + t.off_sx + (long long)p * Sched::sx_stride(n);
+        r.cw = D->cw + base;
+        r.bb = s_bb; r.bmin = s_bmin; r.bmax = s_bmax; r.amin = s_amin; r.amax = s_amax;
+        const int* bbg = D->bbtab + base;
+        for (int b = tid; b <= nb; b += blockDim.x) s_bb[b] = bbg[b];
+        __syncthreads();
+        // per-block extrema of the prefix sums with their FIRST occurrence (CBS.cpp:624-633): a warp per block
+        for (int b = warp; b < nb; b += nwarps) {
+            const int first = s_bb[b] + 1, last = s_bb[b + 1];
+            double lo = __longlong_as_double(0x7ff0000000000000LL), hi = -lo;
+            int ilo = 0x7fffffff, ihi = 0x7fffffff;
+            for (int i = first + lane; i <= last; i += 32) {
+                const double v = r.sx[i];
+                if (v < lo) { lo = v; ilo = i; }
+                if (v > hi) { hi = v; ihi = i; }
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                const double olo = shfl_d(lo, lane ^ o), ohi = shfl_d(hi, lane ^ o);
+                const int oilo = __shfl_xor_sync(FULL, ilo, o), oihi = __shfl_xor_sync(FULL, ihi, o);
+                if (olo < lo || (olo == lo && oilo < ilo)) { lo = olo; ilo = oilo; }
+                if (ohi > hi || (ohi == hi && oihi < ihi)) { hi = ohi; ihi = oihi; }
+            }
+            if (lane == 0) { s_bmin[b] = lo; s_bmax[b] = hi; s_amin[b] = ilo; s_amax[b] = ihi; }
+        }
+        __syncthreads();
+        // global extrema: first block that attains them, only if below / above 0.0 (CBS.cpp:619-620, 634-635)
+        if (warp == 0) {
+            double lo = __longlong_as_double(0x7ff0000000000000LL), hi = -lo;
+            int blo = 0x7fffffff, bhi = 0x7fffffff;
+            for (int b = lane; b < nb; b += 32) {
+                if (s_bmin[b] < lo) { lo = s_bmin[b]; blo = b; }
+                if (s_bmax[b] > hi) { hi = s_bmax[b]; bhi = b; }
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                const double olo = shfl_d(lo, lane ^ o), ohi = shfl_d(hi, lane ^ o);
+                const int oblo = __shfl_xor_sync(FULL, blo, o), obhi = __shfl_xor_sync(FULL, bhi, o);
+                if (olo < lo || (olo == lo && oblo < blo)) { lo = olo; blo = oblo; }
+                if (ohi > hi || (ohi == hi && obhi < bhi)) { hi = ohi; bhi = obhi; }
+            }
+            if (lane == 0) {
+                const bool below = lo < 0.0, above = hi > 0.0;
+                sm->g_min = below ? lo : 0.0; sm->g_imin = below ? s_amin[blo] : n;
+                sm->g_max = above ? hi : 0.0; sm->g_imax = above ? s_amax[bhi] : n;
+            }
+        }
+        __syncthreads();
+        const double psdiff = sm->g_max - sm->g_min;
+        const int gimin = sm->g_imin, gimax = sm->g_imax;
+        int fi = min(gimax, gimin), fj = max(gimax, gimin);
+        const double rn = (double)n;
+        const double tss0 = it.obs ? t.tss : 0.0;  // wtmaxp passes tss = 0.0 (CBS.cpp:741-743): mirrored, not "fixed"
+        double best = 0.0;
+        if (psdiff > 0.0) {  // else CBS.cpp:642-645
+            r.psrn = r.cw[n - 1];
+            r.psrnov2 = r.psrn / 2.0;
+            const double psrj = fabs(r.cw[gimax - 1] - r.cw[gimin - 1]);
+            r.init = (psdiff * psdiff) / (psrj * (r.psrn - psrj));  // :649
+            __syncthreads();
+            if (tid == 0) {
+                double level = r.init;
+                if (it.obs == 0) {
+                    // decision mode: reject <=> thresh <= f(M), f(M) = M/(((M+1)-M)/(n-2)) ~ M(n-2) (tss = 0 makes the
+                    // reference replace tss by M+1); M* sits 1e-9 below the solution, f(M*) < thresh is verified
+                    const double thresh = t.ostat * 0.99999;
+                    const double mstar = thresh / (rn - 2.0) * (1.0 - 1e-9);
+                    if (mstar > level) {
+                        const double f = mstar / (((mstar + 1.0) - mstar) / (rn - 2.0));
+                        if (f < thresh) level = mstar;
+                    }
+                }
+                sm->level = (unsigned long long)__double_as_longlong(level);
+                sm->found = (unsigned long long)__double_as_longlong(r.init);
+                sm->next_pair = 0; sm->lock = 0; sm->r_set = 0;
+                sm->r_corner = 0.0; sm->r_q = 0; sm->r_phase = 0; sm->r_o1 = 0; sm->r_o2 = 0; sm->r_i = 0; sm->r_j = 0;
+            }
+            __syncthreads();
+            wscan_pass<false>(r, sm, 0.0, lane);
+            __syncthreads();
+            best = __longlong_as_double((long long)sm->found);
+            if (it.obs == 1 && best > r.init) {
+                __syncthreads();
+                if (tid == 0) sm->next_pair = 0;
+                __syncthreads();
+                wscan_pass<true>(r, sm, best, lane);
+                __syncthreads();
+                if (sm->r_set) { fi = sm->r_i; fj = sm->r_j; }
+            }
+        }
+        if (tid == 0) {
+            double tss = tss0;
+            if (tss <= best + 0.0001) tss = best + 1.0;  // CBS.cpp:643,737
+            const double stat = best / ((tss - best) / (rn - 2.0));
+            if (it.obs == 1) { t.ostat = stat; t.tmaxi = fi; t.tmaxj = fj; }
+            else if (it.obs == 2) { t.ostat = stat; }
+            else D->rej[t.off_rej + p] = (t.ostat * 0.99999 <= stat) ? 1 : 0;  // CBS.cpp:900,933
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------
+// wtpermp (CBS.cpp:549-591)
+// ------------------------------------------------------------------------------------
+__device__ void wedgeprep_warp(Dev* D, Task& t, int s, int lane, double* bx, double* bw) {
+    const int n1 = t.e_n1[s], n2 = t.e_n2[s], n = n1 + n2;
+    const long long base = D->unit_off[t.unit] + t.lo + t.e_off[s];
+    const double* __restrict__ x = D->cur + base;
+    const double* __restrict__ w = D->w + base;
+    if (n1 == 1 || n2 == 1) { if (lane == 0) { t.e_status[s] = 1; t.e_m1[s] = 0; t.e_nrej[s] = 0; } return; }
+    double xsum1 = 0.0, xsum2 = 0.0, tss = 0.0, rn1 = 0.0, rn2 = 0.0;  // :553-565, one chain across both sides for tss
+    for (int c0 = 0; c0 < n; c0 += WPREP_CHUNK) {
+        const int cnt = min(WPREP_CHUNK, n - c0);
+        __syncwarp();
+        for (int k = lane; k < cnt; k += 32) { bx[k] = x[c0 + k]; bw[k] = w[c0 + k]; }
+        __syncwarp();
+        if (lane == 0)
+            for (int k = 0; k < cnt; ++k) {
+                const double v = bx[k], ww = bw[k];
+                if (c0 + k < n1) { xsum1 = xsum1 + ww * v; tss = tss + ww * v * v; rn1 = rn1 + ww; }
+                else { xsum2 = xsum2 + ww * v; tss = tss + ww * v * v; rn2 = rn2 + ww; }
+            }
+    }
+    if (lane == 0) {
+        t.e_nrej[s] = 0;
+        const double rn = rn1 + rn2;
+        const double xbar = (xsum1 + xsum2) / rn;
+        tss -= rn * (xbar * xbar);
+        int m1; double rm1, ostat, tstat;
+        if (n1 <= n2) { m1 = n1; rm1 = rn1; ostat = 0.99999 * fabs(xsum1 / rn1 - xbar); tstat = (ostat * ostat) * rn1 * rn / rn2; }
+        else          { m1 = n2; rm1 = rn2; ostat = 0.99999 * fabs(xsum2 / rn2 - xbar); tstat = (ostat * ostat) * rn2 * rn / rn1; }
+        tstat /= ((tss - tstat) / ((double)n - 2.0));
+        t.e_m1[s] = m1; t.e_rm1[s] = rm1; t.e_ostat[s] = ostat; t.e_xbar[s] = xbar;
+        t.e_status[s] = (tstat > 25.0 && m1 >= 10) ? 2 : 0;
+    }
+}
+
+__global__ void __launch_bounds__(32) k_wedgeprep(Dev* D) {
+    __shared__ __align__(16) double bx[WPREP_CHUNK];
+    __shared__ __align__(16) double bw[WPREP_CHUNK];
+    if (D->done) return;
+    for (int k = blockIdx.x; k < 2 * D->n_edgeprep; k += gridDim.x)
+        wedgeprep_warp(D, D->tasks[D->edgeprep_task[k >> 1]], k & 1, threadIdx.x, bx, bw);
+}
+
+// value at position k before any swap (CBS.cpp:574-575): x*rw on the left side, x on the right
+__device__ __forceinline__ double wedge_src(const double* x, const double* rw, int n1, int k) {
+    return (k < n1) ? x[k] * rw[k] : x[k];
+}
+
+// m1 <= 64: override list in local memory (see edge_sparse_thread)
+__device__ int wedge_sparse_thread(const Dev& D, const Task& t, const EdgeItem& e, int r) {
+    const int s = e.side, m1 = t.e_m1[s], n1 = t.e_n1[s], n = n1 + t.e_n2[s];
+    const long long base = D.unit_off[t.unit] + t.lo + t.e_off[s];
+    const double* x = D.cur + base;
+    const double* rw = D.rw + base;
+    DrawSrc src;
+    edge_draw_src(D, t, e, r, src);
+    int okey[64];
+    double oval[64];
+    int cnt = 0;
+    double acc = 0.0;
+    uint32_t kd = 0;
+    for (int i = n; i >= n - m1 + 1; --i) {
+        const int j = draw_index(src.u64(kd++), i);
+        double vi = wedge_src(x, rw, n1, i - 1);
+        for (int q = 0; q < cnt; ++q) if (okey[q] == i - 1) vi = oval[q];
+        double vj;
+        int slot = -1;
+        if (j == i) vj = vi;
+        else {
+            vj = wedge_src(x, rw, n1, j - 1);
+            for (int q = 0; q < cnt; ++q) if (okey[q] == j - 1) { vj = oval[q]; slot = q; }
+            if (slot < 0) { slot = cnt++; okey[slot] = j - 1; }
+            oval[slot] = vi;
+        }
+        acc += vj * rw[i - 1];  // :580
+    }
+    const double pstat = fabs(acc / t.e_rm1[s] - t.e_xbar[s]);
+    return t.e_ostat[s] <= pstat ? 1 : 0;
+}
+
+// general case: scratch column with undo (see edge_general_thread)
+__device__ int wedge_general_thread(const Dev& D, const Task& t, const EdgeItem& e, int c) {
+    const int s = e.side, m1 = t.e_m1[s], n1 = t.e_n1[s], n = n1 + t.e_n2[s];
+    const long long base = D.unit_off[t.unit] + t.lo + t.e_off[s];
+    const double* x = D.cur + base;
+    const double* rw = D.rw + base;
+    double* A = D.arena + e.off_scratch;
+    const long long C = e.cols;
+    for (int k = 0; k < n; ++k) A[(long long)k * C + c] = wedge_src(x, rw, n1, k);
+    int rejections = 0;
+    for (int q = 0; q < e.Q; ++q) {
+        const int r = c + q * e.cols;
+        if (r >= e.P) break;
+        DrawSrc src;
+        edge_draw_src(D, t, e, r, src);
+        double acc = 0.0;
+        uint32_t kd = 0;
+        for (int i = n; i >= n - m1 + 1; --i) {
+            const int j = draw_index(src.u64(kd++), i);
+            const double a = A[(long long)(i - 1) * C + c], b = A[(long long)(j - 1) * C + c];
+            A[(long long)(i - 1) * C + c] = b;
+            A[(long long)(j - 1) * C + c] = a;
+            acc += b * rw[i - 1];
+        }
+        const double pstat = fabs(acc / t.e_rm1[s] - t.e_xbar[s]);
+        if (t.e_ostat[s] <= pstat) ++rejections;
+        if (q + 1 < e.Q && r + e.cols < e.P) {
+            for (int i = n - m1 + 1; i <= n; ++i) {  // undo, last swap first
+                const int j = draw_index(src.u64((uint32_t)(n - i)), i);
+                const double a = A[(long long)(i - 1) * C + c], b = A[(long long)(j - 1) * C + c];
+                A[(long long)(i - 1) * C + c] = b;
+                A[(long long)(j - 1) * C + c] = a;
+            }
+        }
+    }
+    return rejections;
+}
+
+__global__ void __launch_bounds__(128) k_wedgeperm(Dev* D) {
+    if (D->done) return;
+    __shared__ int s_base;
+    const int total = D->edge_prefix[D->n_edge];
+    for (;;) {
+        __syncthreads();
+        if (threadIdx.x == 0) s_base = (int)atomicAdd(&D->ctr[2], (unsigned)blockDim.x);
+        __syncthreads();
+        const int g = s_base + threadIdx.x;
+        if (s_base >= total) break;
+        if (g >= total) continue;
+        const int k = find_item(D->edge_prefix, D->n_edge, g);
+        const EdgeItem e = D->edges[k];
+        Task& t = D->tasks[e.task];
+        const int th = g - D->edge_prefix[k];
+        const int r = e.sparse ? wedge_sparse_thread(*D, t, e, th) : wedge_general_thread(*D, t, e, th);
+        if (r) atomicAdd(&t.e_nrej[e.side], r);
+    }
+}
+
+// weighted mean of every final segment (CBS.cpp:1091-1097), sequential sums
+__global__ void __launch_bounds__(32) k_wmeans(const Dev* D, double* means) {
+    __shared__ __align__(16) double bx[WPREP_CHUNK];
+    __shared__ __align__(16) double bw[WPREP_CHUNK];
+    const int lane = threadIdx.x;
+    for (int k = blockIdx.x; k < D->n_segs; k += gridDim.x) {
+        const SegRec sg = D->segs[k];
+        const long long base = D->unit_off[sg.unit] + sg.lo;
+        const double* __restrict__ x = D->x + base;
+        const double* __restrict__ w = D->w + base;
+        const int n = sg.hi - sg.lo;
+        double sw = 0.0, swx = 0.0;
+        for (int c0 = 0; c0 < n; c0 += WPREP_CHUNK) {
+            const int cnt = min(WPREP_CHUNK, n - c0);
+            __syncwarp();
+            for (int q = lane; q < cnt; q += 32) { bx[q] = x[c0 + q]; bw[q] = w[c0 + q]; }
+            __syncwarp();
+            if (lane == 0)
+                for (int q = 0; q < cnt; ++q) { sw = sw + bw[q]; swx = swx + bw[q] * bx[q]; }
+        }
+        if (lane == 0) means[k] = swx / sw;
+        __syncwarp();
+    }
+}
+
+}  // namespace cbsg

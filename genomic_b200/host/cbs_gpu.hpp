@@ -149,6 +149,31 @@ inline SegmentationResult segment(const std::vector<double>& x, bool ibin, doubl
     return r;
 }
 
+// cbs::segment_weighted, CBS.hpp:115-128 (CBS.cpp:1026-1099).  Same conventions as segment(); the weighted hybrid
+// method (hwtmaxp) is not built, so hybrid = true is only accepted while x.size() <= nmin.
+inline SegmentationResult segment_weighted(const std::vector<double>& x, const std::vector<double>& weights, double alpha,
+                                           int nperm, bool hybrid, int min_width, int kmax, int nmin, double eta,
+                                           const std::vector<int>& sbdry, double tol, std::mt19937_64& rng,
+                                           bool undo_prune = false, double undo_prune_cutoff = 0.05) {
+    if (x.size() != weights.size()) throw std::invalid_argument("x and weights must have same length");
+    for (int v : sbdry)
+        if (v <= nperm) throw std::runtime_error("cbs_gpu::segment_weighted: a sequential boundary that can stop early is not supported");
+    Context& c = default_context();
+    const cbs_gpu_params p = detail::params(alpha, nperm, hybrid, min_width, kmax, nmin, eta, tol, false, undo_prune, undo_prune_cutoff);
+    const auto state = detail::next312(rng);
+    SegmentationResult r;
+    int cap = (int)x.size() + 1, nseg = 0;
+    uint64_t draws = 0;
+    r.lengths.resize((size_t)cap);
+    r.means.resize((size_t)cap);
+    c.check(cbs_gpu_segment_weighted(c.get(), x.data(), weights.data(), (int)x.size(), &p, state.data(), cap, r.lengths.data(),
+                                     r.means.data(), &nseg, &draws));
+    r.lengths.resize((size_t)nseg);
+    r.means.resize((size_t)nseg);
+    rng.discard(draws);
+    return r;
+}
+
 }  // namespace cbs_gpu
 
 #endif

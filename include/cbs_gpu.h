@@ -133,6 +133,18 @@ int cbs_gpu_segment(cbs_gpu_ctx* ctx, const double* x, int32_t n, const cbs_gpu_
                     const uint64_t* mt_next312, int32_t cap, int32_t* lengths, double* means, int32_t* n_segments,
                     uint64_t* draws_consumed);
 
+/* cbs::segment_weighted (lib/cbs/CBS.hpp:115-128, CBS.cpp:1026-1099) on one vector: wfindcpt / wtmaxo / wtmaxp (with the
+ * reference's tss = 0 placeholder, CBS.cpp:741-743, mirrored) / wxperm / wtpermp on the device.  weights must be finite
+ * and positive.  hybrid = 1 is accepted while no unit exceeds nmin (the reference then never reaches hwtmaxp);
+ * otherwise CBS_GPU_ERR_UNSUPPORTED.  Other arguments as cbs_gpu_segment. */
+int cbs_gpu_segment_weighted(cbs_gpu_ctx* ctx, const double* x, const double* weights, int32_t n,
+                             const cbs_gpu_params* params, const uint64_t* mt_next312, int32_t cap, int32_t* lengths,
+                             double* means, int32_t* n_segments, uint64_t* draws_consumed);
+/* the same for many units at once (values and weights: float64, laid out alike, host or device memory); no smoothing */
+int cbs_gpu_segment_weighted_batch(cbs_gpu_ctx* ctx, const double* values, const double* weights, int memspace,
+                                   const int64_t* unit_offsets, const uint64_t* unit_ids, int32_t n_units,
+                                   const cbs_gpu_params* params, cbs_gpu_result** out);
+
 /* cbs::tmaxo (CBS.hpp:32, CBS.cpp:378-381): max-t statistic and 0-based arc of x as given
  * (no centring), with tss supplied by the caller. */
 int cbs_gpu_tmaxo(cbs_gpu_ctx* ctx, const double* x, int32_t n, double tss, int32_t al0, int32_t ibin,

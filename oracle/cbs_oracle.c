@@ -998,3 +998,6 @@ int64_t orc_segment_units(const double* values, const int64_t* unit_off, const i
     if (log_n) *log_n = nlog;
     return total;
 }
+
+/* weighted CBS (segment_weighted and what it calls): same translation unit, see the file's header */
+#include "cbs_oracle_weighted.c"

@@ -132,6 +132,20 @@ int64_t orc_segment_units(const double* values, const int64_t* unit_off, const i
                           int* lengths, double* means, uint64_t* draws_out, orc_split_rec* log, int64_t log_cap,
                           int64_t* log_n, int* log_unit);
 
+/* ---- weighted CBS (cbs_oracle_weighted.c; CBS.cpp:538-591, 610-743, 894-957, 1026-1099) ---------------
+ * cw = cumsum(w)/sqrt(sum w) as segment_weighted builds it (:1062-1066); rw = sqrt(w). */
+orc_tmax orc_wtmaxo(const double* x, const double* w, const double* cw, int n, double tss, int al0);
+double orc_wtmaxp(const double* px, const double* w, const double* cw, int n, int al0);
+void orc_wxperm(const double* x, const double* rw, int n, double* px, orc_rng* rng);
+double orc_wtpermp(int n1, int n2, int n, const double* x, const double* w, const double* rw, int nperm, orc_rng* rng,
+                   double* scratch);
+/* segments, or -needed-16 if cap is too small, or -3 when the weighted hybrid method would be reached */
+int orc_segment_weighted(const double* x, const double* w, int n, const orc_seg_opts* o, orc_rng* rng, uint64_t seed,
+                         uint64_t unit_id, int cap, int* lengths, double* means);
+int64_t orc_segment_weighted_units(const double* values, const double* weights, const int64_t* unit_off,
+                                   const uint64_t* unit_ids, int n_units, const orc_cohort_opts* o, int64_t cap,
+                                   int* seg_count, int* lengths, double* means, uint64_t* draws_out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -198,6 +198,13 @@ class Oracle:
         L.orc_segment_units.argtypes = [c_double_p, c_i64_p, c_int_p, c_u64_p, C.c_int, C.POINTER(OrcCohortOpts),
                                         C.c_int64, c_int_p, c_int_p, c_double_p, c_u64_p, C.POINTER(OrcSplitRec),
                                         C.c_int64, c_i64_p, c_int_p]
+        L.orc_segment_weighted.restype = C.c_int
+        L.orc_segment_weighted.argtypes = [c_double_p, c_double_p, C.c_int, C.POINTER(OrcSegOpts), C.POINTER(OrcRng),
+                                           C.c_uint64, C.c_uint64, C.c_int, c_int_p, c_double_p]
+        L.orc_segment_weighted_units.restype = C.c_int64
+        L.orc_segment_weighted_units.argtypes = [c_double_p, c_double_p, c_i64_p, c_u64_p, C.c_int,
+                                                 C.POINTER(OrcCohortOpts), C.c_int64, c_int_p, c_int_p, c_double_p,
+                                                 c_u64_p]
 
     # -- rng ---------------------------------------------------------------
     def rng_mt(self, seed: int) -> OrcRng:
@@ -262,6 +269,44 @@ class Oracle:
         if want_log:
             return out + ([log[i] for i in range(nlog.value)],)
         return out
+
+    def segment_weighted(self, x, w, p: SegParams, rng: OrcRng | None = None, unit_id: int = 0):
+        """cbs::segment_weighted restated (cbs_oracle_weighted.c) -> (lengths, means)."""
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        w = np.ascontiguousarray(w, dtype=np.float64)
+        if rng is None:
+            rng = self.rng_philox(p.seed) if p.rng_kind else self.rng_mt(p.seed)
+        cap = max(16, len(x))
+        lengths = np.zeros(cap, dtype=np.int32)
+        means = np.zeros(cap, dtype=np.float64)
+        opts = p.seg_opts()
+        k = self.lib.orc_segment_weighted(_dp(x), _dp(w), len(x), C.byref(opts), C.byref(rng), p.seed, unit_id, cap,
+                                          _ip(lengths), _dp(means))
+        if k == -3:
+            raise NotImplementedError("weighted hybrid method is not restated")
+        assert k >= 0, k
+        return lengths[:k].copy(), means[:k].copy()
+
+    def segment_weighted_units(self, values, weights, unit_off, p: SegParams, unit_ids=None):
+        values = np.ascontiguousarray(values, dtype=np.float64)
+        weights = np.ascontiguousarray(weights, dtype=np.float64)
+        unit_off = np.ascontiguousarray(unit_off, dtype=np.int64)
+        n_units = len(unit_off) - 1
+        cap = int(len(values)) + n_units + 16
+        seg_count = np.zeros(n_units, dtype=np.int32)
+        lengths = np.zeros(cap, dtype=np.int32)
+        means = np.zeros(cap, dtype=np.float64)
+        draws = np.zeros(n_units, dtype=np.uint64)
+        uid = None if unit_ids is None else np.ascontiguousarray(unit_ids, dtype=np.uint64)
+        opts = p.cohort_opts()
+        tot = self.lib.orc_segment_weighted_units(
+            _dp(values), _dp(weights), unit_off.ctypes.data_as(c_i64_p),
+            uid.ctypes.data_as(c_u64_p) if uid is not None else None, n_units, C.byref(opts), cap, _ip(seg_count),
+            _ip(lengths), _dp(means), draws.ctypes.data_as(c_u64_p))
+        if tot == -3:
+            raise NotImplementedError("weighted hybrid method is not restated")
+        assert tot >= 0, tot
+        return dict(seg_count=seg_count, lengths=lengths[:tot].copy(), means=means[:tot].copy(), draws=draws)
 
     def smooth(self, values, chrom, smooth_region=10, outlier_sd_scale=4.0, smooth_sd_scale=2.0, trim=0.025):
         values = np.ascontiguousarray(values, dtype=np.float64)
@@ -346,6 +391,10 @@ class Ref:
         L.ref_segment.argtypes = [c_double_p, C.c_int, C.c_int, C.c_double, C.c_int, C.c_int, C.c_int, C.c_int,
                                   C.c_int, C.c_double, C.c_double, C.c_void_p, C.c_int, C.c_double, C.c_int, c_int_p,
                                   c_double_p]
+        L.ref_segment_weighted.restype = C.c_int
+        L.ref_segment_weighted.argtypes = [c_double_p, c_double_p, C.c_int, C.c_double, C.c_int, C.c_int, C.c_int,
+                                           C.c_int, C.c_int, C.c_double, C.c_double, C.c_void_p, C.c_int, C.c_double,
+                                           C.c_int, c_int_p, c_double_p]
         L.ref_smooth.restype = C.c_int
         L.ref_smooth.argtypes = [c_double_p, c_int_p, C.c_int64, C.c_int, C.c_double, C.c_double, C.c_double,
                                  c_double_p]
@@ -418,6 +467,19 @@ class Ref:
         k = self.lib.ref_segment(_dp(x), len(x), int(p.ibin), p.alpha, p.nperm, int(p.hybrid), p.min_width, p.kmax,
                                  p.nmin, p.eta, p.tol, rng.h, int(p.undo_prune), p.undo_prune_cutoff, cap,
                                  _ip(lengths), _dp(means))
+        assert k >= 0
+        return lengths[:k].copy(), means[:k].copy()
+
+    def segment_weighted(self, x, w, p: SegParams, rng=None):
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        w = np.ascontiguousarray(w, dtype=np.float64)
+        rng = rng or self.rng(p.seed)
+        cap = max(16, len(x))
+        lengths = np.zeros(cap, dtype=np.int32)
+        means = np.zeros(cap, dtype=np.float64)
+        k = self.lib.ref_segment_weighted(_dp(x), _dp(w), len(x), p.alpha, p.nperm, int(p.hybrid), p.min_width, p.kmax,
+                                          p.nmin, p.eta, p.tol, rng.h, int(p.undo_prune), p.undo_prune_cutoff, cap,
+                                          _ip(lengths), _dp(means))
         assert k >= 0
         return lengths[:k].copy(), means[:k].copy()
 

@@ -59,6 +59,45 @@ int main() {
         // both engines must now be at the same position
         for (int i = 0; i < 5; ++i) CHECK(rng() == orc_rng_u64(&orng));
     }
+    {   // Weighted_SegmentDriver_MatchesDNAcopy_SimpleCase (tests/cbs_test.cpp:309-330), all four parameter rows
+        std::vector<double> xw, ww;
+        for (int i = 0; i < 15; ++i) { xw.push_back(0.0); ww.push_back(1.0); }
+        for (int i = 0; i < 15; ++i) { xw.push_back(2.0); ww.push_back(0.5); }
+        for (int i = 0; i < 15; ++i) { xw.push_back(-1.5); ww.push_back(2.0); }
+        for (int i = 0; i < 15; ++i) { xw.push_back(0.0); ww.push_back(1.0); }
+        const struct { double alpha; int nperm; bool hybrid; int mw; } cases[] = {{0.01, 200, false, 2}, {0.05, 100, false, 3},
+                                                                                 {0.01, 200, true, 2}, {0.05, 100, true, 3}};
+        for (const auto& tc : cases) {
+            std::mt19937_64 rng(1);
+            std::vector<int> sbdry((tc.nperm + 1) * (tc.nperm + 2) / 2 + 2, tc.nperm + 1);
+            const auto seg = cbs_gpu::segment_weighted(xw, ww, tc.alpha, tc.nperm, tc.hybrid, tc.mw, 25, 200, 0.05, sbdry, 1e-6, rng, false, 0.05);
+            CHECK(seg.lengths.size() == 4);
+            if (seg.lengths.size() == 4) {
+                CHECK(seg.lengths[0] == 15 && seg.lengths[1] == 15 && seg.lengths[2] == 15 && seg.lengths[3] == 15);
+                CHECK(std::fabs(seg.means[0]) < 1e-9 && std::fabs(seg.means[1] - 2.0) < 1e-9 && std::fabs(seg.means[2] + 1.5) < 1e-9 &&
+                      std::fabs(seg.means[3]) < 1e-9);
+            }
+        }
+        // noisy weighted vector against the oracle, engine position included
+        std::mt19937_64 g(5);
+        std::normal_distribution<double> nz(0.0, 0.2);
+        std::uniform_real_distribution<double> uw(0.5, 2.0);
+        std::vector<double> y(700), w(700);
+        for (size_t i = 0; i < y.size(); ++i) { y[i] = (double)(float)(nz(g) + ((i >= 200 && i < 330) ? 0.4 : 0.0)); w[i] = uw(g); }
+        std::mt19937_64 rng(11);
+        orc_rng orng;
+        orc_rng_seed_mt(&orng, 11);
+        const int nperm = 300;
+        std::vector<int> sbdry(2000, nperm + 1);
+        const auto seg = cbs_gpu::segment_weighted(y, w, 0.01, nperm, false, 2, 25, 200, 0.05, sbdry, 1e-6, rng);
+        orc_seg_opts o = {0, 0.01, nperm, 0, 2, 25, 200, 0.05, 1e-6, 0, 0.05};
+        std::vector<int> len(y.size());
+        std::vector<double> mean(y.size());
+        const int k = orc_segment_weighted(y.data(), w.data(), (int)y.size(), &o, &orng, 11, 0, (int)y.size(), len.data(), mean.data());
+        CHECK(k == (int)seg.lengths.size());
+        for (int i = 0; i < k && i < (int)seg.lengths.size(); ++i) { CHECK(len[i] == seg.lengths[i]); CHECK(mean[i] == seg.means[i]); }
+        for (int i = 0; i < 5; ++i) CHECK(rng() == orc_rng_u64(&orng));
+    }
     {   // smooth: size mismatch and negative region throw std::invalid_argument (smooth.cpp:125-126)
         bool threw = false;
         try { cbs_gpu::smooth({1.0, 2.0}, {1}); } catch (const std::invalid_argument&) { threw = true; }

@@ -163,3 +163,43 @@ def test_cohort_loop_matches_reference(oracle, ref):
         b = ref.segment_units(vals.astype(np.float64), off, lab, p, nthreads=1 if chain else 4)
         assert np.array_equal(a["seg_count"], b["seg_count"])
         assert np.array_equal(a["lengths"], b["lengths"]) and np.array_equal(a["means"], b["means"])
+
+
+# ---- weighted CBS (cbs_oracle_weighted.c) ------------------------------------------------------------------------
+CASE2_X = np.array([0.0] * 15 + [2.0] * 15 + [-1.5] * 15 + [0.0] * 15)
+CASE2_W = np.array([1.0] * 15 + [0.5] * 15 + [2.0] * 15 + [1.0] * 15)
+
+
+@pytest.mark.parametrize("alpha,nperm,hybrid,min_width", [(0.01, 200, False, 2), (0.05, 100, False, 3),
+                                                          (0.01, 200, True, 2), (0.05, 100, True, 3)])
+def test_kat_case2_segment_weighted(oracle, alpha, nperm, hybrid, min_width):
+    # tests/cbs_test.cpp:309-330 (inputs literal in tests/cbs_generate.R:91-92): 15/15/15/15, means 0/2/-1.5/0
+    lengths, means = oracle.segment_weighted(CASE2_X, CASE2_W, SegParams(alpha=alpha, nperm=nperm, hybrid=hybrid,
+                                                                         min_width=min_width, seed=1))
+    assert lengths.tolist() == [15, 15, 15, 15]
+    assert np.allclose(means, [0.0, 2.0, -1.5, 0.0], atol=1e-9)
+
+
+def test_segment_weighted_matches_reference(oracle, ref):
+    from helpers import make_unit
+    rng = np.random.default_rng(81)
+    for trial in range(60):
+        n = int(rng.integers(4, 1200))
+        x = make_unit(rng, n, int(rng.integers(0, 5)))
+        w = [rng.uniform(0.5, 2.0, n), rng.choice([0.5, 1.0, 2.0], n), np.ones(n)][trial % 3]
+        p = SegParams(nperm=int(rng.choice([20, 100, 400])), alpha=float(rng.choice([0.01, 0.05])),
+                      min_width=int(rng.choice([2, 3, 5])), seed=int(rng.integers(1, 100)), undo_prune=bool(trial % 8 == 7))
+        if n < 2 * p.min_width:
+            continue
+        eng = ref.rng(p.seed)
+        wl, wm = ref.segment_weighted(x, w, p, eng)
+        orng = oracle.rng_mt(p.seed)
+        gl, gm = oracle.segment_weighted(x, w, p, orng)
+        assert np.array_equal(gl, wl), (trial, n)
+        assert np.array_equal(gm, wm), (trial, n)
+        assert ref.rng_equals(eng, p.seed, orng.draws), (trial, n)
+
+
+def test_segment_weighted_hybrid_unsupported(oracle):
+    with pytest.raises(NotImplementedError):
+        oracle.segment_weighted(np.arange(300.0), np.ones(300), SegParams(hybrid=True, nmin=200))
