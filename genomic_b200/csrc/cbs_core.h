@@ -172,6 +172,7 @@ struct Task {
     long long off_sx, off_bs, off_A, off_rej;
     long long off_draw;  // MT: offset of this batch's window inside the draws arena
     uint64_t key;        // philox task key
+    int w_ok;            // weighted CBS: cw of the segment is finite and strictly increasing (written by the observed scan)
 };
 
 struct Chain {        // MT replay: one serial stream
@@ -293,6 +294,7 @@ struct Dev {
     double* rw;       // sqrt(w) (CBS.cpp:1056)
     double* cw;       // per pending segment, at the segment's offset: cumsum(w)/sqrt(sum w) (CBS.cpp:1062-1066)
     double* ycur;     // cur * rw: what wxperm shuffles (CBS.cpp:540)
+    int no_early;     // CBS_GPU_NO_EARLY=1: decision-mode scans never stop at the first rejecting arc (A/B switch)
 };
 
 enum { ERR_TASK_CAP = 101, ERR_SEG_CAP = 102, ERR_ARENA = 103, ERR_SPLIT_CAP = 104, ERR_INTERNAL = 105, ERR_STALL = 106, ERR_STREAM_CAP = 107 };

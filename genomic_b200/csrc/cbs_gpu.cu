@@ -425,6 +425,7 @@ int run_cbs(cbs_gpu_ctx* c, const std::vector<long long>& off, const uint64_t* u
         if (c->jump_ready) { hD.jump_polys = c->jump.as<uint64_t>(); hD.span_max = (long long)mtjump::NSEG * mtjump::SEG; }
     }
     hD.profile = c->counting ? 1 : 0;
+    hD.no_early = env_ll("CBS_GPU_NO_EARLY", 0) ? 1 : 0;
     if (weighted) {
         hD.w = c->wts.as<double>(); hD.rw = c->rw.as<double>(); hD.cw = c->cw.as<double>(); hD.ycur = c->ycur.as<double>();
         CUDA_TRY(c, cudaMemsetAsync(c->flag.p, 0, sizeof(int), st));
@@ -546,7 +547,7 @@ int run_cbs(cbs_gpu_ctx* c, const std::vector<long long>& off, const uint64_t* u
                 }
             }
             for (int k = 2; k < 5; ++k) if (used_side[k]) { cudaEventRecord(c->ev_side[k], c->side[k]); cudaStreamWaitEvent(st, c->ev_side[k], 0); }
-            { LaunchTimer t(c, K_PREFIX); k_chain<<<c->sm_count * 12, CHAIN_WARPS * 32, 0, st>>>(dD); }
+            { LaunchTimer t(c, K_PREFIX); if (weighted) k_chain<true><<<c->sm_count * 12, CHAIN_WARPS * 32, 0, st>>>(dD); else k_chain<false><<<c->sm_count * 12, CHAIN_WARPS * 32, 0, st>>>(dD); }
             cudaStreamWaitEvent(st, c->ev_side[0], 0);
             { LaunchTimer t(c, K_SCAN);
               if (weighted) k_wscan<<<c->sm_count * 4, 256, wscan_smem, st>>>(dD, lay.nb_max);

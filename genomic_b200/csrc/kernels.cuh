@@ -753,6 +753,7 @@ __global__ void __launch_bounds__(128) k_perm(Dev* D) {
 // warps per SM keep the FP64 pipe and HBM busy when many permutations are in flight.
 // ------------------------------------------------------------------------------------
 #define CHAIN_WARPS 4
+template <bool WEIGHTED>  // weighted CBS: the chain adds px*w (wtmaxo, CBS.cpp:623,627); the product is rounded before the addition
 __global__ void __launch_bounds__(CHAIN_WARPS * 32) k_chain(Dev* D) {
     __shared__ __align__(16) double buf_all[CHAIN_WARPS][PERM_CHUNK];
     if (D->done) return;
@@ -779,13 +780,12 @@ __global__ void __launch_bounds__(CHAIN_WARPS * 32) k_chain(Dev* D) {
         row_stats_init(rst);
         double prev_last = 0.0;  // S[0]
         const double* __restrict__ src = sx + 1;
-        // weighted CBS: the chain adds px*w (wtmaxo, CBS.cpp:623,627); the product is rounded before the addition
-        const double* __restrict__ wt = D->w ? D->w + D->unit_off[t.unit] + t.lo : nullptr;
+        const double* __restrict__ wt = WEIGHTED ? D->w + D->unit_off[t.unit] + t.lo : nullptr;
         if (lane == 0) sx[0] = 0.0;
         double run = 0.0;
         double r[PERM_CHUNK / 32];
 #pragma unroll
-        for (int q = 0; q < PERM_CHUNK / 32; ++q) { const int i = lane + 32 * q; r[q] = (i < n) ? (wt ? src[i] * wt[i] : src[i]) : 0.0; }
+        for (int q = 0; q < PERM_CHUNK / 32; ++q) { const int i = lane + 32 * q; r[q] = (i < n) ? (WEIGHTED ? src[i] * wt[i] : src[i]) : 0.0; }
         for (int c0 = 0; c0 < n; c0 += PERM_CHUNK) {
             const int cnt = min(PERM_CHUNK, n - c0);
             __syncwarp();
@@ -794,7 +794,7 @@ __global__ void __launch_bounds__(CHAIN_WARPS * 32) k_chain(Dev* D) {
             __syncwarp();
             if (c0 + PERM_CHUNK < n) {
 #pragma unroll
-                for (int q = 0; q < PERM_CHUNK / 32; ++q) { const int i = c0 + PERM_CHUNK + lane + 32 * q; r[q] = (i < n) ? (wt ? src[i] * wt[i] : src[i]) : 0.0; }
+                for (int q = 0; q < PERM_CHUNK / 32; ++q) { const int i = c0 + PERM_CHUNK + lane + 32 * q; r[q] = (i < n) ? (WEIGHTED ? src[i] * wt[i] : src[i]) : 0.0; }
             }
             if (lane == 0) {
                 int kk = 0;
@@ -854,6 +854,12 @@ struct ScanSmem {
     double g_min, g_max;  // global extrema of the prefix sums (0.0 unless below / above it)
     int g_imin, g_imax;
     int n_list, pop;      // list of block pairs that reach the level: entries / next entry to scan
+    // decision mode, early exit: the reject decision is f(max) >= thresh with f(M) = M/((tss-M)/(n-2)); every floating
+    // point operation in f is monotone in M, so the COMPUTED f is non-decreasing while M + 0.0001 < tss (beyond, the
+    // reference replaces tss).  Once an arc with f(stat) >= thresh is found the permutation rejects whatever the
+    // maximum is -- provided no arc of the row can get within 0.0001 of tss, which pass 1 establishes from the pair bounds.
+    double rej_at;        // smallest statistic known to reject (+inf when the early exit is off)
+    int decided;
 };
 
 struct Cand {
@@ -1024,6 +1030,7 @@ __device__ void scan_unit_exact(const ScanCtx& c, unsigned pcode, int i0, int L0
     }
     if (!c.loc) {
         if (best > 0.0) {
+            if (best >= sm->rej_at) sm->decided = 1;
             atomic_max_pos_double(&sm->found, best);
             atomic_max_pos_double(&sm->level, best);
             atomic_max_pos_double(&sm->sms, sqrt(best) * (1.0 - 1e-12));
@@ -1182,6 +1189,7 @@ __device__ void sweep_short(const ScanCtx& c, UnitQueue& uq, ScanSmem* sm, int w
     const int ngs = (Lb >> 5) + 1, total = ((c.n >> 5) + 1) * ngs;
     unsigned long long my_arcs = 0, my_slots = 0;
     for (int base = warp * 32; base < total; base += nwarps * 32) {
+        if (__any_sync(FULL, *((volatile int*)&sm->decided))) break;  // decision mode: settled
         const int idx = base + lane;
         unsigned keep4 = 0, code0 = 0;
         if (idx < total) {
@@ -1452,6 +1460,7 @@ __global__ void __launch_bounds__(256, 3) k_scan(Dev* D, ScanLayout lay) {
                 sm->g_min = below ? lo : 0.0; sm->g_imin = below ? s_amin[blo] : n;
                 sm->g_max = above ? hi : 0.0; sm->g_imax = above ? s_amax[bhi] : n;
                 sm->n_list = 0;
+                sm->decided = 0; sm->rej_at = __longlong_as_double(0x7ff0000000000000LL);
             }
         }
         __syncthreads();
@@ -1478,6 +1487,10 @@ __global__ void __launch_bounds__(256, 3) k_scan(Dev* D, ScanLayout lay) {
                 if (mstar > prov && mstar + 0.001 < tss0 && mstar / ((tss0 - mstar) / (c.rn - 2.0)) < thresh) prov = mstar;
             }
             double lb = 0.0;
+            // early exit of decision mode needs max + 0.0001 < tss for every arc of the row: rn*smx^2/min(L(n-L)) bounds
+            // the arcs of a pair, so  rn*smx^2 < ublim*min(L(n-L))  for all pairs (division free) establishes it
+            const double ublim = (tss0 - 0.001) * (1.0 - 1e-9);
+            bool ub_ok = decide && !D->no_early && init + 0.001 < tss0;
             {
                 int bi = 1, bj = 1;
                 if (tid < npairs) pair_from_index(tid, nb, bi, bj);
@@ -1496,6 +1509,11 @@ __global__ void __launch_bounds__(256, 3) k_scan(Dev* D, ScanLayout lay) {
                         }
                         int ilo, ihi, jlo, jhi, lenlo, lenhi;
                         pair_lengths(c, bi, bj, ilo, ihi, jlo, jhi, lenlo, lenhi);
+                        if (ub_ok && lenlo <= lenhi) {
+                            const double rlo = (double)lenlo, rhi = (double)lenhi;
+                            const double a = rlo * (c.rn - rlo), b2 = rhi * (c.rn - rhi);
+                            if (!(c.rn * smx * smx < ublim * ((b2 < a) ? b2 : a))) ub_ok = false;
+                        }
                         if (lenlo < SCAN_LSMALL) lenlo = SCAN_LSMALL;
                         if (lenlo <= lenhi) {
                             const double rlo = (double)lenlo, rhi = (double)lenhi;
@@ -1518,10 +1536,20 @@ __global__ void __launch_bounds__(256, 3) k_scan(Dev* D, ScanLayout lay) {
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) { const double o2 = shfl_d(lb, lane ^ o); if (o2 > lb) lb = o2; }
             if (lane == 0) sm->red[warp] = lb;
-            __syncthreads();
+            const int ub_all = __syncthreads_and(ub_ok ? 1 : 0);
             if (tid == 0) {
                 double m = init;
                 for (int w = 0; w < nwarps; ++w) if (sm->red[w] > m) m = sm->red[w];
+                sm->rej_at = __longlong_as_double(0x7ff0000000000000LL);
+                sm->decided = 0;
+                if (decide && ub_all) {
+                    const double thresh = t.ostat * 0.99999;
+                    const double ra = thresh * tss0 / (c.rn - 2.0 + thresh) * (1.0 + 1e-9);
+                    if (ra > 0.0 && ra + 0.001 < tss0 && ra / ((tss0 - ra) / (c.rn - 2.0)) >= thresh) {
+                        sm->rej_at = ra;
+                        if (m >= ra) sm->decided = 1;  // the seed arc or the best valid corner already rejects
+                    }
+                }
                 double level = m;
                 if (decide) {
                     // decision mode: only arcs that could make this permutation reject matter.
@@ -1551,8 +1579,9 @@ __global__ void __launch_bounds__(256, 3) k_scan(Dev* D, ScanLayout lay) {
             uq.q = s_queue + warp * (2 * SCAN_QUEUE + SCAN_GRING);
             uq.head = 0; uq.n = 0;
             int* gring = uq.q + 2 * SCAN_QUEUE;
-            sweep_short(c, uq, sm, warp, nwarps, lane);
-            for (;;) {
+            const bool settled = sm->decided != 0;  // uniform: written before the barrier above
+            if (!settled) sweep_short(c, uq, sm, warp, nwarps, lane);
+            for (; !settled;) {
                 for (;;) {
                     if (*((volatile int*)&sm->n_list) > SCAN_LIST - 32 * nwarps) break;  // every warp may still add 32
                     int q0 = 0;
@@ -1584,6 +1613,7 @@ __global__ void __launch_bounds__(256, 3) k_scan(Dev* D, ScanLayout lay) {
                     if (lane == 0) w = atomicAdd(&sm->pop, 1);
                     w = __shfl_sync(FULL, w, 0);
                     if (w >= n_list) break;
+                    if (__any_sync(FULL, *((volatile int*)&sm->decided))) break;  // decision mode: settled
                     const int code = s_list[w];
                     const int bi = code >> 16, bj = code & 0xffff;
                     if (!pair_alive(c, bi, bj, *((volatile double*)&sm->level))) continue;  // the level may have risen
@@ -1591,7 +1621,7 @@ __global__ void __launch_bounds__(256, 3) k_scan(Dev* D, ScanLayout lay) {
                 }
                 drain_units(c, uq, sm, lane, true);  // the level may still rise: flush before the next list
                 __syncthreads();
-                const bool finished = sm->next_pair >= npairs;
+                const bool finished = sm->next_pair >= npairs || sm->decided;
                 __syncthreads();
                 if (finished) break;
                 if (tid == 0) { sm->n_list = 0; sm->pop = 0; }
@@ -1612,7 +1642,7 @@ __global__ void __launch_bounds__(256, 3) k_scan(Dev* D, ScanLayout lay) {
             }
             if (c.loc) { t.ostat = stat; t.tmaxi = fi; t.tmaxj = fj; }
             else if (it.obs == 2) { t.ostat = stat; }
-            else D->rej[t.off_rej + p] = (t.ostat * 0.99999 <= stat) ? 1 : 0;  // CBS.cpp:838,863
+            else D->rej[t.off_rej + p] = (sm->decided || t.ostat * 0.99999 <= stat) ? 1 : 0;  // CBS.cpp:838,863
             bs.result() = stat;
         }
     }

@@ -45,44 +45,73 @@ __device__ void wprep_warp(Dev* D, Task& t, int lane, double* bx, double* bw) {
     flat = __all_sync(FULL, flat);
     if (lane == 0) t.alleq = flat ? 1 : 0;
     if (flat) return;
-    // CBS.cpp:1053-1058: wsum, wxsum (sequential)
+    // CBS.cpp:1053-1058: wsum, wxsum.  Every sum is sequential, but the sums are independent of each other: lane 0 runs
+    // them as interleaved DADD chains over values the whole warp staged in shared memory (products included: they are
+    // rounded before the addition, as in the reference).  The partial sums of w are kept: they are cw before scaling.
     double wsum = 0.0, wxsum = 0.0;
     for (int c0 = 0; c0 < n; c0 += WPREP_CHUNK) {
         const int cnt = min(WPREP_CHUNK, n - c0);
         __syncwarp();
-        for (int k = lane; k < cnt; k += 32) { bx[k] = x[c0 + k]; bw[k] = w[c0 + k]; }
+        for (int k = lane; k < cnt; k += 32) { const double ww = w[c0 + k]; bw[k] = ww; bx[k] = ww * x[c0 + k]; }
         __syncwarp();
-        if (lane == 0)
-            for (int k = 0; k < cnt; ++k) { const double ww = bw[k]; wsum = wsum + ww; wxsum = wxsum + ww * bx[k]; }
+        if (lane == 0) {  // two independent chains interleaved in one thread: both advance at the DADD latency
+            int k = 0;
+            for (; k + 8 <= cnt; k += 8) {  // operands of 8 steps in registers first: the loads do not wait for the stores
+                double a[8], b[8];
+#pragma unroll
+                for (int u = 0; u < 8; u += 2) {
+                    const double2 va = *reinterpret_cast<const double2*>(bw + k + u), vb = *reinterpret_cast<const double2*>(bx + k + u);
+                    a[u] = va.x; a[u + 1] = va.y; b[u] = vb.x; b[u + 1] = vb.y;
+                }
+#pragma unroll
+                for (int u = 0; u < 8; ++u) { wsum = wsum + a[u]; a[u] = wsum; wxsum = wxsum + b[u]; }
+#pragma unroll
+                for (int u = 0; u < 8; u += 2) *reinterpret_cast<double2*>(bw + k + u) = make_double2(a[u], a[u + 1]);
+            }
+            for (; k < cnt; ++k) { wsum = wsum + bw[k]; wxsum = wxsum + bx[k]; bw[k] = wsum; }
+        }
+        __syncwarp();
+        for (int k = lane; k < cnt; k += 32) cw[c0 + k] = bw[k];  // unscaled csum (CBS.cpp:1065), scaled below
     }
     wsum = shfl_d(wsum, 0); wxsum = shfl_d(wxsum, 0);
     const double avg = wxsum / wsum;
     const double cwscale = sqrt(wsum);
     // CBS.cpp:1061-1066 centring, weighted tss, cw; wtmaxo :623,627 prefix sums of cur*w
     double* sx = D->arena + t.off_sx;
-    double wxx = 0.0, csum = 0.0, run = 0.0;
+    double wxx = 0.0, run = 0.0;
     if (lane == 0) sx[0] = 0.0;
     for (int c0 = 0; c0 < n; c0 += WPREP_CHUNK) {
         const int cnt = min(WPREP_CHUNK, n - c0);
         __syncwarp();
         for (int k = lane; k < cnt; k += 32) {
-            const double v = x[c0 + k] - avg;
-            bx[k] = v; bw[k] = w[c0 + k];
+            const double v = x[c0 + k] - avg, ww = w[c0 + k];
+            bx[k] = v * ww;       // :623,627
+            bw[k] = ww * v * v;   // :1063
             cur[c0 + k] = v;
             ycur[c0 + k] = v * rw[c0 + k];
+            cw[c0 + k] = cw[c0 + k] / cwscale;  // :1066
         }
         __syncwarp();
-        if (lane == 0)
-            for (int k = 0; k < cnt; ++k) {
-                const double v = bx[k], ww = bw[k];
-                wxx = wxx + ww * v * v;
-                csum = csum + ww;
-                run = run + v * ww;
-                bx[k] = run; bw[k] = csum;
+        if (lane == 0) {
+            int k = 0;
+            for (; k + 8 <= cnt; k += 8) {
+                double a[8], b[8];
+#pragma unroll
+                for (int u = 0; u < 8; u += 2) {
+                    const double2 va = *reinterpret_cast<const double2*>(bx + k + u), vb = *reinterpret_cast<const double2*>(bw + k + u);
+                    a[u] = va.x; a[u + 1] = va.y; b[u] = vb.x; b[u + 1] = vb.y;
+                }
+#pragma unroll
+                for (int u = 0; u < 8; ++u) { run = run + a[u]; a[u] = run; wxx = wxx + b[u]; }
+#pragma unroll
+                for (int u = 0; u < 8; u += 2) *reinterpret_cast<double2*>(bx + k + u) = make_double2(a[u], a[u + 1]);
             }
+            for (; k < cnt; ++k) { run = run + bx[k]; wxx = wxx + bw[k]; bx[k] = run; }
+        }
         __syncwarp();
-        for (int k = lane; k < cnt; k += 32) { sx[c0 + 1 + k] = bx[k]; cw[c0 + k] = bw[k] / cwscale; }
+        for (int k = lane; k < cnt; k += 32) sx[c0 + 1 + k] = bx[k];
     }
+    wxx = shfl_d(wxx, 0);
     run = shfl_d(run, 0);
     for (int k = lane; k < SX_PAD; k += 32) sx[n + 1 + k] = run;
     if (lane == 0) t.tss = wxx;
@@ -118,6 +147,8 @@ struct WScanSmem {
     double g_min, g_max;
     int g_imin, g_imax;
     int next_pair, lock;
+    int decided;  // decision mode: an arc that makes the permutation reject has been found, stop scanning
+    double rej_at;  // smallest statistic that certainly rejects (decision mode), +inf otherwise
     // location record: best arc among those that attain the maximum
     double r_corner;
     int r_q, r_phase, r_o1, r_o2, r_i, r_j, r_set;
@@ -195,6 +226,28 @@ __device__ __forceinline__ bool wcand_before(const WCand& a, const WCand& b) {
 
 // one warp scans the two bands of a pair (CBS.cpp:700-734).  LOC == false: raise level/found; LOC == true: record the
 // first-visited arc whose statistic equals `target`.
+// Mapping: every lane owns a row i (its S_i and cw_i stay in registers) and the warp walks j together, so the two loads
+// of a step (S_j, cw_j) are broadcasts that hit L1, independent from step to step (pipelined), and a step evaluates 32
+// arcs.  cw is monotone, hence a row's band is one interval of j: the walk ends when every lane has left its interval.
+template <bool LOC>
+__device__ __forceinline__ void warc_eval(const WPair& p, int q, WScanSmem* sm, double target, WCand& best, double lvl,
+                                          double d, double a1, double psrn, int phase, int o1, int o2, int i, int j) {
+    const double d2 = d * d, den = a1 * (psrn - a1);
+    if (d2 > lvl * den) {
+        const double v = d2 / den;
+        if (LOC) {
+            if (v == target) {
+                WCand c{p.corner, q, phase, o1, o2, i, j, true};
+                if (wcand_before(c, best)) best = c;
+            }
+        } else if (v > __longlong_as_double((long long)*((volatile unsigned long long*)&sm->level))) {
+            atomicMax(&sm->found, (unsigned long long)__double_as_longlong(v));
+            atomicMax(&sm->level, (unsigned long long)__double_as_longlong(v));
+            if (v >= sm->rej_at) sm->decided = 1;
+        }
+    }
+}
+
 template <bool LOC>
 __device__ void wscan_pair(const WRow& r, const WPair& p, int q, WScanSmem* sm, double target, WCand& best, int lane) {
     const double* __restrict__ sx = r.sx;
@@ -206,69 +259,68 @@ __device__ void wscan_pair(const WRow& r, const WPair& p, int q, WScanSmem* sm, 
     if (awtmax > psrn - awtmax) awtmax = psrn - awtmax;
     const volatile unsigned long long* vlevel = &sm->level;
     if (awtlo <= r.psrnov2) {
+        // low band: i = ihi1 .. ilo1 (descending in the reference), j = max(i+al0, jlo) .. jhi while awt1 <= awtmax
         const int ihi1 = (p.bi == p.bj) ? p.ihi - r.al0 : p.ihi;
-        for (int i = ihi1; i >= p.ilo1; --i) {
-            const double sxi = sx[i], cwi = cw[i - 1];
-            const double lvl = LOC ? target * (1.0 - 1e-12) : __longlong_as_double((long long)*vlevel) * (1.0 - 1e-12);
-            const int jlo1 = max(i + r.al0, p.jlo);
-            for (int j0 = jlo1; j0 <= p.jhi; j0 += 32) {
-                const int j = j0 + lane;
-                bool in = false;
-                if (j <= p.jhi) {
-                    const double a1 = cw[j - 1] - cwi;
-                    in = a1 <= awtmax;
-                    if (in) {
-                        const double d = sx[j] - sxi;
-                        const double d2 = d * d, den = a1 * (psrn - a1);
-                        if (d2 > lvl * den) {
-                            const double v = d2 / den;
-                            if (LOC) {
-                                if (v == target) {
-                                    WCand c{p.corner, q, 0, ihi1 - i, j, i, j, true};
-                                    if (wcand_before(c, best)) best = c;
-                                }
-                            } else if (v > __longlong_as_double((long long)*vlevel)) {
-                                atomicMax(&sm->found, (unsigned long long)__double_as_longlong(v));
-                                atomicMax(&sm->level, (unsigned long long)__double_as_longlong(v));
-                            }
+        for (int g0 = ihi1; g0 >= p.ilo1; g0 -= 32) {
+            if (!LOC && __any_sync(FULL, *((volatile int*)&sm->decided))) break;  // warp-uniform exit
+            const int i = g0 - lane;
+            const bool active = i >= p.ilo1;
+            const double sxi = active ? sx[i] : 0.0, cwi = active ? cw[i - 1] : 0.0;
+            const int jlo1 = active ? max(i + r.al0, p.jlo) : 0x7fffffff;
+            double lvl = LOC ? target * (1.0 - 1e-12) : __longlong_as_double((long long)*vlevel) * (1.0 - 1e-12);
+            // the lanes' first j differ only on the diagonal pair: start at the smallest
+            int jstart = jlo1;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) jstart = min(jstart, __shfl_xor_sync(FULL, jstart, o));
+            bool done = !active;
+            for (int j0 = jstart; j0 <= p.jhi; j0 += 4) {
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int j = j0 + u;
+                    if (j <= p.jhi) {
+                        const double sj = sx[j], cj = cw[j - 1];
+                        if (!done && j >= jlo1) {
+                            const double a1 = cj - cwi;
+                            if (a1 <= awtmax) warc_eval<LOC>(p, q, sm, target, best, lvl, sj - sxi, a1, psrn, 0, ihi1 - i, j, i, j);
+                            else done = true;
                         }
                     }
                 }
-                if (!__any_sync(FULL, in)) break;
+                if (__all_sync(FULL, done)) break;
+                if (!LOC && ((j0 - jstart) & 63) == 60) lvl = __longlong_as_double((long long)*vlevel) * (1.0 - 1e-12);
             }
         }
     }
     awtmax = psrn - awtmax;
     if (awthi >= r.psrnov2) {
+        // high band: i = ilo1 .. ihi (ascending), j = jhi1 .. jlo (descending) while awt1 >= psrn - awtmax
         const bool wrap = (p.bi == 1) && (p.bj == r.nb);
-        for (int i = p.ilo1; i <= p.ihi; ++i) {
-            const double sxi = sx[i], cwi = cw[i - 1];
-            const double lvl = LOC ? target * (1.0 - 1e-12) : __longlong_as_double((long long)*vlevel) * (1.0 - 1e-12);
-            const int jhi1 = wrap ? min(p.jhi, p.jhi - r.al0 + i) : p.jhi;
-            for (int j0 = jhi1; j0 >= p.jlo; j0 -= 32) {
-                const int j = j0 - lane;
-                bool in = false;
-                if (j >= p.jlo) {
-                    const double a1 = cw[j - 1] - cwi;
-                    in = a1 >= awtmax;
-                    if (in) {
-                        const double d = sx[j] - sxi;
-                        const double d2 = d * d, den = a1 * (psrn - a1);
-                        if (d2 > lvl * den) {
-                            const double v = d2 / den;
-                            if (LOC) {
-                                if (v == target) {
-                                    WCand c{p.corner, q, 1, i - p.ilo1, -j, i, j, true};
-                                    if (wcand_before(c, best)) best = c;
-                                }
-                            } else if (v > __longlong_as_double((long long)*vlevel)) {
-                                atomicMax(&sm->found, (unsigned long long)__double_as_longlong(v));
-                                atomicMax(&sm->level, (unsigned long long)__double_as_longlong(v));
-                            }
+        for (int g0 = p.ilo1; g0 <= p.ihi; g0 += 32) {
+            if (!LOC && __any_sync(FULL, *((volatile int*)&sm->decided))) break;
+            const int i = g0 + lane;
+            const bool active = i <= p.ihi;
+            const double sxi = active ? sx[i] : 0.0, cwi = active ? cw[i - 1] : 0.0;
+            const int jhi1 = active ? (wrap ? min(p.jhi, p.jhi - r.al0 + i) : p.jhi) : -1;
+            double lvl = LOC ? target * (1.0 - 1e-12) : __longlong_as_double((long long)*vlevel) * (1.0 - 1e-12);
+            int jstart = jhi1;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) jstart = max(jstart, __shfl_xor_sync(FULL, jstart, o));
+            bool done = !active;
+            for (int j0 = jstart; j0 >= p.jlo; j0 -= 4) {
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int j = j0 - u;
+                    if (j >= p.jlo) {
+                        const double sj = sx[j], cj = cw[j - 1];
+                        if (!done && j <= jhi1) {
+                            const double a1 = cj - cwi;
+                            if (a1 >= awtmax) warc_eval<LOC>(p, q, sm, target, best, lvl, sj - sxi, a1, psrn, 1, i - p.ilo1, -j, i, j);
+                            else done = true;
                         }
                     }
                 }
-                if (!__any_sync(FULL, in)) break;
+                if (__all_sync(FULL, done)) break;
+                if (!LOC && ((jstart - j0) & 63) == 60) lvl = __longlong_as_double((long long)*vlevel) * (1.0 - 1e-12);
             }
         }
     }
@@ -285,6 +337,7 @@ __device__ void wscan_pass(const WRow& r, WScanSmem* sm, double target, int lane
         if (lane == 0) q0 = atomicAdd(&sm->next_pair, 32);
         q0 = __shfl_sync(FULL, q0, 0);
         if (q0 >= npairs) break;
+        if (!LOC && __any_sync(FULL, *((volatile int*)&sm->decided))) break;
         const int q = q0 + lane;
         WPair p;
         bool alive = false;
@@ -422,6 +475,19 @@ __global__ void __launch_bounds__(256) k_wscan(Dev* D, int nb_max) {
         const double rn = (double)n;
         const double tss0 = it.obs ? t.tss : 0.0;  // wtmaxp passes tss = 0.0 (CBS.cpp:741-743): mirrored, not "fixed"
         double best = 0.0;
+        bool decided = false;
+        if (it.obs == 1) {
+            // strictly increasing, finite cw <=> every arc weight a and psrn - a is positive, so no arc statistic of this
+            // segment can be inf or NaN: the precondition of the early reject decision of its permutations (an inf
+            // statistic makes the reference's pstat NaN, which never rejects)
+            int bad = 0;
+            for (int i = tid; i < n; i += blockDim.x) {
+                const double ci = r.cw[i], cp = i ? r.cw[i - 1] : 0.0;
+                if (!(ci > cp) || isinf(ci)) bad = 1;
+            }
+            bad = __syncthreads_or(bad);
+            if (tid == 0) t.w_ok = bad ? 0 : 1;
+        }
         if (psdiff > 0.0) {  // else CBS.cpp:642-645
             r.psrn = r.cw[n - 1];
             r.psrnov2 = r.psrn / 2.0;
@@ -440,15 +506,29 @@ __global__ void __launch_bounds__(256) k_wscan(Dev* D, int nb_max) {
                         if (f < thresh) level = mstar;
                     }
                 }
+                sm->decided = 0;
+                sm->rej_at = __longlong_as_double(0x7ff0000000000000LL);
+                if (it.obs == 0 && !D->no_early && t.w_ok && r.init < 1e300) {  // (init is inf when the seed arc is empty)
+                    // early decision: f(M) = M(n-2)(1 +- (M+1) 2^-52) is increasing up to that wobble, so any arc with
+                    // M >= rej_at = thresh/(n-2) (1+1e-9) settles "reject" whatever the maximum turns out to be
+                    const double thresh = t.ostat * 0.99999;
+                    const double ra = thresh / (rn - 2.0) * (1.0 + 1e-9);
+                    const double f = ra / (((ra + 1.0) - ra) / (rn - 2.0));
+                    if (ra < 1e5 && f >= thresh * (1.0 + 5e-10)) {
+                        sm->rej_at = ra;
+                        if (r.init >= ra) sm->decided = 1;
+                    }
+                }
                 sm->level = (unsigned long long)__double_as_longlong(level);
                 sm->found = (unsigned long long)__double_as_longlong(r.init);
                 sm->next_pair = 0; sm->lock = 0; sm->r_set = 0;
                 sm->r_corner = 0.0; sm->r_q = 0; sm->r_phase = 0; sm->r_o1 = 0; sm->r_o2 = 0; sm->r_i = 0; sm->r_j = 0;
             }
             __syncthreads();
-            wscan_pass<false>(r, sm, 0.0, lane);
+            if (!sm->decided) wscan_pass<false>(r, sm, 0.0, lane);
             __syncthreads();
             best = __longlong_as_double((long long)sm->found);
+            decided = sm->decided != 0;
             if (it.obs == 1 && best > r.init) {
                 __syncthreads();
                 if (tid == 0) sm->next_pair = 0;
@@ -464,7 +544,7 @@ __global__ void __launch_bounds__(256) k_wscan(Dev* D, int nb_max) {
             const double stat = best / ((tss - best) / (rn - 2.0));
             if (it.obs == 1) { t.ostat = stat; t.tmaxi = fi; t.tmaxj = fj; }
             else if (it.obs == 2) { t.ostat = stat; }
-            else D->rej[t.off_rej + p] = (t.ostat * 0.99999 <= stat) ? 1 : 0;  // CBS.cpp:900,933
+            else D->rej[t.off_rej + p] = (decided || t.ostat * 0.99999 <= stat) ? 1 : 0;  // CBS.cpp:900,933
         }
     }
 }
