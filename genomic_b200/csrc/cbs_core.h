@@ -173,6 +173,11 @@ struct Task {
     long long off_draw;  // MT: offset of this batch's window inside the draws arena
     uint64_t key;        // philox task key
     int w_ok;            // weighted CBS: cw of the segment is finite and strictly increasing (written by the observed scan)
+    // weighted CBS, observed scan spread over several CTAs (weighted.cuh, k_wscan<1>/<2>, k_wobs_fin): running maximum
+    // shared through global memory (bit patterns of positive doubles) and the first-visited arc that attains it
+    unsigned long long w_level, w_found;
+    double w_init, w_corner;
+    int w_q, w_phase, w_o1, w_o2, w_i, w_j, w_set, w_lock;
 };
 
 struct Chain {        // MT replay: one serial stream

@@ -502,7 +502,7 @@ int run_cbs(cbs_gpu_ctx* c, const std::vector<long long>& off, const uint64_t* u
             { LaunchTimer t(c, K_SCHED); k_sched<<<1, 256, 0, st>>>(dD, c->d_done); }
             cudaEventRecord(c->ev_sched, st);
             cudaStreamWaitEvent(c->side[0], c->ev_sched, 0);
-            { LaunchTimer t(c, K_PREP, c->side[0]); k_tables<<<dim3(16, 64), 256, 0, c->side[0]>>>(dD); if (weighted) k_wprep<<<c->sm_count * 8, 32, 0, c->side[0]>>>(dD); else k_prep<<<c->sm_count * 8, 32, 0, c->side[0]>>>(dD); c->launches++; }
+            { LaunchTimer t(c, K_PREP, c->side[0]); k_tables<<<dim3(16, 64), 256, 0, c->side[0]>>>(dD); if (weighted) { k_wprep<<<c->sm_count * 8, 32, 0, c->side[0]>>>(dD); k_wtables<<<c->sm_count * 2, 256, 0, c->side[0]>>>(dD); c->launches++; } else k_prep<<<c->sm_count * 8, 32, 0, c->side[0]>>>(dD); c->launches++; }
             cudaEventRecord(c->ev_side[0], c->side[0]);
             cudaStreamWaitEvent(c->side[1], c->ev_sched, 0);
             { LaunchTimer t(c, K_EDGEPREP, c->side[1]); if (weighted) k_wedgeprep<<<c->sm_count * 4, 32, 0, c->side[1]>>>(dD); else k_edgeprep<<<c->sm_count * 4, 32, 0, c->side[1]>>>(dD); }
@@ -550,7 +550,13 @@ int run_cbs(cbs_gpu_ctx* c, const std::vector<long long>& off, const uint64_t* u
             { LaunchTimer t(c, K_PREFIX); if (weighted) k_chain<true><<<c->sm_count * 12, CHAIN_WARPS * 32, 0, st>>>(dD); else k_chain<false><<<c->sm_count * 12, CHAIN_WARPS * 32, 0, st>>>(dD); }
             cudaStreamWaitEvent(st, c->ev_side[0], 0);
             { LaunchTimer t(c, K_SCAN);
-              if (weighted) k_wscan<<<c->sm_count * 4, 256, wscan_smem, st>>>(dD, lay.nb_max);
+              if (weighted) {
+                  k_wscan<1><<<c->sm_count * 4, 256, wscan_smem, st>>>(dD, lay.nb_max);   // observed rows, sliced over CTAs
+                  k_wscan<2><<<c->sm_count * 4, 256, wscan_smem, st>>>(dD, lay.nb_max);   // their location pass
+                  k_wobs_fin<<<8, 128, 0, st>>>(dD);
+                  k_wscan<0><<<c->sm_count * 4, 256, wscan_smem, st>>>(dD, lay.nb_max);   // permutation rows
+                  c->launches += 3;
+              }
               else k_scan<<<scan_grid, lay.warps * 32, scan_smem, st>>>(dD, lay); }
             if (p->hybrid) {
                 k_hscan<<<c->sm_count * 4, 256, 0, st>>>(dD);

@@ -29,21 +29,28 @@ __global__ void k_wsetup(const double* __restrict__ w, double* __restrict__ rw, 
 // k_wprep: one warp per new pending segment (CBS.cpp:1046-1067 and the prefix sums of wtmaxo :621-637 on observed data)
 // ------------------------------------------------------------------------------------
 #define WPREP_CHUNK 512
-__device__ void wprep_warp(Dev* D, Task& t, int lane, double* bx, double* bw) {
+#define WPREP_Q (WPREP_CHUNK / 32)
+__device__ void wprep_warp(Dev* D, Task& t, int lane, double* __restrict__ bx, double* __restrict__ bw) {
     const long long base = D->unit_off[t.unit] + t.lo;
     const double* __restrict__ x = D->x + base;
     const double* __restrict__ w = D->w + base;
     const double* __restrict__ rw = D->rw + base;
-    double* cur = D->cur + base;
-    double* cw = D->cw + base;
-    double* ycur = D->ycur + base;
+    double* __restrict__ cur = D->cur + base;
+    double* __restrict__ cw = D->cw + base;
+    double* __restrict__ ycur = D->ycur + base;
     const int n = t.n;
-    // CBS.cpp:1051 all-equal test
+    // CBS.cpp:1051 all-equal test (loads batched in registers: a warp has nothing else to hide their latency with)
     const double x0 = x[0];
     bool flat = true;
-    for (int i = lane; i < n; i += 32) if (!(fabs(x[i] - x0) < 1e-12)) flat = false;
+    for (int i0 = 0; i0 < n; i0 += 32 * WPREP_Q) {
+        double v[WPREP_Q];
+#pragma unroll
+        for (int q = 0; q < WPREP_Q; ++q) { const int i = i0 + lane + 32 * q; v[q] = (i < n) ? x[i] : x0; }
+#pragma unroll
+        for (int q = 0; q < WPREP_Q; ++q) if (!(fabs(v[q] - x0) < 1e-12)) flat = false;
+    }
     flat = __all_sync(FULL, flat);
-    if (lane == 0) t.alleq = flat ? 1 : 0;
+    if (lane == 0) { t.alleq = flat ? 1 : 0; t.w_level = 0ull; t.w_found = 0ull; t.w_set = 0; t.w_lock = 0; t.w_init = -1.0; }
     if (flat) return;
     // CBS.cpp:1053-1058: wsum, wxsum.  Every sum is sequential, but the sums are independent of each other: lane 0 runs
     // them as interleaved DADD chains over values the whole warp staged in shared memory (products included: they are
@@ -51,8 +58,12 @@ __device__ void wprep_warp(Dev* D, Task& t, int lane, double* bx, double* bw) {
     double wsum = 0.0, wxsum = 0.0;
     for (int c0 = 0; c0 < n; c0 += WPREP_CHUNK) {
         const int cnt = min(WPREP_CHUNK, n - c0);
+        double vx[WPREP_Q], vw[WPREP_Q];
+#pragma unroll
+        for (int q = 0; q < WPREP_Q; ++q) { const int k = lane + 32 * q; vx[q] = (k < cnt) ? x[c0 + k] : 0.0; vw[q] = (k < cnt) ? w[c0 + k] : 0.0; }
         __syncwarp();
-        for (int k = lane; k < cnt; k += 32) { const double ww = w[c0 + k]; bw[k] = ww; bx[k] = ww * x[c0 + k]; }
+#pragma unroll
+        for (int q = 0; q < WPREP_Q; ++q) { const int k = lane + 32 * q; bw[k] = vw[q]; bx[k] = vw[q] * vx[q]; }
         __syncwarp();
         if (lane == 0) {  // two independent chains interleaved in one thread: both advance at the DADD latency
             int k = 0;
@@ -71,25 +82,37 @@ __device__ void wprep_warp(Dev* D, Task& t, int lane, double* bx, double* bw) {
             for (; k < cnt; ++k) { wsum = wsum + bw[k]; wxsum = wxsum + bx[k]; bw[k] = wsum; }
         }
         __syncwarp();
-        for (int k = lane; k < cnt; k += 32) cw[c0 + k] = bw[k];  // unscaled csum (CBS.cpp:1065), scaled below
+#pragma unroll
+        for (int q = 0; q < WPREP_Q; ++q) { const int k = lane + 32 * q; if (k < cnt) cw[c0 + k] = bw[k]; }  // unscaled csum (CBS.cpp:1065)
     }
     wsum = shfl_d(wsum, 0); wxsum = shfl_d(wxsum, 0);
     const double avg = wxsum / wsum;
     const double cwscale = sqrt(wsum);
     // CBS.cpp:1061-1066 centring, weighted tss, cw; wtmaxo :623,627 prefix sums of cur*w
-    double* sx = D->arena + t.off_sx;
+    double* __restrict__ sx = D->arena + t.off_sx;
     double wxx = 0.0, run = 0.0;
     if (lane == 0) sx[0] = 0.0;
     for (int c0 = 0; c0 < n; c0 += WPREP_CHUNK) {
         const int cnt = min(WPREP_CHUNK, n - c0);
+        double vx[WPREP_Q], vw[WPREP_Q], vr[WPREP_Q], vc[WPREP_Q];
+#pragma unroll
+        for (int q = 0; q < WPREP_Q; ++q) {
+            const int k = lane + 32 * q;
+            const bool in = k < cnt;
+            vx[q] = in ? x[c0 + k] : 0.0; vw[q] = in ? w[c0 + k] : 0.0; vr[q] = in ? rw[c0 + k] : 0.0; vc[q] = in ? cw[c0 + k] : 0.0;
+        }
         __syncwarp();
-        for (int k = lane; k < cnt; k += 32) {
-            const double v = x[c0 + k] - avg, ww = w[c0 + k];
+#pragma unroll
+        for (int q = 0; q < WPREP_Q; ++q) {
+            const int k = lane + 32 * q;
+            const double v = vx[q] - avg, ww = vw[q];
             bx[k] = v * ww;       // :623,627
             bw[k] = ww * v * v;   // :1063
-            cur[c0 + k] = v;
-            ycur[c0 + k] = v * rw[c0 + k];
-            cw[c0 + k] = cw[c0 + k] / cwscale;  // :1066
+            if (k < cnt) {
+                cur[c0 + k] = v;
+                ycur[c0 + k] = v * vr[q];
+                cw[c0 + k] = vc[q] / cwscale;  // :1066
+            }
         }
         __syncwarp();
         if (lane == 0) {
@@ -109,7 +132,8 @@ __device__ void wprep_warp(Dev* D, Task& t, int lane, double* bx, double* bw) {
             for (; k < cnt; ++k) { run = run + bx[k]; wxx = wxx + bw[k]; bx[k] = run; }
         }
         __syncwarp();
-        for (int k = lane; k < cnt; k += 32) sx[c0 + 1 + k] = bx[k];
+#pragma unroll
+        for (int q = 0; q < WPREP_Q; ++q) { const int k = lane + 32 * q; if (k < cnt) sx[c0 + 1 + k] = bx[k]; }
     }
     wxx = shfl_d(wxx, 0);
     run = shfl_d(run, 0);
@@ -122,6 +146,42 @@ __global__ void __launch_bounds__(32) k_wprep(Dev* D) {
     __shared__ __align__(16) double bw[WPREP_CHUNK];
     if (D->done) return;
     for (int k = blockIdx.x; k < D->n_prep; k += gridDim.x) wprep_warp(D, D->tasks[D->prep_task[k]], threadIdx.x, bx, bw);
+}
+
+// k_wtables: per new segment and block b the smallest weight of an arc of al0 markers inside the block (bound of the
+// diagonal pair (b,b), CBS.cpp:662-664) and across the boundary to block b+1 (pair (b,b+1), :665-667).  They depend on cw
+// only, not on the row, so every permutation of the segment reuses them (the reference recomputes them per call).
+// Stored in the per-marker tables the unweighted scan uses for g[L] / fac[L] (unused by weighted CBS), at the segment's
+// offset.  Runs after k_wprep on the same stream.
+__global__ void __launch_bounds__(256) k_wtables(Dev* D) {
+    if (D->done) return;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    const int al0 = D->prm.min_width;
+    for (int k = blockIdx.x; k < D->n_prep; k += gridDim.x) {
+        const Task& t = D->tasks[D->prep_task[k]];
+        if (t.alleq) continue;
+        const long long base = D->unit_off[t.unit] + t.lo;
+        const double* __restrict__ cw = D->cw + base;
+        const int* __restrict__ bb = D->bbtab + base;
+        double* dmin = D->gtab + base;
+        double* adjmin = D->factab + base;
+        const int n = t.n, nb = t.nb;
+        const double inf = __longlong_as_double(0x7ff0000000000000LL);
+        for (int b = 1 + warp; b <= nb; b += nwarps) {
+            const int ilo = bb[b - 1] + 1, ihi = bb[b];
+            double m1 = inf, m2 = inf;
+            if (lane == 0) m1 = cw[min(ilo + al0, n) - 1] - cw[ilo - 1];
+            for (int kk = ilo + 1 + lane; kk <= ihi - al0; kk += 32) m1 = fmin(m1, cw[kk + al0 - 1] - cw[kk - 1]);
+            if (b < nb) {
+                const int jlo = ihi + 1;
+                if (lane == 0) m2 = cw[jlo - 1] - cw[max(jlo - al0, 1) - 1];
+                for (int kk = max(jlo - al0 + 1, 1) + lane; kk <= ihi; kk += 32) m2 = fmin(m2, cw[min(kk + al0, n) - 1] - cw[kk - 1]);
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) { m1 = fmin(m1, shfl_d(m1, lane ^ o)); m2 = fmin(m2, shfl_d(m2, lane ^ o)); }
+            if (lane == 0) { dmin[b - 1] = m1; adjmin[b - 1] = m2; }
+        }
+    }
 }
 
 // ------------------------------------------------------------------------------------
@@ -147,6 +207,7 @@ struct WScanSmem {
     double g_min, g_max;
     int g_imin, g_imax;
     int next_pair, lock;
+    unsigned long long* glevel; unsigned long long* gfound;  // copies of WRow's
     int decided;  // decision mode: an arc that makes the permutation reject has been found, stop scanning
     double rej_at;  // smallest statistic that certainly rejects (decision mode), +inf otherwise
     // location record: best arc among those that attain the maximum
@@ -160,6 +221,9 @@ struct WRow {
     const double* cw;   // cw[0..n-1]
     const int* bb;      // smem bb[0..nb]
     const double* bmin; const double* bmax; const int* amin; const int* amax;  // smem, per block (0-based)
+    const double* dmin; const double* adjmin;  // k_wtables
+    int q_first, q_stride;                     // pairs of this CTA: batches of 32 starting at q_first, q_stride apart
+    unsigned long long* glevel; unsigned long long* gfound;  // observed scan shared by several CTAs (else nullptr)
     double psrn, psrnov2, init;
 };
 
@@ -186,11 +250,9 @@ __device__ void wpair_eval(const WRow& r, int bi, int bj, WPair& p) {
     }
     double awtlo;
     if (bi == bj) {
-        awtlo = cw[min(p.ilo1 + al0, r.n) - 1] - cw[p.ilo1 - 1];
-        for (int kk = p.ilo1 + 1; kk <= p.ihi - al0; ++kk) awtlo = fmin(awtlo, cw[kk + al0 - 1] - cw[kk - 1]);
+        awtlo = r.dmin[bi - 1];    // :662-664 (k_wtables)
     } else if (bi + 1 == bj) {
-        awtlo = cw[p.jlo - 1] - cw[max(p.jlo - al0, 1) - 1];
-        for (int kk = max(p.jlo - al0 + 1, 1); kk <= p.ihi; ++kk) awtlo = fmin(awtlo, cw[min(kk + al0, r.n) - 1] - cw[kk - 1]);
+        awtlo = r.adjmin[bi - 1];  // :665-667
     } else {
         awtlo = cw[p.jlo - 1] - cw[p.ihi - 1];
     }
@@ -243,6 +305,7 @@ __device__ __forceinline__ void warc_eval(const WPair& p, int q, WScanSmem* sm, 
         } else if (v > __longlong_as_double((long long)*((volatile unsigned long long*)&sm->level))) {
             atomicMax(&sm->found, (unsigned long long)__double_as_longlong(v));
             atomicMax(&sm->level, (unsigned long long)__double_as_longlong(v));
+            if (sm->gfound) { atomicMax(sm->gfound, (unsigned long long)__double_as_longlong(v)); atomicMax(sm->glevel, (unsigned long long)__double_as_longlong(v)); }
             if (v >= sm->rej_at) sm->decided = 1;
         }
     }
@@ -334,7 +397,11 @@ __device__ void wscan_pass(const WRow& r, WScanSmem* sm, double target, int lane
     best.set = false; best.corner = 0.0; best.q = 0; best.phase = 0; best.o1 = 0; best.o2 = 0; best.i = 0; best.j = 0;
     for (;;) {
         int q0 = 0;
-        if (lane == 0) q0 = atomicAdd(&sm->next_pair, 32);
+        if (lane == 0) {
+            q0 = atomicAdd(&sm->next_pair, r.q_stride);
+            // level found by the other CTAs that scan this row
+            if (!LOC && r.glevel) atomicMax(&sm->level, *((volatile unsigned long long*)r.glevel));
+        }
         q0 = __shfl_sync(FULL, q0, 0);
         if (q0 >= npairs) break;
         if (!LOC && __any_sync(FULL, *((volatile int*)&sm->decided))) break;
@@ -393,6 +460,14 @@ __device__ void wscan_pass(const WRow& r, WScanSmem* sm, double target, int lane
     }
 }
 
+// MODE 0: the permutation rows of the round, one CTA per row (reject decision).
+// MODE 1: the observed rows (PermItem::obs == 1), each spread over WOBS_SLICES CTAs that take interleaved batches of
+//         block pairs and share the running maximum through Task::w_level / w_found: an observed scan is ~n^1.5 arcs
+//         (1e8 for a 150 000 marker chromosome) and a round has only a few of them, so one CTA per row leaves the GPU idle.
+// MODE 2: location pass of the observed rows, same slicing, once the maximum is final (the kernel boundary is the
+//         grid-wide barrier); k_wobs_fin then writes ostat / tmaxi / tmaxj.
+#define WOBS_SLICES 24
+template <int MODE>
 __global__ void __launch_bounds__(256) k_wscan(Dev* D, int nb_max) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     if (D->done) return;
@@ -405,25 +480,32 @@ __global__ void __launch_bounds__(256) k_wscan(Dev* D, int nb_max) {
     __shared__ int s_g;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int nwarps = blockDim.x >> 5;
-    const int total = D->item_prefix[D->n_items];
+    const int total = MODE == 0 ? D->item_prefix[D->n_items] : D->n_items * WOBS_SLICES;
     for (;;) {
         __syncthreads();
-        if (tid == 0) s_g = (int)atomicAdd(&D->ctr[1], 1u);
+        if (tid == 0) s_g = (int)atomicAdd(&D->ctr[MODE == 0 ? 1 : 4 + MODE], 1u);
         __syncthreads();
         const int gidx = s_g;
         if (gidx >= total) break;
-        const int k = find_item(D->item_prefix, D->n_items, gidx);
+        int k, p = 0, slice = 0;
+        if (MODE == 0) { k = find_item(D->item_prefix, D->n_items, gidx); p = gidx - D->item_prefix[k]; }
+        else { k = gidx / WOBS_SLICES; slice = gidx - k * WOBS_SLICES; }
         const PermItem it = D->items[k];
+        if ((MODE == 0) != (it.obs != 1)) continue;  // observed rows: MODE 1/2 only
         Task& t = D->tasks[it.task];
         if (it.obs && t.alleq) continue;
-        const int p = gidx - D->item_prefix[k];
         const int n = t.n, nb = t.nb;
         const long long base = D->unit_off[t.unit] + t.lo;
         WRow r;
         r.n = n; r.nb = nb; r.al0 = D->prm.min_width; r.nal0 = n - r.al0;
         r.sx = D->arena + t.off_sx + (long long)p * Sched::sx_stride(n);
         r.cw = D->cw + base;
+        r.dmin = D->gtab + base; r.adjmin = D->factab + base;
         r.bb = s_bb; r.bmin = s_bmin; r.bmax = s_bmax; r.amin = s_amin; r.amax = s_amax;
+        r.q_first = MODE == 0 ? 0 : 32 * slice;
+        r.q_stride = MODE == 0 ? 32 : 32 * WOBS_SLICES;
+        r.glevel = MODE == 1 ? &t.w_level : nullptr;
+        r.gfound = MODE == 1 ? &t.w_found : nullptr;
         const int* bbg = D->bbtab + base;
         for (int b = tid; b <= nb; b += blockDim.x) s_bb[b] = bbg[b];
         __syncthreads();
@@ -471,12 +553,11 @@ __global__ void __launch_bounds__(256) k_wscan(Dev* D, int nb_max) {
         __syncthreads();
         const double psdiff = sm->g_max - sm->g_min;
         const int gimin = sm->g_imin, gimax = sm->g_imax;
-        int fi = min(gimax, gimin), fj = max(gimax, gimin);
+        const int fi = min(gimax, gimin), fj = max(gimax, gimin);
         const double rn = (double)n;
-        const double tss0 = it.obs ? t.tss : 0.0;  // wtmaxp passes tss = 0.0 (CBS.cpp:741-743): mirrored, not "fixed"
         double best = 0.0;
         bool decided = false;
-        if (it.obs == 1) {
+        if (MODE == 1 && slice == 0) {
             // strictly increasing, finite cw <=> every arc weight a and psrn - a is positive, so no arc statistic of this
             // segment can be inf or NaN: the precondition of the early reject decision of its permutations (an inf
             // statistic makes the reference's pstat NaN, which never rejects)
@@ -486,17 +567,18 @@ __global__ void __launch_bounds__(256) k_wscan(Dev* D, int nb_max) {
                 if (!(ci > cp) || isinf(ci)) bad = 1;
             }
             bad = __syncthreads_or(bad);
-            if (tid == 0) t.w_ok = bad ? 0 : 1;
+            if (tid == 0) { t.w_ok = bad ? 0 : 1; t.tmaxi = fi; t.tmaxj = fj; }  // location: the seed arc unless MODE 2 finds better
         }
         if (psdiff > 0.0) {  // else CBS.cpp:642-645
             r.psrn = r.cw[n - 1];
             r.psrnov2 = r.psrn / 2.0;
             const double psrj = fabs(r.cw[gimax - 1] - r.cw[gimin - 1]);
             r.init = (psdiff * psdiff) / (psrj * (r.psrn - psrj));  // :649
+            const unsigned long long init_bits = (unsigned long long)__double_as_longlong(r.init);
             __syncthreads();
             if (tid == 0) {
                 double level = r.init;
-                if (it.obs == 0) {
+                if (MODE == 0) {
                     // decision mode: reject <=> thresh <= f(M), f(M) = M/(((M+1)-M)/(n-2)) ~ M(n-2) (tss = 0 makes the
                     // reference replace tss by M+1); M* sits 1e-9 below the solution, f(M*) < thresh is verified
                     const double thresh = t.ostat * 0.99999;
@@ -508,7 +590,7 @@ __global__ void __launch_bounds__(256) k_wscan(Dev* D, int nb_max) {
                 }
                 sm->decided = 0;
                 sm->rej_at = __longlong_as_double(0x7ff0000000000000LL);
-                if (it.obs == 0 && !D->no_early && t.w_ok && r.init < 1e300) {  // (init is inf when the seed arc is empty)
+                if (MODE == 0 && !D->no_early && t.w_ok && r.init < 1e300) {  // (init is inf when the seed arc is empty)
                     // early decision: f(M) = M(n-2)(1 +- (M+1) 2^-52) is increasing up to that wobble, so any arc with
                     // M >= rej_at = thresh/(n-2) (1+1e-9) settles "reject" whatever the maximum turns out to be
                     const double thresh = t.ostat * 0.99999;
@@ -519,33 +601,69 @@ __global__ void __launch_bounds__(256) k_wscan(Dev* D, int nb_max) {
                         if (r.init >= ra) sm->decided = 1;
                     }
                 }
+                sm->glevel = r.glevel; sm->gfound = r.gfound;
+                if (MODE == 1) {  // the seed arc counts for every slice; then join the level the other slices reached
+                    atomicMax(&t.w_found, init_bits);
+                    atomicMax(&t.w_level, init_bits);
+                    if (slice == 0) t.w_init = r.init;
+                    const double gl = __longlong_as_double((long long)*((volatile unsigned long long*)&t.w_level));
+                    if (gl > level) level = gl;
+                }
                 sm->level = (unsigned long long)__double_as_longlong(level);
-                sm->found = (unsigned long long)__double_as_longlong(r.init);
-                sm->next_pair = 0; sm->lock = 0; sm->r_set = 0;
+                sm->found = init_bits;
+                sm->next_pair = r.q_first; sm->lock = 0; sm->r_set = 0;
                 sm->r_corner = 0.0; sm->r_q = 0; sm->r_phase = 0; sm->r_o1 = 0; sm->r_o2 = 0; sm->r_i = 0; sm->r_j = 0;
             }
             __syncthreads();
-            if (!sm->decided) wscan_pass<false>(r, sm, 0.0, lane);
-            __syncthreads();
-            best = __longlong_as_double((long long)sm->found);
-            decided = sm->decided != 0;
-            if (it.obs == 1 && best > r.init) {
+            if (MODE == 2) {
+                const unsigned long long fb = *((volatile unsigned long long*)&t.w_found);
+                if (fb > init_bits) {  // else the seed arc is the location (it is visited first and wins ties)
+                    wscan_pass<true>(r, sm, __longlong_as_double((long long)fb), lane);
+                    __syncthreads();
+                    if (tid == 0 && sm->r_set) {
+                        WCand mine{sm->r_corner, sm->r_q, sm->r_phase, sm->r_o1, sm->r_o2, sm->r_i, sm->r_j, true};
+                        while (atomicCAS(&t.w_lock, 0, 1) != 0) {}
+                        __threadfence();
+                        const volatile Task& vt = t;
+                        WCand cur{vt.w_corner, vt.w_q, vt.w_phase, vt.w_o1, vt.w_o2, vt.w_i, vt.w_j, vt.w_set != 0};
+                        if (wcand_before(mine, cur)) {
+                            t.w_corner = mine.corner; t.w_q = mine.q; t.w_phase = mine.phase; t.w_o1 = mine.o1; t.w_o2 = mine.o2;
+                            t.w_i = mine.i; t.w_j = mine.j; t.w_set = 1;
+                        }
+                        __threadfence();
+                        atomicExch(&t.w_lock, 0);
+                    }
+                }
+            } else {
+                if (!sm->decided) wscan_pass<false>(r, sm, 0.0, lane);
                 __syncthreads();
-                if (tid == 0) sm->next_pair = 0;
-                __syncthreads();
-                wscan_pass<true>(r, sm, best, lane);
-                __syncthreads();
-                if (sm->r_set) { fi = sm->r_i; fj = sm->r_j; }
+                best = __longlong_as_double((long long)sm->found);
+                decided = sm->decided != 0;
             }
         }
-        if (tid == 0) {
-            double tss = tss0;
+        if (MODE == 0 && tid == 0) {
+            double tss = 0.0;  // wtmaxp passes tss = 0.0 (CBS.cpp:741-743): mirrored, not "fixed"
             if (tss <= best + 0.0001) tss = best + 1.0;  // CBS.cpp:643,737
             const double stat = best / ((tss - best) / (rn - 2.0));
-            if (it.obs == 1) { t.ostat = stat; t.tmaxi = fi; t.tmaxj = fj; }
-            else if (it.obs == 2) { t.ostat = stat; }
+            if (it.obs == 2) t.ostat = stat;
             else D->rej[t.off_rej + p] = (decided || t.ostat * 0.99999 <= stat) ? 1 : 0;  // CBS.cpp:900,933
         }
+    }
+}
+
+// observed rows: statistic and location from the shared records (after k_wscan<1> and k_wscan<2>)
+__global__ void k_wobs_fin(Dev* D) {
+    if (D->done) return;
+    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < D->n_items; k += gridDim.x * blockDim.x) {
+        const PermItem it = D->items[k];
+        if (it.obs != 1) continue;
+        Task& t = D->tasks[it.task];
+        if (t.alleq) continue;
+        const double best = __longlong_as_double((long long)t.w_found);  // 0.0 when the prefix sums have no spread
+        double tss = t.tss;
+        if (tss <= best + 0.0001) tss = best + 1.0;  // CBS.cpp:643,737
+        t.ostat = best / ((tss - best) / ((double)t.n - 2.0));
+        if (t.w_set) { t.tmaxi = t.w_i; t.tmaxj = t.w_j; }
     }
 }
 
