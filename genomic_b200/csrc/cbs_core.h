@@ -178,6 +178,7 @@ struct Task {
     unsigned long long w_level, w_found;
     double w_init, w_corner;
     int w_q, w_phase, w_o1, w_o2, w_i, w_j, w_set, w_lock;
+    double w_delta;      // weighted hybrid: min weight of a (kmax+1)-marker arc / total weight (getmncwt, CBS.cpp:602-607)
 };
 
 struct Chain {        // MT replay: one serial stream

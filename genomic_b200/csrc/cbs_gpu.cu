@@ -289,8 +289,8 @@ int run_cbs(cbs_gpu_ctx* c, const std::vector<long long>& off, const uint64_t* u
     if (Nmax > 1000000) return fail(c, CBS_GPU_ERR_UNSUPPORTED, "units longer than 1,000,000 markers are not supported");
     if (N > 2000000000LL) return fail(c, CBS_GPU_ERR_UNSUPPORTED, "more than 2e9 markers per call are not supported");
     const bool mt = p->rng_mode == CBS_GPU_RNG_MT19937_64;
-    if (weighted && p->hybrid && Nmax > p->nmin)
-        return fail(c, CBS_GPU_ERR_UNSUPPORTED, "weighted CBS with hybrid p-values (hwtmaxp) is not implemented: units must not exceed nmin");
+    if (weighted && p->hybrid && p->nmin < p->kmax + 2)
+        return fail(c, CBS_GPU_ERR_UNSUPPORTED, "weighted hybrid CBS needs nmin >= kmax + 2");
 
     RunCaps cap;
     cap.task_cap = (int)std::min<long long>(std::max<long long>(4096, 64LL * n_units + 1024), 1 << 22);
@@ -502,7 +502,7 @@ int run_cbs(cbs_gpu_ctx* c, const std::vector<long long>& off, const uint64_t* u
             { LaunchTimer t(c, K_SCHED); k_sched<<<1, 256, 0, st>>>(dD, c->d_done); }
             cudaEventRecord(c->ev_sched, st);
             cudaStreamWaitEvent(c->side[0], c->ev_sched, 0);
-            { LaunchTimer t(c, K_PREP, c->side[0]); k_tables<<<dim3(16, 64), 256, 0, c->side[0]>>>(dD); if (weighted) { k_wprep<<<c->sm_count * 8, 32, 0, c->side[0]>>>(dD); k_wtables<<<c->sm_count * 2, 256, 0, c->side[0]>>>(dD); c->launches++; } else k_prep<<<c->sm_count * 8, 32, 0, c->side[0]>>>(dD); c->launches++; }
+            { LaunchTimer t(c, K_PREP, c->side[0]); k_tables<<<dim3(16, 64), 256, 0, c->side[0]>>>(dD); if (weighted) { k_wprep<<<c->sm_count * 8, 32, 0, c->side[0]>>>(dD); k_wtables<<<c->sm_count * 2, 256, 0, c->side[0]>>>(dD); c->launches++; if (p->hybrid) { k_wdelta<<<c->sm_count * 2, 32, 0, c->side[0]>>>(dD); c->launches++; } } else k_prep<<<c->sm_count * 8, 32, 0, c->side[0]>>>(dD); c->launches++; }
             cudaEventRecord(c->ev_side[0], c->side[0]);
             cudaStreamWaitEvent(c->side[1], c->ev_sched, 0);
             { LaunchTimer t(c, K_EDGEPREP, c->side[1]); if (weighted) k_wedgeprep<<<c->sm_count * 4, 32, 0, c->side[1]>>>(dD); else k_edgeprep<<<c->sm_count * 4, 32, 0, c->side[1]>>>(dD); }
@@ -547,7 +547,7 @@ int run_cbs(cbs_gpu_ctx* c, const std::vector<long long>& off, const uint64_t* u
                 }
             }
             for (int k = 2; k < 5; ++k) if (used_side[k]) { cudaEventRecord(c->ev_side[k], c->side[k]); cudaStreamWaitEvent(st, c->ev_side[k], 0); }
-            { LaunchTimer t(c, K_PREFIX); if (weighted) k_chain<true><<<c->sm_count * 12, CHAIN_WARPS * 32, 0, st>>>(dD); else k_chain<false><<<c->sm_count * 12, CHAIN_WARPS * 32, 0, st>>>(dD); }
+            { LaunchTimer t(c, K_PREFIX); if (weighted && p->hybrid) { k_wssq<<<c->sm_count * 8, 128, 0, st>>>(dD); c->launches++; } if (weighted) k_chain<true><<<c->sm_count * 12, CHAIN_WARPS * 32, 0, st>>>(dD); else k_chain<false><<<c->sm_count * 12, CHAIN_WARPS * 32, 0, st>>>(dD); }
             cudaStreamWaitEvent(st, c->ev_side[0], 0);
             { LaunchTimer t(c, K_SCAN);
               if (weighted) {
@@ -559,7 +559,7 @@ int run_cbs(cbs_gpu_ctx* c, const std::vector<long long>& off, const uint64_t* u
               }
               else k_scan<<<scan_grid, lay.warps * 32, scan_smem, st>>>(dD, lay); }
             if (p->hybrid) {
-                k_hscan<<<c->sm_count * 4, 256, 0, st>>>(dD);
+                if (weighted) k_whscan<<<c->sm_count * 4, 256, 0, st>>>(dD); else k_hscan<<<c->sm_count * 4, 256, 0, st>>>(dD);
                 k_tailp_terms<<<c->sm_count * 8, 128, 0, st>>>(dD, c->tailp.as<double>());
                 k_tailp_sum<<<c->sm_count, 64, 0, st>>>(dD, c->tailp.as<double>());
                 c->launches += 3;

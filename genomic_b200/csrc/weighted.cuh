@@ -10,7 +10,7 @@
 //   k_wscan    wtmaxo / wtmaxp (CBS.cpp:610-743): CTA per (segment, permutation)
 //   k_wedgeprep, k_wedgeperm   wtpermp (CBS.cpp:549-591)
 //   k_wmeans   weighted segment means (CBS.cpp:1091-1097)
-// The hybrid method (hwtmaxp/getmncwt) is not built: calls that would reach it are rejected by the host.
+//   k_wdelta, k_wssq, k_whscan   the weighted hybrid method (getmncwt :593-608, hwtmaxp :745-828)
 #pragma once
 
 namespace cbsg {
@@ -494,6 +494,7 @@ __global__ void __launch_bounds__(256) k_wscan(Dev* D, int nb_max) {
         if ((MODE == 0) != (it.obs != 1)) continue;  // observed rows: MODE 1/2 only
         Task& t = D->tasks[it.task];
         if (it.obs && t.alleq) continue;
+        if (!it.obs && t.use_hybrid) continue;  // k_whscan
         const int n = t.n, nb = t.nb;
         const long long base = D->unit_off[t.unit] + t.lo;
         WRow r;
@@ -664,6 +665,140 @@ __global__ void k_wobs_fin(Dev* D) {
         if (tss <= best + 0.0001) tss = best + 1.0;  // CBS.cpp:643,737
         t.ostat = best / ((tss - best) / ((double)t.n - 2.0));
         if (t.w_set) { t.tmaxi = t.w_i; t.tmaxj = t.w_j; }
+    }
+}
+
+// ------------------------------------------------------------------------------------
+// weighted hybrid method (wfindcpt :908-921): delta from the weights (getmncwt :593-608), hwtmaxp (:745-828)
+//   k_wdelta  per new segment: smallest weight of an arc of kmax+1 markers (wrap-around arcs included) / total weight;
+//             k_tailp_* then evaluate the tail probability with it
+//   k_wssq    per permutation row, BEFORE the chain turns the row into prefix sums: ssq = sum w*px*px, sequential (:757,762)
+//   k_whscan  hwtmaxp for one permutation per CTA.  Its pruning (lengths are abandoned once the bound from mncwt drops
+//             below the running maximum) only skips arcs that cannot exceed the maximum, so the value is the maximum of
+//             d^2/(a(W-a)) over ALL arcs of al0..k markers, wrap-around arcs included; evaluated by brute force like
+//             k_hscan, with the division only for arcs that can raise the thread's maximum.  mncwt itself is not needed.
+// ------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(32) k_wdelta(Dev* D) {
+    if (D->done || !D->prm.hybrid) return;
+    const int lane = threadIdx.x;
+    for (int k = blockIdx.x; k < D->n_prep; k += gridDim.x) {
+        Task& t = D->tasks[D->prep_task[k]];
+        if (!t.use_hybrid || t.alleq) continue;
+        const double* __restrict__ cw = D->cw + D->unit_off[t.unit] + t.lo;
+        const int n = t.n, len = D->prm.kmax + 1, rest = n - len;
+        if (rest < 1) { if (lane == 0) t.w_delta = 0.5; continue; }
+        const double total = cw[n - 1];
+        double m = cw[len - 1];
+        for (int i = 1 + lane; i <= rest; i += 32) m = fmin(m, cw[i + len - 1] - cw[i - 1]);
+        for (int i = 1 + lane; i <= len; i += 32) m = fmin(m, total - (cw[i + rest - 1] - cw[i - 1]));
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) m = fmin(m, shfl_d(m, lane ^ o));
+        if (lane == 0) t.w_delta = m / total;
+    }
+}
+
+__global__ void __launch_bounds__(128) k_wssq(Dev* D) {
+    __shared__ __align__(16) double buf_all[4][WPREP_CHUNK];
+    if (D->done || !D->prm.hybrid) return;
+    const int lane = threadIdx.x & 31;
+    double* __restrict__ buf = buf_all[threadIdx.x >> 5];
+    const int total = D->item_prefix[D->n_items];
+    for (;;) {
+        int g = 0;
+        if (lane == 0) g = (int)atomicAdd(&D->ctr[7], 1u);
+        g = __shfl_sync(FULL, g, 0);
+        if (g >= total) break;
+        const int k = find_item(D->item_prefix, D->n_items, g);
+        const PermItem it = D->items[k];
+        const Task& t = D->tasks[it.task];
+        if (it.obs || !t.use_hybrid) continue;
+        const int p = g - D->item_prefix[k], n = t.n;
+        const double* __restrict__ px = D->arena + t.off_sx + (long long)p * Sched::sx_stride(n) + 1;
+        const double* __restrict__ w = D->w + D->unit_off[t.unit] + t.lo;
+        double ssq = 0.0;
+        for (int c0 = 0; c0 < n; c0 += WPREP_CHUNK) {
+            const int cnt = min(WPREP_CHUNK, n - c0);
+            double v[WPREP_Q];
+#pragma unroll
+            for (int q = 0; q < WPREP_Q; ++q) {
+                const int kk = lane + 32 * q;
+                const double a = (kk < cnt) ? px[c0 + kk] : 0.0, ww = (kk < cnt) ? w[c0 + kk] : 0.0;
+                v[q] = ww * a * a;
+            }
+            __syncwarp();
+#pragma unroll
+            for (int q = 0; q < WPREP_Q; ++q) buf[lane + 32 * q] = v[q];
+            __syncwarp();
+            if (lane == 0) {
+                int kk = 0;
+                for (; kk + 8 <= cnt; kk += 8) {
+                    double a[8];
+#pragma unroll
+                    for (int u = 0; u < 8; u += 2) { const double2 va = *reinterpret_cast<const double2*>(buf + kk + u); a[u] = va.x; a[u + 1] = va.y; }
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) ssq = ssq + a[u];
+                }
+                for (; kk < cnt; ++kk) ssq = ssq + buf[kk];
+            }
+        }
+        if (lane == 0) BlockStats(D->arena + t.off_bs + (long long)p * Sched::bs_stride(t.nb), t.nb).result() = ssq;
+        __syncwarp();
+    }
+}
+
+__global__ void __launch_bounds__(256) k_whscan(Dev* D) {
+    __shared__ double s_red[8];
+    __shared__ int s_g;
+    if (D->done || !D->prm.hybrid) return;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int total = D->item_prefix[D->n_items];
+    const int kk = D->prm.kmax, al0 = D->prm.min_width;
+    for (;;) {
+        __syncthreads();
+        if (tid == 0) s_g = (int)atomicAdd(&D->ctr[4], 1u);
+        __syncthreads();
+        const int gidx = s_g;
+        if (gidx >= total) break;
+        const int it_k = find_item(D->item_prefix, D->n_items, gidx);
+        const PermItem it = D->items[it_k];
+        Task& t = D->tasks[it.task];
+        if (it.obs || !t.use_hybrid) continue;
+        const int p = gidx - D->item_prefix[it_k];
+        const int n = t.n;
+        const double* __restrict__ sx = D->arena + t.off_sx + (long long)p * Sched::sx_stride(n);
+        const double* __restrict__ cw = D->cw + D->unit_off[t.unit] + t.lo;
+        const double W = cw[n - 1];
+        double best = 0.0;
+        for (int i = 1 + tid; i <= n; i += blockDim.x) {
+            const double si = sx[i], ci = cw[i - 1];
+            for (int j = al0; j <= kk; ++j) {  // arcs (i, i+j) (:763-775, :795-805)
+                const int e = i + j;
+                if (e > n) break;
+                const double d = sx[e] - si, a = cw[e - 1] - ci;
+                const double d2 = d * d, den = a * (W - a);
+                if (d2 > best * den * (1.0 - 1e-12)) { const double v = d2 / den; if (v > best) best = v; }
+            }
+            for (int j = (i > al0 ? i : al0); j <= kk; ++j) {  // wrap-around arcs: i <= j, against i+n-j (:780-790)
+                const int e = i + n - j;
+                const double d = sx[e] - si, a = cw[e - 1] - ci;
+                const double d2 = d * d, den = a * (W - a);
+                if (d2 > best * den * (1.0 - 1e-12)) { const double v = d2 / den; if (v > best) best = v; }
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) { const double o2 = shfl_d(best, lane ^ o); if (o2 > best) best = o2; }
+        if (lane == 0) s_red[warp] = best;
+        __syncthreads();
+        if (tid == 0) {
+            double m = 0.0;
+            for (int w = 0; w < (int)(blockDim.x >> 5); ++w) if (s_red[w] > m) m = s_red[w];
+            const double ssq = BlockStats(D->arena + t.off_bs + (long long)p * Sched::bs_stride(t.nb), t.nb).result();
+            const double mean = sx[n] / W;
+            double tss = ssq - mean * mean;  // :776
+            if (tss <= m + 0.0001) tss = m + 1.0;
+            const double stat = m / ((tss - m) / ((double)n - 2.0));
+            D->rej[t.off_rej + p] = (t.ostat * 0.99999 <= stat) ? 1 : 0;
+        }
     }
 }
 

@@ -149,8 +149,7 @@ inline SegmentationResult segment(const std::vector<double>& x, bool ibin, doubl
     return r;
 }
 
-// cbs::segment_weighted, CBS.hpp:115-128 (CBS.cpp:1026-1099).  Same conventions as segment(); the weighted hybrid
-// method (hwtmaxp) is not built, so hybrid = true is only accepted while x.size() <= nmin.
+// cbs::segment_weighted, CBS.hpp:115-128 (CBS.cpp:1026-1099).  Same conventions as segment().
 inline SegmentationResult segment_weighted(const std::vector<double>& x, const std::vector<double>& weights, double alpha,
                                            int nperm, bool hybrid, int min_width, int kmax, int nmin, double eta,
                                            const std::vector<int>& sbdry, double tol, std::mt19937_64& rng,

@@ -135,8 +135,8 @@ int cbs_gpu_segment(cbs_gpu_ctx* ctx, const double* x, int32_t n, const cbs_gpu_
 
 /* cbs::segment_weighted (lib/cbs/CBS.hpp:115-128, CBS.cpp:1026-1099) on one vector: wfindcpt / wtmaxo / wtmaxp (with the
  * reference's tss = 0 placeholder, CBS.cpp:741-743, mirrored) / wxperm / wtpermp on the device.  weights must be finite
- * and positive.  hybrid = 1 is accepted while no unit exceeds nmin (the reference then never reaches hwtmaxp);
- * otherwise CBS_GPU_ERR_UNSUPPORTED.  Other arguments as cbs_gpu_segment. */
+ * and positive.  hybrid = 1 selects the weighted hybrid method (getmncwt / hwtmaxp, CBS.cpp:593-608, 745-828) for
+ * segments longer than nmin, as in the reference.  Other arguments as cbs_gpu_segment. */
 int cbs_gpu_segment_weighted(cbs_gpu_ctx* ctx, const double* x, const double* weights, int32_t n,
                              const cbs_gpu_params* params, const uint64_t* mt_next312, int32_t cap, int32_t* lengths,
                              double* means, int32_t* n_segments, uint64_t* draws_consumed);

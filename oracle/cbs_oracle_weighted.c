@@ -10,11 +10,11 @@
  * randomized inputs, and reproduces the inline KAT of tests/cbs_test.cpp:309-330
  * (15/15/15/15, means 0/2/-1.5/0) -- tests/test_oracle.py.
  *
- * NOT restated: the weighted hybrid method (getmncwt :593-608, hwtmaxp :745-828); calls
- * that would reach it (hybrid && nmin < n) return ORC_W_UNSUPPORTED.
+ * The weighted hybrid method (getmncwt :593-608, hwtmaxp :745-828, the hybrid branch of wfindcpt
+ * :908-921) is restated too and pinned the same way.
  */
 
-#define ORC_W_UNSUPPORTED (-3)
+#define ORC_W_UNSUPPORTED (-3) /* kept for the ABI of the python wrapper; no longer returned */
 
 /* ---- wtmaxo / wtmaxp ------------------------------------------------------------ */
 typedef struct {
@@ -226,9 +226,97 @@ double orc_wtpermp(int n1, int n2, int n, const double* x, const double* w, cons
     return (double)nrej / (double)nperm;
 }
 
-/* ---- one split decision (wfindcpt :894-957), full-permutation p-values only -------- */
+/* ---- weighted hybrid pieces ------------------------------------------------------------ */
+/* smallest weight of an arc of `len` markers, wrap-around arcs included (the loop body of getmncwt, :597-601 / :603-607) */
+static double min_arc_weight(const double* cw, int n, int len) {
+    const double total = cw[n - 1];
+    const int rest = n - len;
+    double m = cw[len - 1];
+    for (int i = 1; i <= rest; ++i) m = fmin(m, cw[i + len - 1] - cw[i - 1]);
+    for (int i = 1; i <= len; ++i) m = fmin(m, total - (cw[i + rest - 1] - cw[i - 1]));
+    return m;
+}
+
+/* getmncwt :593-608: mn[1..k] and delta = min weight of a (k+1)-marker arc / total weight */
+void orc_getmncwt(const double* cw, int n, int k, double* mn, double* delta) {
+    mn[0] = 0.0;
+    for (int j = 1; j <= k; ++j) mn[j] = min_arc_weight(cw, n, j);
+    *delta = min_arc_weight(cw, n, k + 1) / cw[n - 1];
+}
+
+/* arcs of al0..k markers starting in [from, to-len] / wrapping around / ending just behind `seam`; a length is only
+   looked at while its bound spread^2/(mn(total-mn)) reaches the running maximum (:763-775, :780-790, :795-805) */
+static double hw_short_arcs(const double* s, const double* cw, const double* mn, double total, int al0, int k, int n,
+                            int mode, int from, int to, int seam, double spread, double out) {
+    const double spread_sq = spread * spread;
+    for (int len = al0; len <= k; ++len) {
+        const double lim = spread_sq / (mn[len] * (total - mn[len]));
+        if (lim < out) break;
+        int i0, i1, shift;
+        if (mode == 0) { i0 = from; i1 = to - len; shift = len; }
+        else if (mode == 1) { i0 = 1; i1 = len; shift = n - len; }
+        else { i0 = seam + 1 - len; i1 = seam; shift = len; }
+        for (int i = i0; i <= i1; ++i) {
+            const int j = i + shift;
+            const double a = cw[j - 1] - cw[i - 1];
+            const double d = s[j] - s[i];
+            const double v = (d * d) / (a * (total - a));
+            if (v > out) out = v;
+        }
+    }
+    return out;
+}
+
+/* hwtmaxp :745-828 */
+double orc_hwtmaxp(const double* px, const double* w, const double* cw, const double* mn, int n, int k, int al0) {
+    const double rn = (double)n;
+    const int nb = (int)(rn / (double)k);
+    double* s = (double*)calloc((size_t)n + 2, sizeof(double));
+    int* bb = (int*)malloc(sizeof(int) * (size_t)(nb + 1));
+    double* bmin = (double*)malloc(sizeof(double) * (size_t)(nb + 1));
+    double* bmax = (double*)malloc(sizeof(double) * (size_t)(nb + 1));
+    bb[0] = 0;
+    block_ends(n, nb, bb);
+    const double total = cw[n - 1];
+    double run = 0.0, ssq = 0.0, out = 0.0;
+    for (int b = 1; b <= nb; ++b) {
+        const int first = bb[b - 1] + 1;
+        double lo = 0.0, hi = 0.0;
+        int ilo = first, ihi = first;
+        for (int i = first; i <= bb[b]; ++i) {
+            run = run + px[i - 1] * w[i - 1];
+            ssq += w[i - 1] * px[i - 1] * px[i - 1];
+            s[i] = run;
+            if (i == first || run < lo) { lo = run; ilo = i; }
+            if (i == first || run > hi) { hi = run; ihi = i; }
+        }
+        bmin[b] = lo; bmax[b] = hi;
+        const int d = abs(ilo - ihi);
+        if (d <= k && d >= al0) {
+            const double a = fabs(cw[ihi - 1] - cw[ilo - 1]);
+            const double df = hi - lo;
+            const double v = (df * df) / (a * (total - a));
+            if (out < v) out = v;
+        }
+    }
+    const double mean = s[n] / total;
+    double tss = ssq - mean * mean; /* :776 */
+    out = hw_short_arcs(s, cw, mn, total, al0, k, n, 0, 1, bb[1], 0, bmax[1] - bmin[1], out);
+    out = hw_short_arcs(s, cw, mn, total, al0, k, n, 1, 0, 0, 0,
+                        fmax(fabs(bmax[1] - bmin[nb]), fabs(bmax[nb] - bmin[1])), out);
+    for (int l = 2; l <= nb; ++l) {
+        out = hw_short_arcs(s, cw, mn, total, al0, k, n, 0, bb[l - 1] + 1, bb[l], 0, bmax[l] - bmin[l], out);
+        out = hw_short_arcs(s, cw, mn, total, al0, k, n, 2, 0, 0, bb[l - 1],
+                            fmax(fabs(bmax[l] - bmin[l - 1]), fabs(bmax[l - 1] - bmin[l])), out);
+    }
+    free(s); free(bb); free(bmin); free(bmax);
+    if (tss <= out + 0.0001) tss = out + 1.0;
+    return out / ((tss - out) / (rn - 2.0));
+}
+
+/* ---- one split decision (wfindcpt :894-957) -------------------------------------------- */
 static orc_cpt orc_wfndcpt(const double* x, int n, double tss, const double* w, const double* rw, const double* cw,
-                           int nperm, double cpval, int al0, orc_rng* rng) {
+                           int nperm, double cpval, int hybrid, int al0, int hk, int ngrid, double tol, orc_rng* rng) {
     orc_cpt r;
     memset(&r, 0, sizeof(r));
     r.edge_p[0] = r.edge_p[1] = -1.0;
@@ -243,15 +331,25 @@ static orc_cpt orc_wfndcpt(const double* x, int n, double tss, const double* w, 
     const int i1 = obs.start + 1, i2 = obs.end + 1;
     const int arc = imin(i2 - i1, n - i2 + i1);
     if (!(t1 >= 7.0 && arc >= 10)) {
-        const int nrejc = (int)(cpval * (double)nperm);
+        int nrejc = (int)(cpval * (double)nperm);
+        double* mn = NULL;
+        if (hybrid) { /* :908-913: delta is recomputed from the weights */
+            double delta = 0.0;
+            mn = (double*)malloc(sizeof(double) * (size_t)(hk + 2));
+            orc_getmncwt(cw, n, hk, mn, &delta);
+            const double p1 = orc_tailp(t1, delta, n, ngrid, tol);
+            if (p1 > cpval) { r.exit_code = 4; free(mn); free(px); return r; }
+            nrejc = (int)((cpval - p1) * (double)nperm);
+        }
         for (int np = 1; np <= nperm; ++np) { /* sbdry never fires on this path (see orc_fndcpt) */
             orc_rng_begin(rng, 0u, (uint32_t)(np - 1));
             orc_wxperm(x, rw, n, px, rng);
-            const double p = orc_wtmaxp(px, w, cw, n, al0);
+            const double p = hybrid ? orc_hwtmaxp(px, w, cw, mn, n, hk, al0) : orc_wtmaxp(px, w, cw, n, al0);
             r.perms_run = np;
             if (thresh <= p) ++r.nrej;
-            if (r.nrej > nrejc) { r.exit_code = 3; free(px); return r; }
+            if (r.nrej > nrejc) { r.exit_code = 3; free(mn); free(px); return r; }
         }
+        free(mn);
     } else {
         r.exit_code = 2;
     }
@@ -294,7 +392,7 @@ int orc_segment_weighted(const double* x, const double* w, int n, const orc_seg_
         orc_cpt z;
         memset(&z, 0, sizeof(z));
         if (len >= 2 * o->min_width) {
-            if (o->hybrid && o->nmin < len) { unsupported = 1; break; }
+            const int use_hybrid = o->hybrid && (o->nmin < len);
             int flat = 1;
             for (int i = 0; i < len; ++i) if (!(fabs(x[lo + i] - x[lo]) < 1e-12)) { flat = 0; break; }
             if (!flat) {
@@ -310,7 +408,7 @@ int orc_segment_weighted(const double* x, const double* w, int n, const orc_seg_
                     cw[i] = run / scale;
                 }
                 orc_rng_set_task(rng, seed, unit_id, (uint32_t)lo, (uint32_t)hi);
-                z = orc_wfndcpt(cur, len, wxx, ws, rw, cw, o->nperm, o->alpha, o->min_width, rng);
+                z = orc_wfndcpt(cur, len, wxx, ws, rw, cw, o->nperm, o->alpha, use_hybrid, o->min_width, o->kmax, 100, o->tol, rng);
             }
         }
         if (nends + 2 > ends_cap) { ends_cap *= 2; ends = (int*)realloc(ends, sizeof(int) * (size_t)ends_cap); }

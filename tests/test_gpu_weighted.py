@@ -100,5 +100,40 @@ def test_weighted_rejects(ctx):
     x = np.zeros(10)
     with pytest.raises(ValueError):  # invalid argument
         ctx.segment_weighted(x, np.r_[np.ones(9), 0.0], Params(do_smooth=False))  # non-positive weight
-    with pytest.raises(genomic_b200.CbsGpuError):  # hybrid on a unit longer than nmin would need hwtmaxp
-        ctx.segment_weighted(np.arange(300.0), np.ones(300), Params(do_smooth=False, hybrid=True, nmin=200))
+    with pytest.raises(ValueError):
+        ctx.segment_weighted(x, np.ones(9), Params(do_smooth=False))  # size mismatch
+
+
+def test_weighted_hybrid_matches_reference(ctx, ref):
+    # hybrid p-values: delta from the weights (getmncwt), tail probability, hwtmaxp permutations (CBS.cpp:908-921)
+    rng = np.random.default_rng(76)
+    for trial in range(12):
+        n = int(rng.integers(201, 3000))
+        x = make_unit(rng, n, int(rng.integers(0, 4)))
+        w = make_weights(rng, n, trial % 3)
+        p = SegParams(nperm=int(rng.choice([50, 200, 1000])), alpha=float(rng.choice([0.01, 0.05])),
+                      min_width=int(rng.choice([2, 3, 5])), do_smooth=False, seed=int(rng.integers(1, 100)),
+                      hybrid=True, kmax=int(rng.choice([25, 10])), nmin=200)
+        eng = ref.rng(p.seed)
+        wl, wm = ref.segment_weighted(x, w, p, eng)
+        gl, gm, draws = ctx.segment_weighted(x, w, gparams(p, first_batch=int(rng.choice([16, 64, 256]))))
+        assert np.array_equal(gl, wl), (trial, n, gl, wl)
+        assert np.allclose(gm, wm, rtol=1e-9, atol=0), (trial, n)
+        assert ref.rng_equals(eng, p.seed, draws), (trial, n, draws)
+
+
+@pytest.mark.parametrize("mode", ["mt_unit", "philox"])
+def test_weighted_hybrid_batch_matches_oracle(ctx, oracle, mode):
+    rng = np.random.default_rng({"mt_unit": 77, "philox": 78}[mode])
+    units = [make_unit(rng, n, 1) for n in (150, 400, 2500, 9000)]
+    vals, off = pack(units)
+    w = make_weights(rng, len(vals), 0)
+    p = SegParams(nperm=300, alpha=0.01, min_width=2, do_smooth=False, rng_kind=1 if mode == "philox" else 0, chain=False,
+                  seed=5, hybrid=True)
+    want = oracle.segment_weighted_units(vals, w, off, p)
+    got = ctx.segment_weighted_batch(vals, w, off, gparams(p, first_batch=64))
+    assert np.array_equal(got.seg_count, want["seg_count"])
+    assert np.array_equal(got.lengths, want["lengths"])
+    assert np.allclose(got.means, want["means"], rtol=1e-9, atol=0)
+    if p.rng_kind == 0:
+        assert np.array_equal(got.draws, want["draws"])

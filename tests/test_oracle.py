@@ -200,6 +200,21 @@ def test_segment_weighted_matches_reference(oracle, ref):
         assert ref.rng_equals(eng, p.seed, orng.draws), (trial, n)
 
 
-def test_segment_weighted_hybrid_unsupported(oracle):
-    with pytest.raises(NotImplementedError):
-        oracle.segment_weighted(np.arange(300.0), np.ones(300), SegParams(hybrid=True, nmin=200))
+def test_segment_weighted_hybrid_matches_reference(oracle, ref):
+    # getmncwt / hwtmaxp / the hybrid branch of wfindcpt (CBS.cpp:593-608, 745-828, 908-921)
+    from helpers import make_unit
+    rng = np.random.default_rng(91)
+    for trial in range(30):
+        n = int(rng.integers(201, 1500))
+        x = make_unit(rng, n, int(rng.integers(0, 5)))
+        w = [rng.uniform(0.5, 2.0, n), rng.choice([0.5, 1.0, 2.0], n), np.ones(n)][trial % 3]
+        p = SegParams(nperm=int(rng.choice([20, 100, 400])), alpha=float(rng.choice([0.01, 0.05])),
+                      min_width=int(rng.choice([2, 3, 5])), seed=int(rng.integers(1, 100)), hybrid=True,
+                      kmax=int(rng.choice([25, 10])), nmin=200)
+        eng = ref.rng(p.seed)
+        wl, wm = ref.segment_weighted(x, w, p, eng)
+        orng = oracle.rng_mt(p.seed)
+        gl, gm = oracle.segment_weighted(x, w, p, orng)
+        assert np.array_equal(gl, wl), (trial, n)
+        assert np.array_equal(gm, wm), (trial, n)
+        assert ref.rng_equals(eng, p.seed, orng.draws), (trial, n)
