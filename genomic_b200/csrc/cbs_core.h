@@ -176,7 +176,7 @@ struct Task {
     // weighted CBS, observed scan spread over several CTAs (weighted.cuh, k_wscan<1>/<2>, k_wobs_fin): running maximum
     // shared through global memory (bit patterns of positive doubles) and the first-visited arc that attains it
     unsigned long long w_level, w_found;
-    double w_init, w_corner;
+    double w_init, w_corner, w_v;
     int w_q, w_phase, w_o1, w_o2, w_i, w_j, w_set, w_lock;
     double w_delta;      // weighted hybrid: min weight of a (kmax+1)-marker arc / total weight (getmncwt, CBS.cpp:602-607)
 };

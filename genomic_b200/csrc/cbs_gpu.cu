@@ -552,10 +552,9 @@ int run_cbs(cbs_gpu_ctx* c, const std::vector<long long>& off, const uint64_t* u
             { LaunchTimer t(c, K_SCAN);
               if (weighted) {
                   k_wscan<1><<<c->sm_count * 4, 256, wscan_smem, st>>>(dD, lay.nb_max);   // observed rows, sliced over CTAs
-                  k_wscan<2><<<c->sm_count * 4, 256, wscan_smem, st>>>(dD, lay.nb_max);   // their location pass
                   k_wobs_fin<<<8, 128, 0, st>>>(dD);
                   k_wscan<0><<<c->sm_count * 4, 256, wscan_smem, st>>>(dD, lay.nb_max);   // permutation rows
-                  c->launches += 3;
+                  c->launches += 2;
               }
               else k_scan<<<scan_grid, lay.warps * 32, scan_smem, st>>>(dD, lay); }
             if (p->hybrid) {

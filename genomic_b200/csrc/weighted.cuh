@@ -211,7 +211,7 @@ struct WScanSmem {
     int decided;  // decision mode: an arc that makes the permutation reject has been found, stop scanning
     double rej_at;  // smallest statistic that certainly rejects (decision mode), +inf otherwise
     // location record: best arc among those that attain the maximum
-    double r_corner;
+    double r_corner, r_v;
     int r_q, r_phase, r_o1, r_o2, r_i, r_j, r_set;
 };
 
@@ -274,6 +274,7 @@ struct WCand {
     double corner;
     int q, phase, o1, o2, i, j;
     bool set;
+    double v;  // statistic of the arc
 };
 // true if a is visited before b by the reference
 __device__ __forceinline__ bool wcand_before(const WCand& a, const WCand& b) {
@@ -286,23 +287,32 @@ __device__ __forceinline__ bool wcand_before(const WCand& a, const WCand& b) {
     return a.o2 < b.o2;
 }
 
-// one warp scans the two bands of a pair (CBS.cpp:700-734).  LOC == false: raise level/found; LOC == true: record the
-// first-visited arc whose statistic equals `target`.
+// larger statistic first, then the reference's visiting order
+__device__ __forceinline__ bool wcand_better(const WCand& a, const WCand& b) {
+    if (!b.set) return a.set;
+    if (!a.set) return false;
+    if (a.v != b.v) return a.v > b.v;
+    return wcand_before(a, b);
+}
+
+// one warp scans the two bands of a pair (CBS.cpp:700-734), raising level/found.  LOC == true (observed rows): every
+// lane also keeps the best arc it has seen -- largest statistic, earliest in the reference's visiting order among equals.
+// An arc that attains the final maximum M always passes the filter (the level never exceeds M) and its pair is never
+// skipped (bound >= M >= level), so the reduction of these records over lanes, warps and CTAs is the reference's location.
 // Mapping: every lane owns a row i (its S_i and cw_i stay in registers) and the warp walks j together, so the two loads
 // of a step (S_j, cw_j) are broadcasts that hit L1, independent from step to step (pipelined), and a step evaluates 32
 // arcs.  cw is monotone, hence a row's band is one interval of j: the walk ends when every lane has left its interval.
 template <bool LOC>
-__device__ __forceinline__ void warc_eval(const WPair& p, int q, WScanSmem* sm, double target, WCand& best, double lvl,
+__device__ __forceinline__ void warc_eval(const WPair& p, int q, WScanSmem* sm, WCand& best, double lvl,
                                           double d, double a1, double psrn, int phase, int o1, int o2, int i, int j) {
     const double d2 = d * d, den = a1 * (psrn - a1);
     if (d2 > lvl * den) {
         const double v = d2 / den;
         if (LOC) {
-            if (v == target) {
-                WCand c{p.corner, q, phase, o1, o2, i, j, true};
-                if (wcand_before(c, best)) best = c;
-            }
-        } else if (v > __longlong_as_double((long long)*((volatile unsigned long long*)&sm->level))) {
+            WCand c{p.corner, q, phase, o1, o2, i, j, true, v};
+            if (wcand_better(c, best)) best = c;
+        }
+        if (v > __longlong_as_double((long long)*((volatile unsigned long long*)&sm->level))) {
             atomicMax(&sm->found, (unsigned long long)__double_as_longlong(v));
             atomicMax(&sm->level, (unsigned long long)__double_as_longlong(v));
             if (sm->gfound) { atomicMax(sm->gfound, (unsigned long long)__double_as_longlong(v)); atomicMax(sm->glevel, (unsigned long long)__double_as_longlong(v)); }
@@ -312,7 +322,7 @@ __device__ __forceinline__ void warc_eval(const WPair& p, int q, WScanSmem* sm, 
 }
 
 template <bool LOC>
-__device__ void wscan_pair(const WRow& r, const WPair& p, int q, WScanSmem* sm, double target, WCand& best, int lane) {
+__device__ void wscan_pair(const WRow& r, const WPair& p, int q, WScanSmem* sm, WCand& best, int lane) {
     const double* __restrict__ sx = r.sx;
     const double* __restrict__ cw = r.cw;
     const double psrn = r.psrn;
@@ -325,12 +335,12 @@ __device__ void wscan_pair(const WRow& r, const WPair& p, int q, WScanSmem* sm, 
         // low band: i = ihi1 .. ilo1 (descending in the reference), j = max(i+al0, jlo) .. jhi while awt1 <= awtmax
         const int ihi1 = (p.bi == p.bj) ? p.ihi - r.al0 : p.ihi;
         for (int g0 = ihi1; g0 >= p.ilo1; g0 -= 32) {
-            if (!LOC && __any_sync(FULL, *((volatile int*)&sm->decided))) break;  // warp-uniform exit
+            if (__any_sync(FULL, *((volatile int*)&sm->decided))) break;  // warp-uniform exit
             const int i = g0 - lane;
             const bool active = i >= p.ilo1;
             const double sxi = active ? sx[i] : 0.0, cwi = active ? cw[i - 1] : 0.0;
             const int jlo1 = active ? max(i + r.al0, p.jlo) : 0x7fffffff;
-            double lvl = LOC ? target * (1.0 - 1e-12) : __longlong_as_double((long long)*vlevel) * (1.0 - 1e-12);
+            double lvl = __longlong_as_double((long long)*vlevel) * (1.0 - 1e-12);
             // the lanes' first j differ only on the diagonal pair: start at the smallest
             int jstart = jlo1;
 #pragma unroll
@@ -344,13 +354,13 @@ __device__ void wscan_pair(const WRow& r, const WPair& p, int q, WScanSmem* sm, 
                         const double sj = sx[j], cj = cw[j - 1];
                         if (!done && j >= jlo1) {
                             const double a1 = cj - cwi;
-                            if (a1 <= awtmax) warc_eval<LOC>(p, q, sm, target, best, lvl, sj - sxi, a1, psrn, 0, ihi1 - i, j, i, j);
+                            if (a1 <= awtmax) warc_eval<LOC>(p, q, sm, best, lvl, sj - sxi, a1, psrn, 0, ihi1 - i, j, i, j);
                             else done = true;
                         }
                     }
                 }
                 if (__all_sync(FULL, done)) break;
-                if (!LOC && ((j0 - jstart) & 63) == 60) lvl = __longlong_as_double((long long)*vlevel) * (1.0 - 1e-12);
+                if (((j0 - jstart) & 63) == 60) lvl = __longlong_as_double((long long)*vlevel) * (1.0 - 1e-12);
             }
         }
     }
@@ -359,12 +369,12 @@ __device__ void wscan_pair(const WRow& r, const WPair& p, int q, WScanSmem* sm, 
         // high band: i = ilo1 .. ihi (ascending), j = jhi1 .. jlo (descending) while awt1 >= psrn - awtmax
         const bool wrap = (p.bi == 1) && (p.bj == r.nb);
         for (int g0 = p.ilo1; g0 <= p.ihi; g0 += 32) {
-            if (!LOC && __any_sync(FULL, *((volatile int*)&sm->decided))) break;
+            if (__any_sync(FULL, *((volatile int*)&sm->decided))) break;
             const int i = g0 + lane;
             const bool active = i <= p.ihi;
             const double sxi = active ? sx[i] : 0.0, cwi = active ? cw[i - 1] : 0.0;
             const int jhi1 = active ? (wrap ? min(p.jhi, p.jhi - r.al0 + i) : p.jhi) : -1;
-            double lvl = LOC ? target * (1.0 - 1e-12) : __longlong_as_double((long long)*vlevel) * (1.0 - 1e-12);
+            double lvl = __longlong_as_double((long long)*vlevel) * (1.0 - 1e-12);
             int jstart = jhi1;
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) jstart = max(jstart, __shfl_xor_sync(FULL, jstart, o));
@@ -377,13 +387,13 @@ __device__ void wscan_pair(const WRow& r, const WPair& p, int q, WScanSmem* sm, 
                         const double sj = sx[j], cj = cw[j - 1];
                         if (!done && j <= jhi1) {
                             const double a1 = cj - cwi;
-                            if (a1 >= awtmax) warc_eval<LOC>(p, q, sm, target, best, lvl, sj - sxi, a1, psrn, 1, i - p.ilo1, -j, i, j);
+                            if (a1 >= awtmax) warc_eval<LOC>(p, q, sm, best, lvl, sj - sxi, a1, psrn, 1, i - p.ilo1, -j, i, j);
                             else done = true;
                         }
                     }
                 }
                 if (__all_sync(FULL, done)) break;
-                if (!LOC && ((jstart - j0) & 63) == 60) lvl = __longlong_as_double((long long)*vlevel) * (1.0 - 1e-12);
+                if (((jstart - j0) & 63) == 60) lvl = __longlong_as_double((long long)*vlevel) * (1.0 - 1e-12);
             }
         }
     }
@@ -391,20 +401,20 @@ __device__ void wscan_pair(const WRow& r, const WPair& p, int q, WScanSmem* sm, 
 
 // all warps of the CTA walk the pair list once
 template <bool LOC>
-__device__ void wscan_pass(const WRow& r, WScanSmem* sm, double target, int lane) {
+__device__ void wscan_pass(const WRow& r, WScanSmem* sm, int lane) {
     const int npairs = r.nb * (r.nb + 1) / 2;
     WCand best;
-    best.set = false; best.corner = 0.0; best.q = 0; best.phase = 0; best.o1 = 0; best.o2 = 0; best.i = 0; best.j = 0;
+    best.set = false; best.corner = 0.0; best.q = 0; best.phase = 0; best.o1 = 0; best.o2 = 0; best.i = 0; best.j = 0; best.v = 0.0;
     for (;;) {
         int q0 = 0;
         if (lane == 0) {
             q0 = atomicAdd(&sm->next_pair, r.q_stride);
             // level found by the other CTAs that scan this row
-            if (!LOC && r.glevel) atomicMax(&sm->level, *((volatile unsigned long long*)r.glevel));
+            if (r.glevel) atomicMax(&sm->level, *((volatile unsigned long long*)r.glevel));
         }
         q0 = __shfl_sync(FULL, q0, 0);
         if (q0 >= npairs) break;
-        if (!LOC && __any_sync(FULL, *((volatile int*)&sm->decided))) break;
+        if (__any_sync(FULL, *((volatile int*)&sm->decided))) break;
         const int q = q0 + lane;
         WPair p;
         bool alive = false;
@@ -412,7 +422,7 @@ __device__ void wscan_pass(const WRow& r, WScanSmem* sm, double target, int lane
             int bi, bj;
             wpair_from_index(q, r.nb, bi, bj);
             wpair_eval(r, bi, bj, p);
-            const double lvl = LOC ? target : __longlong_as_double((long long)*((volatile unsigned long long*)&sm->level));
+            const double lvl = __longlong_as_double((long long)*((volatile unsigned long long*)&sm->level));
             alive = p.listed && !(p.bsslim * (1.0 + 1e-12) < lvl);
         }
         unsigned mask = __ballot_sync(FULL, alive);
@@ -425,13 +435,13 @@ __device__ void wscan_pass(const WRow& r, WScanSmem* sm, double target, int lane
             s.jlo = __shfl_sync(FULL, p.jlo, src); s.jhi = __shfl_sync(FULL, p.jhi, src);
             s.bsslim = shfl_d(p.bsslim, src); s.awt = shfl_d(p.awt, src); s.corner = shfl_d(p.corner, src);
             s.listed = true;
-            if (!LOC) {  // the level may have risen since the bound was evaluated (read once per warp: uniform branch)
+            {  // the level may have risen since the bound was evaluated (read once per warp: uniform branch)
                 double lvl = 0.0;
                 if (lane == 0) lvl = __longlong_as_double((long long)*((volatile unsigned long long*)&sm->level));
                 lvl = shfl_d(lvl, 0);
                 if (s.bsslim * (1.0 + 1e-12) < lvl) continue;
             }
-            wscan_pair<LOC>(r, s, q0 + src, sm, target, best, lane);
+            wscan_pair<LOC>(r, s, q0 + src, sm, best, lane);
         }
     }
     if (LOC) {
@@ -444,13 +454,15 @@ __device__ void wscan_pass(const WRow& r, WScanSmem* sm, double target, int lane
             c.o1 = __shfl_xor_sync(FULL, best.o1, o); c.o2 = __shfl_xor_sync(FULL, best.o2, o);
             c.i = __shfl_xor_sync(FULL, best.i, o); c.j = __shfl_xor_sync(FULL, best.j, o);
             c.set = __shfl_xor_sync(FULL, best.set ? 1 : 0, o) != 0;
-            if (wcand_before(c, best)) best = c;
+            c.v = shfl_d(best.v, lane ^ o);
+            if (wcand_better(c, best)) best = c;
         }
         if (lane == 0 && best.set) {
             while (atomicCAS(&sm->lock, 0, 1) != 0) {}
             __threadfence_block();
-            WCand cur{sm->r_corner, sm->r_q, sm->r_phase, sm->r_o1, sm->r_o2, sm->r_i, sm->r_j, sm->r_set != 0};
-            if (wcand_before(best, cur)) {
+            WCand cur{sm->r_corner, sm->r_q, sm->r_phase, sm->r_o1, sm->r_o2, sm->r_i, sm->r_j, sm->r_set != 0, sm->r_v};
+            if (wcand_better(best, cur)) {
+                sm->r_v = best.v;
                 sm->r_corner = best.corner; sm->r_q = best.q; sm->r_phase = best.phase; sm->r_o1 = best.o1; sm->r_o2 = best.o2;
                 sm->r_i = best.i; sm->r_j = best.j; sm->r_set = 1;
             }
@@ -464,8 +476,8 @@ __device__ void wscan_pass(const WRow& r, WScanSmem* sm, double target, int lane
 // MODE 1: the observed rows (PermItem::obs == 1), each spread over WOBS_SLICES CTAs that take interleaved batches of
 //         block pairs and share the running maximum through Task::w_level / w_found: an observed scan is ~n^1.5 arcs
 //         (1e8 for a 150 000 marker chromosome) and a round has only a few of them, so one CTA per row leaves the GPU idle.
-// MODE 2: location pass of the observed rows, same slicing, once the maximum is final (the kernel boundary is the
-//         grid-wide barrier); k_wobs_fin then writes ostat / tmaxi / tmaxj.
+//         Every CTA merges its best arc into the row's record (Task::w_v, w_i, w_j, ...); k_wobs_fin then writes
+//         ostat / tmaxi / tmaxj (the kernel boundary is the grid-wide barrier).
 #define WOBS_SLICES 24
 template <int MODE>
 __global__ void __launch_bounds__(256) k_wscan(Dev* D, int nb_max) {
@@ -483,7 +495,7 @@ __global__ void __launch_bounds__(256) k_wscan(Dev* D, int nb_max) {
     const int total = MODE == 0 ? D->item_prefix[D->n_items] : D->n_items * WOBS_SLICES;
     for (;;) {
         __syncthreads();
-        if (tid == 0) s_g = (int)atomicAdd(&D->ctr[MODE == 0 ? 1 : 4 + MODE], 1u);
+        if (tid == 0) s_g = (int)atomicAdd(&D->ctr[MODE == 0 ? 1 : 5], 1u);
         __syncthreads();
         const int gidx = s_g;
         if (gidx >= total) break;
@@ -616,27 +628,24 @@ __global__ void __launch_bounds__(256) k_wscan(Dev* D, int nb_max) {
                 sm->r_corner = 0.0; sm->r_q = 0; sm->r_phase = 0; sm->r_o1 = 0; sm->r_o2 = 0; sm->r_i = 0; sm->r_j = 0;
             }
             __syncthreads();
-            if (MODE == 2) {
-                const unsigned long long fb = *((volatile unsigned long long*)&t.w_found);
-                if (fb > init_bits) {  // else the seed arc is the location (it is visited first and wins ties)
-                    wscan_pass<true>(r, sm, __longlong_as_double((long long)fb), lane);
-                    __syncthreads();
-                    if (tid == 0 && sm->r_set) {
-                        WCand mine{sm->r_corner, sm->r_q, sm->r_phase, sm->r_o1, sm->r_o2, sm->r_i, sm->r_j, true};
-                        while (atomicCAS(&t.w_lock, 0, 1) != 0) {}
-                        __threadfence();
-                        const volatile Task& vt = t;
-                        WCand cur{vt.w_corner, vt.w_q, vt.w_phase, vt.w_o1, vt.w_o2, vt.w_i, vt.w_j, vt.w_set != 0};
-                        if (wcand_before(mine, cur)) {
-                            t.w_corner = mine.corner; t.w_q = mine.q; t.w_phase = mine.phase; t.w_o1 = mine.o1; t.w_o2 = mine.o2;
-                            t.w_i = mine.i; t.w_j = mine.j; t.w_set = 1;
-                        }
-                        __threadfence();
-                        atomicExch(&t.w_lock, 0);
+            if (MODE == 1) {
+                wscan_pass<true>(r, sm, lane);
+                __syncthreads();
+                if (tid == 0 && sm->r_set) {  // this CTA's best arc into the row's record
+                    WCand mine{sm->r_corner, sm->r_q, sm->r_phase, sm->r_o1, sm->r_o2, sm->r_i, sm->r_j, true, sm->r_v};
+                    while (atomicCAS(&t.w_lock, 0, 1) != 0) {}
+                    __threadfence();
+                    const volatile Task& vt = t;
+                    WCand cur{vt.w_corner, vt.w_q, vt.w_phase, vt.w_o1, vt.w_o2, vt.w_i, vt.w_j, vt.w_set != 0, vt.w_v};
+                    if (wcand_better(mine, cur)) {
+                        t.w_v = mine.v; t.w_corner = mine.corner; t.w_q = mine.q; t.w_phase = mine.phase; t.w_o1 = mine.o1;
+                        t.w_o2 = mine.o2; t.w_i = mine.i; t.w_j = mine.j; t.w_set = 1;
                     }
+                    __threadfence();
+                    atomicExch(&t.w_lock, 0);
                 }
             } else {
-                if (!sm->decided) wscan_pass<false>(r, sm, 0.0, lane);
+                if (!sm->decided) wscan_pass<false>(r, sm, lane);
                 __syncthreads();
                 best = __longlong_as_double((long long)sm->found);
                 decided = sm->decided != 0;
@@ -664,7 +673,8 @@ __global__ void k_wobs_fin(Dev* D) {
         double tss = t.tss;
         if (tss <= best + 0.0001) tss = best + 1.0;  // CBS.cpp:643,737
         t.ostat = best / ((tss - best) / ((double)t.n - 2.0));
-        if (t.w_set) { t.tmaxi = t.w_i; t.tmaxj = t.w_j; }
+        // the seed arc is visited first and wins ties; otherwise the first-visited arc that attains the maximum
+        if (t.w_set && t.w_v == best && best > t.w_init) { t.tmaxi = t.w_i; t.tmaxj = t.w_j; }
     }
 }
 
