@@ -56,15 +56,19 @@ __device__ void wprep_warp(Dev* D, Task& t, int lane, double* __restrict__ bx, d
     // them as interleaved DADD chains over values the whole warp staged in shared memory (products included: they are
     // rounded before the addition, as in the reference).  The partial sums of w are kept: they are cw before scaling.
     double wsum = 0.0, wxsum = 0.0;
+    double vx[WPREP_Q], vw[WPREP_Q];  // the next chunk, in flight while lane 0 walks the current one
+#pragma unroll
+    for (int q = 0; q < WPREP_Q; ++q) { const int k = lane + 32 * q; vx[q] = (k < n) ? x[k] : 0.0; vw[q] = (k < n) ? w[k] : 0.0; }
     for (int c0 = 0; c0 < n; c0 += WPREP_CHUNK) {
         const int cnt = min(WPREP_CHUNK, n - c0);
-        double vx[WPREP_Q], vw[WPREP_Q];
-#pragma unroll
-        for (int q = 0; q < WPREP_Q; ++q) { const int k = lane + 32 * q; vx[q] = (k < cnt) ? x[c0 + k] : 0.0; vw[q] = (k < cnt) ? w[c0 + k] : 0.0; }
         __syncwarp();
 #pragma unroll
         for (int q = 0; q < WPREP_Q; ++q) { const int k = lane + 32 * q; bw[k] = vw[q]; bx[k] = vw[q] * vx[q]; }
         __syncwarp();
+        if (c0 + WPREP_CHUNK < n) {
+#pragma unroll
+            for (int q = 0; q < WPREP_Q; ++q) { const int i = c0 + WPREP_CHUNK + lane + 32 * q; vx[q] = (i < n) ? x[i] : 0.0; vw[q] = (i < n) ? w[i] : 0.0; }
+        }
         if (lane == 0) {  // two independent chains interleaved in one thread: both advance at the DADD latency
             int k = 0;
             for (; k + 8 <= cnt; k += 8) {  // operands of 8 steps in registers first: the loads do not wait for the stores
@@ -92,15 +96,10 @@ __device__ void wprep_warp(Dev* D, Task& t, int lane, double* __restrict__ bx, d
     double* __restrict__ sx = D->arena + t.off_sx;
     double wxx = 0.0, run = 0.0;
     if (lane == 0) sx[0] = 0.0;
+#pragma unroll
+    for (int q = 0; q < WPREP_Q; ++q) { const int k = lane + 32 * q; vx[q] = (k < n) ? x[k] : 0.0; vw[q] = (k < n) ? w[k] : 0.0; }
     for (int c0 = 0; c0 < n; c0 += WPREP_CHUNK) {
         const int cnt = min(WPREP_CHUNK, n - c0);
-        double vx[WPREP_Q], vw[WPREP_Q], vr[WPREP_Q], vc[WPREP_Q];
-#pragma unroll
-        for (int q = 0; q < WPREP_Q; ++q) {
-            const int k = lane + 32 * q;
-            const bool in = k < cnt;
-            vx[q] = in ? x[c0 + k] : 0.0; vw[q] = in ? w[c0 + k] : 0.0; vr[q] = in ? rw[c0 + k] : 0.0; vc[q] = in ? cw[c0 + k] : 0.0;
-        }
         __syncwarp();
 #pragma unroll
         for (int q = 0; q < WPREP_Q; ++q) {
@@ -108,13 +107,13 @@ __device__ void wprep_warp(Dev* D, Task& t, int lane, double* __restrict__ bx, d
             const double v = vx[q] - avg, ww = vw[q];
             bx[k] = v * ww;       // :623,627
             bw[k] = ww * v * v;   // :1063
-            if (k < cnt) {
-                cur[c0 + k] = v;
-                ycur[c0 + k] = v * vr[q];
-                cw[c0 + k] = vc[q] / cwscale;  // :1066
-            }
+            if (k < cnt) cur[c0 + k] = v;
         }
         __syncwarp();
+        if (c0 + WPREP_CHUNK < n) {
+#pragma unroll
+            for (int q = 0; q < WPREP_Q; ++q) { const int i = c0 + WPREP_CHUNK + lane + 32 * q; vx[q] = (i < n) ? x[i] : 0.0; vw[q] = (i < n) ? w[i] : 0.0; }
+        }
         if (lane == 0) {
             int k = 0;
             for (; k + 8 <= cnt; k += 8) {
@@ -134,6 +133,14 @@ __device__ void wprep_warp(Dev* D, Task& t, int lane, double* __restrict__ bx, d
         __syncwarp();
 #pragma unroll
         for (int q = 0; q < WPREP_Q; ++q) { const int k = lane + 32 * q; if (k < cnt) sx[c0 + 1 + k] = bx[k]; }
+    }
+    // elementwise tail with all lanes: ycur = cur*rw (what wxperm shuffles, :540), cw scaled (:1066)
+    for (int i0 = 0; i0 < n; i0 += 32 * 8) {
+        double a[8], b[8], c2[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) { const int i = i0 + lane + 32 * q; const bool in = i < n; a[q] = in ? cur[i] : 0.0; b[q] = in ? rw[i] : 0.0; c2[q] = in ? cw[i] : 0.0; }
+#pragma unroll
+        for (int q = 0; q < 8; ++q) { const int i = i0 + lane + 32 * q; if (i < n) { ycur[i] = a[q] * b[q]; cw[i] = c2[q] / cwscale; } }
     }
     wxx = shfl_d(wxx, 0);
     run = shfl_d(run, 0);
