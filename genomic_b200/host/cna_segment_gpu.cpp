@@ -29,107 +29,11 @@
 
 #include "cbs_gpu.h"
 
+#include "cn_reader.hpp"
+
 namespace {
 
-constexpr int kChromosomes = 24;
-
-// 1..24, 0 = unknown (lib/global.hpp:62-90)
-int chromosome_index(const std::string& name) {
-    static const std::map<std::string, int> table = [] {
-        std::map<std::string, int> m;
-        for (int i = 1; i <= kChromosomes; ++i) {
-            m[std::to_string(i)] = i;
-            m["chr" + std::to_string(i)] = i;
-        }
-        m["X"] = 23; m["Y"] = 24; m["chrX"] = 23; m["chrY"] = 24;
-        return m;
-    }();
-    const auto it = table.find(name);
-    return it == table.end() ? 0 : it->second;
-}
-
-// tab separated fields; an empty trailing field counts (lib/parse.cpp:27-38)
-struct Fields {
-    std::string_view line;
-    size_t pos = 0;
-    explicit Fields(const std::string& s) : line(s) {}
-    bool next(std::string_view& f) {
-        if (pos > line.size()) return false;
-        const size_t start = pos;
-        while (pos < line.size() && line[pos] != '\t') ++pos;
-        f = line.substr(start, pos - start);
-        pos = (pos < line.size()) ? pos + 1 : line.size() + 1;
-        return true;
-    }
-};
-
-template <class T>
-bool parse_number(std::string_view text, T& value) {  // lib/parse.hpp:20-26
-    const char* b = text.data();
-    const char* e = b + text.size();
-    const auto r = std::from_chars(b, e, value);
-    return r.ec == std::errc() && r.ptr == e;
-}
-
-struct RawMatrix {
-    std::vector<std::string> sample_names;
-    std::vector<unsigned long> positions[kChromosomes];
-    std::vector<std::vector<float>> values[kChromosomes];  // [chrom][sample][marker]
-};
-
-RawMatrix read_cn(const std::string& path) {
-    std::ifstream file(path);
-    if (!file.is_open()) throw std::runtime_error("Failed to open input file '" + path + "'.");
-    RawMatrix m;
-    std::string line;
-    size_t line_no = 0;
-    for (;;) {
-        std::getline(file, line);
-        if (file.eof()) break;  // as the reference: a last line without newline is not processed
-        ++line_no;
-        Fields fields(line);
-        std::string_view f;
-        if (line_no == 1) {
-            for (int i = 0; i < 3 && fields.next(f); ++i) {}
-            while (fields.next(f)) m.sample_names.emplace_back(f);
-            for (auto& v : m.values) v.assign(m.sample_names.size(), {});
-            continue;
-        }
-        std::string chrom_name;
-        unsigned long pos = 0;
-        if (!fields.next(f)) continue;  // marker name
-        if (!fields.next(f)) continue;
-        chrom_name.assign(f);
-        if (!fields.next(f) || !parse_number(f, pos)) continue;
-        const int chr = chromosome_index(chrom_name);
-        if (chr == 0) continue;  // unknown chromosome: row ignored
-        m.positions[chr - 1].push_back(pos);
-        size_t s = 0;
-        while (fields.next(f)) {
-            float v;
-            if (!parse_number(f, v)) continue;  // unparsable fields are skipped, later columns shift
-            if (s < m.sample_names.size()) m.values[chr - 1][s].push_back(v);
-            ++s;
-        }
-    }
-    // sort every chromosome by position
-    for (int c = 0; c < kChromosomes; ++c) {
-        const size_t n = m.positions[c].size();
-        std::vector<size_t> order(n);
-        for (size_t i = 0; i < n; ++i) order[i] = i;
-        std::stable_sort(order.begin(), order.end(), [&](size_t a, size_t b) { return m.positions[c][a] < m.positions[c][b]; });
-        std::vector<unsigned long> p(n);
-        for (size_t i = 0; i < n; ++i) p[i] = m.positions[c][order[i]];
-        m.positions[c].swap(p);
-        for (auto& sv : m.values[c]) {
-            if (sv.size() != n) throw std::runtime_error("sample column count differs from marker count (unparsable fields?)");
-            std::vector<float> v(n);
-            for (size_t i = 0; i < n; ++i) v[i] = sv[order[i]];
-            sv.swap(v);
-        }
-    }
-    return m;
-}
+using namespace cnio;
 
 // src/cna_segment.hpp:109-125
 void ensure_log_scale(const RawMatrix& m) {
@@ -159,6 +63,7 @@ int main(int argc, char** argv) {
         cbs_gpu_default_params(&p);
         std::string input, output;
         int device = 0;
+        int io_threads = (int)std::max(1u, std::min(16u, std::thread::hardware_concurrency()));  // parser threads (cn_reader.hpp)
         std::vector<std::string> positional;
         auto value_of = [&](int& i, const std::string& arg, const std::string& name, std::string& out) -> bool {
             if (arg == name) { if (i + 1 >= argc) throw std::invalid_argument("missing value for " + name); out = argv[++i]; return true; }
@@ -172,7 +77,7 @@ int main(int argc, char** argv) {
                 std::cout << "usage:  cna_segment_gpu [options] <raw sample matrix file> <output segmentation file>\n"
                              "  --alpha --nperm --min_width --kmax --nmin --eta --trim --smooth_region --outlier_sd_scale\n"
                              "  --smooth_sd_scale --hybrid --undo_prune --undo_prune_cutoff  (as `cna segment`)\n"
-                             "  --device N   --rng mt|philox   --seed S\n";
+                             "  --device N   --rng mt|philox   --seed S   --io_threads T (parser threads, default: all cores up to 16)\n";
                 return 0;
             } else if (value_of(i, a, "--input", v) || value_of(i, a, "-i", v)) input = v;
             else if (value_of(i, a, "--output", v) || value_of(i, a, "-o", v)) output = v;
@@ -190,6 +95,7 @@ int main(int argc, char** argv) {
             else if (value_of(i, a, "--undo_prune", v)) p.undo_prune = (v == "1" || v == "true");
             else if (value_of(i, a, "--undo_prune_cutoff", v)) p.undo_prune_cutoff = std::stod(v);
             else if (value_of(i, a, "--device", v)) device = std::stoi(v);
+            else if (value_of(i, a, "--io_threads", v)) io_threads = std::max(1, std::stoi(v));
             else if (value_of(i, a, "--seed", v)) p.seed = std::stoull(v);
             else if (value_of(i, a, "--rng", v)) { p.rng_mode = (v == "philox") ? CBS_GPU_RNG_PHILOX : CBS_GPU_RNG_MT19937_64; p.chain = (v == "philox") ? 0 : 1; }
             else if (!a.empty() && a[0] == '-') throw std::invalid_argument("unknown option " + a);
@@ -205,7 +111,7 @@ int main(int argc, char** argv) {
         }
         if (output.empty()) output = filestem(input) + ".seg";
 
-        const RawMatrix m = read_cn(input);
+        const RawMatrix m = io_threads > 1 ? read_cn_parallel(input, io_threads) : read_cn(input);
         ensure_log_scale(m);
 
         // units in the reference's order: samples in file order, chromosomes 1..24, empty ones skipped

@@ -147,3 +147,17 @@ def test_sharded_gather_gloo_world2(tmp_path, oracle):
     r = oracle.segment_units(vals.astype(np.float64), off, lab, SegParams(nperm=100, rng_kind=1, seed=11), unit_ids=ids)
     want = shard.pack_table(r["seg_count"], r["lengths"], r["means"], ids)
     assert np.array_equal(got, want)
+
+
+def test_cn_reader_parallel_identical(tmp_path):
+    """genomic_b200/host/cn_reader.hpp: the multi-threaded .cn reader returns exactly what the sequential restatement of
+    RawSampleSet<float>::_read returns (unknown chromosomes, unsorted positions, nan fields, unterminated last line)"""
+    import json
+    import subprocess
+    exe = tmp_path / "reader_test"
+    subprocess.run(["g++", "-std=c++17", "-O2", "-pthread", os.path.join(ROOT, "tests", "cpp", "reader_test.cpp"), "-o", str(exe)],
+                   check=True)
+    for markers, samples, threads in ((37, 3, 4), (1000, 7, 5)):
+        r = subprocess.run([str(exe), str(tmp_path / "t.cn"), str(markers), str(samples), str(threads)], capture_output=True, text=True)
+        assert r.returncode == 0, r.stdout + r.stderr
+        assert json.loads(r.stdout)["identical"] is True
