@@ -324,3 +324,43 @@ def test_undo_prune_matches_oracle(ctx, oracle):
             assert np.array_equal(got.lengths, want["lengths"]) and np.array_equal(got.means, want["means"])
             hits += int(len(want["lengths"]) != len(base["lengths"]))
     assert hits > 0  # pruning actually changed something
+
+
+def test_full_size_sample_properties(ctx, oracle):
+    """BASELINE configs[1] at full size (1.8 M markers, 23 chromosomes, nperm 10 000, smoothing on), where the oracle only
+    finishes the smallest chromosome in seconds: size-independent properties instead -- lengths partition every unit, the
+    means are the sequential sums of the smoothed values, the call is deterministic, and cutting the cohort into two
+    calls (what sharding by sample/chromosome does) changes nothing; the smallest chromosome is checked against the oracle."""
+    from genomic_b200 import synth
+    vals, off, lab, ids = synth.cohort([0], scale=1.0)
+    gp = Params(nperm=10000, alpha=0.01, rng_mode=RNG_MT19937_64, chain=False, seed=1)
+    a = ctx.segment_batch(vals, off, gp, unit_ids=ids)
+    b = ctx.segment_batch(vals, off, gp, unit_ids=ids)
+    assert np.array_equal(a.lengths, b.lengths) and np.array_equal(a.means, b.means) and np.array_equal(a.draws, b.draws)
+    n_units = len(off) - 1
+    x64 = vals.astype(np.float64)
+    for u in range(n_units):
+        s0, s1 = int(a.seg_offsets[u]), int(a.seg_offsets[u + 1])
+        lens = a.lengths[s0:s1]
+        assert lens.min() >= 1 and int(lens.sum()) == int(off[u + 1] - off[u])
+        sm = ctx.smooth(x64[off[u]:off[u + 1]], np.full(int(off[u + 1] - off[u]), int(lab[u]), np.int32))
+        pos = 0
+        for k, ln in enumerate(lens):
+            want = np.cumsum(sm[pos:pos + ln])[-1] / float(ln)  # np.cumsum adds strictly in order, like CBS.cpp:1019
+            assert a.means[s0 + k] == want, (u, k)
+            pos += int(ln)
+    # two calls over disjoint unit ranges == one call (unit ids keep the Philox keys / per-unit MT streams the same)
+    cutu = 12
+    c1 = ctx.segment_batch(vals[:off[cutu]], off[:cutu + 1], gp, unit_ids=ids[:cutu])
+    c2 = ctx.segment_batch(vals[off[cutu]:], off[cutu:] - off[cutu], gp, unit_ids=ids[cutu:])
+    assert np.array_equal(np.concatenate([c1.lengths, c2.lengths]), a.lengths)
+    assert np.array_equal(np.concatenate([c1.means, c2.means]), a.means)
+    assert np.array_equal(np.concatenate([c1.draws, c2.draws]), a.draws)
+    # smallest chromosome against the oracle (same smoothing + CBS, MT replay)
+    u = int(np.argmin(np.diff(off)))
+    p = SegParams(nperm=10000, alpha=0.01, do_smooth=True, rng_kind=0, chain=False, seed=1)
+    want = oracle.segment_units(x64[off[u]:off[u + 1]], np.array([0, off[u + 1] - off[u]], np.int64), lab[u:u + 1], p,
+                                unit_ids=ids[u:u + 1])
+    s0, s1 = int(a.seg_offsets[u]), int(a.seg_offsets[u + 1])
+    assert np.array_equal(a.lengths[s0:s1], want["lengths"]) and np.array_equal(a.means[s0:s1], want["means"])
+    assert a.draws[u] == want["draws"][0]
