@@ -137,3 +137,41 @@ def test_weighted_hybrid_batch_matches_oracle(ctx, oracle, mode):
     assert np.allclose(got.means, want["means"], rtol=1e-9, atol=0)
     if p.rng_kind == 0:
         assert np.array_equal(got.draws, want["draws"])
+
+
+def test_weighted_full_size_sample_properties(ctx, oracle):
+    """weighted CBS on one SNP6-scale sample (1.8 M markers, nperm 10 000): lengths partition every unit, means are the
+    sequential weighted sums, the call is deterministic, splitting it into two calls changes nothing, and the two smallest
+    chromosomes equal the oracle bit for bit (draws included)."""
+    from genomic_b200 import synth
+    vals, off, lab, ids = synth.cohort([0], scale=1.0)
+    x = vals.astype(np.float64)
+    w = np.random.default_rng(20260101).uniform(0.5, 2.0, len(x))
+    gp = Params(nperm=10000, alpha=0.01, do_smooth=False, rng_mode=RNG_MT19937_64, chain=False, seed=1)
+    a = ctx.segment_weighted_batch(x, w, off, gp, unit_ids=ids)
+    b = ctx.segment_weighted_batch(x, w, off, gp, unit_ids=ids)
+    assert np.array_equal(a.lengths, b.lengths) and np.array_equal(a.means, b.means) and np.array_equal(a.draws, b.draws)
+    for u in range(len(off) - 1):
+        s0, s1 = int(a.seg_offsets[u]), int(a.seg_offsets[u + 1])
+        lens = a.lengths[s0:s1]
+        assert lens.min() >= 1 and int(lens.sum()) == int(off[u + 1] - off[u])
+        pos = int(off[u])
+        for k, ln in enumerate(lens):
+            sw = np.cumsum(w[pos:pos + ln])[-1]
+            swx = np.cumsum(w[pos:pos + ln] * x[pos:pos + ln])[-1]  # sequential, like CBS.cpp:1093-1095
+            assert a.means[s0 + k] == swx / sw, (u, k)
+            pos += int(ln)
+    cutu = 10
+    c1 = ctx.segment_weighted_batch(x[:off[cutu]], w[:off[cutu]], off[:cutu + 1], gp, unit_ids=ids[:cutu])
+    c2 = ctx.segment_weighted_batch(x[off[cutu]:], w[off[cutu]:], off[cutu:] - off[cutu], gp, unit_ids=ids[cutu:])
+    assert np.array_equal(np.concatenate([c1.lengths, c2.lengths]), a.lengths)
+    assert np.array_equal(np.concatenate([c1.means, c2.means]), a.means)
+    assert np.array_equal(np.concatenate([c1.draws, c2.draws]), a.draws)
+    p = SegParams(nperm=10000, alpha=0.01, do_smooth=False, seed=1)
+    for u in np.argsort(np.diff(off))[:2]:
+        u = int(u)
+        rng = oracle.rng_mt(1)
+        wl, wm = oracle.segment_weighted(x[off[u]:off[u + 1]], w[off[u]:off[u + 1]], p, rng)
+        s0, s1 = int(a.seg_offsets[u]), int(a.seg_offsets[u + 1])
+        assert np.array_equal(a.lengths[s0:s1], wl) and np.array_equal(a.means[s0:s1], wm)
+        assert int(a.draws[u]) == int(rng.draws)
