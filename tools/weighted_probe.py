@@ -23,6 +23,7 @@ def main():
     ap.add_argument("--scale", type=float, default=1.0)
     ap.add_argument("--reps", type=int, default=3)
     ap.add_argument("--nperm", type=int, default=10000)
+    ap.add_argument("--no-warmup", action="store_true", help="skip the small warm-up call (ncu: the first k_wscan<1> launch is then round 1 of the sample)")
     ap.add_argument("--check", action="store_true", help="compare the two smallest chromosomes with the CPU oracle (slow at scale 1)")
     args = ap.parse_args()
     values, off, lab, ids = synth.cohort([0], scale=args.scale)
@@ -31,7 +32,8 @@ def main():
     w = rng.uniform(0.5, 2.0, len(x))  # per-marker weights (DNAcopy: inverse variances)
     p = Params(alpha=0.01, nperm=args.nperm, do_smooth=False, rng_mode=RNG_MT19937_64, chain=False, seed=1)
     ctx = genomic_b200.Context(0)
-    ctx.segment_weighted_batch(x[: off[2]], w[: off[2]], off[:3], p)  # warm-up
+    if not args.no_warmup:
+        ctx.segment_weighted_batch(x[: off[2]], w[: off[2]], off[:3], p)  # warm-up
     times = []
     res = None
     for _ in range(args.reps):
