@@ -1,4 +1,5 @@
-"""Ad-hoc: step time of the bench workload against the permutation batch sizes (first_batch, max_batch)."""
+"""Ad-hoc: step time of the bench workload against the permutation batch sizes (first_batch, max_batch), configurations
+interleaved so that box-level drift affects all of them alike."""
 import os, sys, time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
@@ -7,16 +8,18 @@ import genomic_b200
 from genomic_b200 import Params, RNG_MT19937_64, synth
 ctx = genomic_b200.Context(0)
 vals, off, lab, ids = synth.cohort([0], scale=1.0)
+cfgs = [(256, 4096), (256, 8192), (256, 16384), (320, 8192)]
+ts = {c: [] for c in cfgs}
 ref = None
-for fb, mb in ((256, 4096), (128, 4096), (512, 4096), (1024, 4096), (256, 8192), (512, 8192), (384, 4096), (256, 2048)):
-    gp = Params(nperm=10000, rng_mode=RNG_MT19937_64, chain=False, seed=1, first_batch=fb, max_batch=mb)
-    ts = []
-    for rep in range(7):
+for rep in range(16):
+    for c in cfgs:
+        gp = Params(nperm=10000, rng_mode=RNG_MT19937_64, chain=False, seed=1, first_batch=c[0], max_batch=c[1])
         t0 = time.perf_counter()
         r = ctx.segment_batch(vals, off, gp, unit_ids=ids)
-        ts.append(1e3 * (time.perf_counter() - t0))
-    if ref is None:
-        ref = r
-    same = np.array_equal(r.lengths, ref.lengths) and np.array_equal(r.means, ref.means) and np.array_equal(r.draws, ref.draws)
-    ts.sort()
-    print(f"first_batch={fb:5d} max_batch={mb:5d} median={ts[3]:7.1f} ms min={ts[0]:7.1f} rounds={r.rounds} perms={r.perms_run} elems={r.perm_elems} same={same}", flush=True)
+        ts[c].append(1e3 * (time.perf_counter() - t0))
+        if ref is None:
+            ref = r
+        assert np.array_equal(r.lengths, ref.lengths) and np.array_equal(r.means, ref.means) and np.array_equal(r.draws, ref.draws)
+for c in cfgs:
+    v = sorted(ts[c][1:])
+    print(f"first_batch={c[0]:5d} max_batch={c[1]:6d} median={v[len(v)//2]:7.1f} ms  p25={v[len(v)//4]:7.1f}  min={v[0]:7.1f}  mean={sum(v)/len(v):7.1f}", flush=True)
