@@ -175,3 +175,22 @@ def test_weighted_full_size_sample_properties(ctx, oracle):
         s0, s1 = int(a.seg_offsets[u]), int(a.seg_offsets[u + 1])
         assert np.array_equal(a.lengths[s0:s1], wl) and np.array_equal(a.means[s0:s1], wm)
         assert int(a.draws[u]) == int(rng.draws)
+
+
+def test_weighted_edge_inputs(ctx, ref):
+    # constant data (all-equal shortcut, CBS.cpp:1051), units shorter than 2*min_width, n = 1, wide-ranging weights
+    rng = np.random.default_rng(79)
+    p = SegParams(nperm=200, alpha=0.05, min_width=3, do_smooth=False, seed=3)
+    cases = [(np.full(40, 0.25), rng.uniform(0.5, 2.0, 40)), (np.array([0.1]), np.array([1.0])),
+             (np.array([0.1, 0.2, 0.3, 0.4, 0.5]), np.ones(5)), (np.r_[np.zeros(30), np.ones(30)], np.ones(60))]
+    for k in range(6):
+        n = int(rng.integers(60, 900))
+        x = make_unit(rng, n, k % 4)
+        cases.append((x, 10.0 ** rng.uniform(-3, 3, n)))
+    for i, (x, w) in enumerate(cases):
+        eng = ref.rng(p.seed)
+        wl, wm = ref.segment_weighted(x, w, p, eng)
+        gl, gm, draws = ctx.segment_weighted(x, w, gparams(p, first_batch=32))
+        assert np.array_equal(gl, wl), (i, gl, wl)
+        assert np.array_equal(gm, wm), i
+        assert ref.rng_equals(eng, p.seed, draws), i
