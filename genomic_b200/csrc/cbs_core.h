@@ -278,12 +278,9 @@ struct Dev {
     int n_edgeprep; int* edgeprep_task;
     int n_edge;   EdgeItem* edges; int* edge_prefix;  // exclusive prefix of threads, [n_edge+1]
     int n_gen;    int* gen_chain;
-    // shuffle work lists by segment-length class (shuffle_class below): 0..6 index arrays in shared
-    // memory (16-bit), 7 = longer than 65535 markers (32-bit index array in the arena)
+    // shuffle work lists by segment-length class (shuffle_class below)
     int n_shuf[SHUF_NCLS_MAX]; int* shuf_item[SHUF_NCLS_MAX]; int* shuf_prefix[SHUF_NCLS_MAX];
-    int* shuf_p0[SHUF_NCLS_MAX];   // first permutation of the item that the entry covers (an item can be split between its
-                       // shared-memory class and the L2 shuffle)
-    int shuf_cap[SHUF_NCLS_MAX];   // permutations of the class that fit on the GPU at once (0: never spill to the L2 shuffle)
+    int* shuf_p0[SHUF_NCLS_MAX];   // first permutation of the item that the entry covers
     // work-stealing counters (reset every round): 0 global shuffle, 1 scan, 2 edge, 3 prefix, 4 hscan,
     // 8+cls shared-memory shuffle of class cls
     unsigned ctr[24];
@@ -305,24 +302,19 @@ struct Dev {
 
 enum { ERR_TASK_CAP = 101, ERR_SEG_CAP = 102, ERR_ARENA = 103, ERR_SPLIT_CAP = 104, ERR_INTERNAL = 105, ERR_STALL = 106, ERR_STREAM_CAP = 107 };
 
-// Shuffle classes.  0..7: the permutation is built on a 16-bit index array in shared memory, one warp per
-// permutation; the class fixes the array size, hence how many permutations an SM holds at once.  The limits are
-// the longest segments for which 22 / 8 / 6 / 5 / 4 / 3 / 2 / 1 arrays (plus 8.5 KB of scratch each) fit in the
-// 227 KB of an SM.  8: 32-bit index array in the arena (L2 / HBM latency per step).
-enum { SHUF_NCLS = 9, SHUF_GLOBAL = 8 };
+// Shuffle classes (shuffle.cuh).  0..5: one CTA per permutation, last[] (16 bit per marker) and the claim table in
+// shared memory; the class fixes the CTA size and the array size, hence how many permutations an SM holds at once
+// (16 / 8 / 4 / 3 / 2 / 1 CTAs).  6: segments of more than 65535 markers.
+enum { SHUF_NCLS = 7, SHUF_GLOBAL = 6 };
 CBS_HD int shuffle_class_max(int cls) {
-    return cls == 0 ? 4096 : cls == 1 ? 8192 : cls == 2 ? 14500 : cls == 3 ? 18400 : cls == 4 ? 24200 : cls == 5 ? 33900
-         : cls == 6 ? 53200 : 65535;
+    return cls == 0 ? 2048 : cls == 1 ? 8192 : cls == 2 ? 20000 : cls == 3 ? 29500 : cls == 4 ? 48500 : 65535;
 }
+CBS_HD int shuffle_class_threads(int cls) { return cls == 0 ? 128 : cls == 1 ? 256 : cls <= 4 ? 512 : 1024; }
+CBS_HD int shuffle_class_hbits(int cls) { return cls <= 1 ? 11 : cls <= 4 ? 12 : 13; }  // log2 of the claim-table slots
 CBS_HD int shuffle_class(int n) {
     for (int cls = 0; cls < SHUF_GLOBAL; ++cls) if (n <= shuffle_class_max(cls)) return cls;
     return SHUF_GLOBAL;
 }
-
-// A shared-memory class holds few permutations at once (1..4 per SM from class 3 on).  When a round brings more than
-// SHUF_WAVES times that many, the rest of a batch goes to the L2 shuffle: slower per permutation, but thousands run at
-// once, so both parts finish at about the same time.
-enum { SHUF_SPILL_MIN = 4, SHUF_WAVES = 4, SHUF_SPILL_LEAST = 64 };
 
 // ------------------------------------------------------------------------------------
 // Scheduler (runs in ONE thread per round; plain sequential C++ so that the very same
@@ -335,10 +327,7 @@ struct Sched {
     int* out_list;
     int n_out;
     long long arena_used, rej_used, draws_used;
-    int shuf_used[SHUF_NCLS];  // permutations given to each shared-memory class this round
-    CBS_HD explicit Sched(Dev& d) : D(d), out_list(nullptr), n_out(0), arena_used(0), rej_used(0), draws_used(0) {
-        for (int k = 0; k < SHUF_NCLS; ++k) shuf_used[k] = 0;
-    }
+    CBS_HD explicit Sched(Dev& d) : D(d), out_list(nullptr), n_out(0), arena_used(0), rej_used(0), draws_used(0) {}
 
     CBS_HD int alloc_task() {
         if (D.free_head == D.free_tail) { D.error = ERR_TASK_CAP; return -1; }
@@ -499,8 +488,8 @@ struct Sched {
         if (want > p.max_batch) want = p.max_batch;
         if (want > p.nperm - t.perms_done) want = p.nperm - t.perms_done;
         const int cls = shuffle_class(t.n);
-        // the global-memory shuffle keeps a 32-bit index array per permutation in the arena
-        const long long idxd = (cls >= SHUF_SPILL_MIN) ? idx_stride(t.n) : 0;  // doubles per permutation (if it goes to L2)
+        // the shuffle of segments > 65535 markers keeps a 32-bit array per permutation in the arena
+        const long long idxd = (cls == SHUF_GLOBAL) ? idx_stride(t.n) : 0;  // doubles per permutation
         const long long per = idxd + sx_stride(t.n) + bs_stride(t.nb);
         const bool mtwin = p.rng_mode == RNG_MT && !D.shared_stream;
         // never let one task take more than half of the arena
@@ -513,14 +502,7 @@ struct Sched {
             if (by_span < 1) { D.error = ERR_ARENA; return false; }
             if (want > by_span) want = (int)by_span;
         }
-        // how many of the batch go to the L2 shuffle
-        int gpart = (cls == SHUF_GLOBAL) ? want : 0;
-        if (cls != SHUF_GLOBAL && cls >= SHUF_SPILL_MIN && D.shuf_cap[cls] > 0) {
-            const int room = SHUF_WAVES * D.shuf_cap[cls] - shuf_used[cls];
-            const int spart = want < room ? want : (room > 0 ? room : 0);
-            gpart = want - spart;
-            if (gpart < SHUF_SPILL_LEAST) gpart = 0;
-        }
+        const int gpart = (cls == SHUF_GLOBAL) ? want : 0;
         const long long need = idxd * gpart + (sx_stride(t.n) + bs_stride(t.nb)) * want;
         const long long dneed = (p.rng_mode == RNG_MT) ? (long long)want * t.n : 0;
         if (arena_used + need > D.arena_cap || rej_used + want > D.rej_cap || (mtwin && draws_used + dneed + 312 > D.draws_cap)) {
@@ -557,7 +539,6 @@ struct Sched {
             D.shuf_item[cls][q] = D.n_items; D.shuf_p0[cls][q] = 0;
             D.shuf_prefix[cls][q + 1] = D.shuf_prefix[cls][q] + (want - gpart);
             D.n_shuf[cls] = q + 1;
-            shuf_used[cls] += want - gpart;
         }
         if (gpart > 0) {  // permutations [want-gpart, want): L2 shuffle (all of them for segments > 65535 markers)
             const int q = D.n_shuf[SHUF_GLOBAL];
@@ -774,7 +755,6 @@ struct Sched {
         for (int k = 0; k < SHUF_NCLS; ++k) { D.n_shuf[k] = 0; D.shuf_prefix[k][0] = 0; }
         for (int k = 0; k < 24; ++k) D.ctr[k] = 0;
         arena_used = 0; rej_used = 0; draws_used = 0;
-        for (int k = 0; k < SHUF_NCLS; ++k) shuf_used[k] = 0;
         const bool mt = D.prm.rng_mode == RNG_MT;
         if (D.shared_stream && D.gen_E > 0) { D.stream_len = D.gen_base + D.gen_E; D.gen_E = 0; }
         int wpos = 0;

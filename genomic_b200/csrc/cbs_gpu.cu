@@ -147,6 +147,8 @@ struct LaunchTimer {
 };
 
 void collect_timers(cbs_gpu_ctx* c) {
+    // CBS_GPU_DEBUG_ROUNDS=1: timeline of the call on stderr, one line per round: kernel=start+duration in ms relative to the
+    // first launch (launches shorter than 0.05 ms are left out)
     const bool dump = getenv("CBS_GPU_DEBUG_ROUNDS") != nullptr;
     static const char* names[] = {"sched", "gen", "prep", "perm", "scan", "edgeprep", "edgeperm", "means", "smooth", "shuf0", "shuf1", "shuf2", "shuf3", "prefix"};
     int round = 0;
@@ -154,8 +156,10 @@ void collect_timers(cbs_gpu_ctx* c) {
         float ms = 0.f;
         if (cudaEventElapsedTime(&ms, c->ev_pool[u.second], c->ev_pool[u.second + 1]) == cudaSuccess) c->kms[u.first] += ms;
         if (dump) {
-            if (u.first == K_SCHED) fprintf(stderr, "\n[round %d]", round++);
-            if (ms > 0.05f) fprintf(stderr, " %s=%.2f", names[u.first], ms);
+            float at = 0.f;
+            cudaEventElapsedTime(&at, c->ev_pool[c->ev_used[0].second], c->ev_pool[u.second]);
+            if (u.first == K_SCHED) fprintf(stderr, "\n[round %d @%.2f]", round++, at);
+            if (ms > 0.05f) fprintf(stderr, " %s=%.2f+%.2f", names[u.first], at, ms);
         }
     }
     if (dump) fprintf(stderr, "\n");
@@ -262,10 +266,30 @@ bool pick_scan_warps(cbs_gpu_ctx* c, ScanLayout& lay, int* occ_out) {
     return true;
 }
 
-// shared-memory shuffle classes: dynamic shared memory of a CTA (one warp, one permutation) and CTAs per SM
-size_t shuffle_smem_bytes(int cls) { return (size_t)shuffle_class_max(cls) * 2 + 32 + FY_SCRATCH; }
-int shuffle_occupancy(const cbs_gpu_ctx* c, int cls) {
-    return (int)std::max<size_t>(1, std::min<size_t>(32, (c->smem_optin + 1024) / (shuffle_smem_bytes(cls) + 1024)));
+// shared-memory shuffle classes (cbs_core.h): dynamic shared memory of a CTA = claim table + last[] of the longest segment
+size_t shuffle_smem_bytes(int cls) { return ((size_t)4 << shuffle_class_hbits(cls)) + (((size_t)shuffle_class_max(cls) + 2) * 2 + 15) / 16 * 16; }
+void launch_shuffle(Dev* dD, int cls, int grid, cudaStream_t ss) {
+    const size_t smem = shuffle_smem_bytes(cls);
+    const int hb = shuffle_class_hbits(cls);
+    switch (shuffle_class_threads(cls)) {
+    case 128: k_shuffle<128, 2><<<grid, 128, smem, ss>>>(dD, cls, hb); break;
+    case 256: k_shuffle<256, 2><<<grid, 256, smem, ss>>>(dD, cls, hb); break;
+    case 512: k_shuffle<512, 2><<<grid, 512, smem, ss>>>(dD, cls, hb); break;
+    default: k_shuffle<1024, 2><<<grid, 1024, smem, ss>>>(dD, cls, hb); break;
+    }
+}
+int shuffle_occupancy(int cls) {
+    int occ = 0;
+    const size_t smem = shuffle_smem_bytes(cls);
+    cudaError_t e;
+    switch (shuffle_class_threads(cls)) {
+    case 128: e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_shuffle<128, 2>, 128, smem); break;
+    case 256: e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_shuffle<256, 2>, 256, smem); break;
+    case 512: e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_shuffle<512, 2>, 512, smem); break;
+    default: e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_shuffle<1024, 2>, 1024, smem); break;
+    }
+    if (e != cudaSuccess) { cudaGetLastError(); occ = 1; }
+    return std::max(1, occ);
 }
 
 struct RunCaps {
@@ -435,13 +459,6 @@ int run_cbs(cbs_gpu_ctx* c, const std::vector<long long>& off, const uint64_t* u
         CUDA_TRY(c, cudaStreamSynchronize(st));
         if (bad) return fail(c, CBS_GPU_ERR_INVALID, "weights must be finite and positive");
     }
-    // permutations a shared-memory shuffle class holds on the GPU at once (the scheduler spills oversized batches of the
-    // classes with few resident permutations to the L2 shuffle)
-    for (int cls = 0; cls < SHUF_NCLS; ++cls) hD.shuf_cap[cls] = 0;
-    if (env_ll("CBS_GPU_SPILL", 0) || getenv("CBS_GPU_SPILL_CAP"))  // opt-in: measured slower on B200 (the L2 shuffle is DRAM bound)
-        for (int cls = SHUF_SPILL_MIN; cls < SHUF_GLOBAL; ++cls)
-            hD.shuf_cap[cls] = (int)env_ll("CBS_GPU_SPILL_CAP", (long long)c->sm_count * shuffle_occupancy(c, cls));  // override: tests
-
     CUDA_TRY(c, cudaMemcpyAsync(c->unit_off.p, off.data(), sizeof(long long) * (size_t)(n_units + 1), cudaMemcpyHostToDevice, st));
     if (unit_ids) CUDA_TRY(c, cudaMemcpyAsync(c->unit_ids.p, unit_ids, sizeof(uint64_t) * (size_t)n_units, cudaMemcpyHostToDevice, st));
     {
@@ -474,14 +491,13 @@ int run_cbs(cbs_gpu_ctx* c, const std::vector<long long>& off, const uint64_t* u
     const int scan_grid = c->sm_count * scan_occ;
 
     // shared-memory shuffle kernel, one launch per segment-length class present in this call
-    size_t shuf_smem[SHUF_GLOBAL]; int shuf_occ[SHUF_GLOBAL]; bool shuf_on[SHUF_GLOBAL];
+    int shuf_occ[SHUF_GLOBAL]; bool shuf_on[SHUF_GLOBAL];
     for (int cls = 0; cls < SHUF_GLOBAL; ++cls) {
-        shuf_smem[cls] = shuffle_smem_bytes(cls);
         shuf_on[cls] = (cls == 0) || Nmax > shuffle_class_max(cls - 1);  // no unit is long enough otherwise
-        shuf_occ[cls] = shuffle_occupancy(c, cls);
+        shuf_occ[cls] = shuf_on[cls] ? shuffle_occupancy(cls) : 1;
     }
-    const bool l2_shuffle_on = Nmax > shuffle_class_max(SHUF_SPILL_MIN - 1);  // own class (> 65535) or spilled batches
-    static const int kShufTimer[SHUF_GLOBAL] = {K_SHUF0, K_SHUF1, K_SHUF1, K_SHUF1, K_SHUF2, K_SHUF2, K_SHUF3, K_SHUF3};
+    const bool l2_shuffle_on = Nmax > shuffle_class_max(SHUF_GLOBAL - 1);
+    static const int kShufTimer[SHUF_GLOBAL] = {K_SHUF0, K_SHUF1, K_SHUF2, K_SHUF2, K_SHUF3, K_SHUF3};
 
     // ---- rounds -------------------------------------------------------------------------------
     *c->h_done = 0;
@@ -506,8 +522,6 @@ int run_cbs(cbs_gpu_ctx* c, const std::vector<long long>& off, const uint64_t* u
             cudaEventRecord(c->ev_side[0], c->side[0]);
             cudaStreamWaitEvent(c->side[1], c->ev_sched, 0);
             { LaunchTimer t(c, K_EDGEPREP, c->side[1]); if (weighted) k_wedgeprep<<<c->sm_count * 4, 32, 0, c->side[1]>>>(dD); else k_edgeprep<<<c->sm_count * 4, 32, 0, c->side[1]>>>(dD); }
-            { LaunchTimer t(c, K_EDGEPERM, c->side[1]); if (weighted) k_wedgeperm<<<c->sm_count * 4, 128, 0, c->side[1]>>>(dD); else k_edgeperm<<<c->sm_count * 4, 128, 0, c->side[1]>>>(dD); }
-            cudaEventRecord(c->ev_side[1], c->side[1]);
             if (mt) {
                 LaunchTimer t(c, K_GEN);
                 if (shared_stream) {
@@ -516,6 +530,10 @@ int run_cbs(cbs_gpu_ctx* c, const std::vector<long long>& off, const uint64_t* u
                 } else k_gen<<<std::min(std::max(1, n_chains), c->sm_count * 4), 192, 0, st>>>(dD);
             }
             cudaEventRecord(c->ev_gen, st);
+            // the edge permutations read this round's draws (plan_edge asked the generator for them): after the generator
+            if (mt) cudaStreamWaitEvent(c->side[1], c->ev_gen, 0);
+            { LaunchTimer t(c, K_EDGEPERM, c->side[1]); if (weighted) k_wedgeperm<<<c->sm_count * 4, 128, 0, c->side[1]>>>(dD); else k_edgeperm<<<c->sm_count * 4, 128, 0, c->side[1]>>>(dD); }
+            cudaEventRecord(c->ev_side[1], c->side[1]);
             if (mt && shared_stream && hD.jump_polys) {
                 // generate ahead for the next round, next to this round's shuffles and scan
                 cudaStreamWaitEvent(c->gen_stream, c->ev_gen, 0);
@@ -543,7 +561,7 @@ int run_cbs(cbs_gpu_ctx* c, const std::vector<long long>& off, const uint64_t* u
                     cudaStream_t ss = where == 0 ? st : c->side[1 + where];
                     if (where != 0 && !used_side[1 + where]) { cudaStreamWaitEvent(ss, c->ev_gen, 0); used_side[1 + where] = true; }
                     LaunchTimer t(c, kShufTimer[cls], ss);
-                    k_perm_smem<<<c->sm_count * shuf_occ[cls], 32, shuf_smem[cls], ss>>>(dD, cls);
+                    launch_shuffle(dD, cls, c->sm_count * shuf_occ[cls], ss);
                 }
             }
             for (int k = 2; k < 5; ++k) if (used_side[k]) { cudaEventRecord(c->ev_side[k], c->side[k]); cudaStreamWaitEvent(st, c->ev_side[k], 0); }
@@ -760,7 +778,10 @@ int cbs_gpu_create(const int* device_ids, int ndev, cbs_gpu_ctx** out) {
     // function attributes are process-wide per device: set them once to the device maximum, never per call
     // (concurrent lanes with different needs would otherwise shrink each other's limit)
     if (cudaFuncSetAttribute(k_scan, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_optin) != cudaSuccess ||
-        cudaFuncSetAttribute(k_perm_smem, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_optin) != cudaSuccess) {
+        cudaFuncSetAttribute(k_shuffle<128, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_optin) != cudaSuccess ||
+        cudaFuncSetAttribute(k_shuffle<256, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_optin) != cudaSuccess ||
+        cudaFuncSetAttribute(k_shuffle<512, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_optin) != cudaSuccess ||
+        cudaFuncSetAttribute(k_shuffle<1024, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_optin) != cudaSuccess) {
         delete c;
         return CBS_GPU_ERR_CUDA;
     }

@@ -16,6 +16,7 @@
 #include <cuda_runtime.h>
 
 #include "cbs_threads.h"
+#include "shuffle.cuh"
 
 namespace cbsg {
 
@@ -698,24 +699,43 @@ __device__ void perm_warp(Dev* D, const Task& t, int p, Idx s_idx, unsigned char
     __syncwarp();
 }
 
-__global__ void __launch_bounds__(32) k_perm_smem(Dev* D, int cls) {
+// k_shuffle: xperm (CBS.cpp:487-493) for segments of up to 65535 markers, one CTA per permutation (shuffle.cuh):
+// exact parallel replay of the Fisher-Yates, last[] (16 bit per marker) and the claim table in shared memory; the
+// permuted values go straight into the S row of the permutation (k_chain turns them into prefix sums in place).
+template <int T, int K>
+__global__ void __launch_bounds__(T) k_shuffle(Dev* D, int cls, int hbits) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    unsigned char* tab = smem_raw;  // FY_SCRATCH bytes, then the index array
-    unsigned short* s_idx = (unsigned short*)(smem_raw + FY_SCRATCH);
+    __shared__ int s_g;
+    unsigned* claim = (unsigned*)smem_raw;
+    unsigned short* last = (unsigned short*)(smem_raw + ((size_t)4 << hbits));
     if (D->done) return;
-    const int lane = threadIdx.x;
-    for (int k = lane; k < FY_SCRATCH - FY_TAB; k += 32) tab[FY_TAB + k] = 0;
-    __syncwarp();
+    const int hmask = (1 << hbits) - 1;
+    for (int k = threadIdx.x; k <= hmask; k += T) claim[k] = 0u;
+    unsigned epoch = 0;
     const int nl = D->n_shuf[cls];
     const int total = D->shuf_prefix[cls][nl];
+    const bool mt = D->prm.rng_mode == RNG_MT;
     for (;;) {
-        int g = 0;
-        if (lane == 0) g = (int)atomicAdd(&D->ctr[8 + cls], 1u);
-        g = __shfl_sync(FULL, g, 0);
+        __syncthreads();
+        if (threadIdx.x == 0) s_g = (int)atomicAdd(&D->ctr[8 + cls], 1u);
+        __syncthreads();
+        const int g = s_g;
         if (g >= total) break;
         const int k = find_item(D->shuf_prefix[cls], nl, g);
         const PermItem it = D->items[D->shuf_item[cls][k]];
-        perm_warp(D, D->tasks[it.task], D->shuf_p0[cls][k] + (g - D->shuf_prefix[cls][k]), IdxSmem{s_idx}, tab, lane);
+        const Task& t = D->tasks[it.task];
+        const int p = D->shuf_p0[cls][k] + (g - D->shuf_prefix[cls][k]);
+        const int n = t.n;
+        const long long base = D->unit_off[t.unit] + t.lo;
+        ShufDraws src;
+        src.mt = mt;
+        src.win = mt ? (D->shared_stream ? D->stream : D->draws[D->round & 1]) + t.off_draw + (long long)p * n : nullptr;
+        src.k0 = (uint32_t)t.key; src.k1 = (uint32_t)(t.key >> 32); src.permno = (uint32_t)(t.perms_done + p);
+        double* sx = D->arena + t.off_sx + (long long)p * Sched::sx_stride(n);
+        // weighted CBS (wxperm, CBS.cpp:538-547): the shuffle runs on y = cur*rw, position i-1 receives y[.]/rw[i-1]
+        const double* vals = D->w ? D->ycur + base : D->cur + base;
+        const double* rdiv = D->w ? D->rw + base : nullptr;
+        shuffle_cta<T, K>(LastSmem16{last}, claim, hmask, epoch, n, src, vals, rdiv, sx);
     }
 }
 

@@ -245,20 +245,6 @@ def test_segment_long_units(ctx, oracle, mode):
     check_batch(ctx, oracle, vals, off, p, first_batch=24, max_batch=64)
 
 
-@pytest.mark.parametrize("mode", ["mt_unit", "philox"])
-def test_batches_spilled_to_l2_shuffle(ctx, oracle, mode, monkeypatch):
-    # oversized batches of a shared-memory shuffle class are split: the first part is shuffled in shared memory, the rest
-    # by the L2 shuffle.  The capacity is forced down so that small batches already split.
-    monkeypatch.setenv("CBS_GPU_SPILL_CAP", "8")
-    rng = np.random.default_rng(62)
-    units = [f32(rng.normal(0, 0.2, n)) for n in (20000, 30000, 40000)]
-    units[0][7000:] += 0.02
-    units[2][:15000] -= 0.015
-    vals, off = pack(units)
-    p = SegParams(nperm=300, alpha=0.05, do_smooth=False, rng_kind=1 if mode == "philox" else 0, chain=False, seed=9)
-    check_batch(ctx, oracle, vals, off, p, first_batch=128, max_batch=256)
-
-
 def test_stress_50k_segments_replay(ctx, oracle):
     """BASELINE configs[4] in small: units of exactly 50,000 markers, deterministic MT replay.  (i) pure null: the
     permutation loop stops at the early exit; (ii) a shift at 25,000 small enough (t ~ 5.6 < 7) that fndcpt does not
