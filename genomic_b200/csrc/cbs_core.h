@@ -61,8 +61,23 @@ CBS_HD double canonical_from_u64(uint64_t v) {
     if (u >= 1.0) u = 0.99999999999999988897769753748434595763683319091796875;
     return u;
 }
-// j = int(u*i) + 1 (CBS.cpp:490,528); returns 1-based index
-CBS_HD int draw_index(uint64_t v, int i) { return (int)(canonical_from_u64(v) * (double)i) + 1; }
+// j = int(u*i) + 1 (CBS.cpp:490,528); returns 1-based index.
+// The reference's expression needs a u64 -> f64 conversion and an f64 -> int truncation per draw; on B200 these run on
+// the XU pipe at about half a lane per clock and SM, which made the shuffle kernels XU bound.  The same integer comes
+// out of integer arithmetic: with r = v*i/2^64 exactly, the double computation yields p = RNE(RNE(v)*2^-64 * i) with
+// |p - r| <= i*2^-54 + ulp(p)/2 <= 2^-33 for i <= 2^20 (the clamp below 1 moves u by at most 2^-53), so
+// floor(p) == floor(r) whenever frac(r) lies in [2^-32, 1 - 2^-32); only then is the fast path taken (all but one draw
+// in 2^31), otherwise the reference's own floating-point expression is evaluated.
+CBS_HD int draw_index(uint64_t v, int i) {
+    if (i <= (1 << 20)) {
+        const uint64_t a = (uint64_t)(uint32_t)v * (uint64_t)(uint32_t)i;
+        const uint64_t b = (v >> 32) * (uint64_t)(uint32_t)i;
+        const uint64_t s = b + (a >> 32);  // floor(v*i / 2^32): integer part of r in the high word, top 32 fraction bits below
+        const uint32_t f = (uint32_t)s;
+        if (f - 1u < 0xFFFFFFFEu) return (int)(s >> 32) + 1;
+    }
+    return (int)(canonical_from_u64(v) * (double)i) + 1;
+}
 
 CBS_HD void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1,
                           uint32_t out[4]) {
@@ -290,6 +305,7 @@ struct Dev {
     int error;  // 0 ok; see cbs_gpu.h status codes
     unsigned long long stat_perms, stat_rounds_active;
     unsigned long long stat_perm_elems;     // sum over max-t permutations of the segment length
+    unsigned long long round_elems[64], round_perms[64];  // per round (first 64): planned permutations and their markers (timeline)
     int profile;                            // count scan work (bench / roofline)
     unsigned long long stat_slots, stat_arcs;  // arc slots issued by the scan fast path / of them real arcs
     // ---- weighted CBS (cbs::segment_weighted, CBS.cpp:1026-1099); w == nullptr otherwise ----------
@@ -297,6 +313,9 @@ struct Dev {
     double* rw;       // sqrt(w) (CBS.cpp:1056)
     double* cw;       // per pending segment, at the segment's offset: cumsum(w)/sqrt(sum w) (CBS.cpp:1062-1066)
     double* ycur;     // cur * rw: what wxperm shuffles (CBS.cpp:540)
+    int shuf_cl2;     // segments of 65536..SHUF_CL2_MAX markers have their own class (cluster of 2 CTAs)
+    int shuf_arena;   // segments > 65535 markers are shuffled by k_perm on 32-bit index arrays in the arena (fallback of k_shuffle_cluster)
+    int stats_in_scan;  // rows of permutations come from k_chain32 without statistics: k_scan computes them (as for observed rows)
     int no_early;     // CBS_GPU_NO_EARLY=1: decision-mode scans never stop at the first rejecting arc (A/B switch)
 };
 
@@ -304,16 +323,17 @@ enum { ERR_TASK_CAP = 101, ERR_SEG_CAP = 102, ERR_ARENA = 103, ERR_SPLIT_CAP = 1
 
 // Shuffle classes (shuffle.cuh).  0..5: one CTA per permutation, last[] (16 bit per marker) and the claim table in
 // shared memory; the class fixes the CTA size and the array size, hence how many permutations an SM holds at once
-// (16 / 8 / 4 / 3 / 2 / 1 CTAs).  6: segments of more than 65535 markers.
-enum { SHUF_NCLS = 7, SHUF_GLOBAL = 6 };
+// (16 / 8 / 4 / 3 / 2 / 1 CTAs).  6, 7: segments of more than 65535 markers, last[] (32 bit per marker) spread over
+// the shared memory of a cluster of 2 (up to SHUF_CL2_MAX markers) or more CTAs.
+enum { SHUF_NCLS = 8, SHUF_CL2 = 6, SHUF_GLOBAL = 7, SHUF_CL2_MAX = 105000 };
 CBS_HD int shuffle_class_max(int cls) {
-    return cls == 0 ? 2048 : cls == 1 ? 8192 : cls == 2 ? 20000 : cls == 3 ? 29500 : cls == 4 ? 48500 : 65535;
+    return cls == 0 ? 2048 : cls == 1 ? 8192 : cls == 2 ? 20000 : cls == 3 ? 29500 : cls == 4 ? 48500 : cls == 5 ? 65535 : SHUF_CL2_MAX;
 }
 CBS_HD int shuffle_class_threads(int cls) { return cls == 0 ? 128 : cls == 1 ? 256 : cls <= 4 ? 512 : 1024; }
 CBS_HD int shuffle_class_hbits(int cls) { return cls <= 1 ? 11 : cls <= 4 ? 12 : 13; }  // log2 of the claim-table slots
-CBS_HD int shuffle_class(int n) {
-    for (int cls = 0; cls < SHUF_GLOBAL; ++cls) if (n <= shuffle_class_max(cls)) return cls;
-    return SHUF_GLOBAL;
+CBS_HD int shuffle_class(int n, bool cl2) {
+    for (int cls = 0; cls < SHUF_CL2; ++cls) if (n <= shuffle_class_max(cls)) return cls;
+    return (cl2 && n <= SHUF_CL2_MAX) ? SHUF_CL2 : SHUF_GLOBAL;
 }
 
 // ------------------------------------------------------------------------------------
@@ -487,9 +507,9 @@ struct Sched {
         }
         if (want > p.max_batch) want = p.max_batch;
         if (want > p.nperm - t.perms_done) want = p.nperm - t.perms_done;
-        const int cls = shuffle_class(t.n);
-        // the shuffle of segments > 65535 markers keeps a 32-bit array per permutation in the arena
-        const long long idxd = (cls == SHUF_GLOBAL) ? idx_stride(t.n) : 0;  // doubles per permutation
+        const int cls = shuffle_class(t.n, D.shuf_cl2 != 0);
+        // fallback shuffle of segments > 65535 markers (k_perm): a 32-bit index array per permutation in the arena
+        const long long idxd = (cls == SHUF_GLOBAL && D.shuf_arena) ? idx_stride(t.n) : 0;  // doubles per permutation
         const long long per = idxd + sx_stride(t.n) + bs_stride(t.nb);
         const bool mtwin = p.rng_mode == RNG_MT && !D.shared_stream;
         // never let one task take more than half of the arena
@@ -807,6 +827,11 @@ struct Sched {
                 if (step(idx)) out_list[wpos++] = idx;
             }
             n_out = wpos;
+        }
+        if (D.round < 64) {
+            unsigned long long pe = 0, pp = 0;
+            for (int k = 0; k < D.n_items; ++k) if (!D.items[k].obs) { pp += (unsigned long long)D.items[k].P; pe += (unsigned long long)D.items[k].P * (unsigned long long)D.tasks[D.items[k].task].n; }
+            D.round_elems[D.round] = pe; D.round_perms[D.round] = pp;
         }
         D.n_active[outl] = n_out;
         D.cur_list = outl;

@@ -9,6 +9,7 @@
 #include <algorithm>
 #include <cstdio>
 #include <cstdlib>
+#include <cstddef>
 #include <cstring>
 #include <string>
 #include <thread>
@@ -449,6 +450,8 @@ int run_cbs(cbs_gpu_ctx* c, const std::vector<long long>& off, const uint64_t* u
         if (c->jump_ready) { hD.jump_polys = c->jump.as<uint64_t>(); hD.span_max = (long long)mtjump::NSEG * mtjump::SEG; }
     }
     hD.profile = c->counting ? 1 : 0;
+    hD.stats_in_scan = env_ll("CBS_GPU_CHAIN_OLD", 0) ? 0 : 1;
+    hD.shuf_arena = 1;  // decided below (cluster shuffle available?) and patched on the device before the first round
     hD.no_early = env_ll("CBS_GPU_NO_EARLY", 0) ? 1 : 0;
     if (weighted) {
         hD.w = c->wts.as<double>(); hD.rw = c->rw.as<double>(); hD.cw = c->cw.as<double>(); hD.ycur = c->ycur.as<double>();
@@ -491,19 +494,56 @@ int run_cbs(cbs_gpu_ctx* c, const std::vector<long long>& off, const uint64_t* u
     const int scan_grid = c->sm_count * scan_occ;
 
     // shared-memory shuffle kernel, one launch per segment-length class present in this call
-    int shuf_occ[SHUF_GLOBAL]; bool shuf_on[SHUF_GLOBAL];
-    for (int cls = 0; cls < SHUF_GLOBAL; ++cls) {
+    int shuf_occ[SHUF_CL2]; bool shuf_on[SHUF_CL2];
+    for (int cls = 0; cls < SHUF_CL2; ++cls) {
         shuf_on[cls] = (cls == 0) || Nmax > shuffle_class_max(cls - 1);  // no unit is long enough otherwise
         shuf_occ[cls] = shuf_on[cls] ? shuffle_occupancy(cls) : 1;
     }
-    const bool l2_shuffle_on = Nmax > shuffle_class_max(SHUF_GLOBAL - 1);
-    static const int kShufTimer[SHUF_GLOBAL] = {K_SHUF0, K_SHUF1, K_SHUF2, K_SHUF2, K_SHUF3, K_SHUF3};
+    const bool l2_shuffle_on = Nmax > shuffle_class_max(SHUF_CL2 - 1);
+    // segments > 65535 markers: a cluster of 2, 4 or 8 CTAs per permutation shares last[] through distributed shared
+    // memory; units too long even for that (or CBS_GPU_SHUF_CLUSTER=0) fall back to k_perm (index arrays in the arena)
+    int cl_R = 0, cl_grid = 0, cl2_grid = 0;
+    const int cl_hbits = 12;
+    size_t cl_smem = 0, cl2_smem = 0;
+    auto cluster_fit = [&](int R, long long nmax, size_t* smem_out) -> int {
+        const size_t smem = ((size_t)4 << cl_hbits) + 4 * ((size_t)nmax / R + 4);
+        if (smem > c->smem_optin) return 0;
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(c->sm_count / R * R); cfg.blockDim = dim3(1024); cfg.dynamicSmemBytes = smem;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = R; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        cfg.attrs = at; cfg.numAttrs = 1;
+        int ncl = 0;
+        cudaError_t e = R == 2 ? cudaOccupancyMaxActiveClusters(&ncl, k_shuffle_cluster<1024, 4, 2>, &cfg)
+                      : R == 4 ? cudaOccupancyMaxActiveClusters(&ncl, k_shuffle_cluster<1024, 4, 4>, &cfg)
+                               : cudaOccupancyMaxActiveClusters(&ncl, k_shuffle_cluster<1024, 4, 8>, &cfg);
+        if (e != cudaSuccess || ncl < 1) { cudaGetLastError(); return 0; }
+        *smem_out = smem;
+        return ncl * R;
+    };
+    if (l2_shuffle_on && env_ll("CBS_GPU_SHUF_CLUSTER", 1)) {
+        if (Nmax > SHUF_CL2_MAX) {
+            for (int R : {4, 8}) { cl_grid = cluster_fit(R, Nmax, &cl_smem); if (cl_grid) { cl_R = R; break; } }
+        } else cl_R = -1;  // nothing longer than the cluster-of-2 class
+        if (cl_R) cl2_grid = cluster_fit(2, std::min<long long>(Nmax, SHUF_CL2_MAX), &cl2_smem);
+        if (cl_R < 0) { cl_R = cl2_grid ? 2 : 0; }
+    }
+    static const int kShufTimer[SHUF_CL2] = {K_SHUF0, K_SHUF1, K_SHUF2, K_SHUF2, K_SHUF3, K_SHUF3};
+
+    if (cl_R) {
+        hD.shuf_arena = 0;
+        hD.shuf_cl2 = cl2_grid ? 1 : 0;
+        CUDA_TRY(c, cudaMemcpyAsync((char*)dD + offsetof(Dev, shuf_arena), &hD.shuf_arena, sizeof(int), cudaMemcpyHostToDevice, st));
+        CUDA_TRY(c, cudaMemcpyAsync((char*)dD + offsetof(Dev, shuf_cl2), &hD.shuf_cl2, sizeof(int), cudaMemcpyHostToDevice, st));
+        CUDA_TRY(c, cudaStreamSynchronize(st));
+    }
 
     // ---- rounds -------------------------------------------------------------------------------
     *c->h_done = 0;
     const int G = 16;  // rounds per group; two groups are kept in flight, so a typical call (20-30 rounds) is enqueued up front and
                        // host scheduling jitter cannot starve the GPU (the surplus rounds are empty launches, ~0.1 ms each)
     const bool debug = env_ll("CBS_GPU_DEBUG", 0) != 0;
+    const bool chain_old = env_ll("CBS_GPU_CHAIN_OLD", 0) != 0;  // A/B: one permutation per warp (lane 0 sums)
     int groups_in_flight = 0, rounds = 0;
     bool ahead_pending = false;
     int gi = 0;
@@ -553,9 +593,12 @@ int run_cbs(cbs_gpu_ctx* c, const std::vector<long long>& off, const uint64_t* u
                     cudaStreamWaitEvent(ss, c->ev_gen, 0);
                     used_side[4] = true;
                     LaunchTimer t(c, K_PERM, ss);
-                    k_perm<<<c->sm_count * 8, 128, 0, ss>>>(dD);
+                    if (cl_R == 4) k_shuffle_cluster<1024, 4, 4><<<cl_grid, 1024, cl_smem, ss>>>(dD, SHUF_GLOBAL, cl_hbits);
+                    else if (cl_R == 8) k_shuffle_cluster<1024, 4, 8><<<cl_grid, 1024, cl_smem, ss>>>(dD, SHUF_GLOBAL, cl_hbits);
+                    else if (cl_R == 0) k_perm<<<c->sm_count * 8, 128, 0, ss>>>(dD);
+                    if (cl2_grid) { k_shuffle_cluster<1024, 4, 2><<<cl2_grid, 1024, cl2_smem, ss>>>(dD, SHUF_CL2, cl_hbits); c->launches++; }
                 }
-                for (int cls = SHUF_GLOBAL - 1; cls >= 0; --cls) {
+                for (int cls = SHUF_CL2 - 1; cls >= 0; --cls) {
                     if (!shuf_on[cls]) continue;
                     const int where = slot++ % 3;  // 0 = main stream, 1,2 = side[2], side[3]
                     cudaStream_t ss = where == 0 ? st : c->side[1 + where];
@@ -565,7 +608,8 @@ int run_cbs(cbs_gpu_ctx* c, const std::vector<long long>& off, const uint64_t* u
                 }
             }
             for (int k = 2; k < 5; ++k) if (used_side[k]) { cudaEventRecord(c->ev_side[k], c->side[k]); cudaStreamWaitEvent(st, c->ev_side[k], 0); }
-            { LaunchTimer t(c, K_PREFIX); if (weighted && p->hybrid) { k_wssq<<<c->sm_count * 8, 128, 0, st>>>(dD); c->launches++; } if (weighted) k_chain<true><<<c->sm_count * 12, CHAIN_WARPS * 32, 0, st>>>(dD); else k_chain<false><<<c->sm_count * 12, CHAIN_WARPS * 32, 0, st>>>(dD); }
+            { LaunchTimer t(c, K_PREFIX); if (weighted && p->hybrid) { k_wssq<<<c->sm_count * 8, 128, 0, st>>>(dD); c->launches++; } if (chain_old) { if (weighted) k_chain<true><<<c->sm_count * 2 * CHAIN_MIN_CTAS, CHAIN_WARPS * 32, 0, st>>>(dD); else k_chain<false><<<c->sm_count * 2 * CHAIN_MIN_CTAS, CHAIN_WARPS * 32, 0, st>>>(dD); }
+              else if (weighted) k_chain32<true><<<c->sm_count * 6, CH32_WARPS * 32, 0, st>>>(dD); else k_chain32<false><<<c->sm_count * 6, CH32_WARPS * 32, 0, st>>>(dD); }
             cudaStreamWaitEvent(st, c->ev_side[0], 0);
             { LaunchTimer t(c, K_SCAN);
               if (weighted) {
@@ -615,6 +659,11 @@ int run_cbs(cbs_gpu_ctx* c, const std::vector<long long>& off, const uint64_t* u
         case ERR_ARENA: return fail(c, CBS_GPU_ERR_OOM, "permutation arena too small for one segment (raise CBS_GPU_ARENA_MB)");
         default: return fail(c, CBS_GPU_ERR_CUDA, "internal scheduler error " + std::to_string(hD.error));
         }
+    }
+    if (getenv("CBS_GPU_DEBUG_ROUNDS")) {
+        fprintf(stderr, "[rounds] planned perms / markers per round:");
+        for (int r = 0; r < std::min(hD.round, 64); ++r) fprintf(stderr, " %d:%llu/%.1fM", r, hD.round_perms[r], hD.round_elems[r] * 1e-6);
+        fprintf(stderr, "\n");
     }
     if (hD.n_segs > 0) {
         LaunchTimer t(c, K_MEANS);
@@ -781,7 +830,10 @@ int cbs_gpu_create(const int* device_ids, int ndev, cbs_gpu_ctx** out) {
         cudaFuncSetAttribute(k_shuffle<128, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_optin) != cudaSuccess ||
         cudaFuncSetAttribute(k_shuffle<256, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_optin) != cudaSuccess ||
         cudaFuncSetAttribute(k_shuffle<512, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_optin) != cudaSuccess ||
-        cudaFuncSetAttribute(k_shuffle<1024, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_optin) != cudaSuccess) {
+        cudaFuncSetAttribute(k_shuffle<1024, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_optin) != cudaSuccess ||
+        cudaFuncSetAttribute(k_shuffle_cluster<1024, 4, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_optin) != cudaSuccess ||
+        cudaFuncSetAttribute(k_shuffle_cluster<1024, 4, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_optin) != cudaSuccess ||
+        cudaFuncSetAttribute(k_shuffle_cluster<1024, 4, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_optin) != cudaSuccess) {
         delete c;
         return CBS_GPU_ERR_CUDA;
     }

@@ -32,6 +32,13 @@ __device__ __forceinline__ void atomic_max_pos_double(double* addr, double v) {
     atomicMax((unsigned long long*)addr, (unsigned long long)__double_as_longlong(v));
 }
 
+// order-preserving map between doubles and signed 64-bit integers (its own inverse on the bit pattern)
+__device__ __forceinline__ long long dkey(double v) {
+    const long long b = __double_as_longlong(v);
+    return b ^ ((b >> 63) & 0x7fffffffffffffffLL);
+}
+__device__ __forceinline__ double dunkey(long long k) { return __longlong_as_double(k ^ ((k >> 63) & 0x7fffffffffffffffLL)); }
+
 // map a global work index to (item, offset) through an exclusive prefix array
 __device__ __forceinline__ int find_item(const int* prefix, int n_items, int g) {
     int lo = 0, hi = n_items;  // prefix[lo] <= g < prefix[hi]
@@ -167,16 +174,18 @@ __device__ void row_stats_chunk(const double* buf, int c0, int cnt, int n, doubl
     const bool last_chunk = hi_idx >= n;
     for (int l = lane; l <= CHUNK / 32; l += 32) {
         if (32 * l - 1 > cnt - 1 || (l == CHUNK / 32 && !last_chunk)) continue;
-        float lo = __int_as_float(0x7f800000), hi = -lo;
+        // extrema of the run in double through order-preserving integer keys (f64 -> f32 conversions run on the XU pipe
+        // at half a lane per clock on B200: two per prefix sum made this kernel XU bound); two conversions per entry remain
+        long long klo = 0x7fffffffffffffffLL, khi = -0x7fffffffffffffffLL - 1;
 #pragma unroll 4
         for (int tt = 0; tt < 32; ++tt) {
             const int k = 32 * l - 1 + ((tt + l) & 31);  // skewed: the lanes hit different banks
             if (k <= cnt - 1) {
-                const double v = (k < 0) ? prev_last : buf[k];
-                lo = fminf(lo, __double2float_rd(v)); hi = fmaxf(hi, __double2float_ru(v));
+                const long long key = dkey((k < 0) ? prev_last : buf[k]);
+                klo = min(klo, key); khi = max(khi, key);
             }
         }
-        tmin[(c0 >> 5) + l] = lo; tmax[(c0 >> 5) + l] = hi;
+        tmin[(c0 >> 5) + l] = __double2float_rd(dunkey(klo)); tmax[(c0 >> 5) + l] = __double2float_ru(dunkey(khi));
     }
 }
 
@@ -739,6 +748,49 @@ __global__ void __launch_bounds__(T) k_shuffle(Dev* D, int cls, int hbits) {
     }
 }
 
+// k_shuffle_cluster: the same for segments of more than 65535 markers; a cluster of R CTAs per permutation shares
+// last[] (32 bit per marker) through distributed shared memory (shuffle.cuh)
+template <int T, int K, int R>
+__global__ void __cluster_dims__(R, 1, 1) __launch_bounds__(T) k_shuffle_cluster(Dev* D, int cls, int hbits) {
+    namespace cg = cooperative_groups;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ int s_g;
+    unsigned* claim = (unsigned*)smem_raw;
+    unsigned* last = (unsigned*)(smem_raw + ((size_t)4 << hbits));
+    if (D->done) return;
+    cg::cluster_group cl = cg::this_cluster();
+    const int hmask = (1 << hbits) - 1;
+    for (int k = threadIdx.x; k <= hmask; k += T) claim[k] = 0u;
+    unsigned epoch = 0;
+    const int nl = D->n_shuf[cls];
+    const int total = D->shuf_prefix[cls][nl];
+    const bool mt = D->prm.rng_mode == RNG_MT;
+    for (;;) {
+        cl.sync();  // the previous permutation's root walks (remote reads of last[]) are over
+        if (cl.block_rank() == 0 && threadIdx.x == 0) {
+            const int g = (int)atomicAdd(&D->ctr[8 + cls], 1u);
+            for (int r = 0; r < R; ++r) *cl.map_shared_rank(&s_g, r) = g;
+        }
+        cl.sync();
+        const int g = s_g;
+        if (g >= total) break;
+        const int k = find_item(D->shuf_prefix[cls], nl, g);
+        const PermItem it = D->items[D->shuf_item[cls][k]];
+        const Task& t = D->tasks[it.task];
+        const int p = D->shuf_p0[cls][k] + (g - D->shuf_prefix[cls][k]);
+        const int n = t.n;
+        const long long base = D->unit_off[t.unit] + t.lo;
+        ShufDraws src;
+        src.mt = mt;
+        src.win = mt ? (D->shared_stream ? D->stream : D->draws[D->round & 1]) + t.off_draw + (long long)p * n : nullptr;
+        src.k0 = (uint32_t)t.key; src.k1 = (uint32_t)(t.key >> 32); src.permno = (uint32_t)(t.perms_done + p);
+        double* sx = D->arena + t.off_sx + (long long)p * Sched::sx_stride(n);
+        const double* vals = D->w ? D->ycur + base : D->cur + base;
+        const double* rdiv = D->w ? D->rw + base : nullptr;
+        shuffle_cluster<T, K, R>(last, claim, hmask, epoch, n, src, vals, rdiv, sx);
+    }
+}
+
 // ------------------------------------------------------------------------------------
 // k_perm: the same warp-per-permutation shuffle for segments of 65536+ markers, whose index
 // array (32-bit) does not fit in shared memory and lives in the arena (L2-resident accesses).
@@ -773,9 +825,15 @@ __global__ void __launch_bounds__(128) k_perm(Dev* D) {
 // warps per SM keep the FP64 pipe and HBM busy when many permutations are in flight.
 // ------------------------------------------------------------------------------------
 #define CHAIN_WARPS 4
+#ifndef CHAIN_CHUNK
+#define CHAIN_CHUNK 1024
+#endif
+#ifndef CHAIN_MIN_CTAS
+#define CHAIN_MIN_CTAS 3
+#endif
 template <bool WEIGHTED>  // weighted CBS: the chain adds px*w (wtmaxo, CBS.cpp:623,627); the product is rounded before the addition
-__global__ void __launch_bounds__(CHAIN_WARPS * 32) k_chain(Dev* D) {
-    __shared__ __align__(16) double buf_all[CHAIN_WARPS][PERM_CHUNK];
+__global__ void __launch_bounds__(CHAIN_WARPS * 32, CHAIN_MIN_CTAS) k_chain(Dev* D) {
+    __shared__ __align__(16) double buf_all[CHAIN_WARPS][CHAIN_CHUNK];
     if (D->done) return;
     const int lane = threadIdx.x & 31;
     double* buf = buf_all[threadIdx.x >> 5];
@@ -803,18 +861,18 @@ __global__ void __launch_bounds__(CHAIN_WARPS * 32) k_chain(Dev* D) {
         const double* __restrict__ wt = WEIGHTED ? D->w + D->unit_off[t.unit] + t.lo : nullptr;
         if (lane == 0) sx[0] = 0.0;
         double run = 0.0;
-        double r[PERM_CHUNK / 32];
+        double r[CHAIN_CHUNK / 32];
 #pragma unroll
-        for (int q = 0; q < PERM_CHUNK / 32; ++q) { const int i = lane + 32 * q; r[q] = (i < n) ? (WEIGHTED ? src[i] * wt[i] : src[i]) : 0.0; }
-        for (int c0 = 0; c0 < n; c0 += PERM_CHUNK) {
-            const int cnt = min(PERM_CHUNK, n - c0);
+        for (int q = 0; q < CHAIN_CHUNK / 32; ++q) { const int i = lane + 32 * q; r[q] = (i < n) ? (WEIGHTED ? src[i] * wt[i] : src[i]) : 0.0; }
+        for (int c0 = 0; c0 < n; c0 += CHAIN_CHUNK) {
+            const int cnt = min(CHAIN_CHUNK, n - c0);
             __syncwarp();
 #pragma unroll
-            for (int q = 0; q < PERM_CHUNK / 32; ++q) buf[lane + 32 * q] = r[q];
+            for (int q = 0; q < CHAIN_CHUNK / 32; ++q) buf[lane + 32 * q] = r[q];
             __syncwarp();
-            if (c0 + PERM_CHUNK < n) {
+            if (c0 + CHAIN_CHUNK < n) {
 #pragma unroll
-                for (int q = 0; q < PERM_CHUNK / 32; ++q) { const int i = c0 + PERM_CHUNK + lane + 32 * q; r[q] = (i < n) ? (WEIGHTED ? src[i] * wt[i] : src[i]) : 0.0; }
+                for (int q = 0; q < CHAIN_CHUNK / 32; ++q) { const int i = c0 + CHAIN_CHUNK + lane + 32 * q; r[q] = (i < n) ? (WEIGHTED ? src[i] * wt[i] : src[i]) : 0.0; }
             }
             if (lane == 0) {
                 int kk = 0;
@@ -829,12 +887,92 @@ __global__ void __launch_bounds__(CHAIN_WARPS * 32) k_chain(Dev* D) {
             }
             __syncwarp();
             for (int kk = lane; kk < cnt; kk += 32) sx[c0 + 1 + kk] = buf[kk];
-            row_stats_chunk<PERM_CHUNK>(buf, c0, cnt, n, prev_last, bb, nb, bs, tmin, tmax, rst, lane);
+            row_stats_chunk<CHAIN_CHUNK>(buf, c0, cnt, n, prev_last, bb, nb, bs, tmin, tmax, rst, lane);
             prev_last = buf[cnt - 1];
         }
         // the scan reads up to SX_PAD values behind S_n without bounds checks: keep them finite
         run = shfl_d(run, 0);
         for (int kk = lane; kk < SX_PAD; kk += 32) sx[n + 1 + kk] = run;
+        __syncwarp();
+    }
+}
+
+// ------------------------------------------------------------------------------------
+// k_chain32: the same prefix sums (CBS.cpp:83-90 order, one strictly sequential DADD chain per permutation), 32
+// permutations of a batch per warp, one per LANE, so a warp instruction of the FP64 pipe advances 32 chains instead
+// of one.  The rows of a batch are far apart in memory, so the warp moves tiles of 32 rows x 32 values through
+// shared memory: rows are loaded and stored coalesced (256 B per row and tile), the transposed access (lane l walks
+// row l) stays on chip.  The next tile is in flight in registers while the current one is summed.  The statistics of
+// a row (block extrema, pruning table) are then computed by k_scan itself (stats_in_scan), with a whole CTA per row.
+// ------------------------------------------------------------------------------------
+#define CH32_WARPS 4
+template <bool WEIGHTED>
+__global__ void __launch_bounds__(CH32_WARPS * 32) k_chain32(Dev* D) {
+    __shared__ double tile_all[CH32_WARPS][32][33];
+    if (D->done) return;
+    const int lane = threadIdx.x & 31;
+    double (*tile)[33] = tile_all[threadIdx.x >> 5];
+    const int total = D->item_uprefix[D->n_items];
+    for (;;) {
+        int g = 0;
+        if (lane == 0) g = (int)atomicAdd(&D->ctr[3], 1u);
+        g = __shfl_sync(FULL, g, 0);
+        if (g >= total) break;
+        const int k = find_item(D->item_uprefix, D->n_items, g);
+        const PermItem it = D->items[k];
+        if (it.obs) continue;  // k_prep wrote the prefix sums of observed data
+        const Task& t = D->tasks[it.task];
+        const int n = t.n;
+        const int p0 = (g - D->item_uprefix[k]) * 32;
+        const int np = min(32, it.P - p0);
+        const long long stride = Sched::sx_stride(n);
+        double* __restrict__ sx0 = D->arena + t.off_sx + (long long)p0 * stride;
+        const double* __restrict__ wt = WEIGHTED ? D->w + D->unit_off[t.unit] + t.lo : nullptr;
+        if (lane < np) sx0[(long long)lane * stride] = 0.0;
+        double run = 0.0;
+        double reg[32];
+#pragma unroll
+        for (int r = 0; r < 32; ++r) {
+            const bool ok = r < np && lane < n;
+            double v = ok ? sx0[(long long)r * stride + 1 + lane] : 0.0;
+            if (WEIGHTED && ok) v = v * wt[lane];
+            reg[r] = v;
+        }
+        for (int c0 = 0; c0 < n; c0 += 32) {
+            __syncwarp();
+#pragma unroll
+            for (int r = 0; r < 32; ++r) tile[r][lane] = reg[r];
+            __syncwarp();
+            if (c0 + 32 < n) {
+                const int col = c0 + 32 + lane;
+                const double wv = (WEIGHTED && col < n) ? wt[col] : 1.0;
+#pragma unroll
+                for (int r = 0; r < 32; ++r) {
+                    const bool ok = r < np && col < n;
+                    double v = ok ? sx0[(long long)r * stride + 1 + col] : 0.0;
+                    if (WEIGHTED) v = v * wv;
+                    reg[r] = v;
+                }
+            }
+            // columns beyond n hold zeros: adding them leaves the sum unchanged, and they are not stored
+            double tv[32];
+#pragma unroll
+            for (int kk = 0; kk < 32; ++kk) tv[kk] = tile[lane][kk];
+#pragma unroll
+            for (int kk = 0; kk < 32; ++kk) { if (c0 + kk < n) run = run + tv[kk]; tile[lane][kk] = run; }
+            __syncwarp();
+            if (c0 + lane < n) {
+#pragma unroll
+                for (int r = 0; r < 32; ++r) if (r < np) sx0[(long long)r * stride + 1 + c0 + lane] = tile[r][lane];
+            }
+        }
+        // the scan reads up to SX_PAD values behind S_n without bounds checks: keep them finite
+        for (int r = 0; r < np; ++r) {
+            const double last = shfl_d(run, r);
+            double* row = sx0 + (long long)r * stride + n + 1;
+            row[lane] = last;
+            if (lane < SX_PAD - 32) row[32 + lane] = last;
+        }
         __syncwarp();
     }
 }
@@ -1379,8 +1517,9 @@ __global__ void __launch_bounds__(256, 3) k_scan(Dev* D, ScanLayout lay) {
         BlockStats bs(D->arena + t.off_bs + (long long)p * Sched::bs_stride(nb), nb);
         const int* bbg = D->bbtab + base;
         for (int b = tid; b <= nb; b += blockDim.x) s_bb[b] = bbg[b];
-        if (it.obs) {
-            // observed data (one row per pending segment, written by k_prep): the statistics are computed here
+        if (it.obs || D->stats_in_scan) {
+            // observed data (one row per pending segment, written by k_prep) and rows summed by k_chain32: the statistics are
+            // computed here
             __syncthreads();
         // ---- phase 0a: extrema table.  A warp takes 1024 consecutive prefix sums (coalesced loads); a
             // reduce-scatter over the lanes leaves lane l with the extrema of run l of 32, in single precision

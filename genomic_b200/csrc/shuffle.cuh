@@ -22,6 +22,7 @@
 // Storage: last[] is the only random-access array, 16 bit per marker in shared memory (segments up to 65535
 // markers) or 32 bit in global memory (L2) for longer segments.
 #pragma once
+#include <cooperative_groups.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -152,6 +153,112 @@ __device__ __forceinline__ void shuffle_cta(Last last, unsigned* claim, int hmas
 #pragma unroll
     for (int k = 0; k < K; ++k) if (pend_i[k] > 0) out[pend_i[k]] = pend_v[k];
     __syncthreads();  // last[] is cleared again by the next permutation
+}
+
+// The same replay for segments of more than 65535 markers: last[] needs 32 bit per marker (591 KB for the longest
+// SNP6 chromosome), more than one SM holds, so a thread-block CLUSTER of R CTAs shares it through distributed shared
+// memory.  Targets are dealt round-robin: CTA r owns last[q] of every q with q mod R == r.  Every CTA evaluates ALL
+// draws of a chunk (index arithmetic is cheap) but only resolves the steps whose target it owns, so claims and last[]
+// updates stay in its own shared memory and need CTA barriers only; one cluster barrier per chunk then makes the
+// chunk's entries visible for the root walks, the only remote (DSMEM) reads.
+template <int T, int K, int R>
+__device__ __forceinline__ void shuffle_cluster(unsigned* last, unsigned* claim, int hmask, unsigned& epoch, int n, const ShufDraws src,
+                                                const double* __restrict__ vals, const double* __restrict__ rdiv, double* out) {
+    namespace cg = cooperative_groups;
+    static_assert((R & (R - 1)) == 0, "cluster size must be a power of two");
+    constexpr int LR = R == 1 ? 0 : R == 2 ? 1 : R == 4 ? 2 : R == 8 ? 3 : 4;
+    cg::cluster_group cl = cg::this_cluster();
+    const int rank = (int)cl.block_rank();
+    const int tid = threadIdx.x;
+    for (int k = tid; k <= (n >> LR) + 1; k += T) last[k] = 0u;
+    double pend_v[K];
+    int pend_i[K];
+    uint64_t raw[K];
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        pend_i[k] = 0; pend_v[k] = 0.0;
+        const int i = n - k * T - tid;
+        raw[k] = (i >= 1) ? src.raw(n - i) : 0ull;
+    }
+    __syncthreads();
+    for (int i0 = n; i0 >= 1; i0 -= K * T) {
+        uint64_t nxt[K];
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            const int i2 = i0 - (K + k) * T - tid;
+            nxt[k] = (i2 >= 1) ? src.raw(n - i2) : 0ull;
+        }
+        int j[K], lnk[K];
+        unsigned un = 0, mine = 0;
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            const int i = i0 - k * T - tid;
+            j[k] = 0; lnk[k] = 0;
+            if (i >= 1) {
+                j[k] = draw_index(src.u64(raw[k]), i);
+                if ((j[k] & (R - 1)) == rank) {
+                    mine |= 1u << k;
+                    if (j[k] == i) lnk[k] = i;
+                    else un |= 1u << k;
+                }
+            }
+        }
+        for (;;) {
+            if (epoch >= SHUF_EPOCH_MAX) {
+                __syncthreads();
+                for (int k = tid; k <= hmask; k += T) claim[k] = 0u;
+                epoch = 0;
+                __syncthreads();
+            }
+            ++epoch;
+            const unsigned ebase = epoch << SHUF_EPOCH_SHIFT;
+#pragma unroll
+            for (int k = 0; k < K; ++k)
+                if (un & (1u << k)) atomicMax(claim + ((j[k] >> LR) & hmask), ebase | (unsigned)(i0 - k * T - tid));
+            __syncthreads();
+#pragma unroll
+            for (int k = 0; k < K; ++k)
+                if (un & (1u << k)) {
+                    const int i = i0 - k * T - tid;
+                    if (claim[(j[k] >> LR) & hmask] == (ebase | (unsigned)i)) {
+                        lnk[k] = (int)last[j[k] >> LR];
+                        last[j[k] >> LR] = (unsigned)i;
+                        un &= ~(1u << k);
+                    }
+                }
+            if (!__syncthreads_or((int)un)) break;
+        }
+        cl.barrier_arrive();  // this CTA's entries of the chunk are final
+#pragma unroll
+        for (int k = 0; k < K; ++k) if (pend_i[k] > 0) out[pend_i[k]] = pend_v[k];
+        cl.barrier_wait();    // ... and so are everybody else's
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            const int i = i0 - k * T - tid;
+            pend_i[k] = 0;
+            if (mine & (1u << k)) {
+                int idx = j[k];
+                if (lnk[k]) {
+                    int r = lnk[k];
+                    for (;;) {
+                        const unsigned* rl = cl.map_shared_rank(last, r & (R - 1));
+                        const int nx = (int)rl[r >> LR];
+                        if (!nx) break;
+                        r = nx;
+                    }
+                    idx = r;
+                }
+                double v = __ldg(vals + idx - 1);
+                if (rdiv && j[k] != i) v = v / __ldg(rdiv + i - 1);
+                pend_v[k] = v; pend_i[k] = i;
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < K; ++k) raw[k] = nxt[k];
+    }
+#pragma unroll
+    for (int k = 0; k < K; ++k) if (pend_i[k] > 0) out[pend_i[k]] = pend_v[k];
+    // the caller's cluster barrier (next work item) keeps last[] alive until every CTA has finished its walks
 }
 
 }  // namespace cbsg
