@@ -315,7 +315,6 @@ struct Dev {
     double* ycur;     // cur * rw: what wxperm shuffles (CBS.cpp:540)
     int shuf_cl2;     // segments of 65536..SHUF_CL2_MAX markers have their own class (cluster of 2 CTAs)
     int shuf_arena;   // segments > 65535 markers are shuffled by k_perm on 32-bit index arrays in the arena (fallback of k_shuffle_cluster)
-    int stats_in_scan;  // rows of permutations come from k_chain32 without statistics: k_scan computes them (as for observed rows)
     int no_early;     // CBS_GPU_NO_EARLY=1: decision-mode scans never stop at the first rejecting arc (A/B switch)
 };
 

@@ -269,29 +269,44 @@ bool pick_scan_warps(cbs_gpu_ctx* c, ScanLayout& lay, int* occ_out) {
 
 // shared-memory shuffle classes (cbs_core.h): dynamic shared memory of a CTA = claim table + last[] of the longest segment
 size_t shuffle_smem_bytes(int cls) { return ((size_t)4 << shuffle_class_hbits(cls)) + (((size_t)shuffle_class_max(cls) + 2) * 2 + 15) / 16 * 16; }
-void launch_shuffle(Dev* dD, int cls, int grid, cudaStream_t ss) {
+template <bool MT>
+void launch_shuffle_t(Dev* dD, int cls, int grid, cudaStream_t ss) {
     const size_t smem = shuffle_smem_bytes(cls);
     const int hb = shuffle_class_hbits(cls);
     switch (shuffle_class_threads(cls)) {
-    case 128: k_shuffle<128, 2><<<grid, 128, smem, ss>>>(dD, cls, hb); break;
-    case 256: k_shuffle<256, 2><<<grid, 256, smem, ss>>>(dD, cls, hb); break;
-    case 512: k_shuffle<512, 2><<<grid, 512, smem, ss>>>(dD, cls, hb); break;
-    default: k_shuffle<1024, 2><<<grid, 1024, smem, ss>>>(dD, cls, hb); break;
+    case 128: k_shuffle<128, 2, MT><<<grid, 128, smem, ss>>>(dD, cls, hb); break;
+    case 256: k_shuffle<256, 2, MT><<<grid, 256, smem, ss>>>(dD, cls, hb); break;
+    case 512: k_shuffle<512, 2, MT><<<grid, 512, smem, ss>>>(dD, cls, hb); break;
+    default: k_shuffle<1024, 2, MT><<<grid, 1024, smem, ss>>>(dD, cls, hb); break;
     }
+}
+void launch_shuffle(Dev* dD, int cls, int grid, cudaStream_t ss, bool mt) {
+    if (mt) launch_shuffle_t<true>(dD, cls, grid, ss); else launch_shuffle_t<false>(dD, cls, grid, ss);
+}
+template <bool MT>
+void launch_shuffle_cluster_t(Dev* dD, int R, int cls, int hbits, int grid, size_t smem, cudaStream_t ss) {
+    if (R == 2) k_shuffle_cluster<1024, 4, 2, MT><<<grid, 1024, smem, ss>>>(dD, cls, hbits);
+    else if (R == 4) k_shuffle_cluster<1024, 4, 4, MT><<<grid, 1024, smem, ss>>>(dD, cls, hbits);
+    else k_shuffle_cluster<1024, 4, 8, MT><<<grid, 1024, smem, ss>>>(dD, cls, hbits);
+}
+void launch_shuffle_cluster(Dev* dD, int R, int cls, int hbits, int grid, size_t smem, cudaStream_t ss, bool mt) {
+    if (mt) launch_shuffle_cluster_t<true>(dD, R, cls, hbits, grid, smem, ss); else launch_shuffle_cluster_t<false>(dD, R, cls, hbits, grid, smem, ss);
 }
 int shuffle_occupancy(int cls) {
     int occ = 0;
     const size_t smem = shuffle_smem_bytes(cls);
     cudaError_t e;
     switch (shuffle_class_threads(cls)) {
-    case 128: e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_shuffle<128, 2>, 128, smem); break;
-    case 256: e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_shuffle<256, 2>, 256, smem); break;
-    case 512: e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_shuffle<512, 2>, 512, smem); break;
-    default: e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_shuffle<1024, 2>, 1024, smem); break;
+    case 128: e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_shuffle<128, 2, true>, 128, smem); break;
+    case 256: e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_shuffle<256, 2, true>, 256, smem); break;
+    case 512: e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_shuffle<512, 2, true>, 512, smem); break;
+    default: e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_shuffle<1024, 2, true>, 1024, smem); break;
     }
     if (e != cudaSuccess) { cudaGetLastError(); occ = 1; }
     return std::max(1, occ);
 }
+template <class F>
+bool set_max_smem(F* f, int bytes) { return cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes) == cudaSuccess; }
 
 struct RunCaps {
     int task_cap, list_cap, seg_cap, split_cap, max_live;
@@ -450,7 +465,6 @@ int run_cbs(cbs_gpu_ctx* c, const std::vector<long long>& off, const uint64_t* u
         if (c->jump_ready) { hD.jump_polys = c->jump.as<uint64_t>(); hD.span_max = (long long)mtjump::NSEG * mtjump::SEG; }
     }
     hD.profile = c->counting ? 1 : 0;
-    hD.stats_in_scan = env_ll("CBS_GPU_CHAIN_OLD", 0) ? 0 : 1;
     hD.shuf_arena = 1;  // decided below (cluster shuffle available?) and patched on the device before the first round
     hD.no_early = env_ll("CBS_GPU_NO_EARLY", 0) ? 1 : 0;
     if (weighted) {
@@ -514,9 +528,9 @@ int run_cbs(cbs_gpu_ctx* c, const std::vector<long long>& off, const uint64_t* u
         at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = R; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
         cfg.attrs = at; cfg.numAttrs = 1;
         int ncl = 0;
-        cudaError_t e = R == 2 ? cudaOccupancyMaxActiveClusters(&ncl, k_shuffle_cluster<1024, 4, 2>, &cfg)
-                      : R == 4 ? cudaOccupancyMaxActiveClusters(&ncl, k_shuffle_cluster<1024, 4, 4>, &cfg)
-                               : cudaOccupancyMaxActiveClusters(&ncl, k_shuffle_cluster<1024, 4, 8>, &cfg);
+        cudaError_t e = R == 2 ? cudaOccupancyMaxActiveClusters(&ncl, k_shuffle_cluster<1024, 4, 2, true>, &cfg)
+                      : R == 4 ? cudaOccupancyMaxActiveClusters(&ncl, k_shuffle_cluster<1024, 4, 4, true>, &cfg)
+                               : cudaOccupancyMaxActiveClusters(&ncl, k_shuffle_cluster<1024, 4, 8, true>, &cfg);
         if (e != cudaSuccess || ncl < 1) { cudaGetLastError(); return 0; }
         *smem_out = smem;
         return ncl * R;
@@ -543,7 +557,6 @@ int run_cbs(cbs_gpu_ctx* c, const std::vector<long long>& off, const uint64_t* u
     const int G = 16;  // rounds per group; two groups are kept in flight, so a typical call (20-30 rounds) is enqueued up front and
                        // host scheduling jitter cannot starve the GPU (the surplus rounds are empty launches, ~0.1 ms each)
     const bool debug = env_ll("CBS_GPU_DEBUG", 0) != 0;
-    const bool chain_old = env_ll("CBS_GPU_CHAIN_OLD", 0) != 0;  // A/B: one permutation per warp (lane 0 sums)
     int groups_in_flight = 0, rounds = 0;
     bool ahead_pending = false;
     int gi = 0;
@@ -593,10 +606,9 @@ int run_cbs(cbs_gpu_ctx* c, const std::vector<long long>& off, const uint64_t* u
                     cudaStreamWaitEvent(ss, c->ev_gen, 0);
                     used_side[4] = true;
                     LaunchTimer t(c, K_PERM, ss);
-                    if (cl_R == 4) k_shuffle_cluster<1024, 4, 4><<<cl_grid, 1024, cl_smem, ss>>>(dD, SHUF_GLOBAL, cl_hbits);
-                    else if (cl_R == 8) k_shuffle_cluster<1024, 4, 8><<<cl_grid, 1024, cl_smem, ss>>>(dD, SHUF_GLOBAL, cl_hbits);
+                    if (cl_R == 4 || cl_R == 8) launch_shuffle_cluster(dD, cl_R, SHUF_GLOBAL, cl_hbits, cl_grid, cl_smem, ss, mt);
                     else if (cl_R == 0) k_perm<<<c->sm_count * 8, 128, 0, ss>>>(dD);
-                    if (cl2_grid) { k_shuffle_cluster<1024, 4, 2><<<cl2_grid, 1024, cl2_smem, ss>>>(dD, SHUF_CL2, cl_hbits); c->launches++; }
+                    if (cl2_grid) { launch_shuffle_cluster(dD, 2, SHUF_CL2, cl_hbits, cl2_grid, cl2_smem, ss, mt); c->launches++; }
                 }
                 for (int cls = SHUF_CL2 - 1; cls >= 0; --cls) {
                     if (!shuf_on[cls]) continue;
@@ -604,12 +616,11 @@ int run_cbs(cbs_gpu_ctx* c, const std::vector<long long>& off, const uint64_t* u
                     cudaStream_t ss = where == 0 ? st : c->side[1 + where];
                     if (where != 0 && !used_side[1 + where]) { cudaStreamWaitEvent(ss, c->ev_gen, 0); used_side[1 + where] = true; }
                     LaunchTimer t(c, kShufTimer[cls], ss);
-                    launch_shuffle(dD, cls, c->sm_count * shuf_occ[cls], ss);
+                    launch_shuffle(dD, cls, c->sm_count * shuf_occ[cls], ss, mt);
                 }
             }
             for (int k = 2; k < 5; ++k) if (used_side[k]) { cudaEventRecord(c->ev_side[k], c->side[k]); cudaStreamWaitEvent(st, c->ev_side[k], 0); }
-            { LaunchTimer t(c, K_PREFIX); if (weighted && p->hybrid) { k_wssq<<<c->sm_count * 8, 128, 0, st>>>(dD); c->launches++; } if (chain_old) { if (weighted) k_chain<true><<<c->sm_count * 2 * CHAIN_MIN_CTAS, CHAIN_WARPS * 32, 0, st>>>(dD); else k_chain<false><<<c->sm_count * 2 * CHAIN_MIN_CTAS, CHAIN_WARPS * 32, 0, st>>>(dD); }
-              else if (weighted) k_chain32<true><<<c->sm_count * 6, CH32_WARPS * 32, 0, st>>>(dD); else k_chain32<false><<<c->sm_count * 6, CH32_WARPS * 32, 0, st>>>(dD); }
+            { LaunchTimer t(c, K_PREFIX); if (weighted && p->hybrid) { k_wssq<<<c->sm_count * 8, 128, 0, st>>>(dD); c->launches++; } if (weighted) k_chain<true><<<c->sm_count * 12, CHAIN_WARPS * 32, 0, st>>>(dD); else k_chain<false><<<c->sm_count * 12, CHAIN_WARPS * 32, 0, st>>>(dD); }
             cudaStreamWaitEvent(st, c->ev_side[0], 0);
             { LaunchTimer t(c, K_SCAN);
               if (weighted) {
@@ -826,14 +837,14 @@ int cbs_gpu_create(const int* device_ids, int ndev, cbs_gpu_ctx** out) {
     c->smem_optin = prop.sharedMemPerBlockOptin - 1024;  // head room for the kernels' static shared memory
     // function attributes are process-wide per device: set them once to the device maximum, never per call
     // (concurrent lanes with different needs would otherwise shrink each other's limit)
-    if (cudaFuncSetAttribute(k_scan, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_optin) != cudaSuccess ||
-        cudaFuncSetAttribute(k_shuffle<128, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_optin) != cudaSuccess ||
-        cudaFuncSetAttribute(k_shuffle<256, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_optin) != cudaSuccess ||
-        cudaFuncSetAttribute(k_shuffle<512, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_optin) != cudaSuccess ||
-        cudaFuncSetAttribute(k_shuffle<1024, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_optin) != cudaSuccess ||
-        cudaFuncSetAttribute(k_shuffle_cluster<1024, 4, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_optin) != cudaSuccess ||
-        cudaFuncSetAttribute(k_shuffle_cluster<1024, 4, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_optin) != cudaSuccess ||
-        cudaFuncSetAttribute(k_shuffle_cluster<1024, 4, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_optin) != cudaSuccess) {
+    const int mx = (int)c->smem_optin;
+    if (!set_max_smem(k_scan, mx) ||
+        !set_max_smem(k_shuffle<128, 2, true>, mx) || !set_max_smem(k_shuffle<256, 2, true>, mx) || !set_max_smem(k_shuffle<512, 2, true>, mx) ||
+        !set_max_smem(k_shuffle<1024, 2, true>, mx) || !set_max_smem(k_shuffle<128, 2, false>, mx) || !set_max_smem(k_shuffle<256, 2, false>, mx) ||
+        !set_max_smem(k_shuffle<512, 2, false>, mx) || !set_max_smem(k_shuffle<1024, 2, false>, mx) ||
+        !set_max_smem(k_shuffle_cluster<1024, 4, 2, true>, mx) || !set_max_smem(k_shuffle_cluster<1024, 4, 4, true>, mx) ||
+        !set_max_smem(k_shuffle_cluster<1024, 4, 8, true>, mx) || !set_max_smem(k_shuffle_cluster<1024, 4, 2, false>, mx) ||
+        !set_max_smem(k_shuffle_cluster<1024, 4, 4, false>, mx) || !set_max_smem(k_shuffle_cluster<1024, 4, 8, false>, mx)) {
         delete c;
         return CBS_GPU_ERR_CUDA;
     }

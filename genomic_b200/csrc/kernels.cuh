@@ -711,7 +711,7 @@ __device__ void perm_warp(Dev* D, const Task& t, int p, Idx s_idx, unsigned char
 // k_shuffle: xperm (CBS.cpp:487-493) for segments of up to 65535 markers, one CTA per permutation (shuffle.cuh):
 // exact parallel replay of the Fisher-Yates, last[] (16 bit per marker) and the claim table in shared memory; the
 // permuted values go straight into the S row of the permutation (k_chain turns them into prefix sums in place).
-template <int T, int K>
+template <int T, int K, bool MT>
 __global__ void __launch_bounds__(T) k_shuffle(Dev* D, int cls, int hbits) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ int s_g;
@@ -723,7 +723,6 @@ __global__ void __launch_bounds__(T) k_shuffle(Dev* D, int cls, int hbits) {
     unsigned epoch = 0;
     const int nl = D->n_shuf[cls];
     const int total = D->shuf_prefix[cls][nl];
-    const bool mt = D->prm.rng_mode == RNG_MT;
     for (;;) {
         __syncthreads();
         if (threadIdx.x == 0) s_g = (int)atomicAdd(&D->ctr[8 + cls], 1u);
@@ -736,9 +735,8 @@ __global__ void __launch_bounds__(T) k_shuffle(Dev* D, int cls, int hbits) {
         const int p = D->shuf_p0[cls][k] + (g - D->shuf_prefix[cls][k]);
         const int n = t.n;
         const long long base = D->unit_off[t.unit] + t.lo;
-        ShufDraws src;
-        src.mt = mt;
-        src.win = mt ? (D->shared_stream ? D->stream : D->draws[D->round & 1]) + t.off_draw + (long long)p * n : nullptr;
+        ShufDraws<MT> src;
+        src.win = MT ? (D->shared_stream ? D->stream : D->draws[D->round & 1]) + t.off_draw + (long long)p * n : nullptr;
         src.k0 = (uint32_t)t.key; src.k1 = (uint32_t)(t.key >> 32); src.permno = (uint32_t)(t.perms_done + p);
         double* sx = D->arena + t.off_sx + (long long)p * Sched::sx_stride(n);
         // weighted CBS (wxperm, CBS.cpp:538-547): the shuffle runs on y = cur*rw, position i-1 receives y[.]/rw[i-1]
@@ -750,7 +748,7 @@ __global__ void __launch_bounds__(T) k_shuffle(Dev* D, int cls, int hbits) {
 
 // k_shuffle_cluster: the same for segments of more than 65535 markers; a cluster of R CTAs per permutation shares
 // last[] (32 bit per marker) through distributed shared memory (shuffle.cuh)
-template <int T, int K, int R>
+template <int T, int K, int R, bool MT>
 __global__ void __cluster_dims__(R, 1, 1) __launch_bounds__(T) k_shuffle_cluster(Dev* D, int cls, int hbits) {
     namespace cg = cooperative_groups;
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -764,7 +762,6 @@ __global__ void __cluster_dims__(R, 1, 1) __launch_bounds__(T) k_shuffle_cluster
     unsigned epoch = 0;
     const int nl = D->n_shuf[cls];
     const int total = D->shuf_prefix[cls][nl];
-    const bool mt = D->prm.rng_mode == RNG_MT;
     for (;;) {
         cl.sync();  // the previous permutation's root walks (remote reads of last[]) are over
         if (cl.block_rank() == 0 && threadIdx.x == 0) {
@@ -780,9 +777,8 @@ __global__ void __cluster_dims__(R, 1, 1) __launch_bounds__(T) k_shuffle_cluster
         const int p = D->shuf_p0[cls][k] + (g - D->shuf_prefix[cls][k]);
         const int n = t.n;
         const long long base = D->unit_off[t.unit] + t.lo;
-        ShufDraws src;
-        src.mt = mt;
-        src.win = mt ? (D->shared_stream ? D->stream : D->draws[D->round & 1]) + t.off_draw + (long long)p * n : nullptr;
+        ShufDraws<MT> src;
+        src.win = MT ? (D->shared_stream ? D->stream : D->draws[D->round & 1]) + t.off_draw + (long long)p * n : nullptr;
         src.k0 = (uint32_t)t.key; src.k1 = (uint32_t)(t.key >> 32); src.permno = (uint32_t)(t.perms_done + p);
         double* sx = D->arena + t.off_sx + (long long)p * Sched::sx_stride(n);
         const double* vals = D->w ? D->ycur + base : D->cur + base;
@@ -893,86 +889,6 @@ __global__ void __launch_bounds__(CHAIN_WARPS * 32, CHAIN_MIN_CTAS) k_chain(Dev*
         // the scan reads up to SX_PAD values behind S_n without bounds checks: keep them finite
         run = shfl_d(run, 0);
         for (int kk = lane; kk < SX_PAD; kk += 32) sx[n + 1 + kk] = run;
-        __syncwarp();
-    }
-}
-
-// ------------------------------------------------------------------------------------
-// k_chain32: the same prefix sums (CBS.cpp:83-90 order, one strictly sequential DADD chain per permutation), 32
-// permutations of a batch per warp, one per LANE, so a warp instruction of the FP64 pipe advances 32 chains instead
-// of one.  The rows of a batch are far apart in memory, so the warp moves tiles of 32 rows x 32 values through
-// shared memory: rows are loaded and stored coalesced (256 B per row and tile), the transposed access (lane l walks
-// row l) stays on chip.  The next tile is in flight in registers while the current one is summed.  The statistics of
-// a row (block extrema, pruning table) are then computed by k_scan itself (stats_in_scan), with a whole CTA per row.
-// ------------------------------------------------------------------------------------
-#define CH32_WARPS 4
-template <bool WEIGHTED>
-__global__ void __launch_bounds__(CH32_WARPS * 32) k_chain32(Dev* D) {
-    __shared__ double tile_all[CH32_WARPS][32][33];
-    if (D->done) return;
-    const int lane = threadIdx.x & 31;
-    double (*tile)[33] = tile_all[threadIdx.x >> 5];
-    const int total = D->item_uprefix[D->n_items];
-    for (;;) {
-        int g = 0;
-        if (lane == 0) g = (int)atomicAdd(&D->ctr[3], 1u);
-        g = __shfl_sync(FULL, g, 0);
-        if (g >= total) break;
-        const int k = find_item(D->item_uprefix, D->n_items, g);
-        const PermItem it = D->items[k];
-        if (it.obs) continue;  // k_prep wrote the prefix sums of observed data
-        const Task& t = D->tasks[it.task];
-        const int n = t.n;
-        const int p0 = (g - D->item_uprefix[k]) * 32;
-        const int np = min(32, it.P - p0);
-        const long long stride = Sched::sx_stride(n);
-        double* __restrict__ sx0 = D->arena + t.off_sx + (long long)p0 * stride;
-        const double* __restrict__ wt = WEIGHTED ? D->w + D->unit_off[t.unit] + t.lo : nullptr;
-        if (lane < np) sx0[(long long)lane * stride] = 0.0;
-        double run = 0.0;
-        double reg[32];
-#pragma unroll
-        for (int r = 0; r < 32; ++r) {
-            const bool ok = r < np && lane < n;
-            double v = ok ? sx0[(long long)r * stride + 1 + lane] : 0.0;
-            if (WEIGHTED && ok) v = v * wt[lane];
-            reg[r] = v;
-        }
-        for (int c0 = 0; c0 < n; c0 += 32) {
-            __syncwarp();
-#pragma unroll
-            for (int r = 0; r < 32; ++r) tile[r][lane] = reg[r];
-            __syncwarp();
-            if (c0 + 32 < n) {
-                const int col = c0 + 32 + lane;
-                const double wv = (WEIGHTED && col < n) ? wt[col] : 1.0;
-#pragma unroll
-                for (int r = 0; r < 32; ++r) {
-                    const bool ok = r < np && col < n;
-                    double v = ok ? sx0[(long long)r * stride + 1 + col] : 0.0;
-                    if (WEIGHTED) v = v * wv;
-                    reg[r] = v;
-                }
-            }
-            // columns beyond n hold zeros: adding them leaves the sum unchanged, and they are not stored
-            double tv[32];
-#pragma unroll
-            for (int kk = 0; kk < 32; ++kk) tv[kk] = tile[lane][kk];
-#pragma unroll
-            for (int kk = 0; kk < 32; ++kk) { if (c0 + kk < n) run = run + tv[kk]; tile[lane][kk] = run; }
-            __syncwarp();
-            if (c0 + lane < n) {
-#pragma unroll
-                for (int r = 0; r < 32; ++r) if (r < np) sx0[(long long)r * stride + 1 + c0 + lane] = tile[r][lane];
-            }
-        }
-        // the scan reads up to SX_PAD values behind S_n without bounds checks: keep them finite
-        for (int r = 0; r < np; ++r) {
-            const double last = shfl_d(run, r);
-            double* row = sx0 + (long long)r * stride + n + 1;
-            row[lane] = last;
-            if (lane < SX_PAD - 32) row[32 + lane] = last;
-        }
         __syncwarp();
     }
 }
@@ -1517,9 +1433,8 @@ __global__ void __launch_bounds__(256, 3) k_scan(Dev* D, ScanLayout lay) {
         BlockStats bs(D->arena + t.off_bs + (long long)p * Sched::bs_stride(nb), nb);
         const int* bbg = D->bbtab + base;
         for (int b = tid; b <= nb; b += blockDim.x) s_bb[b] = bbg[b];
-        if (it.obs || D->stats_in_scan) {
-            // observed data (one row per pending segment, written by k_prep) and rows summed by k_chain32: the statistics are
-            // computed here
+        if (it.obs) {
+            // observed data (one row per pending segment, written by k_prep): the statistics are computed here
             __syncthreads();
         // ---- phase 0a: extrema table.  A warp takes 1024 consecutive prefix sums (coalesced loads); a
             // reduce-scatter over the lanes leaves lane l with the extrema of run l of 32, in single precision

@@ -50,17 +50,21 @@ struct LastGlobal32 {
 };
 
 // uniform source of one permutation: draw d (0-based) belongs to step i = n - d
+template <bool MT>
 struct ShufDraws {
     const uint64_t* win;  // MT: raw (untempered) words of this permutation
-    bool mt;
     uint32_t k0, k1, permno;  // philox: task key and permutation number (cbs_core.h DrawSrc, stage 0)
     __device__ __forceinline__ uint64_t raw(int d) const {
-        if (mt) return __ldg(win + d);
+        if (MT) return __ldg(win + d);
         uint32_t o[4];
         philox4x32_10((uint32_t)d >> 1, permno, 0u, 0u, k0, k1, o);
         return (d & 1) ? (((uint64_t)o[3] << 32) | o[2]) : (((uint64_t)o[1] << 32) | o[0]);
     }
-    __device__ __forceinline__ uint64_t u64(uint64_t r) const { return mt ? mt_temper(r) : r; }
+    __device__ __forceinline__ uint64_t u64(uint64_t r) const { return MT ? mt_temper(r) : r; }
+    // the stream lives in HBM: pull the 128-byte line that holds draw d into L2 ahead of its use
+    __device__ __forceinline__ void prefetch(int d) const {
+        if (MT) asm volatile("prefetch.global.L2 [%0];" ::"l"(win + d));
+    }
 };
 
 enum { SHUF_EPOCH_SHIFT = 20, SHUF_EPOCH_MAX = 4000 };
@@ -69,8 +73,8 @@ enum { SHUF_EPOCH_SHIFT = 20, SHUF_EPOCH_MAX = 4000 };
 //   claim : [hmask+1] words in shared memory, all below (epoch << 20) on entry; epoch is uniform over the CTA
 //   vals  : the values to permute (x of the pending segment), out[i] receives px[i-1] (the S row, 1-based)
 //   rdiv  : weighted CBS (wxperm, CBS.cpp:538-547): position i-1 receives y/rw[i-1] unless the step drew j == i
-template <int T, int K, class Last>
-__device__ __forceinline__ void shuffle_cta(Last last, unsigned* claim, int hmask, unsigned& epoch, int n, const ShufDraws src,
+template <int T, int K, class Last, class Draws>
+__device__ __forceinline__ void shuffle_cta(Last last, unsigned* claim, int hmask, unsigned& epoch, int n, const Draws src,
                                             const double* __restrict__ vals, const double* __restrict__ rdiv, double* out) {
     const int tid = threadIdx.x;
     last.template clear<T>(n);
@@ -90,6 +94,10 @@ __device__ __forceinline__ void shuffle_cta(Last last, unsigned* claim, int hmas
         for (int k = 0; k < K; ++k) {
             const int i2 = i0 - (K + k) * T - tid;
             nxt[k] = (i2 >= 1) ? src.raw(n - i2) : 0ull;
+        }
+        if (tid < K * T / 16) {  // one thread per 128-byte line of the chunk four ahead
+            const int d = n - i0 + 4 * K * T + 16 * tid;
+            if (d < n) src.prefetch(d);
         }
         int j[K], lnk[K];
         unsigned un = 0;
@@ -131,18 +139,25 @@ __device__ __forceinline__ void shuffle_cta(Last last, unsigned* claim, int hmas
         // the values gathered for the previous chunk have had a whole chunk to arrive
 #pragma unroll
         for (int k = 0; k < K; ++k) if (pend_i[k] > 0) out[pend_i[k]] = pend_v[k];
+        // root walks of the thread's K steps side by side: the loads of one hop are independent of each other
+        int idx[K];
+        bool more = false;
+#pragma unroll
+        for (int k = 0; k < K; ++k) { idx[k] = lnk[k] ? lnk[k] : j[k]; more |= lnk[k] != 0; }
+        while (more) {
+            more = false;
+            int nx[K];
+#pragma unroll
+            for (int k = 0; k < K; ++k) nx[k] = lnk[k] ? last.ld(idx[k]) : 0;
+#pragma unroll
+            for (int k = 0; k < K; ++k) { if (nx[k]) { idx[k] = nx[k]; more = true; } else lnk[k] = 0; }
+        }
 #pragma unroll
         for (int k = 0; k < K; ++k) {
             const int i = i0 - k * T - tid;
             pend_i[k] = 0;
             if (i >= 1) {
-                int idx = j[k];
-                if (lnk[k]) {
-                    int r = lnk[k];
-                    for (;;) { const int nx = last.ld(r); if (!nx) break; r = nx; }
-                    idx = r;
-                }
-                double v = __ldg(vals + idx - 1);
+                double v = __ldg(vals + idx[k] - 1);
                 if (rdiv && j[k] != i) v = v / __ldg(rdiv + i - 1);
                 pend_v[k] = v; pend_i[k] = i;
             }
@@ -161,8 +176,8 @@ __device__ __forceinline__ void shuffle_cta(Last last, unsigned* claim, int hmas
 // draws of a chunk (index arithmetic is cheap) but only resolves the steps whose target it owns, so claims and last[]
 // updates stay in its own shared memory and need CTA barriers only; one cluster barrier per chunk then makes the
 // chunk's entries visible for the root walks, the only remote (DSMEM) reads.
-template <int T, int K, int R>
-__device__ __forceinline__ void shuffle_cluster(unsigned* last, unsigned* claim, int hmask, unsigned& epoch, int n, const ShufDraws src,
+template <int T, int K, int R, class Draws>
+__device__ __forceinline__ void shuffle_cluster(unsigned* last, unsigned* claim, int hmask, unsigned& epoch, int n, const Draws src,
                                                 const double* __restrict__ vals, const double* __restrict__ rdiv, double* out) {
     namespace cg = cooperative_groups;
     static_assert((R & (R - 1)) == 0, "cluster size must be a power of two");
@@ -187,6 +202,10 @@ __device__ __forceinline__ void shuffle_cluster(unsigned* last, unsigned* claim,
         for (int k = 0; k < K; ++k) {
             const int i2 = i0 - (K + k) * T - tid;
             nxt[k] = (i2 >= 1) ? src.raw(n - i2) : 0ull;
+        }
+        if (tid < K * T / 16) {  // one thread per 128-byte line of the chunk four ahead
+            const int d = n - i0 + 4 * K * T + 16 * tid;
+            if (d < n) src.prefetch(d);
         }
         int j[K], lnk[K];
         unsigned un = 0, mine = 0;

@@ -29,8 +29,8 @@ __global__ void __launch_bounds__(T) k_probe(const uint64_t* words, const double
         const int p = s_g;
         __syncthreads();
         if (p >= P) break;
-        ShufDraws src;
-        src.win = words + (size_t)p * n; src.mt = true;
+        ShufDraws<true> src;
+        src.win = words + (size_t)p * n;
         double* sx = out + (size_t)p * (n + 1);
         if (GLOBAL) shuffle_cta<T, K>(LastGlobal32{lastg + (size_t)blockIdx.x * (n + 1)}, claim, H - 1, epoch, n, src, cur, nullptr, sx);
         else shuffle_cta<T, K>(LastSmem16{(unsigned short*)(smem_raw + (size_t)H * 4)}, claim, H - 1, epoch, n, src, cur, nullptr, sx);
@@ -58,8 +58,8 @@ __global__ void __cluster_dims__(R, 1, 1) __launch_bounds__(T) k_probe_cluster(c
         cl.sync();
         const int p = s_g;
         if (p >= P) break;
-        ShufDraws src;
-        src.win = words + (size_t)p * n; src.mt = true;
+        ShufDraws<true> src;
+        src.win = words + (size_t)p * n;
         shuffle_cluster<T, K, R>(last, claim, H - 1, epoch, n, src, cur, nullptr, out + (size_t)p * (n + 1));
     }
 }
