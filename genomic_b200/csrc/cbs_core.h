@@ -279,9 +279,14 @@ struct Dev {
     long long draws_cap;
     // MT, chain==0: every unit starts from the same engine state, so all chains read ONE raw stream
     // W[0..) that is generated once and extended on demand (positions are absolute cursors)
+    // The stream is kept as a WINDOW: a ring of stream_cap words (a power of two; position p lives at p & stream_mask)
+    // followed by a mirror of the ring's first stream_mirror words, so that any stream_mirror consecutive positions
+    // can be read linearly from the ring slot of the first.  Positions below stream_lo (the smallest cursor of any
+    // live chain) are dead and may be overwritten; a request that would reach beyond stream_lo + stream_cap is
+    // deferred until the slower chains have moved on, so no input can exhaust the buffer.
     int shared_stream;
     uint64_t* stream;
-    long long stream_cap, stream_len, stream_target;
+    long long stream_cap, stream_mask, stream_mirror, stream_lo, stream_len, stream_target;
     const uint64_t* jump_polys;             // table g_{c*S} (mt_jump.h) or nullptr: sequential generation only
     long long gen_base, gen_E, gen_lead_end;  // extension in flight (written by k_gen_lead)
     long long span_max;                       // words the generator may add per round
@@ -317,6 +322,18 @@ struct Dev {
     int shuf_arena;   // segments > 65535 markers are shuffled by k_perm on 32-bit index arrays in the arena (fallback of k_shuffle_cluster)
     int no_early;     // CBS_GPU_NO_EARLY=1: decision-mode scans never stop at the first rejecting arc (A/B switch)
 };
+
+// shared MT stream (ring + mirror): store one word / linear read pointer for a run of <= stream_mirror positions
+CBS_HD void stream_put(const Dev& D, long long pos, uint64_t v) {
+    const long long idx = pos & D.stream_mask;
+    D.stream[idx] = v;
+    if (idx < D.stream_mirror) D.stream[idx + D.stream_cap] = v;
+}
+CBS_HD uint64_t stream_get(const Dev& D, long long pos) { return D.stream[pos & D.stream_mask]; }
+// raw words of `off .. ` for one permutation (max-t or edge test): this round's per-chain window or the shared ring
+CBS_HD const uint64_t* draw_window(const Dev& D, long long off) {
+    return D.shared_stream ? D.stream + (off & D.stream_mask) : D.draws[D.round & 1] + off;
+}
 
 enum { ERR_TASK_CAP = 101, ERR_SEG_CAP = 102, ERR_ARENA = 103, ERR_SPLIT_CAP = 104, ERR_INTERNAL = 105, ERR_STALL = 106, ERR_STREAM_CAP = 107 };
 
@@ -517,8 +534,12 @@ struct Sched {
         if (fit < 1) { D.error = ERR_ARENA; return false; }
         if (want > fit) want = (int)fit;
         if (D.shared_stream && p.rng_mode == RNG_MT) {
-            const long long by_span = D.span_max / t.n;  // a batch must fit in one generator span
-            if (by_span < 1) { D.error = ERR_ARENA; return false; }
+            // a batch must fit in one generator span and in a quarter of the stream window (the chain with the
+            // smallest cursor then always gets its batch: no deadlock)
+            long long by_span = D.span_max / t.n;
+            const long long by_win = (D.stream_cap / 4) / t.n;
+            if (by_win < by_span) by_span = by_win;
+            if (by_span < 1) { D.error = ERR_STREAM_CAP; return false; }
             if (want > by_span) want = (int)by_span;
         }
         const int gpart = (cls == SHUF_GLOBAL) ? want : 0;
@@ -532,8 +553,8 @@ struct Sched {
             Chain* ch = chain_of(t);
             if (D.shared_stream) {
                 const long long pos = (long long)(ch->cursor + ch->commit_d);
-                if (pos + dneed + 312 > D.stream_cap) { D.error = ERR_STREAM_CAP; return false; }
-                if (pos + dneed > D.stream_len + D.span_max) { t.deferred = 1; return false; }  // generator span per round
+                // outside the window (slower chains still need its low end) or beyond the generator's span per round: wait
+                if (pos + dneed + 312 > D.stream_lo + D.stream_cap || pos + dneed > D.stream_len + D.span_max) { t.deferred = 1; return false; }
                 t.off_draw = pos;
                 if (pos + dneed > D.stream_target) D.stream_target = pos + dneed;
             } else {
@@ -608,14 +629,22 @@ struct Sched {
             e.cols = (int)cols; e.Q = Q; e.P = (int)P;
             aneed = cols * n12;
         }
+        if (D.shared_stream && p.rng_mode == RNG_MT) {  // as plan_perm: a quarter of the window / one generator span at most
+            long long fit = (D.stream_cap / 4) / m1;
+            if (D.span_max / m1 < fit) fit = D.span_max / m1;
+            if (fit < 1) { D.error = ERR_STREAM_CAP; return false; }
+            if (e.P > fit) {
+                e.P = (int)fit;
+                if (!e.sparse) { if (e.cols > e.P) e.cols = e.P; e.Q = (e.P + e.cols - 1) / e.cols; aneed = (long long)e.cols * n12; }
+            }
+        }
         const long long dneed = (p.rng_mode == RNG_MT) ? (long long)e.P * m1 : 0;
         if (arena_used + aneed > D.arena_cap || (mtwin && draws_used + dneed + 312 > D.draws_cap)) { t.deferred = 1; return false; }
         if (p.rng_mode == RNG_MT) {
             Chain* ch = chain_of(t);
             if (D.shared_stream) {
                 const long long pos = (long long)(ch->cursor + ch->commit_d);
-                if (pos + dneed + 312 > D.stream_cap) { D.error = ERR_STREAM_CAP; return false; }
-                if (pos + dneed > D.stream_len + D.span_max) { t.deferred = 1; return false; }
+                if (pos + dneed + 312 > D.stream_lo + D.stream_cap || pos + dneed > D.stream_len + D.span_max) { t.deferred = 1; return false; }
                 e.off_draw = pos;
                 if (pos + dneed > D.stream_target) D.stream_target = pos + dneed;
             } else {
@@ -802,6 +831,16 @@ struct Sched {
                 }
             }
             n_out = wpos;
+            if (D.shared_stream && D.units_started >= D.n_chains) {  // low end of the stream window: the smallest cursor of a live
+                // chain (chains that have not started yet will read from position 0: the window waits for them)
+                long long lo = D.stream_len;
+                for (int k2 = 0; k2 < wpos; ++k2) {
+                    const Chain& ch = D.chains[out_list[k2]];
+                    const long long cpos = (long long)(ch.cursor + ch.commit_d);
+                    if (cpos < lo) lo = cpos;
+                }
+                if (lo > D.stream_lo) D.stream_lo = lo;
+            }
         } else {
             for (int k = 0; k < n_in; ++k) out_list[n_out++] = in_list[k];
             int qhead = 0;

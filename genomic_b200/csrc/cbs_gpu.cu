@@ -340,6 +340,9 @@ int run_cbs(cbs_gpu_ctx* c, const std::vector<long long>& off, const uint64_t* u
     cap.seg_cap = (int)env_ll("CBS_GPU_SEG_CAP", cap.seg_cap);
     cap.split_cap = p->record_splits ? 3 * cap.seg_cap + 16 : 1;
     cap.max_live = mt ? std::max(1, cap.task_cap / 16) : std::max(1, cap.task_cap / 4);
+    // MT with one engine per unit: every chain reads the one shared stream from position 0 and the stream window only moves
+    // forward once all chains have started, so admit them all in the first round
+    if (mt && !p->chain) cap.max_live = std::max(cap.max_live, n_units);
     cap.rej_cap = 1 << 22;
 
     ENSURE(c, c->cur, sizeof(double) * (size_t)(N + 1));
@@ -387,7 +390,19 @@ int run_cbs(cbs_gpu_ctx* c, const std::vector<long long>& off, const uint64_t* u
     const bool shared_stream = mt && !p->chain;
     long long want_draws = (mt && !shared_stream) ? std::max<long long>(want_arena / 3, 8 * (Nmax + 312)) : 1;
     // shared raw MT stream (chain == 0): as long as the largest consumption of any one unit
-    long long want_stream = shared_stream ? std::max<long long>(env_ll("CBS_GPU_STREAM_MB", 16384) * (1LL << 20) / 8, 4 * (Nmax + 312)) : 0;
+    // shared raw MT stream (chain == 0): a ring of 2^k words (default 16 GB, CBS_GPU_STREAM_MB) + a mirror of its first words
+    // (any permutation and the generator's lead-in must be readable linearly).  The ring is a WINDOW on the stream: when the
+    // fastest chain is a whole window ahead of the slowest it waits (cbs_core.h plan_perm), so a small ring costs time, never an error.
+    const long long stream_mirror = shared_stream ? std::max<long long>(Nmax, GEN_LEAD) + 1024 : 0;
+    long long stream_ring = 0;
+    if (shared_stream) {
+        const long long asked = std::max<long long>(env_ll("CBS_GPU_STREAM_MB", 16384), 1) * (1LL << 20) / 8;
+        const long long least = 8 * (Nmax + 312) + 4 * GEN_LEAD;  // a quarter of the ring must hold one permutation
+        stream_ring = 1;
+        while (stream_ring < least) stream_ring <<= 1;
+        while (stream_ring * 2 <= asked) stream_ring <<= 1;
+    }
+    long long want_stream = shared_stream ? stream_ring + stream_mirror : 0;
     const long long env_arena = env_ll("CBS_GPU_ARENA_MB", 0);
     if (env_arena > 0) { want_arena = env_arena * (1LL << 20) / 8; if (mt && !shared_stream) want_draws = std::max<long long>(want_arena / 3, 8 * (Nmax + 312)); }
     {
@@ -398,7 +413,11 @@ int run_cbs(cbs_gpu_ctx* c, const std::vector<long long>& off, const uint64_t* u
             const double f = budget / need;
             want_arena = (long long)((double)want_arena * f);
             want_draws = (long long)((double)want_draws * f);
-            want_stream = (long long)((double)want_stream * f);
+            if (shared_stream) {  // the ring stays a power of two and never shrinks below what one permutation needs
+                const long long least = 8 * (Nmax + 312) + 4 * GEN_LEAD;
+                while (stream_ring / 2 >= least && (double)(stream_ring + stream_mirror) > (double)want_stream * f) stream_ring >>= 1;
+                want_stream = stream_ring + stream_mirror;
+            }
         }
     }
     if (want_arena < 4 * per_perm_max) return fail(c, CBS_GPU_ERR_OOM, "not enough device memory for the permutation arena");
@@ -447,7 +466,7 @@ int run_cbs(cbs_gpu_ctx* c, const std::vector<long long>& off, const uint64_t* u
     for (int k = 0; k < SHUF_NCLS; ++k) hD.shuf_p0[k] = c->shuf.as<int>() + (size_t)(2 * SHUF_NCLS + 1 + k) * (cap.list_cap + 1);
     hD.shared_stream = shared_stream ? 1 : 0;
     hD.stream = c->stream_buf.as<uint64_t>();
-    hD.stream_cap = shared_stream ? (long long)(c->stream_buf.cap / 8) : 0;
+    hD.stream_cap = stream_ring; hD.stream_mask = stream_ring - 1; hD.stream_mirror = stream_mirror; hD.stream_lo = 0;
     hD.stream_len = 312; hD.stream_target = 312;
     hD.jump_polys = nullptr;
     hD.span_max = 1LL << 40;
@@ -493,7 +512,10 @@ int run_cbs(cbs_gpu_ctx* c, const std::vector<long long>& off, const uint64_t* u
         CUDA_TRY(c, cudaMemcpyAsync(c->seed312.p, next, sizeof(next), cudaMemcpyHostToDevice, st));
         CUDA_TRY(c, cudaStreamSynchronize(st));
         k_init_chains<<<std::min(std::max(1, n_chains), 1024), 128, 0, st>>>(dD, c->seed312.as<uint64_t>());
-        if (shared_stream) CUDA_TRY(c, cudaMemcpyAsync(c->stream_buf.p, next, sizeof(next), cudaMemcpyHostToDevice, st));
+        if (shared_stream) {  // positions 0..311 (and their mirror)
+            CUDA_TRY(c, cudaMemcpyAsync(c->stream_buf.p, next, sizeof(next), cudaMemcpyHostToDevice, st));
+            CUDA_TRY(c, cudaMemcpyAsync(c->stream_buf.as<uint64_t>() + stream_ring, next, sizeof(next), cudaMemcpyHostToDevice, st));
+        }
         CUDA_TRY(c, cudaStreamSynchronize(st));
     }
 
@@ -666,7 +688,7 @@ int run_cbs(cbs_gpu_ctx* c, const std::vector<long long>& off, const uint64_t* u
         case ERR_SEG_CAP: return fail(c, CBS_GPU_ERR_CAPACITY, "segment table exhausted (raise CBS_GPU_SEG_CAP)");
         case ERR_SPLIT_CAP: return fail(c, CBS_GPU_ERR_CAPACITY, "split log exhausted");
         case ERR_STALL: return fail(c, CBS_GPU_ERR_CUDA, "scheduler stalled: live segments but no work could be planned");
-        case ERR_STREAM_CAP: return fail(c, CBS_GPU_ERR_CAPACITY, "shared MT stream buffer exhausted (raise CBS_GPU_STREAM_MB)");
+        case ERR_STREAM_CAP: return fail(c, CBS_GPU_ERR_CAPACITY, "MT stream window smaller than one permutation (raise CBS_GPU_STREAM_MB)");
         case ERR_ARENA: return fail(c, CBS_GPU_ERR_OOM, "permutation arena too small for one segment (raise CBS_GPU_ARENA_MB)");
         default: return fail(c, CBS_GPU_ERR_CUDA, "internal scheduler error " + std::to_string(hD.error));
         }

@@ -124,7 +124,7 @@ CBS_HD void perm_thread(const Dev& D, const Task& t, int P, int p) {
     double* sx = D.arena + t.off_sx + (long long)p * Sched::sx_stride(n);
     BlockStats bs(D.arena + t.off_bs + (long long)p * Sched::bs_stride(nb), nb);
     DrawSrc src;
-    if (D.prm.rng_mode == RNG_MT) src.init_mt((D.shared_stream ? D.stream : D.draws[D.round & 1]) + t.off_draw + (long long)p * n);
+    if (D.prm.rng_mode == RNG_MT) src.init_mt(draw_window(D, t.off_draw + (long long)p * n));
     else src.init_philox(t.key, 0u, (uint32_t)(t.perms_done + p));
     fy_shuffle_column(A, P, p, cur, n, src);
     ColumnGet g{A, P, p};
@@ -166,7 +166,7 @@ CBS_HD void edgeprep_finish(Task& t, int s, double sum1, double sum2, double tss
 }
 
 CBS_HD void edge_draw_src(const Dev& D, const Task& t, const EdgeItem& e, int r /*perm index inside the batch*/, DrawSrc& src) {
-    if (D.prm.rng_mode == RNG_MT) src.init_mt((D.shared_stream ? D.stream : D.draws[D.round & 1]) + e.off_draw + (long long)r * t.e_m1[e.side]);
+    if (D.prm.rng_mode == RNG_MT) src.init_mt(draw_window(D, e.off_draw + (long long)r * t.e_m1[e.side]));
     else src.init_philox(t.key, (uint32_t)(1 + e.side), (uint32_t)(e.perm0 + r));
 }
 
@@ -267,9 +267,8 @@ CBS_HD void mt_generate_seq(Chain& ch, const uint64_t* prev_arena, uint64_t* cur
 
 // shared stream: extend W[0..stream_len) to at least stream_target words (sequential form)
 CBS_HD void mt_extend_stream_seq(Dev& D) {
-    uint64_t* w = D.stream;
     long long len = D.stream_len;
-    while (len < D.stream_target) { w[len] = mt_twist(w[len - 312], w[len - 311], w[len - 156]); ++len; }
+    while (len < D.stream_target) { stream_put(D, len, mt_twist(stream_get(D, len - 312), stream_get(D, len - 311), stream_get(D, len - 156))); ++len; }
     D.stream_len = len;
 }
 

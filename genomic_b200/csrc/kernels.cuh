@@ -323,22 +323,22 @@ __global__ void __launch_bounds__(32) k_prep(Dev* D) {
 #define GEN_NSEG 512
 #define GEN_LEAD 20480
 
-// extend the raw stream sequentially from `from` to `to` (state = the 312 words before `from`);
-// called by all threads of a CTA with >= 156 threads
-__device__ void gen_sequential(uint64_t* w, long long from, long long to, uint64_t* st) {
+// extend the raw stream (ring + mirror, cbs_core.h) sequentially from position `from` to `to` (state = the 312 words
+// before `from`); called by all threads of a CTA with >= 156 threads
+__device__ void gen_sequential(const Dev& D, long long from, long long to, uint64_t* st) {
     const int k = threadIdx.x;
     __syncthreads();
-    for (int u = k; u < 312; u += blockDim.x) st[u] = w[from - 312 + u];
+    for (int u = k; u < 312; u += blockDim.x) st[u] = stream_get(D, from - 312 + u);
     __syncthreads();
     for (long long pos = from; pos < to; pos += 312) {
         uint64_t v = 0;
         if (k < 156) v = mt_twist(st[k], st[k + 1], st[k + 156]);
         __syncthreads();
-        if (k < 156) { st[k] = v; if (pos + k < to) w[pos + k] = v; }
+        if (k < 156) { st[k] = v; if (pos + k < to) stream_put(D, pos + k, v); }
         __syncthreads();
         if (k < 156) { const int kk = k + 156; v = mt_twist(st[kk], st[(kk + 1) % 312], st[kk - 156]); }
         __syncthreads();
-        if (k < 156) { st[k + 156] = v; if (pos + 156 + k < to) w[pos + 156 + k] = v; }
+        if (k < 156) { st[k + 156] = v; if (pos + 156 + k < to) stream_put(D, pos + 156 + k, v); }
         __syncthreads();
     }
 }
@@ -346,6 +346,7 @@ __device__ void gen_sequential(uint64_t* w, long long from, long long to, uint64
 // ahead = 0: extend the stream to what this round's shuffles need (normally nothing: see ahead = 1).
 // ahead = 1: runs on its own stream next to the shuffles and the scan of the round and extends the stream
 //            GEN_AHEAD words beyond the need, so that the next round usually finds its words already generated.
+// The stream never grows beyond stream_lo + stream_cap - 312: positions from stream_lo on are still needed by a chain.
 #define GEN_AHEAD (64LL << 20)
 __global__ void __launch_bounds__(192) k_gen_lead(Dev* D, int ahead) {
     __shared__ uint64_t st[312];
@@ -360,13 +361,13 @@ __global__ void __launch_bounds__(192) k_gen_lead(Dev* D, int ahead) {
     if (ahead) {
         target += GEN_AHEAD;
         if (target > len + D->span_max) target = len + D->span_max;
-        if (target > D->stream_cap - 312) target = D->stream_cap - 312;
     }
+    if (target > D->stream_lo + D->stream_cap - 312) target = D->stream_lo + D->stream_cap - 312;  // the scheduler never asks for more
     if (len >= target) { if (threadIdx.x == 0) { D->gen_base = len; D->gen_E = 0; } return; }
     const long long E = target - len;
     long long lead_end = target;
     if (D->jump_polys && E > GEN_SEG) lead_end = len + GEN_LEAD;
-    gen_sequential(D->stream, len, lead_end, st);
+    gen_sequential(*D, len, lead_end, st);
     if (threadIdx.x == 0) { D->gen_base = len; D->gen_E = E; D->gen_lead_end = lead_end; }
 }
 
@@ -378,7 +379,6 @@ __global__ void __launch_bounds__(320) k_gen_par(Dev* D) {
     if (E <= GEN_SEG) return;  // k_gen_lead did everything
     const int c = blockIdx.x;
     if ((long long)c * GEN_SEG >= E) return;
-    uint64_t* w = D->stream;
     const long long seg_lo = base + (long long)c * GEN_SEG;
     const long long seg_hi = base + ((E < (long long)(c + 1) * GEN_SEG) ? E : (long long)(c + 1) * GEN_SEG);
     long long from = D->gen_lead_end;
@@ -387,7 +387,8 @@ __global__ void __launch_bounds__(320) k_gen_par(Dev* D) {
         for (int u = threadIdx.x; u < 312; u += blockDim.x) sp[u] = g[u];
         __syncthreads();
         if (threadIdx.x < 312) {
-            const uint64_t* src = w + base + threadIdx.x;
+            // the lead-in W[base .. base+GEN_LEAD) is read linearly from the ring slot of `base` (the mirror covers it)
+            const uint64_t* src = D->stream + (base & D->stream_mask) + threadIdx.x;
             uint64_t acc0 = 0, acc1 = 0;
             for (int wd = 0; wd < 312; ++wd) {
                 const uint64_t bits = sp[wd];
@@ -398,12 +399,12 @@ __global__ void __launch_bounds__(320) k_gen_par(Dev* D) {
                     if ((bits >> (bpos + 1)) & 1ULL) acc1 ^= s0[bpos + 1];
                 }
             }
-            w[seg_lo + threadIdx.x] = acc0 ^ acc1;
+            stream_put(*D, seg_lo + threadIdx.x, acc0 ^ acc1);
         }
         __syncthreads();
         from = seg_lo + 312;
     }
-    if (from < seg_hi) gen_sequential(w, from, seg_hi, st);
+    if (from < seg_hi) gen_sequential(*D, from, seg_hi, st);
 }
 
 // ------------------------------------------------------------------------------------
@@ -570,7 +571,7 @@ __device__ void perm_warp(Dev* D, const Task& t, int p, Idx s_idx, unsigned char
     const double* __restrict__ cur = D->cur + base;
     const bool mt = D->prm.rng_mode == RNG_MT;
     const uint64_t* win = nullptr;
-    if (mt) win = (D->shared_stream ? D->stream : D->draws[D->round & 1]) + t.off_draw + (long long)p * n;
+    if (mt) win = draw_window(*D, t.off_draw + (long long)p * n);
     const uint32_t k0 = (uint32_t)t.key, k1 = (uint32_t)(t.key >> 32), permno = (uint32_t)(t.perms_done + p);
     for (int k = lane; k < n; k += 32) s_idx.st(k, k);
     __syncwarp();
@@ -736,7 +737,7 @@ __global__ void __launch_bounds__(T) k_shuffle(Dev* D, int cls, int hbits) {
         const int n = t.n;
         const long long base = D->unit_off[t.unit] + t.lo;
         ShufDraws<MT> src;
-        src.win = MT ? (D->shared_stream ? D->stream : D->draws[D->round & 1]) + t.off_draw + (long long)p * n : nullptr;
+        src.win = MT ? draw_window(*D, t.off_draw + (long long)p * n) : nullptr;
         src.k0 = (uint32_t)t.key; src.k1 = (uint32_t)(t.key >> 32); src.permno = (uint32_t)(t.perms_done + p);
         double* sx = D->arena + t.off_sx + (long long)p * Sched::sx_stride(n);
         // weighted CBS (wxperm, CBS.cpp:538-547): the shuffle runs on y = cur*rw, position i-1 receives y[.]/rw[i-1]
@@ -778,7 +779,7 @@ __global__ void __cluster_dims__(R, 1, 1) __launch_bounds__(T) k_shuffle_cluster
         const int n = t.n;
         const long long base = D->unit_off[t.unit] + t.lo;
         ShufDraws<MT> src;
-        src.win = MT ? (D->shared_stream ? D->stream : D->draws[D->round & 1]) + t.off_draw + (long long)p * n : nullptr;
+        src.win = MT ? draw_window(*D, t.off_draw + (long long)p * n) : nullptr;
         src.k0 = (uint32_t)t.key; src.k1 = (uint32_t)(t.key >> 32); src.permno = (uint32_t)(t.perms_done + p);
         double* sx = D->arena + t.off_sx + (long long)p * Sched::sx_stride(n);
         const double* vals = D->w ? D->ycur + base : D->cur + base;

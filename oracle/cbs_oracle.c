@@ -761,6 +761,7 @@ int orc_segment(const double* x, int n, const orc_seg_opts* o, orc_rng* rng, uin
             e->lo = lo; e->hi = hi; e->ostat = z.ostat; e->iseg0 = z.iseg[0]; e->iseg1 = z.iseg[1];
             e->ncpt = z.ncpt; e->icpt0 = z.icpt[0]; e->icpt1 = z.icpt[1];
             e->perms_run = z.perms_run; e->nrej = z.nrej; e->exit_code = z.exit_code; e->called = called;
+            e->edge_p0 = called ? z.edge_p[0] : -1.0; e->edge_p1 = called ? z.edge_p[1] : -1.0;
         }
         ++nlog;
         if (nends + 2 > ends_cap) { ends_cap *= 2; ends = (int*)realloc(ends, sizeof(int) * (size_t)ends_cap); }

@@ -84,6 +84,7 @@ typedef struct orc_split_rec {
     int ncpt, icpt0, icpt1;
     int perms_run, nrej, exit_code;
     int called; /* 1 if fndcpt ran, 0 if skipped (too short / all equal) */
+    double edge_p0, edge_p1; /* tpermp p-values of the two boundaries (CBS.cpp:877,883), -1 when not run */
 } orc_split_rec;
 
 typedef struct orc_seg_opts {

@@ -83,6 +83,8 @@ class OrcSplitRec(C.Structure):
         ("nrej", C.c_int),
         ("exit_code", C.c_int),
         ("called", C.c_int),
+        ("edge_p0", C.c_double),
+        ("edge_p1", C.c_double),
     ]
 
 

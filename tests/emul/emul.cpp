@@ -102,9 +102,20 @@ extern "C" int64_t emul_segment_units(const double* values, const int64_t* unit_
     D.draws[0] = d0.data(); D.draws[1] = d1.data();
     // shared stream exactly as the product configures it: MT replay with one engine per unit
     D.shared_stream = (rng_mode == RNG_MT && !chain) ? 1 : 0;
-    std::vector<uint64_t> stream(D.shared_stream ? (size_t)(1 << 24) : 1);
-    D.stream = stream.data(); D.stream_cap = D.shared_stream ? (1 << 24) : 0;
-    if (D.shared_stream) { mt_seed_next312(seed, D.stream); D.stream_len = 312; D.stream_target = 312; }
+    // ring of 2^k words + mirror; EMUL_STREAM_RING (words) shrinks the ring to exercise the window logic of the scheduler
+    long long nmax_unit = 1;
+    for (int u = 0; u < n_units; ++u) if (unit_off[u + 1] - unit_off[u] > nmax_unit) nmax_unit = unit_off[u + 1] - unit_off[u];
+    const long long stream_ring_words = getenv("EMUL_STREAM_RING") ? atoll(getenv("EMUL_STREAM_RING")) : (1LL << 24);
+    const long long stream_mirror_words = nmax_unit + 1024;
+    const long long sring = D.shared_stream ? stream_ring_words : 0, smirror = D.shared_stream ? stream_mirror_words : 0;
+    std::vector<uint64_t> stream(D.shared_stream ? (size_t)(sring + smirror) : 1);
+    D.stream = stream.data(); D.stream_cap = sring; D.stream_mask = sring - 1; D.stream_mirror = smirror; D.stream_lo = 0;
+    if (D.shared_stream) {
+        uint64_t next[312];
+        mt_seed_next312(seed, next);
+        for (int u = 0; u < 312; ++u) stream_put(D, u, next[u]);
+        D.stream_len = 312; D.stream_target = 312;
+    }
     D.span_max = 1LL << 40;
     std::vector<int> shuf_store(3 * SHUF_NCLS * (size_t)(4 * 4096 + n_units + 32));
     for (int k = 0; k < SHUF_NCLS; ++k) D.shuf_p0[k] = shuf_store.data() + (size_t)(2 * SHUF_NCLS + k) * (4 * 4096 + n_units + 32);
@@ -158,7 +169,7 @@ extern "C" int64_t emul_segment_units(const double* values, const int64_t* unit_
                 {
                     const long long base = D.unit_off[t.unit] + t.lo;
                     DrawSrc src;
-                    if (D.prm.rng_mode == RNG_MT) src.init_mt((D.shared_stream ? D.stream : D.draws[D.round & 1]) + t.off_draw + (long long)p * t.n);
+                    if (D.prm.rng_mode == RNG_MT) src.init_mt(draw_window(D, t.off_draw + (long long)p * t.n));
                     else src.init_philox(t.key, 0u, (uint32_t)(t.perms_done + p));
                     fy_shuffle_column(A.data(), it.P, p, D.cur + base, t.n, src);
                     ColumnGet g{A.data(), it.P, p};

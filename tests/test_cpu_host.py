@@ -94,6 +94,26 @@ def test_scheduler_emulation_matches_oracle(oracle, emul, mode):
             assert np.array_equal(want["draws"], got["draws"])
 
 
+def test_scheduler_emulation_small_stream_window(oracle, emul, monkeypatch):
+    """MT replay, one engine per unit: the shared stream is a window (ring) on the engine's output.  With a ring of
+    16384 words the fast chains must wait for the slow ones and the ring wraps many times; results and draw counts
+    stay those of the oracle (no input may exhaust the stream buffer)."""
+    monkeypatch.setenv("EMUL_STREAM_RING", "16384")
+    rng = np.random.default_rng(77)
+    for trial in range(10):
+        units = [make_unit(rng, int(rng.integers(200, 1500)), int(rng.integers(0, 5))) for _ in range(int(rng.integers(2, 7)))]
+        units.insert(int(rng.integers(0, len(units))), make_unit(rng, 1300, 0))  # a null unit: thousands of draws per permutation batch
+        vals, off = pack(units)
+        p = SegParams(nperm=int(rng.choice([200, 1000])), alpha=0.01, do_smooth=False, rng_kind=0, chain=False,
+                      seed=int(rng.integers(1, 100)))
+        want = oracle.segment_units(vals, off, np.ones(len(off) - 1, np.int32), p)
+        assert int(want["draws"].max()) > 16384  # the stream really outruns the ring
+        got = emul(vals, off, p, first_batch=16, max_batch=64, max_live=64)  # all chains start in round 0, as in the product
+        assert np.array_equal(want["seg_count"], got["seg_count"])
+        assert np.array_equal(want["lengths"], got["lengths"]) and np.array_equal(want["means"], got["means"])
+        assert np.array_equal(want["draws"], got["draws"])
+
+
 def test_scheduler_emulation_edge_tests(oracle, emul):
     rng = np.random.default_rng(9)
     for trial in range(12):

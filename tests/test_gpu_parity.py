@@ -122,6 +122,55 @@ def test_split_log_matches(ctx, oracle):
                 assert g["icpt0"] == w.icpt0
             if w.ncpt == 2:
                 assert g["icpt1"] == w.icpt1
+            check_edge_pvalues(g, w, p.nperm)
+
+
+def check_edge_pvalues(g, w, nperm):
+    """tpermp p-values of both boundaries (CBS.cpp:877,883): the device reports the rejection counts / shortcut status"""
+    for side, want_p in ((0, w.edge_p0), (1, w.edge_p1)):
+        if want_p < 0:
+            continue  # tpermp did not run (no split, or a single change point at the segment end)
+        st, nrej = g[f"e_status{side}"], g[f"e_nrej{side}"]
+        got_p = 1.0 if st == 1 else 0.0 if st == 2 else nrej / nperm
+        assert got_p == want_p, (g["unit"], g["lo"], g["hi"], side, st, nrej, want_p)
+
+
+def check_split_log(got, want, nperm):
+    assert len(got.splits) == len(want["log"])
+    compared = 0
+    by_key = {(g["unit"], g["lo"], g["hi"]): g for g in got.splits}  # decisions are logged in order of completion
+    assert len(by_key) == len(got.splits)
+    for u, w in want["log"]:
+        g = by_key[(u, w.lo, w.hi)]
+        assert (g["called"], g["ncpt"]) == (w.called, w.ncpt)
+        if w.called:
+            assert (g["perms_run"], g["exit_code"]) == (w.perms_run, w.exit_code)
+            check_edge_pvalues(g, w, nperm)
+            compared += int(0.0 < w.edge_p0 < 1.0) + int(0.0 < w.edge_p1 < 1.0)
+    return compared
+
+
+def test_edge_pvalues_chain_mode(ctx, oracle):
+    """One serial stream (chain=1, what `cna segment` does), weak shifts in the middle of units of 4000-7000 markers and a
+    generous alpha, so that tpermp runs on many boundaries, with up to 1400 draws per permutation (nperm x m1 ~ 3e6 per test) and p-values strictly between 0 and 1.  The edge permutations must read THIS round's draws, i.e. run after the
+    generator: every tpermp rejection count is compared with the oracle (lengths alone can hide a stale read)."""
+    rng = np.random.default_rng(131)
+    compared = 0
+    for trial in range(4):
+        units = []
+        for k in range(2):
+            n = int(rng.integers(4000, 7000))
+            x = rng.normal(0, 0.2, n)
+            a = int(rng.integers(n // 5, n // 3)); b = int(rng.integers(n // 2, 4 * n // 5))
+            x[a:b] += float(rng.choice([0.015, 0.02]))
+            units.append(f32(x))
+        vals, off = pack(units)
+        p = SegParams(nperm=2000, alpha=0.6, do_smooth=False, rng_kind=0, chain=True, seed=1 + trial)
+        want = oracle.segment_units(vals, off, np.ones(len(off) - 1, np.int32), p, want_log=True)
+        got = ctx.segment_batch(vals, off, gparams(p, record_splits=True))
+        assert np.array_equal(got.lengths, want["lengths"]) and np.array_equal(got.draws, want["draws"])
+        compared += check_split_log(got, want, p.nperm)
+    assert compared >= 20  # permutation-based edge tests with 0 < p < 1 were compared
 
 
 def test_edge_tests_large_m1(ctx, oracle):
@@ -137,6 +186,9 @@ def test_edge_tests_large_m1(ctx, oracle):
         for mode in range(3):
             p = SegParams(nperm=300, alpha=0.05, do_smooth=False, rng_kind=1 if mode == 2 else 0, chain=(mode == 0), seed=3)
             check_batch(ctx, oracle, vals, off, p, first_batch=32, max_batch=128)
+            want = oracle.segment_units(vals, off, np.ones(1, np.int32), p, want_log=True)
+            got = ctx.segment_batch(vals, off, gparams(p, record_splits=True, first_batch=32, max_batch=128))
+            check_split_log(got, want, p.nperm)
 
 
 def test_smooth_matches_oracle(ctx, oracle):
@@ -243,6 +295,26 @@ def test_segment_long_units(ctx, oracle, mode):
     vals, off = pack(units)
     p = SegParams(nperm=40, alpha=0.05, do_smooth=False, rng_kind=1 if mode == "philox" else 0, chain=False, seed=4)
     check_batch(ctx, oracle, vals, off, p, first_batch=24, max_batch=64)
+
+
+def test_small_stream_window(oracle, monkeypatch):
+    """MT replay with one engine per unit reads ONE shared raw stream through a window (ring buffer).  With the ring
+    forced down to its minimum (CBS_GPU_STREAM_MB=1) the units' cursors run many windows apart: fast chains wait for
+    slow ones, the ring wraps, and the result is still the oracle's, draws included.  (Round 1 materialised the whole
+    stream and failed with a capacity error when a unit outran the buffer.)"""
+    monkeypatch.setenv("CBS_GPU_STREAM_MB", "1")
+    c = genomic_b200.Context(0)
+    try:
+        rng = np.random.default_rng(63)
+        units = [f32(rng.normal(0, 0.2, n)) for n in (3000, 9000, 700, 20000, 5000)]
+        units[1][4000:] += 0.03
+        units[3][:9000] -= 0.02
+        vals, off = pack(units)
+        p = SegParams(nperm=2000, alpha=0.01, do_smooth=False, rng_kind=0, chain=False, seed=5)
+        got, want = check_batch(c, oracle, vals, off, p)
+        assert int(want["draws"].max()) > 8 * (1 << 17)  # far more draws than the 2^17..2^18-word ring holds
+    finally:
+        c.close()
 
 
 def test_stress_50k_segments_replay(ctx, oracle):
