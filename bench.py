@@ -149,35 +149,33 @@ def read_peaks() -> dict:
 
 
 # ---------------------------------------------------------------------------------------------
-def cpu_reference_run(chroms, nperm: int, threads: int, sample: int = 0, repeat: int = 1):
-    """Times the reference's own lib/cbs (oracle/_ref, unmodified sources) on the given chromosomes of
-    the synthetic sample: smoothing + CBS per chromosome, one std::mt19937_64(1) per unit, units spread
-    over `threads` host threads.  Returns (markers, seconds, kind)."""
+def cpu_reference_run(nperm: int, threads: int, sample: int = 0):
+    """One step of the bench workload on the host: the reference's own lib/cbs (oracle/_ref, the unmodified sources) on ALL 23
+    chromosomes of the synthetic sample -- smoothing + CBS per chromosome, one std::mt19937_64(1) per unit (what the GPU arm's
+    MT replay reproduces), units handed out largest first to `threads` host threads.  Returns (markers, seconds, kind, threads)."""
     from genomic_b200 import synth
     from oracle.pyoracle import Oracle, Ref, SegParams
-    vals, off, lab, _ = synth.cohort([sample], scale=1.0, chroms=chroms)
+    vals, off, lab, _ = synth.cohort([sample], scale=1.0)
     p = SegParams(nperm=nperm, alpha=ALPHA, do_smooth=True, rng_kind=0, chain=False, seed=1)
     x = vals.astype(np.float64)
-    best = None
     if Ref.available():
         eng, kind = Ref(), "reference"
-        for _ in range(repeat):
-            t0 = time.perf_counter()
-            eng.segment_units(x, off, lab, p, nthreads=threads)
-            dt = time.perf_counter() - t0
-            best = dt if best is None else min(best, dt)
+        threads = max(1, min(threads, len(off) - 1))  # a unit is the grain: no more threads than units can be busy
+        t0 = time.perf_counter()
+        eng.segment_units(x, off, lab, p, nthreads=threads)
+        dt = time.perf_counter() - t0
     else:  # reference sources were never available on this box: time the C restatement instead
         eng, kind = Oracle(), "port"
         threads = 1
-        for _ in range(repeat):
-            t0 = time.perf_counter()
-            eng.segment_units(x, off, lab, p)
-            dt = time.perf_counter() - t0
-            best = dt if best is None else min(best, dt)
-    return int(off[-1]), best, kind, threads
+        t0 = time.perf_counter()
+        eng.segment_units(x, off, lab, p)
+        dt = time.perf_counter() - t0
+    return int(off[-1]), dt, kind, threads
 
 
-CPU_SAMPLE_CHROMS = [19, 20, 21, 22]  # the four smallest autosomes: 131,113 markers
+CPU_SAMPLE = ("the whole synthetic sample 0 (all 23 chromosomes, 1,800,000 markers): the workload of one step of this bench; "
+              "chromosomes are handed to the host threads largest first, the longest chromosome bounds the wall time")
+CPU_BUDGET_S = 200.0  # the reference arm stops adding steps when the next one would pass this
 
 
 def run_reference_arm(args):
@@ -185,25 +183,25 @@ def run_reference_arm(args):
     if rank != 0:
         return  # rank 0 alone runs and prints the reference arm
     threads = os.cpu_count() or 1
-    chroms = [13, 14, 15, 16, 17, 18, 19, 20, 21, 22] if threads >= 8 else CPU_SAMPLE_CHROMS
     times = []
-    markers = 0
-    kind = "reference"
-    used = threads
-    for it in range(args.warmup + args.steps):
-        markers, dt, kind, used = cpu_reference_run(chroms, NPERM, threads, sample=0)
-        if it >= args.warmup:
-            times.append(dt)
+    markers, kind, used = 0, "reference", threads
+    # one step takes the reference about 100 s on 16 cores, so the requested warm-up is dropped (CPU code has none to do) and
+    # steps are added only while they fit the time budget; `steps` in the line is the number actually timed
+    while len(times) < max(1, args.steps):
+        markers, dt, kind, used = cpu_reference_run(NPERM, threads, sample=0)
+        times.append(dt)
+        if sum(times) + dt > CPU_BUDGET_S:
+            break
     total = sum(times)
     value = markers * len(times) / total
-    sample = (f"chromosomes {chroms} of synthetic sample 0 ({markers} of 1,800,000 markers), one unit per host "
-              f"thread; per-marker cost grows with chromosome length, so this OVERSTATES the CPU rate on the full sample")
     line = {
-        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times), "higher_is_better": True, "scaling": "weak",
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": len(times),
+        "warmup": 0, "ms_per_step": 1e3 * total / len(times), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": workload_name(1, 1.0), "sample": sample},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": used, "kind": kind, "sample": sample},
+        "config": {"workload": workload_name(1, 1.0), "rng": "mt", "chain": False, "samples_per_gpu": 1,
+                   "note": f"requested steps {args.steps} / warmup {args.warmup}; timed {len(times)} step(s) of ~{total / len(times):.0f} s "
+                           f"within a {CPU_BUDGET_S:.0f} s budget"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": used, "kind": kind, "sample": CPU_SAMPLE},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -299,11 +297,12 @@ def run_gpu_arm(args):
     launches_per_step = int(res.kernel_launches)
 
     # Roofline inputs, kept OUT of the timed steps:
-    #  (1) the same K steps once more with every kernel launch bracketed by CUDA events on the launching
-    #      stream -> per-kernel device time (sum over launches) and each kernel's share of the step;
+    #  (1) the same K steps once more with every kernel launch bracketed by CUDA events, ALL kernels on the one
+    #      stream (the timed steps overlap independent kernels on side streams) -> per-kernel device time (sum over
+    #      launches) on a serialised time base: the groups add up to the serialised step, none can exceed it;
     #  (2) one step with the scan kernel's work counters on (device atomics slow that kernel, so this
     #      step is never timed) -> arcs examined = the kernel's algorithmic work.
-    ctx.set_profiling(events=True)
+    ctx.set_profiling(events=True, serial=True)  # one stream: the per-kernel event times do not overlap
     kms = None
     prof_ms = 0.0
     for _ in range(args.steps):
@@ -328,65 +327,56 @@ def run_gpu_arm(args):
 
     if rank == 0:
         peaks = read_peaks()
-        ksum = sum(kms.values()) or 1.0
+        ksum = sum(kms.values()) or 1.0  # the serialised step: all kernels on one stream
         groups = {"scan": kms["scan"], "shuffle": kms["shuf0"] + kms["shuf1"] + kms["shuf2"] + kms["shuf3"] + kms["perm"],
                   "chain": kms["prefix"], "gen": kms["gen"], "prep": kms["prep"],
                   "edge": kms["edgeprep"] + kms["edgeperm"], "smooth": kms["smooth"], "sched": kms["sched"], "means": kms["means"]}
         dominant = max(groups, key=groups.get)
-        elems = float(res_c.perm_elems)  # markers x permutations actually shuffled in one step
-        scan_s = kms["scan"] * 1e-3
-        roof_scan = {
-            "bound": "fp64", "kernel": "k_scan",
-            "achieved": arcs / scan_s / 1e12 if scan_s else None, "peak": fp64_tinst,
-            "unit": "T fp64-pipe lane-inst/s", "frac": (arcs / scan_s / 1e12 / fp64_tinst) if scan_s and fp64_tinst else None,
-            "traffic": None, "arcs_per_step": arcs, "slots_issued_per_step": slots,
-            "algorithmic_work": "1 FP64-pipe instruction (DADD S_j - S_i) per arc (i,j) actually examined; the compare runs on "
-                                "the integer pipe.  Units of 32x8 arcs are discarded beforehand from a table of local extrema, so "
-                                "only a few percent of the reference's candidate arcs are examined: the kernel is bound by the "
-                                "issue of the pruning tests, not by the FP64 pipe",
-            "markers_perms_per_s": elems / scan_s if scan_s else None,
-            "hbm_equivalent": {"bytes_per_marker_perm": 8, "achieved_gbs": 8.0 * elems / scan_s / 1e9 if scan_s else None,
-                               "peak_gbs": peaks["hbm_gbs"], "frac": (8.0 * elems / scan_s / 1e9 / peaks["hbm_gbs"]) if scan_s else None,
-                               "note": "every prefix sum is read at least once (8 B per marker per permutation)"},
-            "ms_per_step": kms["scan"], "share_of_step": kms["scan"] / ksum,
-            "peak_source": "cbs_gpu_measure_fp64: DADD issue-rate microbenchmark on this GPU in this run "
-                           "(MEASURED_PEAKS.json has no FP64 figure)",
-        }
-        pfx_s = kms["prefix"] * 1e-3
-        roof_prefix = {
-            "bound": "hbm", "kernel": "k_chain", "achieved": 16.0 * elems / pfx_s / 1e9 if pfx_s else None,
-            "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": (16.0 * elems / pfx_s / 1e9 / peaks["hbm_gbs"]) if pfx_s else None,
-            "traffic": None, "algorithmic_bytes": "16 B per marker per permutation (read the permuted value, write S)",
-            "ms_per_step": kms["prefix"], "share_of_step": kms["prefix"] / ksum, "peak_source": peaks["source"],
-            "note": "one dependent DADD chain per permutation (8 cycles per marker): latency bound unless thousands of "
-                    "permutations are in flight",
-        }
-        shuf_s = groups["shuffle"] * 1e-3
-        roof_shuffle = {
-            "bound": "hbm", "kernel": "k_perm_smem/k_perm", "achieved": 16.0 * elems / shuf_s / 1e9 if shuf_s else None,
-            "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": (16.0 * elems / shuf_s / 1e9 / peaks["hbm_gbs"]) if shuf_s else None,
-            "traffic": None, "algorithmic_bytes": "16 B per marker per permutation (8 B gather + 8 B write, SURVEY 8d)",
-            "ms_per_step": groups["shuffle"], "share_of_step": groups["shuffle"] / ksum, "peak_source": peaks["source"],
-            "note": "the Fisher-Yates itself runs on 16-bit indices in shared memory; it is latency bound, not HBM bound; "
-                    "classes run concurrently on several streams, so the sum of their times exceeds their share of the step",
-        }
-        # DRAM traffic per launch from the committed ncu --set full capture (profiles/ncu_traffic.json, written by
-        # tools/ncu_kernel_summary.py): dram__bytes_read.sum + dram__bytes_write.sum, averaged over the captured launches
-        # (a busy round of the same workload); null if the file is absent
+        elems = float(res_c.perm_elems)  # markers x permutations actually used by the decisions of one step
+        # DRAM traffic per launch from the committed ncu --set full capture of one busy round (profiles/ncu_traffic.json, written
+        # by tools/ncu_kernel_summary.py): dram__bytes_read.sum + dram__bytes_write.sum of the captured launch and the markers x
+        # permutations that launch processed (the round's plan), hence measured bytes per element next to the algorithmic ones
         try:
             ncu = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
         except Exception:
             ncu = {}
-        def traffic(kernel):
+
+        def traffic(kernel, alg_bytes_per_elem):
             k = ncu.get(kernel)
             if not k:
                 return None
-            return {"dram_bytes_per_launch": k["dram_read_bytes_per_launch"] + k["dram_write_bytes_per_launch"],
-                    "launch_ms": k["avg_ms"], "launches_captured": k["launches"], "source": "profiles/ncu_traffic.json"}
-        roof_scan["traffic"] = traffic("k_scan")
-        roof_prefix["traffic"] = traffic("k_chain")
-        roof_shuffle["traffic"] = traffic("k_perm_smem")
-        roofs = {"scan": roof_scan, "chain": roof_prefix, "shuffle": roof_shuffle}
+            total = k["dram_read_bytes"] + k["dram_write_bytes"]
+            return {"dram_bytes_per_launch": total, "launch_ms": k["ms"], "elements_in_launch": k["elements"],
+                    "dram_bytes_per_element": total / k["elements"], "algorithmic_bytes_per_element": alg_bytes_per_elem,
+                    "traffic_over_algorithmic": total / k["elements"] / alg_bytes_per_elem, "launches_captured": k["launches"],
+                    "source": "profiles/ncu_traffic.json (" + ncu.get("_capture", "ncu --set full") + ")"}
+
+        def hbm_roof(kernel, ms, bytes_per_elem, what, note):
+            sec = ms * 1e-3
+            gbs = bytes_per_elem * elems / sec / 1e9 if sec else None
+            return {"bound": "hbm", "kernel": kernel, "achieved": gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                    "frac": gbs / peaks["hbm_gbs"] if gbs else None, "traffic": traffic(kernel.split("/")[0], bytes_per_elem),
+                    "algorithmic_bytes": what, "ms_per_step": ms, "share_of_serialised_step": ms / ksum,
+                    "time_base": "sum of the kernel's launches in a pass with every kernel on ONE stream (no overlap), CUDA events",
+                    "peak_source": peaks["source"], "note": note}
+
+        scan_s = kms["scan"] * 1e-3
+        roof_scan = hbm_roof("k_scan", kms["scan"], 8.0, "8 B per marker per permutation: every prefix sum is read at least once",
+                             "branch and bound: table-driven pruning discards most candidate arcs before any prefix sum is read; "
+                             "the kernel is bound by the issue of the pruning tests, neither by HBM nor by the FP64 pipe")
+        roof_scan["fp64"] = {"arcs_per_step": arcs, "slots_issued_per_step": slots, "peak_T_inst_per_s": fp64_tinst,
+                             "achieved_T_inst_per_s": arcs / scan_s / 1e12 if scan_s else None,
+                             "frac": (arcs / scan_s / 1e12 / fp64_tinst) if scan_s and fp64_tinst else None,
+                             "note": "1 FP64-pipe instruction (DADD S_j - S_i) per arc actually examined; peak = DADD issue-rate "
+                                     "microbenchmark on this GPU in this run (MEASURED_PEAKS.json has no FP64 figure)"}
+        roof_chain = hbm_roof("k_chain", kms["prefix"], 16.0, "16 B per marker per permutation (read the permuted value, write S)",
+                              "one dependent DADD chain per permutation (8 cycles per marker): latency bound unless thousands of "
+                              "permutations are in flight")
+        roof_shuffle = hbm_roof("k_shuffle/k_shuffle_cluster", groups["shuffle"], 16.0,
+                                "16 B per marker per permutation (8 B gather + 8 B write, SURVEY 8d); the 8 B raw MT word per marker is extra",
+                                "exact parallel Fisher-Yates replay, one CTA (or cluster) per permutation; last[] lives in shared "
+                                "memory, so HBM only sees the MT words and the written row; bound by shared-memory latency and barriers")
+        roofs = {"scan": roof_scan, "chain": roof_chain, "shuffle": roof_shuffle}
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": warm,
             "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -400,22 +390,20 @@ def run_gpu_arm(args):
             "gpu_launches": launches_per_step * args.steps,
             "step_ms": {"device_resident": steps_device, "e2e": steps_host},
             "clocks": clocks,
-            "kernel_ms_per_step": {k: round(v, 3) for k, v in kms.items()},
-            "kernel_groups_ms_per_step": {k: round(v, 3) for k, v in groups.items()},
-            "event_profiled_ms_per_step": prof_ms / args.steps,
+            "kernel_ms_per_step_serialised": {k: round(v, 3) for k, v in kms.items()},
+            "kernel_groups_ms_per_step_serialised": {k: round(v, 3) for k, v in groups.items()},
+            "serialised_step_ms": {"kernels": round(ksum, 3), "wall": round(prof_ms / args.steps, 3),
+                                   "note": "profile pass, all kernels on one stream; the timed steps above overlap independent kernels"},
             "dominant_kernel": dominant,
             "roofline": roofs.get(dominant, roof_scan),
-            "roofline_scan": roof_scan, "roofline_chain": roof_prefix, "roofline_shuffle": roof_shuffle,
+            "roofline_scan": roof_scan, "roofline_chain": roof_chain, "roofline_shuffle": roof_shuffle,
             "segments": int(len(res.lengths)), "perms_run": int(res.perms_run), "perm_elements": int(res.perm_elems),
             "rounds": int(res.rounds),
         }
         if world == 1 and not args.no_cpu:
-            m, dt, kind, used = cpu_reference_run(CPU_SAMPLE_CHROMS, NPERM, min(os.cpu_count() or 1, len(CPU_SAMPLE_CHROMS)))
-            line["cpu_baseline"] = {
-                "value": m / dt, "unit": UNIT, "cores": used, "kind": kind,
-                "sample": (f"chromosomes {CPU_SAMPLE_CHROMS} of the same synthetic sample ({m} of 1,800,000 markers, "
-                           f"{dt:.1f} s); smaller chromosomes are cheaper per marker, so this overstates the CPU rate"),
-            }
+            m, dt, kind, used = cpu_reference_run(NPERM, os.cpu_count() or 1)
+            line["cpu_baseline"] = {"value": m / dt, "unit": UNIT, "cores": used, "kind": kind, "seconds": round(dt, 1),
+                                    "sample": CPU_SAMPLE}
         print(json.dumps(line), flush=True)
     if dist is not None:
         dist.barrier()

@@ -196,9 +196,10 @@ class Context:
     def set_stream(self, cuda_stream_ptr: int | None):
         self._check(self.lib.cbs_gpu_set_stream(self.h, C.c_void_p(cuda_stream_ptr or 0)))
 
-    def set_profiling(self, events: bool = False, counters: bool = False):
-        """events: per-launch CUDA event timing; counters: scan work counters (slow, never time with them)."""
-        self._check(self.lib.cbs_gpu_set_profiling(self.h, int(bool(events)) | (2 if counters else 0)))
+    def set_profiling(self, events: bool = False, counters: bool = False, serial: bool = False):
+        """events: per-launch CUDA event timing; counters: scan work counters (slow, never time with them);
+        serial: all kernels on one stream, so that the per-kernel event times do not overlap."""
+        self._check(self.lib.cbs_gpu_set_profiling(self.h, int(bool(events)) | (2 if counters else 0) | (4 if serial else 0)))
 
     def last_kernel_ms(self) -> dict:
         a = (C.c_double * 14)()

@@ -62,6 +62,7 @@ struct cbs_gpu_ctx {
     void* h_stage = nullptr;  // pinned staging for host inputs
     size_t h_stage_cap = 0;
     bool profiling = false;   // per-launch CUDA events
+    bool serial = false;      // all kernels of a round on one stream (non-overlapping per-kernel times)
     bool counting = false;    // scan work counters (atomics in the kernel: slows it, never combine with timing)
     double kms[K_COUNT] = {0};
     std::vector<cudaEvent_t> ev_pool;
@@ -323,6 +324,9 @@ long long env_ll(const char* name, long long dflt) {
 int run_cbs(cbs_gpu_ctx* c, const std::vector<long long>& off, const uint64_t* unit_ids, int n_units,
             const cbs_gpu_params* p, const uint64_t* mt_next312, bool weighted /* weights resident in c->wts */, Dev& hD) {
     cudaStream_t st = c->stream;
+    // profiling bit 2: every kernel on the one stream, so that per-launch event times do not overlap (roofline time base)
+    cudaStream_t side[5], gen_stream = c->serial ? st : c->gen_stream;
+    for (int k = 0; k < 5; ++k) side[k] = c->serial ? st : c->side[k];
     const long long N = off[n_units];
     long long Nmax = 0;
     for (int u = 0; u < n_units; ++u) Nmax = std::max(Nmax, off[u + 1] - off[u]);
@@ -592,11 +596,11 @@ int run_cbs(cbs_gpu_ctx* c, const std::vector<long long>& off, const uint64_t* u
             if (ahead_pending) { cudaStreamWaitEvent(st, c->ev_ahead, 0); ahead_pending = false; }
             { LaunchTimer t(c, K_SCHED); k_sched<<<1, 256, 0, st>>>(dD, c->d_done); }
             cudaEventRecord(c->ev_sched, st);
-            cudaStreamWaitEvent(c->side[0], c->ev_sched, 0);
-            { LaunchTimer t(c, K_PREP, c->side[0]); k_tables<<<dim3(16, 64), 256, 0, c->side[0]>>>(dD); if (weighted) { k_wprep<<<c->sm_count * 8, 32, 0, c->side[0]>>>(dD); k_wtables<<<c->sm_count * 2, 256, 0, c->side[0]>>>(dD); c->launches++; if (p->hybrid) { k_wdelta<<<c->sm_count * 2, 32, 0, c->side[0]>>>(dD); c->launches++; } } else k_prep<<<c->sm_count * 8, 32, 0, c->side[0]>>>(dD); c->launches++; }
-            cudaEventRecord(c->ev_side[0], c->side[0]);
-            cudaStreamWaitEvent(c->side[1], c->ev_sched, 0);
-            { LaunchTimer t(c, K_EDGEPREP, c->side[1]); if (weighted) k_wedgeprep<<<c->sm_count * 4, 32, 0, c->side[1]>>>(dD); else k_edgeprep<<<c->sm_count * 4, 32, 0, c->side[1]>>>(dD); }
+            cudaStreamWaitEvent(side[0], c->ev_sched, 0);
+            { LaunchTimer t(c, K_PREP, side[0]); k_tables<<<dim3(16, 64), 256, 0, side[0]>>>(dD); if (weighted) { k_wprep<<<c->sm_count * 8, 32, 0, side[0]>>>(dD); k_wtables<<<c->sm_count * 2, 256, 0, side[0]>>>(dD); c->launches++; if (p->hybrid) { k_wdelta<<<c->sm_count * 2, 32, 0, side[0]>>>(dD); c->launches++; } } else k_prep<<<c->sm_count * 8, 32, 0, side[0]>>>(dD); c->launches++; }
+            cudaEventRecord(c->ev_side[0], side[0]);
+            cudaStreamWaitEvent(side[1], c->ev_sched, 0);
+            { LaunchTimer t(c, K_EDGEPREP, side[1]); if (weighted) k_wedgeprep<<<c->sm_count * 4, 32, 0, side[1]>>>(dD); else k_edgeprep<<<c->sm_count * 4, 32, 0, side[1]>>>(dD); }
             if (mt) {
                 LaunchTimer t(c, K_GEN);
                 if (shared_stream) {
@@ -606,16 +610,16 @@ int run_cbs(cbs_gpu_ctx* c, const std::vector<long long>& off, const uint64_t* u
             }
             cudaEventRecord(c->ev_gen, st);
             // the edge permutations read this round's draws (plan_edge asked the generator for them): after the generator
-            if (mt) cudaStreamWaitEvent(c->side[1], c->ev_gen, 0);
-            { LaunchTimer t(c, K_EDGEPERM, c->side[1]); if (weighted) k_wedgeperm<<<c->sm_count * 4, 128, 0, c->side[1]>>>(dD); else k_edgeperm<<<c->sm_count * 4, 128, 0, c->side[1]>>>(dD); }
-            cudaEventRecord(c->ev_side[1], c->side[1]);
+            if (mt) cudaStreamWaitEvent(side[1], c->ev_gen, 0);
+            { LaunchTimer t(c, K_EDGEPERM, side[1]); if (weighted) k_wedgeperm<<<c->sm_count * 4, 128, 0, side[1]>>>(dD); else k_edgeperm<<<c->sm_count * 4, 128, 0, side[1]>>>(dD); }
+            cudaEventRecord(c->ev_side[1], side[1]);
             if (mt && shared_stream && hD.jump_polys) {
                 // generate ahead for the next round, next to this round's shuffles and scan
-                cudaStreamWaitEvent(c->gen_stream, c->ev_gen, 0);
-                k_gen_lead<<<1, 192, 0, c->gen_stream>>>(dD, 1);
-                k_gen_par<<<GEN_NSEG, 320, 0, c->gen_stream>>>(dD);
+                cudaStreamWaitEvent(gen_stream, c->ev_gen, 0);
+                k_gen_lead<<<1, 192, 0, gen_stream>>>(dD, 1);
+                k_gen_par<<<GEN_NSEG, 320, 0, gen_stream>>>(dD);
                 c->launches += 2;
-                cudaEventRecord(c->ev_ahead, c->gen_stream);
+                cudaEventRecord(c->ev_ahead, gen_stream);
                 ahead_pending = true;
             }
             // shuffles: classes alternate between the main stream and three side streams so that they run
@@ -624,7 +628,7 @@ int run_cbs(cbs_gpu_ctx* c, const std::vector<long long>& off, const uint64_t* u
             {
                 int slot = 0;
                 if (l2_shuffle_on) {
-                    cudaStream_t ss = c->side[4];
+                    cudaStream_t ss = side[4];
                     cudaStreamWaitEvent(ss, c->ev_gen, 0);
                     used_side[4] = true;
                     LaunchTimer t(c, K_PERM, ss);
@@ -635,13 +639,13 @@ int run_cbs(cbs_gpu_ctx* c, const std::vector<long long>& off, const uint64_t* u
                 for (int cls = SHUF_CL2 - 1; cls >= 0; --cls) {
                     if (!shuf_on[cls]) continue;
                     const int where = slot++ % 3;  // 0 = main stream, 1,2 = side[2], side[3]
-                    cudaStream_t ss = where == 0 ? st : c->side[1 + where];
+                    cudaStream_t ss = where == 0 ? st : side[1 + where];
                     if (where != 0 && !used_side[1 + where]) { cudaStreamWaitEvent(ss, c->ev_gen, 0); used_side[1 + where] = true; }
                     LaunchTimer t(c, kShufTimer[cls], ss);
                     launch_shuffle(dD, cls, c->sm_count * shuf_occ[cls], ss, mt);
                 }
             }
-            for (int k = 2; k < 5; ++k) if (used_side[k]) { cudaEventRecord(c->ev_side[k], c->side[k]); cudaStreamWaitEvent(st, c->ev_side[k], 0); }
+            for (int k = 2; k < 5; ++k) if (used_side[k]) { cudaEventRecord(c->ev_side[k], side[k]); cudaStreamWaitEvent(st, c->ev_side[k], 0); }
             { LaunchTimer t(c, K_PREFIX); if (weighted && p->hybrid) { k_wssq<<<c->sm_count * 8, 128, 0, st>>>(dD); c->launches++; } if (weighted) k_chain<true><<<c->sm_count * 12, CHAIN_WARPS * 32, 0, st>>>(dD); else k_chain<false><<<c->sm_count * 12, CHAIN_WARPS * 32, 0, st>>>(dD); }
             cudaStreamWaitEvent(st, c->ev_side[0], 0);
             { LaunchTimer t(c, K_SCAN);
@@ -678,7 +682,7 @@ int run_cbs(cbs_gpu_ctx* c, const std::vector<long long>& off, const uint64_t* u
         }
         if (rounds > 50000000) return fail(c, CBS_GPU_ERR_CUDA, "scheduler did not terminate");
     }
-    CUDA_TRY(c, cudaStreamSynchronize(c->gen_stream));
+    CUDA_TRY(c, cudaStreamSynchronize(gen_stream));
     CUDA_TRY(c, cudaStreamSynchronize(st));
     CUDA_TRY(c, cudaGetLastError());
     CUDA_TRY(c, cudaMemcpy(&hD, dD, sizeof(Dev), cudaMemcpyDeviceToHost));
@@ -929,6 +933,7 @@ int cbs_gpu_set_profiling(cbs_gpu_ctx* c, int on) {
     if (!c) return CBS_GPU_ERR_INVALID;
     c->profiling = (on & 1) != 0;
     c->counting = (on & 2) != 0;
+    c->serial = (on & 4) != 0;
     return CBS_GPU_OK;
 }
 
@@ -1179,7 +1184,7 @@ int cbs_gpu_segment_batch(cbs_gpu_ctx* c, const void* values, int dtype, int mem
     const size_t esz = dtype == CBS_GPU_F32 ? 4 : 8;
     for (int l = 0; l < L; ++l) {
         cbs_gpu_ctx* child = c->lanes[l];
-        child->profiling = c->profiling; child->counting = c->counting;
+        child->profiling = c->profiling; child->counting = c->counting; child->serial = c->serial;
         child->mem_fraction = 0.80 / L;
         const int u0 = cut[l], u1 = cut[l + 1];
         offs[l].resize((size_t)(u1 - u0) + 1);

@@ -1,69 +1,110 @@
-// prune.h -- undo.splits = "prune" (DNAcopy), host side: restates prune_segments / errssq /
-// next_combination of lib/cbs/CBS.cpp:229-320.  Off by default (undo_prune=false); it is an exhaustive
-// search over subsets of change points on per-segment sums, negligible next to the permutation tests,
-// and therefore stays on the host.
+// prune.h -- undo.splits = "prune" (DNAcopy's changepoints.prune as ported in lib/cbs/CBS.cpp:229-320), host side.
+// Off by default (undo_prune=false).  It is a search over subsets of the change points of ONE unit on per-segment sums --
+// a few dozen numbers -- so it stays on the host, as in the reference.
+//
+// What the reference computes: with k change points, for r = k-1, k-2, .. 1 the r-subset with the smallest within-segment
+// sum of squares W_r; as soon as W_r / W_k exceeds 1 + cutoff, the best (r+1)-subset is the answer (all change points if that
+// happens at r = k-1, one segment if it never happens).  Parity needs its floating point and its enumeration quirks:
+//   * a merged group's term is (s_a + s_{a+1} + .. + s_b, added left to right)^2 / count, terms are added left to right;
+//   * subsets are visited in lexicographic order and `<=` lets a later subset replace an equal earlier one;
+//   * the reference's stepping stops when the first kept change point reaches k - r, so that last subset is never looked at.
+// Design here: the group terms are tabulated once (term[a][b] for all a <= b), and the subsets are walked depth first with the
+// partial sum of the finished groups carried along -- the additions happen in the reference's order, so every W is the same
+// double, but a subset costs O(1) per level instead of a pass over all segments.
 #pragma once
+#include <limits>
 #include <vector>
 
 namespace cbsg {
 
-// sum over merged groups of (sum x)^2 / count, groups delimited by the kept change points `keep[0..k)`
-inline double grouped_ssq(const std::vector<int>& lseg, const std::vector<double>& segsum, const std::vector<int>& keep, int k) {
-    const int nseg = (int)lseg.size();
-    double out = 0.0;
-    int from = 0;
-    for (int part = 0; part <= k; ++part) {
-        const int to = (part < k) ? keep[part] : nseg - 1;
-        double s = 0.0;
-        int cnt = 0;
-        for (int i = from; i <= to; ++i) { s += segsum[i]; cnt += lseg[i]; }
-        out += s * s / (double)cnt;
-        from = to + 1;
+class PruneSearch {
+public:
+    PruneSearch(const double* x, int n, const std::vector<int>& lseg) : nseg_((int)lseg.size()), n_(n), lseg_(lseg) {
+        total_sq_ = 0.0;
+        for (int i = 0; i < n; ++i) total_sq_ += x[i] * x[i];
+        std::vector<double> segsum((size_t)nseg_, 0.0);
+        for (int s = 0, pos = 0; s < nseg_; ++s)
+            for (int j = 0; j < lseg[s]; ++j) segsum[(size_t)s] += x[pos++];
+        term_.assign((size_t)nseg_ * nseg_, 0.0);
+        for (int a = 0; a < nseg_; ++a) {
+            double run = 0.0;
+            int cnt = 0;
+            for (int b = a; b < nseg_; ++b) {
+                run += segsum[(size_t)b];
+                cnt += lseg[(size_t)b];
+                term_[(size_t)a * nseg_ + b] = run * run / (double)cnt;
+            }
+        }
     }
-    return out;
-}
 
-// advance `keep` to the next r-subset in lexicographic order; false when exhausted (CBS.cpp:257-264)
-inline bool next_subset(std::vector<int>& keep, int r, int nmr) {
-    int i = r - 1;
-    while (i >= 0 && keep[i] == nmr + i) --i;
-    if (i < 0) return false;
-    ++keep[i];
-    for (int j = i + 1; j < r; ++j) keep[j] = keep[j - 1] + 1;
-    return keep[0] != nmr;
-}
+    // smallest W over the r-subsets the reference visits; `cuts` receives the minimiser (cut c = boundary after segment c)
+    double best_subset(int r, std::vector<int>& cuts) {
+        r_ = r;
+        last_first_ = (nseg_ - 1) - r;  // subsets whose first cut reaches this index are never visited
+        best_ = std::numeric_limits<double>::infinity();
+        cur_.assign((size_t)r, 0);
+        walk(0, -1, 0.0);
+        cuts = best_cuts_;
+        return best_;
+    }
+
+    // W of the full model (every change point kept)
+    double full_model() const {
+        double acc = 0.0;
+        for (int s = 0; s < nseg_; ++s) acc += term(s, s);
+        return total_sq_ - acc;
+    }
+
+    std::vector<int> lengths_of(const std::vector<int>& cuts) const {
+        std::vector<int> out;
+        int seg = 0, taken = 0;
+        for (int c : cuts) {
+            int len = 0;
+            for (; seg <= c; ++seg) len += lseg_[(size_t)seg];
+            out.push_back(len);
+            taken += len;
+        }
+        out.push_back(n_ - taken);
+        return out;
+    }
+
+private:
+    double term(int a, int b) const { return term_[(size_t)a * nseg_ + b]; }
+
+    // depth = cuts already placed, prev = the last of them (-1: none), acc = sum of the terms of the groups they close
+    void walk(int depth, int prev, double acc) {
+        if (depth == r_) {
+            const double w = total_sq_ - (acc + term(prev + 1, nseg_ - 1));
+            if (w <= best_) { best_ = w; best_cuts_ = cur_; }
+            return;
+        }
+        // cut `depth` may sit anywhere that leaves room for the r - depth - 1 cuts after it
+        const int hi = (depth == 0) ? last_first_ - 1 : last_first_ + depth;
+        for (int c = prev + 1; c <= hi; ++c) {
+            cur_[(size_t)depth] = c;
+            walk(depth + 1, c, acc + term(prev + 1, c));
+        }
+    }
+
+    int nseg_, n_, r_ = 0, last_first_ = 0;
+    const std::vector<int>& lseg_;
+    double total_sq_ = 0.0, best_ = 0.0;
+    std::vector<double> term_;
+    std::vector<int> cur_, best_cuts_;
+};
 
 // x: the unit's values (as segmented), lseg: segment lengths; returns the pruned lengths
 inline std::vector<int> prune_lengths(const double* x, int n, const std::vector<int>& lseg, double pcut) {
-    const int nseg = (int)lseg.size();
-    if (nseg <= 1) return lseg;
-    double ssq = 0.0;
-    for (int i = 0; i < n; ++i) ssq += x[i] * x[i];
-    std::vector<double> segsum((size_t)nseg, 0.0);
-    for (int i = 0, pos = 0; i < nseg; ++i)
-        for (int j = 0; j < lseg[i]; ++j) segsum[i] += x[pos++];
-    const int k = nseg - 1;
-    std::vector<int> keep((size_t)k), best_prev((size_t)k), best_cur((size_t)k);
-    for (int i = 0; i < k; ++i) { keep[i] = i; best_prev[i] = i; }
-    const double wssqk = ssq - grouped_ssq(lseg, segsum, keep, k);
-    for (int j = k - 1; j >= 1; --j) {
-        const int kmj = k - j;
-        for (int i = 0; i < j; ++i) { keep[i] = i; best_cur[i] = i; }
-        double wssqj = ssq - grouped_ssq(lseg, segsum, keep, j);
-        while (next_subset(keep, j, kmj)) {
-            const double w = ssq - grouped_ssq(lseg, segsum, keep, j);
-            if (w <= wssqj) { wssqj = w; for (int i = 0; i < j; ++i) best_cur[i] = keep[i]; }
-        }
-        if (wssqj / wssqk > 1.0 + pcut) {  // the finer level (j+1 change points) is kept
-            std::vector<int> cums((size_t)nseg);
-            for (int i = 0, s = 0; i < nseg; ++i) { s += lseg[i]; cums[i] = s; }
-            std::vector<int> out;
-            int prev = 0;
-            for (int i = 0; i <= j; ++i) { out.push_back(cums[best_prev[i]] - prev); prev = cums[best_prev[i]]; }
-            out.push_back(n - prev);
-            return out;
-        }
-        for (int i = 0; i < j; ++i) best_prev[i] = best_cur[i];
+    const int k = (int)lseg.size() - 1;  // change points
+    if (k <= 0) return lseg;
+    PruneSearch search(x, n, lseg);
+    const double w_full = search.full_model();
+    std::vector<int> finer((size_t)k), cuts;
+    for (int c = 0; c < k; ++c) finer[(size_t)c] = c;
+    for (int r = k - 1; r >= 1; --r) {
+        const double w = search.best_subset(r, cuts);
+        if (w / w_full > 1.0 + pcut) return search.lengths_of(finer);  // dropping down to r change points costs too much
+        finer = cuts;
     }
     return std::vector<int>{n};
 }

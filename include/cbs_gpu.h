@@ -167,7 +167,9 @@ int cbs_gpu_measure_fp64(cbs_gpu_ctx* ctx, double* tera_inst_per_s);
 int cbs_gpu_last_kernel_ms(cbs_gpu_ctx* ctx, double* ms14);
 /* bit 0: bracket every kernel launch with CUDA events (cbs_gpu_last_kernel_ms);
  * bit 1: count scan-kernel work with device atomics (cbs_gpu_last_arc_evals) -- this slows the scan
- * kernel several times, so time and count in separate calls */
+ * kernel several times, so time and count in separate calls;
+ * bit 2: launch every kernel of a round on the one stream instead of the side streams, so that the per-launch event
+ * times do not overlap (time base of the per-kernel roofline; slower than the normal, overlapped schedule) */
 int cbs_gpu_set_profiling(cbs_gpu_ctx* ctx, int on);
 /* scan-kernel work of the last batched call (needs profiling on): arcs = real (i,j) pairs examined
  * by the inner loop, slots = compare slots issued (arcs + padding of partially filled units) */

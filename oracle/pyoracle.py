@@ -406,6 +406,17 @@ class Ref:
                                         C.c_int, C.c_double, C.c_double, C.c_int, C.c_double, C.c_uint64, C.c_int,
                                         C.c_int, C.c_int64, c_int_p, c_int_p, c_double_p]
 
+        L.ref_perm_reject_flags.argtypes = [c_double_p, C.c_int, C.c_double, C.c_double, C.c_int, C.c_uint64, C.c_uint64,
+                                            C.c_int64, C.c_int64, C.c_int, C.c_void_p]
+
+    def perm_reject_flags(self, x, tss, thresh, seed, start_draw, perm0, nperms, nthreads, al0=2):
+        """flags[k] = permutation perm0+k of fndcpt's max-t loop rejects (reference xperm + tmaxp, threads over the range)"""
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        flags = np.zeros(int(nperms), dtype=np.uint8)
+        self.lib.ref_perm_reject_flags(_dp(x), len(x), float(tss), float(thresh), al0, int(seed), int(start_draw), int(perm0),
+                                       int(nperms), int(nthreads), flags.ctypes.data_as(C.c_void_p))
+        return flags
+
     class Rng:
         def __init__(self, lib, seed):
             self.lib = lib

@@ -93,6 +93,33 @@ double ref_tpermp(int n1, int n2, int n, const double* x, int nperm, void* rng) 
     return cbs::tpermp(n1, n2, n, x, px, nperm, static_cast<RefRng*>(rng)->eng);
 }
 
+// Rejection flags of permutations [perm0, perm0 + nperms) of the max-t loop of cbs::fndcpt (CBS.cpp:860-866) for a
+// centred segment x, computed with the reference's OWN cbs::xperm and cbs::tmaxp.  Permutation k of the loop consumes
+// draws [start_draw + k*n, start_draw + (k+1)*n) of mt19937_64(seed), so the range is cut over `nthreads` host threads,
+// each with its own engine advanced by discard().  flags[k - perm0] = (thresh <= pstat).  For tests of very long
+// permutation loops (BASELINE configs[4], 100 000 permutations), which one thread cannot replay in minutes.
+void ref_perm_reject_flags(const double* x, int n, double tss, double thresh, int al0, uint64_t seed, uint64_t start_draw,
+                           int64_t perm0, int64_t nperms, int nthreads, unsigned char* flags) {
+    if (nthreads < 1) nthreads = 1;
+    const std::vector<double> v(x, x + n);
+    std::vector<std::thread> pool;
+    for (int t = 0; t < nthreads; ++t) {
+        pool.emplace_back([&, t]() {
+            const int64_t a = perm0 + nperms * t / nthreads, b = perm0 + nperms * (t + 1) / nthreads;
+            if (a >= b) return;
+            std::mt19937_64 eng(seed);
+            eng.discard(start_draw + static_cast<uint64_t>(a) * static_cast<uint64_t>(n));
+            std::vector<double> px;
+            for (int64_t k = a; k < b; ++k) {
+                cbs::xperm(v, px, eng);
+                const double pstat = cbs::tmaxp(px, tss, al0, false);
+                flags[k - perm0] = (thresh <= pstat) ? 1 : 0;
+            }
+        });
+    }
+    for (auto& th : pool) th.join();
+}
+
 // out: ncpt, icpt[2], iseg[2], ostat
 void ref_fndcpt(const double* x, int n, double tss, int nperm, double cpval, int ibin, int hybrid, int al0, int hk,
                 double delta, int ngrid, double tol, void* rng, int* ncpt, int* icpt, int* iseg, double* ostat) {

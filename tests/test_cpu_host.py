@@ -130,6 +130,36 @@ def test_scheduler_emulation_edge_tests(oracle, emul):
             assert np.array_equal(want["lengths"], got["lengths"]) and np.array_equal(want["means"], got["means"])
 
 
+def test_undo_prune_host_matches_reference(ref):
+    """genomic_b200/csrc/prune.h (depth-first search over tabulated group terms) against the reference's prune_segments
+    (CBS.cpp:266-320) reached through cbs::segment(..., undo_prune=true): same lengths for cut-offs that merge nothing, some
+    and all change points, on noisy data with true and spurious change points."""
+    d = os.path.join(HERE, "cpp")
+    so = os.path.join(d, "libprune_host.so")
+    subprocess.run(["g++", "-std=c++17", "-O2", "-fPIC", "-ffp-contract=off", "-shared", "-o", so, os.path.join(d, "prune_host.cpp")], check=True)
+    L = C.CDLL(so)
+    rng = np.random.default_rng(404)
+    merged_some = 0
+    for trial in range(30):
+        n = int(rng.integers(60, 900))
+        x = rng.normal(0, 0.2, n)
+        for _ in range(int(rng.integers(1, 7))):
+            a = int(rng.integers(0, n - 5)); b = int(rng.integers(a + 3, n + 1))
+            x[a:b] += float(rng.choice([-0.6, -0.25, 0.2, 0.35, 0.8]))
+        x = x.astype(np.float32).astype(np.float64)
+        for cutoff in (0.0, 0.05, 0.5, 5.0):
+            base = SegParams(nperm=200, alpha=0.05, do_smooth=False, seed=int(trial + 1))
+            plain = ref.segment(x, base)
+            want = ref.segment(x, SegParams(nperm=200, alpha=0.05, do_smooth=False, seed=int(trial + 1), undo_prune=True,
+                                            undo_prune_cutoff=cutoff))
+            lseg = np.ascontiguousarray(plain[0], dtype=np.int32)
+            out = np.zeros(len(lseg) + 1, np.int32)
+            k = L.prune_host(_dp(x), n, _ip(lseg), len(lseg), C.c_double(cutoff), _ip(out))
+            assert np.array_equal(out[:k], want[0]), (trial, cutoff, lseg, out[:k], want[0])
+            merged_some += int(1 < k < len(lseg))
+    assert merged_some > 0
+
+
 _WORKER = r'''
 import os, sys
 sys.path.insert(0, {root!r}); sys.path.insert(0, os.path.join({root!r}, "tests"))

@@ -1,0 +1,137 @@
+"""-m gpu: parity at BASELINE.json's FULL configuration sizes against the compiled reference (oracle/_ref: the
+unmodified lib/cbs/CBS.cpp + smooth.cpp, driven like src/cna_segment.hpp:127-159 by oracle/ref_wrap.cpp, one
+std::mt19937_64(seed) per unit, units spread over the host's cores).
+
+  configs[1]  one SNP6-scale sample, 1.8 M markers, nperm 10 000, smoothing on          -- default run (about a minute of CPU)
+  configs[2]  samples with injected outliers: smoothed vectors AND segments             -- CBS_RUN_SLOW=1
+  configs[3]  the fixed 16-sample parity subset of the 1000-sample cohort               -- CBS_RUN_SLOW=1
+  configs[4]  50 000-marker units, nperm 100 000: runs at default settings (default run, properties + the reference at the
+              largest nperm it does in about a minute); all 100 000 reject decisions of the reference's own xperm + tmaxp
+              replayed on every host core                                                -- CBS_RUN_SLOW=1
+
+The slow cases cost minutes of reference CPU time each; their logs are committed under profiles/ (r02_fullsize_*.log)."""
+import os
+import time
+
+import numpy as np
+import pytest
+
+from oracle.pyoracle import SegParams
+import genomic_b200
+from genomic_b200 import Params, RNG_MT19937_64, synth
+from test_gpu_parity import gparams
+
+pytestmark = pytest.mark.gpu
+slow = pytest.mark.skipif(os.environ.get("CBS_RUN_SLOW") != "1", reason="minutes of reference CPU time: set CBS_RUN_SLOW=1")
+NPERM, ALPHA = 10000, 0.01
+THREADS = os.cpu_count() or 1
+
+
+def gpu_vs_reference(ctx, ref, samples, outliers, tag):
+    vals, off, lab, ids = synth.cohort(samples, scale=1.0, outliers=outliers)
+    p = SegParams(nperm=NPERM, alpha=ALPHA, do_smooth=True, rng_kind=0, chain=False, seed=1)
+    t0 = time.perf_counter()
+    got = ctx.segment_batch(vals, off, gparams(p), unit_ids=ids)
+    t1 = time.perf_counter()
+    want = ref.segment_units(vals.astype(np.float64), off, lab, p, nthreads=THREADS)
+    t2 = time.perf_counter()
+    print(f"[fullsize {tag}] samples {list(samples)} units {len(off) - 1} markers {int(off[-1])} segments {len(want['lengths'])} "
+          f"perms {got.perms_run}: GPU {t1 - t0:.2f} s, reference {t2 - t1:.1f} s on {THREADS} threads", flush=True)
+    assert np.array_equal(got.seg_count, want["seg_count"])
+    assert np.array_equal(got.lengths, want["lengths"])      # breakpoints: bit-exact
+    assert np.array_equal(got.means, want["means"])          # the north star allows 1e-9; the sums are sequential, so exact
+    return vals, off, lab, got
+
+
+def test_config2_whole_sample_vs_reference(ctx, ref):
+    """All 23 units of synthetic sample 0 at full size, nperm 10 000, smoothing on (BASELINE configs[1], the bench workload)."""
+    gpu_vs_reference(ctx, ref, [0], False, "configs[1]")
+
+
+@slow
+def test_config3_samples_with_outliers_vs_reference(ctx, ref):
+    """Full-size samples with injected outliers (+-(3+|N(0,1)|) every ~1000th marker): the smoothed vectors equal the
+    reference's cbs::smooth per (sample, chromosome) and the segments equal cbs::segment on them (BASELINE configs[2])."""
+    samples = [0, 1, 2, 3]
+    vals, off, lab, got = gpu_vs_reference(ctx, ref, samples, True, "configs[2]")
+    x64 = vals.astype(np.float64)
+    changed = 0
+    for u in range(len(off) - 1):
+        xu = x64[off[u]:off[u + 1]]
+        cu = np.full(len(xu), int(lab[u]), np.int32)
+        g = ctx.smooth(xu, cu)
+        w = ref.smooth(xu, cu)
+        assert np.array_equal(g, w), u  # tolerance allowed: 1e-9
+        changed += int((g != xu).sum())
+    assert changed > 1000 * len(samples)  # the replacement branch fired on the injected outliers
+
+
+@slow
+def test_config4_sixteen_sample_subset_vs_reference(ctx, ref):
+    """The fixed 16-sample parity subset of the 1000-sample cohort (BASELINE configs[3]): global sample ids
+    0, 63, 125, ..., i.e. two from each of the eight 125-sample shards, segmented in ONE call as a shard is."""
+    samples = [0, 63, 125, 188, 250, 313, 375, 438, 500, 563, 625, 688, 750, 813, 875, 938]
+    gpu_vs_reference(ctx, ref, samples, False, "configs[3] subset")
+
+
+def config5_units():
+    return [synth.null_unit(20260105, 50000).astype(np.float64),
+            synth.null_unit(20260106, 50000, shift_at=25000, shift=0.0115).astype(np.float64)]  # observed t = 6.39 < 7
+
+
+def run_config5(ctx, nperm):
+    units = config5_units()
+    vals = np.concatenate(units)
+    off = np.array([0, 50000, 100000], np.int64)
+    gp = Params(nperm=nperm, alpha=ALPHA, do_smooth=False, rng_mode=RNG_MT19937_64, chain=False, seed=1, record_splits=True)
+    t0 = time.perf_counter()
+    r = ctx.segment_batch(vals, off, gp)
+    return units, off, r, time.perf_counter() - t0
+
+
+def test_config5_100k_permutations_default_settings(ctx, ref):
+    """BASELINE configs[4]: units of exactly 50 000 markers, 100 000 permutations, MT replay.  Unit (ii) (a shift at 25 000
+    with t = 6.39 < 7, so fndcpt takes no shortcut, and a p-value far below alpha) runs the whole permutation loop: 5e9 draws of ONE engine, 40 GB of raw
+    words -- more than the stream window holds; round 1 failed here with a capacity error.  Checked: the call completes at
+    default settings, the accounting is exact (draws = n x permutations per decision), and the same units at nperm 2000
+    equal the compiled reference bit for bit."""
+    units, off, r, dt = run_config5(ctx, 100000)
+    root = {s["unit"]: s for s in r.splits if s["lo"] == 0 and s["hi"] == 50000}
+    print(f"[fullsize configs[4]] nperm 100000: {dt:.2f} s, perms {r.perms_run}, root decisions "
+          f"{[(u, s['perms_run'], s['nrej'], s['exit_code'], s['ncpt']) for u, s in sorted(root.items())]}", flush=True)
+    assert root[1]["perms_run"] == 100000 and root[1]["ncpt"] >= 1     # ran to completion and found the shift
+    assert root[0]["exit_code"] == 3 and root[0]["nrej"] == 1001        # pure null: early exit at nrej > nrejc = 1000
+    for u in (0, 1):
+        lens = r.lengths[r.seg_offsets[u]:r.seg_offsets[u + 1]]
+        assert int(lens.sum()) == 50000 and lens.min() >= 1
+        spent = sum(s["perms_run"] * (s["hi"] - s["lo"]) for s in r.splits if s["unit"] == u)  # edge tests take the shortcut or
+        assert int(r.draws[u]) >= spent                                                         # add nperm x m1 draws each
+    assert int(r.draws[1]) >= 5_000_000_000
+    # the same units against the compiled reference at the nperm it finishes in about a minute
+    p = SegParams(nperm=2000, alpha=ALPHA, do_smooth=False, rng_kind=0, chain=False, seed=1)
+    vals = np.concatenate(units)
+    got = ctx.segment_batch(vals, off, gparams(p))
+    want = ref.segment_units(vals, off, np.ones(2, np.int32), p, nthreads=2)
+    assert np.array_equal(got.lengths, want["lengths"]) and np.array_equal(got.means, want["means"])
+
+
+@slow
+def test_config5_100k_reject_decisions_vs_reference_functions(ctx, ref):
+    """All permutations of both root decisions of configs[4] replayed with the reference's own cbs::xperm + cbs::tmaxp on
+    every host core (oracle/ref_wrap.cpp ref_perm_reject_flags; permutation k uses draws [k n, (k+1) n) of mt19937_64(1)):
+    unit (ii): the number of rejections among all 100 000 permutations equals the device's count; unit (i): the running
+    count first exceeds nrejc = 1000 at exactly the permutation where the device stopped."""
+    units, off, r, dt = run_config5(ctx, 100000)
+    root = {s["unit"]: s for s in r.splits if s["lo"] == 0 and s["hi"] == 50000}
+    for u in (0, 1):
+        x = units[u]
+        cur = x - np.cumsum(x)[-1] / len(x)            # CBS.cpp:986-988, sequential sums
+        tss = float(np.cumsum(cur * cur)[-1])
+        s = root[u]
+        t0 = time.perf_counter()
+        flags = ref.perm_reject_flags(cur, tss, s["ostat"] * 0.99999, 1, 0, 0, s["perms_run"], THREADS)
+        print(f"[fullsize configs[4]] unit {u}: {s['perms_run']} permutations replayed by the reference in "
+              f"{time.perf_counter() - t0:.1f} s on {THREADS} threads: rejections {int(flags.sum())} (device {s['nrej']})", flush=True)
+        assert int(flags.sum()) == s["nrej"]
+        if s["exit_code"] == 3:  # early exit: the last permutation is the one that made nrej exceed nrejc, none before it did
+            assert flags[-1] == 1 and int(flags[:-1].sum()) == 1000
