@@ -246,10 +246,13 @@ def run_gpu_arm(args):
 
     from genomic_b200 import shard
 
+    gather_cap = 64 * 24 * max(1, S)  # rows per rank of the one fixed-capacity all_gather (same on every rank)
+
     def gather_tables(res):
-        """the only cross-GPU step: gather of the per-rank segment tables (NCCL all_gather)"""
+        """the only cross-GPU step: gather of the per-rank segment tables (ONE NCCL all_gather, one D2H copy)"""
         tab = shard.pack_table(res.seg_count, res.lengths, res.means, ids)
-        return shard.gather_tables(tab, dist, dev).shape[0]
+        gather_tables.last = shard.gather_tables(tab, dist, dev, capacity=gather_cap)
+        return gather_tables.last.shape[0]
 
     def step_device():
         r = ctx.segment_batch(None, off, gp, unit_ids=ids, device_ptr=d_vals.data_ptr(), dtype=genomic_b200.binding.F32)
@@ -289,12 +292,60 @@ def run_gpu_arm(args):
         timed.last_steps = [round(x, 3) for x in per_step]  # this rank's per-step times (diagnostics)
         return float(t.item()), last, clocks
 
-    warm = max(args.warmup, 3)
+    warm = max(args.warmup, 3) if not args.cohort_run else args.warmup
     total_ms, res, clocks = timed(step_device, args.steps, warm, sample_clocks=True)
     steps_device = timed.last_steps
-    e2e_ms, res_h, _ = timed(step_host, args.steps, 1)
+    e2e_ms, res_h, _ = timed(step_host, args.steps, 0 if args.cohort_run else 1)
     steps_host = timed.last_steps
     launches_per_step = int(res.kernel_launches)
+    full_table = gather_tables.last
+
+    if args.cohort_run:
+        # The north-star run (BASELINE configs[3]): a cohort sharded by sample over the ranks, timed end to end, with the
+        # per-rank times (load balance) and the parity subset: the subset samples are segmented once more in ONE call on rank 0
+        # (that call is what tests/test_gpu_fullsize.py::test_config4 compares with the compiled reference, log under profiles/)
+        # and must agree row for row with what the sharded run produced for them.
+        rank_ms = torch.tensor([sum(steps_device) / len(steps_device)], device=dev, dtype=torch.float64)
+        all_ms = [torch.zeros_like(rank_ms) for _ in range(world)]
+        if dist is not None:
+            dist.all_gather(all_ms, rank_ms)
+        else:
+            all_ms = [rank_ms]
+        per_rank = [float(t.item()) for t in all_ms]
+        if rank == 0:
+            total = S * world
+            subset = shard.parity_subset(total)
+            sv, so, sl, sid = synth.cohort(subset, scale=args.scale)
+            rs = ctx.segment_batch(sv, so, gp, unit_ids=sid)
+            want = shard.pack_table(rs.seg_count, rs.lengths, rs.means, sid)
+            keep = np.isin(full_table[:, 0], np.asarray(sid, dtype=np.float64))
+            got = full_table[keep]
+            order = np.lexsort((np.arange(len(got)), got[:, 0]))
+            same = bool(got.shape == want.shape and np.array_equal(got[order], want))
+            markers_total = markers_rank * world
+            line = {
+                "metric": METRIC, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": warm,
+                "value": markers_total * args.steps / (total_ms * 1e-3), "ms_per_step": total_ms / args.steps,
+                "e2e": {"value": markers_total * args.steps / (e2e_ms * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms / args.steps,
+                        "h2d_bytes_per_step": int(vals.nbytes) * world,
+                        "d2h_bytes_per_step": int(len(res_h.lengths) * 12 + len(off) * 16) * world},
+                "config": {"workload": workload_name(S, args.scale), "rng": args.rng, "chain": False, "samples": total,
+                           "parallelism": f"sample-sharded x{world}, one all_gather of the segment tables"},
+                "per_rank_ms_per_step": [round(x, 1) for x in per_rank],
+                "max_over_mean_rank_time": max(per_rank) / (sum(per_rank) / len(per_rank)),
+                "segments": int(full_table.shape[0]), "perms_run_rank0": int(res.perms_run), "rounds_rank0": int(res.rounds),
+                "parity_subset": {"samples": subset, "rows": int(want.shape[0]), "sharded_equals_single_call": same,
+                                  "reference": "the same single call equals the compiled reference bit for bit: "
+                                               "tests/test_gpu_fullsize.py::test_config4_sixteen_sample_subset_vs_reference, "
+                                               "profiles/r02_fullsize_slow.log"},
+                "clocks": clocks, "higher_is_better": True, "scaling": "weak", "dtype": "f64", "data": "synthetic",
+            }
+            print(json.dumps(line), flush=True)
+        if dist is not None:
+            dist.barrier()
+            dist.destroy_process_group()
+        ctx.close()
+        return
 
     # Roofline inputs, kept OUT of the timed steps:
     #  (1) the same K steps once more with every kernel launch bracketed by CUDA events, ALL kernels on the one
@@ -343,7 +394,7 @@ def run_gpu_arm(args):
 
         def traffic(kernel, alg_bytes_per_elem):
             k = ncu.get(kernel)
-            if not k:
+            if not k or "dram_read_bytes" not in k or not k.get("elements"):
                 return None
             total = k["dram_read_bytes"] + k["dram_write_bytes"]
             return {"dram_bytes_per_launch": total, "launch_ms": k["ms"], "elements_in_launch": k["elements"],
@@ -422,6 +473,9 @@ def main():
     ap.add_argument("--samples-per-gpu", type=int, default=1)
     ap.add_argument("--scale", type=float, default=1.0, help="shrink every chromosome (smoke runs only)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--cohort-run", action="store_true",
+                    help="the north-star run: whole cohort (samples-per-gpu x gpus), per-rank times and the 16-sample parity subset; "
+                         "no per-kernel profile passes, warm-up as given")
     ap.add_argument("--hybrid", action="store_true",
                     help="hybrid p-values (DNAcopy's default method, `cna segment --hybrid true`) instead of the CLI default; "
                          "not the headline configuration")

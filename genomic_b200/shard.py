@@ -8,6 +8,18 @@ from __future__ import annotations
 import numpy as np
 
 
+# the fixed 16-sample parity subset of the 1000-sample cohort (BASELINE configs[3]): two samples of each 125-sample shard
+PARITY_SUBSET_1000 = [0, 63, 125, 188, 250, 313, 375, 438, 500, 563, 625, 688, 750, 813, 875, 938]
+
+
+def parity_subset(n_samples: int):
+    if n_samples == 1000:
+        return list(PARITY_SUBSET_1000)
+    if n_samples <= 16:
+        return list(range(n_samples))
+    return sorted(set(int(k * (n_samples - 1) // 15) for k in range(16)))
+
+
 def samples_of_rank(n_samples: int, rank: int, world: int):
     """contiguous blocks, remainder to the first ranks"""
     base, rem = divmod(n_samples, world)
@@ -22,21 +34,26 @@ def pack_table(seg_count, lengths, means, unit_ids) -> np.ndarray:
         if len(lengths) else np.zeros((0, 3))
 
 
-def gather_tables(table: np.ndarray, dist=None, device=None) -> np.ndarray:
-    """all_gather of ragged (n,3) tables; returns the concatenation in rank order"""
+def gather_tables(table: np.ndarray, dist=None, device=None, capacity: int | None = None) -> np.ndarray:
+    """Gather of the ragged (n,3) tables of all ranks; returns their concatenation in rank order.  ONE collective and ONE
+    device->host copy: every rank contributes a fixed-capacity block whose first row carries its row count.  `capacity`
+    (rows per rank) must be the same on all ranks; only if some rank has more rows than that -- every rank sees it in the
+    gathered counts -- is the gather repeated with the largest count."""
     if dist is None or not dist.is_initialized() or dist.get_world_size() == 1:
         return table
     import torch
     world = dist.get_world_size()
     dev = device if device is not None else torch.device("cpu")
-    n = torch.tensor([table.shape[0]], dtype=torch.int64, device=dev)
-    counts = [torch.zeros_like(n) for _ in range(world)]
-    dist.all_gather(counts, n)
-    counts = [int(c.item()) for c in counts]
-    mx = max(max(counts), 1)
-    pad = torch.zeros((mx, 3), dtype=torch.float64, device=dev)
-    if table.shape[0]:
-        pad[: table.shape[0]] = torch.from_numpy(np.ascontiguousarray(table)).to(dev)
-    out = [torch.zeros_like(pad) for _ in range(world)]
-    dist.all_gather(out, pad)
-    return np.concatenate([o[:c].cpu().numpy() for o, c in zip(out, counts)], axis=0)
+    cap = int(capacity) if capacity else 4096
+    while True:
+        block = np.zeros((cap + 1, 3))
+        block[0, 0] = table.shape[0]
+        k = min(table.shape[0], cap)
+        block[1:1 + k] = table[:k]
+        out = torch.empty((world * (cap + 1), 3), dtype=torch.float64, device=dev)
+        dist.all_gather_into_tensor(out, torch.from_numpy(block).to(dev))
+        host = out.cpu().numpy().reshape(world, cap + 1, 3)
+        counts = host[:, 0, 0].astype(np.int64)
+        if int(counts.max()) <= cap:
+            return np.concatenate([host[r, 1:1 + counts[r]] for r in range(world)], axis=0)
+        cap = int(counts.max())

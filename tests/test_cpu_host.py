@@ -173,7 +173,7 @@ mine = shard.samples_of_rank(3, rank, world)
 vals, off, lab, ids = synth.cohort(mine, scale=0.002)
 p = SegParams(nperm=100, rng_kind=1, seed=11)
 r = Oracle().segment_units(vals.astype(np.float64), off, lab, p, unit_ids=ids)
-tab = shard.gather_tables(shard.pack_table(r["seg_count"], r["lengths"], r["means"], ids), dist)
+tab = shard.gather_tables(shard.pack_table(r["seg_count"], r["lengths"], r["means"], ids), dist, capacity=int(sys.argv[4]))
 if rank == 0:
     np.save(sys.argv[3], tab)
 dist.barrier(); dist.destroy_process_group()
@@ -186,17 +186,17 @@ def test_sharded_gather_gloo_world2(tmp_path, oracle):
     from genomic_b200 import shard, synth
     script = tmp_path / "w.py"
     script.write_text(_WORKER.format(root=ROOT))
-    out = tmp_path / "tab.npy"
-    port = str(29500 + os.getpid() % 2000)
-    procs = [subprocess.Popen([sys.executable, str(script), str(r), port, str(out)]) for r in range(2)]
-    for pr in procs:
-        assert pr.wait(timeout=300) == 0
-    got = np.load(out)
     assert shard.samples_of_rank(3, 0, 2) == [0, 1] and shard.samples_of_rank(3, 1, 2) == [2]
     vals, off, lab, ids = synth.cohort([0, 1, 2], scale=0.002)
     r = oracle.segment_units(vals.astype(np.float64), off, lab, SegParams(nperm=100, rng_kind=1, seed=11), unit_ids=ids)
     want = shard.pack_table(r["seg_count"], r["lengths"], r["means"], ids)
-    assert np.array_equal(got, want)
+    for k, capacity in enumerate((4096, 3)):  # one collective; with 3 rows per rank the gather has to be repeated with the real size
+        out = tmp_path / f"tab{k}.npy"
+        port = str(29500 + (os.getpid() + k) % 2000)
+        procs = [subprocess.Popen([sys.executable, str(script), str(r2), port, str(out), str(capacity)]) for r2 in range(2)]
+        for pr in procs:
+            assert pr.wait(timeout=300) == 0
+        assert np.array_equal(np.load(out), want)
 
 
 def test_cn_reader_parallel_identical(tmp_path):

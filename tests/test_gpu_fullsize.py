@@ -70,7 +70,8 @@ def test_config3_samples_with_outliers_vs_reference(ctx, ref):
 def test_config4_sixteen_sample_subset_vs_reference(ctx, ref):
     """The fixed 16-sample parity subset of the 1000-sample cohort (BASELINE configs[3]): global sample ids
     0, 63, 125, ..., i.e. two from each of the eight 125-sample shards, segmented in ONE call as a shard is."""
-    samples = [0, 63, 125, 188, 250, 313, 375, 438, 500, 563, 625, 688, 750, 813, 875, 938]
+    from genomic_b200.shard import PARITY_SUBSET_1000
+    samples = list(PARITY_SUBSET_1000)
     gpu_vs_reference(ctx, ref, samples, False, "configs[3] subset")
 
 
