@@ -19,7 +19,8 @@ namespace cbsg {
 
 enum { RNG_MT = 0, RNG_PHILOX = 1 };
 enum { SHUF_NCLS_MAX = 12 };  // room for the shuffle class tables (cbs_core.h: SHUF_NCLS)
-enum { SX_PAD = 48 };  // finite values kept behind the prefix sums of every permutation
+enum { SX_PAD = 48 };
+enum { CHAIN_Q = 4 };  // permutations of a batch that one pair of warps of k_chain turns into prefix sums together  // finite values kept behind the prefix sums of every permutation
 
 // mirrors the reference call arguments 1:1 (CBS.hpp:100-113) + rng selection
 struct Params {
@@ -294,7 +295,7 @@ struct Dev {
     int round;
     int n_prep;   int* prep_task;
     int n_items;  PermItem* items; int* item_prefix;  // exclusive prefix of P, [n_items+1]
-    int* item_uprefix;                                 // exclusive prefix of ceil(P/32) (k_prefix work units)
+    int* item_uprefix;                                 // exclusive prefix of ceil(P/CHAIN_Q): work units of k_chain
     int n_edgeprep; int* edgeprep_task;
     int n_edge;   EdgeItem* edges; int* edge_prefix;  // exclusive prefix of threads, [n_edge+1]
     int n_gen;    int* gen_chain;
@@ -573,7 +574,7 @@ struct Sched {
         PermItem& it = D.items[D.n_items];
         it.task = idx; it.P = want; it.obs = 0;
         D.item_prefix[D.n_items + 1] = D.item_prefix[D.n_items] + want;
-        D.item_uprefix[D.n_items + 1] = D.item_uprefix[D.n_items] + ((want + 31) >> 5);
+        D.item_uprefix[D.n_items + 1] = D.item_uprefix[D.n_items] + (want + CHAIN_Q - 1) / CHAIN_Q;
         if (want - gpart > 0) {  // permutations [0, want-gpart): the class's own shuffle
             const int q = D.n_shuf[cls];
             D.shuf_item[cls][q] = D.n_items; D.shuf_p0[cls][q] = 0;

@@ -126,70 +126,6 @@ __global__ void __launch_bounds__(192) k_gen(Dev* D) {
 }
 
 // ------------------------------------------------------------------------------------
-// Statistics of a row of prefix sums, computed chunk by chunk by the warp that has just produced the chunk in
-// shared memory (k_chain, k_prep), so that k_scan does not have to read the row again:
-//   * per block of the reference's sqrt(n) blocks: extrema with their FIRST occurrence (CBS.cpp:88-94), double;
-//   * per aligned run of 32 prefix sums: extrema in single precision rounded outwards (the scan's pruning table).
-// buf[k] = S[c0+1+k], k < cnt; prev_last = S[c0].  The state is uniform over the warp.
-// ------------------------------------------------------------------------------------
-struct RowStats {
-    int b;           // block in progress (1-based)
-    double lo, hi;   // its extrema so far
-    int ilo, ihi;
-};
-__device__ __forceinline__ void row_stats_init(RowStats& st) {
-    st.b = 1; st.lo = __longlong_as_double(0x7ff0000000000000LL); st.hi = -st.lo; st.ilo = 0x7fffffff; st.ihi = 0x7fffffff;
-}
-template <int CHUNK>
-__device__ void row_stats_chunk(const double* buf, int c0, int cnt, int n, double prev_last, const int* __restrict__ bb, int nb,
-                                BlockStats bs, float* tmin, float* tmax, RowStats& st, int lane) {
-    const double dinf = __longlong_as_double(0x7ff0000000000000LL);
-    const int hi_idx = c0 + cnt;
-    while (st.b <= nb) {
-        const int first = bb[st.b - 1] + 1, last = bb[st.b];
-        const int a = max(first, c0 + 1), z = min(last, hi_idx);
-        if (a > z) break;
-        double lo = dinf, hi = -dinf;
-        int ilo = 0x7fffffff, ihi = 0x7fffffff;
-        for (int i = a + lane; i <= z; i += 32) {
-            const double v = buf[i - c0 - 1];
-            if (v < lo) { lo = v; ilo = i; }
-            if (v > hi) { hi = v; ihi = i; }
-        }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            const double olo = shfl_d(lo, lane ^ o), ohi = shfl_d(hi, lane ^ o);
-            const int oilo = __shfl_xor_sync(FULL, ilo, o), oihi = __shfl_xor_sync(FULL, ihi, o);
-            if (olo < lo || (olo == lo && oilo < ilo)) { lo = olo; ilo = oilo; }
-            if (ohi > hi || (ohi == hi && oihi < ihi)) { hi = ohi; ihi = oihi; }
-        }
-        if (lo < st.lo) { st.lo = lo; st.ilo = ilo; }  // the part seen earlier holds the earlier indices: it wins ties
-        if (hi > st.hi) { st.hi = hi; st.ihi = ihi; }
-        if (last > hi_idx) break;  // the block continues in the next chunk
-        if (lane == 0) { bs.bmin()[st.b - 1] = st.lo; bs.bmax()[st.b - 1] = st.hi; bs.amin()[st.b - 1] = st.ilo; bs.amax()[st.b - 1] = st.ihi; }
-        ++st.b; st.lo = dinf; st.hi = -dinf; st.ilo = 0x7fffffff; st.ihi = 0x7fffffff;
-    }
-    // table entries e = c0/32 + l cover S[32e .. 32e+31] = buf[32l-1 .. 32l+30] (buf[-1] = prev_last); an entry that
-    // continues in the next chunk is computed there
-    const bool last_chunk = hi_idx >= n;
-    for (int l = lane; l <= CHUNK / 32; l += 32) {
-        if (32 * l - 1 > cnt - 1 || (l == CHUNK / 32 && !last_chunk)) continue;
-        // extrema of the run in double through order-preserving integer keys (f64 -> f32 conversions run on the XU pipe
-        // at half a lane per clock on B200: two per prefix sum made this kernel XU bound); two conversions per entry remain
-        long long klo = 0x7fffffffffffffffLL, khi = -0x7fffffffffffffffLL - 1;
-#pragma unroll 4
-        for (int tt = 0; tt < 32; ++tt) {
-            const int k = 32 * l - 1 + ((tt + l) & 31);  // skewed: the lanes hit different banks
-            if (k <= cnt - 1) {
-                const long long key = dkey((k < 0) ? prev_last : buf[k]);
-                klo = min(klo, key); khi = max(khi, key);
-            }
-        }
-        tmin[(c0 >> 5) + l] = __double2float_rd(dunkey(klo)); tmax[(c0 >> 5) + l] = __double2float_ru(dunkey(khi));
-    }
-}
-
-// ------------------------------------------------------------------------------------
 // k_prep: one warp per pending segment.  The sums of the reference are strictly sequential
 // (CBS.cpp:986-989 mean and tss, :83-87 prefix sums), so lane 0 runs them as ONE dependent DADD chain
 // (8 cycles per marker on B200) over chunks staged in shared memory, while the other lanes already have
@@ -816,81 +752,223 @@ __global__ void __launch_bounds__(128) k_perm(Dev* D) {
 
 // ------------------------------------------------------------------------------------
 // k_chain: turns the gathered values S[1..n] of every permutation into prefix sums IN PLACE with ONE strictly
-// sequential DADD chain per permutation (the reference's order, CBS.cpp:83-90, hence identical rounding).  A warp
-// owns a permutation: lane 0 walks a chunk staged in shared memory at the DADD latency (8 cycles per marker on
-// B200) while all lanes already hold the next chunk in registers; finished chunks are stored coalesced.  Dozens of
-// warps per SM keep the FP64 pipe and HBM busy when many permutations are in flight.
+// sequential DADD chain per permutation (the reference's order, CBS.cpp:83-90, hence identical rounding), and writes
+// the row's statistics for the scan next to it: per block of the reference's sqrt(n) blocks the extrema with their FIRST
+// occurrence (CBS.cpp:88-94), and per aligned run of 32 prefix sums the extrema in single precision rounded outwards.
+// A CTA is a PAIR of warps that owns CHAIN_Q = 4 consecutive permutations of a batch:
+//   warp A  stages chunks of the four rows in shared memory (the next chunk is already in flight in registers); lanes
+//           0, 8, 16, 24 each walk one row at the DADD latency (8 cycles per marker on B200), so one warp instruction
+//           advances four chains and nothing else is ever on their critical path;
+//   warp B  takes each finished chunk: stores it coalesced and computes the statistics, eight lanes per row (block
+//           extrema reduced with redux.sync on order-preserving keys), while A is already summing the next chunk.
+// The chunks go through a ring of CP_SLOTS buffers; the hand-over is two monotone chunk counters in shared memory.
+// Round 1 gave a permutation one warp that did both jobs in turn with one active lane: ~5.4 warp instructions per
+// marker, issue bound at a fraction of the FP64 pipe; this layout needs ~1.3.
 // ------------------------------------------------------------------------------------
-#define CHAIN_WARPS 4
-#ifndef CHAIN_CHUNK
-#define CHAIN_CHUNK 1024
-#endif
-#ifndef CHAIN_MIN_CTAS
-#define CHAIN_MIN_CTAS 3
-#endif
+#define CP_CHUNK 256
+#define CP_ROW (CP_CHUNK + 4)  // doubles: +4 puts the four rows on different banks for the 128-bit accesses of the summing lanes
+#define CP_SLOTS 3
+
+// order-preserving map between floats and signed 32-bit integers (its own inverse on the bit pattern)
+__device__ __forceinline__ int fkey(float v) { const int b = __float_as_int(v); return b ^ ((b >> 31) & 0x7fffffff); }
+__device__ __forceinline__ float funkey(int k) { return __int_as_float(k ^ ((k >> 31) & 0x7fffffff)); }
+
+// first occurrence of the smallest (largest) value among the lanes of `gmask`: three redux.sync on the order-preserving key
+__device__ __forceinline__ void group_argmin(double& v, int& idx, unsigned gmask) {
+    const long long key = dkey(v + 0.0);  // -0.0 and +0.0 compare equal in the reference: one key
+    const int hi = (int)(key >> 32);
+    const unsigned lo = (unsigned)key;
+    const int mhi = __reduce_min_sync(gmask, hi);
+    const unsigned mlo = __reduce_min_sync(gmask, hi == mhi ? lo : 0xffffffffu);
+    const bool win = hi == mhi && lo == mlo;
+    idx = __reduce_min_sync(gmask, win ? idx : 0x7fffffff);
+    v = dunkey(((long long)mhi << 32) | (long long)mlo);
+}
+__device__ __forceinline__ void group_argmax(double& v, int& idx, unsigned gmask) {
+    const long long key = dkey(v + 0.0);
+    const int hi = (int)(key >> 32);
+    const unsigned lo = (unsigned)key;
+    const int mhi = __reduce_max_sync(gmask, hi);
+    const unsigned mlo = __reduce_max_sync(gmask, hi == mhi ? lo : 0u);
+    const bool win = hi == mhi && lo == mlo;
+    idx = __reduce_min_sync(gmask, win ? idx : 0x7fffffff);
+    v = dunkey(((long long)mhi << 32) | (long long)mlo);
+}
+
+#define CP_STAT_WARPS 4                       // warps B: each takes CHAIN_Q / CP_STAT_WARPS rows of the chunk
+#define CP_LPR (32 * CP_STAT_WARPS / CHAIN_Q)  // lanes of a warp B per row (32: a warp per row)
 template <bool WEIGHTED>  // weighted CBS: the chain adds px*w (wtmaxo, CBS.cpp:623,627); the product is rounded before the addition
-__global__ void __launch_bounds__(CHAIN_WARPS * 32, CHAIN_MIN_CTAS) k_chain(Dev* D) {
-    __shared__ __align__(16) double buf_all[CHAIN_WARPS][CHAIN_CHUNK];
+__global__ void __launch_bounds__(32 * (1 + CP_STAT_WARPS)) k_chain(Dev* D) {
+    __shared__ __align__(16) double bufs[CP_SLOTS][CHAIN_Q][CP_ROW];
+    __shared__ volatile int s_full, s_done[CP_STAT_WARPS];
+    __shared__ int s_g;
     if (D->done) return;
-    const int lane = threadIdx.x & 31;
-    double* buf = buf_all[threadIdx.x >> 5];
-    const int total = D->item_prefix[D->n_items];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const bool summing = warp == 0;  // warp A
+    if (threadIdx.x == 0) { s_full = 0; for (int w = 0; w < CP_STAT_WARPS; ++w) s_done[w] = 0; }
+    __syncthreads();
+    const int total = D->item_uprefix[D->n_items];
+    const double dinf = __longlong_as_double(0x7ff0000000000000LL);
+    int seq = 0;  // chunks handled so far (the same number in all warps)
     for (;;) {
-        int g = 0;
-        if (lane == 0) g = (int)atomicAdd(&D->ctr[3], 1u);
-        g = __shfl_sync(FULL, g, 0);
+        if (threadIdx.x == 0) s_g = (int)atomicAdd(&D->ctr[3], 1u);
+        __syncthreads();
+        const int g = s_g;
+        __syncthreads();
         if (g >= total) break;
-        const int k = find_item(D->item_prefix, D->n_items, g);
+        const int k = find_item(D->item_uprefix, D->n_items, g);
         const PermItem it = D->items[k];
         if (it.obs) continue;  // k_prep wrote the prefix sums of observed data
         const Task& t = D->tasks[it.task];
-        const int n = t.n;
-        const int pp = g - D->item_prefix[k], nb = t.nb;
-        double* sx = D->arena + t.off_sx + (long long)pp * Sched::sx_stride(n);
-        BlockStats bs(D->arena + t.off_bs + (long long)pp * Sched::bs_stride(nb), nb);
-        const int* __restrict__ bb = D->bbtab + D->unit_off[t.unit] + t.lo;
-        float* tmin = (float*)(sx + Sched::tbl_offset(n));
-        float* tmax = tmin + Sched::tbl_entries(n);
-        RowStats rst;
-        row_stats_init(rst);
-        double prev_last = 0.0;  // S[0]
-        const double* __restrict__ src = sx + 1;
-        const double* __restrict__ wt = WEIGHTED ? D->w + D->unit_off[t.unit] + t.lo : nullptr;
-        if (lane == 0) sx[0] = 0.0;
-        double run = 0.0;
-        double r[CHAIN_CHUNK / 32];
+        const int n = t.n, nb = t.nb;
+        const int p0 = (g - D->item_uprefix[k]) * CHAIN_Q;
+        const int nq = min(CHAIN_Q, it.P - p0);
+        const long long stride = Sched::sx_stride(n);
+        double* sx0 = D->arena + t.off_sx + (long long)p0 * stride;
+        const int nchunks = (n + CP_CHUNK - 1) / CP_CHUNK;
+        if (summing) {
+            const int q = lane >> 3;  // lanes 0, 8, 16, 24 sum rows 0..3
+            const double* __restrict__ wt = WEIGHTED ? D->w + D->unit_off[t.unit] + t.lo : nullptr;
+            double run = 0.0;
+            double r[CHAIN_Q][CP_CHUNK / 32];
 #pragma unroll
-        for (int q = 0; q < CHAIN_CHUNK / 32; ++q) { const int i = lane + 32 * q; r[q] = (i < n) ? (WEIGHTED ? src[i] * wt[i] : src[i]) : 0.0; }
-        for (int c0 = 0; c0 < n; c0 += CHAIN_CHUNK) {
-            const int cnt = min(CHAIN_CHUNK, n - c0);
-            __syncwarp();
+            for (int q2 = 0; q2 < CHAIN_Q; ++q2)
 #pragma unroll
-            for (int q = 0; q < CHAIN_CHUNK / 32; ++q) buf[lane + 32 * q] = r[q];
-            __syncwarp();
-            if (c0 + CHAIN_CHUNK < n) {
-#pragma unroll
-                for (int q = 0; q < CHAIN_CHUNK / 32; ++q) { const int i = c0 + CHAIN_CHUNK + lane + 32 * q; r[q] = (i < n) ? (WEIGHTED ? src[i] * wt[i] : src[i]) : 0.0; }
-            }
-            if (lane == 0) {
-                int kk = 0;
-#pragma unroll 8
-                for (; kk + 1 < cnt; kk += 2) {
-                    double2 v = *reinterpret_cast<const double2*>(buf + kk);
-                    run = run + v.x; v.x = run;
-                    run = run + v.y; v.y = run;
-                    *reinterpret_cast<double2*>(buf + kk) = v;
+                for (int j = 0; j < CP_CHUNK / 32; ++j) {
+                    const int i = lane + 32 * j;
+                    const bool ok = q2 < nq && i < n;
+                    double v = ok ? sx0[(long long)q2 * stride + 1 + i] : 0.0;
+                    if (WEIGHTED && ok) v = v * wt[i];
+                    r[q2][j] = v;
                 }
-                if (kk < cnt) { run = run + buf[kk]; buf[kk] = run; }
+            for (int c = 0; c < nchunks; ++c) {
+                const int c0 = c * CP_CHUNK, cnt = min(CP_CHUNK, n - c0);
+                double (*buf)[CP_ROW] = bufs[(seq + c) % CP_SLOTS];
+                // the slot's previous chunk has been consumed by every warp B (plain spin: a sleep overshoots by more than a chunk takes)
+#pragma unroll
+                for (int w = 0; w < CP_STAT_WARPS; ++w) while (s_done[w] < seq + c - (CP_SLOTS - 1)) {}
+                __syncwarp();
+#pragma unroll
+                for (int q2 = 0; q2 < CHAIN_Q; ++q2)
+#pragma unroll
+                    for (int j = 0; j < CP_CHUNK / 32; ++j) buf[q2][lane + 32 * j] = r[q2][j];
+                __syncwarp();
+                if (c + 1 < nchunks) {
+#pragma unroll
+                    for (int q2 = 0; q2 < CHAIN_Q; ++q2)
+#pragma unroll
+                        for (int j = 0; j < CP_CHUNK / 32; ++j) {
+                            const int i = c0 + CP_CHUNK + lane + 32 * j;
+                            const bool ok = q2 < nq && i < n;
+                            double v = ok ? sx0[(long long)q2 * stride + 1 + i] : 0.0;
+                            if (WEIGHTED && ok) v = v * wt[i];
+                            r[q2][j] = v;
+                        }
+                }
+                if ((lane & 7) == 0 && q < nq) {
+                    double* row = buf[q];
+                    int kk = 0;
+#pragma unroll 8
+                    for (; kk + 1 < cnt; kk += 2) {
+                        double2 v = *reinterpret_cast<const double2*>(row + kk);
+                        run = run + v.x; v.x = run;
+                        run = run + v.y; v.y = run;
+                        *reinterpret_cast<double2*>(row + kk) = v;
+                    }
+                    if (kk < cnt) { run = run + row[kk]; row[kk] = run; }
+                }
+                __syncwarp();
+                if (lane == 0) { __threadfence_block(); s_full = seq + c + 1; }
             }
-            __syncwarp();
-            for (int kk = lane; kk < cnt; kk += 32) sx[c0 + 1 + kk] = buf[kk];
-            row_stats_chunk<CHAIN_CHUNK>(buf, c0, cnt, n, prev_last, bb, nb, bs, tmin, tmax, rst, lane);
-            prev_last = buf[cnt - 1];
+        } else {
+            const int bw = warp - 1;                       // which warp B
+            const int sub = lane % CP_LPR;                 // lane within the row's group
+            const int q = bw * (32 / CP_LPR) + lane / CP_LPR;  // row of this lane
+            const bool valid = q < nq;
+            const int qr = valid ? q : nq - 1;  // lanes of unused rows shadow the last row (uniform control flow), without writing
+            const unsigned gmask = (CP_LPR == 32 ? 0xffffffffu : ((1u << CP_LPR) - 1u)) << (CP_LPR * (lane / CP_LPR));
+            double* sxg = sx0 + (long long)qr * stride;
+            BlockStats bs(D->arena + t.off_bs + (long long)(p0 + qr) * Sched::bs_stride(nb), nb);
+            const int* __restrict__ bb = D->bbtab + D->unit_off[t.unit] + t.lo;
+            float* tmin = (float*)(sxg + Sched::tbl_offset(n));
+            float* tmax = tmin + Sched::tbl_entries(n);
+            int b = 1;
+            double blo = dinf, bhi = -dinf;
+            int ilo = 0x7fffffff, ihi = 0x7fffffff;
+            double prev_last = 0.0;  // S[0]
+            if (valid && sub == 0) sxg[0] = 0.0;
+            const int q_first = bw * (32 / CP_LPR), q_end = min(nq, q_first + 32 / CP_LPR);  // rows this warp stores
+            for (int c = 0; c < nchunks; ++c) {
+                const int c0 = c * CP_CHUNK, cnt = min(CP_CHUNK, n - c0), hi_idx = c0 + cnt;
+                const double (*buf)[CP_ROW] = bufs[(seq + c) % CP_SLOTS];
+                while (s_full < seq + c + 1) __nanosleep(256);  // B is the faster side and has two slots of slack: do not burn issue slots
+                __threadfence_block();
+                __syncwarp();
+                for (int q2 = q_first; q2 < q_end; ++q2) {
+                    double* dst = sx0 + (long long)q2 * stride + c0 + 1;
+                    for (int kk = lane; kk < cnt; kk += 32) dst[kk] = buf[q2][kk];
+                }
+                const double* row = buf[qr];
+                // per-block extrema with their first occurrence; the blocks are those of the segment, the same for all rows
+                while (b <= nb) {
+                    const int first = bb[b - 1] + 1, last = bb[b];
+                    const int a = max(first, c0 + 1), z = min(last, hi_idx);
+                    if (a > z) break;
+                    double lo = dinf, hi = -dinf;
+                    int jlo = 0x7fffffff, jhi = 0x7fffffff;
+                    for (int i = a + sub; i <= z; i += CP_LPR) {
+                        const double v = row[i - c0 - 1];
+                        if (v < lo) { lo = v; jlo = i; }
+                        if (v > hi) { hi = v; jhi = i; }
+                    }
+                    group_argmin(lo, jlo, gmask);
+                    group_argmax(hi, jhi, gmask);
+                    if (lo < blo) { blo = lo; ilo = jlo; }  // the part seen earlier holds the earlier indices: it wins ties
+                    if (hi > bhi) { bhi = hi; ihi = jhi; }
+                    if (last > hi_idx) break;  // the block continues in the next chunk
+                    if (valid && sub == 0) { bs.bmin()[b - 1] = blo; bs.bmax()[b - 1] = bhi; bs.amin()[b - 1] = ilo; bs.amax()[b - 1] = ihi; }
+                    ++b; blo = dinf; bhi = -dinf; ilo = 0x7fffffff; ihi = 0x7fffffff;
+                }
+                // table entries e = c0/32 + l cover S[32e .. 32e+31] = row[32l-1 .. 32l+30] (row[-1] = prev_last).  One pass per
+                // entry: the row's group of lanes reads the run coalesced, converts (rounded outwards) and reduces with
+                // redux.sync on order-preserving keys; the passes are independent, so their latencies overlap.  The entry that
+                // starts with the chunk's last value is only complete in the last chunk.
+                const bool last_chunk = hi_idx >= n;
+                float mylo = 0.f, myhi = 0.f;
+#pragma unroll
+                for (int l = 0; l <= CP_CHUNK / 32; ++l) {
+                    if (32 * l - 1 > cnt - 1 || (l == CP_CHUNK / 32 && !last_chunk)) continue;  // uniform
+                    int klo = 0x7fffffff, khi = (int)0x80000000;
+                    for (int u = sub; u < 32; u += CP_LPR) {
+                        const int kx = 32 * l - 1 + u;
+                        if (kx <= cnt - 1) {
+                            // order-preserving key of the HIGH word of the double: integer work only (two f64 -> f32 conversions per
+                            // prefix sum saturate the XU pipe, about one lane per clock and SM on B200)
+                            const int hk = fkey(__int_as_float(__double2hiint((kx < 0) ? prev_last : row[kx])));
+                            klo = min(klo, hk); khi = max(khi, hk);
+                        }
+                    }
+                    klo = __reduce_min_sync(gmask, klo); khi = __reduce_max_sync(gmask, khi);
+                    if (sub == (l % CP_LPR)) {
+                        // all doubles with the extreme high words lie between these two; rounded outwards to single precision
+                        const int hlo = __float_as_int(funkey(klo)), hhi = __float_as_int(funkey(khi));
+                        mylo = __double2float_rd(__hiloint2double(hlo, hlo < 0 ? -1 : 0));
+                        myhi = __double2float_ru(__hiloint2double(hhi, hhi < 0 ? 0 : -1));
+                        if (valid) { tmin[(c0 >> 5) + l] = mylo; tmax[(c0 >> 5) + l] = myhi; }
+                    }
+                }
+                prev_last = row[cnt - 1];
+                __syncwarp();
+                if (lane == 0) s_done[bw] = seq + c + 1;
+            }
+            // the scan reads up to SX_PAD values behind S_n without bounds checks: keep them finite
+            for (int q2 = q_first; q2 < q_end; ++q2) {
+                const double lastv = shfl_d(prev_last, CP_LPR * (q2 - q_first));
+                double* dst = sx0 + (long long)q2 * stride + n + 1;
+                for (int kk = lane; kk < SX_PAD; kk += 32) dst[kk] = lastv;
+            }
         }
-        // the scan reads up to SX_PAD values behind S_n without bounds checks: keep them finite
-        run = shfl_d(run, 0);
-        for (int kk = lane; kk < SX_PAD; kk += 32) sx[n + 1 + kk] = run;
-        __syncwarp();
+        seq += nchunks;
     }
 }
 
