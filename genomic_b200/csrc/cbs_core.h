@@ -319,6 +319,10 @@ struct Dev {
     double* rw;       // sqrt(w) (CBS.cpp:1056)
     double* cw;       // per pending segment, at the segment's offset: cumsum(w)/sqrt(sum w) (CBS.cpp:1062-1066)
     double* ycur;     // cur * rw: what wxperm shuffles (CBS.cpp:540)
+    // ---- low-level entry points (cbs::fndcpt / cbs::tpermp on a vector as given) run ONE decision through the same worklist ----
+    int api_mode;     // 0: cbs::segment; 1: one fndcpt decision on unit 0 (x and tss as given, no children); 2: one tpermp test
+    double api_tss, api_delta;  // fndcpt: tss argument; hybrid: delta argument (0: (kmax+1)/n)
+    int api_n1, api_n2;         // tpermp: sizes of the two sides
     int shuf_cl2;     // segments of 65536..SHUF_CL2_MAX markers have their own class (cluster of 2 CTAs)
     int shuf_arena;   // segments > 65535 markers are shuffled by k_perm on 32-bit index arrays in the arena (fallback of k_shuffle_cluster)
     int no_early;     // CBS_GPU_NO_EARLY=1: decision-mode scans never stop at the first rejecting arc (A/B switch)
@@ -392,6 +396,21 @@ struct Sched {
         t.key = task_key(D.prm.seed, D.unit_ids ? D.unit_ids[unit] : (uint64_t)unit, (uint32_t)lo, (uint32_t)hi);
         return idx;
     }
+    // root task of a unit; the low-level entry points hand the vector over as is (cbs::fndcpt gets centred data and its tss)
+    CBS_HD int new_root(int unit, int n) {
+        const int idx = new_task(unit, 0, n);
+        if (idx < 0 || !D.api_mode) return idx;
+        Task& t = D.tasks[idx];
+        t.raw = 1; t.tss = D.api_tss;
+        if (D.api_mode == 2) {  // cbs::tpermp(n1, n2, n, x, ...): only the test of "side 0"; side 1 gets a one-point side: p = 1, no draws
+            t.e_n1[0] = D.api_n1; t.e_n2[0] = D.api_n2; t.e_off[0] = 0;
+            t.e_n1[1] = 1; t.e_n2[1] = 1; t.e_off[1] = 0;
+            t.state = TS_EDGEPREP;
+            D.edgeprep_task[D.n_edgeprep++] = idx;
+            t.obs_round = D.round;  // the sums are computed by this round's k_edgeprep
+        }
+        return idx;
+    }
     CBS_HD void emit_segment(const Task& t) {
         if (D.n_segs >= D.seg_cap) { D.error = ERR_SEG_CAP; return; }
         SegRec& s = D.segs[D.n_segs++];
@@ -435,6 +454,11 @@ struct Sched {
         log_split(t, called, ncpt, icpt0, icpt1);
         Chain* ch = chain_of(t);
         const int unit = t.unit, lo = t.lo, hi = t.hi, below = t.next;
+        if (D.api_mode) {  // a single decision was asked for: it is in the split log, nothing follows
+            free_task(idx);
+            if (ch) ch->top = below;
+            return;
+        }
         if (ncpt == 0) {
             emit_segment(t);
             free_task(idx);
@@ -479,7 +503,7 @@ struct Sched {
             const int u = ch->unit_next++;
             const long long n = D.unit_off[u + 1] - D.unit_off[u];
             if (n <= 0) continue;  // cna_segment.hpp:138
-            const int idx = new_task(u, 0, (int)n);
+            const int idx = new_root(u, (int)n);
             if (idx < 0) return false;
             ch->top = idx;
             ch->unit_cur = u;
@@ -769,6 +793,7 @@ struct Sched {
                 return true;
             }
             case TS_EDGEPREP: {
+                if (D.api_mode == 2 && t.obs_round == D.round) return true;  // cbs::tpermp entry: k_edgeprep runs in this round
                 t.e_side = 0; t.e_done = 0;
                 if (!next_edge_side(t)) { finish_edges(idx); return false; }
                 t.state = TS_EDGEPERM; t.deferred = 1;
@@ -854,7 +879,7 @@ struct Sched {
                         const int u = D.units_started++;
                         const long long n = D.unit_off[u + 1] - D.unit_off[u];
                         if (n <= 0) continue;
-                        const int idx = new_task(u, 0, (int)n);
+                        const int idx = new_root(u, (int)n);
                         if (idx < 0) break;
                         push_out(idx);
                         added = true;

@@ -321,8 +321,15 @@ long long env_ll(const char* name, long long dflt) {
 }
 
 // The core: x already resident (double, device, smoothed if requested) in c->x.
+struct ApiMode {   // low-level entry points: ONE decision on the vector as given (cbs_core.h Dev::api_mode)
+    int mode = 0;
+    double tss = 0.0, delta = 0.0;
+    int n1 = 0, n2 = 0;
+};
+
 int run_cbs(cbs_gpu_ctx* c, const std::vector<long long>& off, const uint64_t* unit_ids, int n_units,
-            const cbs_gpu_params* p, const uint64_t* mt_next312, bool weighted /* weights resident in c->wts */, Dev& hD) {
+            const cbs_gpu_params* p, const uint64_t* mt_next312, bool weighted /* weights resident in c->wts */, Dev& hD,
+            const ApiMode& api = ApiMode()) {
     cudaStream_t st = c->stream;
     // profiling bit 2: every kernel on the one stream, so that per-launch event times do not overlap (roofline time base)
     cudaStream_t side[5], gen_stream = c->serial ? st : c->gen_stream;
@@ -342,7 +349,7 @@ int run_cbs(cbs_gpu_ctx* c, const std::vector<long long>& off, const uint64_t* u
     cap.list_cap = 4 * cap.task_cap + n_units + 16;
     cap.seg_cap = (int)std::min<long long>(N / 2 + n_units + 16, std::max<long long>(1 << 20, 256LL * n_units));
     cap.seg_cap = (int)env_ll("CBS_GPU_SEG_CAP", cap.seg_cap);
-    cap.split_cap = p->record_splits ? 3 * cap.seg_cap + 16 : 1;
+    cap.split_cap = (p->record_splits || api.mode) ? 3 * cap.seg_cap + 16 : 1;
     cap.max_live = mt ? std::max(1, cap.task_cap / 16) : std::max(1, cap.task_cap / 4);
     // MT with one engine per unit: every chain reads the one shared stream from position 0 and the stream window only moves
     // forward once all chains have started, so admit them all in the first round
@@ -446,7 +453,9 @@ int run_cbs(cbs_gpu_ctx* c, const std::vector<long long>& off, const uint64_t* u
     hD.prm.first_batch = p->first_batch > 0 ? p->first_batch : 256;
     hD.prm.max_batch = p->max_batch > 0 ? p->max_batch : 4096;
     if (hD.prm.max_batch < hD.prm.first_batch) hD.prm.max_batch = hD.prm.first_batch;
-    hD.prm.record_splits = p->record_splits ? 1 : 0;
+    hD.prm.record_splits = (p->record_splits || api.mode) ? 1 : 0;
+    hD.api_mode = api.mode; hD.api_tss = api.tss; hD.api_delta = api.delta; hD.api_n1 = api.n1; hD.api_n2 = api.n2;
+    if (api.mode) hD.prm.nmin = 0;  // cbs::fndcpt takes `hybrid` as given (cbs::segment derives it from nmin, CBS.cpp:983)
     hD.cur = c->cur.as<double>(); hD.gtab = c->gtab.as<double>(); hD.factab = c->factab.as<double>(); hD.bbtab = c->bbtab.as<int>();
     hD.tasks = c->tasks.as<Task>(); hD.task_cap = cap.task_cap; hD.free_ring = c->ring.as<int>();
     hD.free_head = 0; hD.free_tail = (unsigned)cap.task_cap;
@@ -510,6 +519,7 @@ int run_cbs(cbs_gpu_ctx* c, const std::vector<long long>& off, const uint64_t* u
         CUDA_TRY(c, cudaStreamSynchronize(st));  // `ring` is a stack temporary
     }
     Dev* dD = c->dev.as<Dev>();
+    if (api.mode == 2 && N) CUDA_TRY(c, cudaMemcpyAsync(c->cur.p, c->x.p, sizeof(double) * (size_t)N, cudaMemcpyDeviceToDevice, st));  // no k_prep in this mode
     if (mt) {
         uint64_t next[312];
         if (mt_next312) memcpy(next, mt_next312, sizeof(next)); else mt_seed_next312(p->seed, next);
@@ -1338,6 +1348,82 @@ int cbs_gpu_segment_weighted(cbs_gpu_ctx* c, const double* x, const double* weig
     if (draws_consumed) *draws_consumed = R.draws[0];
     if (R.pub.n_segments > cap) return fail(c, CBS_GPU_ERR_CAPACITY, "output capacity too small");
     for (int64_t k = 0; k < R.pub.n_segments; ++k) { lengths[k] = R.lengths[k]; means[k] = R.means[k]; }
+    return CBS_GPU_OK;
+}
+
+// ---- low level: one decision on a vector as given -------------------------------------------------------------
+static int decision_impl(cbs_gpu_ctx* c, const double* x, const double* weights, int32_t n, const cbs_gpu_params* params,
+                         const ApiMode& api, const uint64_t* mt_next312, cbs_gpu_split* out, uint64_t* draws_consumed) {
+    if (!c) return CBS_GPU_ERR_INVALID;
+    if (n < 2 || !x || !params || !out) return fail(c, CBS_GPU_ERR_INVALID, "bad arguments");
+    if (cudaSetDevice(c->device) != cudaSuccess) return fail(c, CBS_GPU_ERR_CUDA, "cudaSetDevice failed");
+    cbs_gpu_params p = *params;
+    p.do_smooth = 0; p.undo_prune = 0; p.chain = 0; p.record_splits = 1;
+    int rc = validate_params(c, &p);
+    if (rc) return rc;
+    for (int i = 0; i < n; ++i) if (!std::isfinite(x[i])) return fail(c, CBS_GPU_ERR_NONFINITE, "non-finite values reach CBS");
+    cudaStream_t st = c->stream;
+    ENSURE(c, c->x, sizeof(double) * (size_t)(n + 1));
+    CUDA_TRY(c, cudaMemcpyAsync(c->x.p, x, sizeof(double) * (size_t)n, cudaMemcpyHostToDevice, st));
+    if (weights) {
+        ENSURE(c, c->wts, sizeof(double) * (size_t)(n + 1));
+        CUDA_TRY(c, cudaMemcpyAsync(c->wts.p, weights, sizeof(double) * (size_t)n, cudaMemcpyHostToDevice, st));
+    }
+    std::vector<long long> off = {0, (long long)n};
+    Dev hD;
+    for (int k = 0; k < K_COUNT; ++k) c->kms[k] = 0.0;
+    rc = run_cbs(c, off, nullptr, 1, &p, mt_next312, weights != nullptr, hD, api);
+    if (rc) return rc;
+    if (hD.n_splits < 1) return fail(c, CBS_GPU_ERR_CUDA, "internal: the decision was not recorded");
+    SplitRec s;
+    uint64_t draws = 0;
+    CUDA_TRY(c, cudaMemcpyAsync(&s, c->splits.p, sizeof(SplitRec), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(c, cudaMemcpyAsync(&draws, c->udraws.p, sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(c, cudaStreamSynchronize(st));
+    if (c->profiling) collect_timers(c);
+    memset(out, 0, sizeof(*out));
+    out->unit = 0; out->lo = s.lo; out->hi = s.hi; out->ostat = s.ostat; out->iseg0 = s.iseg0; out->iseg1 = s.iseg1;
+    out->ncpt = s.ncpt; out->icpt0 = s.icpt0; out->icpt1 = s.icpt1; out->perms_run = s.perms_run; out->nrej = s.nrej;
+    out->exit_code = s.exit_code; out->called = s.called; out->e_nrej0 = s.e_nrej0; out->e_nrej1 = s.e_nrej1;
+    out->e_status0 = s.e_status0; out->e_status1 = s.e_status1;
+    if (draws_consumed) *draws_consumed = draws;
+    return CBS_GPU_OK;
+}
+
+int cbs_gpu_fndcpt(cbs_gpu_ctx* c, const double* x, int32_t n, double tss, const cbs_gpu_params* params, double delta,
+                   int32_t ngrid, const uint64_t* mt_next312, cbs_gpu_split* out, uint64_t* draws_consumed) {
+    if (!c) return CBS_GPU_ERR_INVALID;
+    if (params && params->hybrid && ngrid != 100) return fail(c, CBS_GPU_ERR_UNSUPPORTED, "hybrid: ngrid must be 100");
+    if (params && n < 2 * params->min_width) return fail(c, CBS_GPU_ERR_INVALID, "need n >= 2*al0");
+    ApiMode api;
+    api.mode = 1; api.tss = tss; api.delta = delta;
+    return decision_impl(c, x, nullptr, n, params, api, mt_next312, out, draws_consumed);
+}
+
+int cbs_gpu_wfindcpt(cbs_gpu_ctx* c, const double* x, const double* weights, int32_t n, double tss, const cbs_gpu_params* params,
+                     int32_t ngrid, const uint64_t* mt_next312, cbs_gpu_split* out, uint64_t* draws_consumed) {
+    if (!c) return CBS_GPU_ERR_INVALID;
+    if (!weights) return fail(c, CBS_GPU_ERR_INVALID, "weights is NULL");
+    if (params && params->hybrid && ngrid != 100) return fail(c, CBS_GPU_ERR_UNSUPPORTED, "hybrid: ngrid must be 100");
+    if (params && n < 2 * params->min_width) return fail(c, CBS_GPU_ERR_INVALID, "need n >= 2*al0");
+    ApiMode api;
+    api.mode = 1; api.tss = tss;
+    return decision_impl(c, x, weights, n, params, api, mt_next312, out, draws_consumed);
+}
+
+int cbs_gpu_tpermp(cbs_gpu_ctx* c, const double* x, int32_t n1, int32_t n2, const cbs_gpu_params* params,
+                   const uint64_t* mt_next312, double* pvalue, uint64_t* draws_consumed) {
+    if (!c) return CBS_GPU_ERR_INVALID;
+    if (n1 < 1 || n2 < 1 || !pvalue || !params) return fail(c, CBS_GPU_ERR_INVALID, "bad arguments");
+    if (params->nperm < 1) return fail(c, CBS_GPU_ERR_INVALID, "nperm must be >= 1");
+    ApiMode api;
+    api.mode = 2; api.n1 = n1; api.n2 = n2;
+    cbs_gpu_split s;
+    cbs_gpu_params p = *params;
+    p.hybrid = 0; p.min_width = 1;
+    const int rc = decision_impl(c, x, nullptr, n1 + n2, &p, api, mt_next312, &s, draws_consumed);
+    if (rc) return rc;
+    *pvalue = s.e_status0 == 1 ? 1.0 : s.e_status0 == 2 ? 0.0 : (double)s.e_nrej0 / (double)p.nperm;  // CBS.cpp:499,522,535
     return CBS_GPU_OK;
 }
 

@@ -1880,7 +1880,8 @@ __global__ void __launch_bounds__(128) k_tailp_terms(Dev* D, double* terms) {
         if (!t.use_hybrid || t.alleq) continue;
         const double b = sqrt(t.ostat);
         if (!(b > 0.1)) continue;
-        const double delta = D->w ? t.w_delta : (double)(D->prm.kmax + 1) / (double)t.n;  // CBS.cpp:984; weighted: getmncwt (:908)
+        const double delta = D->w ? t.w_delta : (D->api_mode && D->api_delta > 0.0) ? D->api_delta
+                                                : (double)(D->prm.kmax + 1) / (double)t.n;  // CBS.cpp:984; weighted: getmncwt (:908)
         const double dincr = (0.5 - delta) / (double)TAILP_NGRID;
         const double bsqrtm = b / sqrt((double)t.n);
         // tl and t after i increments of dincr, accumulated as the reference does (repeated addition)

@@ -49,7 +49,7 @@ __device__ void wprep_warp(Dev* D, Task& t, int lane, double* __restrict__ bx, d
 #pragma unroll
         for (int q = 0; q < WPREP_Q; ++q) if (!(fabs(v[q] - x0) < 1e-12)) flat = false;
     }
-    flat = __all_sync(FULL, flat);
+    flat = __all_sync(FULL, flat) && !t.raw;  // cbs::wfindcpt (low-level entry) takes the vector as it is
     if (lane == 0) { t.alleq = flat ? 1 : 0; t.w_level = 0ull; t.w_found = 0ull; t.w_set = 0; t.w_lock = 0; t.w_init = -1.0; }
     if (flat) return;
     // CBS.cpp:1053-1058: wsum, wxsum.  Every sum is sequential, but the sums are independent of each other: lane 0 runs
@@ -90,7 +90,7 @@ __device__ void wprep_warp(Dev* D, Task& t, int lane, double* __restrict__ bx, d
         for (int q = 0; q < WPREP_Q; ++q) { const int k = lane + 32 * q; if (k < cnt) cw[c0 + k] = bw[k]; }  // unscaled csum (CBS.cpp:1065)
     }
     wsum = shfl_d(wsum, 0); wxsum = shfl_d(wxsum, 0);
-    const double avg = wxsum / wsum;
+    const double avg = t.raw ? 0.0 : wxsum / wsum;  // raw: x is already centred and its tss is the caller's (wfindcpt arguments)
     const double cwscale = sqrt(wsum);
     // CBS.cpp:1061-1066 centring, weighted tss, cw; wtmaxo :623,627 prefix sums of cur*w
     double* __restrict__ sx = D->arena + t.off_sx;
@@ -145,7 +145,7 @@ __device__ void wprep_warp(Dev* D, Task& t, int lane, double* __restrict__ bx, d
     wxx = shfl_d(wxx, 0);
     run = shfl_d(run, 0);
     for (int k = lane; k < SX_PAD; k += 32) sx[n + 1 + k] = run;
-    if (lane == 0) t.tss = wxx;
+    if (lane == 0 && !t.raw) t.tss = wxx;
 }
 
 __global__ void __launch_bounds__(32) k_wprep(Dev* D) {

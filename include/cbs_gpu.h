@@ -153,6 +153,26 @@ int cbs_gpu_tmaxo(cbs_gpu_ctx* ctx, const double* x, int32_t n, double tss, int3
 int cbs_gpu_tmaxp(cbs_gpu_ctx* ctx, const double* px, int32_t n, int32_t count, double tss, int32_t al0, int32_t ibin,
                   double* statistics);
 
+/* ---- low-level call surface (lib/cbs/CBS.hpp:29-98), each ONE decision on the vector as given ---------------------
+ * cbs::fndcpt (CBS.hpp:68-80, CBS.cpp:830-892): x is the centred segment, tss its sum of squares (both as the caller
+ * computed them); params supplies cpval (alpha), nperm, hybrid, al0 (min_width), hk (kmax), tol and the RNG; delta is the
+ * hybrid method's argument (0: (kmax+1)/n), ngrid must be 100.  sbdry is not an argument: `cna segment` disables the
+ * sequential boundary (src/cna_segment.hpp:130) and so does this library.  The result comes back as a split record:
+ * ncpt, icpt0/icpt1, iseg0/iseg1 (0-based, as cbs::ChangePointResult), ostat, plus perms_run, nrej and the edge tests'
+ * counts for diagnostics.  mt_next312 / draws_consumed as in cbs_gpu_segment. */
+int cbs_gpu_fndcpt(cbs_gpu_ctx* ctx, const double* x, int32_t n, double tss, const cbs_gpu_params* params, double delta,
+                   int32_t ngrid, const uint64_t* mt_next312, cbs_gpu_split* out, uint64_t* draws_consumed);
+/* cbs::wfindcpt (CBS.hpp:81-97, CBS.cpp:894-957).  The reference also takes rwts = sqrt(wts) and cwts =
+ * cumsum(wts)/sqrt(sum wts); they are derived from `weights` on the device with the reference's own expressions
+ * (CBS.cpp:1056-1066), and delta comes from getmncwt as in wfindcpt (:908). */
+int cbs_gpu_wfindcpt(cbs_gpu_ctx* ctx, const double* x, const double* weights, int32_t n, double tss,
+                     const cbs_gpu_params* params, int32_t ngrid, const uint64_t* mt_next312, cbs_gpu_split* out,
+                     uint64_t* draws_consumed);
+/* cbs::tpermp (CBS.hpp:35-36, CBS.cpp:495-536): permutation p-value of the boundary between x[0..n1) and x[n1..n1+n2);
+ * params supplies nperm and the RNG */
+int cbs_gpu_tpermp(cbs_gpu_ctx* ctx, const double* x, int32_t n1, int32_t n2, const cbs_gpu_params* params,
+                   const uint64_t* mt_next312, double* pvalue, uint64_t* draws_consumed);
+
 /* host-only self test (needs no device): 0 if the MT19937-64 jump-ahead polynomials reproduce
  * sequential generation */
 int cbs_gpu_selftest(void);
