@@ -156,6 +156,8 @@ EXPORTED_SYMBOLS = (
     "cbs_gpu_segment_batch", "cbs_gpu_result_free", "cbs_gpu_smooth", "cbs_gpu_segment", "cbs_gpu_tmaxo",
     "cbs_gpu_tmaxp", "cbs_gpu_measure_fp64", "cbs_gpu_last_kernel_ms", "cbs_gpu_set_profiling",
     "cbs_gpu_last_arc_evals", "cbs_gpu_selftest", "cbs_gpu_segment_weighted", "cbs_gpu_segment_weighted_batch",
+    "cbs_gpu_fndcpt", "cbs_gpu_wfindcpt", "cbs_gpu_tpermp", "cbs_gpu_wtmaxo", "cbs_gpu_xperm", "cbs_gpu_htmaxp",
+    "cbs_gpu_tailp", "cbs_gpu_btmax", "cbs_gpu_btailp",
 )
 
 
@@ -355,3 +357,96 @@ class Context:
         self._check(self.lib.cbs_gpu_tmaxp(self.h, m.ctypes.data_as(C.POINTER(C.c_double)), m.shape[1], m.shape[0],
                                            tss, al0, int(ibin), out.ctypes.data_as(C.POINTER(C.c_double))))
         return float(out[0]) if single else out
+
+
+    # ---- low-level call surface (lib/cbs/CBS.hpp:29-98) -------------------------------------------------------------
+    @staticmethod
+    def _dp(a):
+        return a.ctypes.data_as(C.POINTER(C.c_double))
+
+    @staticmethod
+    def _state(mt_next312):
+        if mt_next312 is None:
+            return None, None
+        st = np.ascontiguousarray(mt_next312, dtype=np.uint64)
+        assert st.shape == (312,)
+        return st, st.ctypes.data_as(C.POINTER(C.c_uint64))
+
+    @staticmethod
+    def _decision(s: CSplit, draws: int) -> dict:
+        return dict(ncpt=s.ncpt, icpt=(s.icpt0, s.icpt1), iseg=(s.iseg0, s.iseg1), ostat=s.ostat, perms_run=s.perms_run,
+                    nrej=s.nrej, exit_code=s.exit_code, e_nrej=(s.e_nrej0, s.e_nrej1), e_status=(s.e_status0, s.e_status1),
+                    draws=draws)
+
+    def fndcpt(self, x, tss, params: Params, delta=0.0, ngrid=100, mt_next312=None):
+        """cbs::fndcpt (CBS.hpp:68-80) on a centred segment: dict(ncpt, icpt, iseg, ostat, ..., draws)."""
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        keep, st = self._state(mt_next312)
+        cp, out, draws = params.c(), CSplit(), C.c_uint64(0)
+        self._check(self.lib.cbs_gpu_fndcpt(self.h, self._dp(x), len(x), C.c_double(tss), C.byref(cp), C.c_double(delta), ngrid, st,
+                                            C.byref(out), C.byref(draws)))
+        return self._decision(out, draws.value)
+
+    def wfindcpt(self, x, weights, tss, params: Params, ngrid=100, mt_next312=None):
+        """cbs::wfindcpt (CBS.hpp:81-97); rwts and cwts are derived from weights as cbs::segment_weighted does."""
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        w = np.ascontiguousarray(weights, dtype=np.float64)
+        keep, st = self._state(mt_next312)
+        cp, out, draws = params.c(), CSplit(), C.c_uint64(0)
+        self._check(self.lib.cbs_gpu_wfindcpt(self.h, self._dp(x), self._dp(w), len(x), C.c_double(tss), C.byref(cp), ngrid, st,
+                                              C.byref(out), C.byref(draws)))
+        return self._decision(out, draws.value)
+
+    def tpermp(self, n1, n2, x, params: Params, mt_next312=None):
+        """cbs::tpermp (CBS.hpp:35-36) -> (p-value, draws consumed)."""
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        assert len(x) >= n1 + n2
+        keep, st = self._state(mt_next312)
+        cp, p, draws = params.c(), C.c_double(), C.c_uint64(0)
+        self._check(self.lib.cbs_gpu_tpermp(self.h, self._dp(x), n1, n2, C.byref(cp), st, C.byref(p), C.byref(draws)))
+        return p.value, draws.value
+
+    def wtmaxo(self, x, weights, tss, al0=2):
+        """cbs::wtmaxo (CBS.hpp:54-58) -> (statistic, start, end)."""
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        w = np.ascontiguousarray(weights, dtype=np.float64)
+        stat, s, e = C.c_double(), C.c_int32(), C.c_int32()
+        self._check(self.lib.cbs_gpu_wtmaxo(self.h, self._dp(x), self._dp(w), len(x), C.c_double(tss), al0, C.byref(stat),
+                                            C.byref(s), C.byref(e)))
+        return stat.value, s.value, e.value
+
+    def xperm(self, x, seed=1, mt_next312=None, rwts=None):
+        """cbs::xperm (CBS.hpp:37), or cbs::wxperm (CBS.hpp:39-42) when rwts is given: one permutation, n draws."""
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        rw = None if rwts is None else np.ascontiguousarray(rwts, dtype=np.float64)
+        keep, st = self._state(mt_next312)
+        px = np.zeros(len(x), dtype=np.float64)
+        self._check(self.lib.cbs_gpu_xperm(self.h, self._dp(x), None if rw is None else self._dp(rw), len(x), st, C.c_uint64(seed),
+                                           self._dp(px)))
+        return px
+
+    def htmaxp(self, px, tss, k, al0=2, ibin=False):
+        """cbs::htmaxp (CBS.hpp:34) for one vector (1-D) or a stack of vectors (2-D, one per row)."""
+        px = np.ascontiguousarray(px, dtype=np.float64)
+        single = px.ndim == 1
+        m = px.reshape(1, -1) if single else px
+        out = np.zeros(m.shape[0], dtype=np.float64)
+        self._check(self.lib.cbs_gpu_htmaxp(self.h, self._dp(m), m.shape[1], m.shape[0], C.c_double(tss), k, al0, int(ibin),
+                                            self._dp(out)))
+        return float(out[0]) if single else out
+
+    def tailp(self, b, delta, m, ngrid=100, tol=1e-6):
+        out = C.c_double()
+        self._check(self.lib.cbs_gpu_tailp(self.h, C.c_double(b), C.c_double(delta), m, ngrid, C.c_double(tol), C.byref(out)))
+        return out.value
+
+    def btmax(self, x):
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        out = C.c_double()
+        self._check(self.lib.cbs_gpu_btmax(self.h, self._dp(x), len(x), C.byref(out)))
+        return out.value
+
+    def btailp(self, b, m, ng, tol=1e-6):
+        out = C.c_double()
+        self._check(self.lib.cbs_gpu_btailp(self.h, C.c_double(b), m, ng, C.c_double(tol), C.byref(out)))
+        return out.value

@@ -320,7 +320,8 @@ struct Dev {
     double* cw;       // per pending segment, at the segment's offset: cumsum(w)/sqrt(sum w) (CBS.cpp:1062-1066)
     double* ycur;     // cur * rw: what wxperm shuffles (CBS.cpp:540)
     // ---- low-level entry points (cbs::fndcpt / cbs::tpermp on a vector as given) run ONE decision through the same worklist ----
-    int api_mode;     // 0: cbs::segment; 1: one fndcpt decision on unit 0 (x and tss as given, no children); 2: one tpermp test
+    int api_mode;     // 0: cbs::segment; 1: one fndcpt decision on unit 0 (x and tss as given, no children); 2: one tpermp test;
+                      // 3: observed scan only (wtmaxo); 4: tailp of a given b (hand-built task, no worklist)
     double api_tss, api_delta;  // fndcpt: tss argument; hybrid: delta argument (0: (kmax+1)/n)
     int api_n1, api_n2;         // tpermp: sizes of the two sides
     int shuf_cl2;     // segments of 65536..SHUF_CL2_MAX markers have their own class (cluster of 2 CTAs)
@@ -750,6 +751,7 @@ struct Sched {
             case TS_OBS: {
                 if (t.obs_round == D.round) return true;  // planned ahead in this very round: kernels have not run yet
                 if (t.alleq) { finish(idx, 0, 0, 0, 0); return false; }  // CBS.cpp:985
+                if (D.api_mode == 3) { finish(idx, 1, 0, 0, 0); return false; }  // cbs::wtmaxo entry: the observed scan is all that was asked for
                 const double t1 = sqrt(t.ostat);
                 if (t1 <= 0.1) { t.exit_code = EX_SMALL_T; finish(idx, 1, 0, 0, 0); return false; }  // :839
                 const int i1 = t.tmaxi, i2 = t.tmaxj;

@@ -19,6 +19,7 @@
 #include "host_math.h"
 #include "kernels.cuh"
 #include "weighted.cuh"
+#include "binary.cuh"
 #include "mt_jump.h"
 #include "prune.h"
 #include "smooth.cuh"
@@ -171,7 +172,7 @@ void collect_timers(cbs_gpu_ctx* c) {
 
 int validate_params(cbs_gpu_ctx* c, const cbs_gpu_params* p) {
     if (!p) return fail(c, CBS_GPU_ERR_INVALID, "params is NULL");
-    if (p->ibin) return fail(c, CBS_GPU_ERR_UNSUPPORTED, "ibin=true is not on the cna segment path and is not implemented");
+    if (p->ibin) return fail(c, CBS_GPU_ERR_UNSUPPORTED, "ibin=true is only implemented for cbs::tmaxo / cbs::tmaxp (cbs_gpu_tmaxo, cbs_gpu_tmaxp), not for the segmentation worklist: `cna segment` never sets it");
     if (p->hybrid && (p->kmax < 1 || p->kmax > 128)) return fail(c, CBS_GPU_ERR_UNSUPPORTED, "hybrid: kmax must be in 1..128");
     if (p->min_width < 1) return fail(c, CBS_GPU_ERR_INVALID, "min_width must be >= 1");
     if (p->nperm < 0) return fail(c, CBS_GPU_ERR_INVALID, "nperm must be >= 0");
@@ -308,6 +309,24 @@ int shuffle_occupancy(int cls) {
 }
 template <class F>
 bool set_max_smem(F* f, int bytes) { return cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes) == cudaSuccess; }
+
+// resident clusters x R of k_shuffle_cluster for segments of up to nmax markers (0: does not fit / not schedulable)
+int cluster_fit(cbs_gpu_ctx* c, int R, long long nmax, int hbits, size_t* smem_out) {
+    const size_t smem = ((size_t)4 << hbits) + 4 * ((size_t)nmax / R + 4);
+    if (smem > c->smem_optin) return 0;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(c->sm_count / R * R); cfg.blockDim = dim3(1024); cfg.dynamicSmemBytes = smem;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = R; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    int ncl = 0;
+    cudaError_t e = R == 2 ? cudaOccupancyMaxActiveClusters(&ncl, k_shuffle_cluster<1024, 4, 2, true>, &cfg)
+                  : R == 4 ? cudaOccupancyMaxActiveClusters(&ncl, k_shuffle_cluster<1024, 4, 4, true>, &cfg)
+                           : cudaOccupancyMaxActiveClusters(&ncl, k_shuffle_cluster<1024, 4, 8, true>, &cfg);
+    if (e != cudaSuccess || ncl < 1) { cudaGetLastError(); return 0; }
+    *smem_out = smem;
+    return ncl * R;
+}
 
 struct RunCaps {
     int task_cap, list_cap, seg_cap, split_cap, max_live;
@@ -555,27 +574,12 @@ int run_cbs(cbs_gpu_ctx* c, const std::vector<long long>& off, const uint64_t* u
     int cl_R = 0, cl_grid = 0, cl2_grid = 0;
     const int cl_hbits = 12;
     size_t cl_smem = 0, cl2_smem = 0;
-    auto cluster_fit = [&](int R, long long nmax, size_t* smem_out) -> int {
-        const size_t smem = ((size_t)4 << cl_hbits) + 4 * ((size_t)nmax / R + 4);
-        if (smem > c->smem_optin) return 0;
-        cudaLaunchConfig_t cfg = {};
-        cfg.gridDim = dim3(c->sm_count / R * R); cfg.blockDim = dim3(1024); cfg.dynamicSmemBytes = smem;
-        cudaLaunchAttribute at[1];
-        at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = R; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-        cfg.attrs = at; cfg.numAttrs = 1;
-        int ncl = 0;
-        cudaError_t e = R == 2 ? cudaOccupancyMaxActiveClusters(&ncl, k_shuffle_cluster<1024, 4, 2, true>, &cfg)
-                      : R == 4 ? cudaOccupancyMaxActiveClusters(&ncl, k_shuffle_cluster<1024, 4, 4, true>, &cfg)
-                               : cudaOccupancyMaxActiveClusters(&ncl, k_shuffle_cluster<1024, 4, 8, true>, &cfg);
-        if (e != cudaSuccess || ncl < 1) { cudaGetLastError(); return 0; }
-        *smem_out = smem;
-        return ncl * R;
-    };
+    auto cluster_fit_l = [&](int R, long long nmax, size_t* smem_out) -> int { return cluster_fit(c, R, nmax, cl_hbits, smem_out); };
     if (l2_shuffle_on && env_ll("CBS_GPU_SHUF_CLUSTER", 1)) {
         if (Nmax > SHUF_CL2_MAX) {
-            for (int R : {4, 8}) { cl_grid = cluster_fit(R, Nmax, &cl_smem); if (cl_grid) { cl_R = R; break; } }
+            for (int R : {4, 8}) { cl_grid = cluster_fit_l(R, Nmax, &cl_smem); if (cl_grid) { cl_R = R; break; } }
         } else cl_R = -1;  // nothing longer than the cluster-of-2 class
-        if (cl_R) cl2_grid = cluster_fit(2, std::min<long long>(Nmax, SHUF_CL2_MAX), &cl2_smem);
+        if (cl_R) cl2_grid = cluster_fit_l(2, std::min<long long>(Nmax, SHUF_CL2_MAX), &cl2_smem);
         if (cl_R < 0) { cl_R = cl2_grid ? 2 : 0; }
     }
     static const int kShufTimer[SHUF_CL2] = {K_SHUF0, K_SHUF1, K_SHUF2, K_SHUF2, K_SHUF3, K_SHUF3};
@@ -996,7 +1000,7 @@ int cbs_gpu_measure_fp64(cbs_gpu_ctx* c, double* tera_inst_per_s) {
 static int run_raw_scan(cbs_gpu_ctx* c, const double* xh, int n, int count, double tss, int al0, int ibin, int obs,
                         std::vector<Task>& tasks_out) {
     if (!c) return CBS_GPU_ERR_INVALID;
-    if (ibin) return fail(c, CBS_GPU_ERR_UNSUPPORTED, "ibin=true is not implemented");
+    if (ibin) return fail(c, CBS_GPU_ERR_CUDA, "internal: binary data takes run_bin_scan");
     if (n < 2 || count < 1 || !xh) return fail(c, CBS_GPU_ERR_INVALID, "bad arguments");
     if (al0 < 1 || n < 2 * al0) return fail(c, CBS_GPU_ERR_INVALID, "need n >= 2*al0, al0 >= 1");
     if (n > 1000000) return fail(c, CBS_GPU_ERR_UNSUPPORTED, "vectors longer than 1,000,000 are not supported");
@@ -1063,8 +1067,43 @@ static int run_raw_scan(cbs_gpu_ctx* c, const double* xh, int n, int count, doub
     return CBS_GPU_OK;
 }
 
+// binary data (ibin = true): cbs::tmaxo_impl walked in the reference's own order, one warp per vector (binary.cuh)
+static int run_bin_scan(cbs_gpu_ctx* c, const double* xh, int n, int count, double tss, int al0, std::vector<double>& stat,
+                        std::vector<int>& left, std::vector<int>& right) {
+    if (!c) return CBS_GPU_ERR_INVALID;
+    if (n < 2 || count < 1 || !xh) return fail(c, CBS_GPU_ERR_INVALID, "bad arguments");
+    if (al0 < 1 || n < 2 * al0) return fail(c, CBS_GPU_ERR_INVALID, "need n >= 2*al0, al0 >= 1");
+    if (n > 1000000) return fail(c, CBS_GPU_ERR_UNSUPPORTED, "vectors longer than 1,000,000 are not supported");
+    if (cudaSetDevice(c->device) != cudaSuccess) return fail(c, CBS_GPU_ERR_CUDA, "cudaSetDevice failed");
+    cudaStream_t st = c->stream;
+    const long long N = (long long)n * count, per = bin_scratch_doubles(n);
+    ENSURE(c, c->x, sizeof(double) * (size_t)(N + 1));
+    ENSURE(c, c->arena, sizeof(double) * (size_t)(per * count));
+    ENSURE(c, c->means, sizeof(double) * (size_t)count);
+    ENSURE(c, c->staging, sizeof(int) * 2 * (size_t)count);
+    CUDA_TRY(c, cudaMemcpyAsync(c->x.p, xh, sizeof(double) * (size_t)N, cudaMemcpyHostToDevice, st));
+    k_scan_bin<<<std::min(count, c->sm_count * 16), 32, 0, st>>>(c->x.as<double>(), n, count, tss, al0, 1, c->arena.as<double>(),
+                                                               c->means.as<double>(), c->staging.as<int>(), c->staging.as<int>() + count);
+    CUDA_TRY(c, cudaGetLastError());
+    stat.resize((size_t)count); left.resize((size_t)count); right.resize((size_t)count);
+    CUDA_TRY(c, cudaMemcpyAsync(stat.data(), c->means.p, sizeof(double) * (size_t)count, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(c, cudaMemcpyAsync(left.data(), c->staging.p, sizeof(int) * (size_t)count, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(c, cudaMemcpyAsync(right.data(), c->staging.as<int>() + count, sizeof(int) * (size_t)count, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(c, cudaStreamSynchronize(st));
+    return CBS_GPU_OK;
+}
+
 int cbs_gpu_tmaxo(cbs_gpu_ctx* c, const double* x, int32_t n, double tss, int32_t al0, int32_t ibin, double* statistic,
                   int32_t* start, int32_t* end) {
+    if (ibin) {
+        std::vector<double> st; std::vector<int> l, r;
+        const int rc = run_bin_scan(c, x, n, 1, tss, al0, st, l, r);
+        if (rc) return rc;
+        if (statistic) *statistic = st[0];
+        if (start) *start = l[0] - 1;  // CBS.cpp:380
+        if (end) *end = r[0] - 1;
+        return CBS_GPU_OK;
+    }
     std::vector<Task> t;
     const int rc = run_raw_scan(c, x, n, 1, tss, al0, ibin, 1, t);
     if (rc) return rc;
@@ -1076,6 +1115,13 @@ int cbs_gpu_tmaxo(cbs_gpu_ctx* c, const double* x, int32_t n, double tss, int32_
 
 int cbs_gpu_tmaxp(cbs_gpu_ctx* c, const double* px, int32_t n, int32_t count, double tss, int32_t al0, int32_t ibin,
                   double* statistics) {
+    if (ibin) {
+        std::vector<double> st; std::vector<int> l, r;
+        const int rc = run_bin_scan(c, px, n, count, tss, al0, st, l, r);
+        if (rc) return rc;
+        for (int k = 0; k < count; ++k) statistics[k] = st[k];
+        return CBS_GPU_OK;
+    }
     std::vector<Task> t;
     const int rc = run_raw_scan(c, px, n, count, tss, al0, ibin, 2, t);
     if (rc) return rc;
@@ -1424,6 +1470,226 @@ int cbs_gpu_tpermp(cbs_gpu_ctx* c, const double* x, int32_t n1, int32_t n2, cons
     const int rc = decision_impl(c, x, nullptr, n1 + n2, &p, api, mt_next312, &s, draws_consumed);
     if (rc) return rc;
     *pvalue = s.e_status0 == 1 ? 1.0 : s.e_status0 == 2 ? 0.0 : (double)s.e_nrej0 / (double)p.nperm;  // CBS.cpp:499,522,535
+    return CBS_GPU_OK;
+}
+
+int cbs_gpu_wtmaxo(cbs_gpu_ctx* c, const double* x, const double* weights, int32_t n, double tss, int32_t al0,
+                   double* statistic, int32_t* start, int32_t* end) {
+    if (!c) return CBS_GPU_ERR_INVALID;
+    if (!weights) return fail(c, CBS_GPU_ERR_INVALID, "weights is NULL");
+    if (al0 < 1 || n < 2 * al0) return fail(c, CBS_GPU_ERR_INVALID, "need n >= 2*al0, al0 >= 1");
+    cbs_gpu_params p;
+    cbs_gpu_default_params(&p);
+    p.min_width = al0; p.nperm = 0; p.hybrid = 0;
+    ApiMode api;
+    api.mode = 3; api.tss = tss;
+    cbs_gpu_split s;
+    const int rc = decision_impl(c, x, weights, n, &p, api, nullptr, &s, nullptr);
+    if (rc) return rc;
+    if (statistic) *statistic = s.ostat;
+    if (start) *start = s.iseg0;
+    if (end) *end = s.iseg1;
+    return CBS_GPU_OK;
+}
+
+// cbs::xperm / cbs::wxperm: ONE permutation with the engine state given as its next 312 raw words.  The raw words the
+// permutation consumes are produced on the host with the engine's recurrence (n words, trivial next to the transfer) and the
+// shuffle runs in the same kernels the worklist uses (shuffle.cuh), from a hand-built single-item plan.
+int cbs_gpu_xperm(cbs_gpu_ctx* c, const double* x, const double* rwts, int32_t n, const uint64_t* mt_next312, uint64_t seed,
+                  double* px) {
+    if (!c) return CBS_GPU_ERR_INVALID;
+    if (n < 1 || !x || !px) return fail(c, CBS_GPU_ERR_INVALID, "bad arguments");
+    if (n > 1000000) return fail(c, CBS_GPU_ERR_UNSUPPORTED, "vectors longer than 1,000,000 are not supported");
+    if (cudaSetDevice(c->device) != cudaSuccess) return fail(c, CBS_GPU_ERR_CUDA, "cudaSetDevice failed");
+    cudaStream_t st = c->stream;
+    std::vector<uint64_t> words((size_t)n + 312);
+    if (mt_next312) memcpy(words.data(), mt_next312, sizeof(uint64_t) * 312); else mt_seed_next312(seed, words.data());
+    for (long long k = 312; k < (long long)n + 312; ++k) words[(size_t)k] = mt_twist(words[(size_t)k - 312], words[(size_t)k - 311], words[(size_t)k - 156]);
+    std::vector<double> y(x, x + n);
+    if (rwts) for (int i = 0; i < n; ++i) y[(size_t)i] = x[i] * rwts[i];  // CBS.cpp:540
+    const long long stride = Sched::sx_stride(n);
+    ENSURE(c, c->x, sizeof(double) * (size_t)(n + 1));
+    ENSURE(c, c->cur, sizeof(double) * (size_t)(n + 1));
+    ENSURE(c, c->ycur, sizeof(double) * (size_t)(n + 1));
+    ENSURE(c, c->rw, sizeof(double) * (size_t)(n + 1));
+    ENSURE(c, c->wts, sizeof(double) * (size_t)(n + 1));
+    ENSURE(c, c->unit_off, sizeof(long long) * 2);
+    ENSURE(c, c->tasks, sizeof(Task));
+    ENSURE(c, c->arena, sizeof(double) * (size_t)(stride + Sched::idx_stride(n) + 16));
+    ENSURE(c, c->draws0, sizeof(uint64_t) * (size_t)(n + 312));
+    ENSURE(c, c->items, sizeof(PermItem));
+    ENSURE(c, c->shuf, sizeof(int) * 8);
+    ENSURE(c, c->dev, sizeof(Dev));
+    // which kernel takes a segment of n markers (cbs_core.h shuffle classes)
+    int cls = shuffle_class(n, false), cl_R = 0, cl_grid = 0;
+    size_t cl_smem = 0;
+    if (cls == SHUF_GLOBAL)
+        for (int R : {2, 4, 8}) { cl_grid = cluster_fit(c, R, n, 12, &cl_smem); if (cl_grid) { cl_R = R; break; } }
+    Task t;
+    memset(&t, 0, sizeof(t));
+    t.unit = 0; t.lo = 0; t.hi = n; t.n = n; t.nb = block_count(n); t.raw = 1; t.off_sx = 0; t.off_A = stride; t.off_draw = 0;
+    const PermItem item = {0, 1, 0};
+    const int plan[8] = {0 /*shuf_item*/, 0, 1 /*shuf_prefix*/, 0 /*shuf_p0*/, 0, 0, 0, 0};
+    const long long off[2] = {0, n};
+    Dev hD;
+    memset(&hD, 0, sizeof(hD));
+    hD.x = c->x.as<double>(); hD.cur = c->cur.as<double>(); hD.unit_off = c->unit_off.as<long long>(); hD.n_units = 1;
+    hD.prm.rng_mode = RNG_MT;
+    hD.tasks = c->tasks.as<Task>(); hD.task_cap = 1;
+    hD.arena = c->arena.as<double>(); hD.arena_cap = (long long)(c->arena.cap / 8);
+    hD.draws[0] = c->draws0.as<uint64_t>(); hD.draws[1] = c->draws0.as<uint64_t>();
+    hD.items = c->items.as<PermItem>(); hD.n_items = 1;
+    for (int k = 0; k < SHUF_NCLS; ++k) { hD.shuf_item[k] = c->shuf.as<int>(); hD.shuf_prefix[k] = c->shuf.as<int>() + 1; hD.shuf_p0[k] = c->shuf.as<int>() + 3; }
+    hD.n_shuf[cls] = 1;
+    hD.shuf_arena = (cls == SHUF_GLOBAL && !cl_R) ? 1 : 0;
+    if (rwts) { hD.w = c->wts.as<double>(); hD.rw = c->rw.as<double>(); hD.ycur = c->ycur.as<double>(); }
+    CUDA_TRY(c, cudaMemcpyAsync(c->cur.p, x, sizeof(double) * (size_t)n, cudaMemcpyHostToDevice, st));
+    if (rwts) {
+        CUDA_TRY(c, cudaMemcpyAsync(c->ycur.p, y.data(), sizeof(double) * (size_t)n, cudaMemcpyHostToDevice, st));
+        CUDA_TRY(c, cudaMemcpyAsync(c->rw.p, rwts, sizeof(double) * (size_t)n, cudaMemcpyHostToDevice, st));
+    }
+    CUDA_TRY(c, cudaMemcpyAsync(c->draws0.p, words.data(), sizeof(uint64_t) * (size_t)n, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(c, cudaMemcpyAsync(c->unit_off.p, off, sizeof(off), cudaMemcpyHostToDevice, st));
+    CUDA_TRY(c, cudaMemcpyAsync(c->tasks.p, &t, sizeof(t), cudaMemcpyHostToDevice, st));
+    CUDA_TRY(c, cudaMemcpyAsync(c->items.p, &item, sizeof(item), cudaMemcpyHostToDevice, st));
+    CUDA_TRY(c, cudaMemcpyAsync(c->shuf.p, plan, sizeof(plan), cudaMemcpyHostToDevice, st));
+    CUDA_TRY(c, cudaMemcpyAsync(c->dev.p, &hD, sizeof(Dev), cudaMemcpyHostToDevice, st));
+    Dev* dD = c->dev.as<Dev>();
+    if (cls < SHUF_CL2) launch_shuffle(dD, cls, 1, st, true);
+    else if (cl_R) launch_shuffle_cluster(dD, cl_R, SHUF_GLOBAL, 12, cl_R, cl_smem, st, true);
+    else k_perm<<<1, 128, 0, st>>>(dD);
+    CUDA_TRY(c, cudaGetLastError());
+    CUDA_TRY(c, cudaMemcpyAsync(px, c->arena.as<double>() + 1, sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(c, cudaStreamSynchronize(st));
+    return CBS_GPU_OK;
+}
+
+// cbs::htmaxp (CBS.hpp:34, CBS.cpp:387-485) for `count` vectors of n values laid end to end
+int cbs_gpu_htmaxp(cbs_gpu_ctx* c, const double* px, int32_t n, int32_t count, double tss, int32_t k, int32_t al0, int32_t ibin,
+                   double* statistics) {
+    if (!c) return CBS_GPU_ERR_INVALID;
+    if (ibin) return fail(c, CBS_GPU_ERR_UNSUPPORTED, "htmaxp with ibin=true is not implemented");
+    if (n < 2 || count < 1 || !px || !statistics) return fail(c, CBS_GPU_ERR_INVALID, "bad arguments");
+    if (al0 < 1 || k < al0 || k > 128 || n <= 2 * k) return fail(c, CBS_GPU_ERR_UNSUPPORTED, "need al0 <= k <= 128 and n > 2k");
+    if (n > 1000000) return fail(c, CBS_GPU_ERR_UNSUPPORTED, "vectors longer than 1,000,000 are not supported");
+    if (cudaSetDevice(c->device) != cudaSuccess) return fail(c, CBS_GPU_ERR_CUDA, "cudaSetDevice failed");
+    cudaStream_t st = c->stream;
+    const long long N = (long long)n * count;
+    const int nb = block_count(n);
+    const long long per = Sched::sx_stride(n) + Sched::bs_stride(nb);
+    ENSURE(c, c->x, sizeof(double) * (size_t)(N + 1));
+    ENSURE(c, c->cur, sizeof(double) * (size_t)(N + 1));
+    ENSURE(c, c->gtab, sizeof(double) * (size_t)(N + 1));
+    ENSURE(c, c->factab, sizeof(double) * (size_t)(N + 1));
+    ENSURE(c, c->bbtab, sizeof(int) * (size_t)(N + 1));
+    ENSURE(c, c->unit_off, sizeof(long long) * (size_t)(count + 1));
+    ENSURE(c, c->tasks, sizeof(Task) * (size_t)count);
+    ENSURE(c, c->arena, sizeof(double) * (size_t)(per * count));
+    ENSURE(c, c->rej, sizeof(int) * (size_t)count);
+    ENSURE(c, c->prep_task, sizeof(int) * (size_t)count);
+    ENSURE(c, c->items, sizeof(PermItem) * (size_t)count);
+    ENSURE(c, c->item_prefix, sizeof(int) * (size_t)(count + 1));
+    ENSURE(c, c->dev, sizeof(Dev));
+    std::vector<long long> off((size_t)count + 1);
+    std::vector<Task> tasks((size_t)count);
+    std::vector<int> prep((size_t)count), prefix((size_t)count + 1);
+    std::vector<PermItem> items((size_t)count);
+    memset(tasks.data(), 0, sizeof(Task) * tasks.size());
+    for (int u = 0; u <= count; ++u) off[(size_t)u] = (long long)u * n;
+    for (int u = 0; u < count; ++u) {
+        Task& t = tasks[(size_t)u];
+        t.unit = u; t.lo = 0; t.hi = n; t.n = n; t.nb = nb; t.raw = 1; t.tss = tss; t.state = TS_PERM; t.use_hybrid = 1;
+        t.off_sx = per * u; t.off_bs = per * u + Sched::sx_stride(n); t.off_rej = u; t.next = -1;
+        prep[(size_t)u] = u; prefix[(size_t)u] = u;
+        items[(size_t)u].task = u; items[(size_t)u].P = 1; items[(size_t)u].obs = 0;  // a "permutation" row: k_hscan takes it
+    }
+    prefix[(size_t)count] = count;
+    Dev hD;
+    memset(&hD, 0, sizeof(hD));
+    hD.x = c->x.as<double>(); hD.unit_off = c->unit_off.as<long long>(); hD.n_units = count;
+    hD.prm.min_width = al0; hD.prm.kmax = k; hD.prm.hybrid = 1; hD.prm.nperm = 0; hD.prm.rng_mode = RNG_PHILOX;
+    hD.cur = c->cur.as<double>(); hD.gtab = c->gtab.as<double>(); hD.factab = c->factab.as<double>(); hD.bbtab = c->bbtab.as<int>();
+    hD.tasks = c->tasks.as<Task>(); hD.task_cap = count;
+    hD.arena = c->arena.as<double>(); hD.arena_cap = per * count; hD.rej = c->rej.as<int>(); hD.rej_cap = count;
+    hD.n_prep = count; hD.prep_task = c->prep_task.as<int>();
+    hD.n_items = count; hD.items = c->items.as<PermItem>(); hD.item_prefix = c->item_prefix.as<int>();
+    CUDA_TRY(c, cudaMemcpyAsync(c->x.p, px, sizeof(double) * (size_t)N, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(c, cudaMemcpyAsync(c->unit_off.p, off.data(), sizeof(long long) * off.size(), cudaMemcpyHostToDevice, st));
+    CUDA_TRY(c, cudaMemcpyAsync(c->tasks.p, tasks.data(), sizeof(Task) * tasks.size(), cudaMemcpyHostToDevice, st));
+    CUDA_TRY(c, cudaMemcpyAsync(c->prep_task.p, prep.data(), sizeof(int) * prep.size(), cudaMemcpyHostToDevice, st));
+    CUDA_TRY(c, cudaMemcpyAsync(c->items.p, items.data(), sizeof(PermItem) * items.size(), cudaMemcpyHostToDevice, st));
+    CUDA_TRY(c, cudaMemcpyAsync(c->item_prefix.p, prefix.data(), sizeof(int) * prefix.size(), cudaMemcpyHostToDevice, st));
+    CUDA_TRY(c, cudaMemcpyAsync(c->dev.p, &hD, sizeof(Dev), cudaMemcpyHostToDevice, st));
+    Dev* dD = c->dev.as<Dev>();
+    k_tables<<<dim3(16, 64), 256, 0, st>>>(dD);
+    k_prep<<<std::min(count, c->sm_count * 8), 32, 0, st>>>(dD);  // prefix sums of the vectors as given (CBS.cpp:396-398)
+    k_hscan<<<std::min(count, c->sm_count * 4), 256, 0, st>>>(dD);
+    CUDA_TRY(c, cudaGetLastError());
+    CUDA_TRY(c, cudaMemcpyAsync(tasks.data(), c->tasks.p, sizeof(Task) * tasks.size(), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(c, cudaStreamSynchronize(st));
+    for (int u = 0; u < count; ++u) statistics[u] = tasks[(size_t)u].pval1;
+    return CBS_GPU_OK;
+}
+
+// cbs::tailp (CBS.hpp:29, CBS.cpp:324-339); ngrid must be 100 (the device kernels' quadrature size)
+int cbs_gpu_tailp(cbs_gpu_ctx* c, double b, double delta, int32_t m, int32_t ngrid, double tol, double* out) {
+    if (!c) return CBS_GPU_ERR_INVALID;
+    if (!out || m < 1) return fail(c, CBS_GPU_ERR_INVALID, "bad arguments");
+    if (ngrid != TAILP_NGRID) return fail(c, CBS_GPU_ERR_UNSUPPORTED, "ngrid must be 100");
+    if (cudaSetDevice(c->device) != cudaSuccess) return fail(c, CBS_GPU_ERR_CUDA, "cudaSetDevice failed");
+    cudaStream_t st = c->stream;
+    ENSURE(c, c->tasks, sizeof(Task));
+    ENSURE(c, c->prep_task, sizeof(int));
+    ENSURE(c, c->tailp, sizeof(double) * TAILP_NGRID);
+    ENSURE(c, c->dev, sizeof(Dev));
+    Task t;
+    memset(&t, 0, sizeof(t));
+    t.n = m; t.hi = m; t.use_hybrid = 1; t.ostat = b * b;
+    Dev hD;
+    memset(&hD, 0, sizeof(hD));
+    hD.prm.hybrid = 1; hD.prm.tol = tol; hD.api_mode = 4; hD.api_delta = delta;
+    hD.tasks = c->tasks.as<Task>(); hD.n_prep = 1; hD.prep_task = c->prep_task.as<int>();
+    const int zero = 0;
+    CUDA_TRY(c, cudaMemcpyAsync(c->tasks.p, &t, sizeof(t), cudaMemcpyHostToDevice, st));
+    CUDA_TRY(c, cudaMemcpyAsync(c->prep_task.p, &zero, sizeof(int), cudaMemcpyHostToDevice, st));
+    CUDA_TRY(c, cudaMemcpyAsync(c->dev.p, &hD, sizeof(Dev), cudaMemcpyHostToDevice, st));
+    k_tailp_terms<<<32, 128, 0, st>>>(c->dev.as<Dev>(), c->tailp.as<double>());
+    k_tailp_sum<<<1, 64, 0, st>>>(c->dev.as<Dev>(), c->tailp.as<double>());
+    CUDA_TRY(c, cudaGetLastError());
+    CUDA_TRY(c, cudaMemcpyAsync(&t, c->tasks.p, sizeof(t), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(c, cudaStreamSynchronize(st));
+    *out = t.pval1;
+    return CBS_GPU_OK;
+}
+
+// cbs::btmax (CBS.hpp:31) / cbs::btailp (CBS.hpp:30): binary-data helpers (binary.cuh, kernels.cuh)
+int cbs_gpu_btmax(cbs_gpu_ctx* c, const double* x, int32_t n, double* out) {
+    if (!c) return CBS_GPU_ERR_INVALID;
+    if (!x || !out || n < 1) return fail(c, CBS_GPU_ERR_INVALID, "bad arguments");
+    if (cudaSetDevice(c->device) != cudaSuccess) return fail(c, CBS_GPU_ERR_CUDA, "cudaSetDevice failed");
+    cudaStream_t st = c->stream;
+    ENSURE(c, c->x, sizeof(double) * (size_t)(n + 1));
+    ENSURE(c, c->means, sizeof(double) * 2);
+    CUDA_TRY(c, cudaMemcpyAsync(c->x.p, x, sizeof(double) * (size_t)n, cudaMemcpyHostToDevice, st));
+    k_btmax<<<1, 32, 0, st>>>(c->x.as<double>(), n, c->means.as<double>());
+    CUDA_TRY(c, cudaGetLastError());
+    CUDA_TRY(c, cudaMemcpyAsync(out, c->means.p, sizeof(double), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(c, cudaStreamSynchronize(st));
+    return CBS_GPU_OK;
+}
+
+int cbs_gpu_btailp(cbs_gpu_ctx* c, double b, int32_t m, int32_t ng, double tol, double* out) {
+    if (!c) return CBS_GPU_ERR_INVALID;
+    if (!out || m < 5 || ng < 1 || ng > 100000) return fail(c, CBS_GPU_ERR_INVALID, "bad arguments");
+    if (cudaSetDevice(c->device) != cudaSuccess) return fail(c, CBS_GPU_ERR_CUDA, "cudaSetDevice failed");
+    cudaStream_t st = c->stream;
+    ENSURE(c, c->tailp, sizeof(double) * (size_t)(ng + 2));
+    ENSURE(c, c->means, sizeof(double) * 2);
+    k_btailp_terms<<<std::min(c->sm_count, (ng + 4) / 4), 128, 0, st>>>(b, m, ng, tol, c->tailp.as<double>());
+    k_btailp_sum<<<1, 32, 0, st>>>(b, m, ng, c->tailp.as<double>(), c->means.as<double>());
+    CUDA_TRY(c, cudaGetLastError());
+    CUDA_TRY(c, cudaMemcpyAsync(out, c->means.p, sizeof(double), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(c, cudaStreamSynchronize(st));
     return CBS_GPU_OK;
 }
 

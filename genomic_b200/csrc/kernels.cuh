@@ -1879,7 +1879,7 @@ __global__ void __launch_bounds__(128) k_tailp_terms(Dev* D, double* terms) {
         const Task& t = D->tasks[D->prep_task[k]];
         if (!t.use_hybrid || t.alleq) continue;
         const double b = sqrt(t.ostat);
-        if (!(b > 0.1)) continue;
+        if (!(b > 0.1) && D->api_mode != 4) continue;  // (cbs::tailp itself has no such shortcut: api_mode 4)
         const double delta = D->w ? t.w_delta : (D->api_mode && D->api_delta > 0.0) ? D->api_delta
                                                 : (double)(D->prm.kmax + 1) / (double)t.n;  // CBS.cpp:984; weighted: getmncwt (:908)
         const double dincr = (0.5 - delta) / (double)TAILP_NGRID;
@@ -1898,12 +1898,41 @@ __global__ void __launch_bounds__(64) k_tailp_sum(Dev* D, const double* terms) {
         Task& t = D->tasks[D->prep_task[k]];
         if (!t.use_hybrid || t.alleq) continue;
         const double b = sqrt(t.ostat);
-        if (!(b > 0.1)) { t.pval1 = 1.0; continue; }
+        if (!(b > 0.1) && D->api_mode != 4) { t.pval1 = 1.0; continue; }
         double out = 0.0;
         for (int q = 0; q < TAILP_NGRID; ++q) out += terms[(long long)k * TAILP_NGRID + q];
         out = 9.973557e-2 * pow(b, 3.0) * exp(-b * b / 2.0) * out;
         t.pval1 = 2.0 * out;
     }
+}
+
+// cbs::btailp (CBS.cpp:341-361): nu(x1)/x at the ng+1 quadrature points, a warp per point (x advances by repeated addition
+// as in the reference), then the trapezoid sum in order.  Off the `cna segment` path (binary data).
+__global__ void __launch_bounds__(128) k_btailp_terms(double b, int m, int ng, double tol, double* vals) {
+    const int lane = threadIdx.x & 31;
+    const double dm = (double)m;
+    const double ll = b * sqrt(1.0 / (double)(m - 2) - 1.0 / dm);
+    const double ul = b * sqrt(1.0 / 2.0 - 1.0 / dm);
+    const double dincr = (ul - ll) / (double)ng;
+    for (int i = blockIdx.x * 4 + (threadIdx.x >> 5); i <= ng; i += gridDim.x * 4) {
+        double x = ll;
+        for (int q = 0; q < i; ++q) x += dincr;
+        const double x1 = x + (b * b) / (dm * x);
+        const double v = warp_nu(x1, tol, lane) / x;
+        if (lane == 0) vals[i] = v;
+    }
+}
+__global__ void k_btailp_sum(double b, int m, int ng, const double* vals, double* out) {
+    if (threadIdx.x || blockIdx.x) return;
+    const double dm = (double)m;
+    const double ll = b * sqrt(1.0 / (double)(m - 2) - 1.0 / dm);
+    const double ul = b * sqrt(1.0 / 2.0 - 1.0 / dm);
+    const double dincr = (ul - ll) / (double)ng;
+    double acc = 0.0, nulo = vals[0];
+    for (int i = 1; i <= ng; ++i) { const double nuhi = vals[i]; acc += (nuhi + nulo) * dincr; nulo = nuhi; }
+    acc = b * exp(-b * b / 2.0) * acc * 0.39894228040143267794;  // 1/sqrt(2 pi)
+    acc += 2.0 * (1.0 - dev_fpnorm(b));
+    *out = acc;
 }
 
 __global__ void __launch_bounds__(256) k_hscan(Dev* D) {
@@ -1981,6 +2010,7 @@ __global__ void __launch_bounds__(256) k_hscan(Dev* D) {
             if (tss <= m + 0.0001) tss = m + 1.0;  // CBS.cpp:483-484
             const double stat = m / ((tss - m) / (rn - 2.0));
             D->rej[t.off_rej + p] = (t.ostat * 0.99999 <= stat) ? 1 : 0;
+            if (t.raw) t.pval1 = stat;  // cbs::htmaxp through the low-level entry point: the statistic itself
         }
     }
 }

@@ -173,6 +173,26 @@ int cbs_gpu_wfindcpt(cbs_gpu_ctx* ctx, const double* x, const double* weights, i
 int cbs_gpu_tpermp(cbs_gpu_ctx* ctx, const double* x, int32_t n1, int32_t n2, const cbs_gpu_params* params,
                    const uint64_t* mt_next312, double* pvalue, uint64_t* draws_consumed);
 
+/* cbs::wtmaxo (CBS.hpp:54-58, CBS.cpp:610-739): weighted max-t statistic and 0-based arc of x as given, tss supplied by
+ * the caller; cwts is derived from `weights` as in cbs::segment_weighted (CBS.cpp:1062-1066). */
+int cbs_gpu_wtmaxo(cbs_gpu_ctx* ctx, const double* x, const double* weights, int32_t n, double tss, int32_t al0,
+                   double* statistic, int32_t* start, int32_t* end);
+/* cbs::xperm (CBS.hpp:37, CBS.cpp:487-493) and, with rwts != NULL, cbs::wxperm (CBS.hpp:39-42, CBS.cpp:538-547): ONE
+ * permutation px of x drawn from the engine whose next 312 raw words are mt_next312 (NULL: std::mt19937_64(seed)); the
+ * engine advances by exactly n draws. */
+int cbs_gpu_xperm(cbs_gpu_ctx* ctx, const double* x, const double* rwts, int32_t n, const uint64_t* mt_next312, uint64_t seed,
+                  double* px);
+/* cbs::htmaxp (CBS.hpp:34, CBS.cpp:387-485) for `count` vectors of length n laid end to end; ibin must be 0 */
+int cbs_gpu_htmaxp(cbs_gpu_ctx* ctx, const double* px, int32_t n, int32_t count, double tss, int32_t k, int32_t al0,
+                   int32_t ibin, double* statistics);
+/* cbs::tailp (CBS.hpp:29, CBS.cpp:324-339); ngrid must be 100.  Evaluated with the CUDA erfc/log/exp/pow (<= 4 ulp each), so
+ * the value agrees with the reference's libm result to ~1e-14 relative, not bit for bit. */
+int cbs_gpu_tailp(cbs_gpu_ctx* ctx, double b, double delta, int32_t m, int32_t ngrid, double tol, double* out);
+/* binary-data helpers, off the `cna segment` path: cbs::btmax (CBS.hpp:31, CBS.cpp:363-376), cbs::btailp (CBS.hpp:30,
+ * CBS.cpp:341-361); cbs_gpu_tmaxo / cbs_gpu_tmaxp accept ibin = 1 (CBS.cpp:68-227, ibin branches) */
+int cbs_gpu_btmax(cbs_gpu_ctx* ctx, const double* x, int32_t n, double* out);
+int cbs_gpu_btailp(cbs_gpu_ctx* ctx, double b, int32_t m, int32_t ng, double tol, double* out);
+
 /* host-only self test (needs no device): 0 if the MT19937-64 jump-ahead polynomials reproduce
  * sequential generation */
 int cbs_gpu_selftest(void);

@@ -406,6 +406,14 @@ class Ref:
                                         C.c_int, C.c_double, C.c_double, C.c_int, C.c_double, C.c_uint64, C.c_int,
                                         C.c_int, C.c_int64, c_int_p, c_int_p, c_double_p]
 
+        L.ref_btmax.restype = C.c_double
+        L.ref_btmax.argtypes = [c_double_p, C.c_int]
+        L.ref_btailp.restype = C.c_double
+        L.ref_btailp.argtypes = [C.c_double, C.c_int, C.c_int, C.c_double]
+        L.ref_wtmaxo.argtypes = [c_double_p, c_double_p, C.c_int, C.c_double, C.c_int, c_double_p, c_int_p, c_int_p]
+        L.ref_wxperm.argtypes = [c_double_p, c_double_p, C.c_int, c_double_p, C.c_void_p]
+        L.ref_wfindcpt.argtypes = [c_double_p, c_double_p, C.c_int, C.c_double, C.c_int, C.c_double, C.c_int, C.c_int, C.c_int,
+                                   C.c_int, C.c_double, C.c_void_p, c_int_p, c_int_p, c_int_p, c_double_p]
         L.ref_perm_reject_flags.argtypes = [c_double_p, C.c_int, C.c_double, C.c_double, C.c_int, C.c_uint64, C.c_uint64,
                                             C.c_int64, C.c_int64, C.c_int, C.c_void_p]
 
@@ -416,6 +424,35 @@ class Ref:
         self.lib.ref_perm_reject_flags(_dp(x), len(x), float(tss), float(thresh), al0, int(seed), int(start_draw), int(perm0),
                                        int(nperms), int(nthreads), flags.ctypes.data_as(C.c_void_p))
         return flags
+
+    def btmax(self, x):
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        return self.lib.ref_btmax(_dp(x), len(x))
+
+    def btailp(self, b, m, ng, tol=1e-6):
+        return self.lib.ref_btailp(b, m, ng, tol)
+
+    def wtmaxo(self, x, w, tss, al0=2):
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        w = np.ascontiguousarray(w, dtype=np.float64)
+        stat, s, e = C.c_double(), C.c_int(), C.c_int()
+        self.lib.ref_wtmaxo(_dp(x), _dp(w), len(x), tss, al0, C.byref(stat), C.byref(s), C.byref(e))
+        return stat.value, s.value, e.value
+
+    def wxperm(self, x, rwts, rng):
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        rw = np.ascontiguousarray(rwts, dtype=np.float64)
+        px = np.zeros_like(x)
+        self.lib.ref_wxperm(_dp(x), _dp(rw), len(x), _dp(px), rng.h)
+        return px
+
+    def wfindcpt(self, x, w, tss, nperm, cpval, rng, hybrid=False, al0=2, hk=25, ngrid=100, tol=1e-6):
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        w = np.ascontiguousarray(w, dtype=np.float64)
+        ncpt, icpt, iseg, ostat = C.c_int(), (C.c_int * 2)(), (C.c_int * 2)(), C.c_double()
+        self.lib.ref_wfindcpt(_dp(x), _dp(w), len(x), tss, nperm, cpval, int(hybrid), al0, hk, ngrid, tol, rng.h, C.byref(ncpt), icpt,
+                              iseg, C.byref(ostat))
+        return dict(ncpt=ncpt.value, icpt=(icpt[0], icpt[1]), iseg=(iseg[0], iseg[1]), ostat=ostat.value)
 
     class Rng:
         def __init__(self, lib, seed):

@@ -120,6 +120,39 @@ void ref_perm_reject_flags(const double* x, int n, double tss, double thresh, in
     for (auto& th : pool) th.join();
 }
 
+// ---- rest of the low-level surface (CBS.hpp:29-98), for the tests of the matching cbs_gpu_* entry points ---------------
+double ref_btmax(const double* x, int n) { return cbs::btmax(std::vector<double>(x, x + n)); }
+double ref_btailp(double b, int m, int ng, double tol) { return cbs::btailp(b, m, ng, tol); }
+
+// rwts / cwts exactly as cbs::segment_weighted derives them (CBS.cpp:1053-1066)
+static void derive_weights(const double* w, int n, std::vector<double>& wts, std::vector<double>& rw, std::vector<double>& cw) {
+    wts.assign(w, w + n); rw.resize(n); cw.resize(n);
+    double wsum = 0.0, csum = 0.0;
+    for (int i = 0; i < n; ++i) { rw[i] = std::sqrt(w[i]); wsum += w[i]; }
+    const double cwscale = std::sqrt(wsum);
+    for (int i = 0; i < n; ++i) { csum += w[i]; cw[i] = csum / cwscale; }
+}
+void ref_wtmaxo(const double* x, const double* w, int n, double tss, int al0, double* stat, int* start, int* end) {
+    std::vector<double> wts, rw, cw;
+    derive_weights(w, n, wts, rw, cw);
+    const auto r = cbs::wtmaxo(std::vector<double>(x, x + n), wts, tss, cw, al0);
+    *stat = r.statistic; *start = r.start; *end = r.end;
+}
+void ref_wxperm(const double* x, const double* rwts, int n, double* px, void* rng) {
+    std::vector<double> p;
+    cbs::wxperm(std::vector<double>(x, x + n), p, std::vector<double>(rwts, rwts + n), static_cast<RefRng*>(rng)->eng);
+    std::memcpy(px, p.data(), sizeof(double) * static_cast<size_t>(n));
+}
+void ref_wfindcpt(const double* x, const double* w, int n, double tss, int nperm, double cpval, int hybrid, int al0, int hk,
+                  int ngrid, double tol, void* rng, int* ncpt, int* icpt, int* iseg, double* ostat) {
+    std::vector<double> wts, rw, cw;
+    derive_weights(w, n, wts, rw, cw);
+    const std::vector<int> sbdry = make_sbdry(nperm, cpval);
+    const auto r = cbs::wfindcpt(std::vector<double>(x, x + n), tss, wts, rw, cw, nperm, cpval, hybrid != 0, al0, hk, 0.0, ngrid, sbdry,
+                                 tol, static_cast<RefRng*>(rng)->eng);
+    *ncpt = r.ncpt; icpt[0] = r.icpt[0]; icpt[1] = r.icpt[1]; iseg[0] = r.iseg[0]; iseg[1] = r.iseg[1]; *ostat = r.ostat;
+}
+
 // out: ncpt, icpt[2], iseg[2], ostat
 void ref_fndcpt(const double* x, int n, double tss, int nperm, double cpval, int ibin, int hybrid, int al0, int hk,
                 double delta, int ngrid, double tol, void* rng, int* ncpt, int* icpt, int* iseg, double* ostat) {
