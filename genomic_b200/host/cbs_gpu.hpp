@@ -33,6 +33,13 @@ struct SegmentationResult {  // CBS.hpp:24-27
     std::vector<double> means;
 };
 
+struct ChangePointResult {  // CBS.hpp:11-16
+    int ncpt = 0;
+    std::array<int, 2> icpt{{0, 0}};
+    std::array<int, 2> iseg{{0, 0}};
+    double ostat = 0.0;
+};
+
 class Context {
 public:
     explicit Context(int device = 0) {
@@ -125,6 +132,124 @@ inline double tmaxp(const std::vector<double>& px, double tss, int al0, bool ibi
     double stat = 0.0;
     c.check(cbs_gpu_tmaxp(c.get(), px.data(), (int)px.size(), 1, tss, al0, ibin, &stat));
     return stat;
+}
+
+// cbs::htmaxp, CBS.hpp:34
+inline double htmaxp(const std::vector<double>& px, double tss, int k, int al0, bool ibin) {
+    Context& c = default_context();
+    double stat = 0.0;
+    c.check(cbs_gpu_htmaxp(c.get(), px.data(), (int)px.size(), 1, tss, k, al0, ibin, &stat));
+    return stat;
+}
+
+// cbs::tailp / cbs::btailp / cbs::btmax, CBS.hpp:29-31
+inline double tailp(double b, double delta, int m, int ngrid, double tol) {
+    Context& c = default_context();
+    double out = 0.0;
+    c.check(cbs_gpu_tailp(c.get(), b, delta, m, ngrid, tol, &out));
+    return out;
+}
+inline double btailp(double b, int m, int ng, double tol) {
+    Context& c = default_context();
+    double out = 0.0;
+    c.check(cbs_gpu_btailp(c.get(), b, m, ng, tol, &out));
+    return out;
+}
+inline double btmax(const std::vector<double>& x) {
+    Context& c = default_context();
+    double out = 0.0;
+    c.check(cbs_gpu_btmax(c.get(), x.data(), (int)x.size(), &out));
+    return out;
+}
+
+// cbs::xperm / cbs::wxperm, CBS.hpp:37-42: rng advances by exactly x.size() draws
+inline void xperm(const std::vector<double>& x, std::vector<double>& px, std::mt19937_64& rng) {
+    Context& c = default_context();
+    const auto state = detail::next312(rng);
+    px.resize(x.size());
+    if (x.empty()) return;
+    c.check(cbs_gpu_xperm(c.get(), x.data(), nullptr, (int)x.size(), state.data(), 0, px.data()));
+    rng.discard(x.size());
+}
+inline void wxperm(const std::vector<double>& x, std::vector<double>& px, const std::vector<double>& rwts, std::mt19937_64& rng) {
+    if (x.size() != rwts.size()) throw std::invalid_argument("x and rwts must have same length");
+    Context& c = default_context();
+    const auto state = detail::next312(rng);
+    px.resize(x.size());
+    if (x.empty()) return;
+    c.check(cbs_gpu_xperm(c.get(), x.data(), rwts.data(), (int)x.size(), state.data(), 0, px.data()));
+    rng.discard(x.size());
+}
+
+// cbs::tpermp, CBS.hpp:35-36.  px is scratch in the reference; it is left untouched here.
+inline double tpermp(int n1, int n2, int n, const double* x, std::vector<double>& px, int nperm, std::mt19937_64& rng) {
+    (void)px;
+    if (n != n1 + n2) throw std::invalid_argument("tpermp: n must be n1 + n2");
+    Context& c = default_context();
+    cbs_gpu_params p;
+    cbs_gpu_default_params(&p);
+    p.nperm = nperm; p.rng_mode = CBS_GPU_RNG_MT19937_64;
+    const auto state = detail::next312(rng);
+    double pv = 0.0;
+    uint64_t draws = 0;
+    c.check(cbs_gpu_tpermp(c.get(), x, n1, n2, &p, state.data(), &pv, &draws));
+    rng.discard(draws);
+    return pv;
+}
+
+// cbs::wtmaxo, CBS.hpp:54-58.  cwts is recomputed from wts on the device (the reference's callers derive it from wts).
+inline BinarySegmentationResult wtmaxo(const std::vector<double>& x, const std::vector<double>& wts, double tss,
+                                       const std::vector<double>& cwts, int al0) {
+    (void)cwts;
+    if (x.size() != wts.size()) throw std::invalid_argument("x and wts must have same length");
+    Context& c = default_context();
+    BinarySegmentationResult r;
+    c.check(cbs_gpu_wtmaxo(c.get(), x.data(), wts.data(), (int)x.size(), tss, al0, &r.statistic, &r.start, &r.end));
+    return r;
+}
+
+namespace detail {
+inline void no_early_boundary(const std::vector<int>& sbdry, int nperm, const char* who) {
+    for (int v : sbdry)
+        if (v <= nperm) throw std::runtime_error(std::string(who) + ": a sequential boundary that can stop early is not supported");
+}
+inline ChangePointResult to_result(const cbs_gpu_split& s) {
+    ChangePointResult r;
+    r.ncpt = s.ncpt; r.icpt = {{s.icpt0, s.icpt1}}; r.iseg = {{s.iseg0, s.iseg1}}; r.ostat = s.ostat;
+    return r;
+}
+}  // namespace detail
+
+// cbs::fndcpt, CBS.hpp:68-80
+inline ChangePointResult fndcpt(const std::vector<double>& x, double tss, int nperm, double cpval, bool ibin, bool hybrid, int al0,
+                                int hk, double delta, int ngrid, const std::vector<int>& sbdry, double tol, std::mt19937_64& rng) {
+    detail::no_early_boundary(sbdry, nperm, "cbs_gpu::fndcpt");
+    Context& c = default_context();
+    const cbs_gpu_params p = detail::params(cpval, nperm, hybrid, al0, hk, 0, 0.05, tol, ibin, false, 0.05);
+    const auto state = detail::next312(rng);
+    cbs_gpu_split s;
+    uint64_t draws = 0;
+    c.check(cbs_gpu_fndcpt(c.get(), x.data(), (int)x.size(), tss, &p, delta, ngrid, state.data(), &s, &draws));
+    rng.discard(draws);
+    return detail::to_result(s);
+}
+
+// cbs::wfindcpt, CBS.hpp:81-97.  rwts / cwts / delta are derived from wts on the device (see cbs_gpu.h).
+inline ChangePointResult wfindcpt(const std::vector<double>& x, double tss, const std::vector<double>& wts,
+                                  const std::vector<double>& rwts, const std::vector<double>& cwts, int nperm, double cpval,
+                                  bool hybrid, int al0, int hk, double delta, int ngrid, const std::vector<int>& sbdry, double tol,
+                                  std::mt19937_64& rng) {
+    (void)rwts; (void)cwts; (void)delta;
+    if (x.size() != wts.size()) throw std::invalid_argument("x and wts must have same length");
+    detail::no_early_boundary(sbdry, nperm, "cbs_gpu::wfindcpt");
+    Context& c = default_context();
+    const cbs_gpu_params p = detail::params(cpval, nperm, hybrid, al0, hk, 0, 0.05, tol, false, false, 0.05);
+    const auto state = detail::next312(rng);
+    cbs_gpu_split s;
+    uint64_t draws = 0;
+    c.check(cbs_gpu_wfindcpt(c.get(), x.data(), wts.data(), (int)x.size(), tss, &p, ngrid, state.data(), &s, &draws));
+    rng.discard(draws);
+    return detail::to_result(s);
 }
 
 // cbs::segment, CBS.hpp:100-113.  `sbdry` must be the boundary `cna segment` builds

@@ -1,5 +1,5 @@
 // GPU test of the header-only shim (genomic_b200/host/cbs_gpu.hpp): the reference's own unit tests
-// (tests/cbs_test.cpp:154-177, :287-307; tests/smooth_test.cpp) with namespace cbs -> cbs_gpu, plus a
+// (tests/cbs_test.cpp:154-203, :287-330; tests/smooth_test.cpp) with namespace cbs -> cbs_gpu, the low-level surface, plus a
 // noisy vector checked against the oracle (liboracle.so) including the in/out engine state.
 #include <cmath>
 #include <cstdio>
@@ -24,12 +24,66 @@ int main() {
         const auto obs = cbs_gpu::tmaxo(x, tss, 2, false);
         CHECK(obs.start == 0); CHECK(obs.end == 58); CHECK(obs.statistic > 1000.0);
     }
-    {   // Unweighted_SegmentDriver_MatchesDNAcopy_SimpleCase (full-permutation rows)
-        const struct { double alpha; int nperm; int mw; } cases[] = {{0.01, 200, 2}, {0.05, 100, 3}};
+    {   // the same test's ibin = true half (tests/cbs_test.cpp:171-175): [0,58], statistic > 10
+        const auto obs = cbs_gpu::tmaxo(x, tss, 2, true);
+        CHECK(obs.start == 0); CHECK(obs.end == 58); CHECK(obs.statistic > 10.0);
+        CHECK(std::fabs(obs.statistic - 900.259) < 1e-3);  // what the compiled reference returns
+    }
+    {   // Weighted_wtmaxo_Matches_FortranRawStatisticBehavior (tests/cbs_test.cpp:179-203)
+        std::vector<double> xw, ww;
+        for (int i = 0; i < 15; ++i) { xw.push_back(0.0); ww.push_back(1.0); }
+        for (int i = 0; i < 15; ++i) { xw.push_back(2.0); ww.push_back(0.5); }
+        for (int i = 0; i < 15; ++i) { xw.push_back(-1.5); ww.push_back(2.0); }
+        for (int i = 0; i < 15; ++i) { xw.push_back(0.0); ww.push_back(1.0); }
+        double sw = 0, swx = 0, swxx = 0;
+        for (size_t i = 0; i < xw.size(); ++i) { sw += ww[i]; swx += ww[i] * xw[i]; swxx += ww[i] * xw[i] * xw[i]; }
+        const double wtss = swxx - (swx * swx) / sw;
+        std::vector<double> cw(xw.size());
+        double cs = 0.0;
+        for (size_t i = 0; i < xw.size(); ++i) { cs += ww[i]; cw[i] = cs / std::sqrt(sw); }
+        const auto o2 = cbs_gpu::wtmaxo(xw, ww, wtss, cw, 2);
+        CHECK(o2.start == 0); CHECK(o2.end == 58);
+        const auto o3 = cbs_gpu::wtmaxo(xw, ww, wtss, cw, 3);
+        CHECK(o3.start == 0); CHECK(o3.end == 57);
+    }
+    {   // low-level surface with the engine in/out (CBS.hpp:35-37,68-80): xperm, tpermp, fndcpt against the oracle restatement
+        std::mt19937_64 g(21);
+        std::normal_distribution<double> nz(0.0, 0.2);
+        std::vector<double> y(1200);
+        double s = 0.0;
+        for (size_t i = 0; i < y.size(); ++i) { y[i] = (double)(float)(nz(g) + ((i >= 500 && i < 640) ? 0.12 : 0.0)); }
+        for (double v : y) s += v;
+        const double avg = s / (double)y.size();
+        double ytss = 0.0;
+        for (auto& v : y) v -= avg;
+        for (double v : y) ytss += v * v;
+        std::mt19937_64 rng(5);
+        orc_rng orng;
+        orc_rng_seed_mt(&orng, 5);
+        std::vector<double> px, want(y.size());
+        cbs_gpu::xperm(y, px, rng);
+        orc_xperm(y.data(), (int)y.size(), want.data(), &orng);
+        for (size_t i = 0; i < y.size(); ++i) CHECK(px[i] == want[i]);
+        std::vector<double> scratch(y.size());
+        const double p1 = cbs_gpu::tpermp(500, 140, 640, y.data(), px, 300, rng);
+        CHECK(p1 == orc_tpermp(500, 140, 640, y.data(), 300, &orng, scratch.data()));
+        const int nperm = 400;
+        std::vector<int> sbdry(2000, nperm + 1);
+        const auto cp = cbs_gpu::fndcpt(y, ytss, nperm, 0.05, false, false, 2, 25, 0.0, 100, sbdry, 1e-6, rng);
+        const orc_cpt oc = orc_fndcpt(y.data(), (int)y.size(), ytss, nperm, 0.05, 0, 0, 2, 25, 0.0, 100, 1e-6, &orng);
+        CHECK(cp.ncpt == oc.ncpt); CHECK(cp.iseg[0] == oc.iseg[0] && cp.iseg[1] == oc.iseg[1]); CHECK(cp.ostat == oc.ostat);
+        if (oc.ncpt >= 1) CHECK(cp.icpt[0] == oc.icpt[0]);
+        if (oc.ncpt == 2) CHECK(cp.icpt[1] == oc.icpt[1]);
+        for (int i = 0; i < 5; ++i) CHECK(rng() == orc_rng_u64(&orng));  // three calls later both engines agree
+    }
+    {   // Unweighted_SegmentDriver_MatchesDNAcopy_SimpleCase (tests/cbs_test.cpp:287-306)
+        // all four parameter rows of the reference's fixture table: perm, perm_alt, hybrid, hybrid_alt
+        const struct { double alpha; int nperm; bool hybrid; int mw; } cases[] = {{0.01, 200, false, 2}, {0.05, 100, false, 3},
+                                                                                 {0.01, 200, true, 2}, {0.05, 100, true, 3}};
         for (const auto& tc : cases) {
             std::mt19937_64 rng(1);
             std::vector<int> sbdry((tc.nperm + 1) * (tc.nperm + 2) / 2 + 2, tc.nperm + 1);
-            const auto seg = cbs_gpu::segment(x, false, tc.alpha, tc.nperm, false, tc.mw, 25, 200, 0.05, sbdry, 1e-6, rng, false, 0.05);
+            const auto seg = cbs_gpu::segment(x, false, tc.alpha, tc.nperm, tc.hybrid, tc.mw, 25, 200, 0.05, sbdry, 1e-6, rng, false, 0.05);
             CHECK(seg.lengths.size() == 3);
             if (seg.lengths.size() == 3) {
                 CHECK(seg.lengths[0] == 20 && seg.lengths[1] == 20 && seg.lengths[2] == 20);
