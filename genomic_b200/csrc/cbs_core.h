@@ -194,6 +194,8 @@ struct Task {
     unsigned long long w_level, w_found;
     double w_init, w_corner, w_v;
     int w_q, w_phase, w_o1, w_o2, w_i, w_j, w_set, w_lock;
+    int w_tie;           // the maximum was attained in two pairs with EQUAL corner statistics: k_wobs_fin walks the pairs in the reference's
+                         // own (std::sort) order to get the location (weighted.cuh wtmaxo_ordered)
     double w_delta;      // weighted hybrid: min weight of a (kmax+1)-marker arc / total weight (getmncwt, CBS.cpp:602-607)
 };
 
@@ -441,6 +443,8 @@ struct Sched {
     CBS_HD static long long tbl_entries(int n) { return ((long long)n >> 5) + 2; }
     CBS_HD static long long sx_stride(int n) { return tbl_offset(n) + ((tbl_entries(n) + 3) & ~3LL); }
     CBS_HD static long long bs_stride(int nb) { return (3LL * nb + 4 + 3) & ~3LL; }
+    // scratch of wtmaxo_ordered (weighted.cuh), in doubles: per block 2 doubles + 2 ints, per block pair 3 doubles + 3 ints
+    CBS_HD static long long wexact_stride(int nb) { const long long nb2 = (long long)nb * (nb + 1) / 2; return (3 * (nb + 1) + 5 * (nb2 + 1) + 8 + 3) & ~3LL; }
     // 32-bit index array of the global-memory shuffle, in doubles; all strides are multiples of 4 doubles so
     // that every row of prefix sums starts on a 32-byte boundary (k_prefix moves rows with 128-bit accesses)
     CBS_HD static long long idx_stride(int n) { return (((long long)n + 1) / 2 + 1 + 3) & ~3LL; }
@@ -518,10 +522,11 @@ struct Sched {
     CBS_HD bool plan_obs(int idx) {
         Task& t = D.tasks[idx];
         t.nb = block_count(t.n);
-        const long long need = sx_stride(t.n) + bs_stride(t.nb);
+        const long long wx = D.w ? wexact_stride(t.nb) : 0;  // weighted: scratch of the ordered walk (only used when maxima tie)
+        const long long need = sx_stride(t.n) + bs_stride(t.nb) + wx;
         if (need > D.arena_cap) { D.error = ERR_ARENA; return false; }
         if (arena_used + need > D.arena_cap || rej_used + 1 > D.rej_cap) { t.deferred = 1; return false; }
-        t.off_sx = arena_used; t.off_bs = arena_used + sx_stride(t.n); t.off_A = -1;
+        t.off_sx = arena_used; t.off_bs = arena_used + sx_stride(t.n); t.off_A = wx ? t.off_bs + bs_stride(t.nb) : -1;
         arena_used += need;
         t.off_rej = rej_used; rej_used += 1;
         D.prep_task[D.n_prep++] = idx;

@@ -18,8 +18,8 @@
 #include "../../include/cbs_gpu.h"
 #include "host_math.h"
 #include "kernels.cuh"
-#include "weighted.cuh"
 #include "binary.cuh"
+#include "weighted.cuh"
 #include "mt_jump.h"
 #include "prune.h"
 #include "smooth.cuh"
@@ -364,10 +364,10 @@ int run_cbs(cbs_gpu_ctx* c, const std::vector<long long>& off, const uint64_t* u
 
     RunCaps cap;
     cap.task_cap = (int)std::min<long long>(std::max<long long>(4096, 64LL * n_units + 1024), 1 << 22);
-    cap.task_cap = (int)env_ll("CBS_GPU_TASK_CAP", cap.task_cap);
+    cap.task_cap = (int)std::max<long long>(64, std::min<long long>(env_ll("CBS_GPU_TASK_CAP", cap.task_cap), 1 << 24));  // env overrides: sane range only
     cap.list_cap = 4 * cap.task_cap + n_units + 16;
     cap.seg_cap = (int)std::min<long long>(N / 2 + n_units + 16, std::max<long long>(1 << 20, 256LL * n_units));
-    cap.seg_cap = (int)env_ll("CBS_GPU_SEG_CAP", cap.seg_cap);
+    cap.seg_cap = (int)std::max<long long>(n_units + 16, std::min<long long>(env_ll("CBS_GPU_SEG_CAP", cap.seg_cap), 1LL << 30));
     cap.split_cap = (p->record_splits || api.mode) ? 3 * cap.seg_cap + 16 : 1;
     cap.max_live = mt ? std::max(1, cap.task_cap / 16) : std::max(1, cap.task_cap / 4);
     // MT with one engine per unit: every chain reads the one shared stream from position 0 and the stream window only moves
@@ -471,6 +471,9 @@ int run_cbs(cbs_gpu_ctx* c, const std::vector<long long>& off, const uint64_t* u
     hD.prm.rng_mode = mt ? RNG_MT : RNG_PHILOX; hD.prm.chain = p->chain ? 1 : 0; hD.prm.seed = p->seed;
     hD.prm.first_batch = p->first_batch > 0 ? p->first_batch : 256;
     hD.prm.max_batch = p->max_batch > 0 ? p->max_batch : 4096;
+    // a batch needs one rejection flag per permutation: never ask for more than the flag table holds (it would be deferred forever)
+    hD.prm.first_batch = (int)std::min<long long>(hD.prm.first_batch, cap.rej_cap / 4);
+    hD.prm.max_batch = (int)std::min<long long>(hD.prm.max_batch, cap.rej_cap / 4);
     if (hD.prm.max_batch < hD.prm.first_batch) hD.prm.max_batch = hD.prm.first_batch;
     hD.prm.record_splits = (p->record_splits || api.mode) ? 1 : 0;
     hD.api_mode = api.mode; hD.api_tss = api.tss; hD.api_delta = api.delta; hD.api_n1 = api.n1; hD.api_n2 = api.n2;
@@ -699,8 +702,11 @@ int run_cbs(cbs_gpu_ctx* c, const std::vector<long long>& off, const uint64_t* u
                         snap.n_edgeprep, snap.n_edge, snap.n_gen, snap.n_segs, snap.stat_perms, snap.error);
             }
         }
-        if (rounds > 50000000) return fail(c, CBS_GPU_ERR_CUDA, "scheduler did not terminate");
+        if (rounds > 50000000) { cudaDeviceSynchronize(); return fail(c, CBS_GPU_ERR_CUDA, "scheduler did not terminate"); }
     }
+    // everything that was enqueued (up to two groups of rounds, on the main, generator and side streams) has to be over before
+    // anything is read back or an error is reported
+    for (int k = 0; k < 5; ++k) cudaStreamSynchronize(side[k]);
     CUDA_TRY(c, cudaStreamSynchronize(gen_stream));
     CUDA_TRY(c, cudaStreamSynchronize(st));
     CUDA_TRY(c, cudaGetLastError());

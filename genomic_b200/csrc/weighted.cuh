@@ -50,7 +50,7 @@ __device__ void wprep_warp(Dev* D, Task& t, int lane, double* __restrict__ bx, d
         for (int q = 0; q < WPREP_Q; ++q) if (!(fabs(v[q] - x0) < 1e-12)) flat = false;
     }
     flat = __all_sync(FULL, flat) && !t.raw;  // cbs::wfindcpt (low-level entry) takes the vector as it is
-    if (lane == 0) { t.alleq = flat ? 1 : 0; t.w_level = 0ull; t.w_found = 0ull; t.w_set = 0; t.w_lock = 0; t.w_init = -1.0; }
+    if (lane == 0) { t.alleq = flat ? 1 : 0; t.w_level = 0ull; t.w_found = 0ull; t.w_set = 0; t.w_lock = 0; t.w_tie = 0; t.w_init = -1.0; }
     if (flat) return;
     // CBS.cpp:1053-1058: wsum, wxsum.  Every sum is sequential, but the sums are independent of each other: lane 0 runs
     // them as interleaved DADD chains over values the whole warp staged in shared memory (products included: they are
@@ -220,6 +220,7 @@ struct WScanSmem {
     // location record: best arc among those that attain the maximum
     double r_corner, r_v;
     int r_q, r_phase, r_o1, r_o2, r_i, r_j, r_set;
+    int tie;  // wcand_tied was seen: the location needs the ordered walk
 };
 
 struct WRow {
@@ -288,10 +289,18 @@ __device__ __forceinline__ bool wcand_before(const WCand& a, const WCand& b) {
     if (!b.set) return a.set;
     if (!a.set) return false;
     if (a.corner != b.corner) return a.corner > b.corner;
-    if (a.q != b.q) return a.q < b.q;
+    // equal corner statistics: the reference's std::sort leaves short runs of equal keys in enumeration order (its final
+    // insertion sort is stable) and visits the sorted list from the back, so the LATER pair of the enumeration comes first
+    if (a.q != b.q) return a.q > b.q;
     if (a.phase != b.phase) return a.phase < b.phase;
     if (a.o1 != b.o1) return a.o1 < b.o1;
     return a.o2 < b.o2;
+}
+
+// the same maximum in two different pairs whose corner statistics are EQUAL: which one the reference visits first depends on
+// where std::sort leaves equal keys (it is not stable beyond 16 elements), which the keys above cannot express
+__device__ __forceinline__ bool wcand_tied(const WCand& a, const WCand& b) {
+    return a.set && b.set && a.v == b.v && a.corner == b.corner && a.q != b.q;
 }
 
 // larger statistic first, then the reference's visiting order
@@ -317,6 +326,7 @@ __device__ __forceinline__ void warc_eval(const WPair& p, int q, WScanSmem* sm, 
         const double v = d2 / den;
         if (LOC) {
             WCand c{p.corner, q, phase, o1, o2, i, j, true, v};
+            if (wcand_tied(c, best)) sm->tie = 1;
             if (wcand_better(c, best)) best = c;
         }
         if (v > __longlong_as_double((long long)*((volatile unsigned long long*)&sm->level))) {
@@ -462,12 +472,14 @@ __device__ void wscan_pass(const WRow& r, WScanSmem* sm, int lane) {
             c.i = __shfl_xor_sync(FULL, best.i, o); c.j = __shfl_xor_sync(FULL, best.j, o);
             c.set = __shfl_xor_sync(FULL, best.set ? 1 : 0, o) != 0;
             c.v = shfl_d(best.v, lane ^ o);
+            if (wcand_tied(c, best)) sm->tie = 1;
             if (wcand_better(c, best)) best = c;
         }
         if (lane == 0 && best.set) {
             while (atomicCAS(&sm->lock, 0, 1) != 0) {}
             __threadfence_block();
             WCand cur{sm->r_corner, sm->r_q, sm->r_phase, sm->r_o1, sm->r_o2, sm->r_i, sm->r_j, sm->r_set != 0, sm->r_v};
+            if (wcand_tied(best, cur)) sm->tie = 1;
             if (wcand_better(best, cur)) {
                 sm->r_v = best.v;
                 sm->r_corner = best.corner; sm->r_q = best.q; sm->r_phase = best.phase; sm->r_o1 = best.o1; sm->r_o2 = best.o2;
@@ -631,7 +643,7 @@ __global__ void __launch_bounds__(256) k_wscan(Dev* D, int nb_max) {
                 }
                 sm->level = (unsigned long long)__double_as_longlong(level);
                 sm->found = init_bits;
-                sm->next_pair = r.q_first; sm->lock = 0; sm->r_set = 0;
+                sm->next_pair = r.q_first; sm->lock = 0; sm->r_set = 0; sm->tie = 0;
                 sm->r_corner = 0.0; sm->r_q = 0; sm->r_phase = 0; sm->r_o1 = 0; sm->r_o2 = 0; sm->r_i = 0; sm->r_j = 0;
             }
             __syncthreads();
@@ -644,6 +656,7 @@ __global__ void __launch_bounds__(256) k_wscan(Dev* D, int nb_max) {
                     __threadfence();
                     const volatile Task& vt = t;
                     WCand cur{vt.w_corner, vt.w_q, vt.w_phase, vt.w_o1, vt.w_o2, vt.w_i, vt.w_j, vt.w_set != 0, vt.w_v};
+                    if (sm->tie || wcand_tied(mine, cur)) t.w_tie = 1;
                     if (wcand_better(mine, cur)) {
                         t.w_v = mine.v; t.w_corner = mine.corner; t.w_q = mine.q; t.w_phase = mine.phase; t.w_o1 = mine.o1;
                         t.w_o2 = mine.o2; t.w_i = mine.i; t.w_j = mine.j; t.w_set = 1;
@@ -668,20 +681,182 @@ __global__ void __launch_bounds__(256) k_wscan(Dev* D, int nb_max) {
     }
 }
 
-// observed rows: statistic and location from the shared records (after k_wscan<1> and k_wscan<2>)
+// cbs::wtmaxo (CBS.cpp:610-739) walked in the reference's own order by one warp: lane 0 runs the control flow (block extrema,
+// pair list, std::sort order of the corner statistics, descending visit with the running maximum), the lanes share the inner
+// loop over j.  Only used for an observed row whose maximum is attained in pairs with equal corner statistics (structured
+// data: constant stretches, periodic signals), where the location depends on std::sort's treatment of equal keys.
+__device__ void wtmaxo_ordered(const double* __restrict__ sx, const double* __restrict__ cw, const int* __restrict__ bb, int n, int nb,
+                               int al0, double* scratch, int lane, double& bss_out, int& ti_out, int& tj_out) {
+    const int nb2 = nb * (nb + 1) / 2;
+    double* bpsmax = scratch;
+    double* bpsmin = bpsmax + nb + 1;
+    double* bssbij = bpsmin + nb + 1;
+    double* bssijmax = bssbij + nb2 + 1;
+    double* awt = bssijmax + nb2 + 1;
+    int* ibmin = (int*)(awt + nb2 + 1);
+    int* ibmax = ibmin + nb + 1;
+    int* bloc = ibmax + nb + 1;   // (i << 16) | j
+    int* loc = bloc + nb2 + 1;
+    double psmin0 = 0.0, psmax0 = 0.0;
+    int ipsmin0 = n, ipsmax0 = n;
+    if (lane == 0) {  // :621-637 from the prefix sums that k_wprep wrote
+        for (int j = 1; j <= nb; ++j) {
+            const int ilo = bb[j - 1] + 1;
+            double psmin = sx[ilo], psmax = sx[ilo];
+            int ipsmin = ilo, ipsmax = ilo;
+            for (int i = ilo + 1; i <= bb[j]; ++i) {
+                if (sx[i] < psmin) { psmin = sx[i]; ipsmin = i; }
+                if (sx[i] > psmax) { psmax = sx[i]; ipsmax = i; }
+            }
+            ibmin[j] = ipsmin; ibmax[j] = ipsmax; bpsmin[j] = psmin; bpsmax[j] = psmax;
+            if (psmin < psmin0) { psmin0 = psmin; ipsmin0 = ipsmin; }
+            if (psmax > psmax0) { psmax0 = psmax; ipsmax0 = ipsmax; }
+        }
+    }
+    __syncwarp();
+    psmin0 = shfl_d(psmin0, 0); psmax0 = shfl_d(psmax0, 0);
+    ipsmin0 = __shfl_sync(FULL, ipsmin0, 0); ipsmax0 = __shfl_sync(FULL, ipsmax0, 0);
+    double bssmax = 0.0;
+    int tmaxi = min(ipsmax0, ipsmin0), tmaxj = max(ipsmax0, ipsmin0);
+    const double psdiff = psmax0 - psmin0;
+    if (psdiff <= 0.0) { bss_out = 0.0; ti_out = tmaxi; tj_out = tmaxj; return; }
+    const double psrn = cw[n - 1];
+    {
+        const double psrj = fabs(cw[ipsmax0 - 1] - cw[ipsmin0 - 1]);
+        bssmax = (psdiff * psdiff) / (psrj * (psrn - psrj));
+    }
+    const double psrnov2 = psrn / 2.0;
+    const int nal0 = n - al0;
+    int l = 0;
+    for (int i = 1; i <= nb; ++i) {  // :650-693, the list keeps the (i, j) order (ballot compaction)
+        for (int j0 = i; j0 <= nb; j0 += 32) {
+            const int j = j0 + lane;
+            bool take = false;
+            double e_lim = 0.0, e_bij = 0.0, e_awt = 0.0;
+            if (j <= nb) {
+                const int ilo1 = (i == 1) ? 1 : bb[i - 1] + 1, ihi = bb[i];
+                const int jlo = (j == 1) ? 1 : bb[j - 1] + 1, jhi = bb[j];
+                double awthi = cw[jhi - 1] - cw[ilo1 - 1];
+                if (jhi - ilo1 > nal0) {
+                    awthi = 0.0;
+                    for (int kk = 1; kk <= al0; ++kk) awthi = fmax(awthi, cw[nal0 + kk - 1] - cw[kk - 1]);
+                }
+                double awtlo;
+                if (i == j) {
+                    awtlo = cw[ilo1 + al0 - 1] - cw[ilo1 - 1];
+                    for (int kk = ilo1 + 1; kk <= ihi - al0; ++kk) awtlo = fmin(awtlo, cw[kk + al0 - 1] - cw[kk - 1]);
+                } else if (i + 1 == j) {
+                    awtlo = cw[jlo - 1] - cw[jlo - al0 - 1];
+                    for (int kk = jlo - al0 + 1; kk <= ihi; ++kk) awtlo = fmin(awtlo, cw[kk + al0 - 1] - cw[kk - 1]);
+                } else awtlo = cw[jlo - 1] - cw[ihi - 1];
+                const double sij1 = fabs(bpsmax[j] - bpsmin[i]), sij2 = fabs(bpsmax[i] - bpsmin[j]);
+                const double sijmx0 = fmax(sij1, sij2);
+                const double bsslim = (sijmx0 * sijmx0) / fmin(awtlo * (psrn - awtlo), awthi * (psrn - awthi));
+                if (bssmax <= bsslim) {
+                    take = true; e_lim = bsslim;
+                    if (sij1 > sij2) { e_awt = fabs(cw[ibmax[j] - 1] - cw[ibmin[i] - 1]); e_bij = (sij1 * sij1) / (e_awt * (psrn - e_awt)); }
+                    else { e_awt = fabs(cw[ibmin[j] - 1] - cw[ibmax[i] - 1]); e_bij = (sij2 * sij2) / (e_awt * (psrn - e_awt)); }
+                }
+            }
+            const unsigned mask = __ballot_sync(FULL, take);
+            if (take) {
+                const int pos = l + 1 + __popc(mask & ((1u << lane) - 1u));
+                loc[pos] = pos; bloc[pos] = (i << 16) | j; bssijmax[pos] = e_lim; awt[pos] = e_awt; bssbij[pos] = e_bij;
+            }
+            l += __popc(mask);
+        }
+    }
+    const int nb1 = l;
+    __syncwarp();
+    if (lane == 0) { IdxSort srt{loc + 1, bssbij}; srt.run(nb1); }
+    __syncwarp();
+    for (int ll = nb1; ll >= 1; --ll) {  // :698-735
+        const int k = loc[ll];
+        if (bssmax > bssijmax[k]) continue;
+        const int bi = bloc[k] >> 16, bj = bloc[k] & 0xffff;
+        double awtmax = awt[k];
+        const int ilo1 = (bi == 1) ? 1 : bb[bi - 1] + 1, ihi = bb[bi];
+        const int jlo = (bj == 1) ? 1 : bb[bj - 1] + 1, jhi = bb[bj];
+        const double awthi = cw[jhi - 1] - cw[ilo1 - 1];
+        const double awtlo = (bi == bj) ? 0.0 : (cw[jlo - 1] - cw[ihi - 1]);
+        if (awtmax > psrn - awtmax) awtmax = psrn - awtmax;
+        if (awtlo <= psrnov2) {
+            const int ihi1 = (bi == bj) ? ihi - al0 : ihi;
+            for (int i = ihi1; i >= ilo1; --i) {
+                const int jlo1 = max(i + al0, jlo);
+                double rv = -1.0;
+                int rj = 0x7fffffff;
+                for (int j = jlo1 + lane; j <= jhi; j += 32) {  // ascending j: the first j that attains the row's maximum counts
+                    const double awt1 = cw[j - 1] - cw[i - 1];
+                    if (awt1 <= awtmax) {
+                        const double d = sx[j] - sx[i];
+                        const double v = (d * d) / (awt1 * (psrn - awt1));
+                        if (v > rv) { rv = v; rj = j; }
+                    }
+                }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                    const double ov = shfl_d(rv, lane ^ o);
+                    const int oj = __shfl_xor_sync(FULL, rj, o);
+                    if (ov > rv || (ov == rv && oj < rj)) { rv = ov; rj = oj; }
+                }
+                if (rv > bssmax) { bssmax = rv; tmaxi = i; tmaxj = rj; }
+            }
+        }
+        awtmax = psrn - awtmax;
+        if (awthi >= psrnov2) {
+            for (int i = ilo1; i <= ihi; ++i) {
+                const int jhi1 = ((bi == 1) && (bj == nb)) ? min(jhi, jhi - al0 + i) : jhi;
+                double rv = -1.0;
+                int rj = -1;
+                for (int j = jhi1 - lane; j >= jlo; j -= 32) {  // descending j: the LARGEST j among equal maxima is met first
+                    const double awt1 = cw[j - 1] - cw[i - 1];
+                    if (awt1 >= awtmax) {
+                        const double d = sx[j] - sx[i];
+                        const double v = (d * d) / (awt1 * (psrn - awt1));
+                        if (v > rv) { rv = v; rj = j; }
+                    }
+                }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                    const double ov = shfl_d(rv, lane ^ o);
+                    const int oj = __shfl_xor_sync(FULL, rj, o);
+                    if (ov > rv || (ov == rv && oj > rj)) { rv = ov; rj = oj; }
+                }
+                if (rv > bssmax) { bssmax = rv; tmaxi = i; tmaxj = rj; }
+            }
+        }
+    }
+    bss_out = bssmax; ti_out = tmaxi; tj_out = tmaxj;
+}
+
+// observed rows: statistic and location from the shared records (after k_wscan<1> and k_wscan<2>); a warp per row
 __global__ void k_wobs_fin(Dev* D) {
     if (D->done) return;
-    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < D->n_items; k += gridDim.x * blockDim.x) {
+    const int lane = threadIdx.x & 31;
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
+    for (int k = warp; k < D->n_items; k += nwarps) {
         const PermItem it = D->items[k];
         if (it.obs != 1) continue;
         Task& t = D->tasks[it.task];
         if (t.alleq) continue;
         const double best = __longlong_as_double((long long)t.w_found);  // 0.0 when the prefix sums have no spread
-        double tss = t.tss;
-        if (tss <= best + 0.0001) tss = best + 1.0;  // CBS.cpp:643,737
-        t.ostat = best / ((tss - best) / ((double)t.n - 2.0));
+        int ti = t.tmaxi, tj = t.tmaxj;
         // the seed arc is visited first and wins ties; otherwise the first-visited arc that attains the maximum
-        if (t.w_set && t.w_v == best && best > t.w_init) { t.tmaxi = t.w_i; t.tmaxj = t.w_j; }
+        if (t.w_set && t.w_v == best && best > t.w_init) { ti = t.w_i; tj = t.w_j; }
+        if (t.w_tie && t.off_A >= 0) {  // equal corner statistics and equal maxima: take the location from the reference's own walk
+            const long long base = D->unit_off[t.unit] + t.lo;
+            double b2;
+            int i2, j2;
+            wtmaxo_ordered(D->arena + t.off_sx, D->cw + base, D->bbtab + base, t.n, t.nb, D->prm.min_width, D->arena + t.off_A, lane, b2, i2, j2);
+            if (b2 == best) { ti = i2; tj = j2; }
+        }
+        if (lane == 0) {
+            double tss = t.tss;
+            if (tss <= best + 0.0001) tss = best + 1.0;  // CBS.cpp:643,737
+            t.ostat = best / ((tss - best) / ((double)t.n - 2.0));
+            t.tmaxi = ti; t.tmaxj = tj;
+        }
     }
 }
 
