@@ -67,6 +67,39 @@ struct RawMatrix {
     std::vector<std::vector<float>> values[kChromosomes];  // [chrom][sample][marker]
 };
 
+// every chromosome ordered by position (RawSampleSet<V>::sort, lib/RawSampleSet.hpp:332-386).  A sample column whose length
+// differs from the marker count (a row had unparsable or missing fields) is indexed out of bounds by the reference; here
+// it is an error.
+inline void sort_by_position(RawMatrix& m, int nthreads) {
+    auto sort_chrom = [&](int c) {
+        const size_t n = m.positions[c].size();
+        // (position, row) pairs ordered on the position alone by std::sort, as lib/RawSampleSet.hpp:361-368 with
+        // lib/global.hpp:170-173: rows that share a position come out in whatever order libstdc++'s introsort leaves
+        // them (insertion order up to 16 rows, not stable beyond), and the same call gives the same order here
+        std::vector<std::pair<unsigned long, size_t>> order;
+        order.reserve(n);
+        for (size_t i = 0; i < n; ++i) order.emplace_back(m.positions[c][i], i);
+        std::sort(order.begin(), order.end(),
+                  [](const std::pair<unsigned long, size_t>& a, const std::pair<unsigned long, size_t>& b) { return a.first < b.first; });
+        std::vector<unsigned long> p(n);
+        for (size_t i = 0; i < n; ++i) p[i] = order[i].first;
+        m.positions[c].swap(p);
+        for (auto& sv : m.values[c]) {
+            if (sv.size() != n) throw std::runtime_error("sample column count differs from marker count (unparsable fields?)");
+            std::vector<float> v(n);
+            for (size_t i = 0; i < n; ++i) v[i] = sv[order[i].second];
+            sv.swap(v);
+        }
+    };
+    if (nthreads <= 1) { for (int c = 0; c < kChromosomes; ++c) sort_chrom(c); return; }
+    std::vector<std::thread> th;
+    std::vector<std::string> errs((size_t)kChromosomes);
+    for (int c = 0; c < kChromosomes; ++c)
+        th.emplace_back([&, c] { try { sort_chrom(c); } catch (const std::exception& e) { errs[(size_t)c] = e.what(); } });
+    for (auto& t : th) t.join();
+    for (const auto& e : errs) if (!e.empty()) throw std::runtime_error(e);
+}
+
 inline RawMatrix read_cn(const std::string& path) {
     std::ifstream file(path);
     if (!file.is_open()) throw std::runtime_error("Failed to open input file '" + path + "'.");
@@ -102,22 +135,7 @@ inline RawMatrix read_cn(const std::string& path) {
             ++s;
         }
     }
-    // sort every chromosome by position
-    for (int c = 0; c < kChromosomes; ++c) {
-        const size_t n = m.positions[c].size();
-        std::vector<size_t> order(n);
-        for (size_t i = 0; i < n; ++i) order[i] = i;
-        std::stable_sort(order.begin(), order.end(), [&](size_t a, size_t b) { return m.positions[c][a] < m.positions[c][b]; });
-        std::vector<unsigned long> p(n);
-        for (size_t i = 0; i < n; ++i) p[i] = m.positions[c][order[i]];
-        m.positions[c].swap(p);
-        for (auto& sv : m.values[c]) {
-            if (sv.size() != n) throw std::runtime_error("sample column count differs from marker count (unparsable fields?)");
-            std::vector<float> v(n);
-            for (size_t i = 0; i < n; ++i) v[i] = sv[order[i]];
-            sv.swap(v);
-        }
-    }
+    sort_by_position(m, 1);
     return m;
 }
 
@@ -149,31 +167,6 @@ inline void parse_cn_line(std::string_view line, size_t n_samples, RawMatrix& m)
         if (s < n_samples) m.values[chr - 1][s].push_back(v);
         ++s;
     }
-}
-
-inline void sort_by_position(RawMatrix& m, int nthreads) {
-    auto sort_chrom = [&](int c) {
-        const size_t n = m.positions[c].size();
-        std::vector<size_t> order(n);
-        for (size_t i = 0; i < n; ++i) order[i] = i;
-        std::stable_sort(order.begin(), order.end(), [&](size_t a, size_t b) { return m.positions[c][a] < m.positions[c][b]; });
-        std::vector<unsigned long> p(n);
-        for (size_t i = 0; i < n; ++i) p[i] = m.positions[c][order[i]];
-        m.positions[c].swap(p);
-        for (auto& sv : m.values[c]) {
-            if (sv.size() != n) throw std::runtime_error("sample column count differs from marker count (unparsable fields?)");
-            std::vector<float> v(n);
-            for (size_t i = 0; i < n; ++i) v[i] = sv[order[i]];
-            sv.swap(v);
-        }
-    };
-    if (nthreads <= 1) { for (int c = 0; c < kChromosomes; ++c) sort_chrom(c); return; }
-    std::vector<std::thread> th;
-    std::vector<std::string> errs((size_t)kChromosomes);
-    for (int c = 0; c < kChromosomes; ++c)
-        th.emplace_back([&, c] { try { sort_chrom(c); } catch (const std::exception& e) { errs[(size_t)c] = e.what(); } });
-    for (auto& t : th) t.join();
-    for (const auto& e : errs) if (!e.empty()) throw std::runtime_error(e);
 }
 
 inline RawMatrix read_cn_parallel(const std::string& path, int nthreads) {

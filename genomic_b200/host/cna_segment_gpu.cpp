@@ -14,6 +14,7 @@
 // usage: cna_segment_gpu [options] <raw sample matrix file> [<output segmentation file>]
 #include <algorithm>
 #include <charconv>
+#include <chrono>
 #include <cmath>
 #include <cstdint>
 #include <cstdio>
@@ -62,7 +63,8 @@ int main(int argc, char** argv) {
         cbs_gpu_params p;
         cbs_gpu_default_params(&p);
         std::string input, output;
-        int device = 0;
+        int device = 0, chain_opt = -1;
+        bool timing = false;
         int io_threads = (int)std::max(1u, std::min(16u, std::thread::hardware_concurrency()));  // parser threads (cn_reader.hpp)
         std::vector<std::string> positional;
         auto value_of = [&](int& i, const std::string& arg, const std::string& name, std::string& out) -> bool {
@@ -77,7 +79,10 @@ int main(int argc, char** argv) {
                 std::cout << "usage:  cna_segment_gpu [options] <raw sample matrix file> <output segmentation file>\n"
                              "  --alpha --nperm --min_width --kmax --nmin --eta --trim --smooth_region --outlier_sd_scale\n"
                              "  --smooth_sd_scale --hybrid --undo_prune --undo_prune_cutoff  (as `cna segment`)\n"
-                             "  --device N   --rng mt|philox   --seed S   --io_threads T (parser threads, default: all cores up to 16)\n";
+                             "  --device N   --rng mt|philox   --seed S   --io_threads T (parser threads, default: all cores up to 16)\n"
+                             "  --chain 0|1  MT replay: 1 = ONE engine shared serially by all units, as `cna segment` does (default);\n"
+                             "               0 = a fresh std::mt19937_64(seed) per (sample, chromosome): units are independent and run together\n"
+                             "  --timing     phase times as one JSON line on stderr   --format cn (accepted for compatibility)\n";
                 return 0;
             } else if (value_of(i, a, "--input", v) || value_of(i, a, "-i", v)) input = v;
             else if (value_of(i, a, "--output", v) || value_of(i, a, "-o", v)) output = v;
@@ -97,10 +102,14 @@ int main(int argc, char** argv) {
             else if (value_of(i, a, "--device", v)) device = std::stoi(v);
             else if (value_of(i, a, "--io_threads", v)) io_threads = std::max(1, std::stoi(v));
             else if (value_of(i, a, "--seed", v)) p.seed = std::stoull(v);
+            else if (value_of(i, a, "--format", v)) { if (v != "cn") throw std::invalid_argument("segment command currently supports raw log-ratio matrices only."); }
+            else if (value_of(i, a, "--chain", v)) chain_opt = (v == "1" || v == "true") ? 1 : 0;
+            else if (a == "--timing") timing = true;
             else if (value_of(i, a, "--rng", v)) { p.rng_mode = (v == "philox") ? CBS_GPU_RNG_PHILOX : CBS_GPU_RNG_MT19937_64; p.chain = (v == "philox") ? 0 : 1; }
             else if (!a.empty() && a[0] == '-') throw std::invalid_argument("unknown option " + a);
             else positional.push_back(a);
         }
+        if (chain_opt >= 0 && p.rng_mode == CBS_GPU_RNG_MT19937_64) p.chain = chain_opt;
         if (input.empty() && !positional.empty()) { input = positional.front(); positional.erase(positional.begin()); }
         if (output.empty() && !positional.empty()) output = positional.front();
         if (input.empty()) throw std::invalid_argument("Input file not specified.");
@@ -111,8 +120,10 @@ int main(int argc, char** argv) {
         }
         if (output.empty()) output = filestem(input) + ".seg";
 
+        const auto t_start = std::chrono::steady_clock::now();
         const RawMatrix m = io_threads > 1 ? read_cn_parallel(input, io_threads) : read_cn(input);
         ensure_log_scale(m);
+        const auto t_read = std::chrono::steady_clock::now();
 
         // units in the reference's order: samples in file order, chromosomes 1..24, empty ones skipped
         std::vector<float> values;
@@ -128,6 +139,7 @@ int main(int argc, char** argv) {
                 units.push_back({s, c});
             }
 
+        const auto t_pack = std::chrono::steady_clock::now();
         const int ids[1] = {device};
         cbs_gpu_ctx* ctx = nullptr;
         if (cbs_gpu_create(ids, 1, &ctx) != CBS_GPU_OK) throw std::runtime_error("no usable CUDA device (there is no CPU fallback)");
@@ -140,9 +152,10 @@ int main(int argc, char** argv) {
             throw std::runtime_error(msg);
         }
 
+        const auto t_gpu = std::chrono::steady_clock::now();
         std::ofstream out(output);
         if (!out.is_open()) throw std::runtime_error("Failed to open output file '" + output + "'.");
-        out << "sample\tchromosome\tstart\tend\tcount\tstate" << std::endl;
+        out << "sample\tchromosome\tstart\tend\tcount\tstate" << '\n';
         for (size_t u = 0; u < units.size(); ++u) {
             const auto& pos = m.positions[units[u].chrom];
             size_t start = 0;
@@ -152,9 +165,23 @@ int main(int argc, char** argv) {
                 const size_t end = start + len - 1;
                 const float state = (float)res->means[k];  // Segment<rvalue>: rvalue = float (lib/typedefs.h:20)
                 out << m.sample_names[units[u].sample] << '\t' << (units[u].chrom + 1) << '\t' << pos[start] << '\t' << pos[end]
-                    << '\t' << (unsigned long)len << '\t' << state << std::endl;
+                    << '\t' << (unsigned long)len << '\t' << state << '\n';
                 start += len;
             }
+        }
+        out.flush();
+        const auto t_write = std::chrono::steady_clock::now();
+        if (timing) {
+            auto ms = [](auto a, auto b) { return std::chrono::duration<double, std::milli>(b - a).count(); };
+            long long markers = 0;
+            for (size_t u = 0; u < units.size(); ++u) markers += off[u + 1] - off[u];
+            std::fprintf(stderr,
+                         "{\"samples\": %zu, \"units\": %zu, \"markers_x_samples\": %lld, \"segments\": %lld, \"io_threads\": %d, "
+                         "\"read_parse_sort_ms\": %.1f, \"pack_ms\": %.1f, \"gpu_call_ms\": %.1f, \"gpu_h2d_ms\": %.1f, \"gpu_smooth_ms\": %.1f, "
+                         "\"gpu_segment_ms\": %.1f, \"gpu_d2h_ms\": %.1f, \"write_seg_ms\": %.1f, \"total_ms\": %.1f}\n",
+                         m.sample_names.size(), units.size(), markers, (long long)res->n_segments, io_threads, ms(t_start, t_read),
+                         ms(t_read, t_pack), ms(t_pack, t_gpu), res->ms_h2d, res->ms_smooth, res->ms_segment, res->ms_d2h, ms(t_gpu, t_write),
+                         ms(t_start, t_write));
         }
         cbs_gpu_result_free(res);
         cbs_gpu_destroy(ctx);

@@ -39,7 +39,7 @@ int main(int argc, char** argv) {
         for (int c = 1; c <= 25; ++c) {  // chromosome "25" is unknown: its rows are ignored
             for (int i = 0; i < per_chrom; ++i) {
                 const char* pre = (c % 2) ? "chr" : "";
-                // positions deliberately not monotone: the reader sorts them (stable)
+                // positions deliberately not monotone: the reader sorts them
                 const unsigned long pos = 1000ul + (unsigned long)((i * 7919L) % per_chrom) * 10ul + (unsigned long)(i % 3 == 0);
                 if (c == 23) std::fprintf(f, "m%ld\t%sX\t%lu", id++, pre, pos);
                 else std::fprintf(f, "m%ld\t%s%d\t%lu", id++, pre, c, pos);

@@ -211,3 +211,15 @@ def test_cn_reader_parallel_identical(tmp_path):
         r = subprocess.run([str(exe), str(tmp_path / "t.cn"), str(markers), str(samples), str(threads)], capture_output=True, text=True)
         assert r.returncode == 0, r.stdout + r.stderr
         assert json.loads(r.stdout)["identical"] is True
+
+
+def test_cn_reader_reference_rules(tmp_path):
+    """tests/cpp/reader_rules_test.cpp: adversarial .cn inputs (rows the reference drops, fields it skips and the column
+    shift that follows, nan/inf, rows sharing a position in std::sort's order, unterminated last line, empty files)
+    against expectations derived from lib/RawSampleSet.hpp:217-285,332-386 and lib/parse.hpp:20-26"""
+    import subprocess
+    exe = tmp_path / "reader_rules_test"
+    subprocess.run(["g++", "-std=c++17", "-O2", "-pthread", os.path.join(ROOT, "tests", "cpp", "reader_rules_test.cpp"), "-o", str(exe)],
+                   check=True)
+    r = subprocess.run([str(exe), str(tmp_path)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
