@@ -295,7 +295,7 @@ def run_gpu_arm(args):
     warm = max(args.warmup, 3) if not args.cohort_run else args.warmup
     total_ms, res, clocks = timed(step_device, args.steps, warm, sample_clocks=True)
     steps_device = timed.last_steps
-    e2e_ms, res_h, _ = timed(step_host, args.steps, 0 if args.cohort_run else 1)
+    e2e_ms, res_h, _ = timed(step_host, args.steps, 0 if args.cohort_run else max(args.warmup, 3))
     steps_host = timed.last_steps
     launches_per_step = int(res.kernel_launches)
     full_table = gather_tables.last

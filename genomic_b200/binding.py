@@ -57,7 +57,7 @@ class CResult(C.Structure):
         ("lengths", C.POINTER(C.c_int32)), ("means", C.POINTER(C.c_double)),
         ("draws_consumed", C.POINTER(C.c_uint64)), ("n_splits", C.c_int64), ("splits", C.POINTER(CSplit)),
         ("rounds", C.c_int32), ("perms_run", C.c_uint64), ("perm_elements", C.c_uint64), ("kernel_launches", C.c_uint64), ("ms_h2d", C.c_double),
-        ("ms_smooth", C.c_double), ("ms_segment", C.c_double), ("ms_d2h", C.c_double),
+        ("ms_smooth", C.c_double), ("ms_segment", C.c_double), ("ms_d2h", C.c_double), ("ms_call", C.c_double),
     ]
 
 
@@ -257,7 +257,7 @@ class Context:
             means=np.ctypeslib.as_array(r.means, shape=(ns,)).copy() if ns else np.zeros(0),
             draws=np.ctypeslib.as_array(r.draws_consumed, shape=(n_units,)).copy() if n_units else np.zeros(0, np.uint64),
             rounds=int(r.rounds), perms_run=int(r.perms_run), perm_elems=int(r.perm_elements), kernel_launches=int(r.kernel_launches),
-            ms=dict(h2d=r.ms_h2d, smooth=r.ms_smooth, segment=r.ms_segment, d2h=r.ms_d2h),
+            ms=dict(h2d=r.ms_h2d, smooth=r.ms_smooth, segment=r.ms_segment, d2h=r.ms_d2h, call=r.ms_call),
         )
         if r.n_splits:
             res.splits = [dict((f, getattr(r.splits[i], f)) for f, _ in CSplit._fields_) for i in range(int(r.n_splits))]

@@ -7,6 +7,7 @@
 #include <cub/cub.cuh>
 
 #include <algorithm>
+#include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <cstddef>
@@ -60,8 +61,6 @@ struct cbs_gpu_ctx {
     std::vector<cbs_gpu_ctx*> lanes;
     double mem_fraction = 0.80;  // share of free device memory the arenas of this context may take
     bool is_lane = false;
-    void* h_stage = nullptr;  // pinned staging for host inputs
-    size_t h_stage_cap = 0;
     bool profiling = false;   // per-launch CUDA events
     bool serial = false;      // all kernels of a round on one stream (non-overlapping per-kernel times)
     bool counting = false;    // scan work counters (atomics in the kernel: slows it, never combine with timing)
@@ -114,15 +113,6 @@ int ensure(cbs_gpu_ctx* c, DevBuf& b, size_t bytes) {
         const int rc__ = ensure(c, buf, bytes);                 \
         if (rc__ != CBS_GPU_OK) return rc__;                    \
     } while (0)
-
-int ensure_host_stage(cbs_gpu_ctx* c, size_t bytes) {
-    if (bytes <= c->h_stage_cap) return CBS_GPU_OK;
-    if (c->h_stage) cudaFreeHost(c->h_stage);
-    c->h_stage = nullptr; c->h_stage_cap = 0;
-    CUDA_TRY(c, cudaHostAlloc(&c->h_stage, bytes + bytes / 8, cudaHostAllocDefault));
-    c->h_stage_cap = bytes + bytes / 8;
-    return CBS_GPU_OK;
-}
 
 // event-bracketed launch bookkeeping (profiling mode)
 struct LaunchTimer {
@@ -932,7 +922,6 @@ void cbs_gpu_destroy(cbs_gpu_ctx* c) {
                       &c->diffs_sorted, &c->gout, &c->cubtmp, &c->flag, &c->goff, &c->stream_buf, &c->shuf, &c->jump, &c->tailp,
                       &c->wts, &c->rw, &c->cw, &c->ycur};
     for (DevBuf* b : bufs) if (b->p) cudaFree(b->p);
-    if (c->h_stage) cudaFreeHost(c->h_stage);
     if (c->h_done) cudaFreeHost(c->h_done);
     for (auto e : c->ev_pool) cudaEventDestroy(e);
     cudaEvent_t evs[] = {c->e0, c->e1, c->e2, c->e3, c->e4, c->grp[0], c->grp[1]};
@@ -1140,6 +1129,7 @@ static int segment_batch_impl(cbs_gpu_ctx* c, const void* values, int dtype, int
     if (!c) return CBS_GPU_ERR_INVALID;
     if (!out) return fail(c, CBS_GPU_ERR_INVALID, "out is NULL");
     *out = nullptr;
+    const auto wall0 = std::chrono::steady_clock::now();
     if (cudaSetDevice(c->device) != cudaSuccess) return fail(c, CBS_GPU_ERR_CUDA, "cudaSetDevice failed");
     int rc = validate_params(c, params);
     if (rc) return rc;
@@ -1198,6 +1188,7 @@ static int segment_batch_impl(cbs_gpu_ctx* c, const void* values, int dtype, int
     cudaEventElapsedTime(&ms, c->e1, c->e2); R->pub.ms_smooth = ms;
     cudaEventElapsedTime(&ms, c->e2, c->e3); R->pub.ms_segment = ms;
     cudaEventElapsedTime(&ms, c->e3, c->e4); R->pub.ms_d2h = ms;
+    R->pub.ms_call = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - wall0).count();
     if (c->profiling) collect_timers(c);
     R->pub.kernel_launches = c->launches;
     c->last_arcs = hD.stat_arcs;

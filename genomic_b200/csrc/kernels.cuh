@@ -137,7 +137,7 @@ __device__ void prep_warp(Dev* D, Task& t, int lane, double* buf) {
     const long long base = D->unit_off[t.unit] + t.lo;
     const double* __restrict__ x = D->x + base;
     double* cur = D->cur + base;
-    const int n = t.n, nb = t.nb;
+    const int n = t.n;
     const bool raw = t.raw != 0;
     double avg = 0.0;
     double r[PREP_CHUNK / 32];

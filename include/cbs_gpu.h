@@ -96,6 +96,7 @@ typedef struct cbs_gpu_result {
     uint64_t perm_elements;         /* sum over those permutations of the segment length (markers shuffled) */
     uint64_t kernel_launches;       /* kernels launched by this call */
     double ms_h2d, ms_smooth, ms_segment, ms_d2h; /* CUDA-event timings on the call's stream */
+    double ms_call;                 /* host wall clock of the whole call (buffer growth, staging and read-back included) */
 } cbs_gpu_result;
 
 /* ---- context -----------------------------------------------------------------------

@@ -1,6 +1,6 @@
 // make_cn.cpp -- writes a synthetic SNP6-scale cohort (genomic_b200/host/synth.cpp) as a `.cn` raw matrix
 // (lib/RawSampleSet.hpp:217-263 layout: marker, chromosome, position, one column per sample) for end-to-end runs of
-// cna_segment_gpu.   g++ -O2 -std=c++17 -o tools/make_cn tools/make_cn.cpp genomic_b200/libsynth.so
+// cna_segment_gpu.   g++ -O2 -std=c++17 -o tools/make_cn tools/make_cn.cpp -Lgenomic_b200 -l:libsynth.so -Wl,-rpath,'$ORIGIN/../genomic_b200'
 #include <cstdio>
 #include <cstdlib>
 #include <vector>
