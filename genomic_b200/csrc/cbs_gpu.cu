@@ -49,6 +49,9 @@ struct cbs_gpu_ctx {
     cudaStream_t own_stream = nullptr, stream = nullptr;
     std::string err;
     int* h_done = nullptr;  // mapped pinned
+    cudaGraphExec_t call_exec = nullptr;  // graph of a whole call: WHILE node around one scheduler round (run_cbs)
+    std::vector<unsigned char> call_key;  // the launch configuration it was captured with
+    unsigned long long round_launches = 0;
     int* d_done = nullptr;  // device alias of h_done
     DevBuf x, cur, gtab, factab, bbtab, unit_off, unit_ids, tasks, ring, act0, act1, chains, segs, splits, udraws, arena,
         rej, draws0, draws1, prep_task, items, item_prefix, edgeprep_task, edges, edge_prefix, gen_chain, means, seed312,
@@ -340,6 +343,15 @@ int run_cbs(cbs_gpu_ctx* c, const std::vector<long long>& off, const uint64_t* u
             const cbs_gpu_params* p, const uint64_t* mt_next312, bool weighted /* weights resident in c->wts */, Dev& hD,
             const ApiMode& api = ApiMode()) {
     cudaStream_t st = c->stream;
+    // CBS_GPU_DEBUG_SETUP=1: host wall clock of the set-up phases on stderr
+    const bool setup_debug = getenv("CBS_GPU_DEBUG_SETUP") != nullptr;
+    auto setup_t0 = std::chrono::steady_clock::now();
+    auto setup_mark = [&](const char* what) {
+        if (!setup_debug) return;
+        const auto now = std::chrono::steady_clock::now();
+        fprintf(stderr, "[setup] %s %.3f ms\n", what, std::chrono::duration<double, std::milli>(now - setup_t0).count());
+        setup_t0 = now;
+    };
     // profiling bit 2: every kernel on the one stream, so that per-launch event times do not overlap (roofline time base)
     cudaStream_t side[5], gen_stream = c->serial ? st : c->gen_stream;
     for (int k = 0; k < 5; ++k) side[k] = c->serial ? st : c->side[k];
@@ -400,9 +412,8 @@ int run_cbs(cbs_gpu_ctx* c, const std::vector<long long>& off, const uint64_t* u
     ENSURE(c, c->dev, sizeof(Dev));
     if (p->hybrid) ENSURE(c, c->tailp, sizeof(double) * 100 * (size_t)cap.list_cap);  // tailp quadrature terms per new segment
 
+    setup_mark("buffers");
     // arenas: sized from the workload, bounded by what the device has left
-    size_t free_b = 0, total_b = 0;
-    CUDA_TRY(c, cudaMemGetInfo(&free_b, &total_b));
     const long long per_perm_max = 3 * Nmax + 64;
     long long want_arena = std::min<long long>(24LL * 4096 * std::max<long long>(N, 1), 32LL << 30) / 8;
     want_arena = std::max<long long>(want_arena, 16 * per_perm_max);
@@ -425,7 +436,13 @@ int run_cbs(cbs_gpu_ctx* c, const std::vector<long long>& off, const uint64_t* u
     long long want_stream = shared_stream ? stream_ring + stream_mirror : 0;
     const long long env_arena = env_ll("CBS_GPU_ARENA_MB", 0);
     if (env_arena > 0) { want_arena = env_arena * (1LL << 20) / 8; if (mt && !shared_stream) want_draws = std::max<long long>(want_arena / 3, 8 * (Nmax + 312)); }
-    {
+    // (cudaMemGetInfo goes to the kernel driver and was measured to take tens of milliseconds now and then: it is asked only
+    // when a buffer has to grow, i.e. normally on the first call of a context)
+    const bool must_grow = (long long)(c->arena.cap / 8) < want_arena || (shared_stream && (long long)(c->stream_buf.cap / 8) < want_stream) ||
+                           (mt && !shared_stream && (long long)(std::min(c->draws0.cap, c->draws1.cap) / 8) < want_draws);
+    if (must_grow) {
+        size_t free_b = 0, total_b = 0;
+        CUDA_TRY(c, cudaMemGetInfo(&free_b, &total_b));
         const size_t have = c->arena.cap + c->draws0.cap + c->draws1.cap + c->stream_buf.cap;
         const double budget = c->mem_fraction * (double)(free_b + have);
         const double need = 8.0 * ((double)want_arena + 2.0 * (double)want_draws + (double)want_stream);
@@ -450,6 +467,7 @@ int run_cbs(cbs_gpu_ctx* c, const std::vector<long long>& off, const uint64_t* u
     cap.arena_cap = (long long)(c->arena.cap / 8);
     cap.draws_cap = (mt && !shared_stream) ? (long long)(std::min(c->draws0.cap, c->draws1.cap) / 8) : 0;
 
+    setup_mark("arenas");
     // ---- device state ---------------------------------------------------------------------
     memset(&hD, 0, sizeof(hD));
     hD.x = c->x.as<double>();
@@ -545,6 +563,7 @@ int run_cbs(cbs_gpu_ctx* c, const std::vector<long long>& off, const uint64_t* u
         CUDA_TRY(c, cudaStreamSynchronize(st));
     }
 
+    setup_mark("device state");
     // ---- scan kernel configuration ------------------------------------------------------------
     ScanLayout lay;
     lay.nb_max = block_count((int)std::max<long long>(Nmax, 1)) + 2;
@@ -590,91 +609,163 @@ int run_cbs(cbs_gpu_ctx* c, const std::vector<long long>& off, const uint64_t* u
                   : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&chain_occ, k_chain<false>, 32 * (1 + CP_STAT_WARPS), 0)) != cudaSuccess) { cudaGetLastError(); chain_occ = 4; }
     chain_occ = std::max(1, chain_occ);
 
+    setup_mark("launch configuration");
     // ---- rounds -------------------------------------------------------------------------------
     *c->h_done = 0;
-    const int G = 16;  // rounds per group; two groups are kept in flight, so a typical call (20-30 rounds) is enqueued up front and
-                       // host scheduling jitter cannot starve the GPU (the surplus rounds are empty launches, ~0.1 ms each)
+    const int G = (int)std::min<long long>(64, std::max<long long>(1, env_ll("CBS_GPU_ROUND_GROUP", 16)));
+    // rounds per group; two groups are kept in flight, so the host is 16-32 rounds ahead of the device and its scheduling
+    // jitter cannot starve the GPU; the rounds enqueued beyond the last one find D->done set and every kernel returns at once
     const bool debug = env_ll("CBS_GPU_DEBUG", 0) != 0;
     int groups_in_flight = 0, rounds = 0;
-    bool ahead_pending = false;
     int gi = 0;
-    for (;;) {
+    // One round = one fork-join of launches over the main stream, the side streams and the generator stream, and every launch
+    // configuration is fixed for the call.  The round is therefore captured ONCE as the body of a WHILE node of a CUDA graph
+    // whose condition the scheduler kernel keeps at 1 until the work list is empty: the whole call is one graph launch, the
+    // device runs exactly the rounds it needs and the host plays no part between them.  The instantiated graph is kept in
+    // the context and reused by later calls with the same configuration.  Event-timed profiling, CBS_GPU_DEBUG and
+    // CBS_GPU_GRAPH=0 enqueue the rounds from the host instead, in groups with a done flag polled in between.
+    cudaGraphConditionalHandle loop_handle = 0;
+    int looped = 0;
+    auto enqueue_round = [&]() {
+        bool ahead_pending = false;
+        // One round.  Dependencies: everything after k_sched; shuffles after the generator;
+        // k_prefix after the shuffles; k_scan after k_prefix and k_prep; next k_sched after all.
+        //   main : sched, gen, [shuffle classes], prefix, scan
+        //   side0: prep            side1: edgeprep, edgeperm
+        //   side2, side3: other shuffle classes      side4: shuffle of segments > 65535 markers
+        { LaunchTimer t(c, K_SCHED); k_sched<<<1, 256, 0, st>>>(dD, c->d_done, loop_handle, looped); }
+        cudaEventRecord(c->ev_sched, st);
+        cudaStreamWaitEvent(side[0], c->ev_sched, 0);
+        { LaunchTimer t(c, K_PREP, side[0]); k_tables<<<dim3(16, 64), 256, 0, side[0]>>>(dD); if (weighted) { k_wprep<<<c->sm_count * 8, 32, 0, side[0]>>>(dD); k_wtables<<<c->sm_count * 2, 256, 0, side[0]>>>(dD); c->launches++; if (p->hybrid) { k_wdelta<<<c->sm_count * 2, 32, 0, side[0]>>>(dD); c->launches++; } } else k_prep<<<c->sm_count * 8, 32, 0, side[0]>>>(dD); c->launches++; }
+        cudaEventRecord(c->ev_side[0], side[0]);
+        cudaStreamWaitEvent(side[1], c->ev_sched, 0);
+        { LaunchTimer t(c, K_EDGEPREP, side[1]); if (weighted) k_wedgeprep<<<c->sm_count * 4, 32, 0, side[1]>>>(dD); else k_edgeprep<<<c->sm_count * 4, 32, 0, side[1]>>>(dD); }
+        if (mt) {
+            LaunchTimer t(c, K_GEN);
+            if (shared_stream) {
+                k_gen_lead<<<1, 192, 0, st>>>(dD, 0);
+                if (hD.jump_polys) { k_gen_par<<<GEN_NSEG, 320, 0, st>>>(dD); c->launches++; }
+            } else k_gen<<<std::min(std::max(1, n_chains), c->sm_count * 4), 192, 0, st>>>(dD);
+        }
+        cudaEventRecord(c->ev_gen, st);
+        // the edge permutations read this round's draws (plan_edge asked the generator for them): after the generator
+        if (mt) cudaStreamWaitEvent(side[1], c->ev_gen, 0);
+        { LaunchTimer t(c, K_EDGEPERM, side[1]); if (weighted) k_wedgeperm<<<c->sm_count * 4, 128, 0, side[1]>>>(dD); else k_edgeperm<<<c->sm_count * 4, 128, 0, side[1]>>>(dD); }
+        cudaEventRecord(c->ev_side[1], side[1]);
+        if (mt && shared_stream && hD.jump_polys) {
+            // generate ahead for the next round, next to this round's shuffles and scan
+            cudaStreamWaitEvent(gen_stream, c->ev_gen, 0);
+            k_gen_lead<<<1, 192, 0, gen_stream>>>(dD, 1);
+            k_gen_par<<<GEN_NSEG, 320, 0, gen_stream>>>(dD);
+            c->launches += 2;
+            cudaEventRecord(c->ev_ahead, gen_stream);
+            ahead_pending = true;
+        }
+        // shuffles: classes alternate between the main stream and three side streams so that they run
+        // concurrently (each class is latency bound on its own); the longest present class goes first
+        bool used_side[5] = {false, false, false, false, false};
+        {
+            int slot = 0;
+            if (l2_shuffle_on) {
+                cudaStream_t ss = side[4];
+                cudaStreamWaitEvent(ss, c->ev_gen, 0);
+                used_side[4] = true;
+                LaunchTimer t(c, K_PERM, ss);
+                if (cl_R == 4 || cl_R == 8) launch_shuffle_cluster(dD, cl_R, SHUF_GLOBAL, cl_hbits, cl_grid, cl_smem, ss, mt);
+                else if (cl_R == 0) k_perm<<<c->sm_count * 8, 128, 0, ss>>>(dD);
+                if (cl2_grid) { launch_shuffle_cluster(dD, 2, SHUF_CL2, cl_hbits, cl2_grid, cl2_smem, ss, mt); c->launches++; }
+            }
+            for (int cls = SHUF_CL2 - 1; cls >= 0; --cls) {
+                if (!shuf_on[cls]) continue;
+                const int where = slot++ % 3;  // 0 = main stream, 1,2 = side[2], side[3]
+                cudaStream_t ss = where == 0 ? st : side[1 + where];
+                if (where != 0 && !used_side[1 + where]) { cudaStreamWaitEvent(ss, c->ev_gen, 0); used_side[1 + where] = true; }
+                LaunchTimer t(c, kShufTimer[cls], ss);
+                launch_shuffle(dD, cls, c->sm_count * shuf_occ[cls], ss, mt);
+            }
+        }
+        for (int k = 2; k < 5; ++k) if (used_side[k]) { cudaEventRecord(c->ev_side[k], side[k]); cudaStreamWaitEvent(st, c->ev_side[k], 0); }
+        { LaunchTimer t(c, K_PREFIX); if (weighted && p->hybrid) { k_wssq<<<c->sm_count * 8, 128, 0, st>>>(dD); c->launches++; } if (weighted) k_chain<true><<<c->sm_count * chain_occ, 32 * (1 + CP_STAT_WARPS), 0, st>>>(dD); else k_chain<false><<<c->sm_count * chain_occ, 32 * (1 + CP_STAT_WARPS), 0, st>>>(dD); }
+        cudaStreamWaitEvent(st, c->ev_side[0], 0);
+        { LaunchTimer t(c, K_SCAN);
+          if (weighted) {
+              k_wscan<1><<<c->sm_count * 4, 256, wscan_smem, st>>>(dD, lay.nb_max);   // observed rows, sliced over CTAs
+              k_wobs_fin<<<8, 128, 0, st>>>(dD);
+              k_wscan<0><<<c->sm_count * 4, 256, wscan_smem, st>>>(dD, lay.nb_max);   // permutation rows
+              c->launches += 2;
+          }
+          else k_scan<<<scan_grid, lay.warps * 32, scan_smem, st>>>(dD, lay); }
+        if (p->hybrid) {
+            if (weighted) k_whscan<<<c->sm_count * 4, 256, 0, st>>>(dD); else k_hscan<<<c->sm_count * 4, 256, 0, st>>>(dD);
+            k_tailp_terms<<<c->sm_count * 8, 128, 0, st>>>(dD, c->tailp.as<double>());
+            k_tailp_sum<<<c->sm_count, 64, 0, st>>>(dD, c->tailp.as<double>());
+            c->launches += 3;
+        }
+        cudaStreamWaitEvent(st, c->ev_side[1], 0);
+        if (ahead_pending) cudaStreamWaitEvent(st, c->ev_ahead, 0);  // the next k_sched plans on the extended stream
+    };
+    const bool use_graph = !c->profiling && !debug && env_ll("CBS_GPU_GRAPH", 1) != 0;
+    unsigned long long launches_per_round = 0;
+    cudaGraphExec_t call_exec = nullptr;
+    if (use_graph) {
+        std::vector<unsigned char> key;
+        auto put = [&](const void* v, size_t nbytes) { const unsigned char* b = (const unsigned char*)v; key.insert(key.end(), b, b + nbytes); };
+#define KEY_POD(v) put(&(v), sizeof(v))
+        const int flags[6] = {weighted ? 1 : 0, mt ? 1 : 0, shared_stream ? 1 : 0, hD.jump_polys ? 1 : 0, p->hybrid ? 1 : 0, l2_shuffle_on ? 1 : 0};
+        KEY_POD(dD); KEY_POD(st); KEY_POD(flags); KEY_POD(n_chains); KEY_POD(shuf_occ); KEY_POD(shuf_on); KEY_POD(cl_R); KEY_POD(cl_grid);
+        KEY_POD(cl2_grid); KEY_POD(cl_smem); KEY_POD(cl2_smem); KEY_POD(chain_occ); KEY_POD(scan_grid); KEY_POD(scan_smem);
+        KEY_POD(wscan_smem); KEY_POD(lay);
+        const void* tailp_ptr = c->tailp.p; KEY_POD(tailp_ptr);
+#undef KEY_POD
+        if (c->call_exec && key == c->call_key) {
+            call_exec = c->call_exec;
+            launches_per_round = c->round_launches;
+        } else {
+            if (c->call_exec) { cudaGraphExecDestroy(c->call_exec); c->call_exec = nullptr; }
+            const unsigned long long before = c->launches;
+            cudaGraph_t graph = nullptr;
+            cudaError_t ce = cudaGraphCreate(&graph, 0);
+            if (ce == cudaSuccess) ce = cudaGraphConditionalHandleCreate(&loop_handle, graph, 1, cudaGraphCondAssignDefault);
+            cudaGraphNodeParams wp = {cudaGraphNodeTypeConditional};
+            wp.conditional.handle = loop_handle;
+            wp.conditional.type = cudaGraphCondTypeWhile;
+            wp.conditional.size = 1;
+            cudaGraphNode_t wnode = nullptr;
+            if (ce == cudaSuccess) ce = cudaGraphAddNode(&wnode, graph, nullptr, 0, &wp);
+            if (ce == cudaSuccess) {
+                looped = 1;
+                ce = cudaStreamBeginCaptureToGraph(st, wp.conditional.phGraph_out[0], nullptr, nullptr, 0, cudaStreamCaptureModeRelaxed);
+                if (ce == cudaSuccess) {
+                    enqueue_round();
+                    ce = cudaStreamEndCapture(st, nullptr);
+                }
+                looped = 0;
+            }
+            launches_per_round = c->launches - before;
+            c->launches = before;
+            if (ce == cudaSuccess) ce = cudaGraphInstantiate(&call_exec, graph, 0);
+            if (graph) cudaGraphDestroy(graph);
+            if (ce != cudaSuccess) {
+                // (a driver without conditional nodes, or a capture that could not be closed: rounds are enqueued by the host)
+                cudaGetLastError();
+                call_exec = nullptr;
+                if (env_ll("CBS_GPU_GRAPH", 1) == 2) return fail(c, CBS_GPU_ERR_CUDA, std::string("call graph: ") + cudaGetErrorString(ce));
+            } else {
+                c->call_exec = call_exec;
+                c->call_key = key;
+                c->round_launches = launches_per_round;
+            }
+        }
+    }
+    setup_mark("graph");
+    if (call_exec) {
+        CUDA_TRY(c, cudaGraphLaunch(call_exec, st));
+        CUDA_TRY(c, cudaStreamSynchronize(st));
+        if (*(volatile int*)c->h_done == 0) return fail(c, CBS_GPU_ERR_CUDA, "the call graph ended before the scheduler was done");
+    }
+    for (; !call_exec;) {
         for (int r = 0; r < G; ++r) {
-            // One round.  Dependencies: everything after k_sched; shuffles after the generator;
-            // k_prefix after the shuffles; k_scan after k_prefix and k_prep; next k_sched after all.
-            //   main : sched, gen, [shuffle classes], prefix, scan
-            //   side0: prep            side1: edgeprep, edgeperm
-            //   side2, side3: other shuffle classes      side4: shuffle of segments > 65535 markers
-            if (ahead_pending) { cudaStreamWaitEvent(st, c->ev_ahead, 0); ahead_pending = false; }
-            { LaunchTimer t(c, K_SCHED); k_sched<<<1, 256, 0, st>>>(dD, c->d_done); }
-            cudaEventRecord(c->ev_sched, st);
-            cudaStreamWaitEvent(side[0], c->ev_sched, 0);
-            { LaunchTimer t(c, K_PREP, side[0]); k_tables<<<dim3(16, 64), 256, 0, side[0]>>>(dD); if (weighted) { k_wprep<<<c->sm_count * 8, 32, 0, side[0]>>>(dD); k_wtables<<<c->sm_count * 2, 256, 0, side[0]>>>(dD); c->launches++; if (p->hybrid) { k_wdelta<<<c->sm_count * 2, 32, 0, side[0]>>>(dD); c->launches++; } } else k_prep<<<c->sm_count * 8, 32, 0, side[0]>>>(dD); c->launches++; }
-            cudaEventRecord(c->ev_side[0], side[0]);
-            cudaStreamWaitEvent(side[1], c->ev_sched, 0);
-            { LaunchTimer t(c, K_EDGEPREP, side[1]); if (weighted) k_wedgeprep<<<c->sm_count * 4, 32, 0, side[1]>>>(dD); else k_edgeprep<<<c->sm_count * 4, 32, 0, side[1]>>>(dD); }
-            if (mt) {
-                LaunchTimer t(c, K_GEN);
-                if (shared_stream) {
-                    k_gen_lead<<<1, 192, 0, st>>>(dD, 0);
-                    if (hD.jump_polys) { k_gen_par<<<GEN_NSEG, 320, 0, st>>>(dD); c->launches++; }
-                } else k_gen<<<std::min(std::max(1, n_chains), c->sm_count * 4), 192, 0, st>>>(dD);
-            }
-            cudaEventRecord(c->ev_gen, st);
-            // the edge permutations read this round's draws (plan_edge asked the generator for them): after the generator
-            if (mt) cudaStreamWaitEvent(side[1], c->ev_gen, 0);
-            { LaunchTimer t(c, K_EDGEPERM, side[1]); if (weighted) k_wedgeperm<<<c->sm_count * 4, 128, 0, side[1]>>>(dD); else k_edgeperm<<<c->sm_count * 4, 128, 0, side[1]>>>(dD); }
-            cudaEventRecord(c->ev_side[1], side[1]);
-            if (mt && shared_stream && hD.jump_polys) {
-                // generate ahead for the next round, next to this round's shuffles and scan
-                cudaStreamWaitEvent(gen_stream, c->ev_gen, 0);
-                k_gen_lead<<<1, 192, 0, gen_stream>>>(dD, 1);
-                k_gen_par<<<GEN_NSEG, 320, 0, gen_stream>>>(dD);
-                c->launches += 2;
-                cudaEventRecord(c->ev_ahead, gen_stream);
-                ahead_pending = true;
-            }
-            // shuffles: classes alternate between the main stream and three side streams so that they run
-            // concurrently (each class is latency bound on its own); the longest present class goes first
-            bool used_side[5] = {false, false, false, false, false};
-            {
-                int slot = 0;
-                if (l2_shuffle_on) {
-                    cudaStream_t ss = side[4];
-                    cudaStreamWaitEvent(ss, c->ev_gen, 0);
-                    used_side[4] = true;
-                    LaunchTimer t(c, K_PERM, ss);
-                    if (cl_R == 4 || cl_R == 8) launch_shuffle_cluster(dD, cl_R, SHUF_GLOBAL, cl_hbits, cl_grid, cl_smem, ss, mt);
-                    else if (cl_R == 0) k_perm<<<c->sm_count * 8, 128, 0, ss>>>(dD);
-                    if (cl2_grid) { launch_shuffle_cluster(dD, 2, SHUF_CL2, cl_hbits, cl2_grid, cl2_smem, ss, mt); c->launches++; }
-                }
-                for (int cls = SHUF_CL2 - 1; cls >= 0; --cls) {
-                    if (!shuf_on[cls]) continue;
-                    const int where = slot++ % 3;  // 0 = main stream, 1,2 = side[2], side[3]
-                    cudaStream_t ss = where == 0 ? st : side[1 + where];
-                    if (where != 0 && !used_side[1 + where]) { cudaStreamWaitEvent(ss, c->ev_gen, 0); used_side[1 + where] = true; }
-                    LaunchTimer t(c, kShufTimer[cls], ss);
-                    launch_shuffle(dD, cls, c->sm_count * shuf_occ[cls], ss, mt);
-                }
-            }
-            for (int k = 2; k < 5; ++k) if (used_side[k]) { cudaEventRecord(c->ev_side[k], side[k]); cudaStreamWaitEvent(st, c->ev_side[k], 0); }
-            { LaunchTimer t(c, K_PREFIX); if (weighted && p->hybrid) { k_wssq<<<c->sm_count * 8, 128, 0, st>>>(dD); c->launches++; } if (weighted) k_chain<true><<<c->sm_count * chain_occ, 32 * (1 + CP_STAT_WARPS), 0, st>>>(dD); else k_chain<false><<<c->sm_count * chain_occ, 32 * (1 + CP_STAT_WARPS), 0, st>>>(dD); }
-            cudaStreamWaitEvent(st, c->ev_side[0], 0);
-            { LaunchTimer t(c, K_SCAN);
-              if (weighted) {
-                  k_wscan<1><<<c->sm_count * 4, 256, wscan_smem, st>>>(dD, lay.nb_max);   // observed rows, sliced over CTAs
-                  k_wobs_fin<<<8, 128, 0, st>>>(dD);
-                  k_wscan<0><<<c->sm_count * 4, 256, wscan_smem, st>>>(dD, lay.nb_max);   // permutation rows
-                  c->launches += 2;
-              }
-              else k_scan<<<scan_grid, lay.warps * 32, scan_smem, st>>>(dD, lay); }
-            if (p->hybrid) {
-                if (weighted) k_whscan<<<c->sm_count * 4, 256, 0, st>>>(dD); else k_hscan<<<c->sm_count * 4, 256, 0, st>>>(dD);
-                k_tailp_terms<<<c->sm_count * 8, 128, 0, st>>>(dD, c->tailp.as<double>());
-                k_tailp_sum<<<c->sm_count, 64, 0, st>>>(dD, c->tailp.as<double>());
-                c->launches += 3;
-            }
-            cudaStreamWaitEvent(st, c->ev_side[1], 0);
+            enqueue_round();
             ++rounds;
         }
         CUDA_TRY(c, cudaEventRecord(c->grp[gi], st));
@@ -701,6 +792,7 @@ int run_cbs(cbs_gpu_ctx* c, const std::vector<long long>& off, const uint64_t* u
     CUDA_TRY(c, cudaStreamSynchronize(st));
     CUDA_TRY(c, cudaGetLastError());
     CUDA_TRY(c, cudaMemcpy(&hD, dD, sizeof(Dev), cudaMemcpyDeviceToHost));
+    if (call_exec) c->launches += launches_per_round * (unsigned long long)std::max(1, hD.round);  // one body per scheduler round
     if (hD.error) {
         switch (hD.error) {
         case ERR_TASK_CAP: return fail(c, CBS_GPU_ERR_CAPACITY, "pending-segment pool exhausted (raise CBS_GPU_TASK_CAP)");
@@ -922,6 +1014,7 @@ void cbs_gpu_destroy(cbs_gpu_ctx* c) {
                       &c->diffs_sorted, &c->gout, &c->cubtmp, &c->flag, &c->goff, &c->stream_buf, &c->shuf, &c->jump, &c->tailp,
                       &c->wts, &c->rw, &c->cw, &c->ycur};
     for (DevBuf* b : bufs) if (b->p) cudaFree(b->p);
+    if (c->call_exec) cudaGraphExecDestroy(c->call_exec);
     if (c->h_done) cudaFreeHost(c->h_done);
     for (auto e : c->ev_pool) cudaEventDestroy(e);
     cudaEvent_t evs[] = {c->e0, c->e1, c->e2, c->e3, c->e4, c->grp[0], c->grp[1]};

@@ -74,15 +74,21 @@ __device__ void count_item_warp(Dev* D, const PermItem& it, int lane) {
     if (lane == 0) { t.cnt_exit = hit; t.cnt_nrej = running; }
 }
 
-__global__ void __launch_bounds__(256) k_sched(Dev* D, volatile int* host_done) {
+// `looped`: the round is the body of a WHILE node of a CUDA graph (cbs_gpu.cu run_cbs) and `loop` its condition: the
+// scheduler keeps it at 1 until the work list is empty (or an error is raised), so the whole call is one graph launch.
+__global__ void __launch_bounds__(256) k_sched(Dev* D, volatile int* host_done, cudaGraphConditionalHandle loop, int looped) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    if (D->done) return;
+    if (D->done) {
+        if (looped && threadIdx.x == 0) cudaGraphSetConditional(loop, 0);
+        return;
+    }
     for (int k = warp; k < D->n_items; k += 8) count_item_warp(D, D->items[k], lane);
     __syncthreads();
     if (threadIdx.x == 0) {
         Sched S(*D);
         S.run_round();
         if (D->done) { __threadfence_system(); *host_done = D->error ? -D->error : 1; }
+        if (looped) cudaGraphSetConditional(loop, D->done ? 0u : 1u);
     }
 }
 
@@ -143,25 +149,22 @@ __device__ void prep_warp(Dev* D, Task& t, int lane, double* buf) {
     double r[PREP_CHUNK / 32];
     if (!raw) {
         // CBS.cpp:985
+        // (the all-equal test rides on the loads of the mean pass: one pass over x less for the one warp)
         const double x0 = x[0];
         bool flat = true;
-        for (int i = lane; i < n; i += 32) if (!(fabs(x[i] - x0) < 1e-12)) flat = false;
-        flat = __all_sync(FULL, flat);
-        if (lane == 0) t.alleq = flat ? 1 : 0;
-        if (flat) return;
         // CBS.cpp:986 mean, sequential
         double s = 0.0;
 #pragma unroll
-        for (int q = 0; q < PREP_CHUNK / 32; ++q) { const int i = lane + 32 * q; r[q] = (i < n) ? x[i] : 0.0; }
+        for (int q = 0; q < PREP_CHUNK / 32; ++q) { const int i = lane + 32 * q; r[q] = (i < n) ? x[i] : x0; }
         for (int c0 = 0; c0 < n; c0 += PREP_CHUNK) {
             const int cnt = min(PREP_CHUNK, n - c0);
             __syncwarp();
 #pragma unroll
-            for (int q = 0; q < PREP_CHUNK / 32; ++q) buf[lane + 32 * q] = r[q];
+            for (int q = 0; q < PREP_CHUNK / 32; ++q) { buf[lane + 32 * q] = r[q]; if (!(fabs(r[q] - x0) < 1e-12)) flat = false; }
             __syncwarp();
             if (c0 + PREP_CHUNK < n) {
 #pragma unroll
-                for (int q = 0; q < PREP_CHUNK / 32; ++q) { const int i = c0 + PREP_CHUNK + lane + 32 * q; r[q] = (i < n) ? x[i] : 0.0; }
+                for (int q = 0; q < PREP_CHUNK / 32; ++q) { const int i = c0 + PREP_CHUNK + lane + 32 * q; r[q] = (i < n) ? x[i] : x0; }
             }
             if (lane == 0) {
                 int k = 0;
@@ -174,6 +177,9 @@ __device__ void prep_warp(Dev* D, Task& t, int lane, double* buf) {
                 if (k < cnt) s = s + buf[k];
             }
         }
+        flat = __all_sync(FULL, flat);
+        if (lane == 0) t.alleq = flat ? 1 : 0;
+        if (flat) return;
         s = shfl_d(s, 0);
         avg = s / (double)n;
     }
@@ -295,7 +301,9 @@ __global__ void __launch_bounds__(192) k_gen_lead(Dev* D, int ahead) {
     const long long len = D->stream_len;
     long long target = D->stream_target;
     if (ahead) {
-        target += GEN_AHEAD;
+        // a launch costs about the same for one segment or for all of them (the GF(2) combination of the segment heads
+        // dominates), so the ahead pass always goes for the whole span
+        target += D->jump_polys ? D->span_max : GEN_AHEAD;
         if (target > len + D->span_max) target = len + D->span_max;
     }
     if (target > D->stream_lo + D->stream_cap - 312) target = D->stream_lo + D->stream_cap - 312;  // the scheduler never asks for more
