@@ -4,7 +4,8 @@
 // sample, cna_segment.hpp:139-140):
 //   k_sm_compact  drop non-finite values, keep their indices            (smooth.cpp:135-141)
 //   k_sm_diffs    |v[i+1]-v[i]| of the finite subsequence               (smooth.cpp:37-39)
-//   (segmented ascending sort of the differences, cub::DeviceSegmentedSort)
+//   (ascending sort of the differences within each group: two radix sorts, by value and then -- stable -- by group;
+//    cub::DeviceSegmentedSort for very large calls)
 //   k_sm_sd       sum of the n_keep smallest squares in ascending order -> trimmed SD (:36-44,:144-148)
 //   k_sm_window   per finite marker: +-k window outlier test, median shrink (smooth.cpp:76-115)
 // The window kernel is the HBM-streaming part (24 B per marker); the sort only feeds one
@@ -61,14 +62,17 @@ __global__ void __launch_bounds__(256) k_sm_compact(const double* __restrict__ x
 
 // |differences| of the finite subsequence; slots beyond m-1 of a group are filled with +inf so
 // that a segmented sort over the fixed group extents leaves them at the end
+// gid (optional): the group of every slot, the second key of the two-pass radix sort (smooth_device)
 __global__ void k_sm_diffs(const double* __restrict__ fv, const long long* __restrict__ off, int n_groups,
-                           const SmoothGroupOut* __restrict__ gout, double* __restrict__ d) {
+                           const SmoothGroupOut* __restrict__ gout, double* __restrict__ d, int* __restrict__ gid) {
     for (int g = blockIdx.y; g < n_groups; g += gridDim.y) {
         const long long lo = off[g];
         const int n = (int)(off[g + 1] - lo);
         const int m = gout[g].m;
-        for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+        for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
             d[lo + i] = (i + 1 < m) ? fabs(fv[lo + i + 1] - fv[lo + i]) : __longlong_as_double(0x7ff0000000000000LL);
+            if (gid) gid[lo + i] = g;
+        }
     }
 }
 
