@@ -1325,32 +1325,58 @@ int cbs_gpu_segment_batch(cbs_gpu_ctx* c, const void* values, int dtype, int mem
     *out = nullptr;
     int want_lanes = (int)env_ll("CBS_GPU_LANES", 1);  // opt-in: measured no gain on B200 (persistent grids fill the SMs)
     const bool serial_stream = params && params->rng_mode == CBS_GPU_RNG_MT19937_64 && params->chain;
-    if (c->is_lane || want_lanes < 2 || !params || !unit_offsets || n_units < 2 * want_lanes || serial_stream ||
-        (dtype != CBS_GPU_F32 && dtype != CBS_GPU_F64))
+    bool splittable = !c->is_lane && params && unit_offsets && n_units >= 2 && !serial_stream && (dtype == CBS_GPU_F32 || dtype == CBS_GPU_F64);
+    if (splittable) {  // (malformed unit tables go to segment_batch_impl as they are: it reports them)
+        if (unit_offsets[0] != 0) splittable = false;
+        for (int u = 0; splittable && u < n_units; ++u) if (unit_offsets[u + 1] < unit_offsets[u]) splittable = false;
+    }
+    // Large cohorts are segmented in consecutive sub-batches of about CBS_GPU_CHUNK_MARKERS markers (default 48 M, some 25
+    // SNP6 samples): units are independent (Philox keys and chain == 0 streams do not depend on the neighbours), the cost per
+    // sample is flat between 4 and 64 samples per call and rises beyond (the one-thread scheduler walks thousands of live
+    // segments per round and the stream window has to span thousands of cursors: 58 ms per sample at 125 samples, 50 at 32).
+    const long long chunk_max = std::max<long long>(1024, env_ll("CBS_GPU_CHUNK_MARKERS", 48LL << 20));
+    const long long N_all = splittable ? (long long)unit_offsets[n_units] : 0;
+    const bool parallel = splittable && want_lanes >= 2 && n_units >= 2 * want_lanes;
+    if (!parallel && (!splittable || N_all <= chunk_max))
         return segment_batch_impl(c, values, dtype, memspace, unit_offsets, unit_ids, n_units, params, out);
     if (want_lanes > 4) want_lanes = 4;
     if (cudaSetDevice(c->device) != cudaSuccess) return fail(c, CBS_GPU_ERR_CUDA, "cudaSetDevice failed");
-    const int L = want_lanes;
-    while ((int)c->lanes.size() < L) {
-        cbs_gpu_ctx* child = nullptr;
-        const int ids[1] = {c->device};
-        if (cbs_gpu_create(ids, 1, &child) != CBS_GPU_OK) return fail(c, CBS_GPU_ERR_CUDA, "cannot create lane context");
-        child->is_lane = true;
-        c->lanes.push_back(child);
-    }
-    // contiguous ranges balanced by sum n^1.5 (the cost of the permutation scans)
-    std::vector<double> cost((size_t)n_units + 1, 0.0);
-    for (int u = 0; u < n_units; ++u) {
-        const double n = (double)(unit_offsets[u + 1] - unit_offsets[u]);
-        cost[u + 1] = cost[u] + (n > 0 ? n * std::sqrt(n) : 0.0);
-    }
-    std::vector<int> cut((size_t)L + 1, 0);
-    cut[L] = n_units;
-    for (int l = 1; l < L; ++l) {
-        const double target = cost[n_units] * l / L;
-        int u = cut[l - 1];
-        while (u < n_units && cost[u + 1] <= target) ++u;
-        cut[l] = std::max(u, cut[l - 1]);
+    int L = want_lanes;
+    std::vector<int> cut;
+    if (parallel) {
+        while ((int)c->lanes.size() < L) {
+            cbs_gpu_ctx* child = nullptr;
+            const int ids[1] = {c->device};
+            if (cbs_gpu_create(ids, 1, &child) != CBS_GPU_OK) return fail(c, CBS_GPU_ERR_CUDA, "cannot create lane context");
+            child->is_lane = true;
+            c->lanes.push_back(child);
+        }
+        // contiguous ranges balanced by sum n^1.5 (the cost of the permutation scans)
+        std::vector<double> cost((size_t)n_units + 1, 0.0);
+        for (int u = 0; u < n_units; ++u) {
+            const double n = (double)(unit_offsets[u + 1] - unit_offsets[u]);
+            cost[u + 1] = cost[u] + (n > 0 ? n * std::sqrt(n) : 0.0);
+        }
+        cut.assign((size_t)L + 1, 0);
+        cut[L] = n_units;
+        for (int l = 1; l < L; ++l) {
+            const double target = cost[n_units] * l / L;
+            int u = cut[l - 1];
+            while (u < n_units && cost[u + 1] <= target) ++u;
+            cut[l] = std::max(u, cut[l - 1]);
+        }
+    } else {
+        // sub-batches of equal marker counts, cut at unit boundaries
+        const int want = (int)std::min<long long>((N_all + chunk_max - 1) / chunk_max, n_units);
+        cut.push_back(0);
+        for (int k = 1; k < want; ++k) {
+            const long long target = N_all * k / want;
+            int u = cut.back();
+            while (u < n_units && (long long)unit_offsets[u + 1] <= target) ++u;
+            if (u > cut.back() && u < n_units) cut.push_back(u);
+        }
+        cut.push_back(n_units);
+        L = (int)cut.size() - 1;
     }
     // the input must be complete before other streams read it
     if (memspace == CBS_GPU_DEVICE) cudaStreamSynchronize(c->stream);
@@ -1361,24 +1387,40 @@ int cbs_gpu_segment_batch(cbs_gpu_ctx* c, const void* values, int dtype, int mem
     std::vector<std::vector<int64_t>> offs((size_t)L);
     std::vector<std::thread> th;
     const size_t esz = dtype == CBS_GPU_F32 ? 4 : 8;
+    std::vector<std::vector<double>> part_kms((size_t)L, std::vector<double>((size_t)K_COUNT, 0.0));
+    std::vector<unsigned long long> part_arcs((size_t)L, 0), part_slots((size_t)L, 0);
     for (int l = 0; l < L; ++l) {
-        cbs_gpu_ctx* child = c->lanes[l];
-        child->profiling = c->profiling; child->counting = c->counting; child->serial = c->serial;
-        child->mem_fraction = 0.80 / L;
         const int u0 = cut[l], u1 = cut[l + 1];
         offs[l].resize((size_t)(u1 - u0) + 1);
         for (int u = u0; u <= u1; ++u) offs[l][u - u0] = unit_offsets[u] - unit_offsets[u0];
         const char* base = (const char*)values + (size_t)unit_offsets[u0] * esz;
-        th.emplace_back([=, &rcs, &parts, &offs, &ids_all]() {
-            rcs[l] = segment_batch_impl(child, base, dtype, memspace, offs[l].data(), ids_all.data() + u0, u1 - u0, params, &parts[l]);
-        });
+        if (parallel) {
+            cbs_gpu_ctx* child = c->lanes[l];
+            child->profiling = c->profiling; child->counting = c->counting; child->serial = c->serial;
+            child->mem_fraction = 0.80 / L;
+            th.emplace_back([=, &rcs, &parts, &offs, &ids_all]() {
+                rcs[l] = segment_batch_impl(child, base, dtype, memspace, offs[l].data(), ids_all.data() + u0, u1 - u0, params, &parts[l]);
+            });
+        } else {
+            rcs[l] = segment_batch_impl(c, base, dtype, memspace, offs[l].data(), ids_all.data() + u0, u1 - u0, params, &parts[l]);
+            if (rcs[l] != CBS_GPU_OK) {
+                for (auto* p : parts) if (p) cbs_gpu_result_free(p);
+                return rcs[l];  // the message is already in c
+            }
+            for (int k = 0; k < K_COUNT; ++k) part_kms[l][k] = c->kms[k];
+            part_arcs[l] = c->last_arcs; part_slots[l] = c->last_slots;
+        }
     }
     for (auto& t : th) t.join();
-    for (int l = 0; l < L; ++l)
-        if (rcs[l] != CBS_GPU_OK) {
-            const std::string msg = cbs_gpu_last_error(c->lanes[l]);
-            for (auto* p : parts) if (p) cbs_gpu_result_free(p);
-            return fail(c, rcs[l], msg);
+    if (parallel)
+        for (int l = 0; l < L; ++l) {
+            if (rcs[l] != CBS_GPU_OK) {
+                const std::string msg = cbs_gpu_last_error(c->lanes[l]);
+                for (auto* p : parts) if (p) cbs_gpu_result_free(p);
+                return fail(c, rcs[l], msg);
+            }
+            for (int k = 0; k < K_COUNT; ++k) part_kms[l][k] = c->lanes[l]->kms[k];
+            part_arcs[l] = c->lanes[l]->last_arcs; part_slots[l] = c->lanes[l]->last_slots;
         }
     ResultOwner* R = new ResultOwner();
     memset(&R->pub, 0, sizeof(R->pub));
@@ -1397,12 +1439,19 @@ int cbs_gpu_segment_batch(cbs_gpu_ctx* c, const void* values, int dtype, int mem
         R->lengths.insert(R->lengths.end(), p->lengths, p->lengths + p->n_segments);
         R->means.insert(R->means.end(), p->means, p->means + p->n_segments);
         for (int64_t k = 0; k < p->n_splits; ++k) { cbs_gpu_split sp = p->splits[k]; sp.unit += u0; R->splits.push_back(sp); }
-        R->pub.rounds = std::max(R->pub.rounds, p->rounds);
         R->pub.perms_run += p->perms_run; R->pub.perm_elements += p->perm_elements; R->pub.kernel_launches += p->kernel_launches;
-        R->pub.ms_h2d = std::max(R->pub.ms_h2d, p->ms_h2d); R->pub.ms_smooth = std::max(R->pub.ms_smooth, p->ms_smooth);
-        R->pub.ms_segment = std::max(R->pub.ms_segment, p->ms_segment); R->pub.ms_d2h = std::max(R->pub.ms_d2h, p->ms_d2h);
-        for (int k = 0; k < K_COUNT; ++k) c->kms[k] += c->lanes[l]->kms[k];
-        c->last_arcs += c->lanes[l]->last_arcs; c->last_slots += c->lanes[l]->last_slots;
+        if (parallel) {  // lanes run side by side, sub-batches one after the other
+            R->pub.rounds = std::max(R->pub.rounds, p->rounds);
+            R->pub.ms_h2d = std::max(R->pub.ms_h2d, p->ms_h2d); R->pub.ms_smooth = std::max(R->pub.ms_smooth, p->ms_smooth);
+            R->pub.ms_segment = std::max(R->pub.ms_segment, p->ms_segment); R->pub.ms_d2h = std::max(R->pub.ms_d2h, p->ms_d2h);
+            R->pub.ms_call = std::max(R->pub.ms_call, p->ms_call);
+        } else {
+            R->pub.rounds += p->rounds;
+            R->pub.ms_h2d += p->ms_h2d; R->pub.ms_smooth += p->ms_smooth; R->pub.ms_segment += p->ms_segment; R->pub.ms_d2h += p->ms_d2h;
+            R->pub.ms_call += p->ms_call;
+        }
+        for (int k = 0; k < K_COUNT; ++k) c->kms[k] += part_kms[l][k];
+        c->last_arcs += part_arcs[l]; c->last_slots += part_slots[l];
     }
     // empty leading/trailing units keep monotone offsets
     for (int u = 0; u < n_units; ++u) if (R->seg_offsets[u + 1] < R->seg_offsets[u]) R->seg_offsets[u + 1] = R->seg_offsets[u];

@@ -317,6 +317,31 @@ def test_small_stream_window(oracle, monkeypatch):
         c.close()
 
 
+def test_sub_batches_of_a_large_call(oracle, monkeypatch):
+    """Calls beyond CBS_GPU_CHUNK_MARKERS markers are segmented in consecutive sub-batches (cbs_gpu.cu
+    cbs_gpu_segment_batch) and merged: with the limit forced down to a few thousand markers the result -- segments, means,
+    draws, split log, smoothing included -- is still the oracle's for Philox keys (global unit ids) and for MT replay with one
+    engine per unit; MT replay with ONE chained engine is never split."""
+    monkeypatch.setenv("CBS_GPU_CHUNK_MARKERS", "4000")
+    c = genomic_b200.Context(0)
+    try:
+        rng = np.random.default_rng(77)
+        units = [f32(rng.normal(0, 0.2, n)) for n in (1500, 2500, 300, 0, 5200, 900, 2100, 40, 3300)]
+        units[1][1000:] += 0.5
+        units[4][2000:2600] -= 0.6
+        units[8][::500] += 3.0  # outliers for the smoother
+        vals, off = pack(units)
+        for kind, chain in ((1, False), (0, False), (0, True)):
+            p = SegParams(nperm=400, alpha=0.01, do_smooth=True, rng_kind=kind, chain=chain, seed=11)
+            got, want = check_batch(c, oracle, vals, off, p)
+            monkeypatch.delenv("CBS_GPU_CHUNK_MARKERS")
+            whole, _ = check_batch(c, oracle, vals, off, p)  # one call for all units
+            monkeypatch.setenv("CBS_GPU_CHUNK_MARKERS", "4000")
+            assert (got.rounds > whole.rounds) == (not chain)  # the rounds of the sub-batches add up
+    finally:
+        c.close()
+
+
 def test_stress_50k_segments_replay(ctx, oracle):
     """BASELINE configs[4] in small: units of exactly 50,000 markers, deterministic MT replay.  (i) pure null: the
     permutation loop stops at the early exit; (ii) a shift at 25,000 small enough (t ~ 5.6 < 7) that fndcpt does not
