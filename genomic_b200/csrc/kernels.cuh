@@ -763,15 +763,17 @@ __global__ void __launch_bounds__(128) k_perm(Dev* D) {
 // sequential DADD chain per permutation (the reference's order, CBS.cpp:83-90, hence identical rounding), and writes
 // the row's statistics for the scan next to it: per block of the reference's sqrt(n) blocks the extrema with their FIRST
 // occurrence (CBS.cpp:88-94), and per aligned run of 32 prefix sums the extrema in single precision rounded outwards.
-// A CTA is a PAIR of warps that owns CHAIN_Q = 4 consecutive permutations of a batch:
-//   warp A  stages chunks of the four rows in shared memory (the next chunk is already in flight in registers); lanes
-//           0, 8, 16, 24 each walk one row at the DADD latency (8 cycles per marker on B200), so one warp instruction
-//           advances four chains and nothing else is ever on their critical path;
-//   warp B  takes each finished chunk: stores it coalesced and computes the statistics, eight lanes per row (block
-//           extrema reduced with redux.sync on order-preserving keys), while A is already summing the next chunk.
+// A CTA is one summing warp and CP_STAT_WARPS = 4 statistics warps, and owns CHAIN_Q = 4 consecutive permutations of a batch:
+//   warp A   stages chunks of the four rows in shared memory (the next chunk is already in flight in registers); lanes
+//            0, 8, 16, 24 each walk one row at the DADD latency (8 cycles per marker on B200), so one warp instruction
+//            advances four chains and nothing else is ever on their critical path;
+//   warps B  take each finished chunk, one warp per row: store it coalesced and compute the statistics (block extrema
+//            reduced with redux.sync on order-preserving keys), while A is already summing the next chunk.  One
+//            statistics warp for all four rows (the first form of this layout) could not keep up with the summing warp.
 // The chunks go through a ring of CP_SLOTS buffers; the hand-over is two monotone chunk counters in shared memory.
 // Round 1 gave a permutation one warp that did both jobs in turn with one active lane: ~5.4 warp instructions per
-// marker, issue bound at a fraction of the FP64 pipe; this layout needs ~1.3.
+// marker, issue bound at a fraction of the FP64 pipe; here the summing warp issues ~1.3 per marker and the
+// statistics warps, on the other schedulers of the SM, the rest (4.2 in total, profiles/r02_ncu_round4_final.md).
 // ------------------------------------------------------------------------------------
 #define CP_CHUNK 256
 #define CP_ROW (CP_CHUNK + 4)  // doubles: +4 puts the four rows on different banks for the 128-bit accesses of the summing lanes

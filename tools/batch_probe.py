@@ -8,10 +8,10 @@ import genomic_b200
 from genomic_b200 import Params, RNG_MT19937_64, synth
 ctx = genomic_b200.Context(0)
 vals, off, lab, ids = synth.cohort([0], scale=1.0)
-cfgs = [(256, 4096), (256, 8192), (256, 16384), (320, 8192)]
+cfgs = [(256, 4096), (256, 10000), (192, 4096), (384, 4096), (128, 4096), (256, 2048)]
 ts = {c: [] for c in cfgs}
 ref = None
-for rep in range(16):
+for rep in range(10):
     for c in cfgs:
         gp = Params(nperm=10000, rng_mode=RNG_MT19937_64, chain=False, seed=1, first_batch=c[0], max_batch=c[1])
         t0 = time.perf_counter()
