@@ -157,7 +157,7 @@ EXPORTED_SYMBOLS = (
     "cbs_gpu_tmaxp", "cbs_gpu_measure_fp64", "cbs_gpu_last_kernel_ms", "cbs_gpu_set_profiling",
     "cbs_gpu_last_arc_evals", "cbs_gpu_selftest", "cbs_gpu_segment_weighted", "cbs_gpu_segment_weighted_batch",
     "cbs_gpu_fndcpt", "cbs_gpu_wfindcpt", "cbs_gpu_tpermp", "cbs_gpu_wtmaxo", "cbs_gpu_xperm", "cbs_gpu_htmaxp",
-    "cbs_gpu_tailp", "cbs_gpu_btmax", "cbs_gpu_btailp",
+    "cbs_gpu_tailp", "cbs_gpu_btmax", "cbs_gpu_btailp", "cbs_gpu_summarize_cn",
 )
 
 
@@ -450,3 +450,29 @@ class Context:
         out = C.c_double()
         self._check(self.lib.cbs_gpu_btailp(self.h, C.c_double(b), m, ng, C.c_double(tol), C.byref(out)))
         return out.value
+
+    def summarize_cn(self, seg_offsets, start, end, value, direction, cutoff, pos_offsets=None, positions=None):
+        """cngpld::summarize_cn (lib/cngpld/summarize.cpp:77-100) for every unit of a segment table.
+        Returns (out_offsets [n_units+1], positions uint64, values float64)."""
+        so = np.ascontiguousarray(seg_offsets, np.int64)
+        n_units = len(so) - 1
+        st = np.ascontiguousarray(start, np.uint64)
+        en = np.ascontiguousarray(end, np.uint64)
+        va = np.ascontiguousarray(value, np.float32)
+        if positions is not None:
+            po = np.ascontiguousarray(pos_offsets, np.int64)
+            ps = np.ascontiguousarray(positions, np.uint64)
+            cap = int(po[-1]) if len(po) else 0
+            po_p, ps_p = po.ctypes.data_as(C.c_void_p), ps.ctypes.data_as(C.c_void_p)
+        else:
+            cap = 2 * len(st)
+            po_p = ps_p = None
+        out_off = np.zeros(n_units + 1, np.int64)
+        out_pos = np.zeros(max(cap, 1), np.uint64)
+        out_val = np.zeros(max(cap, 1), np.float64)
+        self._check(self.lib.cbs_gpu_summarize_cn(
+            self.h, so.ctypes.data_as(C.c_void_p), n_units, st.ctypes.data_as(C.c_void_p), en.ctypes.data_as(C.c_void_p),
+            va.ctypes.data_as(C.c_void_p), int(direction), C.c_double(cutoff), po_p, ps_p, out_off.ctypes.data_as(C.c_void_p),
+            out_pos.ctypes.data_as(C.c_void_p), out_val.ctypes.data_as(C.c_void_p)))
+        n = int(out_off[-1])
+        return out_off, out_pos[:n].copy(), out_val[:n].copy()

@@ -55,7 +55,7 @@ struct cbs_gpu_ctx {
     int* d_done = nullptr;  // device alias of h_done
     DevBuf x, cur, gtab, factab, bbtab, unit_off, unit_ids, tasks, ring, act0, act1, chains, segs, splits, udraws, arena,
         rej, draws0, draws1, prep_task, items, item_prefix, edgeprep_task, edges, edge_prefix, gen_chain, means, seed312,
-        dev, staging, fv, fidx, flab, lab, diffs, diffs_sorted, sm_keys, sm_gid, gout, cubtmp, flag, goff, stream_buf, shuf, jump, tailp,
+        dev, staging, fv, fidx, flab, lab, diffs, diffs_sorted, sm_keys, sm_gid, cn_scratch, gout, cubtmp, flag, goff, stream_buf, shuf, jump, tailp,
         wts, rw, cw, ycur;  // weighted CBS
     bool jump_ready = false;
     // lanes: a call with independent units is split into contiguous unit ranges that run as separate
@@ -1039,7 +1039,7 @@ void cbs_gpu_destroy(cbs_gpu_ctx* c) {
                       &c->act1, &c->chains, &c->segs, &c->splits, &c->udraws, &c->arena, &c->rej, &c->draws0, &c->draws1,
                       &c->prep_task, &c->items, &c->item_prefix, &c->edgeprep_task, &c->edges, &c->edge_prefix, &c->gen_chain,
                       &c->means, &c->seed312, &c->dev, &c->staging, &c->fv, &c->fidx, &c->flab, &c->lab, &c->diffs,
-                      &c->diffs_sorted, &c->sm_keys, &c->sm_gid, &c->gout, &c->cubtmp, &c->flag, &c->goff, &c->stream_buf, &c->shuf, &c->jump, &c->tailp,
+                      &c->diffs_sorted, &c->sm_keys, &c->sm_gid, &c->cn_scratch, &c->gout, &c->cubtmp, &c->flag, &c->goff, &c->stream_buf, &c->shuf, &c->jump, &c->tailp,
                       &c->wts, &c->rw, &c->cw, &c->ycur};
     for (DevBuf* b : bufs) if (b->p) cudaFree(b->p);
     if (c->call_exec) cudaGraphExecDestroy(c->call_exec);
@@ -1863,6 +1863,70 @@ int cbs_gpu_btailp(cbs_gpu_ctx* c, double b, int32_t m, int32_t ng, double tol, 
 void cbs_gpu_result_free(cbs_gpu_result* r) {
     if (!r) return;
     delete reinterpret_cast<ResultOwner*>(r);  // pub is the first member
+}
+
+int cbs_gpu_summarize_cn(cbs_gpu_ctx* c, const int64_t* seg_offsets, int32_t n_units, const uint64_t* seg_start,
+                         const uint64_t* seg_end, const float* seg_value, int32_t direction, double cutoff,
+                         const int64_t* pos_offsets, const uint64_t* positions, int64_t* out_offsets, uint64_t* out_pos,
+                         double* out_value) {
+    if (!c) return CBS_GPU_ERR_INVALID;
+    if (direction != 1 && direction != -1) return fail(c, CBS_GPU_ERR_INVALID, "direction must be 1 or -1.");  // summarize.cpp:49-51
+    if (n_units < 0 || !seg_offsets || !out_offsets) return fail(c, CBS_GPU_ERR_INVALID, "bad segment table");
+    if (seg_offsets[0] != 0) return fail(c, CBS_GPU_ERR_INVALID, "seg_offsets[0] must be 0");
+    for (int u = 0; u < n_units; ++u) if (seg_offsets[u + 1] < seg_offsets[u]) return fail(c, CBS_GPU_ERR_INVALID, "seg_offsets must be non-decreasing");
+    const long long S = seg_offsets[n_units];
+    if (S > 0 && (!seg_start || !seg_end || !seg_value)) return fail(c, CBS_GPU_ERR_INVALID, "segment columns are NULL");
+    if (positions && !pos_offsets) return fail(c, CBS_GPU_ERR_INVALID, "positions without pos_offsets");
+    // output positions per unit: given, or the sorted distinct starts and ends (summarize.cpp:24-36; a few per unit: host)
+    std::vector<long long> poff((size_t)n_units + 1, 0);
+    std::vector<unsigned long long> pos;
+    for (int u = 0; u < n_units; ++u) {
+        if (positions) {
+            if (pos_offsets[u + 1] < pos_offsets[u] || pos_offsets[0] != 0) return fail(c, CBS_GPU_ERR_INVALID, "pos_offsets must start at 0 and be non-decreasing");
+            pos.insert(pos.end(), positions + pos_offsets[u], positions + pos_offsets[u + 1]);
+        } else {
+            const size_t at = pos.size();
+            for (long long k = seg_offsets[u]; k < seg_offsets[u + 1]; ++k) { pos.push_back(seg_start[k]); pos.push_back(seg_end[k]); }
+            std::sort(pos.begin() + (long)at, pos.end());
+            pos.erase(std::unique(pos.begin() + (long)at, pos.end()), pos.end());
+        }
+        poff[(size_t)u + 1] = (long long)pos.size();
+        // the reference meets a segment with start > end while it scans for the first position of the unit (summarize.cpp:59-61)
+        if (poff[(size_t)u + 1] > poff[(size_t)u])
+            for (long long k = seg_offsets[u]; k < seg_offsets[u + 1]; ++k)
+                if (seg_start[k] > seg_end[k]) return fail(c, CBS_GPU_ERR_INVALID, "Segment start is greater than end.");
+    }
+    for (int u = 0; u <= n_units; ++u) out_offsets[u] = poff[(size_t)u];
+    const long long P = poff[(size_t)n_units];
+    if (P == 0) return CBS_GPU_OK;
+    if (!out_pos || !out_value) return fail(c, CBS_GPU_ERR_INVALID, "output arrays are NULL");
+    if (cudaSetDevice(c->device) != cudaSuccess) return fail(c, CBS_GPU_ERR_CUDA, "cudaSetDevice failed");
+    cudaStream_t st = c->stream;
+    std::vector<long long> soff((size_t)n_units + 1);
+    for (int u = 0; u <= n_units; ++u) soff[(size_t)u] = seg_offsets[u];
+    // one scratch buffer: start | end | positions (8 B each), offsets, values (4 B), output
+    const size_t b_start = 0, b_end = b_start + 8 * (size_t)S, b_pos = b_end + 8 * (size_t)S, b_soff = b_pos + 8 * (size_t)P,
+                 b_poff = b_soff + 8 * ((size_t)n_units + 1), b_out = b_poff + 8 * ((size_t)n_units + 1), b_val = b_out + 8 * (size_t)P;
+    ENSURE(c, c->cn_scratch, b_val + 4 * (size_t)S + 16);
+    char* base = (char*)c->cn_scratch.p;
+    if (S) {
+        CUDA_TRY(c, cudaMemcpyAsync(base + b_start, seg_start, 8 * (size_t)S, cudaMemcpyHostToDevice, st));
+        CUDA_TRY(c, cudaMemcpyAsync(base + b_end, seg_end, 8 * (size_t)S, cudaMemcpyHostToDevice, st));
+        CUDA_TRY(c, cudaMemcpyAsync(base + b_val, seg_value, 4 * (size_t)S, cudaMemcpyHostToDevice, st));
+    }
+    CUDA_TRY(c, cudaMemcpyAsync(base + b_pos, pos.data(), 8 * (size_t)P, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(c, cudaMemcpyAsync(base + b_soff, soff.data(), 8 * ((size_t)n_units + 1), cudaMemcpyHostToDevice, st));
+    CUDA_TRY(c, cudaMemcpyAsync(base + b_poff, poff.data(), 8 * ((size_t)n_units + 1), cudaMemcpyHostToDevice, st));
+    k_summarize_cn<<<(unsigned)std::min<long long>((P + 127) / 128, c->sm_count * 16), 128, 0, st>>>(
+        (const unsigned long long*)(base + b_start), (const unsigned long long*)(base + b_end), (const float*)(base + b_val),
+        (const long long*)(base + b_soff), (const long long*)(base + b_poff), n_units, (const unsigned long long*)(base + b_pos),
+        direction, cutoff, (double*)(base + b_out));
+    c->launches++;
+    CUDA_TRY(c, cudaGetLastError());
+    CUDA_TRY(c, cudaMemcpyAsync(out_value, base + b_out, 8 * (size_t)P, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(c, cudaStreamSynchronize(st));
+    for (long long i = 0; i < P; ++i) out_pos[i] = pos[(size_t)i];
+    return CBS_GPU_OK;
 }
 
 int cbs_gpu_smooth(cbs_gpu_ctx* c, const double* values, const int32_t* chrom, int64_t n, int32_t smooth_region,

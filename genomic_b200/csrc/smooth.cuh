@@ -160,6 +160,30 @@ __global__ void __launch_bounds__(256) k_sm_window(const double* __restrict__ fv
     }
 }
 
+// cngpld::summarize_cn (lib/cngpld/summarize.cpp:41-75): thread per output position; `pos_off` delimits the positions of a
+// unit, `seg_off` its segments.  Overlap and altered counts and the sum follow the reference's loop order.
+__global__ void k_summarize_cn(const unsigned long long* __restrict__ start, const unsigned long long* __restrict__ end,
+                               const float* __restrict__ value, const long long* __restrict__ seg_off,
+                               const long long* __restrict__ pos_off, int n_units, const unsigned long long* __restrict__ pos,
+                               int direction, double cutoff, double* __restrict__ out) {
+    const long long total = pos_off[n_units];
+    for (long long p = blockIdx.x * (long long)blockDim.x + threadIdx.x; p < total; p += (long long)gridDim.x * blockDim.x) {
+        int lo = 0, hi = n_units;  // unit u with pos_off[u] <= p < pos_off[u+1]
+        while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (pos_off[mid] <= p) lo = mid; else hi = mid; }
+        const unsigned long long q = pos[p];
+        long long overlap = 0, altered = 0;
+        double sum = 0.0;
+        for (long long k = seg_off[lo]; k < seg_off[lo + 1]; ++k) {
+            if (start[k] <= q && q <= end[k]) {
+                ++overlap;
+                const double adj = (double)direction * (double)value[k];
+                if (adj > cutoff) { sum += exp(adj); ++altered; }
+            }
+        }
+        out[p] = altered == 0 ? 0.0 : sum / (double)overlap;
+    }
+}
+
 __global__ void k_count_nonfinite(const double* x, long long n, int* flag) {
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
         if (!isfinite(x[i])) *flag = 1;

@@ -300,4 +300,43 @@ inline SegmentationResult segment_weighted(const std::vector<double>& x, const s
 
 }  // namespace cbs_gpu
 
+// cngpld::summarize_cn (lib/cngpld/summarize.hpp:11-34) on the segments of one sample and chromosome.  The reference takes
+// a SegmentedSampleSet, a sample name and a chromosome index and looks the segments up; here the caller passes them
+// (`Seg` needs the members start, end and value of cna::Segment<rvalue>, lib/Segment.hpp).
+namespace cngpld_gpu {
+
+struct CNSummaryPoint {
+    unsigned long pos;
+    double value;
+};
+typedef std::vector<CNSummaryPoint> CNSummary;
+
+template <class Seg>
+CNSummary summarize_cn(const std::vector<Seg>& segments, int direction, double cutoff,
+                       const std::vector<unsigned long>* positions = nullptr) {
+    if (direction != 1 && direction != -1) throw std::invalid_argument("direction must be 1 or -1.");
+    if (positions && positions->empty()) return CNSummary();  // (an empty array is not "default positions" to the C entry)
+    cbs_gpu::Context& c = cbs_gpu::default_context();
+    const size_t n = segments.size();
+    std::vector<uint64_t> start(n), end(n);
+    std::vector<float> value(n);
+    for (size_t i = 0; i < n; ++i) { start[i] = segments[i].start; end[i] = segments[i].end; value[i] = (float)segments[i].value; }
+    const int64_t seg_off[2] = {0, (int64_t)n};
+    std::vector<uint64_t> pos_in;
+    int64_t pos_off[2] = {0, 0};
+    if (positions) { pos_in.assign(positions->begin(), positions->end()); pos_off[1] = (int64_t)pos_in.size(); }
+    const size_t cap = positions ? pos_in.size() : 2 * n;
+    std::vector<uint64_t> out_pos(cap + 1);
+    std::vector<double> out_val(cap + 1);
+    int64_t out_off[2] = {0, 0};
+    c.check(cbs_gpu_summarize_cn(c.get(), seg_off, 1, start.data(), end.data(), value.data(), direction, cutoff,
+                                 positions ? pos_off : nullptr, positions ? pos_in.data() : nullptr, out_off, out_pos.data(),
+                                 out_val.data()));
+    CNSummary out((size_t)out_off[1]);
+    for (size_t i = 0; i < out.size(); ++i) { out[i].pos = (unsigned long)out_pos[i]; out[i].value = out_val[i]; }
+    return out;
+}
+
+}  // namespace cngpld_gpu
+
 #endif

@@ -194,6 +194,21 @@ int cbs_gpu_tailp(cbs_gpu_ctx* ctx, double b, double delta, int32_t m, int32_t n
 int cbs_gpu_btmax(cbs_gpu_ctx* ctx, const double* x, int32_t n, double* out);
 int cbs_gpu_btailp(cbs_gpu_ctx* ctx, double b, int32_t m, int32_t ng, double tol, double* out);
 
+/* ---- downstream of the segment table ---------------------------------
+ * cngpld::summarize_cn (lib/cngpld/summarize.hpp:28-34, summarize.cpp:77-100) for every unit (one chromosome of one
+ * sample) of a segment table: at every position -- by default the sorted distinct segment starts and ends of the unit
+ * (summarize.cpp:24-36) -- the sum of exp(direction * value) over the overlapping segments with direction * value > cutoff,
+ * divided by the number of overlapping segments (0 if none is altered; summarize.cpp:41-75).
+ * seg_offsets: [n_units+1] into seg_start / seg_end / seg_value (float = the reference's rvalue).
+ * positions == NULL: default positions; out_offsets [n_units+1], out_pos / out_value need room for 2 * n_segments.
+ * positions != NULL: pos_offsets [n_units+1] into positions; out_pos / out_value need room for pos_offsets[n_units]
+ * (out_pos receives a copy).  direction must be 1 or -1 and every segment needs start <= end (INVALID otherwise, the
+ * reference's std::invalid_argument). */
+int cbs_gpu_summarize_cn(cbs_gpu_ctx* ctx, const int64_t* seg_offsets, int32_t n_units, const uint64_t* seg_start,
+                         const uint64_t* seg_end, const float* seg_value, int32_t direction, double cutoff,
+                         const int64_t* pos_offsets, const uint64_t* positions, int64_t* out_offsets, uint64_t* out_pos,
+                         double* out_value);
+
 /* host-only self test (needs no device): 0 if the MT19937-64 jump-ahead polynomials reproduce
  * sequential generation */
 int cbs_gpu_selftest(void);

@@ -220,6 +220,28 @@ class Oracle:
         return r
 
     # -- kernels ------------------------------------------------------------
+    def summarize_cn(self, start, end, value, direction, cutoff, positions=None):
+        """cngpld::summarize_cn for the segments of one sample and chromosome (oracle/cngpld_oracle.c).
+        Returns (positions uint64, values float64); raises ValueError where the reference throws invalid_argument."""
+        L = self.lib
+        L.orc_summarize_cn.restype = C.c_longlong
+        st = np.ascontiguousarray(start, np.uint64)
+        en = np.ascontiguousarray(end, np.uint64)
+        va = np.ascontiguousarray(value, np.float32)
+        n = len(st)
+        ps = None if positions is None else np.ascontiguousarray(positions, np.uint64)
+        cap = max(2 * n, 0 if ps is None else len(ps), 1)
+        out_pos = np.zeros(cap, np.uint64)
+        out_val = np.zeros(cap, np.float64)
+        got = L.orc_summarize_cn(st.ctypes.data_as(C.c_void_p), en.ctypes.data_as(C.c_void_p), va.ctypes.data_as(C.c_void_p),
+                                 C.c_longlong(n), C.c_int(direction), C.c_double(cutoff),
+                                 None if ps is None else ps.ctypes.data_as(C.c_void_p),
+                                 C.c_longlong(0 if ps is None else len(ps)), out_pos.ctypes.data_as(C.c_void_p),
+                                 out_val.ctypes.data_as(C.c_void_p))
+        if got < 0:
+            raise ValueError("invalid_argument")
+        return out_pos[:got].copy(), out_val[:got].copy()
+
     def tmaxo(self, x, tss, al0=2, ibin=False):
         x = np.ascontiguousarray(x, dtype=np.float64)
         r = self.lib.orc_tmaxo(_dp(x), len(x), tss, al0, int(ibin))

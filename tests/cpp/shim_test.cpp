@@ -171,6 +171,27 @@ int main() {
         for (size_t i = 0; i < v.size(); ++i) CHECK((got[i] == want[i]) || (std::isnan(got[i]) && std::isnan(want[i])));
         CHECK(got[100] != v[100]);
     }
+    {   // cngpld::summarize_cn, tests/cngpld_test.cpp:46-83: cases 1 (amp and del) and 4 (explicit positions, empty overlap)
+        struct Seg { unsigned long start, end; float value; };
+        const std::vector<Seg> c1 = {{10, 25, 0.2f}, {20, 35, 0.8f}, {30, 40, 0.1f}};
+        const auto amp = cngpld_gpu::summarize_cn(c1, 1, 0.5);
+        const unsigned long p1[6] = {10, 20, 25, 30, 35, 40};
+        const double v1[6] = {0, 1.11277046424623, 1.11277046424623, 1.11277046424623, 1.11277046424623, 0};
+        CHECK(amp.size() == 6);
+        for (size_t i = 0; i < amp.size() && i < 6; ++i) { CHECK(amp[i].pos == p1[i]); CHECK(std::fabs(amp[i].value - v1[i]) <= 1e-7 * v1[i]); }
+        for (const auto& pt : cngpld_gpu::summarize_cn(c1, -1, 0.5)) CHECK(pt.value == 0.0);
+        const std::vector<Seg> c4 = {{100, 120, 1.0f}, {200, 220, -1.0f}};
+        const std::vector<unsigned long> at = {50, 100, 120, 150, 200, 220, 250};
+        const auto e4 = cngpld_gpu::summarize_cn(c4, 1, 0.5, &at);
+        const double v4[7] = {0, 2.71828182845905, 2.71828182845905, 0, 0, 0, 0};
+        CHECK(e4.size() == 7);
+        for (size_t i = 0; i < e4.size() && i < 7; ++i) { CHECK(e4[i].pos == at[i]); CHECK(std::fabs(e4[i].value - v4[i]) <= 1e-7 * v4[i]); }
+        bool threw = false;
+        try { cngpld_gpu::summarize_cn(c1, 2, 0.5); } catch (const std::invalid_argument&) { threw = true; }
+        CHECK(threw);
+        const std::vector<unsigned long> none;
+        CHECK(cngpld_gpu::summarize_cn(c1, 1, 0.5, &none).empty());
+    }
     std::printf(fails ? "shim_test: %d failures\n" : "shim_test: ok\n", fails);
     return fails ? 1 : 0;
 }

@@ -218,3 +218,22 @@ def test_segment_weighted_hybrid_matches_reference(oracle, ref):
         assert np.array_equal(gl, wl), (trial, n)
         assert np.array_equal(gm, wm), (trial, n)
         assert ref.rng_equals(eng, p.seed, orng.draws), (trial, n)
+
+
+def test_summarize_cn_golden(oracle):
+    """SURVEY 8 row f4: the restatement of cngpld::summarize_cn (oracle/cngpld_oracle.c) reproduces the reference's four
+    golden cases (tests/golden/cngpld, from /root/reference/tests/data via tests/cngpld_test.cpp:46-83) within the
+    reference's own tolerance, and raises where the reference throws."""
+    import cngpld_cases as cc
+    for seg, direction, expected, positions in cc.CASES:
+        s, e, v = cc.read_seg(seg)
+        pos, val = oracle.summarize_cn(s, e, v, direction, cc.CUTOFF, positions)
+        wpos, wval = cc.read_expected(expected)
+        assert np.array_equal(pos, wpos), (seg, direction)
+        assert np.allclose(val, wval, rtol=cc.RTOL, atol=0), (seg, direction)
+    s, e, v = cc.read_seg("cngpld_case1_input.seg")
+    with pytest.raises(ValueError):
+        oracle.summarize_cn(s, e, v, 0, 0.5)           # summarize.cpp:49-51
+    with pytest.raises(ValueError):
+        oracle.summarize_cn(e, s, v, 1, 0.5)           # start > end, summarize.cpp:59-61
+    assert len(oracle.summarize_cn(s[:0], e[:0], v[:0], 1, 0.5)[0]) == 0
