@@ -254,13 +254,22 @@ def run_gpu_arm(args):
         gather_tables.last = shard.gather_tables(tab, dist, dev, capacity=gather_cap)
         return gather_tables.last.shape[0]
 
+    local_done = {"ev": None}  # recorded when this rank's own samples are segmented, before the collective
+
+    def mark_local():
+        ev = torch.cuda.Event(enable_timing=True)
+        ev.record(stream)
+        local_done["ev"] = ev
+
     def step_device():
         r = ctx.segment_batch(None, off, gp, unit_ids=ids, device_ptr=d_vals.data_ptr(), dtype=genomic_b200.binding.F32)
+        mark_local()
         gather_tables(r)
         return r
 
     def step_host():
         r = ctx.segment_batch(host_pinned.numpy(), off, gp, unit_ids=ids)
+        mark_local()
         gather_tables(r)
         return r
 
@@ -269,6 +278,7 @@ def run_gpu_arm(args):
             fn()
         sampler = ClockSampler(local_rank) if sample_clocks else None
         per_step = []
+        local = []
         last = None
         barrier()
         if sampler:
@@ -283,6 +293,7 @@ def run_gpu_arm(args):
             e1.record(stream)
             torch.cuda.synchronize(dev)
             per_step.append(e0.elapsed_time(e1))
+            local.append(e0.elapsed_time(local_done["ev"]))
         barrier()
         clocks = sampler.stop() if sampler else None
         total_ms = float(sum(per_step))
@@ -290,11 +301,13 @@ def run_gpu_arm(args):
         if dist is not None:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)  # max over ranks
         timed.last_steps = [round(x, 3) for x in per_step]  # this rank's per-step times (diagnostics)
+        timed.last_local = [round(x, 3) for x in local]     # ... without the gather of the tables (the ranks' own work)
         return float(t.item()), last, clocks
 
     warm = max(args.warmup, 3) if not args.cohort_run else args.warmup
     total_ms, res, clocks = timed(step_device, args.steps, warm, sample_clocks=True)
     steps_device = timed.last_steps
+    local_device = timed.last_local
     e2e_ms, res_h, _ = timed(step_host, args.steps, 0 if args.cohort_run else max(args.warmup, 3))
     steps_host = timed.last_steps
     launches_per_step = int(res.kernel_launches)
@@ -305,7 +318,9 @@ def run_gpu_arm(args):
         # per-rank times (load balance) and the parity subset: the subset samples are segmented once more in ONE call on rank 0
         # (that call is what tests/test_gpu_fullsize.py::test_config4 compares with the compiled reference, log under profiles/)
         # and must agree row for row with what the sharded run produced for them.
-        rank_ms = torch.tensor([sum(steps_device) / len(steps_device)], device=dev, dtype=torch.float64)
+        # per rank: the time of its own samples, taken BEFORE the collective (the step time is the same on every rank: the
+        # all_gather waits for the slowest)
+        rank_ms = torch.tensor([sum(local_device) / len(local_device)], device=dev, dtype=torch.float64)
         all_ms = [torch.zeros_like(rank_ms) for _ in range(world)]
         if dist is not None:
             dist.all_gather(all_ms, rank_ms)
@@ -331,7 +346,7 @@ def run_gpu_arm(args):
                         "d2h_bytes_per_step": int(len(res_h.lengths) * 12 + len(off) * 16) * world},
                 "config": {"workload": workload_name(S, args.scale), "rng": args.rng, "chain": False, "samples": total,
                            "parallelism": f"sample-sharded x{world}, one all_gather of the segment tables"},
-                "per_rank_ms_per_step": [round(x, 1) for x in per_rank],
+                "per_rank_local_ms_per_step": [round(x, 1) for x in per_rank],
                 "max_over_mean_rank_time": max(per_rank) / (sum(per_rank) / len(per_rank)),
                 "segments": int(full_table.shape[0]), "perms_run_rank0": int(res.perms_run), "rounds_rank0": int(res.rounds),
                 "parity_subset": {"samples": subset, "rows": int(want.shape[0]), "sharded_equals_single_call": same,

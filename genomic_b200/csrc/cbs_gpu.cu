@@ -1330,11 +1330,12 @@ int cbs_gpu_segment_batch(cbs_gpu_ctx* c, const void* values, int dtype, int mem
         if (unit_offsets[0] != 0) splittable = false;
         for (int u = 0; splittable && u < n_units; ++u) if (unit_offsets[u + 1] < unit_offsets[u]) splittable = false;
     }
-    // Large cohorts are segmented in consecutive sub-batches of about CBS_GPU_CHUNK_MARKERS markers (default 48 M, some 25
-    // SNP6 samples): units are independent (Philox keys and chain == 0 streams do not depend on the neighbours), the cost per
-    // sample is flat between 4 and 64 samples per call and rises beyond (the one-thread scheduler walks thousands of live
-    // segments per round and the stream window has to span thousands of cursors: 58 ms per sample at 125 samples, 50 at 32).
-    const long long chunk_max = std::max<long long>(1024, env_ll("CBS_GPU_CHUNK_MARKERS", 48LL << 20));
+    // Large cohorts are segmented in consecutive sub-batches of about CBS_GPU_CHUNK_MARKERS markers (default 96 M, some 50
+    // SNP6 samples) so that a call of any size runs in bounded device memory (~100 B per marker of per-call buffers besides
+    // the arenas).  Units are independent (Philox keys and chain == 0 streams do not depend on the neighbours), and the cost
+    // per sample does not depend on the batch size beyond a few samples per call (125 samples: 6.77 s in one batch, 6.81 s in
+    // five), so the split costs nothing.
+    const long long chunk_max = std::max<long long>(1024, env_ll("CBS_GPU_CHUNK_MARKERS", 96LL << 20));
     const long long N_all = splittable ? (long long)unit_offsets[n_units] : 0;
     const bool parallel = splittable && want_lanes >= 2 && n_units >= 2 * want_lanes;
     if (!parallel && (!splittable || N_all <= chunk_max))

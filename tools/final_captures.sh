@@ -9,9 +9,10 @@ python bench.py > $O/bench_mt.json 2> $O/bench_mt.err; echo "bench rc=$?"
 python bench.py --rng philox --no-cpu > $O/bench_philox.json 2> $O/bench_philox.err
 python bench.py --samples-per-gpu 16 --steps 3 --warmup 3 --no-cpu > $O/bench_mt_16samples.json 2> $O/bench_16.err
 python bench.py --impl reference --steps 1 --warmup 0 > $O/bench_reference.json 2> $O/bench_reference.err
-# launch list of the bench command (graph nodes are profiled one by one)
-if python bench.py --steps 2 --warmup 3 --no-cpu > $O/bench_pre_ncu.json 2>/dev/null; then
-  timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 6000 --csv --log-file $O/launches.csv \
+# launch list of the bench command; rounds enqueued by the host (CBS_GPU_GRAPH=0): ncu does not profile the kernel nodes
+# of a graph that has conditional nodes
+if CBS_GPU_GRAPH=0 python bench.py --steps 2 --warmup 3 --no-cpu > $O/bench_pre_ncu.json 2>/dev/null; then
+  CBS_GPU_GRAPH=0 timeout 1200 ncu --metrics gpu__time_duration.sum --clock-control none -c 12000 --csv --log-file $O/launches.csv \
       python bench.py --steps 2 --warmup 3 --no-cpu > $O/ncu_launches.log 2>&1; echo "ncu launches rc=$?"
 fi
 # one call, planned work per round, then the full capture of round 4 (rounds enqueued by the host: launch k of a kernel = round k)
