@@ -283,7 +283,9 @@ int smooth_device(cbs_gpu_ctx* c, const double* xin, const long long* goff, cons
 // resident on an SM
 bool pick_scan_warps(cbs_gpu_ctx* c, ScanLayout& lay, int* occ_out) {
     int best_w = 0, best_res = 0, best_occ = 1;
+    const int forced = (int)env_ll("CBS_GPU_SCAN_WARPS", 0);  // experiments only
     for (int w : {8, 4, 2, 1}) {
+        if (forced && w != forced) continue;
         lay.warps = w;
         if (lay.bytes() > c->smem_optin) continue;
         int occ = 0;
