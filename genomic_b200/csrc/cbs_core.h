@@ -290,6 +290,7 @@ struct Dev {
     int shared_stream;
     uint64_t* stream;
     long long stream_cap, stream_mask, stream_mirror, stream_lo, stream_len, stream_target;
+    long long stream_target_prev;             // the need one round ago (k_gen_lead sizes its look-ahead on the growth)
     const uint64_t* jump_polys;             // table g_{c*S} (mt_jump.h) or nullptr: sequential generation only
     long long gen_base, gen_E, gen_lead_end;  // extension in flight (written by k_gen_lead)
     long long span_max;                       // words the generator may add per round

@@ -540,7 +540,7 @@ int run_cbs(cbs_gpu_ctx* c, const std::vector<long long>& off, const uint64_t* u
     hD.shared_stream = shared_stream ? 1 : 0;
     hD.stream = c->stream_buf.as<uint64_t>();
     hD.stream_cap = stream_ring; hD.stream_mask = stream_ring - 1; hD.stream_mirror = stream_mirror; hD.stream_lo = 0;
-    hD.stream_len = 312; hD.stream_target = 312;
+    hD.stream_len = 312; hD.stream_target = 312; hD.stream_target_prev = 312;
     hD.jump_polys = nullptr;
     hD.span_max = 1LL << 40;
     if (shared_stream && (long long)Nmax * hD.prm.first_batch > mtjump::SEG && !env_ll("CBS_GPU_NO_JUMP", 0)) {
@@ -838,6 +838,7 @@ int run_cbs(cbs_gpu_ctx* c, const std::vector<long long>& off, const uint64_t* u
         fprintf(stderr, "[rounds] planned perms / markers per round:");
         for (int r = 0; r < std::min(hD.round, 64); ++r) fprintf(stderr, " %d:%llu/%.1fM", r, hD.round_perms[r], hD.round_elems[r] * 1e-6);
         fprintf(stderr, "\n");
+        if (hD.shared_stream) fprintf(stderr, "[stream] words generated %.1fM, furthest word asked for %.1fM\n", hD.stream_len * 1e-6, hD.stream_target * 1e-6);
     }
     if (hD.n_segs > 0) {
         LaunchTimer t(c, K_MEANS);

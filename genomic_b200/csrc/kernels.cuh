@@ -301,9 +301,19 @@ __global__ void __launch_bounds__(192) k_gen_lead(Dev* D, int ahead) {
     const long long len = D->stream_len;
     long long target = D->stream_target;
     if (ahead) {
-        // a launch costs about the same for one segment or for all of them (the GF(2) combination of the segment heads
-        // dominates), so the ahead pass always goes for the whole span
-        target += D->jump_polys ? D->span_max : GEN_AHEAD;
+        // How far ahead: a launch costs about the same for one segment or for all of them (the GF(2) combination of the
+        // segment heads dominates), and a round whose need outruns the stream pays a whole generator launch on its critical
+        // path -- but words nobody reads are HBM writes and SM time taken from the shuffles running next to this kernel.
+        // So: twice the growth of the need over the last round, at least GEN_AHEAD, at most the span of one launch.
+        long long extra = GEN_AHEAD;
+        if (D->jump_polys) {
+            const long long growth = target - D->stream_target_prev;
+            if (2 * growth > extra) extra = 2 * growth;
+            if (extra > D->span_max) extra = D->span_max;
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) D->stream_target_prev = target;
+        target += extra;
         if (target > len + D->span_max) target = len + D->span_max;
     }
     if (target > D->stream_lo + D->stream_cap - 312) target = D->stream_lo + D->stream_cap - 312;  // the scheduler never asks for more
