@@ -1,14 +1,21 @@
 // kernels.cuh -- sm_100a kernels of the CBS hot path.
 //
-//   k_sched      count phase + the single-thread worklist scheduler (cbs_core.h)
-//   k_gen        MT19937-64 raw stream generator, one CTA per chain (replay mode)
-//   k_prep       per pending segment: all-equal test, mean, centring, tss, observed prefix
-//                sums / block extrema, g[L] and fac[L] tables     (CBS.cpp:985-989, :79-97)
-//   k_perm       thread per permutation: Fisher-Yates + prefix sums (CBS.cpp:487-493, :79-97)
-//   k_scan       CTA per permutation: branch-and-bound max-t arc scan (CBS.cpp:99-224)
-//   k_edgeprep   tpermp set-up sums (CBS.cpp:496-522)
-//   k_edgeperm   tpermp permutation loop (CBS.cpp:524-534)
-//   k_means      segment means (CBS.cpp:1014-1022)
+//   k_sched          count phase + the single-thread worklist scheduler (cbs_core.h); holds the loop condition of the
+//                    call graph (cbs_gpu.cu run_cbs: one scheduler round = the body of a WHILE node)
+//   k_gen_lead/par   MT19937-64 raw stream, one shared ring for all units, extended in parallel with jump-ahead
+//                    polynomials (mt_jump.h); k_gen: one CTA per chain when ONE engine is shared serially (chain mode)
+//   k_tables, k_prep per new pending segment: block ends, g[L] and fac[L]; all-equal test, mean, centring, tss and the
+//                    observed prefix sums as lane-0 chains                              (CBS.cpp:985-989, :71-97)
+//   k_shuffle, k_shuffle_cluster   xperm as an exact parallel Fisher-Yates, CTA or thread-block cluster per permutation
+//                    (shuffle.cuh; CBS.cpp:487-493); k_perm: fallback with index arrays in L2 for units no cluster holds
+//   k_chain          prefix sums of the permuted rows (one dependent DADD chain per row) + the row statistics the scan
+//                    prunes with                                                          (CBS.cpp:83-94)
+//   k_scan           CTA per permutation: branch-and-bound max-t arc scan (CBS.cpp:99-224)
+//   k_hscan, k_tailp_*   hybrid p-values: htmaxp (CBS.cpp:387-485) and tailp (:324-339)
+//   k_edgeprep       tpermp set-up sums (CBS.cpp:496-522)
+//   k_edgeperm       tpermp permutation loop (CBS.cpp:524-534)
+//   k_means          segment means (CBS.cpp:1014-1022)
+//   (binary.cuh: the ibin = true scan, btmax; weighted.cuh: the weighted variants; smooth.cuh: smoothing, summarize_cn)
 //
 // All floating point that feeds a comparison is plain IEEE double with the reference's
 // operation order; the library is compiled with -fmad=false.
