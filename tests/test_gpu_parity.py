@@ -410,10 +410,11 @@ def test_undo_prune_matches_oracle(ctx, oracle):
 
 
 def test_full_size_sample_properties(ctx, oracle):
-    """BASELINE configs[1] at full size (1.8 M markers, 23 chromosomes, nperm 10 000, smoothing on), where the oracle only
-    finishes the smallest chromosome in seconds: size-independent properties instead -- lengths partition every unit, the
-    means are the sequential sums of the smoothed values, the call is deterministic, and cutting the cohort into two
-    calls (what sharding by sample/chromosome does) changes nothing; the smallest chromosome is checked against the oracle."""
+    """BASELINE configs[1] at full size (1.8 M markers, 23 chromosomes, nperm 10 000, smoothing on): size-independent
+    properties -- lengths partition every unit, the means are the sequential sums of the smoothed values, the call is
+    deterministic, and cutting the cohort into two calls (what sharding by sample/chromosome does) changes nothing; the
+    smallest chromosome is checked against the single-threaded C oracle.  The comparison of ALL units of this sample with
+    the compiled reference (16 host threads, ~100 s) is tests/test_gpu_fullsize.py::test_config2_whole_sample_vs_reference."""
     from genomic_b200 import synth
     vals, off, lab, ids = synth.cohort([0], scale=1.0)
     gp = Params(nperm=10000, alpha=0.01, rng_mode=RNG_MT19937_64, chain=False, seed=1)
