@@ -1,7 +1,8 @@
 """Ad-hoc GPU probe: times a few calls per mode with a watchdog so a hang costs seconds, not minutes."""
 import os, sys, time, faulthandler
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
 faulthandler.dump_traceback_later(int(os.environ.get("PROBE_WATCHDOG", "240")), exit=True)
 import numpy as np
 from helpers import make_unit, pack

@@ -1,7 +1,7 @@
 """Weighted CBS (cbs::segment_weighted) on one synthetic SNP6-scale sample: wall time per call, per-kernel event times,
 and a parity check of the two smallest chromosomes against the CPU oracle.  Prints one JSON line.
 
-    python tools/weighted_probe.py [--scale 1.0] [--reps 3] [--nperm 10000] [--check]
+    python tests/tools/weighted_probe.py [--scale 1.0] [--reps 3] [--nperm 10000] [--check]
 """
 import argparse
 import json
@@ -11,7 +11,7 @@ import time
 
 import numpy as np
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 
 import genomic_b200  # noqa: E402
